@@ -1,0 +1,241 @@
+/*=================================================================================================
+ *  gsph.h -- C ABI of the B200-native grad-h SPH neighbour path ("libgsph").
+ *
+ *  This is the drop-in boundary for ONE hot path of GANDALF v0.4.0: tree build -> h-rho
+ *  iteration -> hydro / hydro+gravity force sums.  In the reference that path sits behind the
+ *  C++ pure-virtual surface
+ *      NeighbourSearch<ndim>        src/Headers/NeighbourSearch.h:66-137
+ *      SphNeighbourSearch<ndim>     src/Headers/SphNeighbourSearch.h:77-94
+ *  whose concrete class GradhSphTree<ndim,GradhSphParticle> is created in
+ *      GradhSphSimulation<ndim>::ProcessSphParameters   src/GradhSph/GradhSphSimulation.cpp:232-246
+ *  from the .dat parameter `neib_search`.  A host-side subclass (host/GpuSphTree.h in this
+ *  repository; binding shown in INTEGRATION.md) forwards each virtual to one entry point below.
+ *
+ *  Conventions
+ *    - plain C, no C++/torch types; every function returns 0 on success, a GSPH_E* code
+ *      otherwise, never throws (the reference library is built -fno-exceptions, src/Makefile:57);
+ *      gsph_last_error() gives the message the host wrapper hands to
+ *      ExceptionHandler::raise (src/Common/Exception.cpp:47-69).
+ *    - all entry points are called from one host thread (the reference calls the L3 surface from
+ *      the main thread only, src/Hydrodynamics/SphSimulation.cpp:616-710).
+ *    - FLOAT = double (the reference's default PRECISION=DOUBLE, Makefile:27).
+ *    - there is NO CPU fallback: without a CUDA device gsph_create fails with GSPH_ENODEVICE.
+ *=================================================================================================*/
+#ifndef GSPH_H
+#define GSPH_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSPH_ABI_VERSION 1
+
+/* ---- return codes ---------------------------------------------------------------------------*/
+enum {
+  GSPH_OK          = 0,
+  GSPH_EINVAL      = 1,   /* bad argument / unsupported parameter combination                  */
+  GSPH_ENODEVICE   = 2,   /* no CUDA device (there is no CPU fallback)                          */
+  GSPH_ECUDA       = 3,   /* CUDA runtime error, text in gsph_last_error                        */
+  GSPH_ENOMEM      = 4,
+  GSPH_ESTATE      = 5,   /* call out of order (e.g. forces before tree build)                  */
+  GSPH_ECONVERGE   = 6    /* h-rho iteration failed: reference raises "Problem with convergence
+                             of h-rho iteration" (src/GradhSph/GradhSph.cpp:249-250)             */
+};
+
+/* ---- enumerations mirroring the reference's run-time parameters -------------------------------*/
+/* kernel = m4 | quintic            (src/Common/Parameters.cpp:253; SmoothingKernel.h:131,281)    */
+enum { GSPH_KERNEL_M4 = 0, GSPH_KERNEL_QUINTIC = 1 };
+/* avisc  = none | mon97 | mon97mm97 | mon97cd2010   (src/Headers/Hydrodynamics.h aviscenum)      */
+enum { GSPH_AVISC_NONE = 0, GSPH_AVISC_MON97 = 1, GSPH_AVISC_MON97MM97 = 2, GSPH_AVISC_MON97CD2010 = 3 };
+/* acond  = none | wadsley2008 | price2008                                                         */
+enum { GSPH_ACOND_NONE = 0, GSPH_ACOND_WADSLEY2008 = 1, GSPH_ACOND_PRICE2008 = 2 };
+/* time_dependent_avisc = none | mm97 | cd2010 (cd2010 is not on the accelerated path)             */
+enum { GSPH_TDAVISC_NONE = 0, GSPH_TDAVISC_MM97 = 1 };
+/* gas_eos = energy_eqn|constant_temp (Adiabatic) | isothermal | barotropic
+ *           (src/Hydrodynamics/Hydrodynamics.cpp:91-108; src/Thermal/{Adiabatic,Isothermal,Barotropic}EOS.cpp) */
+enum { GSPH_EOS_ADIABATIC = 0, GSPH_EOS_ISOTHERMAL = 1, GSPH_EOS_BAROTROPIC = 2 };
+/* boundary_lhs/rhs = open | periodic | mirror (src/Headers/DomainBox.h:49-92)                     */
+enum { GSPH_BOUNDARY_OPEN = 0, GSPH_BOUNDARY_PERIODIC = 1, GSPH_BOUNDARY_MIRROR = 2 };
+/* gravity_mac = geometric | eigenmac | gadget2 (src/Headers/Tree.h:413-432)                        */
+enum { GSPH_MAC_GEOMETRIC = 0, GSPH_MAC_EIGEN = 1, GSPH_MAC_GADGET2 = 2 };
+/* multipole = monopole | quadrupole | fast_monopole | fast_quadrupole
+ *           (src/GradhSph/GradhSphTree.cpp:549-556,588-593)                                       */
+enum { GSPH_MULTIPOLE_MONOPOLE = 0, GSPH_MULTIPOLE_QUADRUPOLE = 1,
+       GSPH_MULTIPOLE_FAST_MONOPOLE = 2, GSPH_MULTIPOLE_FAST_QUADRUPOLE = 3 };
+/* particle types (src/Headers/Particle.h:44)                                                      */
+enum { GSPH_TYPE_GAS = 0, GSPH_TYPE_ICM = 1, GSPH_TYPE_CDM = 2, GSPH_TYPE_DUST = 3,
+       GSPH_TYPE_BOUNDARY = 4, GSPH_NTYPES = 5 };
+/* flag bits of Particle::flags used by the path (src/Headers/Flags.h:93-136)                       */
+enum { GSPH_FLAG_DEAD = 1u << 0, GSPH_FLAG_ACTIVE = 1u << 1, GSPH_FLAG_POTMIN = 1u << 3 };
+
+/* ---- configuration ----------------------------------------------------------------------------
+ * Everything the reference passes to GradhSph / GradhSphTree constructors
+ * (src/GradhSph/GradhSphSimulation.cpp:131-161,243-246) plus the DomainBox.                        */
+typedef struct gsph_config {
+  int32_t abi_version;        /* = GSPH_ABI_VERSION                                               */
+  int32_t ndim;               /* 1, 2 or 3                                                        */
+  int32_t kernel;             /* GSPH_KERNEL_*                                                    */
+  int32_t tabulated_kernel;   /* 1: TabulatedKernel semantics (1000 bins, truncating look-up,
+                                 SmoothingKernel.h:619-637), 0: analytic polynomials              */
+  double  h_fac;              /* h = h_fac (m/rho)^(1/ndim)          (Sph.h:259-263)               */
+  double  h_converge;         /* |h - h(rho)|/h tolerance            (GradhSph.cpp:219-220)        */
+  int32_t avisc, acond, tdavisc;
+  double  alpha_visc, beta_visc, alpha_visc_min;
+  int32_t eos;                /* GSPH_EOS_*                                                       */
+  double  gamma_eos;          /* ratio of specific heats                                          */
+  double  temp0;              /* isothermal/barotropic temperature, CODE units (temp0/temp.outscale) */
+  double  mu_bar;             /* mean molecular weight                                            */
+  double  rho_bary;           /* barotropic critical density, CODE units                          */
+  double  boxmin[3], boxmax[3];
+  int32_t boundary_lhs[3], boundary_rhs[3];      /* GSPH_BOUNDARY_*                               */
+  int32_t hydro_forces;       /* 1: hydro terms on                                                */
+  int32_t self_gravity;       /* 1: UpdateAllSphForces path available                             */
+  double  thetamaxsqd;        /* geometric MAC (KDTree.cpp:917)                                   */
+  int32_t gravity_mac;        /* GSPH_MAC_*                                                       */
+  double  macerror;
+  int32_t multipole;          /* GSPH_MULTIPOLE_*                                                 */
+  int32_t Nleafmax;           /* max particles per KD-tree leaf (Parameters.cpp:306)              */
+  /* ParticleTypeRegister (src/Common/Particle.cpp:31-71): bit j of mask[i] <=> mask[i][j]         */
+  uint32_t hmask[GSPH_NTYPES], hydromask[GSPH_NTYPES];
+  uint32_t gravmask;          /* bit j: type j contributes to gravity                             */
+  uint32_t hydro_forces_type; /* bit i: type i experiences hydro forces                           */
+  uint32_t self_gravity_type; /* bit i: type i experiences gravity                                */
+  int32_t create_sinks;       /* 1: compute the potmin flag in the density pass (GradhSph.cpp:271) */
+  int32_t device;             /* CUDA device ordinal                                              */
+  int32_t reserved[7];
+} gsph_config;
+
+/* Fill *cfg with the reference's defaults (Parameters::SetDefaultValues, Parameters.cpp:166-536):
+ * ndim 3, m4, tabulated, h_fac 1.2, h_converge 0.01, mon97 alpha 1 beta 2, no conductivity,
+ * energy_eqn gamma 5/3, open boundaries, Nleafmax 6, theta^2 0.1, geometric MAC, quadrupole;
+ * gas-only type masks.                                                                             */
+int gsph_default_config(gsph_config* cfg);
+
+/* ---- particle views ---------------------------------------------------------------------------
+ * A view describes where each per-particle field lives in HOST memory as (base pointer, byte
+ * stride), so the same call serves the reference's AoS array (stride = sizeof(GradhSphParticle<ndim>)
+ * = 448 B in 3-D double, src/Headers/Particle.h:286-368; base = &sphdata[0].field) and plain SoA
+ * arrays (stride = 8).  Vector fields are given per component.  A NULL base means "absent":
+ * on upload the field takes the reference's constructor default (Particle.h:180-221); on download
+ * it is skipped.  The array may be reallocated by the host between calls (Sph::AllocateMemory,
+ * GradhSph.cpp:83-111), so views are never cached.                                                 */
+typedef struct gsph_field { void* base; size_t stride; } gsph_field;
+
+typedef struct gsph_particle_view {
+  gsph_field r[3], v[3], a[3], atree[3];
+  gsph_field m, h, u, rho, hrangesqd, hfactor, invomega, zeta, sound, pressure;
+  gsph_field dudt, div_v, alpha, dalphadt, gpot, gpot_hydro;
+  gsph_field flags;      /* uint32  Particle::flags                                               */
+  gsph_field ptype;      /* int32                                                                  */
+  gsph_field level;      /* int32                                                                  */
+  gsph_field levelneib;  /* int32                                                                  */
+  gsph_field iorig;      /* int32                                                                  */
+  gsph_field sinkid;     /* int32 (-1: not inside a sink)                                          */
+} gsph_particle_view;
+
+/* field_mask bits for gsph_download                                                               */
+enum {
+  GSPH_F_DENSITY = 1u << 0,   /* h, rho, hrangesqd, hfactor, invomega, zeta, u, sound, pressure,
+                                 div_v(=0), flags (potmin)  -- what ComputeH writes                */
+  GSPH_F_FORCES  = 1u << 1,   /* a, dudt, div_v, dalphadt, levelneib (+ atree, gpot, gpot_hydro)    */
+  GSPH_F_ALL     = 0xffffffffu
+};
+
+typedef struct gsph_handle gsph_handle;
+
+/* ---- lifecycle ---------------------------------------------------------------------------------*/
+int  gsph_create(const gsph_config* cfg, gsph_handle** out);       /* replaces `new GradhSphTree`,
+                                                                      GradhSphSimulation.cpp:243-246 */
+void gsph_destroy(gsph_handle* h);
+const char* gsph_last_error(const gsph_handle* h);                  /* h may be NULL: create errors  */
+
+/* ---- data movement (host <-> HBM) --------------------------------------------------------------
+ * gsph_upload : Nhydro real particles [0,Nhydro) of the host array -> device SoA.
+ *               (Boundary ghosts are never materialised on the device: periodic images are taken
+ *               on the fly in the walks, as the reference's force pass does,
+ *               NeighbourManager.h:417-444 / GhostNeighbours.hpp:146-166.)
+ * gsph_download: results back into the host view, in the host's particle order.                    */
+int gsph_upload(gsph_handle* h, const gsph_particle_view* view, int64_t Nhydro);
+int gsph_download(gsph_handle* h, const gsph_particle_view* view, uint32_t field_mask);
+
+/* ---- the operator surface ----------------------------------------------------------------------
+ * gsph_build_tree           NeighbourSearch::BuildTree          HydroTree.cpp:310-372
+ *                           (+ BuildGhostTree/SearchBoundaryGhostParticles, :382-441,:495-543,
+ *                            which become no-ops: see gsph_upload)
+ *     mode 0 = rebuild (KDTree::BuildTree, KDTree.cpp:220-313), 1 = restock (StockTree, :760-798),
+ *     2 = extrapolate cell boxes by v*dt (Tree.cpp:172-198).
+ * gsph_update_active_counters  KDTree::UpdateActiveParticleCounters   KDTree.cpp:1217-1254
+ * gsph_update_properties    SphNeighbourSearch::UpdateAllSphProperties  GradhSphTree.cpp:83-271
+ *                           (ComputeH GradhSph.cpp:142-326 + UpdateAllHmaxValues KDTree.cpp:1128-1208)
+ * gsph_zero_accelerations   Sph::ZeroAccelerations               Sph.cpp:126-140
+ * gsph_update_hydro_forces  ::UpdateAllSphHydroForces            GradhSphTree.cpp:280-435
+ * gsph_update_all_forces    ::UpdateAllSphForces                 GradhSphTree.cpp:444-657
+ *                           stars = Nstar x {r[3], m, h} doubles (ComputeStarGravForces,
+ *                           GradhSph.cpp:699-743); may be NULL/0.
+ * gsph_get_hmax             NeighbourSearch::GetMaximumSmoothingLength (SphSimulation.cpp:762-771)  */
+int gsph_build_tree(gsph_handle* h, int mode, double dt);
+int gsph_update_active_counters(gsph_handle* h);
+int gsph_update_properties(gsph_handle* h);
+int gsph_zero_accelerations(gsph_handle* h);
+int gsph_update_hydro_forces(gsph_handle* h);
+int gsph_update_all_forces(gsph_handle* h, const double* stars, int Nstar);
+int gsph_get_hmax(gsph_handle* h, double* hmax);
+int gsph_synchronize(gsph_handle* h);
+
+/* ---- parity / debug access ---------------------------------------------------------------------
+ * Neighbour lists as defined by NeighbourManager::TrimNeighbourLists (NeighbourManager.h:521):
+ *   j is a neighbour of i  <=>  NOT( drsqd >= hrangesqd_i && drsqd >= hrangesqd_j )  and
+ *   hydromask[ptype_i][ptype_j]; self included.  Indices are HOST particle indices (upload order).
+ * Call gsph_neighbour_counts first (counts[Nhydro]), build offsets, then gsph_neighbour_lists
+ * (idx sorted ascending within each row).                                                          */
+int gsph_neighbour_counts(gsph_handle* h, int32_t* counts);
+int gsph_neighbour_lists(gsph_handle* h, const int64_t* offsets, int32_t* idx);
+
+/* KD-tree inspection.  Cells are reported with the reference's depth-first ids
+ * (KDTree::CreateTreeStructure, KDTree.cpp:362-433).                                              */
+typedef struct gsph_tree_info {
+  int32_t ltot;        /* leaf level                                                               */
+  int32_t Ncell;       /* 2^(ltot+1) - 1                                                           */
+  int32_t gtot;        /* number of leaf cells 2^ltot                                              */
+  int32_t Nleafmax;
+  int64_t Ntot;
+} gsph_tree_info;
+int gsph_tree_info_get(gsph_handle* h, gsph_tree_info* info);
+/* leaf_of[i] = depth-first id of the leaf cell holding host particle i                            */
+int gsph_tree_leaf_of(gsph_handle* h, int32_t* leaf_of);
+/* per cell (depth-first id c): box[c][4*ndim] = bb.min, bb.max, hbox.min, hbox.max;
+ * com[c][2*ndim] = rcell, r; scalars[c][5] = m, rmax, hmax, cdistsqd, mac; q[c][5]; N[c].
+ * Any pointer may be NULL.                                                                         */
+int gsph_tree_cells(gsph_handle* h, double* box, double* com, double* scalars, double* q, int32_t* N);
+
+/* run statistics of the most recent calls (SURVEY 8d "value distributions")                        */
+typedef struct gsph_stats {
+  int64_t Nhydro;
+  int64_t n_active;            /* particles updated by the last pass                               */
+  double  ngb_mean; int32_t ngb_max;      /* hydro neighbours per particle, last force pass        */
+  double  cand_mean;                      /* candidates tested per target, last force pass         */
+  double  hiter_mean; int32_t hiter_max;  /* h-rho iterations, last density pass                   */
+  int32_t density_retries;                /* cohorts that needed a larger search radius            */
+  double  ndirect_mean, ncell_mean;       /* gravity: direct-sum particles / cells per particle    */
+  int64_t kernel_launches;     /* CUDA kernels launched by this handle since create               */
+  float   ms_build_tree, ms_properties, ms_forces;   /* device time of the last call of each       */
+  float   ms_upload, ms_download;
+} gsph_stats;
+int gsph_get_stats(gsph_handle* h, gsph_stats* st);
+
+/* Kernel tables exactly as TabulatedKernel builds them (TabulatedKernel.cpp:58-105,
+ * SmoothingKernel.h:585-605): which = 0 w0_s2, 1 womega_s2, 2 wzeta_s2, 3 w1, 4 wgrav, 5 wpot;
+ * out[1000].  Host-side, no device needed (parity stage P0).                                      */
+int gsph_kernel_table(int ndim, int kernel, int which, double* out);
+
+/* Device peak probe used by bench.py for the FP64 roofline ("measure FP64 and FP32 FMA
+ * peak with a register-resident micro-kernel").  Returns TFLOP/s (2 flops per FMA).               */
+int gsph_measure_fp_peak(int device, double* fp64_tflops, double* fp32_tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSPH_H */

@@ -1,0 +1,245 @@
+"""ctypes binding of the CPU oracle (oracle/gsph_oracle.c) -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / reference legs may
+import this module.  The product path (gandalf_b200) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_ORACLE_DIR = os.path.join(_ROOT, "oracle")
+_LIB_PATH = os.path.join(_ORACLE_DIR, "_build", "liboracle.so")
+
+
+class OrcParams(C.Structure):
+    _fields_ = [
+        ("ndim", C.c_int), ("kernel", C.c_int), ("tabulated", C.c_int),
+        ("h_fac", C.c_double), ("h_converge", C.c_double),
+        ("avisc", C.c_int), ("acond", C.c_int), ("tdavisc", C.c_int),
+        ("alpha_visc", C.c_double), ("beta_visc", C.c_double), ("alpha_visc_min", C.c_double),
+        ("eos", C.c_int),
+        ("gamma_eos", C.c_double), ("temp0", C.c_double), ("mu_bar", C.c_double),
+        ("rho_bary", C.c_double),
+        ("boxmin", C.c_double * 3), ("boxmax", C.c_double * 3), ("periodic", C.c_int * 3),
+        ("self_gravity", C.c_int), ("thetamaxsqd", C.c_double), ("gravity_mac", C.c_int),
+        ("macerror", C.c_double), ("multipole", C.c_int), ("Nleafmax", C.c_int),
+        ("hydro_forces", C.c_int),
+    ]
+
+
+def build(force=False):
+    if force or not os.path.exists(_LIB_PATH) or (
+            os.path.getmtime(_LIB_PATH) < os.path.getmtime(os.path.join(_ORACLE_DIR, "gsph_oracle.c"))):
+        subprocess.check_call(["make", "-C", _ORACLE_DIR, "port"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+_lib = None
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_lp = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        P = C.POINTER(OrcParams)
+        _lib.orc_kernel.restype = C.c_double
+        _lib.orc_kernel.argtypes = [P, C.c_int, C.c_double]
+        _lib.orc_kernel_s2.restype = C.c_double
+        _lib.orc_kernel_s2.argtypes = [P, C.c_int, C.c_double]
+        _lib.orc_kernel_table.restype = None
+        _lib.orc_kernel_table.argtypes = [P, C.c_int, _dp]
+        _lib.orc_neighbour_lists.restype = C.c_int64
+        _lib.orc_neighbour_lists.argtypes = [P, C.c_int, _dp, _dp, _lp, C.c_void_p]
+        _lib.orc_density.restype = C.c_int
+        _lib.orc_density.argtypes = [P, C.c_int] + [_dp] * 11 + [_ip]
+        _lib.orc_hydro_forces.restype = C.c_int
+        _lib.orc_hydro_forces.argtypes = [P, C.c_int] + [_dp] * 12 + [_ip] + [_dp] * 4 + [_ip]
+        _lib.orc_hydro_grav_forces_direct.restype = C.c_int
+        _lib.orc_hydro_grav_forces_direct.argtypes = [P, C.c_int] + [_dp] * 13 + [_ip] + [_dp] * 6 + [_ip]
+        _lib.orc_tree_build.restype = C.c_void_p
+        _lib.orc_tree_build.argtypes = [P, C.c_int, _dp, _dp, _dp, _dp]
+        _lib.orc_tree_free.restype = None
+        _lib.orc_tree_free.argtypes = [C.c_void_p]
+        _lib.orc_tree_ncell.restype = C.c_int
+        _lib.orc_tree_ncell.argtypes = [C.c_void_p]
+        _lib.orc_tree_ltot.restype = C.c_int
+        _lib.orc_tree_ltot.argtypes = [C.c_void_p]
+        _lib.orc_tree_leaf_of.restype = None
+        _lib.orc_tree_leaf_of.argtypes = [C.c_void_p, _ip]
+        _lib.orc_tree_cells.restype = None
+        _lib.orc_tree_cells.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, _ip]
+        _lib.orc_hydro_grav_forces_tree.restype = C.c_int
+        _lib.orc_hydro_grav_forces_tree.argtypes = ([P, C.c_void_p, C.c_int] + [_dp] * 13 + [_ip]
+                                                    + [_dp] * 6 + [_ip, _ip, _ip])
+    return _lib
+
+
+_KERNELS = {"m4": 0, "quintic": 1}
+_AVISC = {"none": 0, "mon97": 1, "mon97mm97": 2, "mon97cd2010": 3}
+_ACOND = {"none": 0, "wadsley2008": 1, "price2008": 2}
+_TDAVISC = {"none": 0, "mm97": 1, "cd2010": 2}
+_EOS = {"energy_eqn": 0, "constant_temp": 0, "isothermal": 1, "barotropic": 2}
+_MULTIPOLE = {"monopole": 0, "quadrupole": 1, "fast_monopole": 2, "fast_quadrupole": 3}
+_MAC = {"geometric": 0, "eigenmac": 1, "gadget2": 2}
+
+
+def params_from_dict(d):
+    """d uses the reference's .dat parameter names (src/Common/Parameters.cpp:166-536)."""
+    p = OrcParams()
+    p.ndim = int(d.get("ndim", 3))
+    p.kernel = _KERNELS[d.get("kernel", "m4")]
+    p.tabulated = int(d.get("tabulated_kernel", 1))
+    p.h_fac = float(d.get("h_fac", 1.2))
+    p.h_converge = float(d.get("h_converge", 0.01))
+    # src/GradhSph/GradhSphSimulation.cpp:71-92: the pair (avisc, time_dependent_avisc) selects both enums
+    av, td = d.get("avisc", "mon97"), d.get("time_dependent_avisc", "none")
+    if av == "none":
+        p.avisc, p.tdavisc = 0, 0
+    elif av == "mon97" and td == "mm97":
+        p.avisc, p.tdavisc = 2, 1
+    elif av == "mon97" and td == "cd2010":
+        p.avisc, p.tdavisc = 3, 2
+    elif av == "mon97":
+        p.avisc, p.tdavisc = 1, 0
+    else:
+        raise ValueError("Unrecognised parameter : avisc = %s" % av)
+    p.acond = _ACOND[d.get("acond", "none")]
+    p.alpha_visc = float(d.get("alpha_visc", 1.0))
+    p.beta_visc = float(d.get("beta_visc", 2.0))
+    p.alpha_visc_min = float(d.get("alpha_visc_min", 0.1))
+    p.eos = _EOS[d.get("gas_eos", "energy_eqn")]
+    p.gamma_eos = float(d.get("gamma_eos", 1.66666666666666))
+    p.temp0 = float(d.get("temp0", 1.0))
+    p.mu_bar = float(d.get("mu_bar", 1.0))
+    p.rho_bary = float(d.get("rho_bary", 1.0e-14))
+    for k in range(3):
+        p.boxmin[k] = float(d.get("boxmin[%d]" % k, 0.0))
+        p.boxmax[k] = float(d.get("boxmax[%d]" % k, 0.0))
+        p.periodic[k] = 1 if d.get("boundary_lhs[%d]" % k, "open") == "periodic" else 0
+    p.self_gravity = int(d.get("self_gravity", 0))
+    p.thetamaxsqd = float(d.get("thetamaxsqd", 0.1))
+    p.gravity_mac = _MAC[d.get("gravity_mac", "geometric")]
+    p.macerror = float(d.get("macerror", 1e-4))
+    p.multipole = _MULTIPOLE[d.get("multipole", "quadrupole")]
+    p.Nleafmax = int(d.get("Nleafmax", 6))
+    p.hydro_forces = int(d.get("hydro_forces", 1))
+    return p
+
+
+def _c(a, dtype=np.float64):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def kernel_table(p, which):
+    out = np.empty(1000)
+    lib().orc_kernel_table(C.byref(p), which, out)
+    return out
+
+
+def neighbour_lists(p, r, hrangesqd):
+    r = _c(r).reshape(len(hrangesqd), -1)
+    N = r.shape[0]
+    off = np.zeros(N + 1, dtype=np.int64)
+    hr = _c(hrangesqd)
+    tot = lib().orc_neighbour_lists(C.byref(p), N, r, hr, off, None)
+    idx = np.empty(tot, dtype=np.int32)
+    lib().orc_neighbour_lists(C.byref(p), N, r, hr, off, idx.ctypes.data_as(C.c_void_p))
+    return off, idx
+
+
+def density(p, r, m, h, u):
+    N = len(m)
+    r = _c(r).reshape(N, -1)
+    out = {k: np.zeros(N) for k in ("rho", "invomega", "zeta", "hfactor", "hrangesqd", "sound", "pressure")}
+    out["h"] = _c(h).copy()
+    out["u"] = _c(u).copy()
+    out["niter"] = np.zeros(N, dtype=np.int32)
+    rc = lib().orc_density(C.byref(p), N, r, _c(m), out["h"], out["u"], out["rho"], out["invomega"],
+                           out["zeta"], out["hfactor"], out["hrangesqd"], out["sound"], out["pressure"],
+                           out["niter"])
+    if rc != 0:
+        raise RuntimeError("oracle: h-rho iteration did not converge")
+    return out
+
+
+def hydro_forces(p, s):
+    """s: dict with r,v,m,h,rho,pressure,invomega,sound,u,alpha,hfactor,hrangesqd,level."""
+    N = len(s["m"])
+    nd = p.ndim
+    out = dict(a=np.zeros((N, nd)), dudt=np.zeros(N), div_v=np.zeros(N), dalphadt=np.zeros(N),
+               levelneib=np.zeros(N, dtype=np.int32))
+    lib().orc_hydro_forces(C.byref(p), N, _c(s["r"]).reshape(N, nd), _c(s["v"]).reshape(N, nd), _c(s["m"]),
+                           _c(s["h"]), _c(s["rho"]), _c(s["pressure"]), _c(s["invomega"]), _c(s["sound"]),
+                           _c(s["u"]), _c(s["alpha"]), _c(s["hfactor"]), _c(s["hrangesqd"]),
+                           _c(s["level"], np.int32), out["a"], out["dudt"], out["div_v"], out["dalphadt"],
+                           out["levelneib"])
+    return out
+
+
+def _grav_args(p, s):
+    N = len(s["m"])
+    nd = p.ndim
+    return [_c(s["r"]).reshape(N, nd), _c(s["v"]).reshape(N, nd), _c(s["m"]), _c(s["h"]), _c(s["rho"]),
+            _c(s["pressure"]), _c(s["invomega"]), _c(s["zeta"]), _c(s["sound"]), _c(s["u"]), _c(s["alpha"]),
+            _c(s["hfactor"]), _c(s["hrangesqd"]), _c(s["level"], np.int32)]
+
+
+def _grav_out(N, nd):
+    return dict(a=np.zeros((N, nd)), atree=np.zeros((N, nd)), gpot=np.zeros(N), dudt=np.zeros(N),
+                div_v=np.zeros(N), dalphadt=np.zeros(N), levelneib=np.zeros(N, dtype=np.int32))
+
+
+def hydro_grav_forces_direct(p, s):
+    N = len(s["m"])
+    out = _grav_out(N, p.ndim)
+    lib().orc_hydro_grav_forces_direct(C.byref(p), N, *_grav_args(p, s), out["a"], out["atree"], out["gpot"],
+                                       out["dudt"], out["div_v"], out["dalphadt"], out["levelneib"])
+    return out
+
+
+class Tree:
+    def __init__(self, p, r, v, m, h):
+        N = len(m)
+        self.p, self.N = p, N
+        # keep the arrays alive: the C tree stores pointers
+        self._r = _c(r).reshape(N, p.ndim)
+        self._v = _c(v).reshape(N, p.ndim)
+        self._m, self._h = _c(m), _c(h)
+        self.ptr = lib().orc_tree_build(C.byref(p), N, self._r, self._v, self._m, self._h)
+        self.ncell = lib().orc_tree_ncell(self.ptr)
+        self.ltot = lib().orc_tree_ltot(self.ptr)
+
+    def __del__(self):
+        if getattr(self, "ptr", None):
+            lib().orc_tree_free(self.ptr)
+            self.ptr = None
+
+    def leaf_of(self):
+        out = np.full(self.N, -1, dtype=np.int32)
+        lib().orc_tree_leaf_of(self.ptr, out)
+        return out
+
+    def cells(self):
+        nd, nc = self.p.ndim, self.ncell
+        box = np.zeros((nc, 4 * nd)); com = np.zeros((nc, 2 * nd)); sc = np.zeros((nc, 5)); q = np.zeros((nc, 5))
+        n = np.zeros(nc, dtype=np.int32)
+        lib().orc_tree_cells(self.ptr, box, com, sc, q, n)
+        return dict(box=box, com=com, scalars=sc, q=q, N=n)
+
+    def hydro_grav_forces(self, s):
+        N = self.N
+        out = _grav_out(N, self.p.ndim)
+        out["ndirect"] = np.zeros(N, dtype=np.int32)
+        out["ncell"] = np.zeros(N, dtype=np.int32)
+        rc = lib().orc_hydro_grav_forces_tree(C.byref(self.p), self.ptr, N, *_grav_args(self.p, s), out["a"],
+                                              out["atree"], out["gpot"], out["dudt"], out["div_v"],
+                                              out["dalphadt"], out["levelneib"], out["ndirect"], out["ncell"])
+        if rc != 0:
+            raise RuntimeError("oracle tree gravity: unsupported parameters")
+        return out
