@@ -1,0 +1,847 @@
+/*=================================================================================================
+ *  capi.cu -- the C ABI of libgsph (include/gsph.h): lifecycle, host<->HBM data movement, the
+ *  operator surface and the parity/inspection calls.  No CPU fallback: every compute entry point
+ *  launches CUDA kernels and fails with GSPH_ENODEVICE / GSPH_ECUDA when that is impossible.
+ *=================================================================================================*/
+#include "gsph_internal.cuh"
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+static std::string g_create_error;
+
+namespace {
+
+struct FieldMap { int pf; size_t off; };      /* offset of a gsph_field inside gsph_particle_view */
+#define VOFF(member) offsetof(gsph_particle_view, member)
+const FieldMap kDoubleFields[] = {
+  {F_RX, VOFF(r[0])}, {F_RY, VOFF(r[1])}, {F_RZ, VOFF(r[2])},
+  {F_VX, VOFF(v[0])}, {F_VY, VOFF(v[1])}, {F_VZ, VOFF(v[2])},
+  {F_AX, VOFF(a[0])}, {F_AY, VOFF(a[1])}, {F_AZ, VOFF(a[2])},
+  {F_ATX, VOFF(atree[0])}, {F_ATY, VOFF(atree[1])}, {F_ATZ, VOFF(atree[2])},
+  {F_M, VOFF(m)}, {F_H, VOFF(h)}, {F_U, VOFF(u)}, {F_RHO, VOFF(rho)}, {F_HR2, VOFF(hrangesqd)},
+  {F_HFAC, VOFF(hfactor)}, {F_INVOMEGA, VOFF(invomega)}, {F_ZETA, VOFF(zeta)},
+  {F_SOUND, VOFF(sound)}, {F_PRESS, VOFF(pressure)}, {F_DUDT, VOFF(dudt)}, {F_DIVV, VOFF(div_v)},
+  {F_ALPHA, VOFF(alpha)}, {F_DALPHADT, VOFF(dalphadt)}, {F_GPOT, VOFF(gpot)},
+  {F_GPOTHYDRO, VOFF(gpot_hydro)},
+};
+const FieldMap kIntFields[] = {
+  {I_FLAGS, VOFF(flags)}, {I_PTYPE, VOFF(ptype)}, {I_LEVEL, VOFF(level)},
+  {I_LEVELNEIB, VOFF(levelneib)}, {I_IORIG, VOFF(iorig)}, {I_SINKID, VOFF(sinkid)},
+};
+const int kNDoubleFields = sizeof(kDoubleFields)/sizeof(kDoubleFields[0]);
+const int kNIntFields = sizeof(kIntFields)/sizeof(kIntFields[0]);
+
+inline const gsph_field& vfield(const gsph_particle_view* v, size_t off)
+{
+  return *reinterpret_cast<const gsph_field*>(reinterpret_cast<const char*>(v) + off);
+}
+
+double default_double(int pf) { return (pf == F_H || pf == F_INVOMEGA) ? 1.0 : 0.0; }
+int default_int(int f)
+{
+  if (f == I_FLAGS) return (int) GSPH_FLAG_ACTIVE;     /* absent flags: every particle is active */
+  if (f == I_SINKID) return -1;
+  if (f == I_IORIG) return -1;
+  return 0;
+}
+
+template <class T>
+__global__ void fill_kernel(int64_t n, T* a, T v)
+{
+  const int64_t i = (int64_t) blockIdx.x*blockDim.x + threadIdx.x;
+  if (i < n) a[i] = v;
+}
+
+/* de-interleave fields of an AoS image that was copied to the device in one piece */
+struct AosPlan { int nf; int ni; unsigned off_d[NF_DOUBLE]; int pf_d[NF_DOUBLE]; unsigned off_i[NF_INT]; int pf_i[NF_INT]; };
+struct DevPtrs { double* f[NF_DOUBLE]; int32_t* i[NF_INT]; };
+
+__global__ void aos_unpack_kernel(int64_t n0, int64_t n, const char* __restrict__ aos, size_t stride, AosPlan plan, DevPtrs out)
+{
+  const int64_t i = (int64_t) blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const char* rec = aos + (size_t) i*stride;
+  for (int k = 0; k < plan.nf; k++) out.f[plan.pf_d[k]][n0 + i] = *reinterpret_cast<const double*>(rec + plan.off_d[k]);
+  for (int k = 0; k < plan.ni; k++) out.i[plan.pf_i[k]][n0 + i] = *reinterpret_cast<const int32_t*>(rec + plan.off_i[k]);
+}
+
+__global__ void scatter_fields_kernel(int N, const int32_t* perm, DevPtrs P, DevPtrs H, unsigned long long dmask, unsigned imask)
+{
+  const int p = blockIdx.x*blockDim.x + threadIdx.x;
+  if (p >= N) return;
+  const int i = perm[p];
+  for (int f = 0; f < NF_DOUBLE; f++) if ((dmask >> f) & 1ull) H.f[f][i] = P.f[f][p];
+  for (int f = 0; f < NF_INT; f++) if ((imask >> f) & 1u) H.i[f][i] = P.i[f][p];
+}
+
+template <int NDIM>
+__global__ void zero_acc_kernel(int N, DevPtrs P)
+{
+  const int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  if (!(((unsigned) P.i[I_FLAGS][i]) & GSPH_FLAG_ACTIVE)) return;
+  P.i[I_LEVELNEIB][i] = 0;
+  P.f[F_DIVV][i] = 0.0; P.f[F_DUDT][i] = 0.0; P.f[F_GPOT][i] = 0.0; P.f[F_GPOTHYDRO][i] = 0.0;
+#pragma unroll
+  for (int k = 0; k < NDIM; k++) { P.f[F_AX + k][i] = 0.0; P.f[F_ATX + k][i] = 0.0; }
+}
+
+/* register-resident FMA chains for the FP roofline denominators */
+template <class T>
+__global__ void fma_peak_kernel(T* out, int iters)
+{
+  T a0 = (T) threadIdx.x*(T) 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const T b = (T) 0.999999, c = (T) 1e-7;
+  for (int i = 0; i < iters; i++) {
+    a0 = a0*b + c; a1 = a1*b + c; a2 = a2*b + c; a3 = a3*b + c;
+    a4 = a4*b + c; a5 = a5*b + c; a6 = a6*b + c; a7 = a7*b + c;
+  }
+  out[blockIdx.x*blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+DevPtrs devptrs(double* const* f, int32_t* const* i)
+{
+  DevPtrs d;
+  for (int k = 0; k < NF_DOUBLE; k++) d.f[k] = f[k];
+  for (int k = 0; k < NF_INT; k++) d.i[k] = i[k];
+  return d;
+}
+
+int ensure_capacity(gsph_handle* h, int64_t N)
+{
+  if (N <= h->Ncap) return GSPH_OK;
+  const int64_t cap = N + N/16 + 1024;
+  for (int f = 0; f < NF_DOUBLE; f++) {
+    if (h->H[f]) cudaFree(h->H[f]); if (h->P[f]) cudaFree(h->P[f]);
+    h->H[f] = h->P[f] = nullptr;
+    CUDA_TRY(h, cudaMalloc(&h->H[f], cap*sizeof(double)));
+    CUDA_TRY(h, cudaMalloc(&h->P[f], cap*sizeof(double)));
+  }
+  for (int f = 0; f < NF_INT; f++) {
+    if (h->HI[f]) cudaFree(h->HI[f]); if (h->PI[f]) cudaFree(h->PI[f]);
+    h->HI[f] = h->PI[f] = nullptr;
+    CUDA_TRY(h, cudaMalloc(&h->HI[f], cap*sizeof(int32_t)));
+    CUDA_TRY(h, cudaMalloc(&h->PI[f], cap*sizeof(int32_t)));
+  }
+  if (h->perm) cudaFree(h->perm);
+  h->perm = nullptr;
+  CUDA_TRY(h, cudaMalloc(&h->perm, cap*sizeof(int32_t)));
+  h->Ncap = cap;
+  h->have_tree = false;
+  return GSPH_OK;
+}
+
+int ensure_pinned(gsph_handle* h, size_t bytes)
+{
+  if (bytes <= h->pinned_bytes) return GSPH_OK;
+  if (h->pinned) cudaFreeHost(h->pinned);
+  h->pinned = nullptr; h->pinned_bytes = 0;
+  CUDA_TRY(h, cudaMallocHost(&h->pinned, bytes));
+  h->pinned_bytes = bytes;
+  return GSPH_OK;
+}
+
+void fill_devparams(gsph_handle* h)
+{
+  const gsph_config& c = h->cfg;
+  DevParams& d = h->dp;
+  memset(&d, 0, sizeof d);
+  d.ndim = c.ndim; d.kernel = c.kernel; d.tabulated = c.tabulated_kernel;
+  d.kernrange = c.kernel == GSPH_KERNEL_M4 ? 2.0 : 3.0;
+  d.kernrangesqd = d.kernrange*d.kernrange;
+  d.kernnorm = gsph_kernnorm(c.ndim, c.kernel);
+  d.h_fac = c.h_fac; d.h_converge = c.h_converge;
+  d.avisc = c.avisc; d.acond = c.acond; d.tdavisc = c.tdavisc;
+  d.alpha_visc = c.alpha_visc; d.beta_visc = c.beta_visc; d.alpha_visc_min = c.alpha_visc_min;
+  d.eos = c.eos; d.gamma_eos = c.gamma_eos; d.gammam1 = c.gamma_eos - 1.0;
+  d.temp0 = c.temp0; d.mu_bar = c.mu_bar; d.rho_bary = c.rho_bary;
+  d.any_periodic = 0;
+  for (int k = 0; k < 3; k++) {
+    d.boxmin[k] = c.boxmin[k]; d.boxmax[k] = c.boxmax[k];
+    d.boxsize[k] = c.boxmax[k] - c.boxmin[k]; d.boxhalf[k] = 0.5*d.boxsize[k];
+    d.periodic[k] = (k < c.ndim && c.boundary_lhs[k] == GSPH_BOUNDARY_PERIODIC) ? 1 : 0;
+    d.any_periodic |= d.periodic[k];
+  }
+  d.hydro_forces = c.hydro_forces; d.self_gravity = c.self_gravity; d.multipole = c.multipole;
+  d.gravity_mac = c.gravity_mac; d.thetamaxsqd = c.thetamaxsqd; d.invthetamaxsqd = 1.0/c.thetamaxsqd;
+  d.macerror = c.macerror; d.Nleafmax = c.Nleafmax; d.create_sinks = c.create_sinks;
+}
+
+int validate_config(const gsph_config* c, std::string& err)
+{
+  if (c->abi_version != GSPH_ABI_VERSION) { err = "gsph_config.abi_version mismatch"; return GSPH_EINVAL; }
+  if (c->ndim < 1 || c->ndim > 3) { err = "ndim must be 1, 2 or 3"; return GSPH_EINVAL; }
+  if (c->kernel != GSPH_KERNEL_M4 && c->kernel != GSPH_KERNEL_QUINTIC) { err = "kernel must be m4 or quintic"; return GSPH_EINVAL; }
+  if (!(c->h_fac > 0) || !(c->h_converge > 0)) { err = "h_fac and h_converge must be positive"; return GSPH_EINVAL; }
+  if (c->Nleafmax < 1) { err = "Nleafmax must be >= 1"; return GSPH_EINVAL; }
+  if (c->tdavisc != GSPH_TDAVISC_NONE && c->tdavisc != GSPH_TDAVISC_MM97) { err = "time_dependent_avisc = cd2010 is not on the accelerated path"; return GSPH_EINVAL; }
+  for (int k = 0; k < c->ndim; k++) {
+    if (c->boundary_lhs[k] == GSPH_BOUNDARY_MIRROR || c->boundary_rhs[k] == GSPH_BOUNDARY_MIRROR) {
+      err = "mirror boundaries are not on the accelerated path"; return GSPH_EINVAL;
+    }
+    if ((c->boundary_lhs[k] == GSPH_BOUNDARY_PERIODIC) != (c->boundary_rhs[k] == GSPH_BOUNDARY_PERIODIC)) {
+      err = "periodic boundaries must be set on both sides of a dimension"; return GSPH_EINVAL;
+    }
+    if (c->boundary_lhs[k] == GSPH_BOUNDARY_PERIODIC && !(c->boxmax[k] > c->boxmin[k])) {
+      err = "periodic dimension needs boxmax > boxmin"; return GSPH_EINVAL;
+    }
+  }
+  if (c->self_gravity) {
+    if (c->gravity_mac != GSPH_MAC_GEOMETRIC) { err = "only gravity_mac = geometric is on the accelerated path"; return GSPH_EINVAL; }
+    if (!(c->thetamaxsqd > 0)) { err = "thetamaxsqd must be positive"; return GSPH_EINVAL; }
+    for (int k = 0; k < c->ndim; k++)
+      if (c->boundary_lhs[k] == GSPH_BOUNDARY_PERIODIC) { err = "periodic (Ewald) gravity is not on the accelerated path"; return GSPH_EINVAL; }
+  }
+  return GSPH_OK;
+}
+
+struct Timer {
+  gsph_handle* h; float* out;
+  Timer(gsph_handle* h_, float* o) : h(h_), out(o) { cudaEventRecord(h->ev0, h->stream); }
+  void stop() { cudaEventRecord(h->ev1, h->stream); cudaEventSynchronize(h->ev1); cudaEventElapsedTime(out, h->ev0, h->ev1); }
+};
+
+int reset_status(gsph_handle* h)
+{
+  CUDA_TRY(h, cudaMemsetAsync(h->status, 0, sizeof(DevStatus), h->stream));
+  return GSPH_OK;
+}
+
+int fetch_status(gsph_handle* h)
+{
+  CUDA_TRY(h, cudaMemcpyAsync(h->status_host, h->status, sizeof(DevStatus), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return GSPH_OK;
+}
+
+}  // namespace
+
+/*------------------------------------------------------------------------------------------------*/
+int gsph_ensure_cand(gsph_handle* h, int warps, size_t cap_per_warp)
+{
+  if (cap_per_warp == 0) cap_per_warp = h->cand_cap_per_warp;
+  if (cap_per_warp == 0) {
+    const char* e = getenv("GSPH_CAND_CAP");
+    cap_per_warp = e ? (size_t) atol(e) : 8192;
+  }
+  if (h->cand && warps <= h->cand_warps && cap_per_warp <= h->cand_cap_per_warp) return GSPH_OK;
+  if (h->cand) cudaFree(h->cand);
+  h->cand = nullptr;
+  if (warps < h->cand_warps) warps = h->cand_warps;
+  CUDA_TRY(h, cudaMalloc(&h->cand, (size_t) warps*cap_per_warp*sizeof(int32_t)));
+  h->cand_warps = warps; h->cand_cap_per_warp = cap_per_warp;
+  return GSPH_OK;
+}
+
+int gsph_check_status(gsph_handle* h, const char* where)
+{
+  int rc = fetch_status(h);
+  if (rc) return rc;
+  const DevStatus& s = *h->status_host;
+  if (s.err_stack_overflow) { h->err = std::string(where) + ": tree-walk stack overflow"; return GSPH_ENOMEM; }
+  if (s.err_converge) { h->err = "Problem with convergence of h-rho iteration"; return GSPH_ECONVERGE; }
+  if (s.err_hsearch) { h->err = std::string(where) + ": search radius grew more than 60 times"; return GSPH_ECONVERGE; }
+  return GSPH_OK;
+}
+
+extern "C" {
+
+int gsph_default_config(gsph_config* c)
+{
+  if (!c) return GSPH_EINVAL;
+  memset(c, 0, sizeof *c);
+  c->abi_version = GSPH_ABI_VERSION;
+  c->ndim = 3; c->kernel = GSPH_KERNEL_M4; c->tabulated_kernel = 1;
+  c->h_fac = 1.2; c->h_converge = 0.01;
+  c->avisc = GSPH_AVISC_MON97; c->acond = GSPH_ACOND_NONE; c->tdavisc = GSPH_TDAVISC_NONE;
+  c->alpha_visc = 1.0; c->beta_visc = 2.0; c->alpha_visc_min = 0.1;
+  c->eos = GSPH_EOS_ADIABATIC; c->gamma_eos = 1.6666666666666;
+  c->temp0 = 1.0; c->mu_bar = 1.0; c->rho_bary = 1.0e-14;
+  for (int k = 0; k < 3; k++) { c->boxmin[k] = 0.0; c->boxmax[k] = 0.0; c->boundary_lhs[k] = c->boundary_rhs[k] = GSPH_BOUNDARY_OPEN; }
+  c->hydro_forces = 1; c->self_gravity = 0;
+  c->thetamaxsqd = 0.1; c->gravity_mac = GSPH_MAC_GEOMETRIC; c->macerror = 1.0e-4;
+  c->multipole = GSPH_MULTIPOLE_QUADRUPOLE; c->Nleafmax = 6;
+  for (int i = 0; i < GSPH_NTYPES; i++) { c->hmask[i] = 0; c->hydromask[i] = 0; }
+  c->hmask[GSPH_TYPE_GAS] = 1u << GSPH_TYPE_GAS; c->hydromask[GSPH_TYPE_GAS] = 1u << GSPH_TYPE_GAS;
+  c->gravmask = 1u << GSPH_TYPE_GAS; c->hydro_forces_type = 1u << GSPH_TYPE_GAS;
+  c->self_gravity_type = 1u << GSPH_TYPE_GAS;
+  c->create_sinks = 0; c->device = 0;
+  return GSPH_OK;
+}
+
+int gsph_create(const gsph_config* cfg, gsph_handle** out)
+{
+  if (!cfg || !out) { g_create_error = "gsph_create: NULL argument"; return GSPH_EINVAL; }
+  *out = nullptr;
+  int rc = validate_config(cfg, g_create_error);
+  if (rc) return rc;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_error = "gsph_create: no CUDA device (libgsph has no CPU fallback)";
+    return GSPH_ENODEVICE;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) { g_create_error = "gsph_create: bad device ordinal"; return GSPH_EINVAL; }
+  gsph_handle* h = new gsph_handle();
+  h->cfg = *cfg; h->device = cfg->device;
+  memset(&h->stats, 0, sizeof h->stats);
+  auto fail = [&](const char* what, cudaError_t ce) {
+    g_create_error = std::string(what) + ": " + cudaGetErrorString(ce);
+    gsph_destroy(h);
+    return GSPH_ECUDA;
+  };
+  if ((e = cudaSetDevice(h->device)) != cudaSuccess) return fail("cudaSetDevice", e);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, h->device)) != cudaSuccess) return fail("cudaGetDeviceProperties", e);
+  h->sm_count = prop.multiProcessorCount;
+  if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+  if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return fail("cudaEventCreate", e);
+  if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return fail("cudaEventCreate", e);
+  fill_devparams(h);
+  std::vector<double> tab(6*GSPH_TABLE_RES);
+  gsph_make_tables(cfg->ndim, cfg->kernel, tab.data());
+  if ((e = cudaMalloc(&h->tables, tab.size()*sizeof(double))) != cudaSuccess) return fail("cudaMalloc", e);
+  if ((e = cudaMemcpy(h->tables, tab.data(), tab.size()*sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) return fail("cudaMemcpy", e);
+  if ((e = cudaMalloc(&h->status, sizeof(DevStatus))) != cudaSuccess) return fail("cudaMalloc", e);
+  if ((e = cudaMallocHost(&h->status_host, sizeof(DevStatus))) != cudaSuccess) return fail("cudaMallocHost", e);
+  if ((e = cudaMalloc(&h->work_counter, 4*sizeof(int))) != cudaSuccess) return fail("cudaMalloc", e);
+  *out = h;
+  return GSPH_OK;
+}
+
+void gsph_destroy(gsph_handle* h)
+{
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  auto fre = [](void* p) { if (p) cudaFree(p); };
+  for (int f = 0; f < NF_DOUBLE; f++) { fre(h->H[f]); fre(h->P[f]); }
+  for (int f = 0; f < NF_INT; f++) { fre(h->HI[f]); fre(h->PI[f]); }
+  fre(h->perm); fre(h->tables); fre(h->scratch); fre(h->cand); fre(h->gravlist); fre(h->status); fre(h->work_counter); fre(h->done);
+  TreeDev& T = h->tree;
+  fre(T.first); fre(T.count); fre(T.nactive); fre(T.m); fre(T.rmax); fre(T.hmax); fre(T.cdistsqd);
+  for (int k = 0; k < 3; k++) { fre(T.bbmin[k]); fre(T.bbmax[k]); fre(T.hbmin[k]); fre(T.hbmax[k]); fre(T.rcell[k]); fre(T.com[k]); fre(T.vcom[k]); }
+  for (int k = 0; k < 5; k++) fre(T.q[k]);
+  if (h->status_host) cudaFreeHost(h->status_host);
+  if (h->pinned) cudaFreeHost(h->pinned);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char* gsph_last_error(const gsph_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+/*------------------------------------------------------------------------------------------------
+ * upload: contiguous (stride == element size) fields go straight to the device; strided fields
+ * that all live inside one AoS record (the reference's GradhSphParticle array) are moved as ONE
+ * bulk copy per chunk and de-interleaved on the device.
+ *-----------------------------------------------------------------------------------------------*/
+int gsph_upload(gsph_handle* h, const gsph_particle_view* view, int64_t N)
+{
+  if (!h) return GSPH_EINVAL;
+  if (!view || N <= 0 || N > 2000000000ll) { h->err = "gsph_upload: bad arguments"; return GSPH_EINVAL; }
+  cudaSetDevice(h->device);
+  Timer tm(h, &h->stats.ms_upload);
+  int rc = ensure_capacity(h, N);
+  if (rc) return rc;
+  const int nd = h->cfg.ndim;
+  if (!vfield(view, VOFF(r[0])).base || !vfield(view, VOFF(m)).base || !vfield(view, VOFF(h)).base) {
+    h->err = "gsph_upload: r, m and h are required"; return GSPH_EINVAL;
+  }
+  /* classify */
+  AosPlan plan; plan.nf = plan.ni = 0;
+  const char* lo = nullptr; const char* hi = nullptr; size_t stride = 0; bool bulk_ok = true;
+  auto consider = [&](const gsph_field& f, size_t esize) {
+    if (!f.base || f.stride == esize) return;
+    const char* b = (const char*) f.base;
+    if (!lo || b < lo) lo = b;
+    if (!hi || b + esize > hi) hi = b + esize;
+    if (stride == 0) stride = f.stride; else if (stride != f.stride) bulk_ok = false;
+  };
+  for (int k = 0; k < kNDoubleFields; k++) consider(vfield(view, kDoubleFields[k].off), sizeof(double));
+  for (int k = 0; k < kNIntFields; k++) consider(vfield(view, kIntFields[k].off), sizeof(int32_t));
+  if (lo && (size_t)(hi - lo) > stride) bulk_ok = false;
+
+  const int nb = (int)((N + 255)/256);
+  for (int k = 0; k < kNDoubleFields; k++) {
+    const int pf = kDoubleFields[k].pf;
+    const gsph_field& f = vfield(view, kDoubleFields[k].off);
+    const bool unused_dim = (pf >= F_RX && pf <= F_ATZ) && ((pf - F_RX) % 3 >= nd);
+    if (!f.base || unused_dim) fill_kernel<double><<<nb, 256, 0, h->stream>>>(N, h->H[pf], default_double(pf));
+    else if (f.stride == sizeof(double))
+      CUDA_TRY(h, cudaMemcpyAsync(h->H[pf], f.base, N*sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    else if (bulk_ok) { plan.off_d[plan.nf] = (unsigned)((const char*) f.base - lo); plan.pf_d[plan.nf++] = pf; }
+    else {
+      rc = ensure_pinned(h, N*sizeof(double)); if (rc) return rc;
+      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+      double* st = (double*) h->pinned; const char* b = (const char*) f.base;
+#pragma omp parallel for schedule(static)
+      for (int64_t i = 0; i < N; i++) st[i] = *(const double*)(b + (size_t) i*f.stride);
+      CUDA_TRY(h, cudaMemcpyAsync(h->H[pf], st, N*sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    }
+  }
+  for (int k = 0; k < kNIntFields; k++) {
+    const int pf = kIntFields[k].pf;
+    const gsph_field& f = vfield(view, kIntFields[k].off);
+    if (!f.base) fill_kernel<int32_t><<<nb, 256, 0, h->stream>>>(N, h->HI[pf], default_int(pf));
+    else if (f.stride == sizeof(int32_t))
+      CUDA_TRY(h, cudaMemcpyAsync(h->HI[pf], f.base, N*sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    else if (bulk_ok) { plan.off_i[plan.ni] = (unsigned)((const char*) f.base - lo); plan.pf_i[plan.ni++] = pf; }
+    else {
+      rc = ensure_pinned(h, N*sizeof(int32_t)); if (rc) return rc;
+      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+      int32_t* st = (int32_t*) h->pinned; const char* b = (const char*) f.base;
+#pragma omp parallel for schedule(static)
+      for (int64_t i = 0; i < N; i++) st[i] = *(const int32_t*)(b + (size_t) i*f.stride);
+      CUDA_TRY(h, cudaMemcpyAsync(h->HI[pf], st, N*sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+    }
+  }
+  if (bulk_ok && (plan.nf || plan.ni)) {
+    /* AoS records [lo + i*stride, +span) in chunks through the tree-build scratch buffer */
+    const size_t chunk_bytes = (size_t) 256 << 20;
+    int64_t per = (int64_t)(chunk_bytes/stride); if (per < 1) per = 1;
+    if (h->scratch_bytes < (size_t) std::min<int64_t>(per, N)*stride) {
+      if (h->scratch) cudaFree(h->scratch);
+      h->scratch = nullptr; h->scratch_bytes = 0;
+      const size_t want = (size_t) std::min<int64_t>(per, N)*stride;
+      CUDA_TRY(h, cudaMalloc(&h->scratch, want)); h->scratch_bytes = want;
+    }
+    DevPtrs out = devptrs(h->H, h->HI);
+    for (int64_t n0 = 0; n0 < N; n0 += per) {
+      const int64_t n = std::min<int64_t>(per, N - n0);
+      size_t bytes = (size_t) n*stride;
+      if (n0 + n == N) bytes = (size_t)(n - 1)*stride + (size_t)(hi - lo);   /* do not read past the last record */
+      CUDA_TRY(h, cudaMemcpyAsync(h->scratch, lo + (size_t) n0*stride, bytes, cudaMemcpyHostToDevice, h->stream));
+      aos_unpack_kernel<<<(int)((n + 255)/256), 256, 0, h->stream>>>(n0, n, (const char*) h->scratch, stride, plan, out);
+      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  if (N != h->N) h->have_tree = false;
+  h->N = N; h->uploaded = true; h->sorted_valid = false; h->density_done = false;
+  h->stats.Nhydro = N;
+  tm.stop();
+  return GSPH_OK;
+}
+
+int gsph_download(gsph_handle* h, const gsph_particle_view* view, uint32_t field_mask)
+{
+  if (!h) return GSPH_EINVAL;
+  if (!view) { h->err = "gsph_download: NULL view"; return GSPH_EINVAL; }
+  if (!h->sorted_valid) { h->err = "gsph_download before gsph_build_tree"; return GSPH_ESTATE; }
+  cudaSetDevice(h->device);
+  Timer tm(h, &h->stats.ms_download);
+  const int64_t N = h->N;
+  unsigned long long dmask = 0; unsigned imask = 0;
+  auto want_d = [&](int pf) {
+    if (field_mask == GSPH_F_ALL) return true;
+    const bool dens = pf == F_H || pf == F_RHO || pf == F_HR2 || pf == F_HFAC || pf == F_INVOMEGA || pf == F_ZETA ||
+                      pf == F_U || pf == F_SOUND || pf == F_PRESS || pf == F_DIVV;
+    const bool forc = (pf >= F_AX && pf <= F_ATZ) || pf == F_DUDT || pf == F_DIVV || pf == F_DALPHADT ||
+                      pf == F_GPOT || pf == F_GPOTHYDRO;
+    return ((field_mask & GSPH_F_DENSITY) && dens) || ((field_mask & GSPH_F_FORCES) && forc);
+  };
+  auto want_i = [&](int pf) {
+    if (field_mask == GSPH_F_ALL) return true;
+    return ((field_mask & GSPH_F_DENSITY) && pf == I_FLAGS) || ((field_mask & GSPH_F_FORCES) && pf == I_LEVELNEIB);
+  };
+  for (int k = 0; k < kNDoubleFields; k++)
+    if (vfield(view, kDoubleFields[k].off).base && want_d(kDoubleFields[k].pf)) dmask |= 1ull << kDoubleFields[k].pf;
+  for (int k = 0; k < kNIntFields; k++)
+    if (vfield(view, kIntFields[k].off).base && want_i(kIntFields[k].pf)) imask |= 1u << kIntFields[k].pf;
+  scatter_fields_kernel<<<(int)((N + 255)/256), 256, 0, h->stream>>>((int) N, h->perm, devptrs(h->P, h->PI),
+                                                                   devptrs(h->H, h->HI), dmask, imask);
+  h->stats.kernel_launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  for (int k = 0; k < kNDoubleFields; k++) {
+    const int pf = kDoubleFields[k].pf;
+    if (!((dmask >> pf) & 1ull)) continue;
+    const gsph_field& f = vfield(view, kDoubleFields[k].off);
+    if (f.stride == sizeof(double))
+      CUDA_TRY(h, cudaMemcpyAsync(f.base, h->H[pf], N*sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    else {
+      int rc = ensure_pinned(h, N*sizeof(double)); if (rc) return rc;
+      CUDA_TRY(h, cudaMemcpyAsync(h->pinned, h->H[pf], N*sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+      const double* st = (const double*) h->pinned; char* b = (char*) f.base;
+#pragma omp parallel for schedule(static)
+      for (int64_t i = 0; i < N; i++) *(double*)(b + (size_t) i*f.stride) = st[i];
+    }
+  }
+  for (int k = 0; k < kNIntFields; k++) {
+    const int pf = kIntFields[k].pf;
+    if (!((imask >> pf) & 1u)) continue;
+    const gsph_field& f = vfield(view, kIntFields[k].off);
+    if (f.stride == sizeof(int32_t))
+      CUDA_TRY(h, cudaMemcpyAsync(f.base, h->HI[pf], N*sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    else {
+      int rc = ensure_pinned(h, N*sizeof(int32_t)); if (rc) return rc;
+      CUDA_TRY(h, cudaMemcpyAsync(h->pinned, h->HI[pf], N*sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+      const int32_t* st = (const int32_t*) h->pinned; char* b = (char*) f.base;
+#pragma omp parallel for schedule(static)
+      for (int64_t i = 0; i < N; i++) *(int32_t*)(b + (size_t) i*f.stride) = st[i];
+    }
+  }
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  tm.stop();
+  return GSPH_OK;
+}
+
+/*------------------------------------------------------------------------------------------------*/
+int gsph_build_tree(gsph_handle* h, int mode, double dt)
+{
+  if (!h) return GSPH_EINVAL;
+  if (!h->uploaded) { h->err = "gsph_build_tree before gsph_upload"; return GSPH_ESTATE; }
+  if (mode < 0 || mode > 2) { h->err = "gsph_build_tree: mode must be 0, 1 or 2"; return GSPH_EINVAL; }
+  cudaSetDevice(h->device);
+  Timer tm(h, &h->stats.ms_build_tree);
+  if (!h->have_tree) mode = 0;
+  int rc = gsph_tree_build(h, mode, dt);
+  if (rc) return rc;
+  int nact = 0;
+  CUDA_TRY(h, cudaMemcpyAsync(&nact, h->tree.nactive, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  tm.stop();
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->all_active = (nact == h->N);
+  h->stats.n_active = nact;
+  return GSPH_OK;
+}
+
+int gsph_update_active_counters(gsph_handle* h)
+{
+  if (!h) return GSPH_EINVAL;
+  if (!h->have_tree || !h->sorted_valid) { h->err = "gsph_update_active_counters before gsph_build_tree"; return GSPH_ESTATE; }
+  cudaSetDevice(h->device);
+  int rc = gsph_tree_update_active(h);
+  if (rc) return rc;
+  int nact = 0;
+  CUDA_TRY(h, cudaMemcpyAsync(&nact, h->tree.nactive, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->all_active = (nact == h->N); h->stats.n_active = nact;
+  return GSPH_OK;
+}
+
+static int run_with_regrow(gsph_handle* h, const char* where, int (*pass)(gsph_handle*, int), int arg)
+{
+  /* a cohort whose candidate list overflows its scratch slot is skipped and flagged (nothing of it
+     is written); the pass is repeated for the flagged cohorts with doubled scratch -- the
+     reference's "return -1 and double the buffer" convention (Tree.cpp:263-265,
+     GradhSphTree.cpp:172-185) */
+  for (int attempt = 0; attempt < 8; attempt++) {
+    int rc = pass(h, arg);
+    if (rc) return rc;
+    rc = gsph_check_status(h, where);
+    if (rc) return rc;
+    const DevStatus& s = *h->status_host;
+    if (!s.err_cand_overflow) return GSPH_OK;
+    if (s.err_cand_overflow == 2) { h->grav_cap_cells *= 2; h->grav_cap_direct *= 2; cudaFree(h->gravlist); h->gravlist = nullptr; }
+    else {
+      size_t want = h->cand_cap_per_warp*2;
+      while (want < s.cand_need) want *= 2;
+      const int w = h->cand_warps;
+      cudaFree(h->cand); h->cand = nullptr; h->cand_warps = 0;
+      rc = gsph_ensure_cand(h, w, want);
+      if (rc) return rc;
+    }
+    CUDA_TRY(h, cudaMemsetAsync(&h->status->err_cand_overflow, 0, sizeof(int), h->stream));
+  }
+  h->err = std::string(where) + ": candidate scratch overflow persists";
+  return GSPH_ENOMEM;
+}
+
+static int pass_density(gsph_handle* h, int) { return gsph_run_density(h); }
+static int pass_hydro(gsph_handle* h, int g) { return gsph_run_hydro(h, g); }
+static int pass_gravity(gsph_handle* h, int) { return gsph_run_gravity(h); }
+int gsph_prepare_done_flags(gsph_handle* h)
+{
+  const size_t need = (size_t) 1 << h->tree.ltot;
+  if (need > h->done_cap) {
+    if (h->done) cudaFree(h->done);
+    h->done = nullptr; h->done_cap = 0;
+    CUDA_TRY(h, cudaMalloc(&h->done, need));
+    h->done_cap = need;
+  }
+  CUDA_TRY(h, cudaMemsetAsync(h->done, 0, need, h->stream));
+  return GSPH_OK;
+}
+
+int gsph_update_properties(gsph_handle* h)
+{
+  if (!h) return GSPH_EINVAL;
+  if (!h->have_tree || !h->sorted_valid) { h->err = "gsph_update_properties before gsph_build_tree"; return GSPH_ESTATE; }
+  cudaSetDevice(h->device);
+  Timer tm(h, &h->stats.ms_properties);
+  int rc = reset_status(h); if (rc) return rc;
+  rc = gsph_prepare_done_flags(h); if (rc) return rc;
+  rc = run_with_regrow(h, "gsph_update_properties", pass_density, 0);
+  if (rc) return rc;
+  rc = gsph_tree_update_hmax(h);                        /* tree->UpdateAllHmaxValues, GradhSphTree.cpp:268 */
+  if (rc) return rc;
+  tm.stop();
+  const DevStatus& s = *h->status_host;
+  h->stats.n_active = (int64_t) s.ntarget;
+  h->stats.hiter_mean = s.ntarget ? (double) s.hiter_sum/(double) s.ntarget : 0.0;
+  h->stats.hiter_max = s.hiter_max;
+  h->stats.density_retries = s.density_retries;
+  h->density_done = true;
+  return GSPH_OK;
+}
+
+int gsph_zero_accelerations(gsph_handle* h)
+{
+  if (!h) return GSPH_EINVAL;
+  if (!h->sorted_valid) { h->err = "gsph_zero_accelerations before gsph_build_tree"; return GSPH_ESTATE; }
+  cudaSetDevice(h->device);
+  const int N = (int) h->N;
+  DevPtrs P = devptrs(h->P, h->PI);
+  switch (h->cfg.ndim) {
+  case 1: zero_acc_kernel<1><<<(N + 255)/256, 256, 0, h->stream>>>(N, P); break;
+  case 2: zero_acc_kernel<2><<<(N + 255)/256, 256, 0, h->stream>>>(N, P); break;
+  default: zero_acc_kernel<3><<<(N + 255)/256, 256, 0, h->stream>>>(N, P); break;
+  }
+  h->stats.kernel_launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return GSPH_OK;
+}
+
+static void force_stats(gsph_handle* h)
+{
+  const DevStatus& s = *h->status_host;
+  h->stats.n_active = (int64_t) s.ntarget;
+  h->stats.ngb_mean = s.ntarget ? (double) s.ngb_sum/(double) s.ntarget : 0.0;
+  h->stats.ngb_max = s.ngb_max;
+  h->stats.cand_mean = s.ntarget ? (double) s.cand_sum/(double) s.ntarget : 0.0;
+  h->stats.ndirect_mean = s.nleaf_grav ? (double) s.ndirect_sum/(double) s.nleaf_grav : 0.0;
+  h->stats.ncell_mean = s.nleaf_grav ? (double) s.ncell_sum/(double) s.nleaf_grav : 0.0;
+}
+
+int gsph_update_hydro_forces(gsph_handle* h)
+{
+  if (!h) return GSPH_EINVAL;
+  if (!h->have_tree || !h->sorted_valid) { h->err = "gsph_update_hydro_forces before gsph_build_tree"; return GSPH_ESTATE; }
+  cudaSetDevice(h->device);
+  Timer tm(h, &h->stats.ms_forces);
+  int rc = reset_status(h); if (rc) return rc;
+  rc = gsph_prepare_done_flags(h); if (rc) return rc;
+  rc = run_with_regrow(h, "gsph_update_hydro_forces", pass_hydro, 0);
+  if (rc) return rc;
+  tm.stop();
+  force_stats(h);
+  return GSPH_OK;
+}
+
+int gsph_update_all_forces(gsph_handle* h, const double* stars, int Nstar)
+{
+  if (!h) return GSPH_EINVAL;
+  if (!h->have_tree || !h->sorted_valid) { h->err = "gsph_update_all_forces before gsph_build_tree"; return GSPH_ESTATE; }
+  if (!h->cfg.self_gravity) { h->err = "gsph_update_all_forces needs self_gravity = 1 in the config"; return GSPH_EINVAL; }
+  if (Nstar > 0 || stars) { h->err = "star particles are not on the accelerated path yet (ComputeStarGravForces)"; return GSPH_EINVAL; }
+  cudaSetDevice(h->device);
+  Timer tm(h, &h->stats.ms_forces);
+  int rc = reset_status(h); if (rc) return rc;
+  rc = gsph_prepare_done_flags(h); if (rc) return rc;
+  rc = run_with_regrow(h, "gsph_update_all_forces(neighbours)", pass_hydro, 1);
+  if (rc) return rc;
+  const DevStatus keep = *h->status_host;
+  rc = gsph_prepare_done_flags(h); if (rc) return rc;
+  rc = run_with_regrow(h, "gsph_update_all_forces(gravity)", pass_gravity, 0);
+  if (rc) return rc;
+  tm.stop();
+  (void) keep;
+  force_stats(h);
+  return GSPH_OK;
+}
+
+int gsph_get_hmax(gsph_handle* h, double* hmax)
+{
+  if (!h || !hmax) return GSPH_EINVAL;
+  if (!h->have_tree) { h->err = "gsph_get_hmax before gsph_build_tree"; return GSPH_ESTATE; }
+  cudaSetDevice(h->device);
+  CUDA_TRY(h, cudaMemcpyAsync(hmax, h->tree.hmax, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return GSPH_OK;
+}
+
+int gsph_synchronize(gsph_handle* h)
+{
+  if (!h) return GSPH_EINVAL;
+  cudaSetDevice(h->device);
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return GSPH_OK;
+}
+
+/*------------------------------------------------------------------------------------------------*/
+int gsph_neighbour_counts(gsph_handle* h, int32_t* counts)
+{
+  if (!h || !counts) return GSPH_EINVAL;
+  if (!h->have_tree || !h->sorted_valid) { h->err = "gsph_neighbour_counts before gsph_build_tree"; return GSPH_ESTATE; }
+  cudaSetDevice(h->device);
+  const int64_t N = h->N;
+  int32_t* d = nullptr;
+  CUDA_TRY(h, cudaMalloc(&d, N*sizeof(int32_t)));
+  CUDA_TRY(h, cudaMemsetAsync(d, 0, N*sizeof(int32_t), h->stream));
+  int rc = reset_status(h);
+  if (!rc) rc = gsph_run_neiblist(h, d, nullptr, nullptr);
+  if (!rc) rc = gsph_check_status(h, "gsph_neighbour_counts");
+  if (!rc && h->status_host->err_cand_overflow) { h->err = "gsph_neighbour_counts: candidate scratch overflow (set GSPH_CAND_CAP)"; rc = GSPH_ENOMEM; }
+  if (!rc && cudaMemcpy(counts, d, N*sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess) { h->err = "cudaMemcpy failed"; rc = GSPH_ECUDA; }
+  cudaFree(d);
+  return rc;
+}
+
+int gsph_neighbour_lists(gsph_handle* h, const int64_t* offsets, int32_t* idx)
+{
+  if (!h || !offsets || !idx) return GSPH_EINVAL;
+  if (!h->have_tree || !h->sorted_valid) { h->err = "gsph_neighbour_lists before gsph_build_tree"; return GSPH_ESTATE; }
+  cudaSetDevice(h->device);
+  const int64_t N = h->N, total = offsets[N];
+  int64_t* doff = nullptr; int32_t* didx = nullptr;
+  CUDA_TRY(h, cudaMalloc(&doff, (N + 1)*sizeof(int64_t)));
+  if (cudaMalloc(&didx, std::max<int64_t>(total, 1)*sizeof(int32_t)) != cudaSuccess) { cudaFree(doff); h->err = "cudaMalloc failed"; return GSPH_ENOMEM; }
+  cudaMemcpy(doff, offsets, (N + 1)*sizeof(int64_t), cudaMemcpyHostToDevice);
+  int rc = reset_status(h);
+  if (!rc) rc = gsph_run_neiblist(h, nullptr, doff, didx);
+  if (!rc) rc = gsph_check_status(h, "gsph_neighbour_lists");
+  if (!rc && h->status_host->err_cand_overflow) { h->err = "gsph_neighbour_lists: candidate scratch overflow (set GSPH_CAND_CAP)"; rc = GSPH_ENOMEM; }
+  if (!rc && cudaMemcpy(idx, didx, total*sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess) { h->err = "cudaMemcpy failed"; rc = GSPH_ECUDA; }
+  cudaFree(doff); cudaFree(didx);
+  if (!rc) {
+#pragma omp parallel for schedule(dynamic, 1024)
+    for (int64_t i = 0; i < N; i++) std::sort(idx + offsets[i], idx + offsets[i + 1]);
+  }
+  return rc;
+}
+
+/* depth-first id (KDTree::CreateTreeStructure, KDTree.cpp:362-433) of heap node (level, k) */
+static inline int dfs_id(int ltot, int level, int k)
+{
+  int id = 0;
+  for (int j = 0; j < level; j++) {
+    const int bit = (k >> (level - 1 - j)) & 1;
+    id += bit ? (1 << (ltot - j)) : 1;
+  }
+  return id;
+}
+
+int gsph_tree_info_get(gsph_handle* h, gsph_tree_info* info)
+{
+  if (!h || !info) return GSPH_EINVAL;
+  if (!h->have_tree) { h->err = "gsph_tree_info_get before gsph_build_tree"; return GSPH_ESTATE; }
+  info->ltot = h->tree.ltot; info->Ncell = h->tree.ncell; info->gtot = 1 << h->tree.ltot;
+  info->Nleafmax = h->cfg.Nleafmax; info->Ntot = h->N;
+  return GSPH_OK;
+}
+
+int gsph_tree_leaf_of(gsph_handle* h, int32_t* leaf_of)
+{
+  if (!h || !leaf_of) return GSPH_EINVAL;
+  if (!h->have_tree) { h->err = "gsph_tree_leaf_of before gsph_build_tree"; return GSPH_ESTATE; }
+  cudaSetDevice(h->device);
+  const TreeDev& T = h->tree;
+  const int nleaf = 1 << T.ltot;
+  std::vector<int> first(nleaf), count(nleaf), perm(h->N);
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  CUDA_TRY(h, cudaMemcpy(first.data(), T.first + (nleaf - 1), nleaf*sizeof(int), cudaMemcpyDeviceToHost));
+  CUDA_TRY(h, cudaMemcpy(count.data(), T.count + (nleaf - 1), nleaf*sizeof(int), cudaMemcpyDeviceToHost));
+  CUDA_TRY(h, cudaMemcpy(perm.data(), h->perm, h->N*sizeof(int), cudaMemcpyDeviceToHost));
+  for (int g = 0; g < nleaf; g++) {
+    const int id = dfs_id(T.ltot, T.ltot, g);
+    for (int p = first[g]; p < first[g] + count[g]; p++) leaf_of[perm[p]] = id;
+  }
+  return GSPH_OK;
+}
+
+int gsph_tree_cells(gsph_handle* h, double* box, double* com, double* scalars, double* q, int32_t* Nout)
+{
+  if (!h) return GSPH_EINVAL;
+  if (!h->have_tree) { h->err = "gsph_tree_cells before gsph_build_tree"; return GSPH_ESTATE; }
+  cudaSetDevice(h->device);
+  const TreeDev& T = h->tree;
+  const int nd = h->cfg.ndim, nc = T.ncell;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  std::vector<double> tmp(nc);
+  std::vector<int> dfs(nc), cnt(nc);
+  for (int l = 0; l <= T.ltot; l++)
+    for (int k = 0; k < (1 << l); k++) dfs[(1 << l) - 1 + k] = dfs_id(T.ltot, l, k);
+  auto pull = [&](const double* dev) { return cudaMemcpy(tmp.data(), dev, nc*sizeof(double), cudaMemcpyDeviceToHost); };
+  if (box) {
+    const double* src[4][3] = {{T.bbmin[0], T.bbmin[1], T.bbmin[2]}, {T.bbmax[0], T.bbmax[1], T.bbmax[2]},
+                               {T.hbmin[0], T.hbmin[1], T.hbmin[2]}, {T.hbmax[0], T.hbmax[1], T.hbmax[2]}};
+    for (int b = 0; b < 4; b++) for (int k = 0; k < nd; k++) {
+      CUDA_TRY(h, pull(src[b][k]));
+      for (int n = 0; n < nc; n++) box[((size_t) dfs[n]*4 + b)*nd + k] = tmp[n];
+    }
+  }
+  if (com) {
+    const double* src[2][3] = {{T.rcell[0], T.rcell[1], T.rcell[2]}, {T.com[0], T.com[1], T.com[2]}};
+    for (int b = 0; b < 2; b++) for (int k = 0; k < nd; k++) {
+      CUDA_TRY(h, pull(src[b][k]));
+      for (int n = 0; n < nc; n++) com[((size_t) dfs[n]*2 + b)*nd + k] = tmp[n];
+    }
+  }
+  if (scalars) {
+    const double* src[4] = {T.m, T.rmax, T.hmax, T.cdistsqd};
+    for (int b = 0; b < 4; b++) {
+      CUDA_TRY(h, pull(src[b]));
+      for (int n = 0; n < nc; n++) scalars[(size_t) dfs[n]*5 + b] = tmp[n];
+    }
+    for (int n = 0; n < nc; n++) scalars[(size_t) n*5 + 4] = 0.0;      /* eigen-MAC value: not on this path */
+  }
+  if (q) for (int b = 0; b < 5; b++) {
+    CUDA_TRY(h, pull(T.q[b]));
+    for (int n = 0; n < nc; n++) q[(size_t) dfs[n]*5 + b] = tmp[n];
+  }
+  if (Nout) {
+    CUDA_TRY(h, cudaMemcpy(cnt.data(), T.count, nc*sizeof(int), cudaMemcpyDeviceToHost));
+    for (int n = 0; n < nc; n++) Nout[dfs[n]] = cnt[n];
+  }
+  return GSPH_OK;
+}
+
+int gsph_get_stats(gsph_handle* h, gsph_stats* st)
+{
+  if (!h || !st) return GSPH_EINVAL;
+  *st = h->stats;
+  return GSPH_OK;
+}
+
+int gsph_kernel_table(int ndim, int kernel, int which, double* out)
+{
+  if (ndim < 1 || ndim > 3 || (kernel != GSPH_KERNEL_M4 && kernel != GSPH_KERNEL_QUINTIC) || which < 0 || which > 5 || !out)
+    return GSPH_EINVAL;
+  std::vector<double> tab(6*GSPH_TABLE_RES);
+  gsph_make_tables(ndim, kernel, tab.data());
+  memcpy(out, tab.data() + (size_t) which*GSPH_TABLE_RES, GSPH_TABLE_RES*sizeof(double));
+  return GSPH_OK;
+}
+
+int gsph_measure_fp_peak(int device, double* fp64_tflops, double* fp32_tflops)
+{
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return GSPH_ENODEVICE;
+  if (device < 0 || device >= ndev) return GSPH_EINVAL;
+  cudaSetDevice(device);
+  cudaDeviceProp prop; cudaGetDeviceProperties(&prop, device);
+  const int blocks = prop.multiProcessorCount*8, threads = 256, iters = 1 << 15;
+  void* out = nullptr;
+  if (cudaMalloc(&out, (size_t) blocks*threads*sizeof(double)) != cudaSuccess) return GSPH_ENOMEM;
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float ms = 0;
+  const double flops = 2.0*8.0*(double) iters*(double) blocks*threads;
+  fma_peak_kernel<double><<<blocks, threads>>>((double*) out, 1024);
+  cudaEventRecord(e0); fma_peak_kernel<double><<<blocks, threads>>>((double*) out, iters); cudaEventRecord(e1);
+  cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
+  if (fp64_tflops) *fp64_tflops = flops/(ms*1e-3)/1e12;
+  fma_peak_kernel<float><<<blocks, threads>>>((float*) out, 1024);
+  cudaEventRecord(e0); fma_peak_kernel<float><<<blocks, threads>>>((float*) out, iters); cudaEventRecord(e1);
+  cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
+  if (fp32_tflops) *fp32_tflops = flops/(ms*1e-3)/1e12;
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  return cudaGetLastError() == cudaSuccess ? GSPH_OK : GSPH_ECUDA;
+}
+
+}  /* extern "C" */

@@ -1,0 +1,294 @@
+/*=================================================================================================
+ *  device_common.cuh -- device helpers shared by the density / force / gravity kernels:
+ *  smoothing-kernel evaluation, exact (non-contracted) distance arithmetic, periodic helpers and
+ *  the warp-cooperative KD-tree walk.
+ *=================================================================================================*/
+#pragma once
+#include "gsph_internal.cuh"
+
+#define FULLMASK 0xffffffffu
+#define WALK_STACK_CAP 1024          /* ints per warp */
+
+struct PartView {
+  double* f[NF_DOUBLE];
+  int32_t* i[NF_INT];
+};
+
+/*------------------------------------------------------------------------------------------------
+ * Exact arithmetic for anything that feeds a comparison or a truncation in the reference:
+ * DotProduct is evaluated left to right without FMA (src/Headers/InlineFuncs.h:46-54); nvcc would
+ * contract a*b+c, so these use the explicit round-to-nearest intrinsics.
+ *-----------------------------------------------------------------------------------------------*/
+template <int NDIM>
+__device__ __forceinline__ double dot_exact(const double (&a)[3])
+{
+  double s = __dmul_rn(a[0], a[0]);
+  if (NDIM > 1) s = __dadd_rn(s, __dmul_rn(a[1], a[1]));
+  if (NDIM > 2) s = __dadd_rn(s, __dmul_rn(a[2], a[2]));
+  return s;
+}
+
+/* NearestPeriodicVector / ApplyPeriodicDistanceCorrection, src/Headers/GhostNeighbours.hpp:119-166 */
+template <int NDIM>
+__device__ __forceinline__ void wrap_dr(const DevParams& dp, double (&dr)[3])
+{
+#pragma unroll
+  for (int k = 0; k < NDIM; k++) {
+    if (dp.periodic[k]) {
+      if (dr[k] > dp.boxhalf[k]) dr[k] -= dp.boxsize[k];
+      else if (dr[k] < -dp.boxhalf[k]) dr[k] += dp.boxsize[k];
+    }
+  }
+}
+
+/*------------------------------------------------------------------------------------------------
+ * Smoothing kernels.  Analytic forms: M4 src/Headers/SmoothingKernel.h:131-240, quintic :281-408;
+ * norms src/Hydrodynamics/{M4,Quintic}Kernel.cpp:39-53.  Tabulated forms: 1000-bin truncating
+ * look-up without interpolation, SmoothingKernel.h:585-661.
+ * `which`: 0 w0, 1 w1, 2 womega, 3 wzeta, 4 wgrav, 5 wpot.
+ *-----------------------------------------------------------------------------------------------*/
+template <int KERN, int NDIM>
+__host__ __device__ __forceinline__ double kern_analytic(int which, double s, double kn)
+{
+  const double nd = (double) NDIM;
+  const double s2 = s*s, s3 = s2*s, s4 = s2*s2, s5 = s4*s;
+  if (KERN == GSPH_KERNEL_M4) {
+    switch (which) {
+    case 0:
+      if (s < 1.0) return kn*(1.0 - 1.5*s2 + 0.75*s3);
+      else if (s < 2.0) { const double t = 2.0 - s; return 0.25*kn*(t*t*t); }
+      return 0.0;
+    case 1:
+      if (s < 1.0) return kn*(-3.0*s + 2.25*s2);
+      else if (s < 2.0) return -0.75*kn*(2.0 - s)*(2.0 - s);
+      return 0.0;
+    case 2:
+      if (s < 1.0) return kn*(-nd + 1.5*(nd + 2.0)*s2 - 0.75*(nd + 3.0)*s3);
+      else if (s < 2.0)
+        return kn*(-2.0*nd + 3.0*(nd + 1.0)*s - 1.50*(nd + 2.0)*s2 + 0.25*(nd + 3.0)*s3);
+      return 0.0;
+    case 3:
+      if (s < 1.0) return 1.4 - 2.0*s2 + 1.5*s4 - 0.6*s5;
+      else if (s < 2.0) return 1.6 - 4.0*s2 + 4.0*s3 - 1.5*s4 + 0.2*s5;
+      return 0.0;
+    case 4:
+      if (s < 1.0) return 1.333333333333333333333*s - 1.2*s3 + 0.5*s4;
+      else if (s < 2.0)
+        return 2.6666666666666666667*s - 3.0*s2 + 1.2*s3 - 0.166666666666666666667*s4 -
+          0.06666666666666666667/s2;
+      return 1.0/s2;
+    default:
+      if (s < 1.0) return 1.4 - 0.666666666666666666666666*s2 + 0.3*s4 - 0.1*s5;
+      else if (s < 2.0)
+        return -1.0/(15.0*s) + 1.6 - 1.33333333333333333333333333*s2 + s3 - 0.3*s4 +
+          (1.0/30.0)*s5;
+      return 1.0/s;
+    }
+  }
+  else {
+    const double s6 = s3*s3, s7 = s6*s;
+    switch (which) {
+    case 0:
+      if (s < 1.0) return kn*(66.0 - 60.0*s2 + 30.0*s4 - 10.0*s5);
+      else if (s < 2.0) return kn*(51.0 + 75.0*s - 210.0*s2 + 150.0*s3 - 45.0*s4 + 5.0*s5);
+      else if (s < 3.0) return kn*(243.0 - 405*s + 270.0*s2 - 90.0*s3 + 15.0*s4 - s5);
+      return 0.0;
+    case 1:
+      if (s < 1.0) return kn*(-120.0*s + 120.0*s3 - 50.0*s4);
+      else if (s < 2.0) return kn*(75.0 - 420.0*s + 450.0*s2 - 180.0*s3 + 25.0*s4);
+      else if (s < 3.0) return kn*(-405.0 + 540.0*s - 270.0*s2 + 60.0*s3 - 5.0*s4);
+      return 0.0;
+    case 2:
+      if (s < 1.0)
+        return kn*(-66.0*nd + 60.0*(nd + 2.0)*s2 - 30.0*(nd + 4.0)*s4 + 10.0*(nd + 5.0)*s5);
+      else if (s < 2.0)
+        return kn*(-51.0*nd - 75.0*(nd + 1.0)*s + 210.0*(nd + 2.0)*s2 - 150.0*(nd + 3.0)*s3 +
+                   45.0*(nd + 4.0)*s4 - 5.0*(nd + 5.0)*s5);
+      else if (s < 3.0)
+        return kn*(-243.0*nd + 405.0*(nd + 1.0)*s - 270.0*(nd + 2.0)*s2 + 90.0*(nd + 3.0)*s3 -
+                   15.0*(nd + 4.0)*s4 + (nd + 5.0)*s5);
+      return 0.0;
+    case 3:
+      if (s < 1.0) return 33.0*s2 - 15.0*s4 + 5.0*s6 - 1.42857142857*s7 - 34.14285714;
+      else if (s < 2.0)
+        return 25.5*s2 + 25.0*s3 - 52.5*s4 + 30.0*s5 - 7.5*s6 + 0.7142857143*s7 - 33.785714286;
+      else if (s < 3.0)
+        return 121.5*s2 - 135.0*s3 + 67.5*s4 - 18.0*s5 + 2.5*s6 - 0.142857143*s7 - 52.07142857;
+      return 0.0;
+    case 4:
+      if (s < 1.0)
+        return (12.0/359.0)*(22.0*s - 12.0*s3 + (30.0/7.0)*s5 - (5.0/4.0)*s6);
+      else if (s < 2.0)
+        return (12.0/359.0)*(17.0*s + (75.0/4.0)*s2 - 42.0*s3 + 25.0*s4 - (45.0/7.0)*s5 +
+                             (5.0/8.0)*s6 + (5.0/56.0)/s2);
+      else if (s < 3.0)
+        return (12.0/359.0)*(81.0*s - (405.0/4.0)*s2 + 54.0*s3 - 15.0*s4 + (15.0/7.0)*s5 -
+                             (1.0/8.0)*s6 - (507.0/56.0)/s2);
+      return 1.0/s2;
+    default:
+      if (s < 1.0)
+        return (12.0/359.0)*(-11.0*s2 + 3.0*s4 - (5.0/7.0)*s6 + (5.0/28.0)*s7 + (478.0/14.0));
+      else if (s < 2.0)
+        return (12.0/359.0)*(-(17.0/2.0)*s2 - (25.0/4.0)*s3 + (21.0/2.0)*s4 - 5.0*s5 +
+                             (15.0/14.0)*s6 - (5.0/56.0)*s7 + (473.0/14.0) + (5.0/56.0)/s);
+      else if (s < 3.0)
+        return (12.0/359.0)*(-(81.0/2.0)*s2 + (135.0/4.0)*s3 - (27.0/2.0)*s4 + 3.0*s5 -
+                             (5.0/14.0)*s6 + (1.0/56.0)*s7 + (729.0/14.0) - (507.0/56.0)/s);
+      return 1.0/s;
+    }
+  }
+}
+
+/* Kernel evaluator bound to one (kernel, ndim, tabulated) combination.  `tab` points at the six
+ * tables (shared memory): 0 w0_s2, 1 womega_s2, 2 wzeta_s2, 3 w1, 4 wgrav, 5 wpot.               */
+template <int KERN, int NDIM, bool TAB>
+struct KernelEval {
+  const double* tab;
+  double kn, kr, krs, res_invkr, res_invkrs;
+  __device__ __forceinline__ KernelEval(const DevParams& dp, const double* t) : tab(t)
+  {
+    kn = dp.kernnorm; kr = dp.kernrange; krs = dp.kernrangesqd;
+    res_invkr = (double) GSPH_TABLE_RES/kr; res_invkrs = (double) GSPH_TABLE_RES/krs;
+  }
+  /* s^2-argument family used by ComputeH (which: 0 w0, 1 womega, 2 wzeta) */
+  __device__ __forceinline__ void density_terms(double ssqd, double& w0, double& wom, double& wze) const
+  {
+    if (TAB) {
+      const int idx = (int)(ssqd*res_invkrs);
+      w0 = tab[idx]; wom = tab[GSPH_TABLE_RES + idx]; wze = tab[2*GSPH_TABLE_RES + idx];
+    }
+    else {
+      const double s = sqrt(ssqd);
+      w0 = kern_analytic<KERN, NDIM>(0, s, kn);
+      wom = kern_analytic<KERN, NDIM>(2, s, kn);
+      wze = kern_analytic<KERN, NDIM>(3, s, kn);
+    }
+  }
+  __device__ __forceinline__ double w1(double s) const
+  {
+    if (TAB) { if (s >= kr) return 0.0; return tab[3*GSPH_TABLE_RES + (int)(s*res_invkr)]; }
+    return kern_analytic<KERN, NDIM>(1, s, kn);
+  }
+  __device__ __forceinline__ double wgrav(double s) const
+  {
+    if (TAB) { if (s >= kr) return 1.0/(s*s); return tab[4*GSPH_TABLE_RES + (int)(s*res_invkr)]; }
+    return kern_analytic<KERN, NDIM>(4, s, kn);
+  }
+  __device__ __forceinline__ double wpot(double s) const
+  {
+    if (TAB) { if (s >= kr) return 1.0/s; return tab[5*GSPH_TABLE_RES + (int)(s*res_invkr)]; }
+    return kern_analytic<KERN, NDIM>(5, s, kn);
+  }
+};
+
+/*------------------------------------------------------------------------------------------------
+ * warp helpers
+ *-----------------------------------------------------------------------------------------------*/
+__device__ __forceinline__ int warp_excl_scan(int v, int lane, int& total)
+{
+  int x = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(FULLMASK, x, o);
+    if (lane >= o) x += y;
+  }
+  total = __shfl_sync(FULLMASK, x, 31);
+  return x - v;
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+  return v;
+}
+
+/*------------------------------------------------------------------------------------------------
+ * Conservative periodic-aware interval-overlap test used by the neighbour walks.  The candidate
+ * set only has to be a SUPERSET of the true neighbours (membership is decided afterwards by the
+ * exact predicate), so a small relative slack is added.
+ *-----------------------------------------------------------------------------------------------*/
+template <int NDIM>
+__device__ __forceinline__ bool boxes_overlap(const DevParams& dp, const double (&amin)[3],
+                                              const double (&amax)[3], const double (&bmin)[3],
+                                              const double (&bmax)[3])
+{
+#pragma unroll
+  for (int k = 0; k < NDIM; k++) {
+    const double ca = 0.5*(amin[k] + amax[k]), cb = 0.5*(bmin[k] + bmax[k]);
+    const double hw = 0.5*(amax[k] - amin[k]) + 0.5*(bmax[k] - bmin[k]);
+    double d = fabs(ca - cb);
+    if (dp.periodic[k]) d = fmin(d, dp.boxsize[k] - d);
+    if (d > hw*(1.0 + 1.0e-12) + 1.0e-300) return false;
+  }
+  return true;
+}
+
+/*------------------------------------------------------------------------------------------------
+ * Warp-cooperative KD-tree walk.  The tree is a perfect binary tree in heap order (children of n
+ * are 2n+1, 2n+2; leaves are the nodes >= leaf0).  Up to 32 nodes are popped from a per-warp
+ * shared-memory stack and tested by one lane each; opened internal nodes push their children.
+ * Visitor interface:
+ *     int  test(int node, bool leaf)        per lane : 0 skip, 1 open, >=2 visitor-defined
+ *     bool emit(int node, int code, bool leaf, int lane)   warp collective; false = overflow
+ * This replaces the serial copen/cnext pointer chase of Tree::ComputeGatherNeighbourList,
+ * ComputeNeighbourAndGhostList and ComputeGravityInteractionAndGhostList
+ * (src/Tree/Tree.cpp:291-381, :562-617, :628-735).
+ *-----------------------------------------------------------------------------------------------*/
+template <class Visitor>
+__device__ __forceinline__ bool warp_walk(const TreeDev& T, int* stack, Visitor& V, DevStatus* st)
+{
+  const int lane = threadIdx.x & 31;
+  const int leaf0 = (1 << T.ltot) - 1;
+  int sp = 1;
+  if (lane == 0) stack[0] = 0;
+  __syncwarp();
+  while (sp > 0) {
+    const int take = sp < 32 ? sp : 32;
+    int node = -1;
+    if (lane < take) node = stack[sp - 1 - lane];
+    sp -= take;
+    __syncwarp();
+    const bool leaf = node >= leaf0;
+    int code = 0;
+    if (node >= 0 && T.count[node] > 0) code = V.test(node, leaf);
+    const bool push = (code == 1) && !leaf;
+    const unsigned pm = __ballot_sync(FULLMASK, push);
+    const int npush = __popc(pm);
+    if (sp + 2*npush > WALK_STACK_CAP) {
+      if (lane == 0) atomicExch(&st->err_stack_overflow, 1);
+      return false;
+    }
+    if (push) {
+      const int off = __popc(pm & ((1u << lane) - 1u));
+      stack[sp + 2*off]     = 2*node + 2;
+      stack[sp + 2*off + 1] = 2*node + 1;
+    }
+    sp += 2*npush;
+    if (!V.emit(node, code, leaf, lane)) return false;
+    __syncwarp();
+  }
+  return true;
+}
+
+/* Visitor pieces shared by the neighbour walks: append the particles of accepted leaves to a
+ * per-warp candidate list in global scratch.                                                     */
+struct CandList {
+  int32_t* list; int cap; int n;
+  DevStatus* st;
+  __device__ __forceinline__ bool append_leaf(const TreeDev& T, int node, bool take, int lane)
+  {
+    int cnt = 0, first = 0;
+    if (take) { cnt = T.count[node]; first = T.first[node]; }
+    int total;
+    const int off = warp_excl_scan(cnt, lane, total);
+    if (total == 0) return true;
+    if (n + total > cap) {
+      if (lane == 0) { atomicExch(&st->err_cand_overflow, 1); atomicMax(&st->cand_need, (unsigned long long)(n + total)); }
+      return false;
+    }
+    for (int i = 0; i < cnt; i++) list[n + off + i] = first + i;
+    n += total;
+    return true;
+  }
+};

@@ -1,0 +1,149 @@
+/*=================================================================================================
+ *  gsph_internal.cuh -- shared declarations of libgsph (B200 / sm_100a grad-h SPH neighbour path).
+ *
+ *  Data layout in HBM
+ *  ------------------
+ *  Particles live twice on the device:
+ *    - `host order`  staging arrays (H*): exactly the order of the host array handed to gsph_upload;
+ *    - `tree order`  SoA arrays     (P*): particles permuted so that every KD-tree cell of every
+ *      level is ONE contiguous slab [first, first+count).  All kernels work on tree order; `perm`
+ *      maps tree position -> host index.
+ *  The KD-tree is the reference's balanced tree (KDTree.cpp:220-595): a perfect binary tree of depth
+ *  ltot whose node sizes follow N -> (N/2, N - N/2).  Nodes are stored in HEAP order
+ *  (node = 2^level - 1 + k); the reference's depth-first ids are only produced for the inspection
+ *  API (gsph_tree_cells).
+ *=================================================================================================*/
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include "../../include/gsph.h"
+
+#define GSPH_TABLE_RES 1000
+#define GSPH_SMALL 1.0e-20           /* small_number, src/Headers/Constants.h:73 */
+#define GSPH_BIG   9.9e20            /* big_number,   src/Headers/Constants.h:72 */
+#define GSPH_INVPI 0.31830988618379  /* invpi as spelled in src/Headers/Constants.h:63 */
+
+/* particle fields, double precision, tree order and host order */
+enum PField {
+  F_RX, F_RY, F_RZ, F_VX, F_VY, F_VZ, F_AX, F_AY, F_AZ, F_ATX, F_ATY, F_ATZ,
+  F_M, F_H, F_U, F_RHO, F_HR2, F_HFAC, F_INVOMEGA, F_ZETA, F_SOUND, F_PRESS,
+  F_DUDT, F_DIVV, F_ALPHA, F_DALPHADT, F_GPOT, F_GPOTHYDRO,
+  NF_DOUBLE
+};
+enum IField { I_FLAGS, I_PTYPE, I_LEVEL, I_LEVELNEIB, I_IORIG, I_SINKID, NF_INT };
+
+/* per-node fields of the tree (heap order) */
+struct TreeDev {
+  int ltot = 0;            /* leaf level */
+  int ncell = 0;           /* 2^(ltot+1) - 1 */
+  int ncell_cap = 0;
+  int* first = nullptr;    /* first tree-order particle of the node */
+  int* count = nullptr;    /* number of particles */
+  int* nactive = nullptr;  /* active particles below the node */
+  double* bbmin[3] = {0, 0, 0};   /* tight particle box                  (TreeCell::bb)    */
+  double* bbmax[3] = {0, 0, 0};
+  double* hbmin[3] = {0, 0, 0};   /* box of r -+ kernrange*h             (TreeCell::hbox)  */
+  double* hbmax[3] = {0, 0, 0};
+  double* rcell[3] = {0, 0, 0};   /* geometric centre of bb              (TreeCell::rcell) */
+  double* com[3] = {0, 0, 0};     /* centre of mass                      (TreeCell::r)     */
+  double* vcom[3] = {0, 0, 0};    /* mass-weighted velocity              (TreeCell::v)     */
+  double* m = nullptr;
+  double* rmax = nullptr;         /* half diagonal of bb                                   */
+  double* hmax = nullptr;
+  double* cdistsqd = nullptr;     /* geometric MAC distance^2, KDTree.cpp:917              */
+  double* q[5] = {0, 0, 0, 0, 0}; /* traceless quadrupole, KDTree.cpp:937-1000             */
+};
+
+struct DevParams {
+  int ndim, kernel, tabulated;
+  double kernrange, kernrangesqd, kernnorm;
+  double h_fac, h_converge;
+  int avisc, acond, tdavisc;
+  double alpha_visc, beta_visc, alpha_visc_min;
+  int eos;
+  double gamma_eos, gammam1, temp0, mu_bar, rho_bary;
+  double boxmin[3], boxmax[3], boxsize[3], boxhalf[3];
+  int periodic[3];
+  int any_periodic;
+  int hydro_forces, self_gravity, multipole, gravity_mac;
+  double thetamaxsqd, invthetamaxsqd, macerror;
+  int Nleafmax;
+  int create_sinks;
+};
+
+/* device-side error / statistics block */
+struct DevStatus {
+  int err_cand_overflow;     /* candidate scratch too small                                    */
+  int err_stack_overflow;    /* walk stack too small                                           */
+  int err_converge;          /* h-rho iteration did not converge (GradhSph.cpp:249-250)        */
+  int err_hsearch;           /* search radius had to grow too often                            */
+  int density_retries;
+  int hiter_max;
+  int ngb_max;
+  int pad;
+  unsigned long long hiter_sum, ngb_sum, cand_sum, ntarget, ndirect_sum, ncell_sum, nleaf_grav;
+  unsigned long long cand_need;   /* largest candidate count requested */
+};
+
+struct gsph_handle {
+  gsph_config cfg;
+  DevParams dp;
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+
+  int64_t N = 0;             /* particles currently uploaded */
+  int64_t Ncap = 0;          /* capacity of particle arrays  */
+  double* H[NF_DOUBLE] = {0};   /* host-order staging */
+  int32_t* HI[NF_INT] = {0};
+  double* P[NF_DOUBLE] = {0};   /* tree order */
+  int32_t* PI[NF_INT] = {0};
+  int32_t* perm = nullptr;      /* tree position -> host index */
+  bool uploaded = false, have_tree = false, sorted_valid = false, all_active = true;
+  bool density_done = false;
+
+  TreeDev tree;
+  double* tables = nullptr;     /* 6 x 1000 doubles: w0_s2, womega_s2, wzeta_s2, w1, wgrav, wpot */
+
+  /* scratch */
+  void* scratch = nullptr; size_t scratch_bytes = 0;          /* tree build temporaries          */
+  int32_t* cand = nullptr; size_t cand_cap_per_warp = 0; int cand_warps = 0;
+  int32_t* gravlist = nullptr; size_t grav_cap_cells = 0, grav_cap_direct = 0; int grav_warps = 0;
+  DevStatus* status = nullptr;  /* device */
+  DevStatus* status_host = nullptr; /* pinned */
+  int* work_counter = nullptr;
+  uint8_t* done = nullptr; size_t done_cap = 0;   /* per cohort / leaf: finished in this pass */
+  void* pinned = nullptr; size_t pinned_bytes = 0;             /* host staging for strided views  */
+
+  gsph_stats stats;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+#define CUDA_TRY(h, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { \
+  (h)->err = std::string(#call) + ": " + cudaGetErrorString(e__); return GSPH_ECUDA; } } while (0)
+
+/* ---- module entry points (host side) -----------------------------------------------------------*/
+void gsph_make_tables(int ndim, int kernel, double* out6x1000);       /* tables.cu  */
+double gsph_kernnorm(int ndim, int kernel);
+int gsph_tree_build(gsph_handle* h, int mode, double dt);             /* tree.cu    */
+int gsph_tree_update_hmax(gsph_handle* h);
+int gsph_tree_update_active(gsph_handle* h);
+int gsph_run_density(gsph_handle* h);                                 /* density.cu */
+int gsph_run_hydro(gsph_handle* h, int with_gravity);                 /* hydro.cu   */
+int gsph_run_neiblist(gsph_handle* h, int32_t* counts_dev, const int64_t* offsets_dev, int32_t* idx_dev);
+int gsph_run_gravity(gsph_handle* h);                                 /* gravity.cu */
+int gsph_check_status(gsph_handle* h, const char* where);             /* capi.cu    */
+int gsph_ensure_cand(gsph_handle* h, int warps, size_t cap_per_warp);
+
+static inline int cohort_level_for(int64_t N, int ltot, int maxsize)
+{
+  /* shallowest level whose largest node has <= maxsize particles (node sizes are
+     ceil/floor of N / 2^level in the balanced tree) */
+  int l = 0;
+  while (l < ltot && ((N + ((int64_t)1 << l) - 1) >> l) > maxsize) l++;
+  return l;
+}

@@ -1,0 +1,553 @@
+/*=================================================================================================
+ *  tree.cu -- GPU build and stocking of the reference's balanced KD-tree.
+ *
+ *  Replaces  KDTree::BuildTree / DivideTreeCell / QuickSelect   src/Tree/KDTree.cpp:220-313,442-595,682-750
+ *            KDTree::StockTree / StockCellProperties            src/Tree/KDTree.cpp:760-798,808-1083
+ *            KDTree::UpdateHmaxValues                           src/Tree/KDTree.cpp:1128-1208
+ *            KDTree::UpdateActiveParticleCounters               src/Tree/KDTree.cpp:1217-1254
+ *            Tree::ExtrapolateCellProperties                    src/Tree/Tree.cpp:172-198
+ *
+ *  The reference recursion (median QuickSelect along the longest axis of the INHERITED box, cell
+ *  sizes N -> N/2, N-N/2) is turned into a level-synchronous build from three pre-sorted index
+ *  lists: at every level the median of a node along its split axis is simply the element at
+ *  first + count/2 of that axis' list, and the other lists are brought into the children's order
+ *  by a stable segmented partition (one exclusive scan + one scatter per list and level).
+ *  For particle sets without coordinate ties this yields exactly the reference's leaf membership
+ *  and therefore bit-identical bb/rcell/rmax/hmax/cdistsqd (the quantities the MAC reads); ties
+ *  are broken by host index instead of QuickSelect's visiting order (documented in DESIGN.md).
+ *=================================================================================================*/
+#include "device_common.cuh"
+#include <cub/cub.cuh>
+
+namespace {
+
+struct Bump {
+  char* base; size_t off, cap;
+  template <class T> T* get(size_t n)
+  {
+    off = (off + 255) & ~(size_t)255;
+    T* p = (T*)(base + off);
+    off += n*sizeof(T);
+    return p;
+  }
+};
+
+/* ---- root box: extent of r -+ kernrange*h, KDTree.cpp:272-279 ---------------------------------*/
+template <int NDIM>
+__global__ void root_box_kernel(int N, PartView Hh, double kr, double* part /*[blocks][2*NDIM]*/)
+{
+  double mn[3] = {GSPH_BIG, GSPH_BIG, GSPH_BIG}, mx[3] = {-GSPH_BIG, -GSPH_BIG, -GSPH_BIG};
+  for (int i = blockIdx.x*blockDim.x + threadIdx.x; i < N; i += gridDim.x*blockDim.x) {
+    const double hr = __dmul_rn(kr, Hh.f[F_H][i]);
+#pragma unroll
+    for (int k = 0; k < NDIM; k++) {
+      const double x = Hh.f[F_RX + k][i];
+      mx[k] = fmax(mx[k], __dadd_rn(x, hr));
+      mn[k] = fmin(mn[k], __dadd_rn(x, -hr));
+    }
+  }
+  __shared__ double sm[256];
+  for (int k = 0; k < 2*NDIM; k++) {
+    double v = k < NDIM ? mn[k] : mx[k - NDIM];
+    sm[threadIdx.x] = v;
+    __syncthreads();
+    for (int s = blockDim.x/2; s > 0; s >>= 1) {
+      if (threadIdx.x < s)
+        sm[threadIdx.x] = k < NDIM ? fmin(sm[threadIdx.x], sm[threadIdx.x + s])
+                                   : fmax(sm[threadIdx.x], sm[threadIdx.x + s]);
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) part[blockIdx.x*2*NDIM + k] = sm[0];
+    __syncthreads();
+  }
+}
+
+template <int NDIM>
+__global__ void root_box_final(int nblocks, const double* part, double* ibmin0, double* ibmin1,
+                               double* ibmin2, double* ibmax0, double* ibmax1, double* ibmax2)
+{
+  double* mnp[3] = {ibmin0, ibmin1, ibmin2};
+  double* mxp[3] = {ibmax0, ibmax1, ibmax2};
+  if (threadIdx.x < 2*NDIM) {
+    const int k = threadIdx.x;
+    double v = part[k];
+    for (int b = 1; b < nblocks; b++)
+      v = k < NDIM ? fmin(v, part[b*2*NDIM + k]) : fmax(v, part[b*2*NDIM + k]);
+    if (k < NDIM) mnp[k][0] = v; else mxp[k - NDIM][0] = v;
+  }
+}
+
+__global__ void iota_kernel(int N, int* a)
+{
+  const int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i < N) a[i] = i;
+}
+
+struct LevelPtrs {
+  const int* list[3];
+  int* newlist[3];
+  const double* r[3];     /* host-order coordinates */
+  double* ibmin[3]; double* ibmax[3];       /* inherited boxes of this level, index k          */
+  double* cibmin[3]; double* cibmax[3];     /* inherited boxes of the next level               */
+  int* first; int* count;                   /* heap-order node arrays                          */
+  int8_t* splitdim;                         /* per node of this level                          */
+  uint8_t* side;                            /* per particle (host index)                       */
+  int* nodeidx;                             /* per position: node index inside the level       */
+  const int* scan[3];
+};
+
+/* DivideTreeCell for every node of one level, KDTree.cpp:492-560 */
+template <int NDIM>
+__global__ void split_nodes_kernel(int level, LevelPtrs L)
+{
+  const int k = blockIdx.x*blockDim.x + threadIdx.x;
+  if (k >= (1 << level)) return;
+  const int n = (1 << level) - 1 + k;
+  const int cnt = L.count[n], fst = L.first[n];
+  int kd = 0; double rkmax = 0.0;
+#pragma unroll
+  for (int d = 0; d < NDIM; d++) {
+    const double w = __dadd_rn(L.ibmax[d][k], -L.ibmin[d][k]);
+    if (w > rkmax) { rkmax = w; kd = d; }
+  }
+  const int left = cnt/2;
+  double rdiv = 0.0;
+  if (cnt > 0) rdiv = L.r[kd][L.list[kd][fst + left]];
+  const int c1 = 2*n + 1, c2 = 2*n + 2;
+  L.first[c1] = fst;        L.count[c1] = left;
+  L.first[c2] = fst + left; L.count[c2] = cnt - left;
+#pragma unroll
+  for (int d = 0; d < NDIM; d++) {
+    const double mn = L.ibmin[d][k], mx = L.ibmax[d][k];
+    L.cibmin[d][2*k] = mn;                       L.cibmax[d][2*k] = (d == kd) ? rdiv : mx;
+    L.cibmin[d][2*k + 1] = (d == kd) ? rdiv : mn; L.cibmax[d][2*k + 1] = mx;
+  }
+  L.splitdim[k] = (int8_t) kd;
+}
+
+__global__ void mark_side_kernel(int N, int level, LevelPtrs L)
+{
+  const int p = blockIdx.x*blockDim.x + threadIdx.x;
+  if (p >= N) return;
+  const int k = L.nodeidx[p];
+  const int n = (1 << level) - 1 + k;
+  const int kd = L.splitdim[k];
+  const int pm = L.first[n] + L.count[n]/2;
+  L.side[L.list[kd][p]] = (uint8_t)(p >= pm);
+}
+
+struct SideOfList {
+  const int* list; const uint8_t* side;
+  __host__ __device__ __forceinline__ int operator()(const int& p) const { return (int) side[list[p]]; }
+};
+
+__global__ void partition_kernel(int N, int level, int d, LevelPtrs L)
+{
+  const int p = blockIdx.x*blockDim.x + threadIdx.x;
+  if (p >= N) return;
+  const int k = L.nodeidx[p];
+  const int n = (1 << level) - 1 + k;
+  const int fst = L.first[n], nl = L.count[n]/2;
+  const int id = L.list[d][p];
+  const int f = L.side[id];
+  const int rb = L.scan[d][p] - L.scan[d][fst];       /* right-going elements before p in the node */
+  const int dest = f ? fst + nl + rb : p - rb;
+  L.newlist[d][dest] = id;
+}
+
+__global__ void update_nodeidx_kernel(int N, int level, LevelPtrs L)
+{
+  const int p = blockIdx.x*blockDim.x + threadIdx.x;
+  if (p >= N) return;
+  const int k = L.nodeidx[p];
+  const int n = (1 << level) - 1 + k;
+  L.nodeidx[p] = 2*k + (p >= L.first[n] + L.count[n]/2 ? 1 : 0);
+}
+
+/* ---- permute all particle fields from host order into tree order -------------------------------*/
+__global__ void gather_kernel(int N, const int32_t* perm, PartView Hh, PartView Pp)
+{
+  const int p = blockIdx.x*blockDim.x + threadIdx.x;
+  if (p >= N) return;
+  const int i = perm[p];
+#pragma unroll 4
+  for (int f = 0; f < NF_DOUBLE; f++) Pp.f[f][p] = Hh.f[f][i];
+#pragma unroll
+  for (int f = 0; f < NF_INT; f++) Pp.i[f][p] = Hh.i[f][i];
+}
+
+/* ---- StockCellProperties for the leaves, KDTree.cpp:841-1010 -----------------------------------*/
+template <int NDIM>
+__global__ void stock_leaves_kernel(TreeDev T, PartView P, DevParams dp, int full)
+{
+  const int g = blockIdx.x*blockDim.x + threadIdx.x;
+  const int nleaf = 1 << T.ltot;
+  if (g >= nleaf) return;
+  const int n = nleaf - 1 + g;
+  const int fst = T.first[n], cnt = T.count[n];
+  const double kr = dp.kernrange;
+  double hmax = 0.0, hbmin[3], hbmax[3];
+  double m = 0.0, com[3] = {0, 0, 0}, vc[3] = {0, 0, 0}, bmin[3], bmax[3];
+  int nact = 0;
+#pragma unroll
+  for (int k = 0; k < 3; k++) { bmin[k] = hbmin[k] = GSPH_BIG; bmax[k] = hbmax[k] = -GSPH_BIG; }
+  for (int i = fst; i < fst + cnt; i++) {
+    const unsigned fl = (unsigned) P.i[I_FLAGS][i];
+    if (fl & GSPH_FLAG_DEAD) continue;
+    if (fl & GSPH_FLAG_ACTIVE) nact++;
+    const double hi = P.f[F_H][i], mi = P.f[F_M][i];
+    hmax = fmax(hmax, hi);
+    m += mi;
+    const double hr = __dmul_rn(kr, hi);
+#pragma unroll
+    for (int k = 0; k < NDIM; k++) {
+      const double x = P.f[F_RX + k][i];
+      com[k] += mi*x;
+      vc[k] += mi*P.f[F_VX + k][i];
+      bmin[k] = fmin(bmin[k], x); bmax[k] = fmax(bmax[k], x);
+      hbmin[k] = fmin(hbmin[k], __dadd_rn(x, -hr)); hbmax[k] = fmax(hbmax[k], __dadd_rn(x, hr));
+    }
+  }
+  T.nactive[n] = nact;
+  T.hmax[n] = hmax;
+#pragma unroll
+  for (int k = 0; k < NDIM; k++) { T.hbmin[k][n] = hbmin[k]; T.hbmax[k][n] = hbmax[k]; }
+  if (!full) return;
+  if (m > 0.0) {
+#pragma unroll
+    for (int k = 0; k < NDIM; k++) { com[k] = com[k]/m; vc[k] = vc[k]/m; }
+  }
+  double rc[3] = {0, 0, 0}, rmax = 0.0, cdist = GSPH_BIG;
+  if (cnt > 0) {
+    double dr[3] = {0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < NDIM; k++) {
+      rc[k] = __dmul_rn(0.5, __dadd_rn(bmin[k], bmax[k]));
+      dr[k] = __dmul_rn(0.5, __dadd_rn(bmax[k], -bmin[k]));
+    }
+    const double d2 = dot_exact<NDIM>(dr);
+    cdist = __ddiv_rn(fmax(d2, __dmul_rn(hmax, hmax)), dp.thetamaxsqd);
+    rmax = __dsqrt_rn(d2);
+  }
+  T.m[n] = m; T.rmax[n] = rmax; T.cdistsqd[n] = cdist;
+#pragma unroll
+  for (int k = 0; k < NDIM; k++) {
+    T.bbmin[k][n] = bmin[k]; T.bbmax[k][n] = bmax[k];
+    T.rcell[k][n] = rc[k]; T.com[k][n] = com[k]; T.vcom[k][n] = vc[k];
+  }
+  /* quadrupole about the centre of mass, KDTree.cpp:937-1000 */
+  double q[5] = {0, 0, 0, 0, 0};
+  for (int i = fst; i < fst + cnt; i++) {
+    if (((unsigned) P.i[I_FLAGS][i]) & GSPH_FLAG_DEAD) continue;
+    const double mi = P.f[F_M][i];
+    double dr[3] = {0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < NDIM; k++) dr[k] = P.f[F_RX + k][i] - com[k];
+    const double d2 = dr[0]*dr[0] + dr[1]*dr[1] + dr[2]*dr[2];
+    q[0] += mi*(3.0*dr[0]*dr[0] - d2);
+    if (NDIM > 1) { q[1] += mi*3.0*dr[0]*dr[1]; q[2] += mi*(3.0*dr[1]*dr[1] - d2); }
+    if (NDIM > 2) { q[3] += mi*3.0*dr[2]*dr[0]; q[4] += mi*3.0*dr[2]*dr[1]; }
+  }
+#pragma unroll
+  for (int k = 0; k < 5; k++) T.q[k][n] = q[k];
+}
+
+/* ---- StockCellProperties for one internal level, KDTree.cpp:1013-1080 ---------------------------*/
+template <int NDIM>
+__global__ void stock_level_kernel(TreeDev T, DevParams dp, int level, int full)
+{
+  const int k = blockIdx.x*blockDim.x + threadIdx.x;
+  if (k >= (1 << level)) return;
+  const int n = (1 << level) - 1 + k;
+  const int c[2] = {2*n + 1, 2*n + 2};
+  double hmax = 0.0, hbmin[3], hbmax[3], bmin[3], bmax[3];
+#pragma unroll
+  for (int d = 0; d < 3; d++) { bmin[d] = hbmin[d] = GSPH_BIG; bmax[d] = hbmax[d] = -GSPH_BIG; }
+  const int cnt = T.count[n];
+#pragma unroll
+  for (int s = 0; s < 2; s++) {
+    if (T.count[c[s]] > 0) {
+#pragma unroll
+      for (int d = 0; d < NDIM; d++) {
+        hbmin[d] = fmin(T.hbmin[d][c[s]], hbmin[d]); hbmax[d] = fmax(T.hbmax[d][c[s]], hbmax[d]);
+        if (full) { bmin[d] = fmin(T.bbmin[d][c[s]], bmin[d]); bmax[d] = fmax(T.bbmax[d][c[s]], bmax[d]); }
+      }
+      hmax = fmax(hmax, T.hmax[c[s]]);
+    }
+  }
+  T.nactive[n] = T.nactive[c[0]] + T.nactive[c[1]];
+  T.hmax[n] = hmax;
+#pragma unroll
+  for (int d = 0; d < NDIM; d++) { T.hbmin[d][n] = hbmin[d]; T.hbmax[d][n] = hbmax[d]; }
+  if (!full) return;
+  const double m0 = T.m[c[0]], m1 = T.m[c[1]];
+  const double m = m0 + m1;
+  double com[3] = {0, 0, 0}, vc[3] = {0, 0, 0};
+  if (m > 0.0) {
+#pragma unroll
+    for (int d = 0; d < NDIM; d++) {
+      com[d] = (m0*T.com[d][c[0]] + m1*T.com[d][c[1]])/m;
+      vc[d] = (m0*T.vcom[d][c[0]] + m1*T.vcom[d][c[1]])/m;
+    }
+  }
+  double rc[3] = {0, 0, 0}, rmax = 0.0, cdist = GSPH_BIG;
+  if (cnt > 0) {
+    double dr[3] = {0, 0, 0};
+#pragma unroll
+    for (int d = 0; d < NDIM; d++) {
+      rc[d] = __dmul_rn(0.5, __dadd_rn(bmin[d], bmax[d]));
+      dr[d] = __dmul_rn(0.5, __dadd_rn(bmax[d], -bmin[d]));
+    }
+    const double d2 = dot_exact<NDIM>(dr);
+    cdist = __ddiv_rn(fmax(d2, __dmul_rn(hmax, hmax)), dp.thetamaxsqd);
+    rmax = __dsqrt_rn(d2);
+  }
+  T.m[n] = m; T.rmax[n] = rmax; T.cdistsqd[n] = cdist;
+#pragma unroll
+  for (int d = 0; d < NDIM; d++) {
+    T.bbmin[d][n] = bmin[d]; T.bbmax[d][n] = bmax[d];
+    T.rcell[d][n] = rc[d]; T.com[d][n] = com[d]; T.vcom[d][n] = vc[d];
+  }
+  double q[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+  for (int s = 0; s < 2; s++) {
+    const double mi = s ? m1 : m0;
+    if (mi > 0.0) {
+      double dr[3] = {0, 0, 0};
+#pragma unroll
+      for (int d = 0; d < NDIM; d++) dr[d] = T.com[d][c[s]] - com[d];
+      const double d2 = dr[0]*dr[0] + dr[1]*dr[1] + dr[2]*dr[2];
+#pragma unroll
+      for (int j = 0; j < 5; j++) q[j] += T.q[j][c[s]];
+      q[0] += mi*(3.0*dr[0]*dr[0] - d2);
+      if (NDIM > 1) { q[1] += mi*3.0*dr[0]*dr[1]; q[2] += mi*(3.0*dr[1]*dr[1] - d2); }
+      if (NDIM > 2) { q[3] += mi*3.0*dr[2]*dr[0]; q[4] += mi*3.0*dr[2]*dr[1]; }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 5; j++) T.q[j][n] = q[j];
+}
+
+/* Tree::ExtrapolateCellProperties, Tree.cpp:172-198 */
+template <int NDIM>
+__global__ void extrapolate_kernel(TreeDev T, double dt)
+{
+  const int n = blockIdx.x*blockDim.x + threadIdx.x;
+  if (n >= T.ncell) return;
+#pragma unroll
+  for (int d = 0; d < NDIM; d++) {
+    const double s = T.vcom[d][n]*dt;
+    T.com[d][n] += s; T.rcell[d][n] += s;
+    T.bbmin[d][n] += s; T.bbmax[d][n] += s; T.hbmin[d][n] += s; T.hbmax[d][n] += s;
+  }
+}
+
+int alloc_tree(gsph_handle* h, int ltot)
+{
+  TreeDev& T = h->tree;
+  const int ncell = (2 << ltot) - 1;
+  T.ltot = ltot; T.ncell = ncell;
+  if (ncell <= T.ncell_cap) return GSPH_OK;
+  auto fre = [](void* p) { if (p) cudaFree(p); };
+  fre(T.first); fre(T.count); fre(T.nactive); fre(T.m); fre(T.rmax); fre(T.hmax); fre(T.cdistsqd);
+  for (int k = 0; k < 3; k++) {
+    fre(T.bbmin[k]); fre(T.bbmax[k]); fre(T.hbmin[k]); fre(T.hbmax[k]);
+    fre(T.rcell[k]); fre(T.com[k]); fre(T.vcom[k]);
+  }
+  for (int k = 0; k < 5; k++) fre(T.q[k]);
+  const size_t cap = (size_t) ncell + 1;
+  const int nd = h->dp.ndim;
+  CUDA_TRY(h, cudaMalloc(&T.first, cap*sizeof(int)));
+  CUDA_TRY(h, cudaMalloc(&T.count, cap*sizeof(int)));
+  CUDA_TRY(h, cudaMalloc(&T.nactive, cap*sizeof(int)));
+  CUDA_TRY(h, cudaMalloc(&T.m, cap*sizeof(double)));
+  CUDA_TRY(h, cudaMalloc(&T.rmax, cap*sizeof(double)));
+  CUDA_TRY(h, cudaMalloc(&T.hmax, cap*sizeof(double)));
+  CUDA_TRY(h, cudaMalloc(&T.cdistsqd, cap*sizeof(double)));
+  for (int k = 0; k < 3; k++) {
+    T.bbmin[k] = T.bbmax[k] = T.hbmin[k] = T.hbmax[k] = T.rcell[k] = T.com[k] = T.vcom[k] = nullptr;
+    if (k >= nd) continue;
+    CUDA_TRY(h, cudaMalloc(&T.bbmin[k], cap*sizeof(double)));
+    CUDA_TRY(h, cudaMalloc(&T.bbmax[k], cap*sizeof(double)));
+    CUDA_TRY(h, cudaMalloc(&T.hbmin[k], cap*sizeof(double)));
+    CUDA_TRY(h, cudaMalloc(&T.hbmax[k], cap*sizeof(double)));
+    CUDA_TRY(h, cudaMalloc(&T.rcell[k], cap*sizeof(double)));
+    CUDA_TRY(h, cudaMalloc(&T.com[k], cap*sizeof(double)));
+    CUDA_TRY(h, cudaMalloc(&T.vcom[k], cap*sizeof(double)));
+  }
+  for (int k = 0; k < 5; k++) CUDA_TRY(h, cudaMalloc(&T.q[k], cap*sizeof(double)));
+  T.ncell_cap = ncell;
+  return GSPH_OK;
+}
+
+PartView view_of(double* const* f, int32_t* const* i)
+{
+  PartView v;
+  for (int k = 0; k < NF_DOUBLE; k++) v.f[k] = f[k];
+  for (int k = 0; k < NF_INT; k++) v.i[k] = i[k];
+  return v;
+}
+
+template <int NDIM>
+int stock_tree(gsph_handle* h, int full)
+{
+  TreeDev& T = h->tree;
+  const PartView P = view_of(h->P, h->PI);
+  const int nleaf = 1 << T.ltot;
+  stock_leaves_kernel<NDIM><<<(nleaf + 127)/128, 128, 0, h->stream>>>(T, P, h->dp, full);
+  for (int l = T.ltot - 1; l >= 0; l--) {
+    const int nn = 1 << l;
+    stock_level_kernel<NDIM><<<(nn + 127)/128, 128, 0, h->stream>>>(T, h->dp, l, full);
+  }
+  h->stats.kernel_launches += 1 + T.ltot;
+  CUDA_TRY(h, cudaGetLastError());
+  return GSPH_OK;
+}
+
+template <int NDIM>
+int build_tree_nd(gsph_handle* h, int mode, double dt)
+{
+  const int N = (int) h->N;
+  const int nd = NDIM;
+  cudaStream_t s = h->stream;
+  const PartView Hh = view_of(h->H, h->HI);
+  const PartView Pp = view_of(h->P, h->PI);
+
+  if (mode == 2) {                                   /* extrapolate: Tree.cpp:172-198 */
+    if (!h->have_tree) { h->err = "gsph_build_tree(extrapolate) before the first rebuild"; return GSPH_ESTATE; }
+    if (!h->sorted_valid) {
+      gather_kernel<<<(N + 255)/256, 256, 0, s>>>(N, h->perm, Hh, Pp);
+      h->sorted_valid = true; h->stats.kernel_launches++;
+    }
+    extrapolate_kernel<NDIM><<<(h->tree.ncell + 255)/256, 256, 0, s>>>(h->tree, dt);
+    h->stats.kernel_launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return GSPH_OK;
+  }
+  if (mode == 1) {                                   /* restock: KDTree::StockTree */
+    if (!h->have_tree) { h->err = "gsph_build_tree(restock) before the first rebuild"; return GSPH_ESTATE; }
+    gather_kernel<<<(N + 255)/256, 256, 0, s>>>(N, h->perm, Hh, Pp);
+    h->sorted_valid = true; h->stats.kernel_launches++;
+    return stock_tree<NDIM>(h, 1);
+  }
+
+  /* ---- full rebuild ----------------------------------------------------------------------------*/
+  int ltot = 0;                                       /* ComputeTreeSize, KDTree.cpp:322-352 */
+  while ((int64_t) h->cfg.Nleafmax*((int64_t)1 << ltot) < (int64_t) N) ltot++;
+  int rc = alloc_tree(h, ltot);
+  if (rc) return rc;
+  TreeDev& T = h->tree;
+  const int nleaf = 1 << ltot;
+
+  /* scratch layout */
+  size_t cub_sort = 0, cub_scan = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_sort, (const double*) nullptr, (double*) nullptr,
+                                  (const int*) nullptr, (int*) nullptr, N, 0, 64, s);
+  {
+    SideOfList op{nullptr, nullptr};
+    cub::CountingInputIterator<int> cnt(0);
+    cub::TransformInputIterator<int, SideOfList, cub::CountingInputIterator<int>> it(cnt, op);
+    cub::DeviceScan::ExclusiveSum(nullptr, cub_scan, it, (int*) nullptr, N, s);
+  }
+  const size_t cub_bytes = cub_sort > cub_scan ? cub_sort : cub_scan;
+  const size_t need = (size_t) N*(sizeof(int)*(2*nd + 1 + nd) + sizeof(double) + 1)
+                      + (size_t) nleaf*(sizeof(double)*4*nd + 1) + cub_bytes + 64*1024 + 4096*2*nd*sizeof(double);
+  if (need > h->scratch_bytes) {
+    if (h->scratch) cudaFree(h->scratch);
+    h->scratch = nullptr; h->scratch_bytes = 0;
+    CUDA_TRY(h, cudaMalloc(&h->scratch, need + need/8));
+    h->scratch_bytes = need + need/8;
+  }
+  Bump B{(char*) h->scratch, 0, h->scratch_bytes};
+  int* list[3][2]; int* scan[3];
+  for (int d = 0; d < nd; d++) { list[d][0] = B.get<int>(N); list[d][1] = B.get<int>(N); scan[d] = B.get<int>(N); }
+  int* nodeidx = B.get<int>(N);
+  double* keys_out = B.get<double>(N);
+  uint8_t* side = B.get<uint8_t>(N);
+  double *ib[2][2][3];
+  for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) for (int d = 0; d < nd; d++) ib[a][b][d] = B.get<double>(nleaf);
+  int8_t* splitdim = B.get<int8_t>(nleaf);
+  const int rb_blocks = 1024;
+  double* rbpart = B.get<double>((size_t) rb_blocks*2*nd);
+  void* cubtmp = B.get<char>(cub_bytes);
+  if (B.off > B.cap) { h->err = "internal: tree scratch layout overflow"; return GSPH_ENOMEM; }
+
+  /* root box and the three presorted lists */
+  root_box_kernel<NDIM><<<rb_blocks, 256, 0, s>>>(N, Hh, h->dp.kernrange, rbpart);
+  root_box_final<NDIM><<<1, 32, 0, s>>>(rb_blocks, rbpart, ib[0][0][0], nd > 1 ? ib[0][0][1] : nullptr,
+                                        nd > 2 ? ib[0][0][2] : nullptr, ib[0][1][0],
+                                        nd > 1 ? ib[0][1][1] : nullptr, nd > 2 ? ib[0][1][2] : nullptr);
+  h->stats.kernel_launches += 2;
+  for (int d = 0; d < nd; d++) {
+    iota_kernel<<<(N + 255)/256, 256, 0, s>>>(N, list[d][1]);
+    size_t tb = cub_bytes;
+    cub::DeviceRadixSort::SortPairs(cubtmp, tb, (const double*) h->H[F_RX + d], keys_out,
+                                    (const int*) list[d][1], list[d][0], N, 0, 64, s);
+    h->stats.kernel_launches += 8;
+  }
+  CUDA_TRY(h, cudaMemsetAsync(nodeidx, 0, sizeof(int)*(size_t) N, s));
+  {
+    const int one[2] = {0, N};
+    CUDA_TRY(h, cudaMemcpyAsync(T.first, &one[0], sizeof(int), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaMemcpyAsync(T.count, &one[1], sizeof(int), cudaMemcpyHostToDevice, s));
+  }
+  int cur[3] = {0, 0, 0};
+  for (int l = 0; l < ltot; l++) {
+    LevelPtrs L;
+    const int a = l & 1;
+    for (int d = 0; d < 3; d++) {
+      L.list[d] = d < nd ? list[d][cur[d]] : nullptr;
+      L.newlist[d] = d < nd ? list[d][cur[d] ^ 1] : nullptr;
+      L.r[d] = d < nd ? h->H[F_RX + d] : nullptr;
+      L.ibmin[d] = d < nd ? ib[a][0][d] : nullptr;      L.ibmax[d] = d < nd ? ib[a][1][d] : nullptr;
+      L.cibmin[d] = d < nd ? ib[a ^ 1][0][d] : nullptr; L.cibmax[d] = d < nd ? ib[a ^ 1][1][d] : nullptr;
+      L.scan[d] = d < nd ? scan[d] : nullptr;
+    }
+    L.first = T.first; L.count = T.count; L.splitdim = splitdim; L.side = side; L.nodeidx = nodeidx;
+    const int nn = 1 << l;
+    split_nodes_kernel<NDIM><<<(nn + 127)/128, 128, 0, s>>>(l, L);
+    mark_side_kernel<<<(N + 255)/256, 256, 0, s>>>(N, l, L);
+    for (int d = 0; d < nd; d++) {
+      SideOfList op{L.list[d], side};
+      cub::CountingInputIterator<int> cnt(0);
+      cub::TransformInputIterator<int, SideOfList, cub::CountingInputIterator<int>> it(cnt, op);
+      size_t tb = cub_bytes;
+      cub::DeviceScan::ExclusiveSum(cubtmp, tb, it, scan[d], N, s);
+      partition_kernel<<<(N + 255)/256, 256, 0, s>>>(N, l, d, L);
+      cur[d] ^= 1;
+    }
+    update_nodeidx_kernel<<<(N + 255)/256, 256, 0, s>>>(N, l, L);
+    h->stats.kernel_launches += 3 + 3*nd;
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  CUDA_TRY(h, cudaMemcpyAsync(h->perm, list[0][cur[0]], sizeof(int)*(size_t) N, cudaMemcpyDeviceToDevice, s));
+  gather_kernel<<<(N + 255)/256, 256, 0, s>>>(N, h->perm, Hh, Pp);
+  h->stats.kernel_launches++;
+  h->sorted_valid = true;
+  h->have_tree = true;
+  return stock_tree<NDIM>(h, 1);
+}
+
+}  // namespace
+
+int gsph_tree_build(gsph_handle* h, int mode, double dt)
+{
+  switch (h->dp.ndim) {
+  case 1: return build_tree_nd<1>(h, mode, dt);
+  case 2: return build_tree_nd<2>(h, mode, dt);
+  default: return build_tree_nd<3>(h, mode, dt);
+  }
+}
+
+/* KDTree::UpdateAllHmaxValues after the density pass: only hmax and hbox change (cdistsqd keeps
+ * the value of the last stock, exactly like the reference, KDTree.cpp:1163-1205).                 */
+int gsph_tree_update_hmax(gsph_handle* h)
+{
+  switch (h->dp.ndim) {
+  case 1: return stock_tree<1>(h, 0);
+  case 2: return stock_tree<2>(h, 0);
+  default: return stock_tree<3>(h, 0);
+  }
+}
+
+int gsph_tree_update_active(gsph_handle* h) { return gsph_tree_update_hmax(h); }

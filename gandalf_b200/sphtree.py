@@ -1,0 +1,225 @@
+"""Host-side mirror of the reference operator surface for the neighbour path.
+
+``GpuSphTree`` carries the method names of ``SphNeighbourSearch<ndim>`` /
+``GradhSphTree<ndim,GradhSphParticle>`` (src/Headers/SphNeighbourSearch.h:77-94,174-227,
+src/Headers/NeighbourSearch.h:66-137) and forwards each to one libgsph C-ABI call, so the parity
+tests read like calls on the reference's own ``sphneib`` pointer.  The C++ twin used for the real
+drop-in is ``gandalf_b200/host/GpuSphTree.h``.
+
+``ParticleSet`` stands in for the particle array owned by ``GradhSph::sphdata``: it can be laid out
+as SoA (one contiguous array per field) or as an AoS record array with the field order of
+``GradhSphParticle<ndim>`` (src/Headers/Particle.h:134-368) to exercise the strided-view upload.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from .params import Parameters, config_from_params
+
+_DBL = _capi.VEC_FIELDS + _capi.SCALAR_FIELDS
+_INT = _capi.INT_FIELDS
+
+
+class ParticleSet(object):
+    """Host particle data.  ``data[name]`` is an (N,) or (N, ndim) numpy view; the views are
+    strided when ``layout='aos'``."""
+
+    def __init__(self, N, ndim, layout="soa"):
+        self.N, self.ndim, self.layout = int(N), int(ndim), layout
+        self.data = {}
+        if layout == "aos":
+            # field order follows Particle -> SphParticle -> GradhSphParticle (Particle.h:134-368)
+            dt = [("flags", "<u4"), ("ptype", "<i4"), ("iorig", "<i4"), ("sinkid", "<i4"),
+                  ("levelneib", "<i4"), ("nstep", "<i4"), ("nlast", "<i4"), ("level", "<i4"),
+                  ("r", "<f8", (ndim,)), ("v", "<f8", (ndim,)), ("a", "<f8", (ndim,)),
+                  ("atree", "<f8", (ndim,)), ("r0", "<f8", (ndim,)), ("v0", "<f8", (ndim,)),
+                  ("a0", "<f8", (ndim,)), ("m", "<f8"), ("h", "<f8"), ("h_dust", "<f8"),
+                  ("hrangesqd", "<f8"), ("hfactor", "<f8"), ("sound", "<f8"), ("rho", "<f8"),
+                  ("pressure", "<f8"), ("u", "<f8"), ("u0", "<f8"), ("dudt0", "<f8"), ("dudt", "<f8"),
+                  ("gpot", "<f8"), ("gpot_hydro", "<f8"), ("dt", "<f8"), ("dt_next", "<f8"),
+                  ("tlast", "<f8"), ("ionfrac", "<f8"), ("Xion", "<f8"), ("ueq", "<f8"),
+                  ("dt_therm", "<f8"), ("vsig_max", "<f8"), ("rad_pres", "<f8", (ndim,)),
+                  ("ionstate", "<i4"), ("_pad", "<i4"), ("div_v", "<f8"), ("alpha", "<f8"),
+                  ("dalphadt", "<f8"), ("invomega", "<f8"), ("zeta", "<f8")]
+            self.records = np.zeros(self.N, dtype=np.dtype(dt))
+            for n in _DBL + _INT:
+                self.data[n] = self.records[n]
+        else:
+            self.records = None
+            for n in _capi.VEC_FIELDS:
+                self.data[n] = np.zeros((self.N, ndim))
+            for n in _capi.SCALAR_FIELDS:
+                self.data[n] = np.zeros(self.N)
+            for n in _INT:
+                self.data[n] = np.zeros(self.N, dtype=np.uint32 if n == "flags" else np.int32)
+        self.data["h"][...] = 1.0
+        self.data["invomega"][...] = 1.0
+        self.data["sinkid"][...] = -1
+        self.data["flags"][...] = _capi.FLAG_ACTIVE
+        self.data["iorig"][...] = np.arange(self.N)
+
+    def __getitem__(self, k):
+        return self.data[k]
+
+    def set(self, **fields):
+        for k, v in fields.items():
+            self.data[k][...] = v
+        return self
+
+    def view(self, only=None):
+        """gsph_particle_view over the current arrays (never cached: the reference may reallocate
+        its array between calls, GradhSph.cpp:83-111)."""
+        pv = _capi.ParticleView()
+        for n in _capi.VEC_FIELDS:
+            if only is not None and n not in only:
+                continue
+            a = self.data[n]
+            for k in range(self.ndim):
+                f = getattr(pv, n)[k]
+                f.base = a.ctypes.data + k * a.strides[1]
+                f.stride = a.strides[0]
+        for n in _capi.SCALAR_FIELDS + _INT:
+            if only is not None and n not in only:
+                continue
+            a = self.data[n]
+            f = getattr(pv, n)
+            f.base = a.ctypes.data
+            f.stride = a.strides[0]
+        return pv
+
+
+class GpuSphTree(object):
+    """neib_search = gpu : the B200 implementation behind the SphNeighbourSearch surface."""
+
+    def __init__(self, params, device=0):
+        self.params = Parameters(params)
+        self._L = _capi.lib()
+        self.cfg = config_from_params(self.params, device=device)
+        self._h = C.c_void_p()
+        rc = self._L.gsph_create(C.byref(self.cfg), C.byref(self._h))
+        if rc:
+            raise _capi.GsphError(rc, self._L.gsph_last_error(None).decode())
+        self.neibcheck = False
+        self.Nsteps_since_build = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.gsph_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc:
+            raise _capi.GsphError(rc, self._L.gsph_last_error(self._h).decode())
+
+    # ---- data movement (what the C++ wrapper does around every virtual call) --------------------
+    def Upload(self, parts, only=None):
+        pv = parts.view(only)
+        self._check(self._L.gsph_upload(self._h, C.byref(pv), parts.N))
+
+    def Download(self, parts, mask=_capi.F_ALL, only=None):
+        pv = parts.view(only)
+        self._check(self._L.gsph_download(self._h, C.byref(pv), mask))
+
+    # ---- NeighbourSearch / SphNeighbourSearch surface -----------------------------------------------
+    def BuildTree(self, rebuild_tree, n, ntreebuildstep, ntreestockstep, timestep, parts=None):
+        """NeighbourSearch::BuildTree (HydroTree.cpp:310-372): rebuild | restock | extrapolate."""
+        if parts is not None:
+            self.Upload(parts)
+        if n % ntreebuildstep == 0 or rebuild_tree:
+            mode = 0
+        elif n % ntreestockstep == 0:
+            mode = 1
+        else:
+            mode = 2
+        self._check(self._L.gsph_build_tree(self._h, mode, float(timestep)))
+
+    def BuildGhostTree(self, *a, **kw):
+        """Periodic images are taken on the fly in the walks: nothing to build (HydroTree.cpp:382-441)."""
+
+    def SearchBoundaryGhostParticles(self, *a, **kw):
+        """No ghost particles are materialised (HydroTree.cpp:495-543 becomes a no-op)."""
+
+    def UpdateActiveParticleCounters(self):
+        self._check(self._L.gsph_update_active_counters(self._h))
+
+    def UpdateAllSphProperties(self):
+        self._check(self._L.gsph_update_properties(self._h))
+
+    UpdateAllProperties = UpdateAllSphProperties
+
+    def ZeroAccelerations(self):
+        """Sph::ZeroAccelerations (Sph.cpp:126-140), called between the two passes by MainLoop."""
+        self._check(self._L.gsph_zero_accelerations(self._h))
+
+    def UpdateAllSphHydroForces(self):
+        self._check(self._L.gsph_update_hydro_forces(self._h))
+
+    def UpdateAllSphForces(self):
+        self._check(self._L.gsph_update_all_forces(self._h, None, 0))
+
+    def GetMaximumSmoothingLength(self):
+        v = C.c_double()
+        self._check(self._L.gsph_get_hmax(self._h, C.byref(v)))
+        return v.value
+
+    def ToggleNeighbourCheck(self, do):
+        self.neibcheck = bool(do)
+
+    def Synchronize(self):
+        self._check(self._L.gsph_synchronize(self._h))
+
+    # ---- parity / inspection ---------------------------------------------------------------------
+    def NeighbourLists(self):
+        """-> (offsets int64 [N+1], idx int32) rows in host order, entries ascending host index."""
+        N = self.Stats().Nhydro
+        counts = np.zeros(N, dtype=np.int32)
+        self._check(self._L.gsph_neighbour_counts(self._h, counts.ctypes.data))
+        off = np.zeros(N + 1, dtype=np.int64)
+        np.cumsum(counts, out=off[1:])
+        idx = np.zeros(max(int(off[-1]), 1), dtype=np.int32)
+        self._check(self._L.gsph_neighbour_lists(self._h, off.ctypes.data, idx.ctypes.data))
+        return off, idx[:off[-1]]
+
+    def TreeInfo(self):
+        t = _capi.TreeInfo()
+        self._check(self._L.gsph_tree_info_get(self._h, C.byref(t)))
+        return t
+
+    def TreeLeafOf(self):
+        out = np.zeros(self.Stats().Nhydro, dtype=np.int32)
+        self._check(self._L.gsph_tree_leaf_of(self._h, out.ctypes.data))
+        return out
+
+    def TreeCells(self):
+        t = self.TreeInfo()
+        nd, nc = self.cfg.ndim, t.Ncell
+        out = dict(box=np.zeros((nc, 4 * nd)), com=np.zeros((nc, 2 * nd)), scalars=np.zeros((nc, 5)),
+                   q=np.zeros((nc, 5)), N=np.zeros(nc, dtype=np.int32))
+        self._check(self._L.gsph_tree_cells(self._h, out["box"].ctypes.data, out["com"].ctypes.data,
+                                            out["scalars"].ctypes.data, out["q"].ctypes.data,
+                                            out["N"].ctypes.data))
+        return out
+
+    def Stats(self):
+        s = _capi.Stats()
+        self._check(self._L.gsph_get_stats(self._h, C.byref(s)))
+        return s
+
+
+def kernel_table(ndim, kernel, which):
+    out = np.zeros(1000)
+    rc = _capi.lib().gsph_kernel_table(ndim, _capi.KERNEL[kernel], which, out.ctypes.data)
+    if rc:
+        raise _capi.GsphError(rc, "gsph_kernel_table")
+    return out
+
+
+def measure_fp_peak(device=0):
+    a, b = C.c_double(), C.c_double()
+    rc = _capi.lib().gsph_measure_fp_peak(device, C.byref(a), C.byref(b))
+    if rc:
+        raise _capi.GsphError(rc, "gsph_measure_fp_peak")
+    return a.value, b.value

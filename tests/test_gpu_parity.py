@@ -1,0 +1,383 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (gandalf_b200 -> libgsph.so), against
+  (1) golden vectors dumped from the UNMODIFIED reference (tests/golden/*.npz), and
+  (2) the pinned CPU oracle (oracle/gsph_oracle.c) on seeded inputs,
+plus size-independent properties at larger N.
+
+Bars: neighbour lists bit-exact; floating point 1e-6 relative (north star) -- the tests assert the
+much tighter TOL below because only summation order and a few libm/ulp-level sites differ.
+"""
+import numpy as np
+import pytest
+
+import oracle_py as orc
+from conftest import load_golden, stage, rel_err, vec_rel_err, scaled_err, GOLDEN_CASES
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-9          # asserted;   north-star bar is 1e-6
+GRAV = [c for c in GOLDEN_CASES if c.startswith("sphere_grav")]
+HYDRO = [c for c in GOLDEN_CASES if not c.startswith("sphere_grav")]
+
+
+def _by_iorig(st):
+    order = np.argsort(st["iorig"])
+    return {k: v[order] for k, v in st.items()}
+
+
+def _make(params, st, layout="soa", fields=None):
+    import gandalf_b200 as g
+    nd = int(params["ndim"])
+    N = len(st["m"])
+    ps = g.ParticleSet(N, nd, layout)
+    for k in fields or ("r", "v", "m", "h", "u", "rho", "invomega", "zeta", "hfactor", "hrangesqd", "sound",
+                        "pressure", "alpha", "level"):
+        if k in st:
+            ps[k][...] = np.asarray(st[k]).reshape(ps[k].shape)
+    tree = g.GpuSphTree(params)
+    return ps, tree
+
+
+@pytest.mark.parametrize("layout", ["soa", "aos"])
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_density_matches_reference(name, layout):
+    """UpdateAllSphProperties: dens_in -> dens_out of the reference."""
+    params, d = load_golden(name)
+    si, so = stage(d, "dens_in"), stage(d, "dens_out")
+    ps, tree = _make(params, si, layout, fields=("r", "v", "m", "h", "u", "alpha", "level"))
+    tree.BuildTree(True, 0, 1, 1, 0.0, ps)
+    tree.UpdateAllSphProperties()
+    tree.Download(ps)
+    for f in ("h", "rho", "invomega", "zeta", "hfactor", "hrangesqd", "u", "sound", "pressure"):
+        floor = np.abs(so[f]).max()*1e-6 if f == "zeta" else 0.0
+        e = rel_err(ps[f], so[f], floor).max()
+        assert e < TOL, "%s: %s rel err %.3e" % (name, f, e)
+    assert np.all(ps["div_v"] == 0.0)
+    st = tree.Stats()
+    assert st.n_active == len(si["m"]) and 1.0 <= st.hiter_mean < 30
+    tree.close()
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_neighbour_lists_bit_exact(name):
+    """identical neighbour lists: reference's own tree walk + NeighbourManager vs the GPU lists."""
+    params, d = load_golden(name)
+    s = _by_iorig(stage(d, "force_in"))
+    ps, tree = _make(params, s)
+    tree.BuildTree(True, 0, 1, 1, 0.0, ps)
+    off, idx = tree.NeighbourLists()
+    assert np.array_equal(off, d["force_in.neib_off"])
+    assert np.array_equal(idx, d["force_in.neib_idx"])
+    tree.close()
+
+
+@pytest.mark.parametrize("layout", ["soa", "aos"])
+@pytest.mark.parametrize("name", HYDRO)
+def test_hydro_forces_match_reference(name, layout):
+    params, d = load_golden(name)
+    si, so = stage(d, "force_in"), stage(d, "force_out")
+    ps, tree = _make(params, si, layout)
+    tree.BuildTree(True, 0, 1, 1, 0.0, ps)
+    tree.ZeroAccelerations()
+    tree.UpdateAllSphHydroForces()
+    tree.Download(ps)
+    assert vec_rel_err(ps["a"], so["a"].reshape(ps["a"].shape)).max() < TOL
+    for f in ("dudt", "div_v", "dalphadt"):
+        assert scaled_err(ps[f], so[f]).max() < TOL, f
+    assert np.array_equal(ps["levelneib"], so["levelneib"])
+    st = tree.Stats()
+    assert st.ngb_mean > 1 and st.cand_mean >= st.ngb_mean
+    tree.close()
+
+
+@pytest.mark.parametrize("name", GRAV)
+def test_kdtree_matches_reference(name):
+    """GPU level-synchronous build reproduces the reference KD-tree: same leaves, same cell data."""
+    params, d = load_golden(name)
+    s = _by_iorig(stage(d, "force_in"))
+    ps, tree = _make(params, s)
+    tree.BuildTree(True, 0, 1, 1, 0.0, ps)
+    info = tree.TreeInfo()
+    hdr = d["force_in.tree_hdr"]
+    assert info.Ncell == hdr[0] and info.ltot == hdr[1]
+    assert np.array_equal(tree.TreeLeafOf(), d["force_in.tree_leaf_of_iorig"])
+    c = tree.TreeCells()
+    assert np.array_equal(c["N"], d["force_in.tree_meta"][:, 2])
+    live = c["N"] > 0
+    # bb, hbox, rcell, rmax, hmax, cdistsqd are order-independent: bit-exact
+    assert np.array_equal(c["box"][live], d["force_in.tree_box"][live])
+    nd = 3
+    assert np.array_equal(c["com"][live][:, :nd], d["force_in.tree_com"][live][:, :nd])
+    assert np.array_equal(c["scalars"][live][:, 1:4], d["force_in.tree_scalars"][live][:, 1:4])
+    # m, centre of mass, q are sums: summation order differs
+    assert rel_err(c["scalars"][live][:, 0], d["force_in.tree_scalars"][live][:, 0]).max() < 1e-13
+    assert np.abs(c["com"][live][:, nd:] - d["force_in.tree_com"][live][:, nd:]).max() < 1e-13
+    qs = np.abs(d["force_in.tree_q"]).max()
+    if params["multipole"] in ("quadrupole", "fast_quadrupole"):
+        assert (np.abs(c["q"] - d["force_in.tree_q"])/qs).max() < 1e-12
+    tree.close()
+
+
+@pytest.mark.parametrize("name", GRAV)
+def test_gravity_forces_match_reference(name):
+    """UpdateAllSphForces (hydro + tree gravity) vs the reference: same tree -> same lists -> 1e-9."""
+    params, d = load_golden(name)
+    si, so = _by_iorig(stage(d, "force_in")), _by_iorig(stage(d, "force_out"))
+    ps, tree = _make(params, si)
+    tree.BuildTree(True, 0, 1, 1, 0.0, ps)
+    tree.ZeroAccelerations()
+    tree.UpdateAllSphForces()
+    tree.Download(ps)
+    assert vec_rel_err(ps["atree"], so["atree"]).max() < TOL
+    assert vec_rel_err(ps["a"], so["a"]).max() < TOL
+    assert rel_err(ps["gpot"], so["gpot"]).max() < TOL
+    assert scaled_err(ps["dudt"], so["dudt"]).max() < TOL
+    assert scaled_err(ps["div_v"], so["div_v"]).max() < TOL
+    assert np.array_equal(ps["levelneib"], so["levelneib"])
+    # interaction-list sizes equal the reference's (direct list includes the culled candidates)
+    st = tree.Stats()
+    assert st.ncell_mean > 0 and st.ndirect_mean > 0
+    tree.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# seeded inputs vs the oracle
+# ---------------------------------------------------------------------------------------------------
+def _random_box(seed, n, ndim, jitter=0.3):
+    rng = np.random.default_rng(seed)
+    g = (np.arange(n) + 0.5)/n
+    r = np.stack(np.meshgrid(*([g]*ndim), indexing="ij"), -1).reshape(-1, ndim)
+    r = (r + jitter/n*rng.uniform(-1, 1, r.shape)) % 1.0
+    N = len(r)
+    v = 0.3*np.sin(2*np.pi*r[:, ::-1]) + 0.05*rng.normal(size=r.shape)
+    m = np.full(N, 1.0/N)*(1 + 0.2*rng.uniform(-1, 1, N))
+    u = 1.0 + 0.3*np.cos(2*np.pi*r[:, 0])
+    h = np.full(N, 1.3/n)*(1 + 0.1*rng.uniform(-1, 1, N))
+    return dict(r=r, v=v, m=m, u=u, h=h)
+
+
+def _box_params(ndim, **kw):
+    p = {"ndim": ndim, "kernel": "m4", "tabulated_kernel": 1, "Nleafmax": 6}
+    for k in range(ndim):
+        p.update({"boxmin[%d]" % k: 0.0, "boxmax[%d]" % k: 1.0, "boundary_lhs[%d]" % k: "periodic",
+                  "boundary_rhs[%d]" % k: "periodic"})
+    p.update(kw)
+    return p
+
+
+@pytest.mark.parametrize("ndim,n,kw", [
+    (3, 24, {}),
+    (3, 20, {"kernel": "quintic"}),
+    (3, 20, {"tabulated_kernel": 0, "acond": "price2008", "time_dependent_avisc": "mm97"}),
+    (2, 96, {"kernel": "quintic", "acond": "wadsley2008", "Nleafmax": 12}),
+    (2, 64, {"tabulated_kernel": 0}),
+    (1, 700, {"tabulated_kernel": 0, "gamma_eos": 1.4}),
+    (1, 300, {"kernel": "quintic"}),
+    (3, 16, {"gas_eos": "isothermal", "temp0": 2.0, "mu_bar": 1.3}),
+    (3, 16, {"gas_eos": "barotropic", "temp0": 1.5, "mu_bar": 2.35, "rho_bary": 1.2, "gamma_eos": 1.4}),
+])
+def test_full_step_vs_oracle(ndim, n, kw):
+    """density -> hydro forces on a periodic jittered lattice, all option families, vs the oracle."""
+    import gandalf_b200 as g
+    ic = _random_box(100 + n + ndim, n, ndim)
+    params = _box_params(ndim, **kw)
+    p = orc.params_from_dict(params)
+    N = len(ic["m"])
+    ps = g.ParticleSet(N, ndim, "soa").set(r=ic["r"], v=ic["v"], m=ic["m"], h=ic["h"], u=ic["u"], alpha=0.7)
+    ps["level"][...] = np.arange(N) % 4
+    tree = g.GpuSphTree(params)
+    tree.BuildTree(True, 0, 1, 1, 0.0, ps)
+    tree.UpdateAllSphProperties()
+    tree.ZeroAccelerations()
+    tree.UpdateAllSphHydroForces()
+    tree.Download(ps)
+    od = orc.density(p, ic["r"], ic["m"], ic["h"], ic["u"])
+    for f in ("h", "rho", "invomega", "hfactor", "hrangesqd", "u", "sound", "pressure"):
+        assert rel_err(ps[f], od[f]).max() < TOL, f
+    assert scaled_err(ps["zeta"], od["zeta"]).max() < TOL
+    # neighbour lists from OUR h equal the oracle's lists from ITS h (no borderline flips)
+    off, idx = tree.NeighbourLists()
+    ooff, oidx = orc.neighbour_lists(p, ic["r"], od["hrangesqd"])
+    assert np.array_equal(off, ooff) and np.array_equal(idx, oidx)
+    s = dict(ic)
+    s.update(od)
+    s["alpha"] = np.full(N, 0.7)
+    s["level"] = (np.arange(N) % 4).astype(np.int32)
+    of = orc.hydro_forces(p, s)
+    assert vec_rel_err(ps["a"], of["a"]).max() < TOL
+    for f in ("dudt", "div_v", "dalphadt"):
+        assert scaled_err(ps[f], of[f]).max() < TOL, f
+    assert np.array_equal(ps["levelneib"], of["levelneib"])
+    tree.close()
+
+
+def test_open_boundaries_and_ragged_sizes():
+    """non-periodic clumpy distribution with strongly varying h; N not a multiple of anything."""
+    import gandalf_b200 as g
+    rng = np.random.default_rng(7)
+    for N in (1, 2, 7, 13, 100, 1237):
+        r = rng.normal(size=(N, 3))*np.where(rng.uniform(size=(N, 1)) < 0.3, 0.1, 1.0)
+        m = np.full(N, 1.0/N)
+        h = np.full(N, 0.5)
+        u = np.ones(N)
+        params = {"ndim": 3, "kernel": "m4", "tabulated_kernel": 1}
+        p = orc.params_from_dict(params)
+        ps = g.ParticleSet(N, 3).set(r=r, m=m, h=h, u=u)
+        tree = g.GpuSphTree(params)
+        tree.BuildTree(True, 0, 1, 1, 0.0, ps)
+        tree.UpdateAllSphProperties()
+        tree.ZeroAccelerations()
+        tree.UpdateAllSphHydroForces()
+        tree.Download(ps)
+        od = orc.density(p, r, m, h, u)
+        for f in ("h", "rho", "invomega"):
+            assert rel_err(ps[f], od[f]).max() < TOL, (N, f)
+        off, idx = tree.NeighbourLists()
+        ooff, oidx = orc.neighbour_lists(p, r, od["hrangesqd"])
+        assert np.array_equal(off, ooff) and np.array_equal(idx, oidx)
+        assert tree.GetMaximumSmoothingLength() == ps["h"].max()
+        tree.close()
+
+
+def test_inactive_particles_are_sources_only():
+    """block time-steps: only flagged-active particles are updated, everyone is a neighbour; the
+    levelneib scatter reaches inactive neighbours (GradhSph.cpp:445-446)."""
+    import gandalf_b200 as g
+    ic = _random_box(5, 14, 3)
+    params = _box_params(3)
+    N = len(ic["m"])
+    act = (np.arange(N) % 3 == 0)
+    ref = g.ParticleSet(N, 3).set(r=ic["r"], v=ic["v"], m=ic["m"], h=ic["h"], u=ic["u"])
+    ref["level"][...] = np.arange(N) % 5
+    t0 = g.GpuSphTree(params)
+    t0.BuildTree(True, 0, 1, 1, 0.0, ref)
+    t0.UpdateAllSphProperties(); t0.ZeroAccelerations(); t0.UpdateAllSphHydroForces(); t0.Download(ref)
+    # now the same state with 1/3 active: start from the converged density of `ref`
+    ps = g.ParticleSet(N, 3)
+    for k in ("r", "v", "m", "h", "u", "rho", "invomega", "zeta", "hfactor", "hrangesqd", "sound", "pressure", "level"):
+        ps[k][...] = ref[k]
+    ps["flags"][...] = np.where(act, 2, 0)
+    ps["a"][...] = 123.0
+    t1 = g.GpuSphTree(params)
+    t1.BuildTree(True, 0, 1, 1, 0.0, ps)
+    t1.ZeroAccelerations(); t1.UpdateAllSphHydroForces(); t1.Download(ps)
+    assert t1.Stats().n_active == act.sum()
+    assert np.allclose(ps["a"][act], ref["a"][act], rtol=1e-12, atol=1e-14)
+    assert np.all(ps["a"][~act] == 123.0)
+    # levelneib of an inactive particle = max level over its ACTIVE neighbours (scatter half only)
+    off, idx = t1.NeighbourLists()
+    for i in np.where(~act)[0][:200]:
+        nb = idx[off[i]:off[i + 1]]
+        nb = nb[act[nb]]
+        want = ps["level"][nb].max() if len(nb) else 0
+        assert ps["levelneib"][i] == max(want, 0)
+    t0.close(); t1.close()
+
+
+def test_restock_and_extrapolate_modes():
+    import gandalf_b200 as g
+    ic = _random_box(9, 12, 3)
+    params = _box_params(3)
+    N = len(ic["m"])
+    ps = g.ParticleSet(N, 3).set(r=ic["r"], v=ic["v"], m=ic["m"], h=ic["h"], u=ic["u"])
+    tree = g.GpuSphTree(params)
+    tree.BuildTree(True, 0, 1, 1, 0.0, ps)
+    leaf0 = tree.TreeLeafOf()
+    ps["r"][...] = (ps["r"] + 1e-3*ps["v"]) % 1.0
+    tree.BuildTree(False, 1, 10, 1, 1e-3, ps)            # restock: same topology, fresh cell data
+    assert np.array_equal(tree.TreeLeafOf(), leaf0)
+    c1 = tree.TreeCells()
+    tree.UpdateAllSphProperties()
+    tree.Download(ps)
+    p = orc.params_from_dict(params)
+    od = orc.density(p, ps["r"], ic["m"], ic["h"], ic["u"])
+    assert rel_err(ps["rho"], od["rho"]).max() < TOL
+    tree.BuildTree(False, 3, 10, 2, 1e-3, ps)            # extrapolate: boxes drift with the cell velocity
+    c2 = tree.TreeCells()
+    assert not np.array_equal(c1["com"], c2["com"])
+    tree.close()
+
+
+def test_errors_are_loud():
+    import gandalf_b200 as g
+    with pytest.raises(ValueError):
+        g.GpuSphTree({"ndim": 3, "time_dependent_avisc": "cd2010"})
+    with pytest.raises(g.GsphError):
+        g.GpuSphTree({"ndim": 3, "boundary_lhs[0]": "mirror", "boundary_rhs[0]": "mirror"})
+    t = g.GpuSphTree({"ndim": 3})
+    with pytest.raises(g.GsphError):
+        t.UpdateAllSphProperties()                       # no upload / tree yet
+    with pytest.raises(g.GsphError):
+        t.UpdateAllSphForces()
+    t.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# larger N: size-independent properties (the oracle is O(N^2))
+# ---------------------------------------------------------------------------------------------------
+def test_million_particle_properties():
+    import gandalf_b200 as g
+    n = 100
+    ic = _random_box(1, n, 3, jitter=0.2)
+    params = _box_params(3)
+    N = len(ic["m"])
+    ps = g.ParticleSet(N, 3).set(r=ic["r"], v=ic["v"], m=ic["m"], h=ic["h"], u=ic["u"])
+    tree = g.GpuSphTree(params)
+    tree.BuildTree(True, 0, 1, 1, 0.0, ps)
+    tree.UpdateAllSphProperties(); tree.ZeroAccelerations(); tree.UpdateAllSphHydroForces(); tree.Download(ps)
+    st = tree.Stats()
+    assert st.n_active == N and 40 < st.ngb_mean < 80
+    # h = h_fac (m/rho)^(1/3) at convergence
+    assert rel_err(ps["h"], 1.2*np.cbrt(ps["m"]/ps["rho"])).max() < 1e-14
+    assert abs(ps["rho"].mean() - 1.0) < 0.02
+    # pairwise antisymmetry of the momentum exchange: sum m a = 0 (to rounding)
+    mom = (ps["m"][:, None]*ps["a"]).sum(0)
+    scale = np.abs(ps["m"][:, None]*ps["a"]).sum(0)
+    assert np.all(np.abs(mom) < 1e-11*scale)
+    # neighbour relation is symmetric and contains self
+    off, idx = tree.NeighbourLists()
+    cnt = np.diff(off)
+    rows = np.repeat(np.arange(N), cnt)
+    key_f = rows.astype(np.int64)*N + idx
+    key_b = idx.astype(np.int64)*N + rows
+    assert np.array_equal(np.sort(key_f), np.sort(key_b))
+    assert int((rows == idx).sum()) == N
+    # idempotence: a second density pass from the converged h changes nothing beyond tolerance
+    h1 = ps["h"].copy()
+    tree.BuildTree(True, 1, 1, 1, 0.0, ps)
+    tree.UpdateAllSphProperties(); tree.Download(ps)
+    assert rel_err(ps["h"], h1).max() < 0.01
+    tree.close()
+
+
+def test_gravity_sphere_vs_oracle_tree():
+    """larger self-gravitating sphere (N=20000): GPU vs the oracle's restatement of the reference walk."""
+    import gandalf_b200 as g
+    rng = np.random.default_rng(11)
+    N = 20000
+    rad = rng.uniform(0, 1, N)**(1/2.2)
+    dirs = rng.normal(size=(N, 3)); dirs /= np.linalg.norm(dirs, axis=1)[:, None]
+    r = dirs*rad[:, None]
+    v = 0.2*np.cross([0, 0, 1.0], r)
+    m = np.full(N, 1.0/N); u = np.full(N, 0.05)
+    h = np.full(N, 0.08)
+    for multipole, theta in (("quadrupole", 0.1), ("fast_monopole", 0.15), ("monopole", 0.2), ("fast_quadrupole", 0.1)):
+        params = {"ndim": 3, "self_gravity": 1, "multipole": multipole, "thetamaxsqd": theta}
+        p = orc.params_from_dict(params)
+        ps = g.ParticleSet(N, 3).set(r=r, v=v, m=m, h=h, u=u)
+        tree = g.GpuSphTree(params)
+        tree.BuildTree(True, 0, 1, 1, 0.0, ps)
+        tree.UpdateAllSphProperties()
+        tree.Download(ps)
+        tree.BuildTree(True, 1, 1, 1, 0.0, ps)          # restock with the new h, as the oracle tree does
+        tree.ZeroAccelerations(); tree.UpdateAllSphForces(); tree.Download(ps)
+        s = {k: ps[k].copy() for k in ("r", "v", "m", "h", "rho", "pressure", "invomega", "zeta", "sound", "u",
+                                       "alpha", "hfactor", "hrangesqd", "level")}
+        t = orc.Tree(p, s["r"], s["v"], s["m"], s["h"])
+        assert np.array_equal(tree.TreeLeafOf(), t.leaf_of())
+        out = t.hydro_grav_forces(s)
+        assert vec_rel_err(ps["atree"], out["atree"]).max() < TOL, multipole
+        assert vec_rel_err(ps["a"], out["a"]).max() < TOL, multipole
+        assert rel_err(ps["gpot"], out["gpot"]).max() < TOL, multipole
+        st = tree.Stats()
+        assert abs(st.ncell_mean - out["ncell"].mean()) < 1e-9*max(1.0, out["ncell"].mean())
+        tree.close()
