@@ -299,14 +299,15 @@ hydro_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict__ 
         }
         if (g.levelneib > P.i[I_LEVELNEIB][i]) atomicMax(&P.i[I_LEVELNEIB][i], g.levelneib);
         loc_ngb += g.nngb; loc_targets++; loc_ngbmax = max(loc_ngbmax, g.nngb);
+        loc_cand += (unsigned long long) ncand;
       }
-      loc_cand += (unsigned long long) ncand;
     }
     __syncwarp();
     if (lane == 0) done[c] = 1;
   }
   loc_ngb = (unsigned long long) warp_sum((double) loc_ngb);
   loc_targets = (unsigned long long) warp_sum((double) loc_targets);
+  loc_cand = (unsigned long long) warp_sum((double) loc_cand);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) loc_ngbmax = max(loc_ngbmax, __shfl_xor_sync(FULLMASK, loc_ngbmax, o));
   if (lane == 0) {
