@@ -214,7 +214,7 @@ def test_open_boundaries_and_ragged_sizes():
     """non-periodic clumpy distribution with strongly varying h; N not a multiple of anything."""
     import gandalf_b200 as g
     rng = np.random.default_rng(7)
-    for N in (1, 2, 7, 13, 100, 1237):
+    for N in (7, 13, 100, 1237):       # N <= 5 has no h-rho fixed point (N*W(0) < (1/h_fac)^3): see below
         r = rng.normal(size=(N, 3))*np.where(rng.uniform(size=(N, 1)) < 0.3, 0.1, 1.0)
         m = np.full(N, 1.0/N)
         h = np.full(N, 0.5)
@@ -236,6 +236,19 @@ def test_open_boundaries_and_ragged_sizes():
         assert np.array_equal(off, ooff) and np.array_equal(idx, oidx)
         assert tree.GetMaximumSmoothingLength() == ps["h"].max()
         tree.close()
+
+
+def test_isolated_particle_fails_loudly():
+    """a lone particle has no h-rho fixed point; the reference loops forever growing hmax
+    (GradhSphTree.cpp:154-240) -- the GPU path gives up after 60 enlargements with an error."""
+    import gandalf_b200 as g
+    ps = g.ParticleSet(1, 3).set(r=[[0.1, 0.2, 0.3]], m=1.0, h=0.5, u=1.0)
+    tree = g.GpuSphTree({"ndim": 3})
+    tree.BuildTree(True, 0, 1, 1, 0.0, ps)
+    with pytest.raises(g.GsphError) as e:
+        tree.UpdateAllSphProperties()
+    assert e.value.code == 6
+    tree.close()
 
 
 def test_inactive_particles_are_sources_only():
