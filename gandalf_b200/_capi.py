@@ -18,6 +18,7 @@ MAC = {"geometric": 0, "eigenmac": 1, "gadget2": 2}
 MULTIPOLE = {"monopole": 0, "quadrupole": 1, "fast_monopole": 2, "fast_quadrupole": 3}
 FLAG_DEAD, FLAG_ACTIVE, FLAG_POTMIN = 1, 2, 8
 F_DENSITY, F_FORCES, F_ALL = 1, 2, 0xFFFFFFFF
+DEVICE_FIELDS = ("h", "rho", "hrangesqd", "hfactor", "invomega", "zeta", "sound", "pressure", "u")
 ERRORS = {1: "GSPH_EINVAL", 2: "GSPH_ENODEVICE", 3: "GSPH_ECUDA", 4: "GSPH_ENOMEM", 5: "GSPH_ESTATE",
           6: "GSPH_ECONVERGE"}
 
@@ -65,13 +66,17 @@ class Stats(C.Structure):
                 ("hiter_max", C.c_int32), ("density_retries", C.c_int32), ("ndirect_mean", C.c_double),
                 ("ncell_mean", C.c_double), ("kernel_launches", C.c_int64), ("ms_build_tree", C.c_float),
                 ("ms_properties", C.c_float), ("ms_forces", C.c_float), ("ms_upload", C.c_float),
-                ("ms_download", C.c_float)]
+                ("ms_download", C.c_float), ("ms_kernel_density", C.c_float),
+                ("ms_kernel_hydro", C.c_float), ("ms_kernel_gravity", C.c_float), ("ms_tree_sort", C.c_float),
+                ("ms_tree_levels", C.c_float), ("ms_tree_stock", C.c_float)]
 
 
 EXPORTS = [
     "gsph_default_config", "gsph_create", "gsph_destroy", "gsph_last_error", "gsph_upload", "gsph_download",
     "gsph_build_tree", "gsph_update_active_counters", "gsph_update_properties", "gsph_zero_accelerations",
     "gsph_update_hydro_forces", "gsph_update_all_forces", "gsph_get_hmax", "gsph_synchronize",
+    "gsph_timer_start", "gsph_timer_stop", "gsph_set_active_slice", "gsph_density_pass", "gsph_refresh_hmax",
+    "gsph_device_field",
     "gsph_neighbour_counts", "gsph_neighbour_lists", "gsph_tree_info_get", "gsph_tree_leaf_of",
     "gsph_tree_cells", "gsph_get_stats", "gsph_kernel_table", "gsph_measure_fp_peak",
 ]
@@ -105,9 +110,13 @@ def lib():
     L.gsph_download.argtypes = [H, C.POINTER(ParticleView), C.c_uint32]
     L.gsph_build_tree.argtypes = [H, C.c_int, C.c_double]
     for n in ("gsph_update_active_counters", "gsph_update_properties", "gsph_zero_accelerations",
-              "gsph_update_hydro_forces", "gsph_synchronize"):
+              "gsph_update_hydro_forces", "gsph_synchronize", "gsph_timer_start", "gsph_density_pass",
+              "gsph_refresh_hmax"):
         getattr(L, n).argtypes = [H]
     L.gsph_update_all_forces.argtypes = [H, C.c_void_p, C.c_int]
+    L.gsph_set_active_slice.argtypes = [H, C.c_int64, C.c_int64]
+    L.gsph_device_field.argtypes = [H, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    L.gsph_timer_stop.argtypes = [H, C.POINTER(C.c_float)]
     L.gsph_get_hmax.argtypes = [H, C.POINTER(C.c_double)]
     L.gsph_neighbour_counts.argtypes = [H, C.c_void_p]
     L.gsph_neighbour_lists.argtypes = [H, C.c_void_p, C.c_void_p]

@@ -299,6 +299,9 @@ int gsph_create(const gsph_config* cfg, gsph_handle** out)
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
   if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return fail("cudaEventCreate", e);
   if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return fail("cudaEventCreate", e);
+  for (int k = 0; k < 2; k++) if ((e = cudaEventCreate(&h->evt[k])) != cudaSuccess) return fail("cudaEventCreate", e);
+  for (int k = 0; k < 6; k++) for (int j = 0; j < 2; j++)
+    if ((e = cudaEventCreate(&h->evk[k][j])) != cudaSuccess) return fail("cudaEventCreate", e);
   fill_devparams(h);
   std::vector<double> tab(6*GSPH_TABLE_RES);
   gsph_make_tables(cfg->ndim, cfg->kernel, tab.data());
@@ -328,6 +331,8 @@ void gsph_destroy(gsph_handle* h)
   if (h->pinned) cudaFreeHost(h->pinned);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  for (int k = 0; k < 2; k++) if (h->evt[k]) cudaEventDestroy(h->evt[k]);
+  for (int k = 0; k < 6; k++) for (int j = 0; j < 2; j++) if (h->evk[k][j]) cudaEventDestroy(h->evk[k][j]);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -421,7 +426,7 @@ int gsph_upload(gsph_handle* h, const gsph_particle_view* view, int64_t N)
   }
   CUDA_TRY(h, cudaGetLastError());
   if (N != h->N) h->have_tree = false;
-  h->N = N; h->uploaded = true; h->sorted_valid = false; h->density_done = false;
+  h->N = N; h->uploaded = true; h->sorted_valid = false; h->density_done = false; h->slice_mode = false;
   h->stats.Nhydro = N;
   tm.stop();
   return GSPH_OK;
@@ -569,7 +574,7 @@ int gsph_prepare_done_flags(gsph_handle* h)
   return GSPH_OK;
 }
 
-int gsph_update_properties(gsph_handle* h)
+static int update_properties_impl(gsph_handle* h, bool refresh)
 {
   if (!h) return GSPH_EINVAL;
   if (!h->have_tree || !h->sorted_valid) { h->err = "gsph_update_properties before gsph_build_tree"; return GSPH_ESTATE; }
@@ -579,8 +584,10 @@ int gsph_update_properties(gsph_handle* h)
   rc = gsph_prepare_done_flags(h); if (rc) return rc;
   rc = run_with_regrow(h, "gsph_update_properties", pass_density, 0);
   if (rc) return rc;
-  rc = gsph_tree_update_hmax(h);                        /* tree->UpdateAllHmaxValues, GradhSphTree.cpp:268 */
-  if (rc) return rc;
+  if (refresh) {
+    rc = gsph_tree_update_hmax(h);                      /* tree->UpdateAllHmaxValues, GradhSphTree.cpp:268 */
+    if (rc) return rc;
+  }
   tm.stop();
   const DevStatus& s = *h->status_host;
   h->stats.n_active = (int64_t) s.ntarget;
@@ -588,6 +595,51 @@ int gsph_update_properties(gsph_handle* h)
   h->stats.hiter_max = s.hiter_max;
   h->stats.density_retries = s.density_retries;
   h->density_done = true;
+  return GSPH_OK;
+}
+
+int gsph_update_properties(gsph_handle* h) { return update_properties_impl(h, true); }
+int gsph_density_pass(gsph_handle* h) { return update_properties_impl(h, false); }
+
+int gsph_refresh_hmax(gsph_handle* h)
+{
+  if (!h) return GSPH_EINVAL;
+  if (!h->have_tree || !h->sorted_valid) { h->err = "gsph_refresh_hmax before gsph_build_tree"; return GSPH_ESTATE; }
+  cudaSetDevice(h->device);
+  return gsph_tree_update_hmax(h);
+}
+
+__global__ void active_slice_kernel(int N, int lo, int hi, int32_t* flags)
+{
+  const int p = blockIdx.x*blockDim.x + threadIdx.x;
+  if (p >= N) return;
+  unsigned f = (unsigned) flags[p];
+  if (p >= lo && p < hi) f |= GSPH_FLAG_ACTIVE; else f &= ~(unsigned) GSPH_FLAG_ACTIVE;
+  flags[p] = (int32_t) f;
+}
+
+int gsph_set_active_slice(gsph_handle* h, int64_t lo, int64_t hi)
+{
+  if (!h) return GSPH_EINVAL;
+  if (!h->have_tree || !h->sorted_valid) { h->err = "gsph_set_active_slice before gsph_build_tree"; return GSPH_ESTATE; }
+  if (lo < 0 || hi < lo || hi > h->N) { h->err = "gsph_set_active_slice: bad range"; return GSPH_EINVAL; }
+  cudaSetDevice(h->device);
+  const int N = (int) h->N;
+  active_slice_kernel<<<(N + 255)/256, 256, 0, h->stream>>>(N, (int) lo, (int) hi, h->PI[I_FLAGS]);
+  h->stats.kernel_launches++;
+  h->slice_mode = true;
+  CUDA_TRY(h, cudaGetLastError());
+  return gsph_update_active_counters(h);
+}
+
+int gsph_device_field(gsph_handle* h, int field, void** ptr, int64_t* capacity)
+{
+  if (!h || !ptr) return GSPH_EINVAL;
+  static const int map[GSPH_DF_COUNT] = {F_H, F_RHO, F_HR2, F_HFAC, F_INVOMEGA, F_ZETA, F_SOUND, F_PRESS, F_U};
+  if (field < 0 || field >= GSPH_DF_COUNT) { h->err = "gsph_device_field: unknown field"; return GSPH_EINVAL; }
+  if (!h->P[map[field]]) { h->err = "gsph_device_field before gsph_upload"; return GSPH_ESTATE; }
+  *ptr = h->P[map[field]];
+  if (capacity) *capacity = h->Ncap;
   return GSPH_OK;
 }
 
@@ -802,9 +854,33 @@ int gsph_tree_cells(gsph_handle* h, double* box, double* com, double* scalars, d
   return GSPH_OK;
 }
 
+int gsph_timer_start(gsph_handle* h)
+{
+  if (!h) return GSPH_EINVAL;
+  cudaSetDevice(h->device);
+  CUDA_TRY(h, cudaEventRecord(h->evt[0], h->stream));
+  return GSPH_OK;
+}
+
+int gsph_timer_stop(gsph_handle* h, float* ms)
+{
+  if (!h || !ms) return GSPH_EINVAL;
+  cudaSetDevice(h->device);
+  CUDA_TRY(h, cudaEventRecord(h->evt[1], h->stream));
+  CUDA_TRY(h, cudaEventSynchronize(h->evt[1]));
+  CUDA_TRY(h, cudaEventElapsedTime(ms, h->evt[0], h->evt[1]));
+  return GSPH_OK;
+}
+
 int gsph_get_stats(gsph_handle* h, gsph_stats* st)
 {
   if (!h || !st) return GSPH_EINVAL;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  float* dst[6] = {&h->stats.ms_kernel_density, &h->stats.ms_kernel_hydro, &h->stats.ms_kernel_gravity,
+                   &h->stats.ms_tree_sort, &h->stats.ms_tree_levels, &h->stats.ms_tree_stock};
+  for (int k = 0; k < 6; k++)
+    if (h->evk_used[k]) { cudaEventElapsedTime(dst[k], h->evk[k][0], h->evk[k][1]); h->evk_used[k] = false; }
   *st = h->stats;
   return GSPH_OK;
 }

@@ -297,6 +297,7 @@ int launch_density(gsph_handle* h)
   PartView P;
   for (int k = 0; k < NF_DOUBLE; k++) P.f[k] = h->P[k];
   for (int k = 0; k < NF_INT; k++) P.i[k] = h->PI[k];
+  KernelTimer kt(h, 0);
   kern<<<blocks, DENS_THREADS, smem, h->stream>>>(P, h->tree, h->dp, h->tables, Lc, h->work_counter,
                                                   h->cand, (int) h->cand_cap_per_warp, h->status, h->done);
   h->stats.kernel_launches++;

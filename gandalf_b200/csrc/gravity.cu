@@ -290,6 +290,7 @@ int launch_gravity(gsph_handle* h)
   PartView P;
   for (int k = 0; k < NF_DOUBLE; k++) P.f[k] = h->P[k];
   for (int k = 0; k < NF_INT; k++) P.i[k] = h->PI[k];
+  KernelTimer kt(h, 2);
   kern<<<blocks, GRAV_THREADS, smem, h->stream>>>(P, h->tree, h->dp, h->work_counter, h->gravlist,
                                                   (int) h->grav_cap_cells, (int) h->grav_cap_direct, h->status, h->done);
   h->stats.kernel_launches++;

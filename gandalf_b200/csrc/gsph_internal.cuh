@@ -105,6 +105,7 @@ struct gsph_handle {
   int32_t* perm = nullptr;      /* tree position -> host index */
   bool uploaded = false, have_tree = false, sorted_valid = false, all_active = true;
   bool density_done = false;
+  bool slice_mode = false;   /* gsph_set_active_slice: inactive particles belong to other ranks */
 
   TreeDev tree;
   double* tables = nullptr;     /* 6 x 1000 doubles: w0_s2, womega_s2, wzeta_s2, w1, wgrav, wpot */
@@ -121,6 +122,9 @@ struct gsph_handle {
 
   gsph_stats stats;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t evt[2] = {nullptr, nullptr};          /* gsph_timer_start/stop */
+  cudaEvent_t evk[6][2] = {};                        /* per-kernel stopwatches: 0 density 1 hydro 2 gravity 3 sort 4 levels 5 stock */
+  bool evk_used[6] = {false, false, false, false, false, false};
 };
 
 #define CUDA_TRY(h, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { \
@@ -138,6 +142,12 @@ int gsph_run_neiblist(gsph_handle* h, int32_t* counts_dev, const int64_t* offset
 int gsph_run_gravity(gsph_handle* h);                                 /* gravity.cu */
 int gsph_check_status(gsph_handle* h, const char* where);             /* capi.cu    */
 int gsph_ensure_cand(gsph_handle* h, int warps, size_t cap_per_warp);
+
+struct KernelTimer {          /* brackets one launch (or group) with events; read back later */
+  gsph_handle* h; int k;
+  KernelTimer(gsph_handle* h_, int k_) : h(h_), k(k_) { cudaEventRecord(h->evk[k][0], h->stream); }
+  ~KernelTimer() { cudaEventRecord(h->evk[k][1], h->stream); h->evk_used[k] = true; }
+};
 
 static inline int cohort_level_for(int64_t N, int ltot, int maxsize)
 {

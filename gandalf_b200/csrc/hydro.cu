@@ -428,6 +428,7 @@ int launch_hydro(gsph_handle* h)
   PartView P;
   for (int k = 0; k < NF_DOUBLE; k++) P.f[k] = h->P[k];
   for (int k = 0; k < NF_INT; k++) P.i[k] = h->PI[k];
+  KernelTimer kt(h, 1);
   kern<<<blocks, HYD_THREADS, smem, h->stream>>>(P, h->tree, h->dp, h->tables, Lc, h->work_counter,
                                                  h->cand, (int) h->cand_cap_per_warp, h->status, h->done);
   h->stats.kernel_launches++;
@@ -482,7 +483,7 @@ int dispatch_hydro(gsph_handle* h, int with_gravity)
     rc = tab ? dispatch_mode<NDIM, GSPH_KERNEL_QUINTIC, true>(h, with_gravity)
              : dispatch_mode<NDIM, GSPH_KERNEL_QUINTIC, false>(h, with_gravity);
   if (rc) return rc;
-  if (!h->all_active && (h->dp.hydro_forces || !with_gravity))
+  if (!h->all_active && !h->slice_mode && (h->dp.hydro_forces || !with_gravity))
     rc = launch_neib<NDIM, 2>(h, nullptr, nullptr, nullptr);
   return rc;
 }

@@ -478,6 +478,7 @@ int build_tree_nd(gsph_handle* h, int mode, double dt)
                                         nd > 2 ? ib[0][0][2] : nullptr, ib[0][1][0],
                                         nd > 1 ? ib[0][1][1] : nullptr, nd > 2 ? ib[0][1][2] : nullptr);
   h->stats.kernel_launches += 2;
+  cudaEventRecord(h->evk[3][0], s);
   for (int d = 0; d < nd; d++) {
     iota_kernel<<<(N + 255)/256, 256, 0, s>>>(N, list[d][1]);
     size_t tb = cub_bytes;
@@ -485,6 +486,8 @@ int build_tree_nd(gsph_handle* h, int mode, double dt)
                                     (const int*) list[d][1], list[d][0], N, 0, 64, s);
     h->stats.kernel_launches += 8;
   }
+  cudaEventRecord(h->evk[3][1], s); h->evk_used[3] = true;
+  cudaEventRecord(h->evk[4][0], s);
   CUDA_TRY(h, cudaMemsetAsync(nodeidx, 0, sizeof(int)*(size_t) N, s));
   {
     const int one[2] = {0, N};
@@ -525,7 +528,11 @@ int build_tree_nd(gsph_handle* h, int mode, double dt)
   h->stats.kernel_launches++;
   h->sorted_valid = true;
   h->have_tree = true;
-  return stock_tree<NDIM>(h, 1);
+  cudaEventRecord(h->evk[4][1], s); h->evk_used[4] = true;
+  cudaEventRecord(h->evk[5][0], s);
+  const int rcs = stock_tree<NDIM>(h, 1);
+  cudaEventRecord(h->evk[5][1], s); h->evk_used[5] = true;
+  return rcs;
 }
 
 }  // namespace

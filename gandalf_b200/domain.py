@@ -1,0 +1,91 @@
+"""Multi-GPU driver of the path: one process per GPU, torch.distributed (NCCL over NVLink) for
+the one exchange step per pass.
+
+Replaces the MPI layer around the path (src/Mpi/MpiControl.cpp:1002-1157 ghost exchange,
+src/Mpi/MpiKDTreeDecomposition.cpp:56-277 domain decomposition):
+
+ * decomposition: rank r owns the tree-order slice [r*chunk, (r+1)*chunk) -- the leaves of the
+   balanced KD-tree below the r-th node of level log2(R), i.e. the reference's median-split KD
+   domains, with no separate decomposition step;
+ * every rank holds the (replicated) tree and all particle positions, so the density pass needs
+   no halo import at all; the force pass needs the post-density fields of the other slices:
+   ONE in-place ``all_gather_into_tensor`` per field on the device SoA arrays (9 doubles per
+   particle instead of the reference's 448-byte structs);
+ * results are identical to the single-GPU run (same tree, same kernels, same summation order).
+"""
+import numpy as np
+
+
+def slice_bounds(N, world_size, rank):
+    """tree-order slice of `rank`; chunk = ceil(N/R) so that every slice but the last is full."""
+    chunk = -(-int(N) // int(world_size))
+    lo = min(rank * chunk, N)
+    hi = min(lo + chunk, N)
+    return lo, hi, chunk
+
+
+def exchange_plan(N, world_size):
+    """[(lo, hi)] per rank plus the padded length the in-place all-gather works on."""
+    chunk = -(-int(N) // int(world_size))
+    return [slice_bounds(N, world_size, r)[:2] for r in range(world_size)], chunk * world_size
+
+
+class _CudaArray(object):
+    """__cuda_array_interface__ holder so torch can wrap a libgsph device array without a copy."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+class DomainDriver(object):
+    """Runs BuildTree / UpdateAllSphProperties / UpdateAllSph(Hydro)Forces across the ranks of a
+    torch.distributed process group (world_size 1 = plain single-GPU calls)."""
+
+    def __init__(self, tree, rank=0, world_size=1, group=None):
+        self.tree, self.rank, self.world, self.group = tree, rank, world_size, group
+        self.N = 0
+        self._fields = None
+
+    def BuildTree(self, rebuild, n, ntreebuildstep, ntreestockstep, timestep, parts=None):
+        self.tree.BuildTree(rebuild, n, ntreebuildstep, ntreestockstep, timestep, parts)
+        self.N = self.tree.Stats().Nhydro
+        if self.world > 1:
+            lo, hi, chunk = slice_bounds(self.N, self.world, self.rank)
+            self.lo, self.hi, self.chunk = lo, hi, chunk
+            self.tree.SetActiveSlice(lo, hi)
+            self._fields = None
+
+    def _wrap_fields(self):
+        import torch
+        if self._fields is None:
+            out = []
+            for name in ("h", "rho", "hrangesqd", "hfactor", "invomega", "zeta", "sound", "pressure", "u"):
+                ptr, cap = self.tree.DeviceField(name)
+                if cap < self.chunk * self.world:
+                    raise RuntimeError("device arrays too small for the padded all-gather")
+                out.append(torch.as_tensor(_CudaArray(ptr, self.chunk * self.world), device="cuda"))
+            self._fields = out
+        return self._fields
+
+    def UpdateAllSphProperties(self):
+        if self.world == 1:
+            self.tree.UpdateAllSphProperties()
+            return
+        import torch.distributed as dist
+        self.tree.DensityPass()
+        self.tree.Synchronize()
+        for t in self._wrap_fields():          # in-place all-gather: input = this rank's chunk of the output
+            dist.all_gather_into_tensor(t, t[self.rank * self.chunk:(self.rank + 1) * self.chunk], group=self.group)
+        import torch
+        torch.cuda.current_stream().synchronize()
+        self.tree.RefreshHmax()
+
+    def ZeroAccelerations(self):
+        self.tree.ZeroAccelerations()
+
+    def UpdateAllSphHydroForces(self):
+        self.tree.UpdateAllSphHydroForces()
+
+    def UpdateAllSphForces(self):
+        self.tree.UpdateAllSphForces()

@@ -25,9 +25,12 @@ class ParticleSet(object):
     """Host particle data.  ``data[name]`` is an (N,) or (N, ndim) numpy view; the views are
     strided when ``layout='aos'``."""
 
-    def __init__(self, N, ndim, layout="soa"):
+    def __init__(self, N, ndim, layout="soa", fields=None, alloc=None):
+        """fields: restrict a SoA set to these names (absent ones are passed as NULL = reference
+        constructor defaults); alloc(shape, dtype) -> ndarray lets the caller supply e.g. pinned memory."""
         self.N, self.ndim, self.layout = int(N), int(ndim), layout
         self.data = {}
+        alloc = alloc or (lambda shape, dtype: np.zeros(shape, dtype=dtype))
         if layout == "aos":
             # field order follows Particle -> SphParticle -> GradhSphParticle (Particle.h:134-368)
             dt = [("flags", "<u4"), ("ptype", "<i4"), ("iorig", "<i4"), ("sinkid", "<i4"),
@@ -47,17 +50,22 @@ class ParticleSet(object):
                 self.data[n] = self.records[n]
         else:
             self.records = None
+            want = (lambda n: True) if fields is None else (lambda n: n in fields)
             for n in _capi.VEC_FIELDS:
-                self.data[n] = np.zeros((self.N, ndim))
+                # component-major storage: every component is one contiguous array (stride 8)
+                if want(n):
+                    self.data[n] = alloc((ndim, self.N), np.float64).T
             for n in _capi.SCALAR_FIELDS:
-                self.data[n] = np.zeros(self.N)
+                if want(n):
+                    self.data[n] = alloc((self.N,), np.float64)
             for n in _INT:
-                self.data[n] = np.zeros(self.N, dtype=np.uint32 if n == "flags" else np.int32)
-        self.data["h"][...] = 1.0
-        self.data["invomega"][...] = 1.0
-        self.data["sinkid"][...] = -1
-        self.data["flags"][...] = _capi.FLAG_ACTIVE
-        self.data["iorig"][...] = np.arange(self.N)
+                if want(n):
+                    self.data[n] = alloc((self.N,), np.uint32 if n == "flags" else np.int32)
+        for n, v in (("h", 1.0), ("invomega", 1.0), ("sinkid", -1), ("flags", _capi.FLAG_ACTIVE)):
+            if n in self.data:
+                self.data[n][...] = v
+        if "iorig" in self.data:
+            self.data["iorig"][...] = np.arange(self.N)
 
     def __getitem__(self, k):
         return self.data[k]
@@ -72,7 +80,7 @@ class ParticleSet(object):
         its array between calls, GradhSph.cpp:83-111)."""
         pv = _capi.ParticleView()
         for n in _capi.VEC_FIELDS:
-            if only is not None and n not in only:
+            if (only is not None and n not in only) or n not in self.data:
                 continue
             a = self.data[n]
             for k in range(self.ndim):
@@ -80,7 +88,7 @@ class ParticleSet(object):
                 f.base = a.ctypes.data + k * a.strides[1]
                 f.stride = a.strides[0]
         for n in _capi.SCALAR_FIELDS + _INT:
-            if only is not None and n not in only:
+            if (only is not None and n not in only) or n not in self.data:
                 continue
             a = self.data[n]
             f = getattr(pv, n)
@@ -167,6 +175,30 @@ class GpuSphTree(object):
 
     def ToggleNeighbourCheck(self, do):
         self.neibcheck = bool(do)
+
+    # ---- multi-GPU plumbing (include/gsph.h "multi-GPU plumbing") ------------------------------------
+    def SetActiveSlice(self, lo, hi):
+        self._check(self._L.gsph_set_active_slice(self._h, int(lo), int(hi)))
+
+    def DensityPass(self):
+        self._check(self._L.gsph_density_pass(self._h))
+
+    def RefreshHmax(self):
+        self._check(self._L.gsph_refresh_hmax(self._h))
+
+    def DeviceField(self, name):
+        """-> (device pointer, capacity in elements) of a tree-order float64 array."""
+        ptr, cap = C.c_void_p(), C.c_int64()
+        self._check(self._L.gsph_device_field(self._h, _capi.DEVICE_FIELDS.index(name), C.byref(ptr), C.byref(cap)))
+        return ptr.value, cap.value
+
+    def TimerStart(self):
+        self._check(self._L.gsph_timer_start(self._h))
+
+    def TimerStop(self):
+        ms = C.c_float()
+        self._check(self._L.gsph_timer_stop(self._h, C.byref(ms)))
+        return ms.value
 
     def Synchronize(self):
         self._check(self._L.gsph_synchronize(self._h))

@@ -184,6 +184,32 @@ int gsph_update_hydro_forces(gsph_handle* h);
 int gsph_update_all_forces(gsph_handle* h, const double* stars, int Nstar);
 int gsph_get_hmax(gsph_handle* h, double* hmax);
 int gsph_synchronize(gsph_handle* h);
+/* CUDA-event stopwatch on the handle's stream (torch.cuda.Event only sees torch's streams):
+ * start records an event, stop records a second one, synchronises and returns the elapsed ms.     */
+int gsph_timer_start(gsph_handle* h);
+int gsph_timer_stop(gsph_handle* h, float* ms);
+
+/* ---- multi-GPU plumbing (one process per GPU) ----------------------------------------
+ * The reference shards the path by spatial domain decomposition over MPI ranks
+ * (src/Mpi/MpiKDTreeDecomposition.cpp:56-277) and exchanges ghost particles as whole 448-byte
+ * structs (src/Mpi/MpiControl.cpp:1002-1157).  Here every rank holds the tree and works on ONE
+ * contiguous slice of the tree order -- which IS the reference's KD domain decomposition, because
+ * the top log2(R) levels of the balanced KD-tree are exactly its median splits -- and the one
+ * exchange step per pass (post-density fields of the other slices) is an NCCL all-gather issued by
+ * the host layer on the device arrays exposed below.
+ *   gsph_set_active_slice : particles at tree positions [lo, hi) become the active targets, all
+ *                           others stay sources only (replaces the rank-ownership test).
+ *   gsph_density_pass     : gsph_update_properties without the tree refresh (h of the other
+ *                           slices is not known yet);  gsph_refresh_hmax does that refresh
+ *                           (KDTree::UpdateAllHmaxValues) after the exchange.
+ *   gsph_device_field     : device pointer of one tree-order SoA array (field = GSPH_DF_*),
+ *                           valid until the next gsph_upload that grows the arrays.              */
+enum { GSPH_DF_H = 0, GSPH_DF_RHO, GSPH_DF_HRANGESQD, GSPH_DF_HFACTOR, GSPH_DF_INVOMEGA, GSPH_DF_ZETA,
+       GSPH_DF_SOUND, GSPH_DF_PRESSURE, GSPH_DF_U, GSPH_DF_COUNT };
+int gsph_set_active_slice(gsph_handle* h, int64_t lo, int64_t hi);
+int gsph_density_pass(gsph_handle* h);
+int gsph_refresh_hmax(gsph_handle* h);
+int gsph_device_field(gsph_handle* h, int field, void** ptr, int64_t* capacity);
 
 /* ---- parity / debug access ---------------------------------------------------------------------
  * Neighbour lists as defined by NeighbourManager::TrimNeighbourLists (NeighbourManager.h:521):
@@ -223,6 +249,10 @@ typedef struct gsph_stats {
   int64_t kernel_launches;     /* CUDA kernels launched by this handle since create               */
   float   ms_build_tree, ms_properties, ms_forces;   /* device time of the last call of each       */
   float   ms_upload, ms_download;
+  /* device time of the most recent launch of each hot kernel (CUDA events on the handle's stream),
+     the denominators of bench.py's roofline line                                                  */
+  float   ms_kernel_density, ms_kernel_hydro, ms_kernel_gravity;
+  float   ms_tree_sort, ms_tree_levels, ms_tree_stock;   /* parts of the last rebuild              */
 } gsph_stats;
 int gsph_get_stats(gsph_handle* h, gsph_stats* st);
 

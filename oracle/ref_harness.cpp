@@ -25,6 +25,9 @@
 //            x[,y[,z]], vx[,vy[,vz]], m, h, u   (h<=0 everywhere => let the reference guess h)
 //  output  : OUTDIR/<stage>.<field>.npy   (numpy .npy v1.0, little endian)
 //  --bench : time STEPS passes of {BuildTree, ghosts, UpdateAllSphProperties, forces} with all
+//            particles active (with --perturb-h AMP the converged h is perturbed before each pass
+//            so that the h-rho iteration has real work, as after a time step);
+//            prints one JSON line with the wall-clock per block.
 //            particles active and print one JSON line with the wall-clock per block.
 //=================================================================================================
 #include <cstdio>
@@ -421,6 +424,7 @@ static int run(Parameters* params, const string& icfile, double perturb, const s
 #endif
     for (int s = 0; s < bench_steps; s++) {
       H.set_all_active();
+      if (perturb != 0.0) H.perturb_h(perturb);   // every step restarts from the same perturbed guess
       double a0 = now();
       H.sphneib->BuildTree(true, 0, sim->ntreebuildstep, sim->ntreestockstep, sim->timestep, H.sph);
       double a1 = now();

@@ -1,0 +1,160 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol include/gsph.h
+declares (no compute without a GPU), the .dat parameter mirror, the particle views, and the
+multi-GPU slice/exchange logic under a world_size-2 gloo group."""
+import ctypes as C
+import os
+import re
+import socket
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from gandalf_b200 import _capi
+    hdr = open(os.path.join(ROOT, "include", "gsph.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(gsph_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no prototypes found"
+    L = _capi.lib()
+    for name in sorted(declared):
+        assert hasattr(L, name), "libgsph.so does not export %s" % name
+    assert declared == set(_capi.EXPORTS)
+
+
+def test_struct_layouts_match_the_header():
+    """sizes computed by the C compiler from include/gsph.h equal the ctypes mirrors"""
+    from gandalf_b200 import _capi
+    src = '#include "gsph.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu\\n",sizeof(gsph_config),' \
+          'sizeof(gsph_particle_view),sizeof(gsph_stats),sizeof(gsph_tree_info),sizeof(gsph_field));return 0;}\n'
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")])
+        sizes = [int(x) for x in subprocess.check_output([os.path.join(d, "t")]).split()]
+    assert sizes == [C.sizeof(_capi.Config), C.sizeof(_capi.ParticleView), C.sizeof(_capi.Stats),
+                     C.sizeof(_capi.TreeInfo), C.sizeof(_capi.Field)]
+
+
+def test_no_device_is_a_loud_error():
+    import gandalf_b200 as g
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(g.GsphError) as e:
+        g.GpuSphTree({"ndim": 3})
+    assert e.value.code == 2 and "no CPU fallback" in str(e.value)
+
+
+def test_kernel_tables_equal_oracle():
+    """parity stage P0: the six tabulated-kernel tables, bit for bit (host side, no device needed)"""
+    import oracle_py as orc
+    from gandalf_b200 import sphtree
+    for nd in (1, 2, 3):
+        for kn in ("m4", "quintic"):
+            p = orc.params_from_dict({"ndim": nd, "kernel": kn, "tabulated_kernel": 1})
+            for w in range(6):
+                assert np.array_equal(sphtree.kernel_table(nd, kn, w), orc.kernel_table(p, w)), (nd, kn, w)
+
+
+def test_parameter_file_parsing(tmp_path):
+    from gandalf_b200 import Parameters, config_from_params
+    f = tmp_path / "x.dat"
+    f.write_text(textwrap.dedent("""\
+        # comment line
+        Run id : run_id = TEST1
+        Dimensions :  ndim = 2
+        kernel = quintic
+        Tabulate : tabulated_kernel = 0
+        h_fac = 1.3
+        this line has no equals sign
+        : boundary_lhs[0] = periodic
+        boundary_rhs[0] = periodic
+        boxmin[0] = -0.5
+        boxmax[0] = 0.5
+        avisc = mon97
+        time_dependent_avisc = mm97
+        Nleafmax = 12
+        """))
+    p = Parameters().read_params_file(str(f))
+    assert p["run_id"] == "TEST1" and p["ndim"] == 2 and p["kernel"] == "quintic" and p["h_fac"] == 1.3
+    assert p["thetamaxsqd"] == 0.1 and p["multipole"] == "quadrupole"      # defaults (Parameters.cpp:309,313)
+    c = config_from_params(p)
+    assert (c.ndim, c.kernel, c.tabulated_kernel, c.Nleafmax) == (2, 1, 0, 12)
+    assert c.avisc == 2 and c.tdavisc == 1
+    assert c.boundary_lhs[0] == 1 and c.boundary_lhs[1] == 0 and c.boxmin[0] == -0.5
+
+
+def test_particle_views():
+    import gandalf_b200 as g
+    a = g.ParticleSet(7, 3, "aos")
+    assert a.records.dtype.itemsize == 448          # sizeof(GradhSphParticle<3>), SURVEY 8(a)
+    v = a.view()
+    assert v.m.stride == 448 and v.r[2].base - v.r[0].base == 16 and v.flags.stride == 448
+    s = g.ParticleSet(7, 2, "soa")
+    v = s.view()
+    assert v.r[0].stride == 8 and v.r[1].base - v.r[0].base == 7*8 and not v.r[2].base
+    s["r"][...] = np.arange(14).reshape(7, 2)
+    assert s["r"][3, 1] == 7
+    part = g.ParticleSet(7, 3, "soa", fields=("r", "m", "h"))
+    assert not part.view().v[0].base and part.view().m.base
+
+
+def test_slice_bounds_cover_everything():
+    from gandalf_b200 import domain
+    for N in (1, 7, 64, 1000003):
+        for R in (1, 2, 4, 8):
+            plan, padded = domain.exchange_plan(N, R)
+            assert plan[0][0] == 0 and plan[-1][1] == N and padded >= N and padded - N < R
+            for (a, b), (c, d) in zip(plan[:-1], plan[1:]):
+                assert b == c and a <= b
+
+
+_WORKER = r"""
+import os, sys
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["GSPH_ROOT"])
+from gandalf_b200 import domain
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+N = 1001
+lo, hi, chunk = domain.slice_bounds(N, world, rank)
+full = torch.full((chunk*world,), -1.0, dtype=torch.float64)
+full[lo:hi] = torch.arange(lo, hi, dtype=torch.float64)          # "post-density field" of my slice
+dist.all_gather_into_tensor(full, full[rank*chunk:(rank + 1)*chunk].clone())
+assert torch.equal(full[:N], torch.arange(N, dtype=torch.float64)), full
+t = torch.tensor([float(rank + 1)]); dist.all_reduce(t, op=dist.ReduceOp.MAX); assert t.item() == world
+dist.barrier()
+print("rank", rank, "ok")
+"""
+
+
+def test_exchange_step_world_size_2_gloo(tmp_path):
+    """the one exchange step per pass (in-place all-gather of tree-order slices) with 2 CPU ranks"""
+    w = tmp_path / "worker.py"
+    w.write_text(_WORKER)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    env = dict(os.environ, GSPH_ROOT=ROOT)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", str(port), str(w)],
+                         env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=300)
+    text = out.stdout.decode()
+    assert out.returncode == 0, text[-2000:]
+    assert "rank 0 ok" in text and "rank 1 ok" in text
+
+
+def test_reference_perturbation_hash():
+    """bench.py perturbs h with the same integer hash as oracle/ref_harness.cpp perturb_h"""
+    from gandalf_b200 import workloads
+    f = workloads.ref_perturb_factor(np.arange(5), 0.1)
+    want = []
+    for i in range(5):
+        x = (i*2654435761) & 0xFFFFFFFF
+        x ^= x >> 16; x = (x*2246822519) & 0xFFFFFFFF; x ^= x >> 13
+        want.append(1.0 + 0.1*(2.0*((x & 0xFFFFFF)/float(0x1000000)) - 1.0))
+    assert np.allclose(f, want, rtol=0, atol=0)
