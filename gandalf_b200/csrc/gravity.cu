@@ -10,12 +10,19 @@
  *                                                  src/Headers/NeighbourSearch.h:481-827
  *
  *  The reference decides the interaction list PER LEAF CELL (geometric MAC against the leaf's
- *  rcell/rmax/hmax) and, for fast multipoles, expands about the leaf's centre of mass; to give the
- *  same forces the GPU keeps that granularity: one warp per leaf.  The warp walks the tree
- *  cooperatively (32 nodes per step), writing accepted cells and direct-sum particles to its
- *  scratch lists; then the LANES run over the list entries, each lane accumulating the
- *  contributions to all (<= 8) particles of the leaf in registers, and warp-shuffle reductions
- *  produce the per-particle sums.
+ *  rcell/rmax/hmax) and, for fast multipoles, expands about the leaf's centre of mass; forces only
+ *  match if that granularity is kept.  A walk per leaf is latency bound on a GPU, so one warp takes
+ *  a COHORT of 8 neighbouring leaves (one KD-tree node 3 levels above the leaves) and walks the
+ *  tree ONCE for all of them: every stack entry carries an 8-bit mask of the leaves for which the
+ *  node is still undecided, the lane that tests a node evaluates the reference's opening criterion
+ *  separately (and exactly) for every leaf in the mask, and children inherit the mask of the
+ *  leaves that opened their parent.  Accepted cells and direct-sum leaves are queued in small
+ *  shared-memory buffers as (node, leaf-mask) and consumed as soon as a tile is full -- no
+ *  interaction list is ever written to HBM.  In the consumption phase the lanes are the TARGET
+ *  PARTICLES (4 lanes per leaf, T particles per lane): a lane streams the staged tile (broadcast
+ *  reads) and accumulates the entries whose mask contains its leaf.  For fast multipoles the four
+ *  lanes of a leaf share the cell entries and combine their partial Taylor coefficients with two
+ *  warp-shuffle steps.
  *
  *  Split with hydro.cu: a particle j of an opened leaf is a kernel-overlap neighbour of target i
  *  iff the reference's predicate holds (NeighbourManager.h:521); those pairs get the softened
@@ -24,278 +31,377 @@
  *=================================================================================================*/
 #include "device_common.cuh"
 
-#define GRAV_THREADS 128
+#define GRAV_THREADS 256
 #define GRAV_WARPS (GRAV_THREADS/32)
 #define GRAV_NT 8                      /* max particles per leaf on this path */
+#define GRAV_STACK 512                 /* (node, mask) pairs per warp */
+#define CELL_TILE 32
+#define CELL_BUF 64
+#define DIR_TILE 8
+#define DIR_BUF 40
+#define GRAV_LEAVES 8                  /* leaves per cohort: 4 lanes each */
 
 namespace {
 
-struct GravVisitor {
-  const TreeDev& T; const DevParams& dp;
-  double rc[3], rmax, hrangemax;
-  int32_t* cells; int ncells, cap_cells;
-  CandList& direct;
-  DevStatus* st;
-
-  __device__ __forceinline__ int test(int node, bool leaf) const
-  {
-    double dr[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) dr[k] = __dadd_rn(T.rcell[k][node], -rc[k]);
-    const double drsqd = dot_exact<3>(dr);
-    const double crmax = T.rmax[node], chmax = T.hmax[node];
-    const double a = __dadd_rn(__dadd_rn(crmax, rmax), hrangemax);
-    const double b = __dadd_rn(__dadd_rn(rmax, crmax), __dmul_rn(dp.kernrange, chmax));
-    if (drsqd <= __dmul_rn(a, a) || drsqd <= __dmul_rn(b, b)) return 1;       /* overlap: open  */
-    if (!(drsqd < T.cdistsqd[node])) return (leaf && T.count[node] == 1) ? 3 : 2;  /* MAC accepts */
-    return 1;                                                                  /* MAC opens      */
-  }
-  __device__ __forceinline__ bool emit(int node, int code, bool leaf, int lane)
-  {
-    const unsigned cm = __ballot_sync(FULLMASK, code == 2);
-    if (cm) {
-      const int n = __popc(cm);
-      if (ncells + n > cap_cells) {
-        if (lane == 0) { atomicExch(&st->err_cand_overflow, 2); }
-        return false;
-      }
-      if (code == 2) cells[ncells + __popc(cm & ((1u << lane) - 1u))] = node;
-      ncells += n;
-    }
-    return direct.append_leaf(T, node, (code == 1 && leaf) || code == 3, lane);
-  }
+struct WarpShared {
+  int2 stack[GRAV_STACK];
+  double leafgeom[GRAV_LEAVES][5];     /* rcell xyz, rmax, kernrange*hmax of the cohort's leaves */
+  int cell_node[CELL_BUF]; unsigned cell_mask[CELL_BUF];
+  int dir_node[DIR_BUF]; unsigned dir_mask[DIR_BUF];
+  double cell_data[CELL_TILE][9];      /* com xyz, m, q0..q4 */
+  double dir_data[DIR_TILE*GRAV_NT][5];/* x, y, z, m, hrangesqd */
+  int dir_count[DIR_TILE];
 };
 
-struct FastMp { double ac[3], dphi[3], q[6], pot; };
+struct FastMp { double ac[3], q[6], pot; };   /* dphi == ac for HoT = false */
 
-template <int MULTIPOLE>
+template <int MULTIPOLE, int T>
 __global__ void __launch_bounds__(GRAV_THREADS)
-gravity_kernel(PartView P, TreeDev tree, DevParams dp, int* work_counter, int32_t* lists_all,
-               int cap_cells, int cap_direct, DevStatus* st, uint8_t* done)
+gravity_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* work_counter,
+               DevStatus* st, uint8_t* done)
 {
-  extern __shared__ int smem_i[];
+  extern __shared__ char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int* stack = smem_i + warp*WALK_STACK_CAP;
-  const int gwarp = blockIdx.x*GRAV_WARPS + warp;
-  int32_t* cells = lists_all + (size_t) gwarp*(cap_cells + cap_direct);
-  int32_t* dlist = cells + cap_cells;
-  const int nleaf = 1 << tree.ltot;
-  unsigned long long loc_direct = 0, loc_cells = 0, loc_leaf = 0;
+  WarpShared& S = reinterpret_cast<WarpShared*>(smem_raw)[warp];
+  const int leaf0 = (1 << tree.ltot) - 1;
+  const int ncohort = 1 << cohort_level;
+  const int nl = 1 << (tree.ltot - cohort_level);          /* leaves per cohort (<= 8) */
+  const int myl = lane >> 2, sub = lane & 3;               /* my leaf inside the cohort, my slot */
+  constexpr bool FAST = (MULTIPOLE == GSPH_MULTIPOLE_FAST_MONOPOLE || MULTIPOLE == GSPH_MULTIPOLE_FAST_QUADRUPOLE);
+  constexpr bool QUAD = (MULTIPOLE == GSPH_MULTIPOLE_QUADRUPOLE || MULTIPOLE == GSPH_MULTIPOLE_FAST_QUADRUPOLE);
+  unsigned long long loc_direct = 0, loc_cells = 0, loc_part = 0;
 
   while (true) {
-    int g = 0;
-    if (lane == 0) g = atomicAdd(work_counter, 1);
-    g = __shfl_sync(FULLMASK, g, 0);
-    if (g >= nleaf) break;
-    const int node = nleaf - 1 + g;
-    const int first = tree.first[node], cnt = tree.count[node];
-    if (cnt == 0 || tree.nactive[node] == 0 || done[g]) continue;
+    int c = 0;
+    if (lane == 0) c = atomicAdd(work_counter, 1);
+    c = __shfl_sync(FULLMASK, c, 0);
+    if (c >= ncohort) break;
+    const int cnode = ncohort - 1 + c;
+    if (tree.count[cnode] == 0 || tree.nactive[cnode] == 0 || done[c]) continue;
 
-    CandList dl{dlist, cap_direct, 0, st};
-    GravVisitor V{tree, dp, {tree.rcell[0][node], tree.rcell[1][node], tree.rcell[2][node]},
-                  tree.rmax[node], __dmul_rn(dp.kernrange, tree.hmax[node]), cells, 0, cap_cells, dl, st};
-    if (!warp_walk(tree, stack, V, st)) continue;
-    const int ncells = V.ncells, ndirect = dl.n;
-    __syncwarp();
-
-    /* targets (uniform across the warp) */
-    double x[GRAV_NT][3], hr2[GRAV_NT];
-    double ax[GRAV_NT], ay[GRAV_NT], az[GRAV_NT], pot[GRAV_NT];
-#pragma unroll
-    for (int t = 0; t < GRAV_NT; t++) {
-      const int i = first + (t < cnt ? t : 0);
-      x[t][0] = P.f[F_RX][i]; x[t][1] = P.f[F_RY][i]; x[t][2] = P.f[F_RZ][i];
-      hr2[t] = P.f[F_HR2][i];
-      ax[t] = ay[t] = az[t] = pot[t] = 0.0;
+    /* ---- this lane's leaf and target particles ------------------------------------------------------*/
+    const int myleaf = ((cnode + 1) << (tree.ltot - cohort_level)) - 1 + myl;    /* heap id */
+    int first = 0, cnt = 0;
+    bool leaf_live = false;
+    if (myl < nl) {
+      first = tree.first[myleaf]; cnt = tree.count[myleaf];
+      leaf_live = cnt > 0 && tree.nactive[myleaf] > 0;
     }
-
-    /* ---- direct sum, ComputeDirectGravForces GradhSph.cpp:657-690 ------------------------------*/
-    for (int k = lane; k < ndirect; k += 32) {
-      const int j = dlist[k];
-      if (((unsigned) P.i[I_FLAGS][j]) & GSPH_FLAG_DEAD) continue;
-      const double xj = P.f[F_RX][j], yj = P.f[F_RY][j], zj = P.f[F_RZ][j];
-      const double mj = P.f[F_M][j], hr2j = P.f[F_HR2][j];
+    double x[T][3], hr2[T], ax[T], ay[T], az[T], pot[T];
+    bool tlive[T];
 #pragma unroll
-      for (int t = 0; t < GRAV_NT; t++) {
-        if (t >= cnt) break;
-        double dr[3] = {xj - x[t][0], yj - x[t][1], zj - x[t][2]};
-        const double d2 = dot_exact<3>(dr);
-        if (d2 < hr2[t] || d2 < hr2j) continue;            /* kernel-overlap pair: hydro.cu */
-        const double inv = rsqrt(d2 + GSPH_SMALL);
-        const double f = mj*inv*inv*inv;
-        ax[t] += f*dr[0]; ay[t] += f*dr[1]; az[t] += f*dr[2];
-        pot[t] += mj*inv;
+    for (int t = 0; t < T; t++) {
+      const int o = sub + 4*t;
+      tlive[t] = leaf_live && o < cnt;
+      x[t][0] = x[t][1] = x[t][2] = 0.0; hr2[t] = 0.0; ax[t] = ay[t] = az[t] = pot[t] = 0.0;
+      if (tlive[t]) {
+        x[t][0] = P.f[F_RX][first + o]; x[t][1] = P.f[F_RY][first + o]; x[t][2] = P.f[F_RZ][first + o];
+        hr2[t] = P.f[F_HR2][first + o];
       }
     }
-
-    /* ---- cells ------------------------------------------------------------------------------------*/
-    if (MULTIPOLE == GSPH_MULTIPOLE_MONOPOLE || MULTIPOLE == GSPH_MULTIPOLE_QUADRUPOLE) {
-      for (int k = lane; k < ncells; k += 32) {
-        const int c = cells[k];
-        const double cx = tree.com[0][c], cy = tree.com[1][c], cz = tree.com[2][c], cm = tree.m[c];
-        double q0 = 0, q1 = 0, q2 = 0, q3 = 0, q4 = 0;
-        if (MULTIPOLE == GSPH_MULTIPOLE_QUADRUPOLE) {
-          q0 = tree.q[0][c]; q1 = tree.q[1][c]; q2 = tree.q[2][c]; q3 = tree.q[3][c]; q4 = tree.q[4][c];
-        }
+    double rcom[3] = {0, 0, 0};
+    FastMp F;
+    F.pot = 0.0;
 #pragma unroll
-        for (int t = 0; t < GRAV_NT; t++) {
-          if (t >= cnt) break;
-          if (MULTIPOLE == GSPH_MULTIPOLE_MONOPOLE) {            /* NeighbourSearch.h:349-377 */
-            const double dx = cx - x[t][0], dy = cy - x[t][1], dz = cz - x[t][2];
-            const double d2 = dx*dx + dy*dy + dz*dz + GSPH_SMALL;
-            const double inv = rsqrt(d2);
-            const double f = cm*inv*inv*inv;
-            pot[t] += cm*inv;
-            ax[t] += f*dx; ay[t] += f*dy; az[t] += f*dz;
+    for (int k = 0; k < 3; k++) F.ac[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) F.q[k] = 0.0;
+    __syncwarp();
+    if (sub == 0 && myl < nl) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) S.leafgeom[myl][k] = leaf_live ? tree.rcell[k][myleaf] : 0.0;
+      S.leafgeom[myl][3] = leaf_live ? tree.rmax[myleaf] : 0.0;
+      S.leafgeom[myl][4] = leaf_live ? __dmul_rn(dp.kernrange, tree.hmax[myleaf]) : 0.0;
+    }
+    if (FAST && leaf_live) { rcom[0] = tree.com[0][myleaf]; rcom[1] = tree.com[1][myleaf]; rcom[2] = tree.com[2][myleaf]; }
+    const unsigned lb = __ballot_sync(FULLMASK, leaf_live && sub == 0);
+    unsigned rootmask = 0;
+#pragma unroll
+    for (int l = 0; l < GRAV_LEAVES; l++) rootmask |= ((lb >> (4*l)) & 1u) << l;
+    int ncell_mine = 0, ndir_mine = 0;
+
+    /* ---- consumption of queued entries ----------------------------------------------------------------*/
+    auto consume_cells = [&](int n) {
+      __syncwarp();
+      if (lane < n) {
+        const int cc = S.cell_node[lane];
+        S.cell_data[lane][0] = tree.com[0][cc]; S.cell_data[lane][1] = tree.com[1][cc];
+        S.cell_data[lane][2] = tree.com[2][cc]; S.cell_data[lane][3] = tree.m[cc];
+        if (QUAD) {
+#pragma unroll
+          for (int k = 0; k < 5; k++) S.cell_data[lane][4 + k] = tree.q[k][cc];
+        }
+      }
+      __syncwarp();
+      /* fast multipoles: the 4 lanes of a leaf take every 4th entry; otherwise every lane takes all */
+      for (int e = FAST ? sub : 0; e < n; e += FAST ? 4 : 1) {
+        if (!((S.cell_mask[e] >> myl) & 1u)) continue;
+        ncell_mine++;
+        const double cx = S.cell_data[e][0], cy = S.cell_data[e][1], cz = S.cell_data[e][2], cm = S.cell_data[e][3];
+        double q0 = 0, q1 = 0, q2 = 0, q3 = 0, q4 = 0;
+        if (QUAD) { q0 = S.cell_data[e][4]; q1 = S.cell_data[e][5]; q2 = S.cell_data[e][6]; q3 = S.cell_data[e][7]; q4 = S.cell_data[e][8]; }
+        if (FAST) {
+          /* Taylor coefficients about the leaf's centre of mass (NeighbourSearch.h:481-760) */
+          {
+            const double dx = cx - rcom[0], dy = cy - rcom[1], dz = cz - rcom[2];
+            const double inv = rsqrt(dx*dx + dy*dy + dz*dz);
+            const double inv2 = inv*inv;
+            const double mc = cm*inv2*inv;
+            F.pot += cm*inv;
+            F.ac[0] += mc*dx; F.ac[1] += mc*dy; F.ac[2] += mc*dz;
+            F.q[0] += mc*(3.0*dx*dx*inv2 - 1.0);
+            F.q[1] += mc*(3.0*dx*dy*inv2);
+            F.q[2] += mc*(3.0*dy*dy*inv2 - 1.0);
+            F.q[3] += mc*(3.0*dz*dx*inv2);
+            F.q[4] += mc*(3.0*dz*dy*inv2);
+            F.q[5] += mc*(3.0*dz*dz*inv2 - 1.0);
           }
-          else {                                                  /* NeighbourSearch.h:384-475 */
-            const double dx = x[t][0] - cx, dy = x[t][1] - cy, dz = x[t][2] - cz;
-            const double d2 = dx*dx + dy*dy + dz*dz + GSPH_SMALL;
-            const double inv = rsqrt(d2);
+          if (QUAD) {
+            const double dx = rcom[0] - cx, dy = rcom[1] - cy, dz = rcom[2] - cz;
+            const double inv = rsqrt(dx*dx + dy*dy + dz*dz + GSPH_SMALL);
             const double inv2 = inv*inv;
             const double inv5 = inv2*inv2*inv;
-            const double f = cm*inv2*inv;
             const double qs = q0*dx*dx + q2*dy*dy - (q0 + q2)*dz*dz + 2.0*(q1*dx*dy + q3*dx*dz + q4*dy*dz);
             const double qf = 2.5*qs*inv5*inv2;
-            ax[t] += (q0*dx + q1*dy + q3*dz)*inv5 - qf*dx - f*dx;
-            ay[t] += (q1*dx + q2*dy + q4*dz)*inv5 - qf*dy - f*dy;
-            az[t] += (q3*dx + q4*dy - (q0 + q2)*dz)*inv5 - qf*dz - f*dz;
-            pot[t] += cm*inv + 0.5*qs*inv5;
+            double qx0 = (q0*dx + q1*dy + q3*dz)*inv5;
+            double qx1 = (q1*dx + q2*dy + q4*dz)*inv5;
+            double qx2 = (q3*dx + q4*dy - (q0 + q2)*dz)*inv5;
+            F.pot += 0.5*qs*inv5;
+            F.ac[0] += qx0 - qf*dx; F.ac[1] += qx1 - qf*dy; F.ac[2] += qx2 - qf*dz;
+            qx0 *= 5.0*inv2; qx1 *= 5.0*inv2; qx2 *= 5.0*inv2;
+            F.q[0] += qf*(7.0*dx*dx*inv2 - 1.0) - (qx0*dx + qx0*dx - q0*inv5);
+            F.q[1] += qf*(7.0*dx*dy*inv2) - (qx0*dy + qx1*dx - q1*inv5);
+            F.q[2] += qf*(7.0*dy*dy*inv2 - 1.0) - (qx1*dy + qx1*dy - q2*inv5);
+            F.q[3] += qf*(7.0*dx*dz*inv2) - (qx0*dz + qx2*dx - q3*inv5);
+            F.q[4] += qf*(7.0*dy*dz*inv2) - (qx1*dz + qx2*dy - q4*inv5);
+            F.q[5] += qf*(7.0*dz*dz*inv2 - 1.0) - (qx2*dz + qx2*dz + (q0 + q2)*inv5);
+          }
+        }
+        else {
+#pragma unroll
+          for (int t = 0; t < T; t++) {
+            if (!tlive[t]) continue;
+            const double dx = x[t][0] - cx, dy = x[t][1] - cy, dz = x[t][2] - cz;
+            const double inv = rsqrt(dx*dx + dy*dy + dz*dz + GSPH_SMALL);
+            const double inv2 = inv*inv;
+            const double f = cm*inv2*inv;
+            if (!QUAD) {                                       /* NeighbourSearch.h:349-377 */
+              pot[t] += cm*inv;
+              ax[t] -= f*dx; ay[t] -= f*dy; az[t] -= f*dz;
+            }
+            else {                                             /* NeighbourSearch.h:384-475 */
+              const double inv5 = inv2*inv2*inv;
+              const double qs = q0*dx*dx + q2*dy*dy - (q0 + q2)*dz*dz + 2.0*(q1*dx*dy + q3*dx*dz + q4*dy*dz);
+              const double qf = 2.5*qs*inv5*inv2;
+              ax[t] += (q0*dx + q1*dy + q3*dz)*inv5 - qf*dx - f*dx;
+              ay[t] += (q1*dx + q2*dy + q4*dz)*inv5 - qf*dy - f*dy;
+              az[t] += (q3*dx + q4*dy - (q0 + q2)*dz)*inv5 - qf*dz - f*dz;
+              pot[t] += cm*inv + 0.5*qs*inv5;
+            }
           }
         }
       }
-    }
-    else {
-      /* fast multipoles: Taylor expansion about the leaf's centre of mass, HoT = false
-         (NeighbourSearch.h:481-760); applied to each particle below (:768-827).           */
-      const double rcx = tree.com[0][node], rcy = tree.com[1][node], rcz = tree.com[2][node];
-      FastMp F;
-      F.pot = 0.0;
-#pragma unroll
-      for (int k = 0; k < 3; k++) { F.ac[k] = 0.0; F.dphi[k] = 0.0; }
-#pragma unroll
-      for (int k = 0; k < 6; k++) F.q[k] = 0.0;
-      for (int k = lane; k < ncells; k += 32) {
-        const int c = cells[k];
-        const double cm = tree.m[c];
-        {
-          const double dx = tree.com[0][c] - rcx, dy = tree.com[1][c] - rcy, dz = tree.com[2][c] - rcz;
-          const double inv = rsqrt(dx*dx + dy*dy + dz*dz);
-          const double inv2 = inv*inv;
-          const double mc = cm*inv2*inv;
-          F.pot += cm*inv;
-          F.ac[0] += mc*dx; F.ac[1] += mc*dy; F.ac[2] += mc*dz;
-          F.dphi[0] += mc*dx; F.dphi[1] += mc*dy; F.dphi[2] += mc*dz;
-          F.q[0] += mc*(3.0*dx*dx*inv2 - 1.0);
-          F.q[1] += mc*(3.0*dx*dy*inv2);
-          F.q[2] += mc*(3.0*dy*dy*inv2 - 1.0);
-          F.q[3] += mc*(3.0*dz*dx*inv2);
-          F.q[4] += mc*(3.0*dz*dy*inv2);
-          F.q[5] += mc*(3.0*dz*dz*inv2 - 1.0);
-        }
-        if (MULTIPOLE == GSPH_MULTIPOLE_FAST_QUADRUPOLE) {
-          const double q0 = tree.q[0][c], q1 = tree.q[1][c], q2 = tree.q[2][c], q3 = tree.q[3][c],
-                       q4 = tree.q[4][c];
-          const double dx = rcx - tree.com[0][c], dy = rcy - tree.com[1][c], dz = rcz - tree.com[2][c];
-          const double d2 = dx*dx + dy*dy + dz*dz + GSPH_SMALL;
-          const double inv = rsqrt(d2);
-          const double inv2 = inv*inv;
-          const double inv5 = inv2*inv2*inv;
-          const double qs = q0*dx*dx + q2*dy*dy - (q0 + q2)*dz*dz + 2.0*(q1*dx*dy + q3*dx*dz + q4*dy*dz);
-          const double qf = 2.5*qs*inv5*inv2;
-          double qx0 = (q0*dx + q1*dy + q3*dz)*inv5;
-          double qx1 = (q1*dx + q2*dy + q4*dz)*inv5;
-          double qx2 = (q3*dx + q4*dy - (q0 + q2)*dz)*inv5;
-          F.pot += 0.5*qs*inv5;
-          F.ac[0] += qx0 - qf*dx; F.ac[1] += qx1 - qf*dy; F.ac[2] += qx2 - qf*dz;
-          F.dphi[0] += qx0 - qf*dx; F.dphi[1] += qx1 - qf*dy; F.dphi[2] += qx2 - qf*dz;
-          qx0 *= 5.0*inv2; qx1 *= 5.0*inv2; qx2 *= 5.0*inv2;
-          F.q[0] += qf*(7.0*dx*dx*inv2 - 1.0);
-          F.q[1] += qf*(7.0*dx*dy*inv2);
-          F.q[2] += qf*(7.0*dy*dy*inv2 - 1.0);
-          F.q[3] += qf*(7.0*dx*dz*inv2);
-          F.q[4] += qf*(7.0*dy*dz*inv2);
-          F.q[5] += qf*(7.0*dz*dz*inv2 - 1.0);
-          F.q[0] -= qx0*dx + qx0*dx - q0*inv5;
-          F.q[1] -= qx0*dy + qx1*dx - q1*inv5;
-          F.q[2] -= qx1*dy + qx1*dy - q2*inv5;
-          F.q[3] -= qx0*dz + qx2*dx - q3*inv5;
-          F.q[4] -= qx1*dz + qx2*dy - q4*inv5;
-          F.q[5] -= qx2*dz + qx2*dz + (q0 + q2)*inv5;
-        }
-      }
-      F.pot = warp_sum(F.pot);
-#pragma unroll
-      for (int k = 0; k < 3; k++) { F.ac[k] = warp_sum(F.ac[k]); F.dphi[k] = warp_sum(F.dphi[k]); }
-#pragma unroll
-      for (int k = 0; k < 6; k++) F.q[k] = warp_sum(F.q[k]);
-      if (lane == 0) {
-#pragma unroll
-        for (int t = 0; t < GRAV_NT; t++) {
-          const double dx = x[t][0] - rcx, dy = x[t][1] - rcy, dz = x[t][2] - rcz;
-          ax[t] += F.ac[0] + F.q[0]*dx + F.q[1]*dy + F.q[3]*dz;
-          ay[t] += F.ac[1] + F.q[1]*dx + F.q[2]*dy + F.q[4]*dz;
-          az[t] += F.ac[2] + F.q[3]*dx + F.q[4]*dy + F.q[5]*dz;
-          pot[t] += F.pot + F.dphi[0]*dx + F.dphi[1]*dy + F.dphi[2]*dz;
-        }
-      }
-    }
+      __syncwarp();
+    };
 
-    /* ---- reduce over lanes and add to the particles (GradhSphTree.cpp:610-620) -------------------*/
-    double outx = 0, outy = 0, outz = 0, outp = 0;
+    auto consume_direct = [&](int n0, int n) {
+      /* stage the particles of direct leaves [n0, n0+n), n <= DIR_TILE */
+      __syncwarp();
+      for (int s = lane; s < n*GRAV_NT; s += 32) {
+        const int e = s/GRAV_NT, k = s - e*GRAV_NT;
+        const int ln = S.dir_node[n0 + e];
+        const int lf = tree.first[ln], lc = tree.count[ln];
+        if (k == 0) S.dir_count[e] = lc;
+        if (k < lc) {
+          const int j = lf + k;
+          const bool dead = ((unsigned) P.i[I_FLAGS][j]) & GSPH_FLAG_DEAD;
+          S.dir_data[s][0] = P.f[F_RX][j]; S.dir_data[s][1] = P.f[F_RY][j]; S.dir_data[s][2] = P.f[F_RZ][j];
+          S.dir_data[s][3] = dead ? 0.0 : P.f[F_M][j]; S.dir_data[s][4] = dead ? -1.0 : P.f[F_HR2][j];
+        }
+      }
+      __syncwarp();
+      for (int e = 0; e < n; e++) {
+        if (!((S.dir_mask[n0 + e] >> myl) & 1u)) continue;
+        const int lc = S.dir_count[e];
+        if (sub == 0) ndir_mine += lc;
+        for (int k = 0; k < lc; k++) {
+          const double* pj = S.dir_data[e*GRAV_NT + k];
+          const double xj = pj[0], yj = pj[1], zj = pj[2], mj = pj[3], hr2j = pj[4];
 #pragma unroll
-    for (int t = 0; t < GRAV_NT; t++) {
-      const double sx = warp_sum(ax[t]), sy = warp_sum(ay[t]), sz = warp_sum(az[t]), sp = warp_sum(pot[t]);
-      if (lane == t) { outx = sx; outy = sy; outz = sz; outp = sp; }
+          for (int t = 0; t < T; t++) {
+            double dr[3] = {xj - x[t][0], yj - x[t][1], zj - x[t][2]};
+            const double d2 = dot_exact<3>(dr);
+            if (!tlive[t] || d2 < hr2[t] || d2 < hr2j) continue;   /* kernel-overlap pair: hydro.cu */
+            const double inv = rsqrt(d2 + GSPH_SMALL);              /* ComputeDirectGravForces */
+            const double f = mj*inv*inv*inv;
+            ax[t] += f*dr[0]; ay[t] += f*dr[1]; az[t] += f*dr[2];
+            pot[t] += mj*inv;
+          }
+        }
+      }
+      __syncwarp();
+    };
+
+    /* ---- masked cohort walk ------------------------------------------------------------------------*/
+    int sp = 0, ncb = 0, ndb = 0;
+    bool failed = false;
+    if (rootmask) {
+      if (lane == 0) S.stack[0] = make_int2(0, (int) rootmask);
+      sp = 1;
     }
-    if (lane < cnt) {
-      const int i = first + lane;
+    __syncwarp();
+    while (sp > 0) {
+      const int take = sp < 32 ? sp : 32;
+      int node = -1; unsigned mask = 0;
+      if (lane < take) { const int2 e = S.stack[sp - 1 - lane]; node = e.x; mask = (unsigned) e.y; }
+      sp -= take;
+      __syncwarp();
+      unsigned open_mask = 0, acc_mask = 0;
+      bool isleaf = false; int ncount = 0;
+      if (node >= 0) {
+        ncount = tree.count[node];
+        isleaf = node >= leaf0;
+        if (ncount > 0) {
+          const double rx = tree.rcell[0][node], ry = tree.rcell[1][node], rz = tree.rcell[2][node];
+          const double crmax = tree.rmax[node], cdist = tree.cdistsqd[node];
+          const double chr = __dmul_rn(dp.kernrange, tree.hmax[node]);
+#pragma unroll
+          for (int l = 0; l < GRAV_LEAVES; l++) {
+            if (!((mask >> l) & 1u)) continue;
+            double dr[3];
+            dr[0] = __dadd_rn(rx, -S.leafgeom[l][0]); dr[1] = __dadd_rn(ry, -S.leafgeom[l][1]);
+            dr[2] = __dadd_rn(rz, -S.leafgeom[l][2]);
+            const double drsqd = dot_exact<3>(dr);
+            const double rmax = S.leafgeom[l][3];
+            const double a = __dadd_rn(__dadd_rn(crmax, rmax), S.leafgeom[l][4]);
+            const double b = __dadd_rn(__dadd_rn(rmax, crmax), chr);
+            /* Tree.cpp:660-731: overlap -> open; else MAC (Tree.h:413-432 geometric: open iff drsqd < cdistsqd) */
+            if (drsqd <= __dmul_rn(a, a) || drsqd <= __dmul_rn(b, b) || drsqd < cdist) open_mask |= 1u << l;
+            else acc_mask |= 1u << l;
+          }
+        }
+      }
+      /* children of opened internal nodes */
+      const bool push = open_mask && !isleaf;
+      const unsigned pm = __ballot_sync(FULLMASK, push);
+      const int npush = __popc(pm);
+      if (sp + 2*npush > GRAV_STACK) { failed = true; break; }
+      if (push) {
+        const int off = __popc(pm & ((1u << lane) - 1u));
+        S.stack[sp + 2*off] = make_int2(2*node + 2, (int) open_mask);
+        S.stack[sp + 2*off + 1] = make_int2(2*node + 1, (int) open_mask);
+      }
+      sp += 2*npush;
+      /* queue accepted cells / direct leaves */
+      unsigned dmask = isleaf ? open_mask : 0u;
+      unsigned cmask = acc_mask;
+      if (isleaf && ncount == 1) { dmask |= acc_mask; cmask = 0u; }     /* Tree.cpp:698-703 */
+      const unsigned cb = __ballot_sync(FULLMASK, cmask != 0u);
+      const unsigned db = __ballot_sync(FULLMASK, dmask != 0u);
+      if (cmask) { const int o = ncb + __popc(cb & ((1u << lane) - 1u)); S.cell_node[o] = node; S.cell_mask[o] = cmask; }
+      if (dmask) { const int o = ndb + __popc(db & ((1u << lane) - 1u)); S.dir_node[o] = node; S.dir_mask[o] = dmask; }
+      ncb += __popc(cb); ndb += __popc(db);
+      __syncwarp();
+      if (ncb >= CELL_TILE) {
+        consume_cells(CELL_TILE);
+        const int rest = ncb - CELL_TILE;
+        int tn = 0; unsigned tm = 0;
+        if (lane < rest) { tn = S.cell_node[CELL_TILE + lane]; tm = S.cell_mask[CELL_TILE + lane]; }
+        __syncwarp();
+        if (lane < rest) { S.cell_node[lane] = tn; S.cell_mask[lane] = tm; }
+        ncb = rest;
+        __syncwarp();
+      }
+      while (ndb >= DIR_TILE) {
+        consume_direct(ndb - DIR_TILE, DIR_TILE);
+        ndb -= DIR_TILE;
+      }
+    }
+    if (failed) {
+      if (lane == 0) atomicExch(&st->err_stack_overflow, 1);
+      continue;
+    }
+    if (ncb > 0) consume_cells(ncb);
+    if (ndb > 0) consume_direct(0, ndb);
+
+    /* ---- combine the 4 partial expansions of a leaf, apply, add to the particles
+     *      (GradhSphTree.cpp:588-620) ---------------------------------------------------------------------*/
+    if (FAST) {
+#pragma unroll
+      for (int o = 1; o <= 2; o <<= 1) {
+        F.pot += __shfl_xor_sync(FULLMASK, F.pot, o);
+#pragma unroll
+        for (int k = 0; k < 3; k++) F.ac[k] += __shfl_xor_sync(FULLMASK, F.ac[k], o);
+#pragma unroll
+        for (int k = 0; k < 6; k++) F.q[k] += __shfl_xor_sync(FULLMASK, F.q[k], o);
+        ncell_mine += __shfl_xor_sync(FULLMASK, ncell_mine, o);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < T; t++) {
+      if (!tlive[t]) continue;
+      if (FAST) {
+        const double dx = x[t][0] - rcom[0], dy = x[t][1] - rcom[1], dz = x[t][2] - rcom[2];
+        ax[t] += F.ac[0] + F.q[0]*dx + F.q[1]*dy + F.q[3]*dz;
+        ay[t] += F.ac[1] + F.q[1]*dx + F.q[2]*dy + F.q[4]*dz;
+        az[t] += F.ac[2] + F.q[3]*dx + F.q[4]*dy + F.q[5]*dz;
+        pot[t] += F.pot + F.ac[0]*dx + F.ac[1]*dy + F.ac[2]*dz;
+      }
+      const int i = first + sub + 4*t;
       const unsigned fl = (unsigned) P.i[I_FLAGS][i];
       if ((fl & GSPH_FLAG_ACTIVE) && !(fl & GSPH_FLAG_DEAD)) {
-        P.f[F_AX][i] += outx; P.f[F_AY][i] += outy; P.f[F_AZ][i] += outz;
-        P.f[F_ATX][i] += outx; P.f[F_ATY][i] += outy; P.f[F_ATZ][i] += outz;
-        P.f[F_GPOT][i] += outp;
+        P.f[F_AX][i] += ax[t]; P.f[F_AY][i] += ay[t]; P.f[F_AZ][i] += az[t];
+        P.f[F_ATX][i] += ax[t]; P.f[F_ATY][i] += ay[t]; P.f[F_ATZ][i] += az[t];
+        P.f[F_GPOT][i] += pot[t];
       }
     }
-    if (lane == 0) done[g] = 1;
-    loc_direct += (unsigned long long) ndirect*cnt; loc_cells += (unsigned long long) ncells*cnt; loc_leaf += cnt;
+    if (leaf_live && sub == 0) {
+      loc_direct += (unsigned long long) ndir_mine*cnt; loc_cells += (unsigned long long) ncell_mine*cnt;
+      loc_part += cnt;
+    }
+    __syncwarp();
+    if (lane == 0) done[c] = 1;
   }
+  loc_direct = (unsigned long long) warp_sum((double) loc_direct);
+  loc_cells = (unsigned long long) warp_sum((double) loc_cells);
+  loc_part = (unsigned long long) warp_sum((double) loc_part);
   if (lane == 0) {
     atomicAdd(&st->ndirect_sum, loc_direct); atomicAdd(&st->ncell_sum, loc_cells);
-    atomicAdd(&st->nleaf_grav, loc_leaf);
+    atomicAdd(&st->nleaf_grav, loc_part);
   }
 }
 
-template <int MULTIPOLE>
-int launch_gravity(gsph_handle* h)
+template <int MULTIPOLE, int T>
+int launch_gravity_t(gsph_handle* h)
 {
-  const size_t smem = GRAV_WARPS*WALK_STACK_CAP*sizeof(int);
-  auto kern = gravity_kernel<MULTIPOLE>;
+  const size_t smem = GRAV_WARPS*sizeof(WarpShared);
+  auto kern = gravity_kernel<MULTIPOLE, T>;
+  CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   int bps = 0;
   CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, GRAV_THREADS, smem));
   if (bps < 1) bps = 1;
   int blocks = h->sm_count*bps;
-  const int nleaf = 1 << h->tree.ltot;
-  const int need_blocks = (nleaf + GRAV_WARPS - 1)/GRAV_WARPS;
+  const int Lg = h->tree.ltot > 3 ? h->tree.ltot - 3 : 0;
+  const int ncohort = 1 << Lg;
+  const int need_blocks = (ncohort + GRAV_WARPS - 1)/GRAV_WARPS;
   if (blocks > need_blocks) blocks = need_blocks;
-  const int warps = blocks*GRAV_WARPS;
-  if (h->grav_cap_cells == 0) { h->grav_cap_cells = 8192; h->grav_cap_direct = 16384; }
-  if (warps > h->grav_warps || !h->gravlist) {
-    if (h->gravlist) cudaFree(h->gravlist);
-    h->gravlist = nullptr;
-    CUDA_TRY(h, cudaMalloc(&h->gravlist, (size_t) warps*(h->grav_cap_cells + h->grav_cap_direct)*sizeof(int32_t)));
-    h->grav_warps = warps;
-  }
   CUDA_TRY(h, cudaMemsetAsync(h->work_counter, 0, sizeof(int), h->stream));
   PartView P;
   for (int k = 0; k < NF_DOUBLE; k++) P.f[k] = h->P[k];
   for (int k = 0; k < NF_INT; k++) P.i[k] = h->PI[k];
   KernelTimer kt(h, 2);
-  kern<<<blocks, GRAV_THREADS, smem, h->stream>>>(P, h->tree, h->dp, h->work_counter, h->gravlist,
-                                                  (int) h->grav_cap_cells, (int) h->grav_cap_direct, h->status, h->done);
+  kern<<<blocks, GRAV_THREADS, smem, h->stream>>>(P, h->tree, h->dp, Lg, h->work_counter, h->status, h->done);
   h->stats.kernel_launches++;
   CUDA_TRY(h, cudaGetLastError());
   return GSPH_OK;
+}
+
+template <int MULTIPOLE>
+int launch_gravity(gsph_handle* h)
+{
+  /* largest leaf of the balanced tree: ceil(N / 2^ltot); 4 lanes per leaf -> T particles per lane */
+  const int64_t maxleaf = (h->N + ((int64_t) 1 << h->tree.ltot) - 1) >> h->tree.ltot;
+  return maxleaf <= 4 ? launch_gravity_t<MULTIPOLE, 1>(h) : launch_gravity_t<MULTIPOLE, 2>(h);
 }
 
 }  // namespace
