@@ -128,6 +128,13 @@ int ensure_capacity(gsph_handle* h, int64_t N)
   if (h->perm) cudaFree(h->perm);
   h->perm = nullptr;
   CUDA_TRY(h, cudaMalloc(&h->perm, cap*sizeof(int32_t)));
+  if (h->geo4) cudaFree(h->geo4); if (h->geoh) cudaFree(h->geoh); if (h->frec) cudaFree(h->frec);
+  if (h->hnew) cudaFree(h->hnew);
+  h->geo4 = h->geoh = h->frec = h->hnew = nullptr;
+  CUDA_TRY(h, cudaMalloc(&h->hnew, cap*sizeof(double)));
+  CUDA_TRY(h, cudaMalloc(&h->geo4, cap*4*sizeof(double)));
+  CUDA_TRY(h, cudaMalloc(&h->geoh, cap*4*sizeof(double)));
+  CUDA_TRY(h, cudaMalloc(&h->frec, cap*16*sizeof(double)));
   h->Ncap = cap;
   h->have_tree = false;
   return GSPH_OK;
@@ -235,6 +242,22 @@ int gsph_ensure_cand(gsph_handle* h, int warps, size_t cap_per_warp)
   return GSPH_OK;
 }
 
+int gsph_ensure_nlist(gsph_handle* h, int warps, size_t cap)
+{
+  if (cap == 0) cap = h->nlist_cap;
+  if (cap == 0) {
+    const char* e = getenv("GSPH_NLIST_CAP");
+    cap = e ? (size_t) atol(e) : (h->cfg.kernel == GSPH_KERNEL_M4 ? 256 : 768);
+  }
+  if (h->nlist && warps <= h->nlist_warps && cap <= h->nlist_cap) return GSPH_OK;
+  if (h->nlist) cudaFree(h->nlist);
+  h->nlist = nullptr;
+  if (warps < h->nlist_warps) warps = h->nlist_warps;
+  CUDA_TRY(h, cudaMalloc(&h->nlist, (size_t) warps*cap*32*sizeof(int32_t)));
+  h->nlist_warps = warps; h->nlist_cap = cap;
+  return GSPH_OK;
+}
+
 int gsph_check_status(gsph_handle* h, const char* where)
 {
   int rc = fetch_status(h);
@@ -322,7 +345,7 @@ void gsph_destroy(gsph_handle* h)
   auto fre = [](void* p) { if (p) cudaFree(p); };
   for (int f = 0; f < NF_DOUBLE; f++) { fre(h->H[f]); fre(h->P[f]); }
   for (int f = 0; f < NF_INT; f++) { fre(h->HI[f]); fre(h->PI[f]); }
-  fre(h->perm); fre(h->tables); fre(h->scratch); fre(h->cand); fre(h->gravlist); fre(h->status); fre(h->work_counter); fre(h->done);
+  fre(h->perm); fre(h->tables); fre(h->scratch); fre(h->cand); fre(h->gravlist); fre(h->status); fre(h->work_counter); fre(h->done); fre(h->geo4); fre(h->geoh); fre(h->frec); fre(h->nlist); fre(h->hnew);
   TreeDev& T = h->tree;
   fre(T.first); fre(T.count); fre(T.nactive); fre(T.m); fre(T.rmax); fre(T.hmax); fre(T.cdistsqd);
   for (int k = 0; k < 3; k++) { fre(T.bbmin[k]); fre(T.bbmax[k]); fre(T.hbmin[k]); fre(T.hbmax[k]); fre(T.rcell[k]); fre(T.com[k]); fre(T.vcom[k]); }
@@ -542,9 +565,15 @@ static int run_with_regrow(gsph_handle* h, const char* where, int (*pass)(gsph_h
     rc = gsph_check_status(h, where);
     if (rc) return rc;
     const DevStatus& s = *h->status_host;
-    if (!s.err_cand_overflow) return GSPH_OK;
-    if (s.err_cand_overflow == 2) { h->grav_cap_cells *= 2; h->grav_cap_direct *= 2; cudaFree(h->gravlist); h->gravlist = nullptr; }
-    else {
+    if (!s.err_cand_overflow && !s.err_nlist_overflow) return GSPH_OK;
+    if (s.err_nlist_overflow) {
+      const int w = h->nlist_warps; const size_t want = h->nlist_cap*2;
+      cudaFree(h->nlist); h->nlist = nullptr; h->nlist_warps = 0;
+      rc = gsph_ensure_nlist(h, w, want);
+      if (rc) return rc;
+      CUDA_TRY(h, cudaMemsetAsync(&h->status->err_nlist_overflow, 0, sizeof(int), h->stream));
+    }
+    if (s.err_cand_overflow) {
       size_t want = h->cand_cap_per_warp*2;
       while (want < s.cand_need) want *= 2;
       const int w = h->cand_warps;
@@ -574,6 +603,14 @@ int gsph_prepare_done_flags(gsph_handle* h)
   return GSPH_OK;
 }
 
+__global__ void commit_h_kernel(int N, const int32_t* flags, const double* __restrict__ hnew, double* __restrict__ h)
+{
+  const int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const unsigned f = (unsigned) flags[i];
+  if ((f & GSPH_FLAG_ACTIVE) && !(f & GSPH_FLAG_DEAD)) h[i] = hnew[i];
+}
+
 static int update_properties_impl(gsph_handle* h, bool refresh)
 {
   if (!h) return GSPH_EINVAL;
@@ -584,6 +621,14 @@ static int update_properties_impl(gsph_handle* h, bool refresh)
   rc = gsph_prepare_done_flags(h); if (rc) return rc;
   rc = run_with_regrow(h, "gsph_update_properties", pass_density, 0);
   if (rc) return rc;
+  {
+    /* the kernel leaves h untouched (a cohort may have to be redone with larger scratch and must
+       then start from the same guess): commit the new smoothing lengths now */
+    const int N = (int) h->N;
+    commit_h_kernel<<<(N + 255)/256, 256, 0, h->stream>>>(N, h->PI[I_FLAGS], h->hnew, h->P[F_H]);
+    h->stats.kernel_launches++;
+    CUDA_TRY(h, cudaGetLastError());
+  }
   if (refresh) {
     rc = gsph_tree_update_hmax(h);                      /* tree->UpdateAllHmaxValues, GradhSphTree.cpp:268 */
     if (rc) return rc;

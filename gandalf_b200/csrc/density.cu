@@ -6,13 +6,14 @@
  *            GradhSph::ComputeH                     src/GradhSph/GradhSph.cpp:142-326
  *            GradhSph::ComputeThermalProperties     src/GradhSph/GradhSph.cpp:335-347 (+ EOS classes)
  *
- *  Work decomposition: one warp per COHORT = one KD-tree node of <= 32*T particles (a contiguous
- *  slab in tree order).  The warp walks the tree once for the cohort's box grown by
- *  kernrange*hmax*1.05^n, writes the candidate slab indices to its scratch list, then every lane
- *  owns T target particles and streams the candidates through a 32-entry shared-memory tile
- *  (coalesced SoA loads, broadcast reads).  The fixed-point iteration of ComputeH runs per lane
- *  with exactly the reference's control flow; a lane whose h outgrows the search radius makes the
- *  cohort redo the walk with a larger radius (the reference's `hmax *= 1.05` loop).
+ *  Work decomposition: one warp per COHORT = one KD-tree node of <= 32 particles (a contiguous
+ *  slab in tree order), one target particle per lane.  The warp walks the tree once for the
+ *  cohort's box grown by kernrange*hmax*1.05^n, streams the candidate slabs through a 32-entry
+ *  shared-memory tile (coalesced loads of packed (x,y,z,m) records, broadcast reads) and lets every
+ *  lane compact the candidates inside its own search sphere into a private neighbour list; the
+ *  fixed-point iteration of ComputeH then runs per lane over that list only, with exactly the
+ *  reference's control flow.  A lane whose h outgrows the search radius makes the cohort redo the
+ *  walk with a larger radius (the reference's `hmax *= 1.05` loop).
  *=================================================================================================*/
 #include "device_common.cuh"
 
@@ -63,25 +64,38 @@ template <int NDIM> __device__ __forceinline__ double pow_ndim(double x)
   return x*x*x;
 }
 
-template <int NDIM, int KERN, bool TAB, int T>
+/*------------------------------------------------------------------------------------------------
+ * One warp per cohort (KD-tree node of <= 32 particles), one target per lane.
+ *  phase 1  the candidate slabs found by the walk are streamed once through a 32-entry shared
+ *           tile of packed (x,y,z,m) records; every lane appends the candidates inside its search
+ *           sphere kernrange*hmax to its own neighbour-id list (global scratch, [k][lane] layout:
+ *           coalesced rows).
+ *  phase 2  the ComputeH fixed-point iteration runs over the lane's own list only (gathering the
+ *           32-byte records through L1/L2), so every lane does useful work in every instruction.
+ *-----------------------------------------------------------------------------------------------*/
+template <int NDIM, int KERN, bool TAB>
 __global__ void __launch_bounds__(DENS_THREADS)
 density_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict__ gtables,
-               int cohort_level, int* work_counter, int32_t* cand_all, int cand_cap, DevStatus* st,
-               uint8_t* done)
+               const double2* __restrict__ geo4, int cohort_level, int* work_counter,
+               int32_t* cand_all, int cand_cap, int32_t* nlist_all, int nlist_cap, DevStatus* st,
+               uint8_t* done, double* __restrict__ hnew)
 {
   extern __shared__ double smem[];
   double* tab = smem;                                          /* 3 x 1000 (tabulated only) */
   double* tiles = smem + (TAB ? 3*GSPH_TABLE_RES : 0);         /* per warp: 32 x 4 doubles  */
-  int* stacks = (int*)(tiles + DENS_WARPS*32*4);               /* per warp: WALK_STACK_CAP  */
+  int* tilej = (int*)(tiles + DENS_WARPS*32*4);                /* per warp: 32 ids          */
+  int* stacks = tilej + DENS_WARPS*32;                         /* per warp: NB_WALK_STACK   */
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (TAB) {
     for (int i = threadIdx.x; i < 3*GSPH_TABLE_RES; i += blockDim.x) tab[i] = gtables[i];
     __syncthreads();
   }
   double* tile = tiles + warp*32*4;
-  int* stack = stacks + warp*WALK_STACK_CAP;
+  int* tj = tilej + warp*32;
+  int* stack = stacks + warp*NB_WALK_STACK;
   const int gwarp = blockIdx.x*DENS_WARPS + warp;
   int32_t* cand = cand_all + (size_t) gwarp*cand_cap;
+  int32_t* nlist = nlist_all + (size_t) gwarp*nlist_cap*32;
   const KernelEval<KERN, NDIM, TAB> K(dp, tab);
   const int ncohort = 1 << cohort_level;
   const double krs = dp.kernrangesqd;
@@ -101,32 +115,42 @@ density_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict_
     double cmin[3], cmax[3];
 #pragma unroll
     for (int k = 0; k < NDIM; k++) { cmin[k] = tree.bbmin[k][node]; cmax[k] = tree.bbmax[k][node]; }
-    const double hmax_cell = tree.hmax[node];
 
-    for (int t0 = 0; t0 < ccount && !overflow; t0 += 32*T) {
-      /* ---- targets of this lane -----------------------------------------------------------------*/
-      int ti[T]; bool live[T];
-      double x[T][3], mi[T], h0[T];
+    for (int t0 = 0; t0 < ccount && !overflow; t0 += 32) {
+      /* ---- the target of this lane ---------------------------------------------------------------*/
+      const int ti = cfirst + t0 + lane;
+      bool live = t0 + lane < ccount;
+      if (live) {
+        const unsigned fl = (unsigned) P.i[I_FLAGS][ti];
+        live = (fl & GSPH_FLAG_ACTIVE) && !(fl & GSPH_FLAG_DEAD);
+      }
+      double x[3] = {0, 0, 0}, mi = 1.0, h0 = 1.0;
+      if (live) {
 #pragma unroll
-      for (int t = 0; t < T; t++) {
-        const int o = t0 + t*32 + lane;
-        ti[t] = cfirst + o;
-        live[t] = o < ccount;
-        if (live[t]) {
-          const unsigned fl = (unsigned) P.i[I_FLAGS][ti[t]];
-          live[t] = (fl & GSPH_FLAG_ACTIVE) && !(fl & GSPH_FLAG_DEAD);
-        }
-        x[t][0] = x[t][1] = x[t][2] = 0.0; mi[t] = 1.0; h0[t] = 1.0;
-        if (live[t]) {
-#pragma unroll
-          for (int k = 0; k < NDIM; k++) x[t][k] = P.f[F_RX + k][ti[t]];
-          mi[t] = P.f[F_M][ti[t]]; h0[t] = P.f[F_H][ti[t]];
-        }
+        for (int k = 0; k < NDIM; k++) x[k] = P.f[F_RX + k][ti];
+        mi = P.f[F_M][ti]; h0 = P.f[F_H][ti];
       }
 
-      double hmax = hmax_cell;
+      /* The reference iterates per LEAF CELL with hmax = 1.05^n * cell.hmax as search radius and
+         as upper bisection bound, and redoes the whole leaf when one of its particles outgrows it
+         (GradhSphTree.cpp:144-240).  The same tree gives the same leaves here, so every lane
+         carries its own leaf's hmax and retry count; the walk uses the largest radius in the warp. */
+      int leafnode = -1 - lane;
+      double hmax_l = 0.0;
+      if (t0 + lane < ccount) {
+        int nd = node;
+        const int leaf0 = (1 << tree.ltot) - 1;
+        while (nd < leaf0) nd = (ti < tree.first[2*nd + 2]) ? 2*nd + 1 : 2*nd + 2;
+        leafnode = nd;
+        hmax_l = tree.hmax[nd];
+      }
+      bool fin = !live;
       for (int attempt = 0; ; attempt++) {
-        hmax = 1.05*hmax;                                      /* GradhSphTree.cpp:154 */
+        if (!fin) hmax_l = 1.05*hmax_l;                        /* GradhSphTree.cpp:154 */
+        double hmax = fin ? 0.0 : hmax_l;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) hmax = fmax(hmax, __shfl_xor_sync(FULLMASK, hmax, o));
+        if (!(hmax > 0.0)) break;                              /* every lane is finished */
         /* ---- walk: candidates whose leaf overlaps the grown cohort box --------------------------*/
         CandList cl{cand, cand_cap, 0, st};
         GatherVisitor<NDIM> V{tree, dp, cl, {0, 0, 0}, {0, 0, 0}};
@@ -138,125 +162,131 @@ density_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict_
           if (dp.periodic[k] && (V.smin[k] < dp.boxmin[k] || V.smax[k] > dp.boxmax[k] ||
                                  V.smax[k] - V.smin[k] > dp.boxhalf[k])) crosses = true;
         }
-        if (!warp_walk(tree, stack, V, st)) { overflow = true; break; }
+        if (!warp_walk<NB_WALK_STACK>(tree, stack, V, st)) { overflow = true; break; }
         const int ncand = cl.n;
+
+        /* ---- phase 1: per-lane neighbour lists within kernrange*hmax of the lane's leaf -------------*/
+        const double R2 = krs*hmax_l*hmax_l*(1.0 + 1.0e-12);
+        int n = 0; bool full = false;
+        for (int base = 0; base < ncand; base += 32) {
+          const int jl = base + lane;
+          __syncwarp();
+          if (jl < ncand) {
+            const int j = cand[jl];
+            const double2 a = geo4[2*(size_t) j], b = geo4[2*(size_t) j + 1];
+            tile[lane*4 + 0] = a.x; tile[lane*4 + 1] = a.y; tile[lane*4 + 2] = b.x; tile[lane*4 + 3] = b.y;
+            tj[lane] = j;
+          }
+          __syncwarp();
+          const int nt = min(32, ncand - base);
+          for (int jj = 0; jj < nt; jj++) {
+            const double2 a = *reinterpret_cast<const double2*>(tile + jj*4);
+            const double2 b = *reinterpret_cast<const double2*>(tile + jj*4 + 2);
+            double dr[3] = {0, 0, 0};
+            dr[0] = a.x - x[0];
+            if (NDIM > 1) dr[1] = a.y - x[1];
+            if (NDIM > 2) dr[2] = b.x - x[2];
+            if (crosses) wrap_dr<NDIM>(dp, dr);
+            const double d2 = dot_exact<NDIM>(dr);
+            if (!fin && d2 <= R2 && b.y > 0.0) {
+              if (n < nlist_cap) { nlist[(size_t) n*32 + lane] = tj[jj]; n++; }
+              else full = true;
+            }
+          }
+        }
+        if (__any_sync(FULLMASK, full)) {
+          if (lane == 0) atomicExch(&st->err_nlist_overflow, 1);
+          overflow = true; break;
+        }
+        int nmax = n;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(FULLMASK, nmax, o));
         loc_cand += (unsigned long long) ncand;
 
-        /* ---- ComputeH state per target ----------------------------------------------------------*/
-        double h[T], hlo[T], hup[T], rho[T], invom[T], zeta[T];
-        int iter[T]; int state[T];            /* 0 iterating, 1 converged/left loop, 2 need bigger list, 3 failed */
-#pragma unroll
-        for (int t = 0; t < T; t++) {
-          h[t] = h0[t]; hlo[t] = 0.0; hup[t] = hmax; iter[t] = 0; state[t] = live[t] ? 0 : 1;
-          rho[t] = invom[t] = zeta[t] = 0.0;
-        }
-        while (true) {
-          bool any = false;
-#pragma unroll
-          for (int t = 0; t < T; t++) any |= (state[t] == 0);
-          if (!__any_sync(FULLMASK, any)) break;
-
-          double invh[T], invhsqd[T];
-#pragma unroll
-          for (int t = 0; t < T; t++) {
-            invh[t] = 1.0/h[t]; invhsqd[t] = invh[t]*invh[t];
-            if (state[t] == 0) { rho[t] = 0.0; invom[t] = 0.0; zeta[t] = 0.0; }
-          }
-          /* ---- neighbour sums (GradhSph.cpp:197-204) over the candidate stream -----------------*/
-          for (int base = 0; base < ncand; base += 32) {
-            const int jl = base + lane;
-            double cx = 0.0, cy = 0.0, cz = 0.0, cm = 0.0;
-            if (jl < ncand) {
-              const int j = cand[jl];
-              const bool dead = ((unsigned) P.i[I_FLAGS][j]) & GSPH_FLAG_DEAD;
-              cx = P.f[F_RX][j];
-              if (NDIM > 1) cy = P.f[F_RY][j];
-              if (NDIM > 2) cz = P.f[F_RZ][j];
-              cm = dead ? 0.0 : P.f[F_M][j];
-            }
-            __syncwarp();
-            tile[lane*4 + 0] = cx; tile[lane*4 + 1] = cy; tile[lane*4 + 2] = cz; tile[lane*4 + 3] = cm;
-            __syncwarp();
-            const int nt = min(32, ncand - base);
-            for (int jj = 0; jj < nt; jj++) {
-              const double2 a = *reinterpret_cast<const double2*>(tile + jj*4);
-              const double2 b = *reinterpret_cast<const double2*>(tile + jj*4 + 2);
-#pragma unroll
-              for (int t = 0; t < T; t++) {
-                double dr[3] = {0, 0, 0};
-                dr[0] = a.x - x[t][0];
-                if (NDIM > 1) dr[1] = a.y - x[t][1];
-                if (NDIM > 2) dr[2] = b.x - x[t][2];
-                if (crosses) wrap_dr<NDIM>(dp, dr);
-                const double ssqd = __dmul_rn(invhsqd[t], dot_exact<NDIM>(dr));
-                if (ssqd < krs && state[t] == 0) {
-                  double w0, wom, wze;
-                  K.density_terms(ssqd, w0, wom, wze);
-                  rho[t] += b.y*w0;
-                  invom[t] += b.y*invh[t]*wom;
-                  zeta[t] += b.y*wze;
-                }
+        /* ---- phase 2: ComputeH (GradhSph.cpp:142-326) over the lane's own list ------------------------*/
+        double h = h0, hlo = 0.0, hup = hmax_l, rho = 0.0, invom = 0.0, zeta = 0.0;
+        int iter = 0, state = fin ? 1 : 0;     /* 0 iterating, 1 left the loop, 2 need bigger list, 3 failed */
+        while (__any_sync(FULLMASK, state == 0)) {
+          const double invh = 1.0/h, invhsqd = invh*invh;
+          double s_rho = 0.0, s_om = 0.0, s_ze = 0.0;
+          const int kend = state == 0 ? n : 0;
+          for (int k = 0; k < nmax; k++) {
+            if (k < kend) {
+              const int j = nlist[(size_t) k*32 + lane];
+              const double2 a = geo4[2*(size_t) j], b = geo4[2*(size_t) j + 1];
+              double dr[3] = {0, 0, 0};
+              dr[0] = a.x - x[0];
+              if (NDIM > 1) dr[1] = a.y - x[1];
+              if (NDIM > 2) dr[2] = b.x - x[2];
+              if (crosses) wrap_dr<NDIM>(dp, dr);
+              const double ssqd = __dmul_rn(invhsqd, dot_exact<NDIM>(dr));
+              if (ssqd < krs) {
+                double w0, wom, wze;
+                K.density_terms(ssqd, w0, wom, wze);
+                s_rho += b.y*w0;
+                s_om += b.y*invh*wom;
+                s_ze += b.y*wze;
               }
             }
           }
-          /* ---- fixed-point / bisection update (GradhSph.cpp:206-257) ----------------------------*/
-#pragma unroll
-          for (int t = 0; t < T; t++) {
-            if (state[t] != 0) continue;
-            iter[t]++;
-            const double hfac = pow_ndim<NDIM>(invh[t]);
-            rho[t] *= hfac; invom[t] *= hfac; zeta[t] *= invhsqd[t];
-            const double hnew = dp.h_fac*root_ndim<NDIM>(mi[t]/rho[t]);
-            if (rho[t] > 0.0 && h[t] > hlo[t] && fabs(h[t] - hnew)*invh[t] < dp.h_converge) { state[t] = 1; continue; }
-            if (iter[t] < 30) h[t] = hnew;
-            else if (iter[t] == 30) h[t] = 0.5*(hlo[t] + hup[t]);
-            else if (iter[t] < 150) {
-              if (rho[t] < GSPH_SMALL || h[t] > hnew) hup[t] = h[t]; else hlo[t] = h[t];
-              h[t] = 0.5*(hlo[t] + hup[t]);
+          if (state == 0) {
+            /* fixed-point / bisection update (GradhSph.cpp:206-257) */
+            iter++;
+            const double hfac = pow_ndim<NDIM>(invh);
+            rho = s_rho*hfac; invom = s_om*hfac; zeta = s_ze*invhsqd;
+            const double hnew = dp.h_fac*root_ndim<NDIM>(mi/rho);
+            if (rho > 0.0 && h > hlo && fabs(h - hnew)*invh < dp.h_converge) state = 1;
+            else {
+              if (iter < 30) h = hnew;
+              else if (iter == 30) h = 0.5*(hlo + hup);
+              else if (iter < 150) {
+                if (rho < GSPH_SMALL || h > hnew) hup = h; else hlo = h;
+                h = 0.5*(hlo + hup);
+              }
+              else state = 3;
+              if (state == 0) {
+                if (h > hmax_l) state = 2;
+                else if (!(h > hlo && h < hup)) state = 1;
+              }
             }
-            else { state[t] = 3; continue; }
-            if (h[t] > hmax) { state[t] = 2; continue; }
-            if (!(h[t] > hlo[t] && h[t] < hup[t])) state[t] = 1;
           }
         }
-        bool retry = false, failed = false;
-#pragma unroll
-        for (int t = 0; t < T; t++) { retry |= (state[t] == 2); failed |= (state[t] == 3); }
-        if (__any_sync(FULLMASK, failed)) {
+        if (__any_sync(FULLMASK, state == 3)) {
           if (lane == 0) atomicExch(&st->err_converge, 1);
           return;
         }
-        if (__any_sync(FULLMASK, retry)) {
+        /* a leaf is redone as a whole when one of its particles needs a larger list */
+        const unsigned peers = __match_any_sync(FULLMASK, leafnode);
+        const unsigned need = __ballot_sync(FULLMASK, state == 2);
+        const bool redo = (need & peers) != 0u;
+        if (need) {
           loc_retry++;
           if (attempt > 60) { if (lane == 0) atomicExch(&st->err_hsearch, 1); return; }
-          continue;
         }
         /* ---- normalise and store (GradhSph.cpp:260-317) ------------------------------------------*/
-#pragma unroll
-        for (int t = 0; t < T; t++) {
-          if (!live[t]) continue;
-          const double hf = fmax(dp.h_fac*root_ndim<NDIM>(mi[t]/rho[t]), hlo[t]);
+        if (!fin && !redo) {
+          const double hf = fmax(dp.h_fac*root_ndim<NDIM>(mi/rho), hlo);
           const double ih = 1.0/hf;
-          const int i = ti[t];
-          P.f[F_H][i] = hf;
-          P.f[F_RHO][i] = rho[t];
-          P.f[F_HFAC][i] = pow_ndim<NDIM>(ih)*ih;
-          P.f[F_HR2][i] = __dmul_rn(__dmul_rn(krs, hf), hf);
-          P.f[F_DIVV][i] = 0.0;
+          hnew[ti] = hf;                                        /* committed by the host after the pass */
+          P.f[F_RHO][ti] = rho;
+          P.f[F_HFAC][ti] = pow_ndim<NDIM>(ih)*ih;
+          P.f[F_HR2][ti] = __dmul_rn(__dmul_rn(krs, hf), hf);
+          P.f[F_DIVV][ti] = 0.0;
           double io = 1.0, ze = 0.0;
-          if (P.i[I_SINKID][i] == -1) {
-            const double deriv = -invndim*hf/rho[t];                /* h_rho_deriv, Sph.h:264-268 */
-            io = 1.0/(1.0 - deriv*invom[t]);
-            ze = deriv*zeta[t]*io;
+          if (P.i[I_SINKID][ti] == -1) {
+            const double deriv = -invndim*hf/rho;                /* h_rho_deriv, Sph.h:264-268 */
+            io = 1.0/(1.0 - deriv*invom);
+            ze = deriv*zeta*io;
           }
-          P.f[F_INVOMEGA][i] = io;
-          P.f[F_ZETA][i] = ze;
-          double u = P.f[F_U][i], cs, pr;
-          thermal(dp, rho[t], u, cs, pr);
-          P.f[F_U][i] = u; P.f[F_SOUND][i] = cs; P.f[F_PRESS][i] = pr;
-          loc_iter += iter[t]; loc_targets++; loc_itmax = max(loc_itmax, iter[t]);
+          P.f[F_INVOMEGA][ti] = io;
+          P.f[F_ZETA][ti] = ze;
+          double u = P.f[F_U][ti], cs, pr;
+          thermal(dp, rho, u, cs, pr);
+          P.f[F_U][ti] = u; P.f[F_SOUND][ti] = cs; P.f[F_PRESS][ti] = pr;
+          loc_iter += iter; loc_targets++; loc_itmax = max(loc_itmax, iter);
+          fin = true;
         }
-        break;
+        if (!need) break;
       }
     }
     __syncwarp();
@@ -278,11 +308,10 @@ density_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict_
 template <int NDIM, int KERN, bool TAB>
 int launch_density(gsph_handle* h)
 {
-  constexpr int T = 2;
-  const int Lc = cohort_level_for(h->N, h->tree.ltot, 32*T);
+  const int Lc = cohort_level_for(h->N, h->tree.ltot, 32);
   const size_t smem = (TAB ? 3*GSPH_TABLE_RES*sizeof(double) : 0) + DENS_WARPS*32*4*sizeof(double)
-                      + DENS_WARPS*WALK_STACK_CAP*sizeof(int);
-  auto kern = density_kernel<NDIM, KERN, TAB, T>;
+                      + DENS_WARPS*32*sizeof(int) + DENS_WARPS*NB_WALK_STACK*sizeof(int);
+  auto kern = density_kernel<NDIM, KERN, TAB>;
   CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   int bps = 0;
   CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, DENS_THREADS, smem));
@@ -293,13 +322,16 @@ int launch_density(gsph_handle* h)
   if (blocks > need_blocks) blocks = need_blocks;
   int rc = gsph_ensure_cand(h, blocks*DENS_WARPS, 0);
   if (rc) return rc;
+  rc = gsph_ensure_nlist(h, blocks*DENS_WARPS, 0);
+  if (rc) return rc;
   CUDA_TRY(h, cudaMemsetAsync(h->work_counter, 0, sizeof(int), h->stream));
   PartView P;
   for (int k = 0; k < NF_DOUBLE; k++) P.f[k] = h->P[k];
   for (int k = 0; k < NF_INT; k++) P.i[k] = h->PI[k];
   KernelTimer kt(h, 0);
-  kern<<<blocks, DENS_THREADS, smem, h->stream>>>(P, h->tree, h->dp, h->tables, Lc, h->work_counter,
-                                                  h->cand, (int) h->cand_cap_per_warp, h->status, h->done);
+  kern<<<blocks, DENS_THREADS, smem, h->stream>>>(P, h->tree, h->dp, h->tables, (const double2*) h->geo4, Lc,
+                                                  h->work_counter, h->cand, (int) h->cand_cap_per_warp,
+                                                  h->nlist, (int) h->nlist_cap, h->status, h->done, h->hnew);
   h->stats.kernel_launches++;
   CUDA_TRY(h, cudaGetLastError());
   return GSPH_OK;

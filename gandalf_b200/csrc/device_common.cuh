@@ -7,7 +7,7 @@
 #include "gsph_internal.cuh"
 
 #define FULLMASK 0xffffffffu
-#define WALK_STACK_CAP 1024          /* ints per warp */
+#define NB_WALK_STACK 512             /* ints per warp: neighbour walks (frontiers of a few hundred nodes) */
 
 struct PartView {
   double* f[NF_DOUBLE];
@@ -235,7 +235,7 @@ __device__ __forceinline__ bool boxes_overlap(const DevParams& dp, const double 
  * ComputeNeighbourAndGhostList and ComputeGravityInteractionAndGhostList
  * (src/Tree/Tree.cpp:291-381, :562-617, :628-735).
  *-----------------------------------------------------------------------------------------------*/
-template <class Visitor>
+template <int STACKCAP, class Visitor>
 __device__ __forceinline__ bool warp_walk(const TreeDev& T, int* stack, Visitor& V, DevStatus* st)
 {
   const int lane = threadIdx.x & 31;
@@ -255,7 +255,7 @@ __device__ __forceinline__ bool warp_walk(const TreeDev& T, int* stack, Visitor&
     const bool push = (code == 1) && !leaf;
     const unsigned pm = __ballot_sync(FULLMASK, push);
     const int npush = __popc(pm);
-    if (sp + 2*npush > WALK_STACK_CAP) {
+    if (sp + 2*npush > STACKCAP) {
       if (lane == 0) atomicExch(&st->err_stack_overflow, 1);
       return false;
     }

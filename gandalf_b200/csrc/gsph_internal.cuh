@@ -80,10 +80,10 @@ struct DevStatus {
   int err_stack_overflow;    /* walk stack too small                                           */
   int err_converge;          /* h-rho iteration did not converge (GradhSph.cpp:249-250)        */
   int err_hsearch;           /* search radius had to grow too often                            */
+  int err_nlist_overflow;    /* per-lane neighbour list too small                              */
   int density_retries;
   int hiter_max;
   int ngb_max;
-  int pad;
   unsigned long long hiter_sum, ngb_sum, cand_sum, ntarget, ndirect_sum, ncell_sum, nleaf_grav;
   unsigned long long cand_need;   /* largest candidate count requested */
 };
@@ -103,6 +103,12 @@ struct gsph_handle {
   double* P[NF_DOUBLE] = {0};   /* tree order */
   int32_t* PI[NF_INT] = {0};
   int32_t* perm = nullptr;      /* tree position -> host index */
+  /* packed tree-order records for the gather phases of the density / force kernels */
+  double* hnew = nullptr;       /* [N] h written by the density pass, committed when the pass succeeded */
+  double* geo4 = nullptr;       /* [N][4]  x, y, z, m          (density; m = 0 for dead particles)  */
+  double* geoh = nullptr;       /* [N][4]  x, y, z, hrangesqd  (force-pass predicate; dead: x = BIG) */
+  double* frec = nullptr;       /* [N][16] force record, 128 B: x y z vx | vy vz m 1/h | hfactor 1/rho
+                                   P*invomega/rho^2 sound | u alpha zeta (pressure|level)           */
   bool uploaded = false, have_tree = false, sorted_valid = false, all_active = true;
   bool density_done = false;
   bool slice_mode = false;   /* gsph_set_active_slice: inactive particles belong to other ranks */
@@ -113,6 +119,7 @@ struct gsph_handle {
   /* scratch */
   void* scratch = nullptr; size_t scratch_bytes = 0;          /* tree build temporaries          */
   int32_t* cand = nullptr; size_t cand_cap_per_warp = 0; int cand_warps = 0;
+  int32_t* nlist = nullptr; size_t nlist_cap = 0; int nlist_warps = 0;   /* per warp: [cap][32] neighbour ids */
   int32_t* gravlist = nullptr; size_t grav_cap_cells = 0, grav_cap_direct = 0; int grav_warps = 0;
   DevStatus* status = nullptr;  /* device */
   DevStatus* status_host = nullptr; /* pinned */
@@ -142,6 +149,8 @@ int gsph_run_neiblist(gsph_handle* h, int32_t* counts_dev, const int64_t* offset
 int gsph_run_gravity(gsph_handle* h);                                 /* gravity.cu */
 int gsph_check_status(gsph_handle* h, const char* where);             /* capi.cu    */
 int gsph_ensure_cand(gsph_handle* h, int warps, size_t cap_per_warp);
+int gsph_ensure_nlist(gsph_handle* h, int warps, size_t cap);
+int gsph_pack_geo4(gsph_handle* h);                                   /* tree.cu */
 
 struct KernelTimer {          /* brackets one launch (or group) with events; read back later */
   gsph_handle* h; int k;

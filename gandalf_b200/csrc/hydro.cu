@@ -9,24 +9,22 @@
  *            GradhSph::ComputeSphHydroGravForces      src/GradhSph/GradhSph.cpp:474-585
  *            GradhSph::ComputeSphGravForces           src/GradhSph/GradhSph.cpp:598-647
  *
- *  One warp per cohort (KD-tree node of <= 32*T particles).  The walk opens a node when
- *  cohort.bb overlaps node.hbox or cohort.hbox overlaps node.bb (scatter-gather), candidates are
- *  streamed through a shared-memory tile; the loading lane derives 1/h, 1/rho and
- *  P*invomega/rho^2 once per candidate.  Neighbour membership is the reference's predicate
+ *  One warp per cohort (KD-tree node of <= 32 particles), one target per lane.  The walk opens a
+ *  node when cohort.bb overlaps node.hbox or cohort.hbox overlaps node.bb (scatter-gather); the
+ *  candidate slabs are streamed through a shared-memory tile of packed (x,y,z,hrangesqd) records and
+ *  compacted into per-lane neighbour lists, over which the pair terms are then evaluated from packed
+ *  128-byte force records (1/h, 1/rho and P*invomega/rho^2 are derived once per particle by the
+ *  pack kernel).  Neighbour membership is the reference's predicate
  *      NOT (drsqd >= hrangesqd_i && drsqd >= hrangesqd_j)          NeighbourManager.h:521
  *  evaluated with the reference's rounding (no FMA contraction).
  *=================================================================================================*/
 #include "device_common.cuh"
 
-#define HYD_THREADS 128
+#define HYD_THREADS 256
 #define HYD_WARPS (HYD_THREADS/32)
 
 namespace {
 
-/* tile layout per warp: geom[32][4] = x,y,z,hr2 ; then SoA fields [NTF][32] */
-enum TileField { TF_VX, TF_VY, TF_VZ, TF_M, TF_INVH, TF_HFAC, TF_INVRHO, TF_PFAC, TF_SOUND, TF_U,
-                 TF_ALPHA, TF_PRESS, TF_ZETA, TF_LEVEL, NTF };
-#define TILE_DOUBLES (32*4 + NTF*32)
 
 template <int NDIM>
 struct ScatterGatherVisitor {
@@ -78,13 +76,43 @@ struct Target {
   int levelneib, nngb;
 };
 
+struct Neib {            /* one gathered force record (frec, 128 B) */
+  double v[3], m, invh, hfac, invrho, pfac, sound, u, alpha, zeta, press;
+  int level;
+};
+
+/* frec layout: 0 x 1 y 2 z 3 vx | 4 vy 5 vz 6 m 7 1/h | 8 hfactor 9 1/rho 10 P*invomega/rho^2 11 sound |
+ *              12 u 13 alpha 14 zeta 15 (pressure if acond = price2008, else level)                   */
+template <int NDIM>
+__global__ void pack_force_kernel(int N, PartView P, int price2008, double* __restrict__ geoh,
+                                  double* __restrict__ frec)
+{
+  const int p = blockIdx.x*blockDim.x + threadIdx.x;
+  if (p >= N) return;
+  const bool dead = ((unsigned) P.i[I_FLAGS][p]) & GSPH_FLAG_DEAD;
+  const double x = P.f[F_RX][p], y = NDIM > 1 ? P.f[F_RY][p] : 0.0, z = NDIM > 2 ? P.f[F_RZ][p] : 0.0;
+  const double h = P.f[F_H][p], rho = P.f[F_RHO][p], pr = P.f[F_PRESS][p];
+  double2* g = reinterpret_cast<double2*>(geoh) + 2*(size_t) p;
+  g[0] = make_double2(dead ? GSPH_BIG : x, y);
+  g[1] = make_double2(z, dead ? -1.0 : P.f[F_HR2][p]);
+  double2* r = reinterpret_cast<double2*>(frec) + 8*(size_t) p;
+  r[0] = make_double2(x, y);
+  r[1] = make_double2(z, P.f[F_VX][p]);
+  r[2] = make_double2(NDIM > 1 ? P.f[F_VY][p] : 0.0, NDIM > 2 ? P.f[F_VZ][p] : 0.0);
+  r[3] = make_double2(P.f[F_M][p], 1.0/h);
+  r[4] = make_double2(P.f[F_HFAC][p], 1.0/rho);
+  r[5] = make_double2((pr*P.f[F_INVOMEGA][p])/(rho*rho), P.f[F_SOUND][p]);
+  r[6] = make_double2(P.f[F_U][p], P.f[F_ALPHA][p]);
+  r[7] = make_double2(P.f[F_ZETA][p], price2008 ? pr : (double) P.i[I_LEVEL][p]);
+}
+
 /* One (target, neighbour) pair.  GRAV selects ComputeSphHydroGravForces (GradhSph.cpp:498-572),
  * otherwise ComputeSphHydroForces (:384-448); HYDRO = false gives ComputeSphGravForces (:610-645). */
 template <int NDIM, bool GRAV, bool HYDRO, class KE>
 __device__ __forceinline__ void pair_terms(const DevParams& dp, const KE& K, Target& t, double (&dr)[3],
-                                           double drsqd, const double* __restrict__ tf, int jj)
+                                           double drsqd, const Neib& nb)
 {
-  const double mj = tf[TF_M*32 + jj], invh_j = tf[TF_INVH*32 + jj], hfac_j = tf[TF_HFAC*32 + jj];
+  const double mj = nb.m, invh_j = nb.invh, hfac_j = nb.hfac;
   double drmag, dvdr = 0.0;
   if (!GRAV) {
     drmag = sqrt(drsqd);
@@ -104,28 +132,27 @@ __device__ __forceinline__ void pair_terms(const DevParams& dp, const KE& K, Tar
   const double wkerni = t.hfac*w1i, wkernj = hfac_j*w1j;
   if (HYDRO) {
 #pragma unroll
-    for (int k = 0; k < NDIM; k++) dvdr += (tf[(TF_VX + k)*32 + jj] - t.v[k])*dr[k];
-    const double invrho_j = tf[TF_INVRHO*32 + jj];
+    for (int k = 0; k < NDIM; k++) dvdr += (nb.v[k] - t.v[k])*dr[k];
+    const double invrho_j = nb.invrho;
     t.divv -= mj*dvdr*wkerni;
-    double paux = t.pfac*wkerni + tf[TF_PFAC*32 + jj]*wkernj;
+    double paux = t.pfac*wkerni + nb.pfac*wkernj;
     if (dvdr < 0.0) {
       const double winvrho = 0.25*(wkerni + wkernj)*(t.invrho + invrho_j);
       if (dp.avisc == GSPH_AVISC_MON97) {
-        const double vsignal = t.sound + tf[TF_SOUND*32 + jj] - dp.beta_visc*dp.alpha_visc*dvdr;
+        const double vsignal = t.sound + nb.sound - dp.beta_visc*dp.alpha_visc*dvdr;
         paux   -= dp.alpha_visc*vsignal*dvdr*winvrho;
         t.dudt -= 0.5*mj*dp.alpha_visc*vsignal*dvdr*dvdr*winvrho;
       }
       else if (dp.avisc == GSPH_AVISC_MON97MM97 || dp.avisc == GSPH_AVISC_MON97CD2010) {
-        const double alpha_mean = 0.5*(t.alpha + tf[TF_ALPHA*32 + jj]);
-        const double vsignal = t.sound + tf[TF_SOUND*32 + jj] - dp.beta_visc*alpha_mean*dvdr;
+        const double alpha_mean = 0.5*(t.alpha + nb.alpha);
+        const double vsignal = t.sound + nb.sound - dp.beta_visc*alpha_mean*dvdr;
         paux   -= alpha_mean*vsignal*dvdr*winvrho;
         t.dudt -= 0.5*mj*alpha_mean*vsignal*dvdr*dvdr*winvrho;
       }
       if (dp.acond == GSPH_ACOND_WADSLEY2008)
-        t.dudt += mj*dvdr*(tf[TF_U*32 + jj] - t.u)*(t.invrho*wkerni + invrho_j*wkernj);
+        t.dudt += mj*dvdr*(nb.u - t.u)*(t.invrho*wkerni + invrho_j*wkernj);
       else if (dp.acond == GSPH_ACOND_PRICE2008)
-        t.dudt += 0.5*mj*(t.u - tf[TF_U*32 + jj])*winvrho*(t.invrho + invrho_j)*
-          sqrt(fabs(t.press - tf[TF_PRESS*32 + jj]));
+        t.dudt += 0.5*mj*(t.u - nb.u)*winvrho*(t.invrho + invrho_j)*sqrt(fabs(t.press - nb.press));
     }
 #pragma unroll
     for (int k = 0; k < NDIM; k++) t.a[k] += mj*dr[k]*paux;
@@ -133,42 +160,51 @@ __device__ __forceinline__ void pair_terms(const DevParams& dp, const KE& K, Tar
   if (GRAV) {
     const double si = drmag*t.invh, sj = drmag*invh_j;
     const double gaux = 0.5*(t.invh*t.invh*K.wgrav(si) + t.zeta*wkerni +
-                             invh_j*invh_j*K.wgrav(sj) + tf[TF_ZETA*32 + jj]*wkernj);
+                             invh_j*invh_j*K.wgrav(sj) + nb.zeta*wkernj);
 #pragma unroll
     for (int k = 0; k < NDIM; k++) t.at[k] += mj*dr[k]*gaux;
     t.gpot += 0.5*mj*(t.invh*K.wpot(si) + invh_j*K.wpot(sj));
   }
-  if (HYDRO || !GRAV) {
-    const int lj = (int) tf[TF_LEVEL*32 + jj];
-    t.levelneib = max(t.levelneib, lj);
-  }
+  if (HYDRO || !GRAV) t.levelneib = max(t.levelneib, nb.level);
   t.nngb++;
 }
 
-template <int NDIM, int KERN, bool TAB, bool GRAV, bool HYDRO, int T>
+/*------------------------------------------------------------------------------------------------
+ * One warp per cohort (KD-tree node of <= 32 particles), one target per lane.
+ *  phase 1  stream the candidate slabs through a shared tile of packed (x,y,z,hrangesqd) records
+ *           and let every lane append the ids that satisfy the reference's neighbour predicate
+ *           (exact arithmetic) to its own list ([k][lane] rows in global scratch);
+ *  phase 2  every lane walks its own list, gathers the 128-byte force record of the neighbour and
+ *           evaluates the pair terms -- all 32 lanes busy in every instruction.
+ *-----------------------------------------------------------------------------------------------*/
+template <int NDIM, int KERN, bool TAB, bool GRAV, bool HYDRO>
 __global__ void __launch_bounds__(HYD_THREADS)
 hydro_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict__ gtables,
-             int cohort_level, int* work_counter, int32_t* cand_all, int cand_cap, DevStatus* st,
-             uint8_t* done)
+             const double2* __restrict__ geoh, const double2* __restrict__ frec,
+             int cohort_level, int* work_counter, int32_t* cand_all, int cand_cap,
+             int32_t* nlist_all, int nlist_cap, DevStatus* st, uint8_t* done)
 {
   extern __shared__ double smem[];
   constexpr int NTAB = TAB ? (GRAV ? 3 : 1) : 0;
   double* tab = smem;                                   /* w1 [, wgrav, wpot] */
-  double* tiles = smem + NTAB*GSPH_TABLE_RES;
-  int* stacks = (int*)(tiles + HYD_WARPS*TILE_DOUBLES);
+  double* tiles = smem + NTAB*GSPH_TABLE_RES;           /* per warp 32 x 4 doubles */
+  int* tilej = (int*)(tiles + HYD_WARPS*32*4);
+  int* stacks = tilej + HYD_WARPS*32;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (TAB) {
     for (int i = threadIdx.x; i < NTAB*GSPH_TABLE_RES; i += blockDim.x) tab[i] = gtables[3*GSPH_TABLE_RES + i];
     __syncthreads();
   }
-  double* geom = tiles + warp*TILE_DOUBLES;
-  double* tf = geom + 32*4;
-  int* stack = stacks + warp*WALK_STACK_CAP;
+  double* geom = tiles + warp*32*4;
+  int* tj = tilej + warp*32;
+  int* stack = stacks + warp*NB_WALK_STACK;
   const int gwarp = blockIdx.x*HYD_WARPS + warp;
   int32_t* cand = cand_all + (size_t) gwarp*cand_cap;
+  int32_t* nlist = nlist_all + (size_t) gwarp*nlist_cap*32;
   /* evaluator indexes tables as 3=w1, 4=wgrav, 5=wpot: rebase so that slot 3 is tab[0] */
   const KernelEval<KERN, NDIM, TAB> K(dp, tab - 3*GSPH_TABLE_RES);
   const int ncohort = 1 << cohort_level;
+  const bool price = dp.acond == GSPH_ACOND_PRICE2008;
   unsigned long long loc_ngb = 0, loc_cand = 0, loc_targets = 0; int loc_ngbmax = 0;
 
   while (true) {
@@ -188,96 +224,106 @@ hydro_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict__ 
       V.bmin[k] = tree.bbmin[k][node]; V.bmax[k] = tree.bbmax[k][node];
       V.hmin[k] = tree.hbmin[k][node]; V.hmax[k] = tree.hbmax[k][node];
     }
-    if (!warp_walk(tree, stack, V, st)) continue;
+    if (!warp_walk<NB_WALK_STACK>(tree, stack, V, st)) continue;
     const int ncand = cl.n;
     const bool wrap = dp.any_periodic && __any_sync(FULLMASK, V.needwrap);
+    bool overflow = false;
 
-    for (int t0 = 0; t0 < ccount; t0 += 32*T) {
-      Target tg[T]; bool live[T]; int ti[T];
-#pragma unroll
-      for (int t = 0; t < T; t++) {
-        const int o = t0 + t*32 + lane;
-        ti[t] = cfirst + o;
-        live[t] = o < ccount;
-        if (live[t]) {
-          const unsigned fl = (unsigned) P.i[I_FLAGS][ti[t]];
-          live[t] = (fl & GSPH_FLAG_ACTIVE) && !(fl & GSPH_FLAG_DEAD);
-        }
-        Target& g = tg[t];
-        g.x[0] = g.x[1] = g.x[2] = GSPH_BIG; g.v[0] = g.v[1] = g.v[2] = 0.0;
-        g.invh = g.hfac = g.invrho = g.pfac = g.sound = g.u = g.alpha = g.press = g.zeta = 0.0;
-        g.hr2 = -1.0; g.m = 0.0; g.rho = 1.0; g.invomega = 1.0; g.level = 0;
-        if (live[t]) {
-          const int i = ti[t];
-#pragma unroll
-          for (int k = 0; k < NDIM; k++) { g.x[k] = P.f[F_RX + k][i]; g.v[k] = P.f[F_VX + k][i]; }
-#pragma unroll
-          for (int k = NDIM; k < 3; k++) g.x[k] = 0.0;
-          const double hi = P.f[F_H][i];
-          g.rho = P.f[F_RHO][i]; g.press = P.f[F_PRESS][i]; g.invomega = P.f[F_INVOMEGA][i];
-          g.invh = 1.0/hi; g.invrho = 1.0/g.rho; g.hfac = P.f[F_HFAC][i];
-          g.pfac = (g.press*g.invomega)/(g.rho*g.rho);
-          g.sound = P.f[F_SOUND][i]; g.u = P.f[F_U][i]; g.alpha = P.f[F_ALPHA][i];
-          g.zeta = P.f[F_ZETA][i]; g.hr2 = P.f[F_HR2][i]; g.m = P.f[F_M][i];
-          g.level = P.i[I_LEVEL][i];
-        }
-        g.a[0] = g.a[1] = g.a[2] = 0.0; g.at[0] = g.at[1] = g.at[2] = 0.0;
-        g.gpot = 0.0; g.dudt = 0.0; g.divv = 0.0; g.levelneib = 0; g.nngb = 0;
-        if (GRAV && live[t]) g.gpot = (g.m*g.invh)*K.wpot(0.0);          /* GradhSphTree.cpp:512 */
+    for (int t0 = 0; t0 < ccount; t0 += 32) {
+      Target g;
+      const int ti = cfirst + t0 + lane;
+      bool live = t0 + lane < ccount;
+      if (live) {
+        const unsigned fl = (unsigned) P.i[I_FLAGS][ti];
+        live = (fl & GSPH_FLAG_ACTIVE) && !(fl & GSPH_FLAG_DEAD);
       }
+      g.x[0] = g.x[1] = g.x[2] = GSPH_BIG; g.v[0] = g.v[1] = g.v[2] = 0.0;
+      g.invh = g.hfac = g.invrho = g.pfac = g.sound = g.u = g.alpha = g.press = g.zeta = 0.0;
+      g.hr2 = -1.0; g.m = 0.0; g.rho = 1.0; g.invomega = 1.0; g.level = 0;
+      if (live) {
+#pragma unroll
+        for (int k = 0; k < NDIM; k++) { g.x[k] = P.f[F_RX + k][ti]; g.v[k] = P.f[F_VX + k][ti]; }
+#pragma unroll
+        for (int k = NDIM; k < 3; k++) g.x[k] = 0.0;
+        const double hi = P.f[F_H][ti];
+        g.rho = P.f[F_RHO][ti]; g.press = P.f[F_PRESS][ti]; g.invomega = P.f[F_INVOMEGA][ti];
+        g.invh = 1.0/hi; g.invrho = 1.0/g.rho; g.hfac = P.f[F_HFAC][ti];
+        g.pfac = (g.press*g.invomega)/(g.rho*g.rho);
+        g.sound = P.f[F_SOUND][ti]; g.u = P.f[F_U][ti]; g.alpha = P.f[F_ALPHA][ti];
+        g.zeta = P.f[F_ZETA][ti]; g.hr2 = P.f[F_HR2][ti]; g.m = P.f[F_M][ti];
+        g.level = P.i[I_LEVEL][ti];
+      }
+      g.a[0] = g.a[1] = g.a[2] = 0.0; g.at[0] = g.at[1] = g.at[2] = 0.0;
+      g.gpot = 0.0; g.dudt = 0.0; g.divv = 0.0; g.levelneib = 0; g.nngb = 0;
+      if (GRAV && live) g.gpot = (g.m*g.invh)*K.wpot(0.0);          /* GradhSphTree.cpp:512 */
 
+      /* ---- phase 1: neighbour lists by the reference's predicate (NeighbourManager.h:521) -----------*/
+      int n = 0; bool full = false;
       for (int base = 0; base < ncand; base += 32) {
         const int jl = base + lane;
         __syncwarp();
         if (jl < ncand) {
           const int j = cand[jl];
-          const bool dead = ((unsigned) P.i[I_FLAGS][j]) & GSPH_FLAG_DEAD;
-          const double hj = P.f[F_H][j], rhoj = P.f[F_RHO][j];
-          geom[lane*4 + 0] = dead ? GSPH_BIG : P.f[F_RX][j];
-          geom[lane*4 + 1] = NDIM > 1 ? P.f[F_RY][j] : 0.0;
-          geom[lane*4 + 2] = NDIM > 2 ? P.f[F_RZ][j] : 0.0;
-          geom[lane*4 + 3] = dead ? -1.0 : P.f[F_HR2][j];
-#pragma unroll
-          for (int k = 0; k < NDIM; k++) tf[(TF_VX + k)*32 + lane] = P.f[F_VX + k][j];
-          tf[TF_M*32 + lane] = P.f[F_M][j];
-          tf[TF_INVH*32 + lane] = 1.0/hj;
-          tf[TF_HFAC*32 + lane] = P.f[F_HFAC][j];
-          tf[TF_INVRHO*32 + lane] = 1.0/rhoj;
-          const double pj = P.f[F_PRESS][j];
-          tf[TF_PFAC*32 + lane] = (pj*P.f[F_INVOMEGA][j])/(rhoj*rhoj);
-          tf[TF_SOUND*32 + lane] = P.f[F_SOUND][j];
-          tf[TF_U*32 + lane] = P.f[F_U][j];
-          tf[TF_ALPHA*32 + lane] = P.f[F_ALPHA][j];
-          tf[TF_PRESS*32 + lane] = pj;
-          tf[TF_ZETA*32 + lane] = P.f[F_ZETA][j];
-          tf[TF_LEVEL*32 + lane] = (double) P.i[I_LEVEL][j];
+          const double2 a = geoh[2*(size_t) j], b = geoh[2*(size_t) j + 1];
+          geom[lane*4 + 0] = a.x; geom[lane*4 + 1] = a.y; geom[lane*4 + 2] = b.x; geom[lane*4 + 3] = b.y;
+          tj[lane] = j;
         }
         __syncwarp();
         const int nt = min(32, ncand - base);
         for (int jj = 0; jj < nt; jj++) {
           const double2 ga = *reinterpret_cast<const double2*>(geom + jj*4);
           const double2 gb = *reinterpret_cast<const double2*>(geom + jj*4 + 2);
-#pragma unroll
-          for (int t = 0; t < T; t++) {
-            double dr[3] = {0, 0, 0};
-            dr[0] = ga.x - tg[t].x[0];
-            if (NDIM > 1) dr[1] = ga.y - tg[t].x[1];
-            if (NDIM > 2) dr[2] = gb.x - tg[t].x[2];
-            if (wrap) wrap_dr<NDIM>(dp, dr);
-            const double drsqd = dot_exact<NDIM>(dr);
-            if (drsqd < tg[t].hr2 || drsqd < gb.y)
-              pair_terms<NDIM, GRAV, HYDRO>(dp, K, tg[t], dr, drsqd, tf, jj);
+          double dr[3] = {0, 0, 0};
+          dr[0] = ga.x - g.x[0];
+          if (NDIM > 1) dr[1] = ga.y - g.x[1];
+          if (NDIM > 2) dr[2] = gb.x - g.x[2];
+          if (wrap) wrap_dr<NDIM>(dp, dr);
+          const double drsqd = dot_exact<NDIM>(dr);
+          if (drsqd < g.hr2 || drsqd < gb.y) {
+            if (n < nlist_cap) { nlist[(size_t) n*32 + lane] = tj[jj]; n++; }
+            else full = true;
           }
+        }
+      }
+      if (__any_sync(FULLMASK, full)) {
+        if (lane == 0) atomicExch(&st->err_nlist_overflow, 1);
+        overflow = true; break;
+      }
+      int nmax = n;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(FULLMASK, nmax, o));
+
+      /* ---- phase 2: pair terms over the lane's own list ----------------------------------------------*/
+      for (int k = 0; k < nmax; k++) {
+        if (k < n) {
+          const int j = nlist[(size_t) k*32 + lane];
+          const double2* r = frec + 8*(size_t) j;
+          const double2 r0 = r[0], r1 = r[1], r2 = r[2], r3 = r[3], r4 = r[4], r5 = r[5];
+          Neib nb;
+          nb.v[0] = r1.y; nb.v[1] = r2.x; nb.v[2] = r2.y;
+          nb.m = r3.x; nb.invh = r3.y; nb.hfac = r4.x; nb.invrho = r4.y; nb.pfac = r5.x; nb.sound = r5.y;
+          nb.u = 0.0; nb.alpha = 0.0; nb.zeta = 0.0; nb.press = 0.0; nb.level = 0;
+          if (dp.acond != GSPH_ACOND_NONE || dp.avisc >= GSPH_AVISC_MON97MM97) { const double2 r6 = r[6]; nb.u = r6.x; nb.alpha = r6.y; }
+          {
+            const double2 r7 = r[7];
+            nb.zeta = r7.x;
+            if (price) { nb.press = r7.y; nb.level = P.i[I_LEVEL][j]; }
+            else nb.level = (int) r7.y;
+          }
+          double dr[3] = {0, 0, 0};
+          dr[0] = r0.x - g.x[0];
+          if (NDIM > 1) dr[1] = r0.y - g.x[1];
+          if (NDIM > 2) dr[2] = r1.x - g.x[2];
+          if (wrap) wrap_dr<NDIM>(dp, dr);
+          const double drsqd = dot_exact<NDIM>(dr);
+          pair_terms<NDIM, GRAV, HYDRO>(dp, K, g, dr, drsqd, nb);
         }
       }
 
       /* ---- end-of-loop terms and write-back (GradhSph.cpp:451-457 / :576-582;
        *      GradhSphTree.cpp:396-406 / :610-620) ---------------------------------------------------*/
-#pragma unroll
-      for (int t = 0; t < T; t++) {
-        if (!live[t]) continue;
-        Target& g = tg[t];
-        const int i = ti[t];
+      if (live) {
+        const int i = ti;
         if (HYDRO) {
           g.divv *= g.invrho;
           const double press = dp.gammam1*g.rho*g.u;                    /* eos->Pressure(parti) */
@@ -286,11 +332,9 @@ hydro_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict__ 
           for (int k = 0; k < NDIM; k++) P.f[F_AX + k][i] += g.a[k];
           P.f[F_DUDT][i] += g.dudt;
           P.f[F_DIVV][i] += g.divv;
-          if (!GRAV && dp.tdavisc == GSPH_TDAVISC_MM97) {
-            const double hi_inv = g.invh;
-            P.f[F_DALPHADT][i] += 0.1*g.sound*(dp.alpha_visc_min - g.alpha)*hi_inv +
+          if (!GRAV && dp.tdavisc == GSPH_TDAVISC_MM97)
+            P.f[F_DALPHADT][i] += 0.1*g.sound*(dp.alpha_visc_min - g.alpha)*g.invh +
               fmax(-g.divv, 0.0)*(dp.alpha_visc - g.alpha);
-          }
         }
         if (GRAV) {
 #pragma unroll
@@ -303,7 +347,7 @@ hydro_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict__ 
       }
     }
     __syncwarp();
-    if (lane == 0) done[c] = 1;
+    if (!overflow && lane == 0) done[c] = 1;
   }
   loc_ngb = (unsigned long long) warp_sum((double) loc_ngb);
   loc_targets = (unsigned long long) warp_sum((double) loc_targets);
@@ -330,7 +374,7 @@ neib_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* work_
   int* stacks = (int*)(tiles + HYD_WARPS*32*4);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double* geom = tiles + warp*32*4;
-  int* stack = stacks + warp*WALK_STACK_CAP;
+  int* stack = stacks + warp*NB_WALK_STACK;
   __shared__ int jidx[HYD_WARPS][32];
   const int gwarp = blockIdx.x*HYD_WARPS + warp;
   int32_t* cand = cand_all + (size_t) gwarp*cand_cap;
@@ -351,7 +395,7 @@ neib_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* work_
       V.bmin[k] = tree.bbmin[k][node]; V.bmax[k] = tree.bbmax[k][node];
       V.hmin[k] = tree.hbmin[k][node]; V.hmax[k] = tree.hbmax[k][node];
     }
-    if (!warp_walk(tree, stack, V, st)) continue;
+    if (!warp_walk<NB_WALK_STACK>(tree, stack, V, st)) continue;
     const int ncand = cl.n;
     const bool wrap = dp.any_periodic && __any_sync(FULLMASK, V.needwrap);
     for (int t0 = 0; t0 < ccount; t0 += 32) {
@@ -408,12 +452,11 @@ neib_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* work_
 template <int NDIM, int KERN, bool TAB, bool GRAV, bool HYDRO>
 int launch_hydro(gsph_handle* h)
 {
-  constexpr int T = 1;
-  const int Lc = cohort_level_for(h->N, h->tree.ltot, 32*T);
+  const int Lc = cohort_level_for(h->N, h->tree.ltot, 32);
   constexpr int NTAB = TAB ? (GRAV ? 3 : 1) : 0;
-  const size_t smem = NTAB*GSPH_TABLE_RES*sizeof(double) + HYD_WARPS*TILE_DOUBLES*sizeof(double)
-                      + HYD_WARPS*WALK_STACK_CAP*sizeof(int);
-  auto kern = hydro_kernel<NDIM, KERN, TAB, GRAV, HYDRO, T>;
+  const size_t smem = NTAB*GSPH_TABLE_RES*sizeof(double) + HYD_WARPS*32*4*sizeof(double)
+                      + HYD_WARPS*32*sizeof(int) + HYD_WARPS*NB_WALK_STACK*sizeof(int);
+  auto kern = hydro_kernel<NDIM, KERN, TAB, GRAV, HYDRO>;
   CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   int bps = 0;
   CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, HYD_THREADS, smem));
@@ -424,14 +467,21 @@ int launch_hydro(gsph_handle* h)
   if (blocks > need_blocks) blocks = need_blocks;
   int rc = gsph_ensure_cand(h, blocks*HYD_WARPS, 0);
   if (rc) return rc;
+  rc = gsph_ensure_nlist(h, blocks*HYD_WARPS, 0);
+  if (rc) return rc;
   CUDA_TRY(h, cudaMemsetAsync(h->work_counter, 0, sizeof(int), h->stream));
   PartView P;
   for (int k = 0; k < NF_DOUBLE; k++) P.f[k] = h->P[k];
   for (int k = 0; k < NF_INT; k++) P.i[k] = h->PI[k];
+  const int N = (int) h->N;
+  pack_force_kernel<NDIM><<<(N + 255)/256, 256, 0, h->stream>>>(N, P, h->dp.acond == GSPH_ACOND_PRICE2008 ? 1 : 0,
+                                                              h->geoh, h->frec);
   KernelTimer kt(h, 1);
-  kern<<<blocks, HYD_THREADS, smem, h->stream>>>(P, h->tree, h->dp, h->tables, Lc, h->work_counter,
-                                                 h->cand, (int) h->cand_cap_per_warp, h->status, h->done);
-  h->stats.kernel_launches++;
+  kern<<<blocks, HYD_THREADS, smem, h->stream>>>(P, h->tree, h->dp, h->tables, (const double2*) h->geoh,
+                                                 (const double2*) h->frec, Lc, h->work_counter, h->cand,
+                                                 (int) h->cand_cap_per_warp, h->nlist, (int) h->nlist_cap,
+                                                 h->status, h->done);
+  h->stats.kernel_launches += 2;
   CUDA_TRY(h, cudaGetLastError());
   return GSPH_OK;
 }
@@ -440,7 +490,7 @@ template <int NDIM, int MODE>
 int launch_neib(gsph_handle* h, int32_t* counts, const int64_t* offsets, int32_t* idx)
 {
   const int Lc = cohort_level_for(h->N, h->tree.ltot, 32);
-  const size_t smem = HYD_WARPS*32*4*sizeof(double) + HYD_WARPS*WALK_STACK_CAP*sizeof(int);
+  const size_t smem = HYD_WARPS*32*4*sizeof(double) + HYD_WARPS*NB_WALK_STACK*sizeof(int);
   auto kern = neib_kernel<NDIM, MODE>;
   int bps = 0;
   CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, HYD_THREADS, smem));

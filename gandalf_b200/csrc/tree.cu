@@ -176,6 +176,20 @@ __global__ void gather_kernel(int N, const int32_t* perm, PartView Hh, PartView 
   for (int f = 0; f < NF_INT; f++) Pp.i[f][p] = Hh.i[f][i];
 }
 
+/* packed (x, y, z, m) records for the density gather phase; dead particles get m = 0 */
+template <int NDIM>
+__global__ void pack_geo4_kernel(int N, PartView P, double* __restrict__ geo4)
+{
+  const int p = blockIdx.x*blockDim.x + threadIdx.x;
+  if (p >= N) return;
+  const bool dead = ((unsigned) P.i[I_FLAGS][p]) & GSPH_FLAG_DEAD;
+  double2 a, b;
+  a.x = P.f[F_RX][p]; a.y = NDIM > 1 ? P.f[F_RY][p] : 0.0;
+  b.x = NDIM > 2 ? P.f[F_RZ][p] : 0.0; b.y = dead ? 0.0 : P.f[F_M][p];
+  reinterpret_cast<double2*>(geo4)[2*(size_t) p] = a;
+  reinterpret_cast<double2*>(geo4)[2*(size_t) p + 1] = b;
+}
+
 /* ---- StockCellProperties for the leaves, KDTree.cpp:841-1010 -----------------------------------*/
 template <int NDIM>
 __global__ void stock_leaves_kernel(TreeDev T, PartView P, DevParams dp, int full)
@@ -537,13 +551,30 @@ int build_tree_nd(gsph_handle* h, int mode, double dt)
 
 }  // namespace
 
+int gsph_pack_geo4(gsph_handle* h)
+{
+  const int N = (int) h->N;
+  const PartView P = view_of(h->P, h->PI);
+  switch (h->dp.ndim) {
+  case 1: pack_geo4_kernel<1><<<(N + 255)/256, 256, 0, h->stream>>>(N, P, h->geo4); break;
+  case 2: pack_geo4_kernel<2><<<(N + 255)/256, 256, 0, h->stream>>>(N, P, h->geo4); break;
+  default: pack_geo4_kernel<3><<<(N + 255)/256, 256, 0, h->stream>>>(N, P, h->geo4); break;
+  }
+  h->stats.kernel_launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return GSPH_OK;
+}
+
 int gsph_tree_build(gsph_handle* h, int mode, double dt)
 {
+  int rc;
   switch (h->dp.ndim) {
-  case 1: return build_tree_nd<1>(h, mode, dt);
-  case 2: return build_tree_nd<2>(h, mode, dt);
-  default: return build_tree_nd<3>(h, mode, dt);
+  case 1: rc = build_tree_nd<1>(h, mode, dt); break;
+  case 2: rc = build_tree_nd<2>(h, mode, dt); break;
+  default: rc = build_tree_nd<3>(h, mode, dt); break;
   }
+  if (rc) return rc;
+  return gsph_pack_geo4(h);
 }
 
 /* KDTree::UpdateAllHmaxValues after the density pass: only hmax and hbox change (cdistsqd keeps
