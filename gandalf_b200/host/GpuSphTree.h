@@ -1,0 +1,201 @@
+//=================================================================================================
+//  GpuSphTree.h -- host-side C++ twin of the reference's neighbour-search object:
+//  `neib_search = gpu`.
+//
+//  GpuSphTree<ndim> IS-A GradhSphTree<ndim,GradhSphParticle> (src/Headers/SphNeighbourSearch.h:
+//  174-227) and overrides exactly the virtuals of the hot path, forwarding each one to the C ABI of
+//  libgsph (include/gsph.h):
+//
+//      BuildTree                 HydroTree.cpp:310-372      -> gsph_upload + gsph_build_tree
+//      UpdateAllSphProperties    GradhSphTree.cpp:83-271    -> gsph_update_properties
+//      UpdateAllSphHydroForces   GradhSphTree.cpp:280-435   -> gsph_update_hydro_forces
+//      UpdateAllSphForces        GradhSphTree.cpp:444-657   -> gsph_update_all_forces
+//      GetMaximumSmoothingLength                            -> gsph_get_hmax
+//
+//  Everything that is NOT on the accelerated path keeps the inherited CPU implementation
+//  (GetGatherNeighbourList for sinks/feedback, UpdateAllStarGasForces, ghost creation for the
+//  integrator, GetTree for dust ...).  This header is compiled INTO the reference (it needs the
+//  reference headers); it contains no reference code.  The particle array is owned by
+//  GradhSph::sphdata and may be reallocated between calls (GradhSph.cpp:83-111), so the view is
+//  rebuilt from hydro->GetParticleArray() on every call.
+//
+//  Error convention: a non-zero C-ABI status is handed to ExceptionHandler::raise
+//  (src/Common/Exception.cpp:47-69) with gsph_last_error() as the message.
+//=================================================================================================
+#ifndef _GPU_SPH_TREE_H_
+#define _GPU_SPH_TREE_H_
+
+#include <string>
+#include <cstring>
+#include "gsph.h"
+#include "Exception.h"
+#include "Parameters.h"
+#include "SimUnits.h"
+#include "Sph.h"
+#include "Particle.h"
+#include "SphNeighbourSearch.h"
+#include "CodeTiming.h"
+
+template <int ndim>
+class GpuSphTree : public GradhSphTree<ndim, GradhSphParticle>
+{
+  typedef GradhSphTree<ndim, GradhSphParticle> Base;
+  typedef GradhSphParticle<ndim> Part;
+
+  gsph_handle* handle;
+  bool keep_host_tree;        ///< also maintain the CPU tree for the non-accelerated consumers
+  bool staged;                ///< device copy matches the host array of this step
+
+  static int lookup(const std::string& v, const char* const* names, int n, const char* what) {
+    for (int i = 0; i < n; i++) if (v == names[i]) return i;
+    ExceptionHandler::getIstance().raise(std::string("GpuSphTree: unsupported ") + what + " = " + v);
+    return 0;
+  }
+
+  void check(int rc) {
+    if (rc != GSPH_OK) ExceptionHandler::getIstance().raise(std::string("libgsph: ") + gsph_last_error(handle));
+  }
+
+  static gsph_field field(void* base) { gsph_field f; f.base = base; f.stride = sizeof(Part); return f; }
+
+  /// (base pointer, stride) of every field of the reference's AoS particle array
+  static gsph_particle_view make_view(Part* p) {
+    gsph_particle_view v;
+    memset(&v, 0, sizeof v);
+    for (int k = 0; k < ndim; k++) {
+      v.r[k] = field(&p[0].r[k]); v.v[k] = field(&p[0].v[k]);
+      v.a[k] = field(&p[0].a[k]); v.atree[k] = field(&p[0].atree[k]);
+    }
+    v.m = field(&p[0].m); v.h = field(&p[0].h); v.u = field(&p[0].u); v.rho = field(&p[0].rho);
+    v.hrangesqd = field(&p[0].hrangesqd); v.hfactor = field(&p[0].hfactor);
+    v.invomega = field(&p[0].invomega); v.zeta = field(&p[0].zeta); v.sound = field(&p[0].sound);
+    v.pressure = field(&p[0].pressure); v.dudt = field(&p[0].dudt); v.div_v = field(&p[0].div_v);
+    v.alpha = field(&p[0].alpha); v.dalphadt = field(&p[0].dalphadt); v.gpot = field(&p[0].gpot);
+    v.gpot_hydro = field(&p[0].gpot_hydro);
+    v.flags = field(&p[0].flags);            // type_flag holds exactly one unsigned int (Flags.h:93-96)
+    v.ptype = field(&p[0].ptype); v.level = field(&p[0].level); v.levelneib = field(&p[0].levelneib);
+    v.iorig = field(&p[0].iorig); v.sinkid = field(&p[0].sinkid);
+    return v;
+  }
+
+  void upload(Hydrodynamics<ndim>* hydro) {
+    Part* p = hydro->template GetParticleArray<GradhSphParticle>();
+    gsph_particle_view v = make_view(p);
+    check(gsph_upload(handle, &v, hydro->Nhydro));
+  }
+  void download(Hydrodynamics<ndim>* hydro, unsigned mask) {
+    Part* p = hydro->template GetParticleArray<GradhSphParticle>();
+    gsph_particle_view v = make_view(p);
+    check(gsph_download(handle, &v, mask));
+  }
+
+ public:
+
+  /// Same argument list as GradhSphTree (GradhSphSimulation.cpp:243-246) plus the objects the
+  /// configuration is read from.
+  GpuSphTree(int Nleafmax, int Nmpi, int pruning_level_min, int pruning_level_max, FLOAT thetamaxsqd,
+             FLOAT kernrange, FLOAT macerror, std::string gravity_mac, std::string multipole,
+             DomainBox<ndim>* box, SmoothingKernel<ndim>* kern, CodeTiming* timing,
+             ParticleTypeRegister& types, Sph<ndim>* sph, Parameters* params, SimUnits& units,
+             bool keep_host_tree_aux = true)
+    : Base("kdtree", Nleafmax, Nmpi, pruning_level_min, pruning_level_max, thetamaxsqd, kernrange,
+           macerror, gravity_mac, multipole, box, kern, timing, types),
+      handle(NULL), keep_host_tree(keep_host_tree_aux), staged(false)
+  {
+    std::map<std::string, int>& ip = params->intparams;
+    std::map<std::string, double>& fp = params->floatparams;
+    std::map<std::string, std::string>& sp = params->stringparams;
+    gsph_config c;
+    gsph_default_config(&c);
+    c.ndim = ndim;
+    static const char* const kernels[] = {"m4", "quintic"};
+    c.kernel = lookup(sp["kernel"], kernels, 2, "kernel");
+    c.tabulated_kernel = ip["tabulated_kernel"];
+    c.h_fac = sph->h_fac; c.h_converge = sph->h_converge;
+    c.avisc = (int) sph->avisc; c.acond = (int) sph->acond;           // same enum order, Sph.h:50-52
+    if (sph->tdavisc == cd2010) ExceptionHandler::getIstance().raise("GpuSphTree: cd2010 viscosity is not accelerated");
+    c.tdavisc = (int) sph->tdavisc;
+    c.alpha_visc = sph->alpha_visc; c.beta_visc = sph->beta_visc; c.alpha_visc_min = sph->alpha_visc_min;
+    static const char* const eos[] = {"energy_eqn", "isothermal", "barotropic"};
+    c.eos = sp["gas_eos"] == "constant_temp" ? GSPH_EOS_ADIABATIC : lookup(sp["gas_eos"], eos, 3, "gas_eos");
+    c.gamma_eos = fp["gamma_eos"];
+    c.temp0 = fp["temp0"]/units.temp.outscale;                       // code units, as the EOS classes scale them
+    c.mu_bar = fp["mu_bar"];
+    c.rho_bary = fp["rho_bary"]/units.rho.outscale/units.rho.outcgs;
+    static const char* const bnd[] = {"open", "periodic", "mirror"};
+    for (int k = 0; k < ndim; k++) {
+      c.boxmin[k] = box->min[k]; c.boxmax[k] = box->max[k];
+      c.boundary_lhs[k] = box->boundary_lhs[k] == periodicBoundary ? 1 : (box->boundary_lhs[k] == mirrorBoundary ? 2 : 0);
+      c.boundary_rhs[k] = box->boundary_rhs[k] == periodicBoundary ? 1 : (box->boundary_rhs[k] == mirrorBoundary ? 2 : 0);
+    }
+    (void) bnd;
+    c.hydro_forces = sph->hydro_forces; c.self_gravity = sph->self_gravity;
+    c.thetamaxsqd = thetamaxsqd; c.macerror = macerror;
+    static const char* const macs[] = {"geometric", "eigenmac", "gadget2"};
+    c.gravity_mac = lookup(gravity_mac, macs, 3, "gravity_mac");
+    static const char* const mps[] = {"monopole", "quadrupole", "fast_monopole", "fast_quadrupole"};
+    c.multipole = lookup(multipole, mps, 4, "multipole");
+    c.Nleafmax = Nleafmax;
+    c.create_sinks = sph->create_sinks;
+    int rc = gsph_create(&c, &handle);
+    if (rc != GSPH_OK) ExceptionHandler::getIstance().raise(std::string("libgsph: ") + gsph_last_error(NULL));
+  }
+
+  virtual ~GpuSphTree() { gsph_destroy(handle); }
+
+  //-----------------------------------------------------------------------------------------------
+  virtual void BuildTree(const bool rebuild_tree, const int n, const int ntreebuildstep,
+                         const int ntreestockstep, const FLOAT timestep, Hydrodynamics<ndim>* hydro)
+  {
+    if (keep_host_tree) Base::BuildTree(rebuild_tree, n, ntreebuildstep, ntreestockstep, timestep, hydro);
+    CodeTiming::BlockTimer timer = this->timing->StartNewTimer("GPU_BUILD_TREE");
+    upload(hydro);
+    const int mode = (n%ntreebuildstep == 0 || rebuild_tree) ? 0 : (n%ntreestockstep == 0 ? 1 : 2);
+    check(gsph_build_tree(handle, mode, timestep));
+    staged = true;
+  }
+
+  virtual void UpdateAllSphProperties(Sph<ndim>* sph, Nbody<ndim>* nbody)
+  {
+    CodeTiming::BlockTimer timer = this->timing->StartNewTimer("SPH_PROPERTIES");
+    if (!staged) { upload(sph); check(gsph_build_tree(handle, 1, 0.0)); }
+    check(gsph_update_properties(handle));
+    download(sph, GSPH_F_DENSITY);
+    staged = false;                       // the host zeroes accelerations / moves data after this call
+    (void) nbody;
+  }
+
+  virtual void UpdateAllSphHydroForces(Sph<ndim>* sph, Nbody<ndim>* nbody, DomainBox<ndim>& simbox)
+  {
+    CodeTiming::BlockTimer timer = this->timing->StartNewTimer("SPH_HYDRO_FORCES");
+    upload(sph);                          // picks up Sph::ZeroAccelerations and the active flags
+    check(gsph_build_tree(handle, 1, 0.0));
+    check(gsph_update_hydro_forces(handle));
+    download(sph, GSPH_F_FORCES);
+    staged = false;
+    (void) nbody; (void) simbox;
+  }
+
+  virtual void UpdateAllSphForces(Sph<ndim>* sph, Nbody<ndim>* nbody, DomainBox<ndim>& simbox,
+                                  Ewald<ndim>* ewald)
+  {
+    CodeTiming::BlockTimer timer = this->timing->StartNewTimer("SPH_ALL_FORCES");
+    upload(sph);
+    check(gsph_build_tree(handle, 1, 0.0));
+    check(gsph_update_all_forces(handle, NULL, 0));
+    download(sph, GSPH_F_FORCES);
+    staged = false;
+    (void) nbody; (void) simbox; (void) ewald;
+  }
+
+  virtual double GetMaximumSmoothingLength() const
+  {
+    double hmax = 0.0;
+    if (gsph_get_hmax(handle, &hmax) != GSPH_OK) return Base::GetMaximumSmoothingLength();
+    return hmax;
+  }
+
+  gsph_handle* GetHandle() { return handle; }
+};
+
+#endif

@@ -20,6 +20,10 @@
 //  usage:
 //    ref_harness PARAMS.dat OUTDIR [--in IC.bin] [--set key=value]... [--perturb-h AMP]
 //                [--dump setup,density,forces,neib,tree,gravlists] [--bench STEPS] [--quiet]
+//                [--mainloop N [--gpu]]
+//  --mainloop N : run N steps of the reference's own SphSimulation::MainLoop and dump the particles
+//                 ("loop.*"); with --gpu (ref_harness_gpu build only) sim->sphneib is first replaced by
+//                 gandalf_b200/host/GpuSphTree.h, i.e. the reference drives the B200 path.
 //
 //  IC.bin  : "GSPHIC1\0", int32 ndim, int32 pad, int64 N, then N doubles each of
 //            x[,y[,z]], vx[,vy[,vz]], m, h, u   (h<=0 everywhere => let the reference guess h)
@@ -59,11 +63,16 @@
 #include "NeighbourManager.h"
 #include "KDTree.h"
 #include "TreeCell.h"
+#ifdef WITH_GPU
+#include "GpuSphTree.h"      // gandalf_b200/host: the drop-in subclass under test (links libgsph.so)
+#endif
 
 using namespace std;
 
 static string g_outdir;
 static bool g_quiet = false;
+static int g_mainloop = 0;         // --mainloop N : run N steps of the reference's own MainLoop
+static bool g_gpu = false;         // --gpu : swap sim->sphneib for GpuSphTree before doing so
 static FILE* g_out = NULL;          // the caller's stdout (the reference's chatter goes elsewhere)
 
 //-------------------------------------------------------------------------------------------------
@@ -415,6 +424,33 @@ static int run(Parameters* params, const string& icfile, double perturb, const s
     if (want("forces")) H.dump_particles("force_out");
   }
 
+  // ---------------------------------------------------------------- drop-in check: the reference's
+  // own MainLoop (src/Hydrodynamics/SphSimulation.cpp:574-880) drives whichever neighbour-search
+  // object sits behind sim->sphneib -- the CPU GradhSphTree, or (--gpu) our GpuSphTree.
+  if (g_mainloop > 0) {
+    if (g_gpu) {
+#ifdef WITH_GPU
+      Parameters* sp = sim->simparams;
+      sim->sphneib = new GpuSphTree<ndim>(
+          sp->intparams["Nleafmax"], 1, sp->intparams["pruning_level_min"], sp->intparams["pruning_level_max"],
+          sp->floatparams["thetamaxsqd"], sim->sph->kernp->kernrange, sp->floatparams["macerror"],
+          sp->stringparams["gravity_mac"], sp->stringparams["multipole"], &sim->simbox, sim->sph->kernp,
+          sim->timing, sim->sph->types, sim->sph, sp, sim->simunits);
+      sim->sphneib->SetTimingObject(sim->timing);
+      H.sphneib = sim->sphneib;
+#else
+      fprintf(stderr, "--gpu needs the WITH_GPU build (ref_harness_gpu)\n"); return 2;
+#endif
+    }
+    double t1 = now();
+    for (int s = 0; s < g_mainloop; s++) sim->MainLoop();
+    double t_loop = now() - t1;
+    H.dump_particles("loop");
+    fprintf(g_out, "{\"ref_mainloop\": true, \"gpu\": %s, \"N\": %d, \"steps\": %d, \"t\": %.17g, \"wall_s\": %.4f}\n",
+            g_gpu ? "true" : "false", H.sph->Nhydro, g_mainloop, (double) sim->t, t_loop);
+    fflush(g_out);
+  }
+
   // ---------------------------------------------------------------- CPU timing baseline
   if (bench_steps > 0) {
     double tb = 0, tg = 0, tp = 0, tf = 0;
@@ -477,6 +513,8 @@ int main(int argc, char** argv)
     else if (a == "--dump" && i + 1 < argc) dumps = argv[++i];
     else if (a == "--bench" && i + 1 < argc) bench_steps = atoi(argv[++i]);
     else if (a == "--quiet") g_quiet = true;
+    else if (a == "--mainloop" && i + 1 < argc) g_mainloop = atoi(argv[++i]);
+    else if (a == "--gpu") g_gpu = true;
     else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 1; }
   }
 

@@ -102,3 +102,31 @@ def run_harness(params, ic=None, dumps="setup,density,forces,neib", perturb_h=0.
 
 def csr_rows(off, idx):
     return [idx[off[i]:off[i + 1]] for i in range(len(off) - 1)]
+
+
+def run_mainloop(params, ic, steps, gpu, timeout=1800):
+    """N steps of the reference's own SphSimulation::MainLoop through oracle/_ref/ref_harness_gpu;
+    gpu=True swaps sim->sphneib for gandalf_b200/host/GpuSphTree.h first.  -> (arrays, info json)"""
+    exe = harness_path("gpu")
+    if exe is None:
+        raise FileNotFoundError("oracle/_ref/ref_harness_gpu not built (make -C oracle ref_gpu)")
+    work = tempfile.mkdtemp(prefix="gsph_loop_")
+    try:
+        dat = os.path.join(work, "params.dat")
+        write_dat(dat, params)
+        icf = os.path.join(work, "ic.bin")
+        write_ic(icf, int(params["ndim"]), ic["r"], ic["v"], ic["m"], ic["h"], ic["u"])
+        cmd = [exe, dat, os.path.join(work, "out"), "--dump", "", "--quiet", "--in", icf, "--mainloop", str(int(steps))]
+        if gpu:
+            cmd.append("--gpu")
+        res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=timeout)
+        if res.returncode != 0:
+            raise RuntimeError("ref_harness_gpu failed (%d): %s %s" % (res.returncode, res.stdout.decode()[-1000:],
+                                                                     res.stderr.decode()[-2000:]))
+        info = None
+        for line in res.stdout.decode().splitlines():
+            if line.startswith("{\"ref_mainloop\""):
+                info = json.loads(line)
+        return load_dump(os.path.join(work, "out")), info
+    finally:
+        shutil.rmtree(work, ignore_errors=True)

@@ -1,0 +1,54 @@
+"""Drop-in check (parity stage P6): the UNMODIFIED reference's own main loop
+(SphSimulation::MainLoop, src/Hydrodynamics/SphSimulation.cpp:574-880) is run twice from the same
+initial conditions -- once with its CPU GradhSphTree, once with sim->sphneib replaced by our
+GpuSphTree subclass (gandalf_b200/host/GpuSphTree.h -> libgsph.so) -- and the particle state after
+several time steps is compared.  Everything else (integrator, time-step control, ghosts, EOS object,
+zeroing of accelerations) is the reference's own code in both runs.
+
+The binary oracle/_ref/ref_harness_gpu is prebuilt in the build container (it needs the reference
+headers) and travels to the GPU box; nothing here reads /root/reference."""
+import numpy as np
+import pytest
+
+import refio
+from conftest import load_golden, stage, vec_rel_err, rel_err, scaled_err
+
+pytestmark = pytest.mark.gpu
+
+BASE = {"run_id": "DROPIN", "sim": "gradhsph", "ic": "python", "dimensionless": 1, "Nlevels": 1,
+        "Nstepsmax": 1000, "tend": 1.0e10, "dt_snap": 1.0e10, "noutputstep": 1000000, "ndiagstep": 1000000,
+        "out_file_form": "su", "sink_particles": 0, "sph_integration": "lfkdk", "neib_search": "kdtree"}
+
+
+def _case(name):
+    params, d = load_golden(name)
+    p = dict(BASE)
+    p.update(params)
+    p.update({k: BASE[k] for k in ("run_id", "ic", "Nstepsmax", "tend", "neib_search")})
+    s = stage(d, "dens_in")
+    order = np.argsort(s["iorig"])
+    ic = {k: s[k][order] for k in ("r", "v", "m", "h", "u")}
+    p.setdefault("Nhydromax", 8*len(ic["m"]))
+    return p, ic
+
+
+@pytest.mark.parametrize("name,steps", [("adsod", 6), ("khi2d_quintic", 4), ("box3d_m4tab", 4),
+                                        ("box3d_mm97", 3), ("sphere_grav_quad", 4), ("sphere_grav_fastmono", 4)])
+def test_reference_mainloop_with_gpu_tree(name, steps):
+    if refio.harness_path("gpu") is None:
+        pytest.skip("oracle/_ref/ref_harness_gpu not built")
+    p, ic = _case(name)
+    cpu, ci = refio.run_mainloop(p, ic, steps, gpu=False)
+    gpu, gi = refio.run_mainloop(p, ic, steps, gpu=True)
+    assert ci["steps"] == gi["steps"] == steps and gi["gpu"] and not ci["gpu"]
+    assert abs(ci["t"] - gi["t"]) <= 1e-12*abs(ci["t"])          # same time-step sequence
+    oc, og = np.argsort(cpu["loop.iorig"]), np.argsort(gpu["loop.iorig"])
+    tol = 1e-6                                                   # north-star bar (double precision)
+    for f in ("r", "v", "a"):
+        a, b = gpu["loop." + f][og], cpu["loop." + f][oc]
+        a = a.reshape(len(a), -1); b = b.reshape(len(b), -1)
+        e = np.linalg.norm(a - b, axis=1)/np.maximum(np.linalg.norm(b, axis=1), np.abs(b).max()*1e-6)
+        assert e.max() < tol, (f, e.max())
+    for f in ("h", "rho", "u"):
+        assert rel_err(gpu["loop." + f][og], cpu["loop." + f][oc]).max() < tol, f
+    assert scaled_err(gpu["loop.dudt"][og], cpu["loop.dudt"][oc]).max() < tol
