@@ -19,24 +19,26 @@
 
 #define DENS_THREADS 256
 #define DENS_WARPS (DENS_THREADS/32)
+#define DENS_REC_STRIDE 3                         /* double2 units per staged (x,y,z,m) record: 48 B, conflict-free */
+#define DENS_WARP_D2 (2*32*DENS_REC_STRIDE)       /* double2 per warp: two record stages (3 KiB >= walk stack) */
 
 namespace {
 
+/* gather walk on the outward-rounded float boxes (superset of Tree::ComputeGatherNeighbourList) */
 template <int NDIM>
-struct GatherVisitor {
-  const TreeDev& T; const DevParams& dp; CandList& cl;
-  double smin[3], smax[3];
-  __device__ __forceinline__ int test(int node, bool) const
+struct GatherVisitorF {
+  const float4* __restrict__ nodeb; const WalkBox& wb; CandList& cl;
+  float smin[3], smax[3];
+  int first, count;
+  __device__ __forceinline__ int test(int node, bool)
   {
-    double bmin[3], bmax[3];
-#pragma unroll
-    for (int k = 0; k < NDIM; k++) { bmin[k] = T.bbmin[k][node]; bmax[k] = T.bbmax[k][node]; }
-    return boxes_overlap<NDIM>(dp, smin, smax, bmin, bmax) ? 1 : 0;
+    const float4 lo = nodeb[2*(size_t) node], hi = nodeb[2*(size_t) node + 1];
+    first = __float_as_int(lo.w); count = __float_as_int(hi.w);
+    if (count <= 0) return 0;
+    bool wrapped = false;
+    return fboxes_overlap<NDIM>(wb, smin, smax, lo, hi, wrapped) ? 1 : 0;
   }
-  __device__ __forceinline__ bool emit(int node, int code, bool leaf, int lane)
-  {
-    return cl.append_leaf(T, node, code == 1 && leaf, lane);
-  }
+  __device__ __forceinline__ bool emit(bool take, int lane) { return cand_append_range(cl, first, count, take, lane); }
 };
 
 /* EOS: src/Headers/EOS.h:156, src/Thermal/{Adiabatic,Isothermal,Barotropic}EOS.cpp */
@@ -74,7 +76,7 @@ template <int NDIM> __device__ __forceinline__ double pow_ndim(double x)
  *           32-byte records through L1/L2), so every lane does useful work in every instruction.
  *-----------------------------------------------------------------------------------------------*/
 template <int NDIM, int KERN, bool TAB>
-__global__ void __launch_bounds__(DENS_THREADS)
+__global__ void __launch_bounds__(DENS_THREADS, 3)
 density_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict__ gtables,
                const double2* __restrict__ geo4, int cohort_level, int* work_counter,
                int32_t* cand_all, int cand_cap, int32_t* nlist_all, int nlist_cap, DevStatus* st,
@@ -82,17 +84,18 @@ density_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict_
 {
   extern __shared__ double smem[];
   double* tab = smem;                                          /* 3 x 1000 (tabulated only) */
-  double* tiles = smem + (TAB ? 3*GSPH_TABLE_RES : 0);         /* per warp: 32 x 4 doubles  */
-  int* tilej = (int*)(tiles + DENS_WARPS*32*4);                /* per warp: 32 ids          */
-  int* stacks = tilej + DENS_WARPS*32;                         /* per warp: NB_WALK_STACK   */
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  /* per-warp region, time-shared: walk stack | float tile x|y|z|w + ids (phase 1) | two record stages (phase 2) */
+  double2* stage = reinterpret_cast<double2*>(smem + (TAB ? 3*GSPH_TABLE_RES : 0)) + (threadIdx.x >> 5)*DENS_WARP_D2;
+  const int lane = threadIdx.x & 31;
   if (TAB) {
     for (int i = threadIdx.x; i < 3*GSPH_TABLE_RES; i += blockDim.x) tab[i] = gtables[i];
     __syncthreads();
   }
-  double* tile = tiles + warp*32*4;
-  int* tj = tilej + warp*32;
-  int* stack = stacks + warp*NB_WALK_STACK;
+  int* stack = reinterpret_cast<int*>(stage);
+  float* ftile = reinterpret_cast<float*>(stage);
+  int* tj = reinterpret_cast<int*>(ftile + 128);
+  const int warp = threadIdx.x >> 5;
+  const WalkBox wbx(dp);
   const int gwarp = blockIdx.x*DENS_WARPS + warp;
   int32_t* cand = cand_all + (size_t) gwarp*cand_cap;
   int32_t* nlist = nlist_all + (size_t) gwarp*nlist_cap*32;
@@ -153,67 +156,110 @@ density_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict_
         if (!(hmax > 0.0)) break;                              /* every lane is finished */
         /* ---- walk: candidates whose leaf overlaps the grown cohort box --------------------------*/
         CandList cl{cand, cand_cap, 0, st};
-        GatherVisitor<NDIM> V{tree, dp, cl, {0, 0, 0}, {0, 0, 0}};
+        GatherVisitorF<NDIM> V{tree.nodeb, wbx, cl, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, 0, 0};
         const double R = dp.kernrange*hmax;
-        bool crosses = false;
+        bool crosses = false, wide = false;
 #pragma unroll
         for (int k = 0; k < NDIM; k++) {
-          V.smin[k] = cmin[k] - R; V.smax[k] = cmax[k] + R;
-          if (dp.periodic[k] && (V.smin[k] < dp.boxmin[k] || V.smax[k] > dp.boxmax[k] ||
-                                 V.smax[k] - V.smin[k] > dp.boxhalf[k])) crosses = true;
+          const double lo = cmin[k] - R, hi = cmax[k] + R;
+          V.smin[k] = __double2float_rd(lo); V.smax[k] = __double2float_ru(hi);
+          if (dp.periodic[k] && (lo < dp.boxmin[k] || hi > dp.boxmax[k] || hi - lo > dp.boxhalf[k])) crosses = true;
+          if (dp.periodic[k] && 0.5*(hi - lo) >= 0.49*dp.boxsize[k]) wide = true;
         }
-        if (!warp_walk<NB_WALK_STACK>(tree, stack, V, st)) { overflow = true; break; }
+        __syncwarp();
+        if (!warp_walk_f<NB_WALK_STACK>(tree.ltot, stack, V, st)) { overflow = true; break; }
         const int ncand = cl.n;
 
-        /* ---- phase 1: per-lane neighbour lists within kernrange*hmax of the lane's leaf -------------*/
-        const double R2 = krs*hmax_l*hmax_l*(1.0 + 1.0e-12);
+        /* ---- phase 1: per-lane candidate lists on the FP32 pipe.  The list only has to be a SUPERSET
+         *      of the particles inside kernrange*h for every h <= hmax_l (membership is decided in
+         *      phase 2 by the exact ssqd < kernrangesqd test), so positions relative to the cohort
+         *      centre, scaled by the search radius, are compared in single precision with a 1e-3
+         *      margin; lanes whose radius is tiny against the cohort size keep every candidate. -------*/
+        const double sc = 1.0/R;
+        float xf[3] = {0.f, 0.f, 0.f};
+        float thr = -1.0f;
+        if (!fin) {
+          double diag2 = 0.0;
+#pragma unroll
+          for (int k = 0; k < NDIM; k++) {
+            xf[k] = (float)((x[k] - 0.5*(cmin[k] + cmax[k]))*sc);
+            diag2 += 0.25*(cmax[k] - cmin[k])*(cmax[k] - cmin[k]);
+          }
+          const double q = hmax_l/hmax;
+          thr = __double2float_ru(q*q*1.001);
+          if (wide || diag2 > 1.0e6*krs*hmax_l*hmax_l) thr = __int_as_float(0x7f800000);
+        }
         int n = 0; bool full = false;
         for (int base = 0; base < ncand; base += 32) {
           const int jl = base + lane;
           __syncwarp();
-          if (jl < ncand) {
-            const int j = cand[jl];
-            const double2 a = geo4[2*(size_t) j], b = geo4[2*(size_t) j + 1];
-            tile[lane*4 + 0] = a.x; tile[lane*4 + 1] = a.y; tile[lane*4 + 2] = b.x; tile[lane*4 + 3] = b.y;
+          {
+            int j = -1;
+            float fx = __int_as_float(0x7f800000), fy = 0.f, fz = 0.f;
+            if (jl < ncand) {
+              j = cand[jl];
+              const double2 a = geo4[2*(size_t) j], b = geo4[2*(size_t) j + 1];
+              double dr[3] = {0, 0, 0};
+              dr[0] = a.x - 0.5*(cmin[0] + cmax[0]);
+              if (NDIM > 1) dr[1] = a.y - 0.5*(cmin[1] + cmax[1]);
+              if (NDIM > 2) dr[2] = b.x - 0.5*(cmin[2] + cmax[2]);
+              if (dp.any_periodic) wrap_dr<NDIM>(dp, dr);
+              if (b.y > 0.0) fx = (float)(dr[0]*sc);
+              fy = (float)(dr[1]*sc); fz = (float)(dr[2]*sc);
+            }
+            ftile[lane] = fx; ftile[32 + lane] = fy; ftile[64 + lane] = fz;
             tj[lane] = j;
           }
           __syncwarp();
-          const int nt = min(32, ncand - base);
-          for (int jj = 0; jj < nt; jj++) {
-            const double2 a = *reinterpret_cast<const double2*>(tile + jj*4);
-            const double2 b = *reinterpret_cast<const double2*>(tile + jj*4 + 2);
-            double dr[3] = {0, 0, 0};
-            dr[0] = a.x - x[0];
-            if (NDIM > 1) dr[1] = a.y - x[1];
-            if (NDIM > 2) dr[2] = b.x - x[2];
-            if (crosses) wrap_dr<NDIM>(dp, dr);
-            const double d2 = dot_exact<NDIM>(dr);
-            if (!fin && d2 <= R2 && b.y > 0.0) {
-              if (n < nlist_cap) { nlist[(size_t) n*32 + lane] = tj[jj]; n++; }
-              else full = true;
-            }
+          unsigned pass = filter_tile<false>(ftile, xf, thr);
+          if (n + __popc(pass) > nlist_cap) { full = true; pass = 0; }
+          while (pass) {
+            const int jj = __ffs(pass) - 1;
+            pass &= pass - 1u;
+            nlist[(size_t) n*32 + lane] = tj[jj];
+            n++;
           }
         }
         if (__any_sync(FULLMASK, full)) {
           if (lane == 0) atomicExch(&st->err_nlist_overflow, 1);
           overflow = true; break;
         }
-        int nmax = n;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(FULLMASK, nmax, o));
         loc_cand += (unsigned long long) ncand;
+        __syncwarp();                                          /* tile region becomes the record stages */
 
-        /* ---- phase 2: ComputeH (GradhSph.cpp:142-326) over the lane's own list ------------------------*/
+        /* ---- phase 2: ComputeH (GradhSph.cpp:142-326) over the lane's own list.  Per list slot the
+         *      warp gathers the 32 (x,y,z,m) records cooperatively (two lanes per record, 16-byte
+         *      cp.async copies into a padded stage, double buffered). -----------------------------------*/
+        auto gather = [&](int jv, double2* buf) {
+#pragma unroll
+          for (int r = 0; r < 2; r++) {
+            const int src = r*16 + (lane >> 1);
+            const int jj = __shfl_sync(FULLMASK, jv, src);
+            if (jj >= 0) cp_async16(buf + src*DENS_REC_STRIDE + (lane & 1), geo4 + 2*(size_t) jj + (lane & 1));
+          }
+          cp_async_commit();
+        };
         double h = h0, hlo = 0.0, hup = hmax_l, rho = 0.0, invom = 0.0, zeta = 0.0;
         int iter = 0, state = fin ? 1 : 0;     /* 0 iterating, 1 left the loop, 2 need bigger list, 3 failed */
         while (__any_sync(FULLMASK, state == 0)) {
           const double invh = 1.0/h, invhsqd = invh*invh;
           double s_rho = 0.0, s_om = 0.0, s_ze = 0.0;
           const int kend = state == 0 ? n : 0;
+          int nmax = kend;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(FULLMASK, nmax, o));
+          int jc = (0 < kend) ? nlist[lane] : -1;
+          int jn = (1 < kend) ? nlist[32 + lane] : -1;
+          gather(jc, stage);
           for (int k = 0; k < nmax; k++) {
-            if (k < kend) {
-              const int j = nlist[(size_t) k*32 + lane];
-              const double2 a = geo4[2*(size_t) j], b = geo4[2*(size_t) j + 1];
+            const double2* buf = stage + (k & 1)*32*DENS_REC_STRIDE;
+            const bool more = k + 1 < nmax;
+            if (more) gather(jn, stage + ((k + 1) & 1)*32*DENS_REC_STRIDE);
+            const int jnn = (k + 2 < kend) ? nlist[(size_t)(k + 2)*32 + lane] : -1;
+            if (more) cp_async_wait<1>(); else cp_async_wait<0>();
+            __syncwarp();
+            if (jc >= 0) {
+              const double2 a = buf[lane*DENS_REC_STRIDE], b = buf[lane*DENS_REC_STRIDE + 1];
               double dr[3] = {0, 0, 0};
               dr[0] = a.x - x[0];
               if (NDIM > 1) dr[1] = a.y - x[1];
@@ -228,6 +274,8 @@ density_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict_
                 s_ze += b.y*wze;
               }
             }
+            __syncwarp();
+            jc = jn; jn = jnn;
           }
           if (state == 0) {
             /* fixed-point / bisection update (GradhSph.cpp:206-257) */
@@ -309,8 +357,8 @@ template <int NDIM, int KERN, bool TAB>
 int launch_density(gsph_handle* h)
 {
   const int Lc = cohort_level_for(h->N, h->tree.ltot, 32);
-  const size_t smem = (TAB ? 3*GSPH_TABLE_RES*sizeof(double) : 0) + DENS_WARPS*32*4*sizeof(double)
-                      + DENS_WARPS*32*sizeof(int) + DENS_WARPS*NB_WALK_STACK*sizeof(int);
+  static_assert(DENS_WARP_D2*sizeof(double2) >= NB_WALK_STACK*sizeof(int), "walk stack must fit the stage region");
+  const size_t smem = (TAB ? 3*GSPH_TABLE_RES*sizeof(double) : 0) + DENS_WARPS*DENS_WARP_D2*sizeof(double2);
   auto kern = density_kernel<NDIM, KERN, TAB>;
   CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   int bps = 0;

@@ -179,6 +179,18 @@ struct KernelEval {
     if (TAB) { if (s >= kr) return 1.0/s; return tab[5*GSPH_TABLE_RES + (int)(s*res_invkr)]; }
     return kern_analytic<KERN, NDIM>(5, s, kn);
   }
+  /* invh^2 * wgrav(s) and invh * wpot(s) for s = drmag*invh.  Outside the kernel both reduce to the
+     Newtonian 1/drmag^2 and 1/drmag, taken from the caller's 1/drmag instead of two more divisions
+     (the reference evaluates invh^2 * (1/s^2); the two agree to rounding).                        */
+  __device__ __forceinline__ void grav_terms(double s, double invh, double invdr, double& g, double& p) const
+  {
+    if (s >= kr) { g = invdr*invdr; p = invdr; return; }
+    if (TAB) {
+      const int idx = (int)(s*res_invkr);
+      g = invh*invh*tab[4*GSPH_TABLE_RES + idx]; p = invh*tab[5*GSPH_TABLE_RES + idx];
+    }
+    else { g = invh*invh*kern_analytic<KERN, NDIM>(4, s, kn); p = invh*kern_analytic<KERN, NDIM>(5, s, kn); }
+  }
 };
 
 /*------------------------------------------------------------------------------------------------
@@ -292,3 +304,151 @@ struct CandList {
     return true;
   }
 };
+
+/*------------------------------------------------------------------------------------------------
+ * Single-precision walk machinery for the neighbour searches (density gather walk, force
+ * scatter-gather walk).  The walks only have to produce a SUPERSET of the true neighbours -- the
+ * exact predicate is applied afterwards in double precision -- so the node boxes are kept as
+ * outward-rounded floats (TreeDev::nodeb / nodeh, 32 B each incl. first/count) and compared on the
+ * FP32 pipe.  Periodic axes use the centre/half-width form with an explicit slack that covers the
+ * float rounding of the box coordinates.
+ *-----------------------------------------------------------------------------------------------*/
+struct WalkBox {            /* per-kernel constants of the float box tests */
+  float size[3], half[3], slack[3];
+  int periodic[3];
+  __device__ __forceinline__ WalkBox(const DevParams& dp)
+  {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      periodic[k] = dp.periodic[k];
+      size[k] = (float) dp.boxsize[k]; half[k] = (float) dp.boxhalf[k];
+      slack[k] = 2.0e-6f*(float)(fabs(dp.boxmin[k]) + fabs(dp.boxmax[k]) + dp.boxsize[k]);
+    }
+  }
+};
+
+template <int NDIM>
+__device__ __forceinline__ bool fboxes_overlap(const WalkBox& wb, const float (&amin)[3], const float (&amax)[3],
+                                               const float4& bmin, const float4& bmax, bool& wrapped)
+{
+  const float bmn[3] = {bmin.x, bmin.y, bmin.z}, bmx[3] = {bmax.x, bmax.y, bmax.z};
+#pragma unroll
+  for (int k = 0; k < NDIM; k++) {
+    if (!wb.periodic[k]) { if (bmx[k] < amin[k] || bmn[k] > amax[k]) return false; }
+    else {
+      const float hw = 0.5f*(amax[k] - amin[k]) + 0.5f*(bmx[k] - bmn[k]) + wb.slack[k];
+      float d = fabsf(0.5f*(amin[k] + amax[k]) - 0.5f*(bmn[k] + bmx[k]));
+      if (d + hw > wb.half[k]) wrapped = true;
+      d = fminf(d, wb.size[k] - d);
+      if (d > hw) return false;
+    }
+  }
+  return true;
+}
+
+/* same traversal as warp_walk, for visitors that read the packed float node records themselves
+ * (test() returns 0 for empty nodes and remembers first/count for emit())                        */
+template <int STACKCAP, class Visitor>
+__device__ __forceinline__ bool warp_walk_f(int ltot, int* stack, Visitor& V, DevStatus* st)
+{
+  const int lane = threadIdx.x & 31;
+  const int leaf0 = (1 << ltot) - 1;
+  int sp = 1;
+  if (lane == 0) stack[0] = 0;
+  __syncwarp();
+  while (sp > 0) {
+    const int take = sp < 32 ? sp : 32;
+    int node = -1;
+    if (lane < take) node = stack[sp - 1 - lane];
+    sp -= take;
+    __syncwarp();
+    const bool leaf = node >= leaf0;
+    int code = 0;
+    if (node >= 0) code = V.test(node, leaf);
+    const bool push = (code == 1) && !leaf;
+    const unsigned pm = __ballot_sync(FULLMASK, push);
+    const int npush = __popc(pm);
+    if (sp + 2*npush > STACKCAP) {
+      if (lane == 0) atomicExch(&st->err_stack_overflow, 1);
+      return false;
+    }
+    if (push) {
+      const int off = __popc(pm & ((1u << lane) - 1u));
+      stack[sp + 2*off]     = 2*node + 2;
+      stack[sp + 2*off + 1] = 2*node + 1;
+    }
+    sp += 2*npush;
+    if (!V.emit(code == 1 && leaf, lane)) return false;
+    __syncwarp();
+  }
+  return true;
+}
+
+/* append the slab [first, first+cnt) of every lane with take = true to the candidate list */
+__device__ __forceinline__ bool cand_append_range(CandList& cl, int first, int cnt, bool take, int lane)
+{
+  if (!take) cnt = 0;
+  int total;
+  const int off = warp_excl_scan(cnt, lane, total);
+  if (total == 0) return true;
+  if (cl.n + total > cl.cap) {
+    if (lane == 0) { atomicExch(&cl.st->err_cand_overflow, 1); atomicMax(&cl.st->cand_need, (unsigned long long)(cl.n + total)); }
+    return false;
+  }
+  for (int i = 0; i < cnt; i++) cl.list[cl.n + off + i] = first + i;
+  cl.n += total;
+  return true;
+}
+
+/*------------------------------------------------------------------------------------------------
+ * Packed-FP32 candidate filter (Blackwell FADD2 / FMUL2 / FFMA2: two candidates per instruction).
+ * The tile holds 32 candidates as SoA floats (x[32] y[32] z[32] w[32]); a lane tests all of them
+ * against its own position and returns the bitmap of candidates with d^2 < max(thr, w_j) (force
+ * pass) or d^2 < thr (density pass, USEW = false).  Unused tile slots must hold x = +inf.
+ *-----------------------------------------------------------------------------------------------*/
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t f2_pack(float lo, float hi)
+{ return ((f32x2_t) __float_as_uint(hi) << 32) | (f32x2_t) __float_as_uint(lo); }
+__device__ __forceinline__ f32x2_t f2_sub(f32x2_t a, f32x2_t b) { f32x2_t d; asm("sub.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2_t f2_mul(f32x2_t a, f32x2_t b) { f32x2_t d; asm("mul.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2_t f2_fma(f32x2_t a, f32x2_t b, f32x2_t c) { f32x2_t d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+
+template <bool USEW>
+__device__ __forceinline__ unsigned filter_tile(const float* tile /* x|y|z|w, 32 each */, const float (&xf)[3], float thr)
+{
+  const f32x2_t X = f2_pack(xf[0], xf[0]), Y = f2_pack(xf[1], xf[1]), Z = f2_pack(xf[2], xf[2]);
+  const ulonglong2* tx = reinterpret_cast<const ulonglong2*>(tile);
+  const ulonglong2* ty = reinterpret_cast<const ulonglong2*>(tile + 32);
+  const ulonglong2* tz = reinterpret_cast<const ulonglong2*>(tile + 64);
+  const float4* tw = reinterpret_cast<const float4*>(tile + 96);
+  unsigned pass = 0;
+#pragma unroll
+  for (int q = 0; q < 8; q++) {                      /* 4 candidates per step */
+    const ulonglong2 ax = tx[q], ay = ty[q], az = tz[q];
+    const f32x2_t dx0 = f2_sub(ax.x, X), dx1 = f2_sub(ax.y, X);
+    const f32x2_t dy0 = f2_sub(ay.x, Y), dy1 = f2_sub(ay.y, Y);
+    const f32x2_t dz0 = f2_sub(az.x, Z), dz1 = f2_sub(az.y, Z);
+    const f32x2_t s0 = f2_fma(dz0, dz0, f2_fma(dy0, dy0, f2_mul(dx0, dx0)));
+    const f32x2_t s1 = f2_fma(dz1, dz1, f2_fma(dy1, dy1, f2_mul(dx1, dx1)));
+    const float d0 = __uint_as_float((unsigned) s0), d1 = __uint_as_float((unsigned)(s0 >> 32));
+    const float d2 = __uint_as_float((unsigned) s1), d3 = __uint_as_float((unsigned)(s1 >> 32));
+    float t0 = thr, t1 = thr, t2 = thr, t3 = thr;
+    if (USEW) { const float4 w = tw[q]; t0 = fmaxf(thr, w.x); t1 = fmaxf(thr, w.y); t2 = fmaxf(thr, w.z); t3 = fmaxf(thr, w.w); }
+    if (d0 < t0) pass |= 1u << (4*q);
+    if (d1 < t1) pass |= 2u << (4*q);
+    if (d2 < t2) pass |= 4u << (4*q);
+    if (d3 < t3) pass |= 8u << (4*q);
+  }
+  return pass;
+}
+
+/* 16-byte asynchronous global->shared copies (LDGSTS): the gather of the next neighbour slot is in
+ * flight while the terms of the current one are evaluated.                                         */
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
+{
+  const unsigned s = (unsigned) __cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" :: "r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int NPENDING>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(NPENDING) : "memory"); }

@@ -37,8 +37,9 @@
 #define GRAV_STACK 512                 /* (node, mask) pairs per warp */
 #define CELL_TILE 32
 #define CELL_BUF 64
-#define DIR_TILE 8
-#define DIR_BUF 40
+#define DIR_PART 128                   /* staged source particles per direct tile */
+#define DIR_TILE_MAX 32                /* direct leaves per tile: DIR_PART/(4*T) */
+#define DIR_BUF (DIR_TILE_MAX + 32)
 #define GRAV_LEAVES 8                  /* leaves per cohort: 4 lanes each */
 
 namespace {
@@ -49,8 +50,9 @@ struct WarpShared {
   int cell_node[CELL_BUF]; unsigned cell_mask[CELL_BUF];
   int dir_node[DIR_BUF]; unsigned dir_mask[DIR_BUF];
   double cell_data[CELL_TILE][9];      /* com xyz, m, q0..q4 */
-  double dir_data[DIR_TILE*GRAV_NT][5];/* x, y, z, m, hrangesqd */
-  int dir_count[DIR_TILE];
+  double dir_data[DIR_PART][5];        /* x, y, z, m, hrangesqd of the staged source particles */
+  int dir_src[DIR_PART];               /* tree-order index of every staged source particle */
+  int dir_off[DIR_TILE_MAX], dir_count[DIR_TILE_MAX];
 };
 
 struct FastMp { double ac[3], q[6], pot; };   /* dphi == ac for HoT = false */
@@ -67,6 +69,8 @@ gravity_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* wo
   const int ncohort = 1 << cohort_level;
   const int nl = 1 << (tree.ltot - cohort_level);          /* leaves per cohort (<= 8) */
   const int myl = lane >> 2, sub = lane & 3;               /* my leaf inside the cohort, my slot */
+  constexpr int DIR_TILE = DIR_PART/(4*T);               /* direct leaves per tile (<= 4*T particles each) */
+  static_assert(DIR_TILE <= DIR_TILE_MAX, "direct tile");
   constexpr bool FAST = (MULTIPOLE == GSPH_MULTIPOLE_FAST_MONOPOLE || MULTIPOLE == GSPH_MULTIPOLE_FAST_QUADRUPOLE);
   constexpr bool QUAD = (MULTIPOLE == GSPH_MULTIPOLE_QUADRUPOLE || MULTIPOLE == GSPH_MULTIPOLE_FAST_QUADRUPOLE);
   unsigned long long loc_direct = 0, loc_cells = 0, loc_part = 0;
@@ -133,9 +137,23 @@ gravity_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* wo
         }
       }
       __syncwarp();
-      /* fast multipoles: the 4 lanes of a leaf take every 4th entry; otherwise every lane takes all */
-      for (int e = FAST ? sub : 0; e < n; e += FAST ? 4 : 1) {
-        if (!((S.cell_mask[e] >> myl) & 1u)) continue;
+      /* every leaf (4 lanes) visits only the entries whose mask names it: one ballot per leaf gives
+         the leaf's entry bitmap; with fast multipoles the 4 lanes split the set bits round-robin,
+         otherwise each lane (a different target particle) takes them all */
+      unsigned ebits = 0;
+      {
+        const unsigned mm = lane < n ? S.cell_mask[lane] : 0u;
+#pragma unroll
+        for (int l = 0; l < GRAV_LEAVES; l++) {
+          const unsigned bl = __ballot_sync(FULLMASK, (mm >> l) & 1u);
+          if (l == myl) ebits = bl;
+        }
+      }
+      if (FAST) { for (int q = 0; q < sub; q++) ebits &= ebits - 1u; }
+      while (ebits) {
+        const int e = __ffs(ebits) - 1;
+        ebits &= ebits - 1u;
+        if (FAST) { ebits &= ebits - 1u; ebits &= ebits - 1u; ebits &= ebits - 1u; }
         ncell_mine++;
         const double cx = S.cell_data[e][0], cy = S.cell_data[e][1], cz = S.cell_data[e][2], cm = S.cell_data[e][3];
         double q0 = 0, q1 = 0, q2 = 0, q3 = 0, q4 = 0;
@@ -205,27 +223,40 @@ gravity_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* wo
     };
 
     auto consume_direct = [&](int n0, int n) {
-      /* stage the particles of direct leaves [n0, n0+n), n <= DIR_TILE */
+      /* stage the particles of direct leaves [n0, n0+n), n <= DIR_TILE, compactly */
       __syncwarp();
-      for (int s = lane; s < n*GRAV_NT; s += 32) {
-        const int e = s/GRAV_NT, k = s - e*GRAV_NT;
-        const int ln = S.dir_node[n0 + e];
-        const int lf = tree.first[ln], lc = tree.count[ln];
-        if (k == 0) S.dir_count[e] = lc;
-        if (k < lc) {
-          const int j = lf + k;
-          const bool dead = ((unsigned) P.i[I_FLAGS][j]) & GSPH_FLAG_DEAD;
-          S.dir_data[s][0] = P.f[F_RX][j]; S.dir_data[s][1] = P.f[F_RY][j]; S.dir_data[s][2] = P.f[F_RZ][j];
-          S.dir_data[s][3] = dead ? 0.0 : P.f[F_M][j]; S.dir_data[s][4] = dead ? -1.0 : P.f[F_HR2][j];
+      int lf = 0, lc = 0;
+      if (lane < n) { const int ln = S.dir_node[n0 + lane]; lf = tree.first[ln]; lc = tree.count[ln]; }
+      int tot;
+      const int off = warp_excl_scan(lc, lane, tot);
+      if (lane < n) { S.dir_off[lane] = off; S.dir_count[lane] = lc; }
+      for (int k = 0; k < lc; k++) S.dir_src[off + k] = lf + k;
+      unsigned ebits = 0;
+      {
+        const unsigned mm = lane < n ? S.dir_mask[n0 + lane] : 0u;
+#pragma unroll
+        for (int l = 0; l < GRAV_LEAVES; l++) {
+          const unsigned bl = __ballot_sync(FULLMASK, (mm >> l) & 1u);
+          if (l == myl) ebits = bl;
         }
       }
       __syncwarp();
-      for (int e = 0; e < n; e++) {
-        if (!((S.dir_mask[n0 + e] >> myl) & 1u)) continue;
-        const int lc = S.dir_count[e];
-        if (sub == 0) ndir_mine += lc;
-        for (int k = 0; k < lc; k++) {
-          const double* pj = S.dir_data[e*GRAV_NT + k];
+      for (int s = lane; s < tot; s += 32) {
+        const int j = S.dir_src[s];
+        const bool dead = ((unsigned) P.i[I_FLAGS][j]) & GSPH_FLAG_DEAD;
+        S.dir_data[s][0] = P.f[F_RX][j]; S.dir_data[s][1] = P.f[F_RY][j]; S.dir_data[s][2] = P.f[F_RZ][j];
+        S.dir_data[s][3] = dead ? 0.0 : P.f[F_M][j]; S.dir_data[s][4] = dead ? -1.0 : P.f[F_HR2][j];
+      }
+      __syncwarp();
+      /* the 4 lanes of a leaf (different target particles) visit the leaf's own entries only */
+      while (ebits) {
+        const int e = __ffs(ebits) - 1;
+        ebits &= ebits - 1u;
+        const int o = S.dir_off[e], nsrc = S.dir_count[e];
+        if (sub == 0) ndir_mine += nsrc;
+#pragma unroll 2
+        for (int k = 0; k < nsrc; k++) {
+          const double* pj = S.dir_data[o + k];
           const double xj = pj[0], yj = pj[1], zj = pj[2], mj = pj[3], hr2j = pj[4];
 #pragma unroll
           for (int t = 0; t < T; t++) {
@@ -265,15 +296,17 @@ gravity_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* wo
           const double rx = tree.rcell[0][node], ry = tree.rcell[1][node], rz = tree.rcell[2][node];
           const double crmax = tree.rmax[node], cdist = tree.cdistsqd[node];
           const double chr = __dmul_rn(dp.kernrange, tree.hmax[node]);
-#pragma unroll
-          for (int l = 0; l < GRAV_LEAVES; l++) {
-            if (!((mask >> l) & 1u)) continue;
+          /* only the leaves still undecided for this node (set bits of the mask) are evaluated */
+          unsigned todo = mask;
+          while (todo) {
+            const int l = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            const double* lg = S.leafgeom[l];
             double dr[3];
-            dr[0] = __dadd_rn(rx, -S.leafgeom[l][0]); dr[1] = __dadd_rn(ry, -S.leafgeom[l][1]);
-            dr[2] = __dadd_rn(rz, -S.leafgeom[l][2]);
+            dr[0] = __dadd_rn(rx, -lg[0]); dr[1] = __dadd_rn(ry, -lg[1]); dr[2] = __dadd_rn(rz, -lg[2]);
             const double drsqd = dot_exact<3>(dr);
-            const double rmax = S.leafgeom[l][3];
-            const double a = __dadd_rn(__dadd_rn(crmax, rmax), S.leafgeom[l][4]);
+            const double rmax = lg[3];
+            const double a = __dadd_rn(__dadd_rn(crmax, rmax), lg[4]);
             const double b = __dadd_rn(__dadd_rn(rmax, crmax), chr);
             /* Tree.cpp:660-731: overlap -> open; else MAC (Tree.h:413-432 geometric: open iff drsqd < cdistsqd) */
             if (drsqd <= __dmul_rn(a, a) || drsqd <= __dmul_rn(b, b) || drsqd < cdist) open_mask |= 1u << l;

@@ -55,6 +55,12 @@ struct TreeDev {
   double* hmax = nullptr;
   double* cdistsqd = nullptr;     /* geometric MAC distance^2, KDTree.cpp:917              */
   double* q[5] = {0, 0, 0, 0, 0}; /* traceless quadrupole, KDTree.cpp:937-1000             */
+  /* single-precision node records for the neighbour walks (candidate sets only have to be
+     supersets, so boxes rounded OUTWARD to float are enough and cost a third of the loads):
+       nodeb[2n]   = (bbmin.xyz, first as int bits)   nodeb[2n+1] = (bbmax.xyz, count as int bits)
+       nodeh[2n]   = (hbmin.xyz, 0)                   nodeh[2n+1] = (hbmax.xyz, 0)                 */
+  float4* nodeb = nullptr;
+  float4* nodeh = nullptr;
 };
 
 struct DevParams {

@@ -67,6 +67,31 @@ struct ScatterGatherVisitor {
   }
 };
 
+/* scatter-gather walk on the outward-rounded float boxes (superset of
+ * Tree::ComputeNeighbourAndGhostList): open when cohort.bb meets node.hbox or cohort.hbox meets node.bb */
+template <int NDIM>
+struct ScatterGatherVisitorF {
+  const float4* __restrict__ nodeb; const float4* __restrict__ nodeh; const WalkBox& wb; CandList& cl;
+  float bmin[3], bmax[3], hmin[3], hmax[3];
+  bool needwrap;
+  int first, count;
+  __device__ __forceinline__ int test(int node, bool leaf)
+  {
+    const float4 lo = nodeb[2*(size_t) node], hi = nodeb[2*(size_t) node + 1];
+    first = __float_as_int(lo.w); count = __float_as_int(hi.w);
+    if (count <= 0) return 0;
+    bool wrapped = false;
+    bool open = fboxes_overlap<NDIM>(wb, hmin, hmax, lo, hi, wrapped);
+    if (!open) {
+      const float4 hlo = nodeh[2*(size_t) node], hhi = nodeh[2*(size_t) node + 1];
+      open = fboxes_overlap<NDIM>(wb, bmin, bmax, hlo, hhi, wrapped);
+    }
+    if (open && leaf && wrapped) needwrap = true;
+    return open ? 1 : 0;
+  }
+  __device__ __forceinline__ bool emit(bool take, int lane) { return cand_append_range(cl, first, count, take, lane); }
+};
+
 struct Target {
   double x[3], v[3];
   double invh, hfac, invrho, pfac, sound, u, alpha, press, zeta, hr2, m, rho, invomega;
@@ -81,30 +106,34 @@ struct Neib {            /* one gathered force record (frec, 128 B) */
   int level;
 };
 
-/* frec layout: 0 x 1 y 2 z 3 vx | 4 vy 5 vz 6 m 7 1/h | 8 hfactor 9 1/rho 10 P*invomega/rho^2 11 sound |
- *              12 u 13 alpha 14 zeta 15 (pressure if acond = price2008, else level)                   */
+/* frec layout (16 doubles = 128 B, eight 16-byte chunks):
+ *   0 x 1 y | 2 z 3 hrangesqd | 4 vx 5 vy | 6 vz 7 m | 8 1/h 9 hfactor | 10 1/rho 11 P*invomega/rho^2 |
+ *   12 sound 13 zeta | 14 u 15 aux      aux = alpha for the time-dependent viscosity switches, else level.
+ * Chunks 0-1 double as the geometry record of the candidate filter.  Dead particles get x = BIG and
+ * hrangesqd = -1 so that no predicate ever accepts them.                                            */
 template <int NDIM>
-__global__ void pack_force_kernel(int N, PartView P, int price2008, double* __restrict__ geoh,
-                                  double* __restrict__ frec)
+__global__ void pack_force_kernel(int N, PartView P, int aux_is_alpha, double* __restrict__ frec,
+                                  double* __restrict__ geoh)
 {
   const int p = blockIdx.x*blockDim.x + threadIdx.x;
   if (p >= N) return;
   const bool dead = ((unsigned) P.i[I_FLAGS][p]) & GSPH_FLAG_DEAD;
   const double x = P.f[F_RX][p], y = NDIM > 1 ? P.f[F_RY][p] : 0.0, z = NDIM > 2 ? P.f[F_RZ][p] : 0.0;
   const double h = P.f[F_H][p], rho = P.f[F_RHO][p], pr = P.f[F_PRESS][p];
-  double2* g = reinterpret_cast<double2*>(geoh) + 2*(size_t) p;
-  g[0] = make_double2(dead ? GSPH_BIG : x, y);
-  g[1] = make_double2(z, dead ? -1.0 : P.f[F_HR2][p]);
   double2* r = reinterpret_cast<double2*>(frec) + 8*(size_t) p;
-  r[0] = make_double2(x, y);
-  r[1] = make_double2(z, P.f[F_VX][p]);
-  r[2] = make_double2(NDIM > 1 ? P.f[F_VY][p] : 0.0, NDIM > 2 ? P.f[F_VZ][p] : 0.0);
-  r[3] = make_double2(P.f[F_M][p], 1.0/h);
-  r[4] = make_double2(P.f[F_HFAC][p], 1.0/rho);
-  r[5] = make_double2((pr*P.f[F_INVOMEGA][p])/(rho*rho), P.f[F_SOUND][p]);
-  r[6] = make_double2(P.f[F_U][p], P.f[F_ALPHA][p]);
-  r[7] = make_double2(P.f[F_ZETA][p], price2008 ? pr : (double) P.i[I_LEVEL][p]);
+  r[0] = make_double2(dead ? GSPH_BIG : x, y);
+  r[1] = make_double2(z, dead ? -1.0 : P.f[F_HR2][p]);
+  double2* g = reinterpret_cast<double2*>(geoh) + 2*(size_t) p;   /* compact copy for the candidate filter */
+  g[0] = r[0]; g[1] = r[1];
+  r[2] = make_double2(P.f[F_VX][p], NDIM > 1 ? P.f[F_VY][p] : 0.0);
+  r[3] = make_double2(NDIM > 2 ? P.f[F_VZ][p] : 0.0, P.f[F_M][p]);
+  r[4] = make_double2(1.0/h, P.f[F_HFAC][p]);
+  r[5] = make_double2(1.0/rho, (pr*P.f[F_INVOMEGA][p])/(rho*rho));
+  r[6] = make_double2(P.f[F_SOUND][p], P.f[F_ZETA][p]);
+  r[7] = make_double2(P.f[F_U][p], aux_is_alpha ? P.f[F_ALPHA][p] : (double) P.i[I_LEVEL][p]);
 }
+
+#define REC_STRIDE 9      /* double2 units per staged record: 144 B, conflict-free for 16-byte accesses */
 
 /* One (target, neighbour) pair.  GRAV selects ComputeSphHydroGravForces (GradhSph.cpp:498-572),
  * otherwise ComputeSphHydroForces (:384-448); HYDRO = false gives ComputeSphGravForces (:610-645). */
@@ -113,20 +142,22 @@ __device__ __forceinline__ void pair_terms(const DevParams& dp, const KE& K, Tar
                                            double drsqd, const Neib& nb)
 {
   const double mj = nb.m, invh_j = nb.invh, hfac_j = nb.hfac;
-  double drmag, dvdr = 0.0;
+  double drmag, dvdr = 0.0, invdr = 0.0;
+  /* drmag feeds the (truncating) table index and keeps the reference's correctly rounded sqrt; the
+     unit vector only needs 1/drmag to rounding, so rsqrt replaces the division */
   if (!GRAV) {
     drmag = sqrt(drsqd);
     if (drmag > 0.0) {
-      const double inv = 1.0/drmag;
+      invdr = rsqrt(drsqd);
 #pragma unroll
-      for (int k = 0; k < NDIM; k++) dr[k] *= inv;
+      for (int k = 0; k < NDIM; k++) dr[k] *= invdr;
     }
   }
   else {
     drmag = sqrt(drsqd + GSPH_SMALL);
-    const double inv = 1.0/drmag;
+    invdr = rsqrt(drsqd + GSPH_SMALL);
 #pragma unroll
-    for (int k = 0; k < NDIM; k++) dr[k] *= inv;
+    for (int k = 0; k < NDIM; k++) dr[k] *= invdr;
   }
   const double w1i = K.w1(drmag*t.invh), w1j = K.w1(drmag*invh_j);
   const double wkerni = t.hfac*w1i, wkernj = hfac_j*w1j;
@@ -158,12 +189,13 @@ __device__ __forceinline__ void pair_terms(const DevParams& dp, const KE& K, Tar
     for (int k = 0; k < NDIM; k++) t.a[k] += mj*dr[k]*paux;
   }
   if (GRAV) {
-    const double si = drmag*t.invh, sj = drmag*invh_j;
-    const double gaux = 0.5*(t.invh*t.invh*K.wgrav(si) + t.zeta*wkerni +
-                             invh_j*invh_j*K.wgrav(sj) + nb.zeta*wkernj);
+    double gi, pi, gj, pj;
+    K.grav_terms(drmag*t.invh, t.invh, invdr, gi, pi);
+    K.grav_terms(drmag*invh_j, invh_j, invdr, gj, pj);
+    const double gaux = 0.5*(gi + t.zeta*wkerni + gj + nb.zeta*wkernj);
 #pragma unroll
     for (int k = 0; k < NDIM; k++) t.at[k] += mj*dr[k]*gaux;
-    t.gpot += 0.5*mj*(t.invh*K.wpot(si) + invh_j*K.wpot(sj));
+    t.gpot += 0.5*mj*(pi + pj);
   }
   if (HYDRO || !GRAV) t.levelneib = max(t.levelneib, nb.level);
   t.nngb++;
@@ -171,33 +203,41 @@ __device__ __forceinline__ void pair_terms(const DevParams& dp, const KE& K, Tar
 
 /*------------------------------------------------------------------------------------------------
  * One warp per cohort (KD-tree node of <= 32 particles), one target per lane.
- *  phase 1  stream the candidate slabs through a shared tile of packed (x,y,z,hrangesqd) records
- *           and let every lane append the ids that satisfy the reference's neighbour predicate
- *           (exact arithmetic) to its own list ([k][lane] rows in global scratch);
- *  phase 2  every lane walks its own list, gathers the 128-byte force record of the neighbour and
- *           evaluates the pair terms -- all 32 lanes busy in every instruction.
+ *  phase 1  candidate filter on the FP32 pipe: the candidate slabs are streamed through a shared
+ *           tile of float4 records (position relative to the cohort centre, scaled by the largest
+ *           kernel range in the cohort, and hrangesqd_j) and every lane appends the ids inside
+ *           max(hrangesqd_i, hrangesqd_j)*(1 + 1e-3) to its own list ([k][lane] rows in global
+ *           scratch).  The list is a SUPERSET of the neighbours; the margin is far above the FP32
+ *           error (lanes whose range is tiny against the cohort size simply keep every candidate).
+ *  phase 2  per list slot the warp gathers the 32 force records (128 B each) cooperatively -- eight
+ *           lanes per record, 16-byte cp.async copies into a padded shared-memory stage, double
+ *           buffered so that the gather of slot k+1 overlaps the arithmetic of slot k -- then every
+ *           lane reads its own record, applies the reference's predicate (NeighbourManager.h:521)
+ *           in exact FP64 arithmetic and evaluates the pair terms.
  *-----------------------------------------------------------------------------------------------*/
 template <int NDIM, int KERN, bool TAB, bool GRAV, bool HYDRO>
-__global__ void __launch_bounds__(HYD_THREADS)
+__global__ void __launch_bounds__(HYD_THREADS, 2)
 hydro_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict__ gtables,
-             const double2* __restrict__ geoh, const double2* __restrict__ frec,
+             const double2* __restrict__ frec, const double2* __restrict__ geoh, int aux_is_alpha,
              int cohort_level, int* work_counter, int32_t* cand_all, int cand_cap,
              int32_t* nlist_all, int nlist_cap, DevStatus* st, uint8_t* done)
 {
   extern __shared__ double smem[];
   constexpr int NTAB = TAB ? (GRAV ? 3 : 1) : 0;
+  constexpr int WARP_D2 = 2*32*REC_STRIDE;              /* double2 per warp: two record stages */
   double* tab = smem;                                   /* w1 [, wgrav, wpot] */
-  double* tiles = smem + NTAB*GSPH_TABLE_RES;           /* per warp 32 x 4 doubles */
-  int* tilej = (int*)(tiles + HYD_WARPS*32*4);
-  int* stacks = tilej + HYD_WARPS*32;
+  double2* stages = reinterpret_cast<double2*>(smem + NTAB*GSPH_TABLE_RES);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (TAB) {
     for (int i = threadIdx.x; i < NTAB*GSPH_TABLE_RES; i += blockDim.x) tab[i] = gtables[3*GSPH_TABLE_RES + i];
     __syncthreads();
   }
-  double* geom = tiles + warp*32*4;
-  int* tj = tilej + warp*32;
-  int* stack = stacks + warp*NB_WALK_STACK;
+  /* the per-warp region is time-shared: walk stack | float4 tile + ids (phase 1) | record stages (phase 2) */
+  double2* stage = stages + warp*WARP_D2;
+  int* stack = reinterpret_cast<int*>(stage);
+  float* ftile = reinterpret_cast<float*>(stage);       /* x[32] | y[32] | z[32] | w[32] */
+  int* tj = reinterpret_cast<int*>(ftile + 128);
+  const WalkBox wbx(dp);
   const int gwarp = blockIdx.x*HYD_WARPS + warp;
   int32_t* cand = cand_all + (size_t) gwarp*cand_cap;
   int32_t* nlist = nlist_all + (size_t) gwarp*nlist_cap*32;
@@ -205,6 +245,7 @@ hydro_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict__ 
   const KernelEval<KERN, NDIM, TAB> K(dp, tab - 3*GSPH_TABLE_RES);
   const int ncohort = 1 << cohort_level;
   const bool price = dp.acond == GSPH_ACOND_PRICE2008;
+  const double rootR = dp.kernrange*tree.hmax[0];
   unsigned long long loc_ngb = 0, loc_cand = 0, loc_targets = 0; int loc_ngbmax = 0;
 
   while (true) {
@@ -218,13 +259,26 @@ hydro_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict__ 
 
     /* ---- walk ---------------------------------------------------------------------------------*/
     CandList cl{cand, cand_cap, 0, st};
-    ScatterGatherVisitor<NDIM> V{tree, dp, cl, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, false};
+    ScatterGatherVisitorF<NDIM> V{tree.nodeb, tree.nodeh, wbx, cl, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f},
+                                  {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, false, 0, 0};
+    double ctr[3] = {0, 0, 0}, diag2 = 0.0;
+    bool wide = false;                /* periodic images not unique about the cohort centre: keep all */
+    {
+      const float4 lo = tree.nodeb[2*(size_t) node], hi = tree.nodeb[2*(size_t) node + 1];
+      const float4 hlo = tree.nodeh[2*(size_t) node], hhi = tree.nodeh[2*(size_t) node + 1];
+      V.bmin[0] = lo.x; V.bmin[1] = lo.y; V.bmin[2] = lo.z; V.bmax[0] = hi.x; V.bmax[1] = hi.y; V.bmax[2] = hi.z;
+      V.hmin[0] = hlo.x; V.hmin[1] = hlo.y; V.hmin[2] = hlo.z; V.hmax[0] = hhi.x; V.hmax[1] = hhi.y; V.hmax[2] = hhi.z;
+    }
 #pragma unroll
     for (int k = 0; k < NDIM; k++) {
-      V.bmin[k] = tree.bbmin[k][node]; V.bmax[k] = tree.bbmax[k][node];
-      V.hmin[k] = tree.hbmin[k][node]; V.hmax[k] = tree.hbmax[k][node];
+      const double b0 = tree.bbmin[k][node], b1 = tree.bbmax[k][node];
+      ctr[k] = 0.5*(b0 + b1);
+      const double hw = 0.5*(b1 - b0);
+      diag2 += hw*hw;
+      if (dp.periodic[k] && hw + rootR >= 0.49*dp.boxsize[k]) wide = true;
     }
-    if (!warp_walk<NB_WALK_STACK>(tree, stack, V, st)) continue;
+    __syncwarp();
+    if (!warp_walk_f<NB_WALK_STACK>(tree.ltot, stack, V, st)) continue;
     const int ncand = cl.n;
     const bool wrap = dp.any_periodic && __any_sync(FULLMASK, V.needwrap);
     bool overflow = false;
@@ -257,32 +311,49 @@ hydro_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict__ 
       g.gpot = 0.0; g.dudt = 0.0; g.divv = 0.0; g.levelneib = 0; g.nngb = 0;
       if (GRAV && live) g.gpot = (g.m*g.invh)*K.wpot(0.0);          /* GradhSphTree.cpp:512 */
 
-      /* ---- phase 1: neighbour lists by the reference's predicate (NeighbourManager.h:521) -----------*/
+      /* ---- phase 1: FP32 candidate filter (superset of the neighbour list) --------------------------*/
+      double hr2max = live ? g.hr2 : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) hr2max = fmax(hr2max, __shfl_xor_sync(FULLMASK, hr2max, o));
+      if (!(hr2max > 0.0)) continue;                                  /* no live target in this block */
+      const double sc = rsqrt(hr2max), sc2 = sc*sc*1.001;
+      float xf[3] = {0.f, 0.f, 0.f};
+      float thr = -1.0f;
+      if (live) {
+#pragma unroll
+        for (int k = 0; k < NDIM; k++) xf[k] = (float)((g.x[k] - ctr[k])*sc);
+        thr = __double2float_ru(g.hr2*sc2);
+        if (wide || diag2 > 1.0e6*g.hr2) thr = __int_as_float(0x7f800000);   /* keep every candidate */
+      }
       int n = 0; bool full = false;
       for (int base = 0; base < ncand; base += 32) {
         const int jl = base + lane;
         __syncwarp();
-        if (jl < ncand) {
-          const int j = cand[jl];
-          const double2 a = geoh[2*(size_t) j], b = geoh[2*(size_t) j + 1];
-          geom[lane*4 + 0] = a.x; geom[lane*4 + 1] = a.y; geom[lane*4 + 2] = b.x; geom[lane*4 + 3] = b.y;
+        {
+          int j = -1;
+          float fx = __int_as_float(0x7f800000), fy = 0.f, fz = 0.f, fw = -1.0f;
+          if (jl < ncand) {
+            j = cand[jl];
+            const double2 a = geoh[2*(size_t) j], b = geoh[2*(size_t) j + 1];
+            double dr[3] = {0, 0, 0};
+            dr[0] = a.x - ctr[0];
+            if (NDIM > 1) dr[1] = a.y - ctr[1];
+            if (NDIM > 2) dr[2] = b.x - ctr[2];
+            if (dp.any_periodic) wrap_dr<NDIM>(dp, dr);
+            if (b.y > 0.0) { fx = (float)(dr[0]*sc); fw = __double2float_ru(b.y*sc2); }
+            fy = (float)(dr[1]*sc); fz = (float)(dr[2]*sc);
+          }
+          ftile[lane] = fx; ftile[32 + lane] = fy; ftile[64 + lane] = fz; ftile[96 + lane] = fw;
           tj[lane] = j;
         }
         __syncwarp();
-        const int nt = min(32, ncand - base);
-        for (int jj = 0; jj < nt; jj++) {
-          const double2 ga = *reinterpret_cast<const double2*>(geom + jj*4);
-          const double2 gb = *reinterpret_cast<const double2*>(geom + jj*4 + 2);
-          double dr[3] = {0, 0, 0};
-          dr[0] = ga.x - g.x[0];
-          if (NDIM > 1) dr[1] = ga.y - g.x[1];
-          if (NDIM > 2) dr[2] = gb.x - g.x[2];
-          if (wrap) wrap_dr<NDIM>(dp, dr);
-          const double drsqd = dot_exact<NDIM>(dr);
-          if (drsqd < g.hr2 || drsqd < gb.y) {
-            if (n < nlist_cap) { nlist[(size_t) n*32 + lane] = tj[jj]; n++; }
-            else full = true;
-          }
+        unsigned pass = live ? filter_tile<true>(ftile, xf, thr) : 0u;
+        if (n + __popc(pass) > nlist_cap) { full = true; pass = 0; }
+        while (pass) {
+          const int jj = __ffs(pass) - 1;
+          pass &= pass - 1u;
+          nlist[(size_t) n*32 + lane] = tj[jj];
+          n++;
         }
       }
       if (__any_sync(FULLMASK, full)) {
@@ -292,32 +363,52 @@ hydro_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict__ 
       int nmax = n;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(FULLMASK, nmax, o));
+      __syncwarp();                                                   /* tile region becomes the stages */
 
-      /* ---- phase 2: pair terms over the lane's own list ----------------------------------------------*/
+      /* ---- phase 2: cooperative double-buffered gather + pair terms -----------------------------------*/
+      auto gather = [&](int jv, double2* buf) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+          const int src = r*4 + (lane >> 3);
+          const int jj = __shfl_sync(FULLMASK, jv, src);
+          if (jj >= 0) cp_async16(buf + src*REC_STRIDE + (lane & 7), frec + 8*(size_t) jj + (lane & 7));
+        }
+        cp_async_commit();
+      };
+      int jc = (0 < n) ? nlist[lane] : -1;
+      int jn = (1 < n) ? nlist[32 + lane] : -1;
+      if (nmax > 0) gather(jc, stage);
       for (int k = 0; k < nmax; k++) {
-        if (k < n) {
-          const int j = nlist[(size_t) k*32 + lane];
-          const double2* r = frec + 8*(size_t) j;
-          const double2 r0 = r[0], r1 = r[1], r2 = r[2], r3 = r[3], r4 = r[4], r5 = r[5];
-          Neib nb;
-          nb.v[0] = r1.y; nb.v[1] = r2.x; nb.v[2] = r2.y;
-          nb.m = r3.x; nb.invh = r3.y; nb.hfac = r4.x; nb.invrho = r4.y; nb.pfac = r5.x; nb.sound = r5.y;
-          nb.u = 0.0; nb.alpha = 0.0; nb.zeta = 0.0; nb.press = 0.0; nb.level = 0;
-          if (dp.acond != GSPH_ACOND_NONE || dp.avisc >= GSPH_AVISC_MON97MM97) { const double2 r6 = r[6]; nb.u = r6.x; nb.alpha = r6.y; }
-          {
-            const double2 r7 = r[7];
-            nb.zeta = r7.x;
-            if (price) { nb.press = r7.y; nb.level = P.i[I_LEVEL][j]; }
-            else nb.level = (int) r7.y;
-          }
+        double2* buf = stage + (k & 1)*32*REC_STRIDE;
+        const bool more = k + 1 < nmax;
+        if (more) gather(jn, stage + ((k + 1) & 1)*32*REC_STRIDE);
+        const int jnn = (k + 2 < n) ? nlist[(size_t)(k + 2)*32 + lane] : -1;
+        if (more) cp_async_wait<1>(); else cp_async_wait<0>();
+        __syncwarp();
+        if (jc >= 0) {
+          const double2* r = buf + lane*REC_STRIDE;
+          const double2 r0 = r[0], r1 = r[1];
           double dr[3] = {0, 0, 0};
           dr[0] = r0.x - g.x[0];
           if (NDIM > 1) dr[1] = r0.y - g.x[1];
           if (NDIM > 2) dr[2] = r1.x - g.x[2];
           if (wrap) wrap_dr<NDIM>(dp, dr);
           const double drsqd = dot_exact<NDIM>(dr);
-          pair_terms<NDIM, GRAV, HYDRO>(dp, K, g, dr, drsqd, nb);
+          if (drsqd < g.hr2 || drsqd < r1.y) {                  /* NeighbourManager.h:521 */
+            const double2 r2 = r[2], r3 = r[3], r4 = r[4], r5 = r[5], r6 = r[6], r7 = r[7];
+            Neib nb;
+            nb.v[0] = r2.x; nb.v[1] = r2.y; nb.v[2] = r3.x;
+            nb.m = r3.y; nb.invh = r4.x; nb.hfac = r4.y; nb.invrho = r5.x; nb.pfac = r5.y;
+            nb.sound = r6.x; nb.zeta = r6.y; nb.u = r7.x;
+            nb.alpha = 0.0; nb.press = 0.0;
+            if (aux_is_alpha) { nb.alpha = r7.y; nb.level = P.i[I_LEVEL][jc]; }
+            else nb.level = (int) r7.y;
+            if (price) nb.press = P.f[F_PRESS][jc];
+            pair_terms<NDIM, GRAV, HYDRO>(dp, K, g, dr, drsqd, nb);
+          }
         }
+        __syncwarp();
+        jc = jn; jn = jnn;
       }
 
       /* ---- end-of-loop terms and write-back (GradhSph.cpp:451-457 / :576-582;
@@ -326,8 +417,8 @@ hydro_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict__ 
         const int i = ti;
         if (HYDRO) {
           g.divv *= g.invrho;
-          const double press = dp.gammam1*g.rho*g.u;                    /* eos->Pressure(parti) */
-          g.dudt -= press*g.divv*g.invrho*g.invomega;
+          const double press = dp.gammam1*P.f[F_RHO][i]*g.u;            /* eos->Pressure(parti) */
+          g.dudt -= press*g.divv*g.invrho*P.f[F_INVOMEGA][i];
 #pragma unroll
           for (int k = 0; k < NDIM; k++) P.f[F_AX + k][i] += g.a[k];
           P.f[F_DUDT][i] += g.dudt;
@@ -454,8 +545,8 @@ int launch_hydro(gsph_handle* h)
 {
   const int Lc = cohort_level_for(h->N, h->tree.ltot, 32);
   constexpr int NTAB = TAB ? (GRAV ? 3 : 1) : 0;
-  const size_t smem = NTAB*GSPH_TABLE_RES*sizeof(double) + HYD_WARPS*32*4*sizeof(double)
-                      + HYD_WARPS*32*sizeof(int) + HYD_WARPS*NB_WALK_STACK*sizeof(int);
+  static_assert(2*32*REC_STRIDE*sizeof(double2) >= NB_WALK_STACK*sizeof(int), "walk stack must fit the stage region");
+  const size_t smem = NTAB*GSPH_TABLE_RES*sizeof(double) + HYD_WARPS*2*32*REC_STRIDE*sizeof(double2);
   auto kern = hydro_kernel<NDIM, KERN, TAB, GRAV, HYDRO>;
   CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   int bps = 0;
@@ -474,11 +565,11 @@ int launch_hydro(gsph_handle* h)
   for (int k = 0; k < NF_DOUBLE; k++) P.f[k] = h->P[k];
   for (int k = 0; k < NF_INT; k++) P.i[k] = h->PI[k];
   const int N = (int) h->N;
-  pack_force_kernel<NDIM><<<(N + 255)/256, 256, 0, h->stream>>>(N, P, h->dp.acond == GSPH_ACOND_PRICE2008 ? 1 : 0,
-                                                              h->geoh, h->frec);
+  const int aux_is_alpha = (h->dp.avisc == GSPH_AVISC_MON97MM97 || h->dp.avisc == GSPH_AVISC_MON97CD2010) ? 1 : 0;
+  pack_force_kernel<NDIM><<<(N + 255)/256, 256, 0, h->stream>>>(N, P, aux_is_alpha, h->frec, h->geoh);
   KernelTimer kt(h, 1);
-  kern<<<blocks, HYD_THREADS, smem, h->stream>>>(P, h->tree, h->dp, h->tables, (const double2*) h->geoh,
-                                                 (const double2*) h->frec, Lc, h->work_counter, h->cand,
+  kern<<<blocks, HYD_THREADS, smem, h->stream>>>(P, h->tree, h->dp, h->tables, (const double2*) h->frec,
+                                                 (const double2*) h->geoh, aux_is_alpha, Lc, h->work_counter, h->cand,
                                                  (int) h->cand_cap_per_warp, h->nlist, (int) h->nlist_cap,
                                                  h->status, h->done);
   h->stats.kernel_launches += 2;

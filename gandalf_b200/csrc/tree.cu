@@ -356,6 +356,32 @@ __global__ void extrapolate_kernel(TreeDev T, double dt)
   }
 }
 
+/* outward-rounded single-precision node records for the neighbour walks (TreeDev::nodeb / nodeh) */
+template <int NDIM>
+__global__ void pack_nodes_kernel(TreeDev T, int with_bb)
+{
+  const int n = blockIdx.x*blockDim.x + threadIdx.x;
+  if (n >= T.ncell) return;
+  const int cnt = T.count[n];
+  float lo[3] = {0.f, 0.f, 0.f}, hi[3] = {0.f, 0.f, 0.f};
+  if (with_bb) {
+#pragma unroll
+    for (int k = 0; k < NDIM; k++) {
+      lo[k] = cnt > 0 ? __double2float_rd(T.bbmin[k][n]) : 3.0e38f;
+      hi[k] = cnt > 0 ? __double2float_ru(T.bbmax[k][n]) : -3.0e38f;
+    }
+    T.nodeb[2*(size_t) n] = make_float4(lo[0], lo[1], lo[2], __int_as_float(T.first[n]));
+    T.nodeb[2*(size_t) n + 1] = make_float4(hi[0], hi[1], hi[2], __int_as_float(cnt));
+  }
+#pragma unroll
+  for (int k = 0; k < NDIM; k++) {
+    lo[k] = cnt > 0 ? __double2float_rd(T.hbmin[k][n]) : 3.0e38f;
+    hi[k] = cnt > 0 ? __double2float_ru(T.hbmax[k][n]) : -3.0e38f;
+  }
+  T.nodeh[2*(size_t) n] = make_float4(lo[0], lo[1], lo[2], 0.f);
+  T.nodeh[2*(size_t) n + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
+}
+
 int alloc_tree(gsph_handle* h, int ltot)
 {
   TreeDev& T = h->tree;
@@ -364,6 +390,7 @@ int alloc_tree(gsph_handle* h, int ltot)
   if (ncell <= T.ncell_cap) return GSPH_OK;
   auto fre = [](void* p) { if (p) cudaFree(p); };
   fre(T.first); fre(T.count); fre(T.nactive); fre(T.m); fre(T.rmax); fre(T.hmax); fre(T.cdistsqd);
+  fre(T.nodeb); fre(T.nodeh); T.nodeb = T.nodeh = nullptr;
   for (int k = 0; k < 3; k++) {
     fre(T.bbmin[k]); fre(T.bbmax[k]); fre(T.hbmin[k]); fre(T.hbmax[k]);
     fre(T.rcell[k]); fre(T.com[k]); fre(T.vcom[k]);
@@ -378,6 +405,8 @@ int alloc_tree(gsph_handle* h, int ltot)
   CUDA_TRY(h, cudaMalloc(&T.rmax, cap*sizeof(double)));
   CUDA_TRY(h, cudaMalloc(&T.hmax, cap*sizeof(double)));
   CUDA_TRY(h, cudaMalloc(&T.cdistsqd, cap*sizeof(double)));
+  CUDA_TRY(h, cudaMalloc(&T.nodeb, 2*cap*sizeof(float4)));
+  CUDA_TRY(h, cudaMalloc(&T.nodeh, 2*cap*sizeof(float4)));
   for (int k = 0; k < 3; k++) {
     T.bbmin[k] = T.bbmax[k] = T.hbmin[k] = T.hbmax[k] = T.rcell[k] = T.com[k] = T.vcom[k] = nullptr;
     if (k >= nd) continue;
@@ -413,10 +442,14 @@ int stock_tree(gsph_handle* h, int full)
     const int nn = 1 << l;
     stock_level_kernel<NDIM><<<(nn + 127)/128, 128, 0, h->stream>>>(T, h->dp, l, full);
   }
-  h->stats.kernel_launches += 1 + T.ltot;
+  pack_nodes_kernel<NDIM><<<(T.ncell + 255)/256, 256, 0, h->stream>>>(T, full);
+  h->stats.kernel_launches += 2 + T.ltot;
   CUDA_TRY(h, cudaGetLastError());
   return GSPH_OK;
 }
+
+template <int NDIM>
+int build_tree_v2(gsph_handle* h);
 
 template <int NDIM>
 int build_tree_nd(gsph_handle* h, int mode, double dt)
@@ -434,7 +467,8 @@ int build_tree_nd(gsph_handle* h, int mode, double dt)
       h->sorted_valid = true; h->stats.kernel_launches++;
     }
     extrapolate_kernel<NDIM><<<(h->tree.ncell + 255)/256, 256, 0, s>>>(h->tree, dt);
-    h->stats.kernel_launches++;
+    pack_nodes_kernel<NDIM><<<(h->tree.ncell + 255)/256, 256, 0, s>>>(h->tree, 1);
+    h->stats.kernel_launches += 2;
     CUDA_TRY(h, cudaGetLastError());
     return GSPH_OK;
   }
@@ -446,6 +480,10 @@ int build_tree_nd(gsph_handle* h, int mode, double dt)
   }
 
   /* ---- full rebuild ----------------------------------------------------------------------------*/
+  {
+    static const bool use_v1 = getenv("GSPH_TREE_V1") != nullptr;   /* A/B switch: first-generation build */
+    if (!use_v1) return build_tree_v2<NDIM>(h);
+  }
   int ltot = 0;                                       /* ComputeTreeSize, KDTree.cpp:322-352 */
   while ((int64_t) h->cfg.Nleafmax*((int64_t)1 << ltot) < (int64_t) N) ltot++;
   int rc = alloc_tree(h, ltot);
@@ -538,6 +576,280 @@ int build_tree_nd(gsph_handle* h, int mode, double dt)
   }
   CUDA_TRY(h, cudaGetLastError());
   CUDA_TRY(h, cudaMemcpyAsync(h->perm, list[0][cur[0]], sizeof(int)*(size_t) N, cudaMemcpyDeviceToDevice, s));
+  gather_kernel<<<(N + 255)/256, 256, 0, s>>>(N, h->perm, Hh, Pp);
+  h->stats.kernel_launches++;
+  h->sorted_valid = true;
+  h->have_tree = true;
+  cudaEventRecord(h->evk[4][1], s); h->evk_used[4] = true;
+  cudaEventRecord(h->evk[5][0], s);
+  const int rcs = stock_tree<NDIM>(h, 1);
+  cudaEventRecord(h->evk[5][1], s); h->evk_used[5] = true;
+  return rcs;
+}
+
+/*================================================================================================
+ * Second-generation level-synchronous build.  Every per-axis list carries, next to the particle id,
+ * the particle's GLOBAL RANK along the other axes (its position in their sorted lists).  Inside a
+ * node the order of an axis list is the order of its global ranks, so "does this entry go to the
+ * right child of a node split along kd" is simply  rank_kd(entry) >= rank_kd(median entry)  --
+ * no per-particle side array, no random access inside the level loop.  Per level: one kernel per
+ * node (split axis, median, child boxes), one pass counting right-going entries per 1024-entry
+ * tile, one scan of the tile counts, one pass that scans inside the tile and scatters the
+ * (id, ranks) entries of all axis lists to the children's order (stable segmented partition).
+ *================================================================================================*/
+#define TB_THREADS 256
+#define TB_ITEMS 4
+#define TB_TILE (TB_THREADS*TB_ITEMS)
+
+template <int NDIM>
+struct ListPtrs {
+  int* ids[3][2];            /* [axis][buffer]                                                      */
+  int* rk[3][2][2];          /* [axis][q][buffer]: rank along axis (axis+1+q) % NDIM               */
+  const int* rank[3];        /* [axis][host index]: global rank                                     */
+  const double* r[3];
+  double* ib[2][2][3];       /* [buffer][min|max][axis] inherited boxes of a level                 */
+  int* first; int* count;
+  int8_t* splitdim; int* medrank; int* noderb;
+  int* tilecnt;              /* [NDIM][ntile] right-going entries per tile, then its exclusive scan */
+  int ntile;
+};
+
+__global__ void rank_scatter_kernel(int N, const int* __restrict__ list, int* __restrict__ rank)
+{
+  const int p = blockIdx.x*blockDim.x + threadIdx.x;
+  if (p < N) rank[list[p]] = p;
+}
+
+template <int NDIM>
+__global__ void fill_ranks_kernel(int N, ListPtrs<NDIM> L)
+{
+  const int p = blockIdx.x*blockDim.x + threadIdx.x;
+  if (p >= N) return;
+#pragma unroll
+  for (int d = 0; d < NDIM; d++) {
+    const int id = L.ids[d][0][p];
+#pragma unroll
+    for (int q = 0; q < NDIM - 1; q++) L.rk[d][q][0][p] = L.rank[(d + 1 + q) % NDIM][id];
+  }
+}
+
+/* DivideTreeCell for every node of one level, KDTree.cpp:492-560 */
+template <int NDIM>
+__global__ void split_nodes_v2_kernel(int level, int cur, ListPtrs<NDIM> L)
+{
+  const int k = blockIdx.x*blockDim.x + threadIdx.x;
+  if (k >= (1 << level)) return;
+  const int n = (1 << level) - 1 + k;
+  const int a = level & 1;
+  const int cnt = L.count[n], fst = L.first[n];
+  int kd = 0; double rkmax = 0.0;
+#pragma unroll
+  for (int d = 0; d < NDIM; d++) {
+    const double w = __dadd_rn(L.ib[a][1][d][k], -L.ib[a][0][d][k]);
+    if (w > rkmax) { rkmax = w; kd = d; }
+  }
+  const int left = cnt/2;
+  double rdiv = 0.0; int mr = 0x7fffffff;
+  if (cnt > 0) {
+    const int idm = L.ids[kd][cur][fst + left];
+    rdiv = L.r[kd][idm];
+    mr = L.rank[kd][idm];
+  }
+  const int c1 = 2*n + 1, c2 = 2*n + 2;
+  L.first[c1] = fst;        L.count[c1] = left;
+  L.first[c2] = fst + left; L.count[c2] = cnt - left;
+#pragma unroll
+  for (int d = 0; d < NDIM; d++) {
+    const double mn = L.ib[a][0][d][k], mx = L.ib[a][1][d][k];
+    L.ib[a ^ 1][0][d][2*k] = mn;                       L.ib[a ^ 1][1][d][2*k] = (d == kd) ? rdiv : mx;
+    L.ib[a ^ 1][0][d][2*k + 1] = (d == kd) ? rdiv : mn; L.ib[a ^ 1][1][d][2*k + 1] = mx;
+  }
+  L.splitdim[k] = (int8_t) kd;
+  L.medrank[k] = mr;
+  L.noderb[k] = cnt - left;          /* exclusive-scanned over the level afterwards */
+}
+
+/* node (index inside the level) that owns list position p: the balanced tree keeps first[] within a
+ * few entries of the uniform estimate, so a short correction walk from p*2^level/N finds it        */
+__device__ __forceinline__ int node_of_position(int p, int N, int level, const int* __restrict__ first)
+{
+  const int nn = 1 << level, base = nn - 1;
+  int k = (int)(((long long) p << level)/N);
+  if (k > nn - 1) k = nn - 1;
+  while (k > 0 && p < first[base + k]) k--;
+  while (k + 1 < nn && p >= first[base + k + 1]) k++;
+  return k;
+}
+
+template <int NDIM>
+__device__ __forceinline__ int goes_right(const ListPtrs<NDIM>& L, int d, int cur, int level, int N, int p, int& k)
+{
+  k = node_of_position(p, N, level, L.first);
+  const int n = (1 << level) - 1 + k;
+  const int kd = L.splitdim[k];
+  if (d == kd) return p >= L.first[n] + L.count[n]/2;
+  const int q = (kd - d - 1 + NDIM) % NDIM;
+  return L.rk[d][q < NDIM - 1 ? q : 0][cur][p] >= L.medrank[k];
+}
+
+template <int NDIM>
+__global__ void __launch_bounds__(TB_THREADS)
+count_right_kernel(int N, int level, int cur, ListPtrs<NDIM> L)
+{
+  const int d = blockIdx.y;
+  const int p0 = blockIdx.x*TB_TILE + threadIdx.x*TB_ITEMS;
+  int c = 0;
+#pragma unroll
+  for (int i = 0; i < TB_ITEMS; i++) {
+    const int p = p0 + i;
+    int k;
+    if (p < N) c += goes_right<NDIM>(L, d, cur, level, N, p, k);
+  }
+  typedef cub::BlockReduce<int, TB_THREADS> BR;
+  __shared__ typename BR::TempStorage tmp;
+  const int tot = BR(tmp).Sum(c);
+  if (threadIdx.x == 0) L.tilecnt[d*L.ntile + blockIdx.x] = tot;
+}
+
+template <int NDIM>
+__global__ void __launch_bounds__(TB_THREADS)
+partition_v2_kernel(int N, int level, int cur, ListPtrs<NDIM> L)
+{
+  const int d = blockIdx.y;
+  const int p0 = blockIdx.x*TB_TILE + threadIdx.x*TB_ITEMS;
+  int f[TB_ITEMS], kk[TB_ITEMS];
+  int c = 0;
+#pragma unroll
+  for (int i = 0; i < TB_ITEMS; i++) {
+    const int p = p0 + i;
+    f[i] = 0; kk[i] = 0;
+    if (p < N) f[i] = goes_right<NDIM>(L, d, cur, level, N, p, kk[i]);
+    c += f[i];
+  }
+  typedef cub::BlockScan<int, TB_THREADS> BS;
+  __shared__ typename BS::TempStorage tmp;
+  int pre;
+  BS(tmp).ExclusiveSum(c, pre);
+  /* right-going entries of THIS list before the tile: scanned tile counts minus the list's base */
+  int G = L.tilecnt[d*L.ntile + blockIdx.x] - L.tilecnt[d*L.ntile] + pre;
+#pragma unroll
+  for (int i = 0; i < TB_ITEMS; i++) {
+    const int p = p0 + i;
+    if (p < N) {
+      const int n = (1 << level) - 1 + kk[i];
+      const int fst = L.first[n], nl = L.count[n]/2;
+      const int rb = G - L.noderb[kk[i]];              /* right-going entries before p inside the node */
+      const int dest = f[i] ? fst + nl + rb : p - rb;
+      L.ids[d][cur ^ 1][dest] = L.ids[d][cur][p];
+#pragma unroll
+      for (int q = 0; q < NDIM - 1; q++) L.rk[d][q][cur ^ 1][dest] = L.rk[d][q][cur][p];
+      G += f[i];
+    }
+  }
+}
+
+template <int NDIM>
+int build_tree_v2(gsph_handle* h)
+{
+  const int N = (int) h->N;
+  constexpr int nd = NDIM;
+  constexpr int NR = NDIM - 1;
+  cudaStream_t s = h->stream;
+  const PartView Hh = view_of(h->H, h->HI);
+  const PartView Pp = view_of(h->P, h->PI);
+
+  int ltot = 0;                                       /* ComputeTreeSize, KDTree.cpp:322-352 */
+  while ((int64_t) h->cfg.Nleafmax*((int64_t)1 << ltot) < (int64_t) N) ltot++;
+  int rc = alloc_tree(h, ltot);
+  if (rc) return rc;
+  TreeDev& T = h->tree;
+  const int nleaf = 1 << ltot;
+  const int ntile = (N + TB_TILE - 1)/TB_TILE;
+  const size_t Npad = (size_t) ntile*TB_TILE;
+
+  /* scratch layout */
+  size_t cub_sort = 0, cub_scan = 0, cub_scan2 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, cub_sort, (const double*) nullptr, (double*) nullptr,
+                                  (const int*) nullptr, (int*) nullptr, N, 0, 64, s);
+  cub::DeviceScan::ExclusiveSum(nullptr, cub_scan, (const int*) nullptr, (int*) nullptr, nd*ntile, s);
+  cub::DeviceScan::ExclusiveSum(nullptr, cub_scan2, (const int*) nullptr, (int*) nullptr, nleaf, s);
+  size_t cub_bytes = cub_sort > cub_scan ? cub_sort : cub_scan;
+  if (cub_scan2 > cub_bytes) cub_bytes = cub_scan2;
+  const size_t need = Npad*sizeof(int)*(size_t)(nd*2*(1 + NR) + nd) + Npad*sizeof(double)
+                      + (size_t) nleaf*(sizeof(double)*4*nd + 1 + 2*sizeof(int)) + (size_t) nd*ntile*sizeof(int)
+                      + cub_bytes + 256*64 + 4096*2*nd*sizeof(double);
+  if (need > h->scratch_bytes) {
+    if (h->scratch) cudaFree(h->scratch);
+    h->scratch = nullptr; h->scratch_bytes = 0;
+    CUDA_TRY(h, cudaMalloc(&h->scratch, need + need/16));
+    h->scratch_bytes = need + need/16;
+  }
+  Bump B{(char*) h->scratch, 0, h->scratch_bytes};
+  ListPtrs<NDIM> L;
+  int* rank[3] = {nullptr, nullptr, nullptr};
+  for (int d = 0; d < 3; d++) {
+    for (int b = 0; b < 2; b++) {
+      L.ids[d][b] = d < nd ? B.get<int>(Npad) : nullptr;
+      for (int q = 0; q < 2; q++) L.rk[d][q][b] = (d < nd && q < NR) ? B.get<int>(Npad) : nullptr;
+    }
+    rank[d] = d < nd ? B.get<int>(Npad) : nullptr;
+    L.rank[d] = rank[d];
+    L.r[d] = d < nd ? h->H[F_RX + d] : nullptr;
+  }
+  double* keys_out = B.get<double>(Npad);
+  for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) for (int d = 0; d < 3; d++)
+    L.ib[a][b][d] = d < nd ? B.get<double>(nleaf) : nullptr;
+  L.splitdim = B.get<int8_t>(nleaf);
+  L.medrank = B.get<int>(nleaf);
+  L.noderb = B.get<int>(nleaf);
+  L.tilecnt = B.get<int>((size_t) nd*ntile);
+  L.ntile = ntile;
+  L.first = T.first; L.count = T.count;
+  const int rb_blocks = 1024;
+  double* rbpart = B.get<double>((size_t) rb_blocks*2*nd);
+  void* cubtmp = B.get<char>(cub_bytes);
+  if (B.off > B.cap) { h->err = "internal: tree scratch layout overflow"; return GSPH_ENOMEM; }
+
+  /* root box and the presorted lists */
+  root_box_kernel<NDIM><<<rb_blocks, 256, 0, s>>>(N, Hh, h->dp.kernrange, rbpart);
+  root_box_final<NDIM><<<1, 32, 0, s>>>(rb_blocks, rbpart, L.ib[0][0][0], L.ib[0][0][1], L.ib[0][0][2],
+                                        L.ib[0][1][0], L.ib[0][1][1], L.ib[0][1][2]);
+  h->stats.kernel_launches += 2;
+  cudaEventRecord(h->evk[3][0], s);
+  for (int d = 0; d < nd; d++) {
+    iota_kernel<<<(N + 255)/256, 256, 0, s>>>(N, L.ids[d][1]);
+    size_t tb = cub_bytes;
+    cub::DeviceRadixSort::SortPairs(cubtmp, tb, (const double*) h->H[F_RX + d], keys_out,
+                                    (const int*) L.ids[d][1], L.ids[d][0], N, 0, 64, s);
+    h->stats.kernel_launches += 8;
+    if (nd > 1) { rank_scatter_kernel<<<(N + 255)/256, 256, 0, s>>>(N, L.ids[d][0], rank[d]); h->stats.kernel_launches++; }
+  }
+  if (nd > 1) { fill_ranks_kernel<NDIM><<<(N + 255)/256, 256, 0, s>>>(N, L); h->stats.kernel_launches++; }
+  cudaEventRecord(h->evk[3][1], s); h->evk_used[3] = true;
+  cudaEventRecord(h->evk[4][0], s);
+  {
+    const int one[2] = {0, N};
+    CUDA_TRY(h, cudaMemcpyAsync(T.first, &one[0], sizeof(int), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(h, cudaMemcpyAsync(T.count, &one[1], sizeof(int), cudaMemcpyHostToDevice, s));
+  }
+  int cur = 0;
+  for (int l = 0; l < ltot; l++) {
+    const int nn = 1 << l;
+    split_nodes_v2_kernel<NDIM><<<(nn + 127)/128, 128, 0, s>>>(l, cur, L);
+    h->stats.kernel_launches++;
+    if (nd == 1) continue;                             /* one sorted list: nothing to re-order */
+    size_t tb = cub_bytes;
+    cub::DeviceScan::ExclusiveSum(cubtmp, tb, L.noderb, L.noderb, nn, s);
+    const dim3 grid(ntile, nd);
+    count_right_kernel<NDIM><<<grid, TB_THREADS, 0, s>>>(N, l, cur, L);
+    tb = cub_bytes;
+    cub::DeviceScan::ExclusiveSum(cubtmp, tb, L.tilecnt, L.tilecnt, nd*ntile, s);
+    partition_v2_kernel<NDIM><<<grid, TB_THREADS, 0, s>>>(N, l, cur, L);
+    cur ^= 1;
+    h->stats.kernel_launches += 6;
+  }
+  CUDA_TRY(h, cudaGetLastError());
+  CUDA_TRY(h, cudaMemcpyAsync(h->perm, L.ids[0][cur], sizeof(int)*(size_t) N, cudaMemcpyDeviceToDevice, s));
   gather_kernel<<<(N + 255)/256, 256, 0, s>>>(N, h->perm, Hh, Pp);
   h->stats.kernel_launches++;
   h->sorted_valid = true;
