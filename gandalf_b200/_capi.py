@@ -73,6 +73,7 @@ class Stats(C.Structure):
 
 EXPORTS = [
     "gsph_default_config", "gsph_create", "gsph_destroy", "gsph_last_error", "gsph_upload", "gsph_download",
+    "gsph_download_async", "gsph_set_stars",
     "gsph_build_tree", "gsph_update_active_counters", "gsph_update_properties", "gsph_zero_accelerations",
     "gsph_update_hydro_forces", "gsph_update_all_forces", "gsph_get_hmax", "gsph_synchronize",
     "gsph_timer_start", "gsph_timer_stop", "gsph_set_active_slice", "gsph_density_pass", "gsph_refresh_hmax",
@@ -108,6 +109,8 @@ def lib():
     L.gsph_last_error.restype = C.c_char_p
     L.gsph_upload.argtypes = [H, C.POINTER(ParticleView), C.c_int64]
     L.gsph_download.argtypes = [H, C.POINTER(ParticleView), C.c_uint32]
+    L.gsph_download_async.argtypes = [H, C.POINTER(ParticleView), C.c_uint32]
+    L.gsph_set_stars.argtypes = [H, C.c_void_p, C.c_int]
     L.gsph_build_tree.argtypes = [H, C.c_int, C.c_double]
     for n in ("gsph_update_active_counters", "gsph_update_properties", "gsph_zero_accelerations",
               "gsph_update_hydro_forces", "gsph_synchronize", "gsph_timer_start", "gsph_density_pass",

@@ -320,6 +320,10 @@ int gsph_create(const gsph_config* cfg, gsph_handle** out)
   if ((e = cudaGetDeviceProperties(&prop, h->device)) != cudaSuccess) return fail("cudaGetDeviceProperties", e);
   h->sm_count = prop.multiProcessorCount;
   if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+  if ((e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+  if ((e = cudaEventCreateWithFlags(&h->ev_geom, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+  if ((e = cudaEventCreateWithFlags(&h->ev_all, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+  if ((e = cudaEventCreateWithFlags(&h->ev_compute, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
   if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return fail("cudaEventCreate", e);
   if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return fail("cudaEventCreate", e);
   for (int k = 0; k < 2; k++) if ((e = cudaEventCreate(&h->evt[k])) != cudaSuccess) return fail("cudaEventCreate", e);
@@ -342,10 +346,11 @@ void gsph_destroy(gsph_handle* h)
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
   auto fre = [](void* p) { if (p) cudaFree(p); };
   for (int f = 0; f < NF_DOUBLE; f++) { fre(h->H[f]); fre(h->P[f]); }
   for (int f = 0; f < NF_INT; f++) { fre(h->HI[f]); fre(h->PI[f]); }
-  fre(h->perm); fre(h->tables); fre(h->scratch); fre(h->cand); fre(h->gravlist); fre(h->status); fre(h->work_counter); fre(h->done); fre(h->geo4); fre(h->geoh); fre(h->frec); fre(h->nlist); fre(h->hnew);
+  fre(h->perm); fre(h->tables); fre(h->scratch); fre(h->cand); fre(h->gravlist); fre(h->status); fre(h->work_counter); fre(h->done); fre(h->geo4); fre(h->geoh); fre(h->frec); fre(h->nlist); fre(h->hnew); fre(h->stars);
   TreeDev& T = h->tree;
   fre(T.first); fre(T.count); fre(T.nactive); fre(T.m); fre(T.rmax); fre(T.hmax); fre(T.cdistsqd);
   for (int k = 0; k < 3; k++) { fre(T.bbmin[k]); fre(T.bbmax[k]); fre(T.hbmin[k]); fre(T.hbmax[k]); fre(T.rcell[k]); fre(T.com[k]); fre(T.vcom[k]); }
@@ -356,6 +361,11 @@ void gsph_destroy(gsph_handle* h)
   if (h->ev1) cudaEventDestroy(h->ev1);
   for (int k = 0; k < 2; k++) if (h->evt[k]) cudaEventDestroy(h->evt[k]);
   for (int k = 0; k < 6; k++) for (int j = 0; j < 2; j++) if (h->evk[k][j]) cudaEventDestroy(h->evk[k][j]);
+  if (h->ev_geom) cudaEventDestroy(h->ev_geom);
+  if (h->ev_all) cudaEventDestroy(h->ev_all);
+  if (h->ev_compute) cudaEventDestroy(h->ev_compute);
+  fre(h->tree.nodeb); fre(h->tree.nodeh);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
@@ -394,38 +404,49 @@ int gsph_upload(gsph_handle* h, const gsph_particle_view* view, int64_t N)
   if (lo && (size_t)(hi - lo) > stride) bulk_ok = false;
 
   const int nb = (int)((N + 255)/256);
-  for (int k = 0; k < kNDoubleFields; k++) {
-    const int pf = kDoubleFields[k].pf;
-    const gsph_field& f = vfield(view, kDoubleFields[k].off);
-    const bool unused_dim = (pf >= F_RX && pf <= F_ATZ) && ((pf - F_RX) % 3 >= nd);
-    if (!f.base || unused_dim) fill_kernel<double><<<nb, 256, 0, h->stream>>>(N, h->H[pf], default_double(pf));
-    else if (f.stride == sizeof(double))
-      CUDA_TRY(h, cudaMemcpyAsync(h->H[pf], f.base, N*sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    else if (bulk_ok) { plan.off_d[plan.nf] = (unsigned)((const char*) f.base - lo); plan.pf_d[plan.nf++] = pf; }
-    else {
-      rc = ensure_pinned(h, N*sizeof(double)); if (rc) return rc;
-      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-      double* st = (double*) h->pinned; const char* b = (const char*) f.base;
+  /* Contiguous fields travel on the copy stream, geometry (r, h, integer fields) first: the tree
+     build only needs those and starts while v, m, u, ... are still in flight.  The copy stream first
+     waits for the compute stream, which may still be reading the staging arrays of the last step. */
+  CUDA_TRY(h, cudaEventRecord(h->ev_compute, h->stream));
+  CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->ev_compute, 0));
+  for (int pass = 0; pass < 2; pass++) {
+    for (int k = 0; k < kNDoubleFields; k++) {
+      const int pf = kDoubleFields[k].pf;
+      const bool geom = (pf >= F_RX && pf <= F_RZ) || pf == F_H;
+      if (geom != (pass == 0)) continue;
+      const gsph_field& f = vfield(view, kDoubleFields[k].off);
+      const bool unused_dim = (pf >= F_RX && pf <= F_ATZ) && ((pf - F_RX) % 3 >= nd);
+      if (!f.base || unused_dim) fill_kernel<double><<<nb, 256, 0, h->copy_stream>>>(N, h->H[pf], default_double(pf));
+      else if (f.stride == sizeof(double))
+        CUDA_TRY(h, cudaMemcpyAsync(h->H[pf], f.base, N*sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+      else if (bulk_ok) { plan.off_d[plan.nf] = (unsigned)((const char*) f.base - lo); plan.pf_d[plan.nf++] = pf; }
+      else {
+        rc = ensure_pinned(h, N*sizeof(double)); if (rc) return rc;
+        CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
+        double* st = (double*) h->pinned; const char* b = (const char*) f.base;
 #pragma omp parallel for schedule(static)
-      for (int64_t i = 0; i < N; i++) st[i] = *(const double*)(b + (size_t) i*f.stride);
-      CUDA_TRY(h, cudaMemcpyAsync(h->H[pf], st, N*sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        for (int64_t i = 0; i < N; i++) st[i] = *(const double*)(b + (size_t) i*f.stride);
+        CUDA_TRY(h, cudaMemcpyAsync(h->H[pf], st, N*sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+      }
     }
-  }
-  for (int k = 0; k < kNIntFields; k++) {
-    const int pf = kIntFields[k].pf;
-    const gsph_field& f = vfield(view, kIntFields[k].off);
-    if (!f.base) fill_kernel<int32_t><<<nb, 256, 0, h->stream>>>(N, h->HI[pf], default_int(pf));
-    else if (f.stride == sizeof(int32_t))
-      CUDA_TRY(h, cudaMemcpyAsync(h->HI[pf], f.base, N*sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-    else if (bulk_ok) { plan.off_i[plan.ni] = (unsigned)((const char*) f.base - lo); plan.pf_i[plan.ni++] = pf; }
-    else {
-      rc = ensure_pinned(h, N*sizeof(int32_t)); if (rc) return rc;
-      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-      int32_t* st = (int32_t*) h->pinned; const char* b = (const char*) f.base;
+    if (pass == 1) break;
+    for (int k = 0; k < kNIntFields; k++) {
+      const int pf = kIntFields[k].pf;
+      const gsph_field& f = vfield(view, kIntFields[k].off);
+      if (!f.base) fill_kernel<int32_t><<<nb, 256, 0, h->copy_stream>>>(N, h->HI[pf], default_int(pf));
+      else if (f.stride == sizeof(int32_t))
+        CUDA_TRY(h, cudaMemcpyAsync(h->HI[pf], f.base, N*sizeof(int32_t), cudaMemcpyHostToDevice, h->copy_stream));
+      else if (bulk_ok) { plan.off_i[plan.ni] = (unsigned)((const char*) f.base - lo); plan.pf_i[plan.ni++] = pf; }
+      else {
+        rc = ensure_pinned(h, N*sizeof(int32_t)); if (rc) return rc;
+        CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
+        int32_t* st = (int32_t*) h->pinned; const char* b = (const char*) f.base;
 #pragma omp parallel for schedule(static)
-      for (int64_t i = 0; i < N; i++) st[i] = *(const int32_t*)(b + (size_t) i*f.stride);
-      CUDA_TRY(h, cudaMemcpyAsync(h->HI[pf], st, N*sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        for (int64_t i = 0; i < N; i++) st[i] = *(const int32_t*)(b + (size_t) i*f.stride);
+        CUDA_TRY(h, cudaMemcpyAsync(h->HI[pf], st, N*sizeof(int32_t), cudaMemcpyHostToDevice, h->copy_stream));
+      }
     }
+    if (!(bulk_ok && (plan.nf || plan.ni))) CUDA_TRY(h, cudaEventRecord(h->ev_geom, h->copy_stream));
   }
   if (bulk_ok && (plan.nf || plan.ni)) {
     /* AoS records [lo + i*stride, +span) in chunks through the tree-build scratch buffer */
@@ -442,11 +463,14 @@ int gsph_upload(gsph_handle* h, const gsph_particle_view* view, int64_t N)
       const int64_t n = std::min<int64_t>(per, N - n0);
       size_t bytes = (size_t) n*stride;
       if (n0 + n == N) bytes = (size_t)(n - 1)*stride + (size_t)(hi - lo);   /* do not read past the last record */
-      CUDA_TRY(h, cudaMemcpyAsync(h->scratch, lo + (size_t) n0*stride, bytes, cudaMemcpyHostToDevice, h->stream));
-      aos_unpack_kernel<<<(int)((n + 255)/256), 256, 0, h->stream>>>(n0, n, (const char*) h->scratch, stride, plan, out);
-      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+      CUDA_TRY(h, cudaMemcpyAsync(h->scratch, lo + (size_t) n0*stride, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+      aos_unpack_kernel<<<(int)((n + 255)/256), 256, 0, h->copy_stream>>>(n0, n, (const char*) h->scratch, stride, plan, out);
+      CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
     }
+    CUDA_TRY(h, cudaEventRecord(h->ev_geom, h->copy_stream));
   }
+  CUDA_TRY(h, cudaEventRecord(h->ev_all, h->copy_stream));
+  h->upload_pending = true;
   CUDA_TRY(h, cudaGetLastError());
   if (N != h->N) h->have_tree = false;
   h->N = N; h->uploaded = true; h->sorted_valid = false; h->density_done = false; h->slice_mode = false;
@@ -455,7 +479,7 @@ int gsph_upload(gsph_handle* h, const gsph_particle_view* view, int64_t N)
   return GSPH_OK;
 }
 
-int gsph_download(gsph_handle* h, const gsph_particle_view* view, uint32_t field_mask)
+static int download_impl(gsph_handle* h, const gsph_particle_view* view, uint32_t field_mask, bool wait)
 {
   if (!h) return GSPH_EINVAL;
   if (!view) { h->err = "gsph_download: NULL view"; return GSPH_EINVAL; }
@@ -480,20 +504,25 @@ int gsph_download(gsph_handle* h, const gsph_particle_view* view, uint32_t field
     if (vfield(view, kDoubleFields[k].off).base && want_d(kDoubleFields[k].pf)) dmask |= 1ull << kDoubleFields[k].pf;
   for (int k = 0; k < kNIntFields; k++)
     if (vfield(view, kIntFields[k].off).base && want_i(kIntFields[k].pf)) imask |= 1u << kIntFields[k].pf;
+  /* tree order -> host order on the compute stream, then the copies on the copy stream: they
+     overlap whatever the compute stream does next (the force pass, for a density download) */
   scatter_fields_kernel<<<(int)((N + 255)/256), 256, 0, h->stream>>>((int) N, h->perm, devptrs(h->P, h->PI),
                                                                    devptrs(h->H, h->HI), dmask, imask);
   h->stats.kernel_launches++;
   CUDA_TRY(h, cudaGetLastError());
+  CUDA_TRY(h, cudaEventRecord(h->ev_compute, h->stream));
+  CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->ev_compute, 0));
+  cudaStream_t cs = h->copy_stream;
   for (int k = 0; k < kNDoubleFields; k++) {
     const int pf = kDoubleFields[k].pf;
     if (!((dmask >> pf) & 1ull)) continue;
     const gsph_field& f = vfield(view, kDoubleFields[k].off);
     if (f.stride == sizeof(double))
-      CUDA_TRY(h, cudaMemcpyAsync(f.base, h->H[pf], N*sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      CUDA_TRY(h, cudaMemcpyAsync(f.base, h->H[pf], N*sizeof(double), cudaMemcpyDeviceToHost, cs));
     else {
       int rc = ensure_pinned(h, N*sizeof(double)); if (rc) return rc;
-      CUDA_TRY(h, cudaMemcpyAsync(h->pinned, h->H[pf], N*sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+      CUDA_TRY(h, cudaMemcpyAsync(h->pinned, h->H[pf], N*sizeof(double), cudaMemcpyDeviceToHost, cs));
+      CUDA_TRY(h, cudaStreamSynchronize(cs));
       const double* st = (const double*) h->pinned; char* b = (char*) f.base;
 #pragma omp parallel for schedule(static)
       for (int64_t i = 0; i < N; i++) *(double*)(b + (size_t) i*f.stride) = st[i];
@@ -504,19 +533,29 @@ int gsph_download(gsph_handle* h, const gsph_particle_view* view, uint32_t field
     if (!((imask >> pf) & 1u)) continue;
     const gsph_field& f = vfield(view, kIntFields[k].off);
     if (f.stride == sizeof(int32_t))
-      CUDA_TRY(h, cudaMemcpyAsync(f.base, h->HI[pf], N*sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+      CUDA_TRY(h, cudaMemcpyAsync(f.base, h->HI[pf], N*sizeof(int32_t), cudaMemcpyDeviceToHost, cs));
     else {
       int rc = ensure_pinned(h, N*sizeof(int32_t)); if (rc) return rc;
-      CUDA_TRY(h, cudaMemcpyAsync(h->pinned, h->HI[pf], N*sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+      CUDA_TRY(h, cudaMemcpyAsync(h->pinned, h->HI[pf], N*sizeof(int32_t), cudaMemcpyDeviceToHost, cs));
+      CUDA_TRY(h, cudaStreamSynchronize(cs));
       const int32_t* st = (const int32_t*) h->pinned; char* b = (char*) f.base;
 #pragma omp parallel for schedule(static)
       for (int64_t i = 0; i < N; i++) *(int32_t*)(b + (size_t) i*f.stride) = st[i];
     }
   }
-  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (wait) CUDA_TRY(h, cudaStreamSynchronize(cs));
   tm.stop();
   return GSPH_OK;
+}
+
+int gsph_download(gsph_handle* h, const gsph_particle_view* view, uint32_t field_mask)
+{
+  return download_impl(h, view, field_mask, true);
+}
+
+int gsph_download_async(gsph_handle* h, const gsph_particle_view* view, uint32_t field_mask)
+{
+  return download_impl(h, view, field_mask, false);
 }
 
 /*------------------------------------------------------------------------------------------------*/
@@ -716,6 +755,27 @@ static void force_stats(gsph_handle* h)
   h->stats.ncell_mean = s.nleaf_grav ? (double) s.ncell_sum/(double) s.nleaf_grav : 0.0;
 }
 
+/* stars = Nstar x {r[ndim], m, h} doubles (the fields ComputeStarGravForces reads from
+ * nbody->nbodydata, GradhSph.cpp:722-731); kept on the device until the next call; Nstar = 0 clears */
+int gsph_set_stars(gsph_handle* h, const double* stars, int Nstar)
+{
+  if (!h) return GSPH_EINVAL;
+  if (Nstar < 0 || (Nstar > 0 && !stars)) { h->err = "gsph_set_stars: bad arguments"; return GSPH_EINVAL; }
+  cudaSetDevice(h->device);
+  if (Nstar > h->stars_cap) {
+    if (h->stars) cudaFree(h->stars);
+    h->stars = nullptr; h->stars_cap = 0;
+    CUDA_TRY(h, cudaMalloc(&h->stars, (size_t) Nstar*5*sizeof(double)));
+    h->stars_cap = Nstar;
+  }
+  if (Nstar > 0) {
+    CUDA_TRY(h, cudaMemcpyAsync(h->stars, stars, (size_t) Nstar*(h->cfg.ndim + 2)*sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  }
+  h->Nstar = Nstar;
+  return GSPH_OK;
+}
+
 int gsph_update_hydro_forces(gsph_handle* h)
 {
   if (!h) return GSPH_EINVAL;
@@ -725,6 +785,8 @@ int gsph_update_hydro_forces(gsph_handle* h)
   int rc = reset_status(h); if (rc) return rc;
   rc = gsph_prepare_done_flags(h); if (rc) return rc;
   rc = run_with_regrow(h, "gsph_update_hydro_forces", pass_hydro, 0);
+  if (rc) return rc;
+  rc = gsph_run_star_forces(h);                       /* GradhSphTree.cpp:385-392 */
   if (rc) return rc;
   tm.stop();
   force_stats(h);
@@ -736,8 +798,8 @@ int gsph_update_all_forces(gsph_handle* h, const double* stars, int Nstar)
   if (!h) return GSPH_EINVAL;
   if (!h->have_tree || !h->sorted_valid) { h->err = "gsph_update_all_forces before gsph_build_tree"; return GSPH_ESTATE; }
   if (!h->cfg.self_gravity) { h->err = "gsph_update_all_forces needs self_gravity = 1 in the config"; return GSPH_EINVAL; }
-  if (Nstar > 0 || stars) { h->err = "star particles are not on the accelerated path yet (ComputeStarGravForces)"; return GSPH_EINVAL; }
   cudaSetDevice(h->device);
+  if (stars || Nstar > 0) { const int rs = gsph_set_stars(h, stars, Nstar); if (rs) return rs; }
   Timer tm(h, &h->stats.ms_forces);
   int rc = reset_status(h); if (rc) return rc;
   rc = gsph_prepare_done_flags(h); if (rc) return rc;
@@ -746,6 +808,8 @@ int gsph_update_all_forces(gsph_handle* h, const double* stars, int Nstar)
   const DevStatus keep = *h->status_host;
   rc = gsph_prepare_done_flags(h); if (rc) return rc;
   rc = run_with_regrow(h, "gsph_update_all_forces(gravity)", pass_gravity, 0);
+  if (rc) return rc;
+  rc = gsph_run_star_forces(h);                       /* GradhSphTree.cpp:600-607 */
   if (rc) return rc;
   tm.stop();
   (void) keep;
@@ -768,6 +832,7 @@ int gsph_synchronize(gsph_handle* h)
   if (!h) return GSPH_EINVAL;
   cudaSetDevice(h->device);
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
   return GSPH_OK;
 }
 

@@ -30,9 +30,9 @@ struct GatherVisitorF {
   const float4* __restrict__ nodeb; const WalkBox& wb; CandList& cl;
   float smin[3], smax[3];
   int first, count;
-  __device__ __forceinline__ int test(int node, bool)
+  __device__ __forceinline__ int test(int nd, bool)
   {
-    const float4 lo = nodeb[2*(size_t) node], hi = nodeb[2*(size_t) node + 1];
+    const float4 lo = nodeb[2*(size_t) nd], hi = nodeb[2*(size_t) nd + 1];
     first = __float_as_int(lo.w); count = __float_as_int(hi.w);
     if (count <= 0) return 0;
     bool wrapped = false;

@@ -346,15 +346,26 @@ __device__ __forceinline__ bool fboxes_overlap(const WalkBox& wb, const float (&
   return true;
 }
 
-/* same traversal as warp_walk, for visitors that read the packed float node records themselves
- * (test() returns 0 for empty nodes and remembers first/count for emit())                        */
+/* Same traversal as warp_walk, for visitors that read the packed float node records themselves
+ * (test() returns 0 for empty nodes and remembers node/first/count for emit()).
+ *   leaf_level : nodes of this level are treated as leaves (normally ltot);
+ *   init/ninit : start from this node list instead of the top of the tree.                         */
 template <int STACKCAP, class Visitor>
-__device__ __forceinline__ bool warp_walk_f(int ltot, int* stack, Visitor& V, DevStatus* st)
+__device__ __forceinline__ bool warp_walk_f(int leaf_level, int* stack, Visitor& V, DevStatus* st,
+                                            const int* init = nullptr, int ninit = 0)
 {
   const int lane = threadIdx.x & 31;
-  const int leaf0 = (1 << ltot) - 1;
-  int sp = 1;
-  if (lane == 0) stack[0] = 0;
+  const int leaf0 = (1 << leaf_level) - 1;
+  int sp;
+  if (init) {
+    for (int i = lane; i < ninit; i += 32) stack[i] = init[i];
+    sp = ninit;
+  }
+  /* Without a frontier the walk starts with the 32 nodes of level 5 (one round of independent loads
+     instead of six dependent ones): a node that meets the search box has ancestors that meet it
+     too, so skipping the ancestors never loses a leaf.                                            */
+  else if (leaf_level > 5) { stack[lane] = 31 + lane; sp = 32; }
+  else { if (lane == 0) stack[0] = 0; sp = 1; }
   __syncwarp();
   while (sp > 0) {
     const int take = sp < 32 ? sp : 32;

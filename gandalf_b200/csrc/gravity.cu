@@ -37,19 +37,23 @@
 #define GRAV_STACK 512                 /* (node, mask) pairs per warp */
 #define CELL_TILE 32
 #define CELL_BUF 64
-#define DIR_PART 128                   /* staged source particles per direct tile */
-#define DIR_TILE_MAX 32                /* direct leaves per tile: DIR_PART/(4*T) */
+#define DIR_PART 64                    /* staged source particles per direct tile */
+#define DIR_TILE_MAX 16                /* direct leaves per tile: DIR_PART/(4*T) */
 #define DIR_BUF (DIR_TILE_MAX + 32)
 #define GRAV_LEAVES 8                  /* leaves per cohort: 4 lanes each */
+#ifndef GRAV_MINBLOCKS
+#define GRAV_MINBLOCKS 3               /* resident blocks per SM the register allocation is tuned for */
+#endif
 
 namespace {
 
-struct WarpShared {
+template <bool QUAD>
+struct WarpSharedT {
   int2 stack[GRAV_STACK];
   double leafgeom[GRAV_LEAVES][5];     /* rcell xyz, rmax, kernrange*hmax of the cohort's leaves */
   int cell_node[CELL_BUF]; unsigned cell_mask[CELL_BUF];
   int dir_node[DIR_BUF]; unsigned dir_mask[DIR_BUF];
-  double cell_data[CELL_TILE][9];      /* com xyz, m, q0..q4 */
+  double cell_data[CELL_TILE][QUAD ? 9 : 4];   /* com xyz, m [, q0..q4] */
   double dir_data[DIR_PART][5];        /* x, y, z, m, hrangesqd of the staged source particles */
   int dir_src[DIR_PART];               /* tree-order index of every staged source particle */
   int dir_off[DIR_TILE_MAX], dir_count[DIR_TILE_MAX];
@@ -58,12 +62,13 @@ struct WarpShared {
 struct FastMp { double ac[3], q[6], pot; };   /* dphi == ac for HoT = false */
 
 template <int MULTIPOLE, int T>
-__global__ void __launch_bounds__(GRAV_THREADS)
+__global__ void __launch_bounds__(GRAV_THREADS, (T == 1 && MULTIPOLE != GSPH_MULTIPOLE_FAST_QUADRUPOLE) ? GRAV_MINBLOCKS : 2)
 gravity_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* work_counter,
                DevStatus* st, uint8_t* done)
 {
   extern __shared__ char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  typedef WarpSharedT<(MULTIPOLE == GSPH_MULTIPOLE_QUADRUPOLE || MULTIPOLE == GSPH_MULTIPOLE_FAST_QUADRUPOLE)> WarpShared;
   WarpShared& S = reinterpret_cast<WarpShared*>(smem_raw)[warp];
   const int leaf0 = (1 << tree.ltot) - 1;
   const int ncohort = 1 << cohort_level;
@@ -407,7 +412,7 @@ gravity_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* wo
 template <int MULTIPOLE, int T>
 int launch_gravity_t(gsph_handle* h)
 {
-  const size_t smem = GRAV_WARPS*sizeof(WarpShared);
+  const size_t smem = GRAV_WARPS*sizeof(WarpSharedT<(MULTIPOLE == GSPH_MULTIPOLE_QUADRUPOLE || MULTIPOLE == GSPH_MULTIPOLE_FAST_QUADRUPOLE)>);
   auto kern = gravity_kernel<MULTIPOLE, T>;
   CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   int bps = 0;

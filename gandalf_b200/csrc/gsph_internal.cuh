@@ -100,6 +100,13 @@ struct gsph_handle {
   int device = 0;
   int sm_count = 0;
   cudaStream_t stream = nullptr;
+  /* host<->device copies run on their own stream so that they overlap the kernels:
+       ev_geom   : r, h and the integer fields of the last upload have landed (tree build may start)
+       ev_all    : every field of the last upload has landed (permutation into tree order may start)
+       ev_compute: the compute stream reached the point where a copy may touch the staging arrays  */
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_geom = nullptr, ev_all = nullptr, ev_compute = nullptr;
+  bool upload_pending = false;   /* ev_geom / ev_all still have to be waited for by the compute stream */
   std::string err;
 
   int64_t N = 0;             /* particles currently uploaded */
@@ -118,6 +125,8 @@ struct gsph_handle {
   bool uploaded = false, have_tree = false, sorted_valid = false, all_active = true;
   bool density_done = false;
   bool slice_mode = false;   /* gsph_set_active_slice: inactive particles belong to other ranks */
+
+  double* stars = nullptr; int Nstar = 0, stars_cap = 0;   /* device copy of {r[ndim], m, h} per star (gsph_set_stars) */
 
   TreeDev tree;
   double* tables = nullptr;     /* 6 x 1000 doubles: w0_s2, womega_s2, wzeta_s2, w1, wgrav, wpot */
@@ -153,6 +162,7 @@ int gsph_run_density(gsph_handle* h);                                 /* density
 int gsph_run_hydro(gsph_handle* h, int with_gravity);                 /* hydro.cu   */
 int gsph_run_neiblist(gsph_handle* h, int32_t* counts_dev, const int64_t* offsets_dev, int32_t* idx_dev);
 int gsph_run_gravity(gsph_handle* h);                                 /* gravity.cu */
+int gsph_run_star_forces(gsph_handle* h);                             /* hydro.cu   */
 int gsph_check_status(gsph_handle* h, const char* where);             /* capi.cu    */
 int gsph_ensure_cand(gsph_handle* h, int warps, size_t cap_per_warp);
 int gsph_ensure_nlist(gsph_handle* h, int warps, size_t cap);

@@ -75,15 +75,22 @@ struct ScatterGatherVisitorF {
   float bmin[3], bmax[3], hmin[3], hmax[3];
   bool needwrap;
   int first, count;
-  __device__ __forceinline__ int test(int node, bool leaf)
+  __device__ __forceinline__ void set_boxes(int n)
   {
-    const float4 lo = nodeb[2*(size_t) node], hi = nodeb[2*(size_t) node + 1];
+    const float4 lo = nodeb[2*(size_t) n], hi = nodeb[2*(size_t) n + 1];
+    const float4 hlo = nodeh[2*(size_t) n], hhi = nodeh[2*(size_t) n + 1];
+    bmin[0] = lo.x; bmin[1] = lo.y; bmin[2] = lo.z; bmax[0] = hi.x; bmax[1] = hi.y; bmax[2] = hi.z;
+    hmin[0] = hlo.x; hmin[1] = hlo.y; hmin[2] = hlo.z; hmax[0] = hhi.x; hmax[1] = hhi.y; hmax[2] = hhi.z;
+  }
+  __device__ __forceinline__ int test(int nd, bool leaf)
+  {
+    const float4 lo = nodeb[2*(size_t) nd], hi = nodeb[2*(size_t) nd + 1];
     first = __float_as_int(lo.w); count = __float_as_int(hi.w);
     if (count <= 0) return 0;
     bool wrapped = false;
     bool open = fboxes_overlap<NDIM>(wb, hmin, hmax, lo, hi, wrapped);
     if (!open) {
-      const float4 hlo = nodeh[2*(size_t) node], hhi = nodeh[2*(size_t) node + 1];
+      const float4 hlo = nodeh[2*(size_t) nd], hhi = nodeh[2*(size_t) nd + 1];
       open = fboxes_overlap<NDIM>(wb, bmin, bmax, hlo, hhi, wrapped);
     }
     if (open && leaf && wrapped) needwrap = true;
@@ -263,12 +270,7 @@ hydro_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict__ 
                                   {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, false, 0, 0};
     double ctr[3] = {0, 0, 0}, diag2 = 0.0;
     bool wide = false;                /* periodic images not unique about the cohort centre: keep all */
-    {
-      const float4 lo = tree.nodeb[2*(size_t) node], hi = tree.nodeb[2*(size_t) node + 1];
-      const float4 hlo = tree.nodeh[2*(size_t) node], hhi = tree.nodeh[2*(size_t) node + 1];
-      V.bmin[0] = lo.x; V.bmin[1] = lo.y; V.bmin[2] = lo.z; V.bmax[0] = hi.x; V.bmax[1] = hi.y; V.bmax[2] = hi.z;
-      V.hmin[0] = hlo.x; V.hmin[1] = hlo.y; V.hmin[2] = hlo.z; V.hmax[0] = hhi.x; V.hmax[1] = hhi.y; V.hmax[2] = hhi.z;
-    }
+    V.set_boxes(node);
 #pragma unroll
     for (int k = 0; k < NDIM; k++) {
       const double b0 = tree.bbmin[k][node], b1 = tree.bbmax[k][node];
@@ -629,7 +631,73 @@ int dispatch_hydro(gsph_handle* h, int with_gravity)
   return rc;
 }
 
+/* GradhSph::ComputeStarGravForces (GradhSph.cpp:699-743) for every active particle: softened gravity
+ * of the stars with the mean-h kernel into atree, a (both force drivers add atree to a,
+ * GradhSphTree.cpp:396-399 / :611-614) and gpot.  Nstar is small: one thread per particle.        */
+template <int NDIM, int KERN, bool TAB>
+__global__ void star_forces_kernel(int N, PartView P, DevParams dp, const double* __restrict__ gtables,
+                                   const double* __restrict__ stars, int Nstar)
+{
+  const int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const unsigned fl = (unsigned) P.i[I_FLAGS][i];
+  if (!(fl & GSPH_FLAG_ACTIVE) || (fl & GSPH_FLAG_DEAD)) return;
+  const KernelEval<KERN, NDIM, TAB> K(dp, gtables);
+  double x[3] = {0, 0, 0}, at[3] = {0, 0, 0}, pot = 0.0;
+#pragma unroll
+  for (int k = 0; k < NDIM; k++) x[k] = P.f[F_RX + k][i];
+  const double hi = P.f[F_H][i];
+  for (int j = 0; j < Nstar; j++) {
+    const double* s = stars + (size_t) j*(NDIM + 2);
+    double dr[3] = {0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < NDIM; k++) dr[k] = s[k] - x[k];
+    const double drsqd = __dadd_rn(dot_exact<NDIM>(dr), GSPH_SMALL);
+    const double drmag = sqrt(drsqd), invdrmag = 1.0/drmag;
+    const double invhmean = 2.0/(hi + s[NDIM + 1]);
+    const double ms = s[NDIM];
+    const double paux = ms*invhmean*invhmean*K.wgrav(drmag*invhmean)*invdrmag;
+#pragma unroll
+    for (int k = 0; k < NDIM; k++) at[k] += paux*dr[k];
+    pot += ms*invhmean*K.wpot(drmag*invhmean);
+  }
+#pragma unroll
+  for (int k = 0; k < NDIM; k++) { P.f[F_ATX + k][i] += at[k]; P.f[F_AX + k][i] += at[k]; }
+  P.f[F_GPOT][i] += pot;
+}
+
+template <int NDIM, int KERN, bool TAB>
+int launch_stars(gsph_handle* h)
+{
+  PartView P;
+  for (int k = 0; k < NF_DOUBLE; k++) P.f[k] = h->P[k];
+  for (int k = 0; k < NF_INT; k++) P.i[k] = h->PI[k];
+  const int N = (int) h->N;
+  star_forces_kernel<NDIM, KERN, TAB><<<(N + 127)/128, 128, 0, h->stream>>>(N, P, h->dp, h->tables, h->stars, h->Nstar);
+  h->stats.kernel_launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return GSPH_OK;
+}
+
+template <int NDIM>
+int dispatch_stars(gsph_handle* h)
+{
+  const bool tab = h->dp.tabulated != 0;
+  if (h->dp.kernel == GSPH_KERNEL_M4) return tab ? launch_stars<NDIM, GSPH_KERNEL_M4, true>(h) : launch_stars<NDIM, GSPH_KERNEL_M4, false>(h);
+  return tab ? launch_stars<NDIM, GSPH_KERNEL_QUINTIC, true>(h) : launch_stars<NDIM, GSPH_KERNEL_QUINTIC, false>(h);
+}
+
 }  // namespace
+
+int gsph_run_star_forces(gsph_handle* h)
+{
+  if (h->Nstar <= 0) return GSPH_OK;
+  switch (h->dp.ndim) {
+  case 1: return dispatch_stars<1>(h);
+  case 2: return dispatch_stars<2>(h);
+  default: return dispatch_stars<3>(h);
+  }
+}
 
 int gsph_run_hydro(gsph_handle* h, int with_gravity)
 {

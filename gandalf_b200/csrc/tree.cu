@@ -459,11 +459,13 @@ int build_tree_nd(gsph_handle* h, int mode, double dt)
   cudaStream_t s = h->stream;
   const PartView Hh = view_of(h->H, h->HI);
   const PartView Pp = view_of(h->P, h->PI);
+  cudaStreamWaitEvent(s, h->ev_geom, 0);         /* r, h and the integer fields of the last upload have landed */
 
   if (mode == 2) {                                   /* extrapolate: Tree.cpp:172-198 */
     if (!h->have_tree) { h->err = "gsph_build_tree(extrapolate) before the first rebuild"; return GSPH_ESTATE; }
     if (!h->sorted_valid) {
-      gather_kernel<<<(N + 255)/256, 256, 0, s>>>(N, h->perm, Hh, Pp);
+      cudaStreamWaitEvent(s, h->ev_all, 0);      /* every uploaded field has landed */
+  gather_kernel<<<(N + 255)/256, 256, 0, s>>>(N, h->perm, Hh, Pp);
       h->sorted_valid = true; h->stats.kernel_launches++;
     }
     extrapolate_kernel<NDIM><<<(h->tree.ncell + 255)/256, 256, 0, s>>>(h->tree, dt);
@@ -474,7 +476,8 @@ int build_tree_nd(gsph_handle* h, int mode, double dt)
   }
   if (mode == 1) {                                   /* restock: KDTree::StockTree */
     if (!h->have_tree) { h->err = "gsph_build_tree(restock) before the first rebuild"; return GSPH_ESTATE; }
-    gather_kernel<<<(N + 255)/256, 256, 0, s>>>(N, h->perm, Hh, Pp);
+    cudaStreamWaitEvent(s, h->ev_all, 0);      /* every uploaded field has landed */
+  gather_kernel<<<(N + 255)/256, 256, 0, s>>>(N, h->perm, Hh, Pp);
     h->sorted_valid = true; h->stats.kernel_launches++;
     return stock_tree<NDIM>(h, 1);
   }
@@ -576,6 +579,7 @@ int build_tree_nd(gsph_handle* h, int mode, double dt)
   }
   CUDA_TRY(h, cudaGetLastError());
   CUDA_TRY(h, cudaMemcpyAsync(h->perm, list[0][cur[0]], sizeof(int)*(size_t) N, cudaMemcpyDeviceToDevice, s));
+  cudaStreamWaitEvent(s, h->ev_all, 0);      /* every uploaded field has landed */
   gather_kernel<<<(N + 255)/256, 256, 0, s>>>(N, h->perm, Hh, Pp);
   h->stats.kernel_launches++;
   h->sorted_valid = true;
@@ -671,27 +675,46 @@ __global__ void split_nodes_v2_kernel(int level, int cur, ListPtrs<NDIM> L)
 
 /* node (index inside the level) that owns list position p: the balanced tree keeps first[] within a
  * few entries of the uniform estimate, so a short correction walk from p*2^level/N finds it        */
-__device__ __forceinline__ int node_of_position(int p, int N, int level, const int* __restrict__ first)
+__device__ __forceinline__ int node_of_position(int p, double nodes_per_pos, int level, const int* __restrict__ first)
 {
   const int nn = 1 << level, base = nn - 1;
-  int k = (int)(((long long) p << level)/N);
+  int k = (int)((double) p*nodes_per_pos);
   if (k > nn - 1) k = nn - 1;
   while (k > 0 && p < first[base + k]) k--;
   while (k + 1 < nn && p >= first[base + k + 1]) k++;
   return k;
 }
 
+/* Per-thread cursor over TB_ITEMS consecutive list positions: the owning node is searched once and
+ * then advanced incrementally; the node's split data are re-read only when the node changes.      */
 template <int NDIM>
-__device__ __forceinline__ int goes_right(const ListPtrs<NDIM>& L, int d, int cur, int level, int N, int p, int& k)
-{
-  k = node_of_position(p, N, level, L.first);
-  const int n = (1 << level) - 1 + k;
-  const int kd = L.splitdim[k];
-  if (d == kd) return p >= L.first[n] + L.count[n]/2;
-  const int q = (kd - d - 1 + NDIM) % NDIM;
-  return L.rk[d][q < NDIM - 1 ? q : 0][cur][p] >= L.medrank[k];
-}
+struct SideCursor {
+  const ListPtrs<NDIM>& L; int d, cur, level, nn, base;
+  int k, fst, mid, end, kd, mr;
+  __device__ __forceinline__ SideCursor(const ListPtrs<NDIM>& L_, int d_, int cur_, int level_, int N, int p)
+    : L(L_), d(d_), cur(cur_), level(level_), nn(1 << level_), base((1 << level_) - 1)
+  {
+    k = node_of_position(p, (double) nn/(double) N, level, L.first);
+    load();
+  }
+  __device__ __forceinline__ void load()
+  {
+    const int n = base + k;
+    fst = L.first[n]; const int cnt = L.count[n];
+    mid = fst + cnt/2; end = fst + cnt;
+    kd = L.splitdim[k]; mr = L.medrank[k];
+  }
+  __device__ __forceinline__ int goes_right(int p, int rk0, int rk1)
+  {
+    while (p >= end && k + 1 < nn) { k++; load(); }
+    if (d == kd) return p >= mid;
+    const int q = (kd - d - 1 + NDIM) % NDIM;      /* which of the carried ranks belongs to axis kd */
+    return (q == 0 ? rk0 : rk1) >= mr;
+  }
+};
 
+/* Blocked tile layout: every thread owns TB_ITEMS = 4 consecutive list positions, read as one
+ * 16-byte vector per array (the arrays are padded to whole tiles).                                */
 template <int NDIM>
 __global__ void __launch_bounds__(TB_THREADS)
 count_right_kernel(int N, int level, int cur, ListPtrs<NDIM> L)
@@ -699,11 +722,17 @@ count_right_kernel(int N, int level, int cur, ListPtrs<NDIM> L)
   const int d = blockIdx.y;
   const int p0 = blockIdx.x*TB_TILE + threadIdx.x*TB_ITEMS;
   int c = 0;
+  if (p0 < N) {
+    SideCursor<NDIM> sc(L, d, cur, level, N, p0);
+    int4 r0 = make_int4(0, 0, 0, 0), r1 = make_int4(0, 0, 0, 0);
+    if (NDIM > 1) r0 = *reinterpret_cast<const int4*>(L.rk[d][0][cur] + p0);
+    if (NDIM > 2) r1 = *reinterpret_cast<const int4*>(L.rk[d][1][cur] + p0);
+    const int a0[4] = {r0.x, r0.y, r0.z, r0.w}, a1[4] = {r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-  for (int i = 0; i < TB_ITEMS; i++) {
-    const int p = p0 + i;
-    int k;
-    if (p < N) c += goes_right<NDIM>(L, d, cur, level, N, p, k);
+    for (int i = 0; i < TB_ITEMS; i++) {
+      const int p = p0 + i;
+      if (p < N) c += sc.goes_right(p, a0[i], a1[i]);
+    }
   }
   typedef cub::BlockReduce<int, TB_THREADS> BR;
   __shared__ typename BR::TempStorage tmp;
@@ -717,14 +746,23 @@ partition_v2_kernel(int N, int level, int cur, ListPtrs<NDIM> L)
 {
   const int d = blockIdx.y;
   const int p0 = blockIdx.x*TB_TILE + threadIdx.x*TB_ITEMS;
-  int f[TB_ITEMS], kk[TB_ITEMS];
+  int f[TB_ITEMS], kk[TB_ITEMS], md[TB_ITEMS];
+  int idv[4] = {0, 0, 0, 0}, a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0};
   int c = 0;
 #pragma unroll
-  for (int i = 0; i < TB_ITEMS; i++) {
-    const int p = p0 + i;
-    f[i] = 0; kk[i] = 0;
-    if (p < N) f[i] = goes_right<NDIM>(L, d, cur, level, N, p, kk[i]);
-    c += f[i];
+  for (int i = 0; i < TB_ITEMS; i++) { f[i] = 0; kk[i] = 0; md[i] = 0; }
+  if (p0 < N) {
+    SideCursor<NDIM> sc(L, d, cur, level, N, p0);
+    const int4 iv = *reinterpret_cast<const int4*>(L.ids[d][cur] + p0);
+    idv[0] = iv.x; idv[1] = iv.y; idv[2] = iv.z; idv[3] = iv.w;
+    if (NDIM > 1) { const int4 r = *reinterpret_cast<const int4*>(L.rk[d][0][cur] + p0); a0[0] = r.x; a0[1] = r.y; a0[2] = r.z; a0[3] = r.w; }
+    if (NDIM > 2) { const int4 r = *reinterpret_cast<const int4*>(L.rk[d][1][cur] + p0); a1[0] = r.x; a1[1] = r.y; a1[2] = r.z; a1[3] = r.w; }
+#pragma unroll
+    for (int i = 0; i < TB_ITEMS; i++) {
+      const int p = p0 + i;
+      if (p < N) { f[i] = sc.goes_right(p, a0[i], a1[i]); kk[i] = sc.k; md[i] = sc.mid; }
+      c += f[i];
+    }
   }
   typedef cub::BlockScan<int, TB_THREADS> BS;
   __shared__ typename BS::TempStorage tmp;
@@ -736,13 +774,11 @@ partition_v2_kernel(int N, int level, int cur, ListPtrs<NDIM> L)
   for (int i = 0; i < TB_ITEMS; i++) {
     const int p = p0 + i;
     if (p < N) {
-      const int n = (1 << level) - 1 + kk[i];
-      const int fst = L.first[n], nl = L.count[n]/2;
       const int rb = G - L.noderb[kk[i]];              /* right-going entries before p inside the node */
-      const int dest = f[i] ? fst + nl + rb : p - rb;
-      L.ids[d][cur ^ 1][dest] = L.ids[d][cur][p];
-#pragma unroll
-      for (int q = 0; q < NDIM - 1; q++) L.rk[d][q][cur ^ 1][dest] = L.rk[d][q][cur][p];
+      const int dest = f[i] ? md[i] + rb : p - rb;
+      L.ids[d][cur ^ 1][dest] = idv[i];
+      if (NDIM > 1) L.rk[d][0][cur ^ 1][dest] = a0[i];
+      if (NDIM > 2) L.rk[d][1][cur ^ 1][dest] = a1[i];
       G += f[i];
     }
   }
@@ -850,6 +886,7 @@ int build_tree_v2(gsph_handle* h)
   }
   CUDA_TRY(h, cudaGetLastError());
   CUDA_TRY(h, cudaMemcpyAsync(h->perm, L.ids[0][cur], sizeof(int)*(size_t) N, cudaMemcpyDeviceToDevice, s));
+  cudaStreamWaitEvent(s, h->ev_all, 0);      /* every uploaded field has landed */
   gather_kernel<<<(N + 255)/256, 256, 0, s>>>(N, h->perm, Hh, Pp);
   h->stats.kernel_launches++;
   h->sorted_valid = true;

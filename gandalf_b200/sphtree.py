@@ -127,9 +127,13 @@ class GpuSphTree(object):
         pv = parts.view(only)
         self._check(self._L.gsph_upload(self._h, C.byref(pv), parts.N))
 
-    def Download(self, parts, mask=_capi.F_ALL, only=None):
+    def Download(self, parts, mask=_capi.F_ALL, only=None, wait=True):
+        """wait=False queues the device->host copies on the library's copy stream and returns
+        (gsph_download_async); they overlap the kernels issued afterwards.  Synchronize() or the
+        next blocking Download() completes them."""
         pv = parts.view(only)
-        self._check(self._L.gsph_download(self._h, C.byref(pv), mask))
+        fn = self._L.gsph_download if wait else self._L.gsph_download_async
+        self._check(fn(self._h, C.byref(pv), mask))
 
     # ---- NeighbourSearch / SphNeighbourSearch surface -----------------------------------------------
     def BuildTree(self, rebuild_tree, n, ntreebuildstep, ntreestockstep, timestep, parts=None):
@@ -167,6 +171,18 @@ class GpuSphTree(object):
 
     def UpdateAllSphForces(self):
         self._check(self._L.gsph_update_all_forces(self._h, None, 0))
+
+    def SetStars(self, r=None, m=None, h=None):
+        """nbody->nbodydata for GradhSph::ComputeStarGravForces (GradhSph.cpp:699-743): star positions
+        (Nstar, ndim), masses and smoothing lengths; applied by both force passes until cleared
+        with SetStars()."""
+        if r is None or len(m) == 0:
+            self._check(self._L.gsph_set_stars(self._h, None, 0))
+            return
+        r = np.asarray(r, dtype=np.float64).reshape(len(m), -1)
+        stars = np.ascontiguousarray(np.concatenate([r, np.asarray(m, dtype=np.float64)[:, None],
+                                                     np.asarray(h, dtype=np.float64)[:, None]], axis=1))
+        self._check(self._L.gsph_set_stars(self._h, stars.ctypes.data, len(m)))
 
     def GetMaximumSmoothingLength(self):
         v = C.c_double()

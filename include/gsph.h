@@ -160,6 +160,13 @@ const char* gsph_last_error(const gsph_handle* h);                  /* h may be 
  * gsph_download: results back into the host view, in the host's particle order.                    */
 int gsph_upload(gsph_handle* h, const gsph_particle_view* view, int64_t Nhydro);
 int gsph_download(gsph_handle* h, const gsph_particle_view* view, uint32_t field_mask);
+/* Copies run on the library's own copy stream.  gsph_upload returns as soon as the copies are
+ * queued (host memory must stay valid until the next synchronising call; pinned memory makes them
+ * truly asynchronous): r, h and the integer fields go first and gsph_build_tree starts on them while
+ * v, m, u, ... are still in flight.  gsph_download_async queues the device->host copies behind the
+ * kernels issued so far and returns; later kernels (e.g. the force pass after a density download)
+ * overlap them.  gsph_synchronize (or a plain gsph_download) waits for everything.               */
+int gsph_download_async(gsph_handle* h, const gsph_particle_view* view, uint32_t field_mask);
 
 /* ---- the operator surface ----------------------------------------------------------------------
  * gsph_build_tree           NeighbourSearch::BuildTree          HydroTree.cpp:310-372
@@ -182,6 +189,11 @@ int gsph_update_properties(gsph_handle* h);
 int gsph_zero_accelerations(gsph_handle* h);
 int gsph_update_hydro_forces(gsph_handle* h);
 int gsph_update_all_forces(gsph_handle* h, const double* stars, int Nstar);
+/* Star particles for GradhSph::ComputeStarGravForces (GradhSph.cpp:699-743; called for every active
+ * particle by both force drivers when nbody->Nnbody > 0, GradhSphTree.cpp:385-392, :600-607):
+ * stars = Nstar x {r[ndim], m, h} doubles.  The list stays on the device and is applied by
+ * gsph_update_hydro_forces and gsph_update_all_forces until replaced; Nstar = 0 clears it.         */
+int gsph_set_stars(gsph_handle* h, const double* stars, int Nstar);
 int gsph_get_hmax(gsph_handle* h, double* hmax);
 int gsph_synchronize(gsph_handle* h);
 /* CUDA-event stopwatch on the handle's stream (torch.cuda.Event only sees torch's streams):

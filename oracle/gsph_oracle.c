@@ -551,6 +551,31 @@ static void finish_particle(const orc_params* p, const pview* P, int i, int grav
   }
 }
 
+/* GradhSph::ComputeStarGravForces, src/GradhSph/GradhSph.cpp:699-743 (fixed_sink_mass = 0) */
+int orc_star_grav_forces(const orc_params* p, int N, const double* r, const double* h, int Nstar,
+                         const double* stars, double* a, double* atree, double* gpot)
+{
+  const int nd = p->ndim;
+  for (int i = 0; i < N; i++) {
+    double at[3] = {0, 0, 0}, pot = 0.0;
+    for (int j = 0; j < Nstar; j++) {
+      const double* s = stars + (size_t)j*(nd + 2);
+      const double ms = s[nd], hs = s[nd + 1];
+      double dr[3] = {0, 0, 0}, drsqd = 0.0;
+      for (int k = 0; k < nd; k++) { dr[k] = s[k] - r[(size_t)i*nd + k]; drsqd += dr[k]*dr[k]; }
+      drsqd += 1.0e-20;
+      const double drmag = sqrt(drsqd), invdrmag = 1.0/drmag;
+      const double invhmean = 2.0/(h[i] + hs);
+      const double paux = ms*invhmean*invhmean*orc_kernel(p, 4, drmag*invhmean)*invdrmag;
+      for (int k = 0; k < nd; k++) at[k] += paux*dr[k];
+      pot += ms*invhmean*orc_kernel(p, 5, drmag*invhmean);
+    }
+    for (int k = 0; k < nd; k++) { atree[(size_t)i*nd + k] += at[k]; a[(size_t)i*nd + k] += at[k]; }
+    gpot[i] += pot;
+  }
+  return 0;
+}
+
 /* GradhSphTree::UpdateAllSphHydroForces, src/GradhSph/GradhSphTree.cpp:327-406 */
 int orc_hydro_forces(const orc_params* p, int N, const double* r, const double* v, const double* m,
                      const double* h, const double* rho, const double* pressure,

@@ -68,6 +68,13 @@ int orc_hydro_forces(const orc_params* p, int N, const double* r, const double* 
                      const int32_t* level,
                      double* a, double* dudt, double* div_v, double* dalphadt, int32_t* levelneib);
 
+/* GradhSph::ComputeStarGravForces, src/GradhSph/GradhSph.cpp:699-743, for every particle: softened
+ * gravity of Nstar stars {r[ndim], m, h} (stride ndim+2) with the mean-h kernel; adds to atree and,
+ * like both force drivers do (GradhSphTree.cpp:396-399, :611-614), to a, and to gpot.
+ * (parity unpinned: no golden vector of the reference with stars is shipped)                       */
+int orc_star_grav_forces(const orc_params* p, int N, const double* r, const double* h, int Nstar,
+                         const double* stars, double* a, double* atree, double* gpot);
+
 /* hydro+gravity with EXACT direct summation for everything outside the kernel overlap
  * (what the reference computes with neib_search = bruteforce: every other particle is either a
  * hydro neighbour -> ComputeSphHydroGravForces GradhSph.cpp:474-585, or an unsoftened direct

@@ -1,0 +1,8 @@
+#!/bin/bash
+tag=${1:-r}
+out=gpurun_out/$tag
+mkdir -p $out
+echo "== pytest"; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 | tee $out/pytest.txt
+echo "== bench 16M"; timeout 600 python bench.py --particles 16777216 --steps 2 --warmup 1 --no-cpu-baseline > $out/bench16m.json 2> $out/bench16m.err; python scratch/show_bench.py $out/bench16m.json; tail -3 $out/bench16m.err
+echo "== bench 64M"; timeout 900 python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $out/bench64m.json 2> $out/bench64m.err; python scratch/show_bench.py $out/bench64m.json; tail -3 $out/bench64m.err
+echo "== launch list 16M"; timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/launches16m.csv python bench.py --particles 16777216 --steps 1 --warmup 0 --no-cpu-baseline > $out/launches16m.log 2>&1; wc -l $out/launches16m.csv

@@ -62,6 +62,8 @@ def lib():
         _lib.orc_hydro_forces.argtypes = [P, C.c_int] + [_dp] * 12 + [_ip] + [_dp] * 4 + [_ip]
         _lib.orc_hydro_grav_forces_direct.restype = C.c_int
         _lib.orc_hydro_grav_forces_direct.argtypes = [P, C.c_int] + [_dp] * 13 + [_ip] + [_dp] * 6 + [_ip]
+        _lib.orc_star_grav_forces.restype = C.c_int
+        _lib.orc_star_grav_forces.argtypes = [P, C.c_int, _dp, _dp, C.c_int, _dp, _dp, _dp, _dp]
         _lib.orc_tree_build.restype = C.c_void_p
         _lib.orc_tree_build.argtypes = [P, C.c_int, _dp, _dp, _dp, _dp]
         _lib.orc_tree_free.restype = None
@@ -201,6 +203,18 @@ def hydro_grav_forces_direct(p, s):
     lib().orc_hydro_grav_forces_direct(C.byref(p), N, *_grav_args(p, s), out["a"], out["atree"], out["gpot"],
                                        out["dudt"], out["div_v"], out["dalphadt"], out["levelneib"])
     return out
+
+
+def star_grav_forces(p, r, h, rstar, mstar, hstar):
+    """GradhSph::ComputeStarGravForces for every particle -> (a, atree, gpot) contributions"""
+    N = len(h)
+    nd = p.ndim
+    stars = np.ascontiguousarray(np.concatenate([np.asarray(rstar, dtype=np.float64).reshape(len(mstar), nd),
+                                                 np.asarray(mstar, dtype=np.float64)[:, None],
+                                                 np.asarray(hstar, dtype=np.float64)[:, None]], axis=1))
+    a = np.zeros((N, nd)); atree = np.zeros((N, nd)); gpot = np.zeros(N)
+    lib().orc_star_grav_forces(C.byref(p), N, _c(r).reshape(N, nd), _c(h), len(mstar), stars, a, atree, gpot)
+    return a, atree, gpot
 
 
 class Tree:

@@ -400,3 +400,42 @@ def test_gravity_sphere_vs_oracle_tree():
         st = tree.Stats()
         assert abs(st.ncell_mean - out["ncell"].mean()) < 1e-9*max(1.0, out["ncell"].mean())
         tree.close()
+
+
+@pytest.mark.parametrize("grav", [0, 1])
+@pytest.mark.parametrize("tab", [0, 1])
+def test_star_gravity_vs_oracle(grav, tab):
+    """GradhSph::ComputeStarGravForces (GradhSph.cpp:699-743): both force drivers add the softened
+    gravity of the stars to atree, a and gpot of every active particle.  The star terms are linear, so
+    (forces with stars) - (forces without) must equal the oracle's star sum."""
+    import gandalf_b200 as g
+    rng = np.random.default_rng(5)
+    N = 3000
+    r = rng.uniform(-1, 1, (N, 3)); r = r[np.linalg.norm(r, axis=1) < 1.0]
+    N = len(r)
+    v = 0.1*rng.normal(size=(N, 3)); m = np.full(N, 1.0/N); u = np.full(N, 0.05); h = np.full(N, 0.2)
+    rstar = np.array([[0.05, -0.02, 0.01], [0.6, 0.5, -0.4], [-3.0, 0.1, 0.2]])   # inside, inside, far outside
+    mstar = np.array([0.3, 0.05, 2.0]); hstar = np.array([0.05, 0.3, 0.1])
+    params = {"ndim": 3, "self_gravity": grav, "tabulated_kernel": tab, "multipole": "quadrupole"}
+    p = orc.params_from_dict(params)
+    res = []
+    for stars in (False, True):
+        ps = g.ParticleSet(N, 3).set(r=r, v=v, m=m, h=h, u=u)
+        tree = g.GpuSphTree(params)
+        tree.BuildTree(True, 0, 1, 1, 0.0, ps)
+        tree.UpdateAllSphProperties()
+        if stars:
+            tree.SetStars(rstar, mstar, hstar)
+        tree.ZeroAccelerations()
+        if grav:
+            tree.UpdateAllSphForces()
+        else:
+            tree.UpdateAllSphHydroForces()
+        tree.Download(ps)
+        res.append({k: ps[k].copy() for k in ("a", "atree", "gpot", "h")})
+        tree.close()
+    a, atree, gpot = orc.star_grav_forces(p, r, res[1]["h"], rstar, mstar, hstar)
+    scale = np.linalg.norm(atree, axis=1).max()
+    assert np.abs((res[1]["atree"] - res[0]["atree"]) - atree).max() < 1e-9*scale
+    assert np.abs((res[1]["a"] - res[0]["a"]) - a).max() < 1e-9*scale
+    assert np.abs((res[1]["gpot"] - res[0]["gpot"]) - gpot).max() < 1e-9*np.abs(gpot).max()
