@@ -18,7 +18,7 @@ MAC = {"geometric": 0, "eigenmac": 1, "gadget2": 2}
 MULTIPOLE = {"monopole": 0, "quadrupole": 1, "fast_monopole": 2, "fast_quadrupole": 3}
 FLAG_DEAD, FLAG_ACTIVE, FLAG_POTMIN = 1, 2, 8
 F_DENSITY, F_FORCES, F_ALL = 1, 2, 0xFFFFFFFF
-DEVICE_FIELDS = ("h", "rho", "hrangesqd", "hfactor", "invomega", "zeta", "sound", "pressure", "u")
+DEVICE_FIELDS = ("h", "rho", "hrangesqd", "hfactor", "invomega", "zeta", "sound", "pressure", "u", "perm")
 ERRORS = {1: "GSPH_EINVAL", 2: "GSPH_ENODEVICE", 3: "GSPH_ECUDA", 4: "GSPH_ENOMEM", 5: "GSPH_ESTATE",
           6: "GSPH_ECONVERGE"}
 
@@ -73,7 +73,8 @@ class Stats(C.Structure):
 
 EXPORTS = [
     "gsph_default_config", "gsph_create", "gsph_destroy", "gsph_last_error", "gsph_upload", "gsph_download",
-    "gsph_download_async", "gsph_set_stars",
+    "gsph_download_async", "gsph_set_stars", "gsph_tree_shard_range", "gsph_build_tree_shard_begin",
+    "gsph_build_tree_shard_finish",
     "gsph_build_tree", "gsph_update_active_counters", "gsph_update_properties", "gsph_zero_accelerations",
     "gsph_update_hydro_forces", "gsph_update_all_forces", "gsph_get_hmax", "gsph_synchronize",
     "gsph_timer_start", "gsph_timer_stop", "gsph_set_active_slice", "gsph_density_pass", "gsph_refresh_hmax",
@@ -111,6 +112,9 @@ def lib():
     L.gsph_download.argtypes = [H, C.POINTER(ParticleView), C.c_uint32]
     L.gsph_download_async.argtypes = [H, C.POINTER(ParticleView), C.c_uint32]
     L.gsph_set_stars.argtypes = [H, C.c_void_p, C.c_int]
+    L.gsph_tree_shard_range.argtypes = [H, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.gsph_build_tree_shard_begin.argtypes = [H, C.c_int, C.c_int]
+    L.gsph_build_tree_shard_finish.argtypes = [H]
     L.gsph_build_tree.argtypes = [H, C.c_int, C.c_double]
     for n in ("gsph_update_active_counters", "gsph_update_properties", "gsph_zero_accelerations",
               "gsph_update_hydro_forces", "gsph_synchronize", "gsph_timer_start", "gsph_density_pass",

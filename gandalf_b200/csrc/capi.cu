@@ -578,6 +578,58 @@ int gsph_build_tree(gsph_handle* h, int mode, double dt)
   return GSPH_OK;
 }
 
+/* Multi-GPU tree build: rank `rank` of `world` (a power of two) builds the top
+ * log2(world) levels and then only ITS subtree; see build_tree_v2 in tree.cu. */
+int gsph_tree_shard_range(gsph_handle* h, int rank, int world, int64_t* lo, int64_t* hi)
+{
+  if (!h || !lo || !hi) return GSPH_EINVAL;
+  if (world < 1 || (world & (world - 1)) || rank < 0 || rank >= world) { h->err = "gsph_tree_shard_range: world must be a power of two, 0 <= rank < world"; return GSPH_EINVAL; }
+  int ltop = 0; while ((1 << ltop) < world) ltop++;
+  int64_t a = 0, b = h->N;
+  for (int bit = ltop - 1; bit >= 0; bit--) {
+    const int64_t left = (b - a)/2;
+    if ((rank >> bit) & 1) a += left; else b = a + left;
+  }
+  *lo = a; *hi = b;
+  return GSPH_OK;
+}
+
+int gsph_build_tree_shard_begin(gsph_handle* h, int rank, int world)
+{
+  if (!h) return GSPH_EINVAL;
+  if (!h->uploaded) { h->err = "gsph_build_tree_shard_begin before gsph_upload"; return GSPH_ESTATE; }
+  if (world < 1 || (world & (world - 1)) || rank < 0 || rank >= world) { h->err = "gsph_build_tree_shard_begin: world must be a power of two, 0 <= rank < world"; return GSPH_EINVAL; }
+  int ltot = 0;
+  while ((int64_t) h->cfg.Nleafmax*((int64_t)1 << ltot) < h->N) ltot++;
+  if ((1 << ltot) < world) { h->err = "gsph_build_tree_shard_begin: more ranks than leaf cells"; return GSPH_EINVAL; }
+  cudaSetDevice(h->device);
+  Timer tm(h, &h->stats.ms_build_tree);
+  int rc = gsph_tree_build_sharded(h, 1, rank, world);
+  if (rc) return rc;
+  tm.stop();
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return GSPH_OK;
+}
+
+int gsph_build_tree_shard_finish(gsph_handle* h)
+{
+  if (!h) return GSPH_EINVAL;
+  if (!h->uploaded) { h->err = "gsph_build_tree_shard_finish before gsph_upload"; return GSPH_ESTATE; }
+  cudaSetDevice(h->device);
+  float ms_begin = h->stats.ms_build_tree;
+  Timer tm(h, &h->stats.ms_build_tree);
+  int rc = gsph_tree_build_sharded(h, 2, 0, 1);
+  if (rc) return rc;
+  int nact = 0;
+  CUDA_TRY(h, cudaMemcpyAsync(&nact, h->tree.nactive, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  tm.stop();
+  h->stats.ms_build_tree += ms_begin;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  h->all_active = (nact == h->N);
+  h->stats.n_active = nact;
+  return GSPH_OK;
+}
+
 int gsph_update_active_counters(gsph_handle* h)
 {
   if (!h) return GSPH_EINVAL;
@@ -719,8 +771,14 @@ int gsph_set_active_slice(gsph_handle* h, int64_t lo, int64_t hi)
 int gsph_device_field(gsph_handle* h, int field, void** ptr, int64_t* capacity)
 {
   if (!h || !ptr) return GSPH_EINVAL;
-  static const int map[GSPH_DF_COUNT] = {F_H, F_RHO, F_HR2, F_HFAC, F_INVOMEGA, F_ZETA, F_SOUND, F_PRESS, F_U};
+  static const int map[GSPH_DF_COUNT] = {F_H, F_RHO, F_HR2, F_HFAC, F_INVOMEGA, F_ZETA, F_SOUND, F_PRESS, F_U, -1};
   if (field < 0 || field >= GSPH_DF_COUNT) { h->err = "gsph_device_field: unknown field"; return GSPH_EINVAL; }
+  if (field == GSPH_DF_PERM) {
+    if (!h->perm) { h->err = "gsph_device_field before gsph_upload"; return GSPH_ESTATE; }
+    *ptr = h->perm;
+    if (capacity) *capacity = h->Ncap;
+    return GSPH_OK;
+  }
   if (!h->P[map[field]]) { h->err = "gsph_device_field before gsph_upload"; return GSPH_ESTATE; }
   *ptr = h->P[map[field]];
   if (capacity) *capacity = h->Ncap;

@@ -156,6 +156,7 @@ struct gsph_handle {
 void gsph_make_tables(int ndim, int kernel, double* out6x1000);       /* tables.cu  */
 double gsph_kernnorm(int ndim, int kernel);
 int gsph_tree_build(gsph_handle* h, int mode, double dt);             /* tree.cu    */
+int gsph_tree_build_sharded(gsph_handle* h, int phase, int rank, int world);
 int gsph_tree_update_hmax(gsph_handle* h);
 int gsph_tree_update_active(gsph_handle* h);
 int gsph_run_density(gsph_handle* h);                                 /* density.cu */

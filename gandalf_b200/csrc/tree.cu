@@ -83,87 +83,6 @@ __global__ void iota_kernel(int N, int* a)
   if (i < N) a[i] = i;
 }
 
-struct LevelPtrs {
-  const int* list[3];
-  int* newlist[3];
-  const double* r[3];     /* host-order coordinates */
-  double* ibmin[3]; double* ibmax[3];       /* inherited boxes of this level, index k          */
-  double* cibmin[3]; double* cibmax[3];     /* inherited boxes of the next level               */
-  int* first; int* count;                   /* heap-order node arrays                          */
-  int8_t* splitdim;                         /* per node of this level                          */
-  uint8_t* side;                            /* per particle (host index)                       */
-  int* nodeidx;                             /* per position: node index inside the level       */
-  const int* scan[3];
-};
-
-/* DivideTreeCell for every node of one level, KDTree.cpp:492-560 */
-template <int NDIM>
-__global__ void split_nodes_kernel(int level, LevelPtrs L)
-{
-  const int k = blockIdx.x*blockDim.x + threadIdx.x;
-  if (k >= (1 << level)) return;
-  const int n = (1 << level) - 1 + k;
-  const int cnt = L.count[n], fst = L.first[n];
-  int kd = 0; double rkmax = 0.0;
-#pragma unroll
-  for (int d = 0; d < NDIM; d++) {
-    const double w = __dadd_rn(L.ibmax[d][k], -L.ibmin[d][k]);
-    if (w > rkmax) { rkmax = w; kd = d; }
-  }
-  const int left = cnt/2;
-  double rdiv = 0.0;
-  if (cnt > 0) rdiv = L.r[kd][L.list[kd][fst + left]];
-  const int c1 = 2*n + 1, c2 = 2*n + 2;
-  L.first[c1] = fst;        L.count[c1] = left;
-  L.first[c2] = fst + left; L.count[c2] = cnt - left;
-#pragma unroll
-  for (int d = 0; d < NDIM; d++) {
-    const double mn = L.ibmin[d][k], mx = L.ibmax[d][k];
-    L.cibmin[d][2*k] = mn;                       L.cibmax[d][2*k] = (d == kd) ? rdiv : mx;
-    L.cibmin[d][2*k + 1] = (d == kd) ? rdiv : mn; L.cibmax[d][2*k + 1] = mx;
-  }
-  L.splitdim[k] = (int8_t) kd;
-}
-
-__global__ void mark_side_kernel(int N, int level, LevelPtrs L)
-{
-  const int p = blockIdx.x*blockDim.x + threadIdx.x;
-  if (p >= N) return;
-  const int k = L.nodeidx[p];
-  const int n = (1 << level) - 1 + k;
-  const int kd = L.splitdim[k];
-  const int pm = L.first[n] + L.count[n]/2;
-  L.side[L.list[kd][p]] = (uint8_t)(p >= pm);
-}
-
-struct SideOfList {
-  const int* list; const uint8_t* side;
-  __host__ __device__ __forceinline__ int operator()(const int& p) const { return (int) side[list[p]]; }
-};
-
-__global__ void partition_kernel(int N, int level, int d, LevelPtrs L)
-{
-  const int p = blockIdx.x*blockDim.x + threadIdx.x;
-  if (p >= N) return;
-  const int k = L.nodeidx[p];
-  const int n = (1 << level) - 1 + k;
-  const int fst = L.first[n], nl = L.count[n]/2;
-  const int id = L.list[d][p];
-  const int f = L.side[id];
-  const int rb = L.scan[d][p] - L.scan[d][fst];       /* right-going elements before p in the node */
-  const int dest = f ? fst + nl + rb : p - rb;
-  L.newlist[d][dest] = id;
-}
-
-__global__ void update_nodeidx_kernel(int N, int level, LevelPtrs L)
-{
-  const int p = blockIdx.x*blockDim.x + threadIdx.x;
-  if (p >= N) return;
-  const int k = L.nodeidx[p];
-  const int n = (1 << level) - 1 + k;
-  L.nodeidx[p] = 2*k + (p >= L.first[n] + L.count[n]/2 ? 1 : 0);
-}
-
 /* ---- permute all particle fields from host order into tree order -------------------------------*/
 __global__ void gather_kernel(int N, const int32_t* perm, PartView Hh, PartView Pp)
 {
@@ -449,7 +368,7 @@ int stock_tree(gsph_handle* h, int full)
 }
 
 template <int NDIM>
-int build_tree_v2(gsph_handle* h);
+int build_tree_v2(gsph_handle* h, int phase, int shard_rank, int shard_world);
 
 template <int NDIM>
 int build_tree_nd(gsph_handle* h, int mode, double dt)
@@ -483,112 +402,7 @@ int build_tree_nd(gsph_handle* h, int mode, double dt)
   }
 
   /* ---- full rebuild ----------------------------------------------------------------------------*/
-  {
-    static const bool use_v1 = getenv("GSPH_TREE_V1") != nullptr;   /* A/B switch: first-generation build */
-    if (!use_v1) return build_tree_v2<NDIM>(h);
-  }
-  int ltot = 0;                                       /* ComputeTreeSize, KDTree.cpp:322-352 */
-  while ((int64_t) h->cfg.Nleafmax*((int64_t)1 << ltot) < (int64_t) N) ltot++;
-  int rc = alloc_tree(h, ltot);
-  if (rc) return rc;
-  TreeDev& T = h->tree;
-  const int nleaf = 1 << ltot;
-
-  /* scratch layout */
-  size_t cub_sort = 0, cub_scan = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, cub_sort, (const double*) nullptr, (double*) nullptr,
-                                  (const int*) nullptr, (int*) nullptr, N, 0, 64, s);
-  {
-    SideOfList op{nullptr, nullptr};
-    cub::CountingInputIterator<int> cnt(0);
-    cub::TransformInputIterator<int, SideOfList, cub::CountingInputIterator<int>> it(cnt, op);
-    cub::DeviceScan::ExclusiveSum(nullptr, cub_scan, it, (int*) nullptr, N, s);
-  }
-  const size_t cub_bytes = cub_sort > cub_scan ? cub_sort : cub_scan;
-  const size_t need = (size_t) N*(sizeof(int)*(2*nd + 1 + nd) + sizeof(double) + 1)
-                      + (size_t) nleaf*(sizeof(double)*4*nd + 1) + cub_bytes + 64*1024 + 4096*2*nd*sizeof(double);
-  if (need > h->scratch_bytes) {
-    if (h->scratch) cudaFree(h->scratch);
-    h->scratch = nullptr; h->scratch_bytes = 0;
-    CUDA_TRY(h, cudaMalloc(&h->scratch, need + need/8));
-    h->scratch_bytes = need + need/8;
-  }
-  Bump B{(char*) h->scratch, 0, h->scratch_bytes};
-  int* list[3][2]; int* scan[3];
-  for (int d = 0; d < nd; d++) { list[d][0] = B.get<int>(N); list[d][1] = B.get<int>(N); scan[d] = B.get<int>(N); }
-  int* nodeidx = B.get<int>(N);
-  double* keys_out = B.get<double>(N);
-  uint8_t* side = B.get<uint8_t>(N);
-  double *ib[2][2][3];
-  for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) for (int d = 0; d < nd; d++) ib[a][b][d] = B.get<double>(nleaf);
-  int8_t* splitdim = B.get<int8_t>(nleaf);
-  const int rb_blocks = 1024;
-  double* rbpart = B.get<double>((size_t) rb_blocks*2*nd);
-  void* cubtmp = B.get<char>(cub_bytes);
-  if (B.off > B.cap) { h->err = "internal: tree scratch layout overflow"; return GSPH_ENOMEM; }
-
-  /* root box and the three presorted lists */
-  root_box_kernel<NDIM><<<rb_blocks, 256, 0, s>>>(N, Hh, h->dp.kernrange, rbpart);
-  root_box_final<NDIM><<<1, 32, 0, s>>>(rb_blocks, rbpart, ib[0][0][0], nd > 1 ? ib[0][0][1] : nullptr,
-                                        nd > 2 ? ib[0][0][2] : nullptr, ib[0][1][0],
-                                        nd > 1 ? ib[0][1][1] : nullptr, nd > 2 ? ib[0][1][2] : nullptr);
-  h->stats.kernel_launches += 2;
-  cudaEventRecord(h->evk[3][0], s);
-  for (int d = 0; d < nd; d++) {
-    iota_kernel<<<(N + 255)/256, 256, 0, s>>>(N, list[d][1]);
-    size_t tb = cub_bytes;
-    cub::DeviceRadixSort::SortPairs(cubtmp, tb, (const double*) h->H[F_RX + d], keys_out,
-                                    (const int*) list[d][1], list[d][0], N, 0, 64, s);
-    h->stats.kernel_launches += 8;
-  }
-  cudaEventRecord(h->evk[3][1], s); h->evk_used[3] = true;
-  cudaEventRecord(h->evk[4][0], s);
-  CUDA_TRY(h, cudaMemsetAsync(nodeidx, 0, sizeof(int)*(size_t) N, s));
-  {
-    const int one[2] = {0, N};
-    CUDA_TRY(h, cudaMemcpyAsync(T.first, &one[0], sizeof(int), cudaMemcpyHostToDevice, s));
-    CUDA_TRY(h, cudaMemcpyAsync(T.count, &one[1], sizeof(int), cudaMemcpyHostToDevice, s));
-  }
-  int cur[3] = {0, 0, 0};
-  for (int l = 0; l < ltot; l++) {
-    LevelPtrs L;
-    const int a = l & 1;
-    for (int d = 0; d < 3; d++) {
-      L.list[d] = d < nd ? list[d][cur[d]] : nullptr;
-      L.newlist[d] = d < nd ? list[d][cur[d] ^ 1] : nullptr;
-      L.r[d] = d < nd ? h->H[F_RX + d] : nullptr;
-      L.ibmin[d] = d < nd ? ib[a][0][d] : nullptr;      L.ibmax[d] = d < nd ? ib[a][1][d] : nullptr;
-      L.cibmin[d] = d < nd ? ib[a ^ 1][0][d] : nullptr; L.cibmax[d] = d < nd ? ib[a ^ 1][1][d] : nullptr;
-      L.scan[d] = d < nd ? scan[d] : nullptr;
-    }
-    L.first = T.first; L.count = T.count; L.splitdim = splitdim; L.side = side; L.nodeidx = nodeidx;
-    const int nn = 1 << l;
-    split_nodes_kernel<NDIM><<<(nn + 127)/128, 128, 0, s>>>(l, L);
-    mark_side_kernel<<<(N + 255)/256, 256, 0, s>>>(N, l, L);
-    for (int d = 0; d < nd; d++) {
-      SideOfList op{L.list[d], side};
-      cub::CountingInputIterator<int> cnt(0);
-      cub::TransformInputIterator<int, SideOfList, cub::CountingInputIterator<int>> it(cnt, op);
-      size_t tb = cub_bytes;
-      cub::DeviceScan::ExclusiveSum(cubtmp, tb, it, scan[d], N, s);
-      partition_kernel<<<(N + 255)/256, 256, 0, s>>>(N, l, d, L);
-      cur[d] ^= 1;
-    }
-    update_nodeidx_kernel<<<(N + 255)/256, 256, 0, s>>>(N, l, L);
-    h->stats.kernel_launches += 3 + 3*nd;
-  }
-  CUDA_TRY(h, cudaGetLastError());
-  CUDA_TRY(h, cudaMemcpyAsync(h->perm, list[0][cur[0]], sizeof(int)*(size_t) N, cudaMemcpyDeviceToDevice, s));
-  cudaStreamWaitEvent(s, h->ev_all, 0);      /* every uploaded field has landed */
-  gather_kernel<<<(N + 255)/256, 256, 0, s>>>(N, h->perm, Hh, Pp);
-  h->stats.kernel_launches++;
-  h->sorted_valid = true;
-  h->have_tree = true;
-  cudaEventRecord(h->evk[4][1], s); h->evk_used[4] = true;
-  cudaEventRecord(h->evk[5][0], s);
-  const int rcs = stock_tree<NDIM>(h, 1);
-  cudaEventRecord(h->evk[5][1], s); h->evk_used[5] = true;
-  return rcs;
+  return build_tree_v2<NDIM>(h, 0, 0, 1);
 }
 
 /*================================================================================================
@@ -639,13 +453,23 @@ __global__ void fill_ranks_kernel(int N, ListPtrs<NDIM> L)
 
 /* DivideTreeCell for every node of one level, KDTree.cpp:492-560 */
 template <int NDIM>
-__global__ void split_nodes_v2_kernel(int level, int cur, ListPtrs<NDIM> L)
+__global__ void split_nodes_v2_kernel(int level, int cur, int klo, int khi, ListPtrs<NDIM> L)
 {
   const int k = blockIdx.x*blockDim.x + threadIdx.x;
   if (k >= (1 << level)) return;
   const int n = (1 << level) - 1 + k;
   const int a = level & 1;
   const int cnt = L.count[n], fst = L.first[n];
+  /* node sizes of the balanced tree do not depend on the data: every rank fills first/count (and the
+     right-going counts) of ALL nodes; split axis, median and boxes only exist for the nodes of its
+     own shard [klo, khi) */
+  if (k < klo || k >= khi) {
+    const int c1o = 2*n + 1, c2o = 2*n + 2, lefto = cnt/2;
+    L.first[c1o] = fst;         L.count[c1o] = lefto;
+    L.first[c2o] = fst + lefto; L.count[c2o] = cnt - lefto;
+    L.noderb[k] = cnt - lefto;
+    return;
+  }
   int kd = 0; double rkmax = 0.0;
 #pragma unroll
   for (int d = 0; d < NDIM; d++) {
@@ -717,12 +541,16 @@ struct SideCursor {
  * 16-byte vector per array (the arrays are padded to whole tiles).                                */
 template <int NDIM>
 __global__ void __launch_bounds__(TB_THREADS)
-count_right_kernel(int N, int level, int cur, ListPtrs<NDIM> L)
+count_right_kernel(int N, int level, int cur, int plo, int phi, ListPtrs<NDIM> L)
 {
   const int d = blockIdx.y;
   const int p0 = blockIdx.x*TB_TILE + threadIdx.x*TB_ITEMS;
+  if ((int)(blockIdx.x + 1)*TB_TILE <= plo || (int) blockIdx.x*TB_TILE >= phi) {     /* tile of another shard */
+    if (threadIdx.x == 0) L.tilecnt[d*L.ntile + blockIdx.x] = 0;
+    return;
+  }
   int c = 0;
-  if (p0 < N) {
+  if (p0 < phi && p0 + TB_ITEMS > plo) {
     SideCursor<NDIM> sc(L, d, cur, level, N, p0);
     int4 r0 = make_int4(0, 0, 0, 0), r1 = make_int4(0, 0, 0, 0);
     if (NDIM > 1) r0 = *reinterpret_cast<const int4*>(L.rk[d][0][cur] + p0);
@@ -731,7 +559,7 @@ count_right_kernel(int N, int level, int cur, ListPtrs<NDIM> L)
 #pragma unroll
     for (int i = 0; i < TB_ITEMS; i++) {
       const int p = p0 + i;
-      if (p < N) c += sc.goes_right(p, a0[i], a1[i]);
+      if (p >= plo && p < phi) c += sc.goes_right(p, a0[i], a1[i]);
     }
   }
   typedef cub::BlockReduce<int, TB_THREADS> BR;
@@ -742,16 +570,17 @@ count_right_kernel(int N, int level, int cur, ListPtrs<NDIM> L)
 
 template <int NDIM>
 __global__ void __launch_bounds__(TB_THREADS)
-partition_v2_kernel(int N, int level, int cur, ListPtrs<NDIM> L)
+partition_v2_kernel(int N, int level, int cur, int plo, int phi, int klo, ListPtrs<NDIM> L)
 {
   const int d = blockIdx.y;
   const int p0 = blockIdx.x*TB_TILE + threadIdx.x*TB_ITEMS;
+  if ((int)(blockIdx.x + 1)*TB_TILE <= plo || (int) blockIdx.x*TB_TILE >= phi) return;   /* tile of another shard */
   int f[TB_ITEMS], kk[TB_ITEMS], md[TB_ITEMS];
   int idv[4] = {0, 0, 0, 0}, a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0};
   int c = 0;
 #pragma unroll
   for (int i = 0; i < TB_ITEMS; i++) { f[i] = 0; kk[i] = 0; md[i] = 0; }
-  if (p0 < N) {
+  if (p0 < phi && p0 + TB_ITEMS > plo) {
     SideCursor<NDIM> sc(L, d, cur, level, N, p0);
     const int4 iv = *reinterpret_cast<const int4*>(L.ids[d][cur] + p0);
     idv[0] = iv.x; idv[1] = iv.y; idv[2] = iv.z; idv[3] = iv.w;
@@ -760,7 +589,7 @@ partition_v2_kernel(int N, int level, int cur, ListPtrs<NDIM> L)
 #pragma unroll
     for (int i = 0; i < TB_ITEMS; i++) {
       const int p = p0 + i;
-      if (p < N) { f[i] = sc.goes_right(p, a0[i], a1[i]); kk[i] = sc.k; md[i] = sc.mid; }
+      if (p >= plo && p < phi) { f[i] = sc.goes_right(p, a0[i], a1[i]); kk[i] = sc.k; md[i] = sc.mid; }
       c += f[i];
     }
   }
@@ -768,12 +597,13 @@ partition_v2_kernel(int N, int level, int cur, ListPtrs<NDIM> L)
   __shared__ typename BS::TempStorage tmp;
   int pre;
   BS(tmp).ExclusiveSum(c, pre);
-  /* right-going entries of THIS list before the tile: scanned tile counts minus the list's base */
-  int G = L.tilecnt[d*L.ntile + blockIdx.x] - L.tilecnt[d*L.ntile] + pre;
+  /* right-going entries of THIS list before the tile: scanned tile counts minus the list's base;
+     the counts only cover this shard, whose first node klo starts with noderb[klo] entries before it */
+  int G = L.tilecnt[d*L.ntile + blockIdx.x] - L.tilecnt[d*L.ntile] + pre + L.noderb[klo];
 #pragma unroll
   for (int i = 0; i < TB_ITEMS; i++) {
     const int p = p0 + i;
-    if (p < N) {
+    if (p >= plo && p < phi) {
       const int rb = G - L.noderb[kk[i]];              /* right-going entries before p inside the node */
       const int dest = f[i] ? md[i] + rb : p - rb;
       L.ids[d][cur ^ 1][dest] = idv[i];
@@ -784,13 +614,34 @@ partition_v2_kernel(int N, int level, int cur, ListPtrs<NDIM> L)
   }
 }
 
+/* phase 0: whole build on this GPU.  phase 1 / 2: multi-GPU build -- every rank sorts and splits the
+ * top log2(world) levels (they need all particles), then re-orders only the lists of ITS subtree
+ * (1/world of the per-level work); phase 1 ends with this rank's slice of the tree order in
+ * h->perm[lo, hi).  The host layer all-gathers the slices (NCCL) and phase 2 permutes the particle
+ * fields and stocks the tree.  The shard of rank r is the r-th node of level log2(world): the
+ * reference's median-split KD domains (MpiKDTreeDecomposition.cpp:56-277).                         */
 template <int NDIM>
-int build_tree_v2(gsph_handle* h)
+int build_tree_v2(gsph_handle* h, int phase, int shard_rank, int shard_world)
 {
   const int N = (int) h->N;
+  if (phase == 2) {
+    cudaStream_t s2 = h->stream;
+    cudaEventRecord(h->evk[4][0], s2);
+    cudaStreamWaitEvent(s2, h->ev_all, 0);      /* every uploaded field has landed */
+    gather_kernel<<<(N + 255)/256, 256, 0, s2>>>(N, h->perm, view_of(h->H, h->HI), view_of(h->P, h->PI));
+    h->stats.kernel_launches++;
+    h->sorted_valid = true;
+    h->have_tree = true;
+    cudaEventRecord(h->evk[4][1], s2); h->evk_used[4] = true;
+    cudaEventRecord(h->evk[5][0], s2);
+    const int rc2 = stock_tree<NDIM>(h, 1);
+    cudaEventRecord(h->evk[5][1], s2); h->evk_used[5] = true;
+    return rc2;
+  }
   constexpr int nd = NDIM;
   constexpr int NR = NDIM - 1;
   cudaStream_t s = h->stream;
+  cudaStreamWaitEvent(s, h->ev_geom, 0);         /* r, h and the integer fields of the last upload have landed */
   const PartView Hh = view_of(h->H, h->HI);
   const PartView Pp = view_of(h->P, h->PI);
 
@@ -868,23 +719,42 @@ int build_tree_v2(gsph_handle* h)
     CUDA_TRY(h, cudaMemcpyAsync(T.first, &one[0], sizeof(int), cudaMemcpyHostToDevice, s));
     CUDA_TRY(h, cudaMemcpyAsync(T.count, &one[1], sizeof(int), cudaMemcpyHostToDevice, s));
   }
+  /* the shard of this rank below level ltop: node `shard_rank` of that level */
+  int ltop = 0;
+  while ((1 << ltop) < shard_world) ltop++;
+  int slo = 0, shi = N;
+  for (int b = ltop - 1; b >= 0; b--) {                /* node sizes N -> (N/2, N - N/2), KDTree.cpp:545-560 */
+    const int cnt = shi - slo, left = cnt/2;
+    if ((shard_rank >> b) & 1) slo += left; else shi = slo + left;
+  }
   int cur = 0;
   for (int l = 0; l < ltot; l++) {
     const int nn = 1 << l;
-    split_nodes_v2_kernel<NDIM><<<(nn + 127)/128, 128, 0, s>>>(l, cur, L);
+    const bool mine_only = phase == 1 && l >= ltop;
+    const int klo = mine_only ? shard_rank << (l - ltop) : 0;
+    const int khi = mine_only ? (shard_rank + 1) << (l - ltop) : nn;
+    const int plo = mine_only ? slo : 0, phi = mine_only ? shi : N;
+    split_nodes_v2_kernel<NDIM><<<(nn + 127)/128, 128, 0, s>>>(l, cur, klo, khi, L);
     h->stats.kernel_launches++;
     if (nd == 1) continue;                             /* one sorted list: nothing to re-order */
     size_t tb = cub_bytes;
     cub::DeviceScan::ExclusiveSum(cubtmp, tb, L.noderb, L.noderb, nn, s);
     const dim3 grid(ntile, nd);
-    count_right_kernel<NDIM><<<grid, TB_THREADS, 0, s>>>(N, l, cur, L);
+    count_right_kernel<NDIM><<<grid, TB_THREADS, 0, s>>>(N, l, cur, plo, phi, L);
     tb = cub_bytes;
     cub::DeviceScan::ExclusiveSum(cubtmp, tb, L.tilecnt, L.tilecnt, nd*ntile, s);
-    partition_v2_kernel<NDIM><<<grid, TB_THREADS, 0, s>>>(N, l, cur, L);
+    partition_v2_kernel<NDIM><<<grid, TB_THREADS, 0, s>>>(N, l, cur, plo, phi, klo, L);
     cur ^= 1;
     h->stats.kernel_launches += 6;
   }
   CUDA_TRY(h, cudaGetLastError());
+  if (phase == 1) {
+    /* this rank's slice of the tree order; the rest arrives through the host layer's all-gather */
+    CUDA_TRY(h, cudaMemcpyAsync(h->perm + slo, L.ids[0][cur] + slo, sizeof(int)*(size_t)(shi - slo), cudaMemcpyDeviceToDevice, s));
+    cudaEventRecord(h->evk[4][1], s); h->evk_used[4] = true;
+    h->have_tree = false; h->sorted_valid = false;
+    return GSPH_OK;
+  }
   CUDA_TRY(h, cudaMemcpyAsync(h->perm, L.ids[0][cur], sizeof(int)*(size_t) N, cudaMemcpyDeviceToDevice, s));
   cudaStreamWaitEvent(s, h->ev_all, 0);      /* every uploaded field has landed */
   gather_kernel<<<(N + 255)/256, 256, 0, s>>>(N, h->perm, Hh, Pp);
@@ -912,6 +782,18 @@ int gsph_pack_geo4(gsph_handle* h)
   h->stats.kernel_launches++;
   CUDA_TRY(h, cudaGetLastError());
   return GSPH_OK;
+}
+
+int gsph_tree_build_sharded(gsph_handle* h, int phase, int rank, int world)
+{
+  int rc;
+  switch (h->dp.ndim) {
+  case 1: rc = build_tree_v2<1>(h, phase, rank, world); break;
+  case 2: rc = build_tree_v2<2>(h, phase, rank, world); break;
+  default: rc = build_tree_v2<3>(h, phase, rank, world); break;
+  }
+  if (rc || phase == 1) return rc;
+  return gsph_pack_geo4(h);
 }
 
 int gsph_tree_build(gsph_handle* h, int mode, double dt)

@@ -33,9 +33,22 @@ def exchange_plan(N, world_size):
 class _CudaArray(object):
     """__cuda_array_interface__ holder so torch can wrap a libgsph device array without a copy."""
 
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False),
+    def __init__(self, ptr, n, typestr="<f8"):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False),
                                          "version": 2, "strides": None}
+
+
+def shard_ranges(N, world_size):
+    """[(lo, hi)] of the nodes of level log2(world_size) of the balanced KD-tree (sizes N -> N//2,
+    N - N//2, src/Tree/KDTree.cpp:545-560): the reference's median-split KD domains."""
+    out = [(0, int(N))]
+    while len(out) < world_size:
+        nxt = []
+        for lo, hi in out:
+            left = (hi - lo) // 2
+            nxt += [(lo, lo + left), (lo + left, hi)]
+        out = nxt
+    return out
 
 
 class DomainDriver(object):
@@ -44,11 +57,42 @@ class DomainDriver(object):
 
     def __init__(self, tree, rank=0, world_size=1, group=None):
         self.tree, self.rank, self.world, self.group = tree, rank, world_size, group
+        self.shard_build = True      # split the tree build's re-ordering passes across the ranks
         self.N = 0
         self._fields = None
 
+    def _sharded_rebuild(self, parts):
+        """Full rebuild with the per-level re-ordering work split across the ranks: every rank builds
+        the top log2(R) levels and its own subtree, then the slices of the tree order are
+        all-gathered (4 bytes per particle) and every rank finishes the (identical) tree."""
+        import torch
+        import torch.distributed as dist
+        if parts is not None:
+            self.tree.Upload(parts)
+        self.tree.BuildTreeShardBegin(self.rank, self.world)
+        N = self.tree.Stats().Nhydro
+        ranges = shard_ranges(N, self.world)
+        maxc = max(hi - lo for lo, hi in ranges)
+        ptr, cap = self.tree.DeviceField("perm")
+        perm = torch.as_tensor(_CudaArray(ptr, N, "<i4"), device="cuda")
+        lo, hi = ranges[self.rank]
+        send = torch.zeros(maxc, dtype=torch.int32, device=perm.device)
+        send[:hi - lo] = perm[lo:hi]
+        recv = torch.empty(maxc * self.world, dtype=torch.int32, device=perm.device)
+        dist.all_gather_into_tensor(recv, send, group=self.group)
+        for r, (a, b) in enumerate(ranges):
+            if r != self.rank:
+                perm[a:b] = recv[r * maxc:r * maxc + (b - a)]
+        torch.cuda.current_stream().synchronize()
+        self.tree.BuildTreeShardFinish()
+
     def BuildTree(self, rebuild, n, ntreebuildstep, ntreestockstep, timestep, parts=None):
-        self.tree.BuildTree(rebuild, n, ntreebuildstep, ntreestockstep, timestep, parts)
+        full = rebuild or n % ntreebuildstep == 0
+        pow2 = self.world > 1 and (self.world & (self.world - 1)) == 0
+        if full and pow2 and self.shard_build:
+            self._sharded_rebuild(parts)
+        else:
+            self.tree.BuildTree(rebuild, n, ntreebuildstep, ntreestockstep, timestep, parts)
         self.N = self.tree.Stats().Nhydro
         if self.world > 1:
             lo, hi, chunk = slice_bounds(self.N, self.world, self.rank)

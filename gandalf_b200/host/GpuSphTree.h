@@ -27,6 +27,7 @@
 
 #include <string>
 #include <cstring>
+#include <vector>
 #include "gsph.h"
 #include "Exception.h"
 #include "Parameters.h"
@@ -35,6 +36,7 @@
 #include "Particle.h"
 #include "SphNeighbourSearch.h"
 #include "CodeTiming.h"
+#include "Nbody.h"
 
 template <int ndim>
 class GpuSphTree : public GradhSphTree<ndim, GradhSphParticle>
@@ -155,6 +157,22 @@ class GpuSphTree : public GradhSphTree<ndim, GradhSphParticle>
     staged = true;
   }
 
+  /// nbody->nbodydata -> {r[ndim], m, h} rows for gsph_set_stars (the fields
+  /// GradhSph::ComputeStarGravForces reads, GradhSph.cpp:722-731)
+  void set_stars(Sph<ndim>* sph, Nbody<ndim>* nbody)
+  {
+    const int Nstar = nbody ? nbody->Nnbody : 0;
+    if (Nstar > 0 && sph->fixed_sink_mass)
+      ExceptionHandler::getIstance().raise("GpuSphTree: fixed_sink_mass is not on the accelerated path");
+    std::vector<double> rows((size_t) Nstar*(ndim + 2));
+    for (int j = 0; j < Nstar; j++) {
+      for (int k = 0; k < ndim; k++) rows[(size_t) j*(ndim + 2) + k] = nbody->nbodydata[j]->r[k];
+      rows[(size_t) j*(ndim + 2) + ndim] = nbody->nbodydata[j]->m;
+      rows[(size_t) j*(ndim + 2) + ndim + 1] = nbody->nbodydata[j]->h;
+    }
+    check(gsph_set_stars(handle, Nstar > 0 ? rows.data() : NULL, Nstar));
+  }
+
   virtual void UpdateAllSphProperties(Sph<ndim>* sph, Nbody<ndim>* nbody)
   {
     CodeTiming::BlockTimer timer = this->timing->StartNewTimer("SPH_PROPERTIES");
@@ -170,10 +188,11 @@ class GpuSphTree : public GradhSphTree<ndim, GradhSphParticle>
     CodeTiming::BlockTimer timer = this->timing->StartNewTimer("SPH_HYDRO_FORCES");
     upload(sph);                          // picks up Sph::ZeroAccelerations and the active flags
     check(gsph_build_tree(handle, 1, 0.0));
+    set_stars(sph, nbody);                // ComputeStarGravForces, GradhSphTree.cpp:385-392
     check(gsph_update_hydro_forces(handle));
     download(sph, GSPH_F_FORCES);
     staged = false;
-    (void) nbody; (void) simbox;
+    (void) simbox;
   }
 
   virtual void UpdateAllSphForces(Sph<ndim>* sph, Nbody<ndim>* nbody, DomainBox<ndim>& simbox,
@@ -182,10 +201,11 @@ class GpuSphTree : public GradhSphTree<ndim, GradhSphParticle>
     CodeTiming::BlockTimer timer = this->timing->StartNewTimer("SPH_ALL_FORCES");
     upload(sph);
     check(gsph_build_tree(handle, 1, 0.0));
+    set_stars(sph, nbody);                // ComputeStarGravForces, GradhSphTree.cpp:600-607
     check(gsph_update_all_forces(handle, NULL, 0));
     download(sph, GSPH_F_FORCES);
     staged = false;
-    (void) nbody; (void) simbox; (void) ewald;
+    (void) simbox; (void) ewald;
   }
 
   virtual double GetMaximumSmoothingLength() const

@@ -202,8 +202,20 @@ class GpuSphTree(object):
     def RefreshHmax(self):
         self._check(self._L.gsph_refresh_hmax(self._h))
 
+    def TreeShardRange(self, rank, world):
+        """tree positions [lo, hi) of the rank-th node of level log2(world) (gsph_tree_shard_range)"""
+        lo, hi = C.c_int64(), C.c_int64()
+        self._check(self._L.gsph_tree_shard_range(self._h, rank, world, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def BuildTreeShardBegin(self, rank, world):
+        self._check(self._L.gsph_build_tree_shard_begin(self._h, rank, world))
+
+    def BuildTreeShardFinish(self):
+        self._check(self._L.gsph_build_tree_shard_finish(self._h))
+
     def DeviceField(self, name):
-        """-> (device pointer, capacity in elements) of a tree-order float64 array."""
+        """-> (device pointer, capacity in elements) of a tree-order array (float64; "perm": int32)."""
         ptr, cap = C.c_void_p(), C.c_int64()
         self._check(self._L.gsph_device_field(self._h, _capi.DEVICE_FIELDS.index(name), C.byref(ptr), C.byref(cap)))
         return ptr.value, cap.value

@@ -217,7 +217,22 @@ int gsph_timer_stop(gsph_handle* h, float* ms);
  *   gsph_device_field     : device pointer of one tree-order SoA array (field = GSPH_DF_*),
  *                           valid until the next gsph_upload that grows the arrays.              */
 enum { GSPH_DF_H = 0, GSPH_DF_RHO, GSPH_DF_HRANGESQD, GSPH_DF_HFACTOR, GSPH_DF_INVOMEGA, GSPH_DF_ZETA,
-       GSPH_DF_SOUND, GSPH_DF_PRESSURE, GSPH_DF_U, GSPH_DF_COUNT };
+       GSPH_DF_SOUND, GSPH_DF_PRESSURE, GSPH_DF_U,
+       GSPH_DF_PERM,   /* int32 tree position -> host index (the tree order itself) */
+       GSPH_DF_COUNT };
+/* Sharded tree build.  The balanced KD-tree's top log2(world) levels ARE the reference's domain
+ * decomposition (median splits, MpiKDTreeDecomposition.cpp:56-277): rank r owns the r-th node of that
+ * level = tree positions [lo, hi) of gsph_tree_shard_range.
+ *   gsph_build_tree_shard_begin  : sorts, splits the top levels (they need every particle) and then
+ *                                  re-orders only this rank's subtree -- 1/world of the per-level
+ *                                  work; leaves this rank's slice of GSPH_DF_PERM filled;
+ *   (host layer)                 : all-gathers the GSPH_DF_PERM slices over NCCL;
+ *   gsph_build_tree_shard_finish : permutes the particle fields into tree order and stocks the cells
+ *                                  (KDTree::StockTree) -- the tree is then identical on every rank
+ *                                  and identical to the one gsph_build_tree(mode 0) builds.         */
+int gsph_tree_shard_range(gsph_handle* h, int rank, int world, int64_t* lo, int64_t* hi);
+int gsph_build_tree_shard_begin(gsph_handle* h, int rank, int world);
+int gsph_build_tree_shard_finish(gsph_handle* h);
 int gsph_set_active_slice(gsph_handle* h, int64_t lo, int64_t hi);
 int gsph_density_pass(gsph_handle* h);
 int gsph_refresh_hmax(gsph_handle* h);

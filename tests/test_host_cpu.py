@@ -115,6 +115,21 @@ def test_slice_bounds_cover_everything():
                 assert b == c and a <= b
 
 
+def test_shard_ranges_are_the_kd_tree_top_levels():
+    """the multi-GPU tree build shards by the nodes of level log2(R): sizes N -> (N//2, N - N//2)"""
+    from gandalf_b200 import domain
+    for N in (8, 1001, 64 * 2 ** 20, 16003008):
+        for R in (1, 2, 4, 8):
+            rg = domain.shard_ranges(N, R)
+            assert len(rg) == R and rg[0][0] == 0 and rg[-1][1] == N
+            for (a, b), (c, d) in zip(rg[:-1], rg[1:]):
+                assert b == c
+            sizes = [b - a for a, b in rg]
+            assert max(sizes) - min(sizes) <= 1 or R == 1
+    assert domain.shard_ranges(1001, 2) == [(0, 500), (500, 1001)]
+    assert domain.shard_ranges(1001, 4) == [(0, 250), (250, 500), (500, 750), (750, 1001)]
+
+
 _WORKER = r"""
 import os, sys
 import numpy as np, torch, torch.distributed as dist
