@@ -364,7 +364,7 @@ void gsph_destroy(gsph_handle* h)
   if (h->ev_geom) cudaEventDestroy(h->ev_geom);
   if (h->ev_all) cudaEventDestroy(h->ev_all);
   if (h->ev_compute) cudaEventDestroy(h->ev_compute);
-  fre(h->tree.nodeb); fre(h->tree.nodeh);
+  fre(h->tree.nodeb); fre(h->tree.nodeh); fre(h->tree.gnode); fre(h->tree.mnode);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;

@@ -19,8 +19,10 @@
 
 #define DENS_THREADS 256
 #define DENS_WARPS (DENS_THREADS/32)
-#define DENS_REC_STRIDE 3                         /* double2 units per staged (x,y,z,m) record: 48 B, conflict-free */
-#define DENS_WARP_D2 (2*32*DENS_REC_STRIDE)       /* double2 per warp: two record stages (3 KiB >= walk stack) */
+/* staged (x,y,z,m) records: two 16-byte chunks per record, chunk c of record s at unit 2s + (c ^ ((s>>2)&1)):
+   the cooperative cp.async writes (two lanes per record) and the per-lane reads are both conflict-free */
+#define DENS_UNIT(s, c) (2*(s) + ((c) ^ (((s) >> 2) & 1)))
+#define DENS_WARP_D2 (2*32*2)                     /* double2 per warp: two record stages (2 KiB = walk stack) */
 
 namespace {
 
@@ -235,7 +237,7 @@ density_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict_
           for (int r = 0; r < 2; r++) {
             const int src = r*16 + (lane >> 1);
             const int jj = __shfl_sync(FULLMASK, jv, src);
-            if (jj >= 0) cp_async16(buf + src*DENS_REC_STRIDE + (lane & 1), geo4 + 2*(size_t) jj + (lane & 1));
+            if (jj >= 0) cp_async16(buf + DENS_UNIT(src, lane & 1), geo4 + 2*(size_t) jj + (lane & 1));
           }
           cp_async_commit();
         };
@@ -252,14 +254,14 @@ density_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict_
           int jn = (1 < kend) ? nlist[32 + lane] : -1;
           gather(jc, stage);
           for (int k = 0; k < nmax; k++) {
-            const double2* buf = stage + (k & 1)*32*DENS_REC_STRIDE;
+            const double2* buf = stage + (k & 1)*64;
             const bool more = k + 1 < nmax;
-            if (more) gather(jn, stage + ((k + 1) & 1)*32*DENS_REC_STRIDE);
+            if (more) gather(jn, stage + ((k + 1) & 1)*64);
             const int jnn = (k + 2 < kend) ? nlist[(size_t)(k + 2)*32 + lane] : -1;
             if (more) cp_async_wait<1>(); else cp_async_wait<0>();
             __syncwarp();
             if (jc >= 0) {
-              const double2 a = buf[lane*DENS_REC_STRIDE], b = buf[lane*DENS_REC_STRIDE + 1];
+              const double2 a = buf[DENS_UNIT(lane, 0)], b = buf[DENS_UNIT(lane, 1)];
               double dr[3] = {0, 0, 0};
               dr[0] = a.x - x[0];
               if (NDIM > 1) dr[1] = a.y - x[1];

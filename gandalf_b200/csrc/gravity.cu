@@ -42,10 +42,21 @@
 #define DIR_BUF (DIR_TILE_MAX + 32)
 #define GRAV_LEAVES 8                  /* leaves per cohort: 4 lanes each */
 #ifndef GRAV_MINBLOCKS
-#define GRAV_MINBLOCKS 3               /* resident blocks per SM the register allocation is tuned for */
+#define GRAV_MINBLOCKS 2               /* resident blocks per SM the register allocation is tuned for */
 #endif
 
 namespace {
+
+/* 1/sqrt(x) for finite normal x > 0: hardware seed (MUFU.RSQ64H, ~2^-22) + one cubic Newton step,
+ * branch-free so that several independent evaluations can be in flight per thread (the library
+ * rsqrt() carries a special-case branch that blocks that interleaving).  Error <= 2 ulp.         */
+__device__ __forceinline__ double rsqrt_nr(double x)
+{
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-x*y, y, 1.0);
+  return fma(y*e, fma(0.375, e, 0.5), y);
+}
 
 template <bool QUAD>
 struct WarpSharedT {
@@ -54,9 +65,9 @@ struct WarpSharedT {
   int cell_node[CELL_BUF]; unsigned cell_mask[CELL_BUF];
   int dir_node[DIR_BUF]; unsigned dir_mask[DIR_BUF];
   double cell_data[CELL_TILE][QUAD ? 9 : 4];   /* com xyz, m [, q0..q4] */
-  double dir_data[DIR_PART][5];        /* x, y, z, m, hrangesqd of the staged source particles */
-  int dir_src[DIR_PART];               /* tree-order index of every staged source particle */
-  int dir_off[DIR_TILE_MAX], dir_count[DIR_TILE_MAX];
+  double dir_data[DIR_PART][5];        /* x, y, z, m, hrangesqd of the staged sources: 4*T slots per direct
+                                          leaf, unused slots hold m = 0 (they contribute exactly nothing) */
+  int dir_count[DIR_TILE_MAX];
 };
 
 struct FastMp { double ac[3], q[6], pot; };   /* dphi == ac for HoT = false */
@@ -134,8 +145,9 @@ gravity_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* wo
       __syncwarp();
       if (lane < n) {
         const int cc = S.cell_node[lane];
-        S.cell_data[lane][0] = tree.com[0][cc]; S.cell_data[lane][1] = tree.com[1][cc];
-        S.cell_data[lane][2] = tree.com[2][cc]; S.cell_data[lane][3] = tree.m[cc];
+        const double2 m0 = tree.mnode[2*(size_t) cc], m1 = tree.mnode[2*(size_t) cc + 1];
+        S.cell_data[lane][0] = m0.x; S.cell_data[lane][1] = m0.y;
+        S.cell_data[lane][2] = m1.x; S.cell_data[lane][3] = m1.y;
         if (QUAD) {
 #pragma unroll
           for (int k = 0; k < 5; k++) S.cell_data[lane][4 + k] = tree.q[k][cc];
@@ -155,6 +167,31 @@ gravity_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* wo
         }
       }
       if (FAST) { for (int q = 0; q < sub; q++) ebits &= ebits - 1u; }
+      if (FAST && !QUAD) {
+        /* fast monopole: two independent entries per iteration (instruction-level parallelism hides
+           the latency of the dependent rsqrt chains); a missing second entry gets mass 0 */
+        while (ebits) {
+          const int e0 = __ffs(ebits) - 1;
+          ebits &= ebits - 1u; ebits &= ebits - 1u; ebits &= ebits - 1u; ebits &= ebits - 1u;
+          const bool two = ebits != 0u;
+          const int e1 = two ? __ffs(ebits) - 1 : e0;
+          if (two) { ebits &= ebits - 1u; ebits &= ebits - 1u; ebits &= ebits - 1u; ebits &= ebits - 1u; }
+          ncell_mine += two ? 2 : 1;
+          const double ax0 = S.cell_data[e0][0] - rcom[0], ay0 = S.cell_data[e0][1] - rcom[1], az0 = S.cell_data[e0][2] - rcom[2];
+          const double bx0 = S.cell_data[e1][0] - rcom[0], by0 = S.cell_data[e1][1] - rcom[1], bz0 = S.cell_data[e1][2] - rcom[2];
+          const double ma = S.cell_data[e0][3], mb = two ? S.cell_data[e1][3] : 0.0;
+          const double ia = rsqrt_nr(ax0*ax0 + ay0*ay0 + az0*az0), ib = rsqrt_nr(bx0*bx0 + by0*by0 + bz0*bz0);
+          const double ia2 = ia*ia, ib2 = ib*ib;
+          const double ca = ma*ia2*ia, cb = mb*ib2*ib;
+          F.pot += ma*ia; F.pot += mb*ib;
+          F.ac[0] += ca*ax0; F.ac[1] += ca*ay0; F.ac[2] += ca*az0;
+          F.ac[0] += cb*bx0; F.ac[1] += cb*by0; F.ac[2] += cb*bz0;
+          F.q[0] += ca*(3.0*ax0*ax0*ia2 - 1.0); F.q[1] += ca*(3.0*ax0*ay0*ia2); F.q[2] += ca*(3.0*ay0*ay0*ia2 - 1.0);
+          F.q[3] += ca*(3.0*az0*ax0*ia2);       F.q[4] += ca*(3.0*az0*ay0*ia2); F.q[5] += ca*(3.0*az0*az0*ia2 - 1.0);
+          F.q[0] += cb*(3.0*bx0*bx0*ib2 - 1.0); F.q[1] += cb*(3.0*bx0*by0*ib2); F.q[2] += cb*(3.0*by0*by0*ib2 - 1.0);
+          F.q[3] += cb*(3.0*bz0*bx0*ib2);       F.q[4] += cb*(3.0*bz0*by0*ib2); F.q[5] += cb*(3.0*bz0*bz0*ib2 - 1.0);
+        }
+      }
       while (ebits) {
         const int e = __ffs(ebits) - 1;
         ebits &= ebits - 1u;
@@ -167,7 +204,7 @@ gravity_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* wo
           /* Taylor coefficients about the leaf's centre of mass (NeighbourSearch.h:481-760) */
           {
             const double dx = cx - rcom[0], dy = cy - rcom[1], dz = cz - rcom[2];
-            const double inv = rsqrt(dx*dx + dy*dy + dz*dz);
+            const double inv = rsqrt_nr(dx*dx + dy*dy + dz*dz);
             const double inv2 = inv*inv;
             const double mc = cm*inv2*inv;
             F.pot += cm*inv;
@@ -181,7 +218,7 @@ gravity_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* wo
           }
           if (QUAD) {
             const double dx = rcom[0] - cx, dy = rcom[1] - cy, dz = rcom[2] - cz;
-            const double inv = rsqrt(dx*dx + dy*dy + dz*dz + GSPH_SMALL);
+            const double inv = rsqrt_nr(dx*dx + dy*dy + dz*dz + GSPH_SMALL);
             const double inv2 = inv*inv;
             const double inv5 = inv2*inv2*inv;
             const double qs = q0*dx*dx + q2*dy*dy - (q0 + q2)*dz*dz + 2.0*(q1*dx*dy + q3*dx*dz + q4*dy*dz);
@@ -205,7 +242,7 @@ gravity_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* wo
           for (int t = 0; t < T; t++) {
             if (!tlive[t]) continue;
             const double dx = x[t][0] - cx, dy = x[t][1] - cy, dz = x[t][2] - cz;
-            const double inv = rsqrt(dx*dx + dy*dy + dz*dz + GSPH_SMALL);
+            const double inv = rsqrt_nr(dx*dx + dy*dy + dz*dz + GSPH_SMALL);
             const double inv2 = inv*inv;
             const double f = cm*inv2*inv;
             if (!QUAD) {                                       /* NeighbourSearch.h:349-377 */
@@ -228,14 +265,9 @@ gravity_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* wo
     };
 
     auto consume_direct = [&](int n0, int n) {
-      /* stage the particles of direct leaves [n0, n0+n), n <= DIR_TILE, compactly */
+      /* stage the particles of direct leaves [n0, n0+n), n <= DIR_TILE: 4*T slots per leaf */
+      constexpr int SLOTS = 4*T;
       __syncwarp();
-      int lf = 0, lc = 0;
-      if (lane < n) { const int ln = S.dir_node[n0 + lane]; lf = tree.first[ln]; lc = tree.count[ln]; }
-      int tot;
-      const int off = warp_excl_scan(lc, lane, tot);
-      if (lane < n) { S.dir_off[lane] = off; S.dir_count[lane] = lc; }
-      for (int k = 0; k < lc; k++) S.dir_src[off + k] = lf + k;
       unsigned ebits = 0;
       {
         const unsigned mm = lane < n ? S.dir_mask[n0 + lane] : 0u;
@@ -245,33 +277,41 @@ gravity_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* wo
           if (l == myl) ebits = bl;
         }
       }
-      __syncwarp();
-      for (int s = lane; s < tot; s += 32) {
-        const int j = S.dir_src[s];
-        const bool dead = ((unsigned) P.i[I_FLAGS][j]) & GSPH_FLAG_DEAD;
-        S.dir_data[s][0] = P.f[F_RX][j]; S.dir_data[s][1] = P.f[F_RY][j]; S.dir_data[s][2] = P.f[F_RZ][j];
-        S.dir_data[s][3] = dead ? 0.0 : P.f[F_M][j]; S.dir_data[s][4] = dead ? -1.0 : P.f[F_HR2][j];
+      for (int s = lane; s < n*SLOTS; s += 32) {
+        const int e = s/SLOTS, k = s - e*SLOTS;
+        const int ln = S.dir_node[n0 + e];
+        const int lf = tree.first[ln], lc = tree.count[ln];
+        if (k == 0) S.dir_count[e] = lc;
+        double sx = 0.0, sy = 0.0, sz = 0.0, sm = 0.0, sh = -1.0;
+        if (k < lc) {
+          const int j = lf + k;
+          const bool dead = ((unsigned) P.i[I_FLAGS][j]) & GSPH_FLAG_DEAD;
+          sx = P.f[F_RX][j]; sy = P.f[F_RY][j]; sz = P.f[F_RZ][j];
+          sm = dead ? 0.0 : P.f[F_M][j]; sh = dead ? -1.0 : P.f[F_HR2][j];
+        }
+        S.dir_data[s][0] = sx; S.dir_data[s][1] = sy; S.dir_data[s][2] = sz; S.dir_data[s][3] = sm; S.dir_data[s][4] = sh;
       }
       __syncwarp();
-      /* the 4 lanes of a leaf (different target particles) visit the leaf's own entries only */
+      /* the 4 lanes of a leaf (different target particles) visit the leaf's own entries only; the
+         SLOTS sources of an entry are evaluated branch-free (a kernel-overlap pair, which belongs to
+         hydro.cu, or an empty slot simply gets mass 0) so that their rsqrt chains overlap */
       while (ebits) {
         const int e = __ffs(ebits) - 1;
         ebits &= ebits - 1u;
-        const int o = S.dir_off[e], nsrc = S.dir_count[e];
-        if (sub == 0) ndir_mine += nsrc;
-#pragma unroll 2
-        for (int k = 0; k < nsrc; k++) {
-          const double* pj = S.dir_data[o + k];
+        if (sub == 0) ndir_mine += S.dir_count[e];
+#pragma unroll
+        for (int k = 0; k < SLOTS; k++) {
+          const double* pj = S.dir_data[e*SLOTS + k];
           const double xj = pj[0], yj = pj[1], zj = pj[2], mj = pj[3], hr2j = pj[4];
 #pragma unroll
           for (int t = 0; t < T; t++) {
             double dr[3] = {xj - x[t][0], yj - x[t][1], zj - x[t][2]};
             const double d2 = dot_exact<3>(dr);
-            if (!tlive[t] || d2 < hr2[t] || d2 < hr2j) continue;   /* kernel-overlap pair: hydro.cu */
-            const double inv = rsqrt(d2 + GSPH_SMALL);              /* ComputeDirectGravForces */
-            const double f = mj*inv*inv*inv;
+            const double mm = (!tlive[t] || d2 < hr2[t] || d2 < hr2j) ? 0.0 : mj;
+            const double inv = rsqrt_nr(d2 + GSPH_SMALL);           /* ComputeDirectGravForces */
+            const double f = mm*inv*inv*inv;
             ax[t] += f*dr[0]; ay[t] += f*dr[1]; az[t] += f*dr[2];
-            pot[t] += mj*inv;
+            pot[t] += mm*inv;
           }
         }
       }
@@ -295,17 +335,17 @@ gravity_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* wo
       unsigned open_mask = 0, acc_mask = 0;
       bool isleaf = false; int ncount = 0;
       if (node >= 0) {
-        ncount = tree.count[node];
+        const double2 g0 = tree.gnode[4*(size_t) node], g1 = tree.gnode[4*(size_t) node + 1];
+        const double2 g2 = tree.gnode[4*(size_t) node + 2], g3 = tree.gnode[4*(size_t) node + 3];
+        ncount = (int) g3.x;
         isleaf = node >= leaf0;
         if (ncount > 0) {
-          const double rx = tree.rcell[0][node], ry = tree.rcell[1][node], rz = tree.rcell[2][node];
-          const double crmax = tree.rmax[node], cdist = tree.cdistsqd[node];
-          const double chr = __dmul_rn(dp.kernrange, tree.hmax[node]);
-          /* only the leaves still undecided for this node (set bits of the mask) are evaluated */
-          unsigned todo = mask;
-          while (todo) {
-            const int l = __ffs(todo) - 1;
-            todo &= todo - 1u;
+          const double rx = g0.x, ry = g0.y, rz = g1.x;
+          const double crmax = g1.y, cdist = g2.x;
+          const double chr = g2.y;                         /* kernrange*hmax of the node */
+          /* only the leaves still undecided for this node (set bits of the mask) are evaluated, two
+             per iteration so that their dependent arithmetic chains overlap */
+          auto opens = [&](int l) -> bool {
             const double* lg = S.leafgeom[l];
             double dr[3];
             dr[0] = __dadd_rn(rx, -lg[0]); dr[1] = __dadd_rn(ry, -lg[1]); dr[2] = __dadd_rn(rz, -lg[2]);
@@ -314,8 +354,18 @@ gravity_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* wo
             const double a = __dadd_rn(__dadd_rn(crmax, rmax), lg[4]);
             const double b = __dadd_rn(__dadd_rn(rmax, crmax), chr);
             /* Tree.cpp:660-731: overlap -> open; else MAC (Tree.h:413-432 geometric: open iff drsqd < cdistsqd) */
-            if (drsqd <= __dmul_rn(a, a) || drsqd <= __dmul_rn(b, b) || drsqd < cdist) open_mask |= 1u << l;
-            else acc_mask |= 1u << l;
+            return drsqd <= __dmul_rn(a, a) || drsqd <= __dmul_rn(b, b) || drsqd < cdist;
+          };
+          unsigned todo = mask;
+          while (todo) {
+            const int l0 = __ffs(todo) - 1;
+            todo &= todo - 1u;
+            const bool two = todo != 0u;
+            const int l1 = two ? __ffs(todo) - 1 : l0;
+            todo &= todo - 1u;
+            const bool o0 = opens(l0), o1 = opens(l1);
+            if (o0) open_mask |= 1u << l0; else acc_mask |= 1u << l0;
+            if (two) { if (o1) open_mask |= 1u << l1; else acc_mask |= 1u << l1; }
           }
         }
       }

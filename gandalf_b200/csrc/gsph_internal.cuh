@@ -61,6 +61,12 @@ struct TreeDev {
        nodeh[2n]   = (hbmin.xyz, 0)                   nodeh[2n+1] = (hbmax.xyz, 0)                 */
   float4* nodeb = nullptr;
   float4* nodeh = nullptr;
+  /* exact double-precision node records of the gravity walk (one 64-byte line / one 32-byte sector
+     per node instead of seven / four separate arrays):
+       gnode[4n..4n+3] = (rcell.x, rcell.y) (rcell.z, rmax) (cdistsqd, kernrange*hmax) (count, 0)
+       mnode[2n..2n+1] = (com.x, com.y) (com.z, m)                                               */
+  double2* gnode = nullptr;
+  double2* mnode = nullptr;
 };
 
 struct DevParams {

@@ -277,11 +277,22 @@ __global__ void extrapolate_kernel(TreeDev T, double dt)
 
 /* outward-rounded single-precision node records for the neighbour walks (TreeDev::nodeb / nodeh) */
 template <int NDIM>
-__global__ void pack_nodes_kernel(TreeDev T, int with_bb)
+__global__ void pack_nodes_kernel(TreeDev T, int with_bb, double kernrange)
 {
   const int n = blockIdx.x*blockDim.x + threadIdx.x;
   if (n >= T.ncell) return;
   const int cnt = T.count[n];
+  if (T.gnode) {                                   /* gravity walk records (exact doubles) */
+    if (with_bb) {
+      T.gnode[4*(size_t) n] = make_double2(T.rcell[0][n], NDIM > 1 ? T.rcell[1][n] : 0.0);
+      T.gnode[4*(size_t) n + 1] = make_double2(NDIM > 2 ? T.rcell[2][n] : 0.0, T.rmax[n]);
+      T.gnode[4*(size_t) n + 3] = make_double2((double) cnt, 0.0);
+      T.mnode[2*(size_t) n] = make_double2(T.com[0][n], NDIM > 1 ? T.com[1][n] : 0.0);
+      T.mnode[2*(size_t) n + 1] = make_double2(NDIM > 2 ? T.com[2][n] : 0.0, T.m[n]);
+    }
+    /* cdistsqd keeps the value of the last stock, hmax follows the density pass (KDTree.cpp:1163-1205) */
+    T.gnode[4*(size_t) n + 2] = make_double2(T.cdistsqd[n], __dmul_rn(kernrange, T.hmax[n]));
+  }
   float lo[3] = {0.f, 0.f, 0.f}, hi[3] = {0.f, 0.f, 0.f};
   if (with_bb) {
 #pragma unroll
@@ -310,6 +321,7 @@ int alloc_tree(gsph_handle* h, int ltot)
   auto fre = [](void* p) { if (p) cudaFree(p); };
   fre(T.first); fre(T.count); fre(T.nactive); fre(T.m); fre(T.rmax); fre(T.hmax); fre(T.cdistsqd);
   fre(T.nodeb); fre(T.nodeh); T.nodeb = T.nodeh = nullptr;
+  fre(T.gnode); fre(T.mnode); T.gnode = T.mnode = nullptr;
   for (int k = 0; k < 3; k++) {
     fre(T.bbmin[k]); fre(T.bbmax[k]); fre(T.hbmin[k]); fre(T.hbmax[k]);
     fre(T.rcell[k]); fre(T.com[k]); fre(T.vcom[k]);
@@ -326,6 +338,10 @@ int alloc_tree(gsph_handle* h, int ltot)
   CUDA_TRY(h, cudaMalloc(&T.cdistsqd, cap*sizeof(double)));
   CUDA_TRY(h, cudaMalloc(&T.nodeb, 2*cap*sizeof(float4)));
   CUDA_TRY(h, cudaMalloc(&T.nodeh, 2*cap*sizeof(float4)));
+  if (h->dp.self_gravity) {
+    CUDA_TRY(h, cudaMalloc(&T.gnode, 4*cap*sizeof(double2)));
+    CUDA_TRY(h, cudaMalloc(&T.mnode, 2*cap*sizeof(double2)));
+  }
   for (int k = 0; k < 3; k++) {
     T.bbmin[k] = T.bbmax[k] = T.hbmin[k] = T.hbmax[k] = T.rcell[k] = T.com[k] = T.vcom[k] = nullptr;
     if (k >= nd) continue;
@@ -361,7 +377,7 @@ int stock_tree(gsph_handle* h, int full)
     const int nn = 1 << l;
     stock_level_kernel<NDIM><<<(nn + 127)/128, 128, 0, h->stream>>>(T, h->dp, l, full);
   }
-  pack_nodes_kernel<NDIM><<<(T.ncell + 255)/256, 256, 0, h->stream>>>(T, full);
+  pack_nodes_kernel<NDIM><<<(T.ncell + 255)/256, 256, 0, h->stream>>>(T, full, h->dp.kernrange);
   h->stats.kernel_launches += 2 + T.ltot;
   CUDA_TRY(h, cudaGetLastError());
   return GSPH_OK;
@@ -388,7 +404,7 @@ int build_tree_nd(gsph_handle* h, int mode, double dt)
       h->sorted_valid = true; h->stats.kernel_launches++;
     }
     extrapolate_kernel<NDIM><<<(h->tree.ncell + 255)/256, 256, 0, s>>>(h->tree, dt);
-    pack_nodes_kernel<NDIM><<<(h->tree.ncell + 255)/256, 256, 0, s>>>(h->tree, 1);
+    pack_nodes_kernel<NDIM><<<(h->tree.ncell + 255)/256, 256, 0, s>>>(h->tree, 1, h->dp.kernrange);
     h->stats.kernel_launches += 2;
     CUDA_TRY(h, cudaGetLastError());
     return GSPH_OK;
