@@ -12,7 +12,7 @@ KERNEL = {"m4": 0, "quintic": 1}
 AVISC = {"none": 0, "mon97": 1, "mon97mm97": 2, "mon97cd2010": 3}
 ACOND = {"none": 0, "wadsley2008": 1, "price2008": 2}
 TDAVISC = {"none": 0, "mm97": 1}
-EOS = {"energy_eqn": 0, "constant_temp": 0, "isothermal": 1, "barotropic": 2}
+EOS = {"energy_eqn": 0, "constant_temp": 0, "isothermal": 1, "barotropic": 2, "barotropic2": 3}
 BOUNDARY = {"open": 0, "periodic": 1, "mirror": 2}
 MAC = {"geometric": 0, "eigenmac": 1, "gadget2": 2}
 MULTIPOLE = {"monopole": 0, "quadrupole": 1, "fast_monopole": 2, "fast_quadrupole": 3}

@@ -183,6 +183,7 @@ int validate_config(const gsph_config* c, std::string& err)
   if (c->kernel != GSPH_KERNEL_M4 && c->kernel != GSPH_KERNEL_QUINTIC) { err = "kernel must be m4 or quintic"; return GSPH_EINVAL; }
   if (!(c->h_fac > 0) || !(c->h_converge > 0)) { err = "h_fac and h_converge must be positive"; return GSPH_EINVAL; }
   if (c->Nleafmax < 1) { err = "Nleafmax must be >= 1"; return GSPH_EINVAL; }
+  if (c->eos < GSPH_EOS_ADIABATIC || c->eos > GSPH_EOS_BAROTROPIC2) { err = "gas_eos is not on the accelerated path"; return GSPH_EINVAL; }
   if (c->tdavisc != GSPH_TDAVISC_NONE && c->tdavisc != GSPH_TDAVISC_MM97) { err = "time_dependent_avisc = cd2010 is not on the accelerated path"; return GSPH_EINVAL; }
   for (int k = 0; k < c->ndim; k++) {
     if (c->boundary_lhs[k] == GSPH_BOUNDARY_MIRROR || c->boundary_rhs[k] == GSPH_BOUNDARY_MIRROR) {
@@ -196,7 +197,8 @@ int validate_config(const gsph_config* c, std::string& err)
     }
   }
   if (c->self_gravity) {
-    if (c->gravity_mac != GSPH_MAC_GEOMETRIC) { err = "only gravity_mac = geometric is on the accelerated path"; return GSPH_EINVAL; }
+    if (c->gravity_mac < GSPH_MAC_GEOMETRIC || c->gravity_mac > GSPH_MAC_GADGET2) { err = "unknown gravity_mac"; return GSPH_EINVAL; }
+    if (c->gravity_mac != GSPH_MAC_GEOMETRIC && !(c->macerror > 0.0)) { err = "gravity_mac = eigenmac / gadget2 needs macerror > 0"; return GSPH_EINVAL; }
     if (!(c->thetamaxsqd > 0)) { err = "thetamaxsqd must be positive"; return GSPH_EINVAL; }
     for (int k = 0; k < c->ndim; k++)
       if (c->boundary_lhs[k] == GSPH_BOUNDARY_PERIODIC) { err = "periodic (Ewald) gravity is not on the accelerated path"; return GSPH_EINVAL; }
@@ -324,6 +326,8 @@ int gsph_create(const gsph_config* cfg, gsph_handle** out)
   if ((e = cudaEventCreateWithFlags(&h->ev_geom, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
   if ((e = cudaEventCreateWithFlags(&h->ev_all, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
   if ((e = cudaEventCreateWithFlags(&h->ev_compute, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+  for (int k = 0; k < 3; k++)
+    if ((e = cudaEventCreateWithFlags(&h->ev_axis[k], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
   if ((e = cudaEventCreate(&h->ev0)) != cudaSuccess) return fail("cudaEventCreate", e);
   if ((e = cudaEventCreate(&h->ev1)) != cudaSuccess) return fail("cudaEventCreate", e);
   for (int k = 0; k < 2; k++) if ((e = cudaEventCreate(&h->evt[k])) != cudaSuccess) return fail("cudaEventCreate", e);
@@ -364,6 +368,7 @@ void gsph_destroy(gsph_handle* h)
   if (h->ev_geom) cudaEventDestroy(h->ev_geom);
   if (h->ev_all) cudaEventDestroy(h->ev_all);
   if (h->ev_compute) cudaEventDestroy(h->ev_compute);
+  for (int k = 0; k < 3; k++) if (h->ev_axis[k]) cudaEventDestroy(h->ev_axis[k]);
   fre(h->tree.nodeb); fre(h->tree.nodeh); fre(h->tree.gnode); fre(h->tree.mnode);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -377,10 +382,13 @@ const char* gsph_last_error(const gsph_handle* h) { return h ? h->err.c_str() : 
  * that all live inside one AoS record (the reference's GradhSphParticle array) are moved as ONE
  * bulk copy per chunk and de-interleaved on the device.
  *-----------------------------------------------------------------------------------------------*/
-int gsph_upload(gsph_handle* h, const gsph_particle_view* view, int64_t N)
+static int upload_impl(gsph_handle* h, const gsph_particle_view* view, int64_t N, int64_t r0, int64_t r1)
 {
   if (!h) return GSPH_EINVAL;
   if (!view || N <= 0 || N > 2000000000ll) { h->err = "gsph_upload: bad arguments"; return GSPH_EINVAL; }
+  if (r0 < 0 || r1 < r0 || r1 > N) { h->err = "gsph_upload_range: bad range"; return GSPH_EINVAL; }
+  const bool whole = (r0 == 0 && r1 == N);
+  const int64_t nr = r1 - r0;
   cudaSetDevice(h->device);
   Timer tm(h, &h->stats.ms_upload);
   int rc = ensure_capacity(h, N);
@@ -417,8 +425,10 @@ int gsph_upload(gsph_handle* h, const gsph_particle_view* view, int64_t N)
       const gsph_field& f = vfield(view, kDoubleFields[k].off);
       const bool unused_dim = (pf >= F_RX && pf <= F_ATZ) && ((pf - F_RX) % 3 >= nd);
       if (!f.base || unused_dim) fill_kernel<double><<<nb, 256, 0, h->copy_stream>>>(N, h->H[pf], default_double(pf));
-      else if (f.stride == sizeof(double))
-        CUDA_TRY(h, cudaMemcpyAsync(h->H[pf], f.base, N*sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+      else if (f.stride == sizeof(double)) {
+        if (nr > 0) CUDA_TRY(h, cudaMemcpyAsync(h->H[pf] + r0, (const double*) f.base + r0, nr*sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
+      }
+      else if (!whole) { h->err = "gsph_upload_range needs contiguous (SoA) fields"; return GSPH_EINVAL; }
       else if (bulk_ok) { plan.off_d[plan.nf] = (unsigned)((const char*) f.base - lo); plan.pf_d[plan.nf++] = pf; }
       else {
         rc = ensure_pinned(h, N*sizeof(double)); if (rc) return rc;
@@ -428,14 +438,18 @@ int gsph_upload(gsph_handle* h, const gsph_particle_view* view, int64_t N)
         for (int64_t i = 0; i < N; i++) st[i] = *(const double*)(b + (size_t) i*f.stride);
         CUDA_TRY(h, cudaMemcpyAsync(h->H[pf], st, N*sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
       }
+      if (pf >= F_RX && pf <= F_RZ && !(bulk_ok && (plan.nf || plan.ni)))
+        CUDA_TRY(h, cudaEventRecord(h->ev_axis[pf - F_RX], h->copy_stream));
     }
     if (pass == 1) break;
     for (int k = 0; k < kNIntFields; k++) {
       const int pf = kIntFields[k].pf;
       const gsph_field& f = vfield(view, kIntFields[k].off);
       if (!f.base) fill_kernel<int32_t><<<nb, 256, 0, h->copy_stream>>>(N, h->HI[pf], default_int(pf));
-      else if (f.stride == sizeof(int32_t))
-        CUDA_TRY(h, cudaMemcpyAsync(h->HI[pf], f.base, N*sizeof(int32_t), cudaMemcpyHostToDevice, h->copy_stream));
+      else if (f.stride == sizeof(int32_t)) {
+        if (nr > 0) CUDA_TRY(h, cudaMemcpyAsync(h->HI[pf] + r0, (const int32_t*) f.base + r0, nr*sizeof(int32_t), cudaMemcpyHostToDevice, h->copy_stream));
+      }
+      else if (!whole) { h->err = "gsph_upload_range needs contiguous (SoA) fields"; return GSPH_EINVAL; }
       else if (bulk_ok) { plan.off_i[plan.ni] = (unsigned)((const char*) f.base - lo); plan.pf_i[plan.ni++] = pf; }
       else {
         rc = ensure_pinned(h, N*sizeof(int32_t)); if (rc) return rc;
@@ -468,6 +482,7 @@ int gsph_upload(gsph_handle* h, const gsph_particle_view* view, int64_t N)
       CUDA_TRY(h, cudaStreamSynchronize(h->copy_stream));
     }
     CUDA_TRY(h, cudaEventRecord(h->ev_geom, h->copy_stream));
+    for (int k = 0; k < 3; k++) CUDA_TRY(h, cudaEventRecord(h->ev_axis[k], h->copy_stream));
   }
   CUDA_TRY(h, cudaEventRecord(h->ev_all, h->copy_stream));
   h->upload_pending = true;
@@ -479,7 +494,18 @@ int gsph_upload(gsph_handle* h, const gsph_particle_view* view, int64_t N)
   return GSPH_OK;
 }
 
-static int download_impl(gsph_handle* h, const gsph_particle_view* view, uint32_t field_mask, bool wait)
+int gsph_upload(gsph_handle* h, const gsph_particle_view* view, int64_t N) { return upload_impl(h, view, N, 0, N); }
+
+/* multi-process hosts: this rank ships only the host-order particles [lo, hi) of the N-particle set;
+   the other ranks' shares reach the staging arrays through the host layer's NCCL all-gather
+   (gsph_device_array(..., GSPH_ARRAY_STAGING, ...)) -- NVLink instead of R x the PCIe traffic */
+int gsph_upload_range(gsph_handle* h, const gsph_particle_view* view, int64_t N, int64_t lo, int64_t hi)
+{
+  return upload_impl(h, view, N, lo, hi);
+}
+
+static int download_impl(gsph_handle* h, const gsph_particle_view* view, uint32_t field_mask, bool wait,
+                         int64_t r0 = 0, int64_t r1 = -1)
 {
   if (!h) return GSPH_EINVAL;
   if (!view) { h->err = "gsph_download: NULL view"; return GSPH_EINVAL; }
@@ -487,6 +513,10 @@ static int download_impl(gsph_handle* h, const gsph_particle_view* view, uint32_
   cudaSetDevice(h->device);
   Timer tm(h, &h->stats.ms_download);
   const int64_t N = h->N;
+  if (r1 < 0) r1 = N;
+  if (r0 < 0 || r1 < r0 || r1 > N) { h->err = "gsph_download_range: bad range"; return GSPH_EINVAL; }
+  const bool whole = (r0 == 0 && r1 == N);
+  const int64_t nr = r1 - r0;
   unsigned long long dmask = 0; unsigned imask = 0;
   auto want_d = [&](int pf) {
     if (field_mask == GSPH_F_ALL) return true;
@@ -517,8 +547,10 @@ static int download_impl(gsph_handle* h, const gsph_particle_view* view, uint32_
     const int pf = kDoubleFields[k].pf;
     if (!((dmask >> pf) & 1ull)) continue;
     const gsph_field& f = vfield(view, kDoubleFields[k].off);
-    if (f.stride == sizeof(double))
-      CUDA_TRY(h, cudaMemcpyAsync(f.base, h->H[pf], N*sizeof(double), cudaMemcpyDeviceToHost, cs));
+    if (f.stride == sizeof(double)) {
+      if (nr > 0) CUDA_TRY(h, cudaMemcpyAsync((double*) f.base + r0, h->H[pf] + r0, nr*sizeof(double), cudaMemcpyDeviceToHost, cs));
+    }
+    else if (!whole) { h->err = "gsph_download_range needs contiguous (SoA) fields"; return GSPH_EINVAL; }
     else {
       int rc = ensure_pinned(h, N*sizeof(double)); if (rc) return rc;
       CUDA_TRY(h, cudaMemcpyAsync(h->pinned, h->H[pf], N*sizeof(double), cudaMemcpyDeviceToHost, cs));
@@ -532,8 +564,10 @@ static int download_impl(gsph_handle* h, const gsph_particle_view* view, uint32_
     const int pf = kIntFields[k].pf;
     if (!((imask >> pf) & 1u)) continue;
     const gsph_field& f = vfield(view, kIntFields[k].off);
-    if (f.stride == sizeof(int32_t))
-      CUDA_TRY(h, cudaMemcpyAsync(f.base, h->HI[pf], N*sizeof(int32_t), cudaMemcpyDeviceToHost, cs));
+    if (f.stride == sizeof(int32_t)) {
+      if (nr > 0) CUDA_TRY(h, cudaMemcpyAsync((int32_t*) f.base + r0, h->HI[pf] + r0, nr*sizeof(int32_t), cudaMemcpyDeviceToHost, cs));
+    }
+    else if (!whole) { h->err = "gsph_download_range needs contiguous (SoA) fields"; return GSPH_EINVAL; }
     else {
       int rc = ensure_pinned(h, N*sizeof(int32_t)); if (rc) return rc;
       CUDA_TRY(h, cudaMemcpyAsync(h->pinned, h->HI[pf], N*sizeof(int32_t), cudaMemcpyDeviceToHost, cs));
@@ -558,12 +592,47 @@ int gsph_download_async(gsph_handle* h, const gsph_particle_view* view, uint32_t
   return download_impl(h, view, field_mask, false);
 }
 
+/* host-order particles [lo, hi) only (the share of this rank in a multi-process host); wait = 0 queues
+   the copies like gsph_download_async */
+int gsph_download_range(gsph_handle* h, const gsph_particle_view* view, uint32_t field_mask, int64_t lo, int64_t hi, int wait)
+{
+  return download_impl(h, view, field_mask, wait != 0, lo, hi);
+}
+
+/* device pointer of one particle array by name: "rx" "ry" "rz" "vx" "vy" "vz" "ax" .. "atz" "m" "h" "u" "rho"
+   "hrangesqd" "hfactor" "invomega" "zeta" "sound" "pressure" "dudt" "div_v" "alpha" "dalphadt" "gpot"
+   "gpot_hydro" (double) and "flags" "ptype" "level" "levelneib" "iorig" "sinkid" (int32) */
+int gsph_device_array(gsph_handle* h, int which, const char* name, void** ptr, int64_t* capacity, int32_t* elem_size)
+{
+  if (!h || !name || !ptr) return GSPH_EINVAL;
+  static const char* const dn[NF_DOUBLE] = {"rx", "ry", "rz", "vx", "vy", "vz", "ax", "ay", "az", "atx", "aty", "atz",
+    "m", "h", "u", "rho", "hrangesqd", "hfactor", "invomega", "zeta", "sound", "pressure", "dudt", "div_v", "alpha",
+    "dalphadt", "gpot", "gpot_hydro"};
+  static const char* const in[NF_INT] = {"flags", "ptype", "level", "levelneib", "iorig", "sinkid"};
+  if (which != GSPH_ARRAY_TREE_ORDER && which != GSPH_ARRAY_STAGING) { h->err = "gsph_device_array: bad array class"; return GSPH_EINVAL; }
+  if (!h->H[0]) { h->err = "gsph_device_array before gsph_upload"; return GSPH_ESTATE; }
+  for (int k = 0; k < NF_DOUBLE; k++) if (!strcmp(name, dn[k])) {
+    *ptr = which == GSPH_ARRAY_STAGING ? h->H[k] : h->P[k];
+    if (capacity) *capacity = h->Ncap;
+    if (elem_size) *elem_size = 8;
+    return GSPH_OK;
+  }
+  for (int k = 0; k < NF_INT; k++) if (!strcmp(name, in[k])) {
+    *ptr = which == GSPH_ARRAY_STAGING ? (void*) h->HI[k] : (void*) h->PI[k];
+    if (capacity) *capacity = h->Ncap;
+    if (elem_size) *elem_size = 4;
+    return GSPH_OK;
+  }
+  h->err = std::string("gsph_device_array: unknown array ") + name;
+  return GSPH_EINVAL;
+}
+
 /*------------------------------------------------------------------------------------------------*/
 int gsph_build_tree(gsph_handle* h, int mode, double dt)
 {
   if (!h) return GSPH_EINVAL;
   if (!h->uploaded) { h->err = "gsph_build_tree before gsph_upload"; return GSPH_ESTATE; }
-  if (mode < 0 || mode > 2) { h->err = "gsph_build_tree: mode must be 0, 1 or 2"; return GSPH_EINVAL; }
+  if (mode < 0 || mode > 3) { h->err = "gsph_build_tree: mode must be 0, 1, 2 or 3"; return GSPH_EINVAL; }
   cudaSetDevice(h->device);
   Timer tm(h, &h->stats.ms_build_tree);
   if (!h->have_tree) mode = 0;

@@ -50,6 +50,9 @@ __device__ __forceinline__ void thermal(const DevParams& dp, double rho, double&
   if (dp.eos == GSPH_EOS_ISOTHERMAL) u = dp.temp0/dp.gammam1/dp.mu_bar;
   else if (dp.eos == GSPH_EOS_BAROTROPIC)
     u = dp.temp0*(1.0 + pow(rho*(1.0/dp.rho_bary), dp.gammam1))/dp.gammam1/dp.mu_bar;
+  else if (dp.eos == GSPH_EOS_BAROTROPIC2)                   /* Barotropic2EOS.cpp:78-83 */
+    u = rho < dp.rho_bary ? dp.temp0/dp.gammam1/dp.mu_bar
+                          : dp.temp0*pow(rho*(1.0/dp.rho_bary), dp.gammam1)/dp.gammam1/dp.mu_bar;
   if (dp.eos == GSPH_EOS_ADIABATIC) sound = sqrt(dp.gamma_eos*dp.gammam1*u);
   else sound = sqrt(dp.gammam1*u);
   press = dp.gammam1*rho*u;

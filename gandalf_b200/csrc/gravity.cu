@@ -61,7 +61,7 @@ __device__ __forceinline__ double rsqrt_nr(double x)
 template <bool QUAD>
 struct WarpSharedT {
   int2 stack[GRAV_STACK];
-  double leafgeom[GRAV_LEAVES][5];     /* rcell xyz, rmax, kernrange*hmax of the cohort's leaves */
+  double leafgeom[GRAV_LEAVES][6];     /* rcell xyz, rmax, kernrange*hmax, MAC auxiliary (amin | macfactor) of the cohort's leaves */
   int cell_node[CELL_BUF]; unsigned cell_mask[CELL_BUF];
   int dir_node[DIR_BUF]; unsigned dir_mask[DIR_BUF];
   double cell_data[CELL_TILE][QUAD ? 9 : 4];   /* com xyz, m [, q0..q4] */
@@ -72,7 +72,7 @@ struct WarpSharedT {
 
 struct FastMp { double ac[3], q[6], pot; };   /* dphi == ac for HoT = false */
 
-template <int MULTIPOLE, int T>
+template <int MULTIPOLE, int T, bool GEOMAC>
 __global__ void __launch_bounds__(GRAV_THREADS, (T == 1 && MULTIPOLE != GSPH_MULTIPOLE_FAST_QUADRUPOLE) ? GRAV_MINBLOCKS : 2)
 gravity_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* work_counter,
                DevStatus* st, uint8_t* done)
@@ -132,6 +132,7 @@ gravity_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* wo
       for (int k = 0; k < 3; k++) S.leafgeom[myl][k] = leaf_live ? tree.rcell[k][myleaf] : 0.0;
       S.leafgeom[myl][3] = leaf_live ? tree.rmax[myleaf] : 0.0;
       S.leafgeom[myl][4] = leaf_live ? __dmul_rn(dp.kernrange, tree.hmax[myleaf]) : 0.0;
+      if (!GEOMAC) S.leafgeom[myl][5] = (leaf_live && tree.macaux) ? tree.macaux[myleaf] : 0.0;
     }
     if (FAST && leaf_live) { rcom[0] = tree.com[0][myleaf]; rcom[1] = tree.com[1][myleaf]; rcom[2] = tree.com[2][myleaf]; }
     const unsigned lb = __ballot_sync(FULLMASK, leaf_live && sub == 0);
@@ -343,6 +344,8 @@ gravity_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* wo
           const double rx = g0.x, ry = g0.y, rz = g1.x;
           const double crmax = g1.y, cdist = g2.x;
           const double chr = g2.y;                         /* kernrange*hmax of the node */
+          const double cmac = g3.y;                        /* gadget2: rmax^2*m; eigenmac: TreeCell::mac */
+          const int mac = dp.gravity_mac; const double macerror = dp.macerror;
           /* only the leaves still undecided for this node (set bits of the mask) are evaluated, two
              per iteration so that their dependent arithmetic chains overlap */
           auto opens = [&](int l) -> bool {
@@ -353,8 +356,14 @@ gravity_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* wo
             const double rmax = lg[3];
             const double a = __dadd_rn(__dadd_rn(crmax, rmax), lg[4]);
             const double b = __dadd_rn(__dadd_rn(rmax, crmax), chr);
-            /* Tree.cpp:660-731: overlap -> open; else MAC (Tree.h:413-432 geometric: open iff drsqd < cdistsqd) */
-            return drsqd <= __dmul_rn(a, a) || drsqd <= __dmul_rn(b, b) || drsqd < cdist;
+            /* Tree.cpp:660-731: overlap -> open; else open_cell_for_gravity (Tree.h:413-432):
+               geometric part drsqd < cdistsqd, then the eigenvalue or the Gadget-2 criterion with the
+               target leaf's macfactor / amin, evaluated left to right without contraction */
+            if (drsqd <= __dmul_rn(a, a) || drsqd <= __dmul_rn(b, b) || drsqd < cdist) return true;
+            if (GEOMAC) return false;
+            if (mac == GSPH_MAC_EIGEN) return drsqd < __dmul_rn(cmac, lg[5]);
+            if (mac == GSPH_MAC_GADGET2) return __dmul_rn(__dmul_rn(__dmul_rn(drsqd, drsqd), lg[5]), macerror) < cmac;
+            return false;
           };
           unsigned todo = mask;
           while (todo) {
@@ -459,11 +468,11 @@ gravity_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* wo
   }
 }
 
-template <int MULTIPOLE, int T>
+template <int MULTIPOLE, int T, bool GEOMAC>
 int launch_gravity_t(gsph_handle* h)
 {
   const size_t smem = GRAV_WARPS*sizeof(WarpSharedT<(MULTIPOLE == GSPH_MULTIPOLE_QUADRUPOLE || MULTIPOLE == GSPH_MULTIPOLE_FAST_QUADRUPOLE)>);
-  auto kern = gravity_kernel<MULTIPOLE, T>;
+  auto kern = gravity_kernel<MULTIPOLE, T, GEOMAC>;
   CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   int bps = 0;
   CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, GRAV_THREADS, smem));
@@ -489,7 +498,9 @@ int launch_gravity(gsph_handle* h)
 {
   /* largest leaf of the balanced tree: ceil(N / 2^ltot); 4 lanes per leaf -> T particles per lane */
   const int64_t maxleaf = (h->N + ((int64_t) 1 << h->tree.ltot) - 1) >> h->tree.ltot;
-  return maxleaf <= 4 ? launch_gravity_t<MULTIPOLE, 1>(h) : launch_gravity_t<MULTIPOLE, 2>(h);
+  if (h->dp.gravity_mac == GSPH_MAC_GEOMETRIC)
+    return maxleaf <= 4 ? launch_gravity_t<MULTIPOLE, 1, true>(h) : launch_gravity_t<MULTIPOLE, 2, true>(h);
+  return maxleaf <= 4 ? launch_gravity_t<MULTIPOLE, 1, false>(h) : launch_gravity_t<MULTIPOLE, 2, false>(h);
 }
 
 }  // namespace

@@ -55,6 +55,9 @@ struct TreeDev {
   double* hmax = nullptr;
   double* cdistsqd = nullptr;     /* geometric MAC distance^2, KDTree.cpp:917              */
   double* q[5] = {0, 0, 0, 0, 0}; /* traceless quadrupole, KDTree.cpp:937-1000             */
+  double* macaux = nullptr;       /* gadget2: min |atree| below the node (TreeCell::amin); eigenmac:
+                                     max gpot^(-2/3) (TreeCell::macfactor); KDTree.cpp:899-903,967-984;
+                                     allocated only for those criteria                          */
   /* single-precision node records for the neighbour walks (candidate sets only have to be
      supersets, so boxes rounded OUTWARD to float are enough and cost a third of the loads):
        nodeb[2n]   = (bbmin.xyz, first as int bits)   nodeb[2n+1] = (bbmax.xyz, count as int bits)
@@ -63,7 +66,8 @@ struct TreeDev {
   float4* nodeh = nullptr;
   /* exact double-precision node records of the gravity walk (one 64-byte line / one 32-byte sector
      per node instead of seven / four separate arrays):
-       gnode[4n..4n+3] = (rcell.x, rcell.y) (rcell.z, rmax) (cdistsqd, kernrange*hmax) (count, 0)
+       gnode[4n..4n+3] = (rcell.x, rcell.y) (rcell.z, rmax) (cdistsqd, kernrange*hmax) (count, mac)
+                         mac = rmax^2*m for gadget2, TreeCell::mac for eigenmac (Tree.h:413-432)
        mnode[2n..2n+1] = (com.x, com.y) (com.z, m)                                               */
   double2* gnode = nullptr;
   double2* mnode = nullptr;
@@ -112,6 +116,7 @@ struct gsph_handle {
        ev_compute: the compute stream reached the point where a copy may touch the staging arrays  */
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_geom = nullptr, ev_all = nullptr, ev_compute = nullptr;
+  cudaEvent_t ev_axis[3] = {nullptr, nullptr, nullptr};   /* coordinate k of the last upload has landed (its sort may start) */
   bool upload_pending = false;   /* ev_geom / ev_all still have to be waited for by the compute stream */
   std::string err;
 

@@ -146,6 +146,18 @@ __global__ void stock_leaves_kernel(TreeDev T, PartView P, DevParams dp, int ful
 #pragma unroll
   for (int k = 0; k < NDIM; k++) { T.hbmin[k][n] = hbmin[k]; T.hbmax[k][n] = hbmax[k]; }
   if (!full) return;
+  if (T.macaux && full == 1) {                     /* KDTree.cpp:838-841, 899-903 */
+    double aux = dp.gravity_mac == GSPH_MAC_GADGET2 ? GSPH_BIG : 0.0;
+    for (int i = fst; i < fst + cnt; i++) {
+      if (((unsigned) P.i[I_FLAGS][i]) & GSPH_FLAG_DEAD) continue;
+      if (dp.gravity_mac == GSPH_MAC_GADGET2) {
+        double at[3] = {P.f[F_ATX][i], NDIM > 1 ? P.f[F_ATY][i] : 0.0, NDIM > 2 ? P.f[F_ATZ][i] : 0.0};
+        aux = fmin(aux, __dsqrt_rn(dot_exact<NDIM>(at)));
+      }
+      else aux = fmax(aux, pow(P.f[F_GPOT][i], -0.66666666666666666666666));
+    }
+    T.macaux[n] = aux;
+  }
   if (m > 0.0) {
 #pragma unroll
     for (int k = 0; k < NDIM; k++) { com[k] = com[k]/m; vc[k] = vc[k]/m; }
@@ -213,6 +225,14 @@ __global__ void stock_level_kernel(TreeDev T, DevParams dp, int level, int full)
 #pragma unroll
   for (int d = 0; d < NDIM; d++) { T.hbmin[d][n] = hbmin[d]; T.hbmax[d][n] = hbmax[d]; }
   if (!full) return;
+  if (T.macaux && full == 1) {                     /* KDTree.cpp:967-984 */
+    const bool gad = dp.gravity_mac == GSPH_MAC_GADGET2;
+    double aux = gad ? GSPH_BIG : 0.0;
+#pragma unroll
+    for (int s = 0; s < 2; s++)
+      if (T.count[c[s]] > 0) aux = gad ? fmin(aux, T.macaux[c[s]]) : fmax(aux, T.macaux[c[s]]);
+    T.macaux[n] = aux;
+  }
   const double m0 = T.m[c[0]], m1 = T.m[c[1]];
   const double m = m0 + m1;
   double com[3] = {0, 0, 0}, vc[3] = {0, 0, 0};
@@ -277,7 +297,7 @@ __global__ void extrapolate_kernel(TreeDev T, double dt)
 
 /* outward-rounded single-precision node records for the neighbour walks (TreeDev::nodeb / nodeh) */
 template <int NDIM>
-__global__ void pack_nodes_kernel(TreeDev T, int with_bb, double kernrange)
+__global__ void pack_nodes_kernel(TreeDev T, int with_bb, double kernrange, int gravity_mac, double macerror)
 {
   const int n = blockIdx.x*blockDim.x + threadIdx.x;
   if (n >= T.ncell) return;
@@ -286,7 +306,20 @@ __global__ void pack_nodes_kernel(TreeDev T, int with_bb, double kernrange)
     if (with_bb) {
       T.gnode[4*(size_t) n] = make_double2(T.rcell[0][n], NDIM > 1 ? T.rcell[1][n] : 0.0);
       T.gnode[4*(size_t) n + 1] = make_double2(NDIM > 2 ? T.rcell[2][n] : 0.0, T.rmax[n]);
-      T.gnode[4*(size_t) n + 3] = make_double2((double) cnt, 0.0);
+      double mac = 0.0;
+      if (gravity_mac == GSPH_MAC_GADGET2) mac = __dmul_rn(__dmul_rn(T.rmax[n], T.rmax[n]), T.m[n]);
+      else if (gravity_mac == GSPH_MAC_EIGEN) {                      /* KDTree.cpp:1058-1079 */
+        double lambda, pp;
+        const double q0 = T.q[0][n], q1 = T.q[1][n], q2 = T.q[2][n], q3 = T.q[3][n], q4 = T.q[4][n];
+        if (NDIM == 3) {
+          pp = q0*q2 - (q0 + q2)*(q0 + q2) - q1*q1 - q3*q3 - q4*q4;
+          lambda = pp >= 0.0 ? 0.0 : 2.0*sqrt(-pp/3.0);
+        }
+        else if (NDIM == 2) { pp = (q0 - q2)*(q0 - q2) + 4*q1*q1; lambda = 0.5*fmax(q0 + q2 + sqrt(pp), 0.); }
+        else lambda = fabs(q0);
+        mac = pow(0.5*lambda/macerror, 0.66666666666666);
+      }
+      T.gnode[4*(size_t) n + 3] = make_double2((double) cnt, mac);
       T.mnode[2*(size_t) n] = make_double2(T.com[0][n], NDIM > 1 ? T.com[1][n] : 0.0);
       T.mnode[2*(size_t) n + 1] = make_double2(NDIM > 2 ? T.com[2][n] : 0.0, T.m[n]);
     }
@@ -322,6 +355,7 @@ int alloc_tree(gsph_handle* h, int ltot)
   fre(T.first); fre(T.count); fre(T.nactive); fre(T.m); fre(T.rmax); fre(T.hmax); fre(T.cdistsqd);
   fre(T.nodeb); fre(T.nodeh); T.nodeb = T.nodeh = nullptr;
   fre(T.gnode); fre(T.mnode); T.gnode = T.mnode = nullptr;
+  fre(T.macaux); T.macaux = nullptr;
   for (int k = 0; k < 3; k++) {
     fre(T.bbmin[k]); fre(T.bbmax[k]); fre(T.hbmin[k]); fre(T.hbmax[k]);
     fre(T.rcell[k]); fre(T.com[k]); fre(T.vcom[k]);
@@ -338,6 +372,7 @@ int alloc_tree(gsph_handle* h, int ltot)
   CUDA_TRY(h, cudaMalloc(&T.cdistsqd, cap*sizeof(double)));
   CUDA_TRY(h, cudaMalloc(&T.nodeb, 2*cap*sizeof(float4)));
   CUDA_TRY(h, cudaMalloc(&T.nodeh, 2*cap*sizeof(float4)));
+  if (h->dp.self_gravity && h->dp.gravity_mac != GSPH_MAC_GEOMETRIC) CUDA_TRY(h, cudaMalloc(&T.macaux, cap*sizeof(double)));
   if (h->dp.self_gravity) {
     CUDA_TRY(h, cudaMalloc(&T.gnode, 4*cap*sizeof(double2)));
     CUDA_TRY(h, cudaMalloc(&T.mnode, 2*cap*sizeof(double2)));
@@ -377,7 +412,7 @@ int stock_tree(gsph_handle* h, int full)
     const int nn = 1 << l;
     stock_level_kernel<NDIM><<<(nn + 127)/128, 128, 0, h->stream>>>(T, h->dp, l, full);
   }
-  pack_nodes_kernel<NDIM><<<(T.ncell + 255)/256, 256, 0, h->stream>>>(T, full, h->dp.kernrange);
+  pack_nodes_kernel<NDIM><<<(T.ncell + 255)/256, 256, 0, h->stream>>>(T, full, h->dp.kernrange, h->dp.gravity_mac, h->dp.macerror);
   h->stats.kernel_launches += 2 + T.ltot;
   CUDA_TRY(h, cudaGetLastError());
   return GSPH_OK;
@@ -394,7 +429,8 @@ int build_tree_nd(gsph_handle* h, int mode, double dt)
   cudaStream_t s = h->stream;
   const PartView Hh = view_of(h->H, h->HI);
   const PartView Pp = view_of(h->P, h->PI);
-  cudaStreamWaitEvent(s, h->ev_geom, 0);         /* r, h and the integer fields of the last upload have landed */
+  if (mode != 0) cudaStreamWaitEvent(s, h->ev_geom, 0);   /* r, h and the integer fields of the last upload have landed
+                                                             (a rebuild waits per coordinate, see build_tree_v2) */
 
   if (mode == 2) {                                   /* extrapolate: Tree.cpp:172-198 */
     if (!h->have_tree) { h->err = "gsph_build_tree(extrapolate) before the first rebuild"; return GSPH_ESTATE; }
@@ -404,17 +440,17 @@ int build_tree_nd(gsph_handle* h, int mode, double dt)
       h->sorted_valid = true; h->stats.kernel_launches++;
     }
     extrapolate_kernel<NDIM><<<(h->tree.ncell + 255)/256, 256, 0, s>>>(h->tree, dt);
-    pack_nodes_kernel<NDIM><<<(h->tree.ncell + 255)/256, 256, 0, s>>>(h->tree, 1, h->dp.kernrange);
+    pack_nodes_kernel<NDIM><<<(h->tree.ncell + 255)/256, 256, 0, s>>>(h->tree, 1, h->dp.kernrange, h->dp.gravity_mac, h->dp.macerror);
     h->stats.kernel_launches += 2;
     CUDA_TRY(h, cudaGetLastError());
     return GSPH_OK;
   }
-  if (mode == 1) {                                   /* restock: KDTree::StockTree */
+  if (mode == 1 || mode == 3) {                      /* restock: KDTree::StockTree (3: keep amin / macfactor) */
     if (!h->have_tree) { h->err = "gsph_build_tree(restock) before the first rebuild"; return GSPH_ESTATE; }
     cudaStreamWaitEvent(s, h->ev_all, 0);      /* every uploaded field has landed */
   gather_kernel<<<(N + 255)/256, 256, 0, s>>>(N, h->perm, Hh, Pp);
     h->sorted_valid = true; h->stats.kernel_launches++;
-    return stock_tree<NDIM>(h, 1);
+    return stock_tree<NDIM>(h, mode == 3 ? 2 : 1);
   }
 
   /* ---- full rebuild ----------------------------------------------------------------------------*/
@@ -657,7 +693,6 @@ int build_tree_v2(gsph_handle* h, int phase, int shard_rank, int shard_world)
   constexpr int nd = NDIM;
   constexpr int NR = NDIM - 1;
   cudaStream_t s = h->stream;
-  cudaStreamWaitEvent(s, h->ev_geom, 0);         /* r, h and the integer fields of the last upload have landed */
   const PartView Hh = view_of(h->H, h->HI);
   const PartView Pp = view_of(h->P, h->PI);
 
@@ -713,13 +748,10 @@ int build_tree_v2(gsph_handle* h, int phase, int shard_rank, int shard_world)
   void* cubtmp = B.get<char>(cub_bytes);
   if (B.off > B.cap) { h->err = "internal: tree scratch layout overflow"; return GSPH_ENOMEM; }
 
-  /* root box and the presorted lists */
-  root_box_kernel<NDIM><<<rb_blocks, 256, 0, s>>>(N, Hh, h->dp.kernrange, rbpart);
-  root_box_final<NDIM><<<1, 32, 0, s>>>(rb_blocks, rbpart, L.ib[0][0][0], L.ib[0][0][1], L.ib[0][0][2],
-                                        L.ib[0][1][0], L.ib[0][1][1], L.ib[0][1][2]);
-  h->stats.kernel_launches += 2;
+  /* the presorted lists: the sort of an axis starts as soon as that coordinate of the upload has landed */
   cudaEventRecord(h->evk[3][0], s);
   for (int d = 0; d < nd; d++) {
+    cudaStreamWaitEvent(s, h->ev_axis[d], 0);
     iota_kernel<<<(N + 255)/256, 256, 0, s>>>(N, L.ids[d][1]);
     size_t tb = cub_bytes;
     cub::DeviceRadixSort::SortPairs(cubtmp, tb, (const double*) h->H[F_RX + d], keys_out,
@@ -727,6 +759,12 @@ int build_tree_v2(gsph_handle* h, int phase, int shard_rank, int shard_world)
     h->stats.kernel_launches += 8;
     if (nd > 1) { rank_scatter_kernel<<<(N + 255)/256, 256, 0, s>>>(N, L.ids[d][0], rank[d]); h->stats.kernel_launches++; }
   }
+  /* root box = extent of r -+ kernrange*h: needs h (and every coordinate) */
+  cudaStreamWaitEvent(s, h->ev_geom, 0);
+  root_box_kernel<NDIM><<<rb_blocks, 256, 0, s>>>(N, Hh, h->dp.kernrange, rbpart);
+  root_box_final<NDIM><<<1, 32, 0, s>>>(rb_blocks, rbpart, L.ib[0][0][0], L.ib[0][0][1], L.ib[0][0][2],
+                                        L.ib[0][1][0], L.ib[0][1][1], L.ib[0][1][2]);
+  h->stats.kernel_launches += 2;
   if (nd > 1) { fill_ranks_kernel<NDIM><<<(N + 255)/256, 256, 0, s>>>(N, L); h->stats.kernel_launches++; }
   cudaEventRecord(h->evk[3][1], s); h->evk_used[3] = true;
   cudaEventRecord(h->evk[4][0], s);

@@ -118,8 +118,8 @@ class GpuSphTree : public GradhSphTree<ndim, GradhSphParticle>
     if (sph->tdavisc == cd2010) ExceptionHandler::getIstance().raise("GpuSphTree: cd2010 viscosity is not accelerated");
     c.tdavisc = (int) sph->tdavisc;
     c.alpha_visc = sph->alpha_visc; c.beta_visc = sph->beta_visc; c.alpha_visc_min = sph->alpha_visc_min;
-    static const char* const eos[] = {"energy_eqn", "isothermal", "barotropic"};
-    c.eos = sp["gas_eos"] == "constant_temp" ? GSPH_EOS_ADIABATIC : lookup(sp["gas_eos"], eos, 3, "gas_eos");
+    static const char* const eos[] = {"energy_eqn", "isothermal", "barotropic", "barotropic2"};
+    c.eos = sp["gas_eos"] == "constant_temp" ? GSPH_EOS_ADIABATIC : lookup(sp["gas_eos"], eos, 4, "gas_eos");
     c.gamma_eos = fp["gamma_eos"];
     c.temp0 = fp["temp0"]/units.temp.outscale;                       // code units, as the EOS classes scale them
     c.mu_bar = fp["mu_bar"];
@@ -187,7 +187,7 @@ class GpuSphTree : public GradhSphTree<ndim, GradhSphParticle>
   {
     CodeTiming::BlockTimer timer = this->timing->StartNewTimer("SPH_HYDRO_FORCES");
     upload(sph);                          // picks up Sph::ZeroAccelerations and the active flags
-    check(gsph_build_tree(handle, 1, 0.0));
+    check(gsph_build_tree(handle, 3, 0.0));
     set_stars(sph, nbody);                // ComputeStarGravForces, GradhSphTree.cpp:385-392
     check(gsph_update_hydro_forces(handle));
     download(sph, GSPH_F_FORCES);
@@ -200,7 +200,7 @@ class GpuSphTree : public GradhSphTree<ndim, GradhSphParticle>
   {
     CodeTiming::BlockTimer timer = this->timing->StartNewTimer("SPH_ALL_FORCES");
     upload(sph);
-    check(gsph_build_tree(handle, 1, 0.0));
+    check(gsph_build_tree(handle, 3, 0.0));     // restock; amin / macfactor keep their BuildTree values
     set_stars(sph, nbody);                // ComputeStarGravForces, GradhSphTree.cpp:600-607
     check(gsph_update_all_forces(handle, NULL, 0));
     download(sph, GSPH_F_FORCES);

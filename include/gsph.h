@@ -56,7 +56,8 @@ enum { GSPH_ACOND_NONE = 0, GSPH_ACOND_WADSLEY2008 = 1, GSPH_ACOND_PRICE2008 = 2
 enum { GSPH_TDAVISC_NONE = 0, GSPH_TDAVISC_MM97 = 1 };
 /* gas_eos = energy_eqn|constant_temp (Adiabatic) | isothermal | barotropic
  *           (src/Hydrodynamics/Hydrodynamics.cpp:91-108; src/Thermal/{Adiabatic,Isothermal,Barotropic}EOS.cpp) */
-enum { GSPH_EOS_ADIABATIC = 0, GSPH_EOS_ISOTHERMAL = 1, GSPH_EOS_BAROTROPIC = 2 };
+enum { GSPH_EOS_ADIABATIC = 0, GSPH_EOS_ISOTHERMAL = 1, GSPH_EOS_BAROTROPIC = 2,
+       GSPH_EOS_BAROTROPIC2 = 3 /* src/Thermal/Barotropic2EOS.cpp:69-91 */ };
 /* boundary_lhs/rhs = open | periodic | mirror (src/Headers/DomainBox.h:49-92)                     */
 enum { GSPH_BOUNDARY_OPEN = 0, GSPH_BOUNDARY_PERIODIC = 1, GSPH_BOUNDARY_MIRROR = 2 };
 /* gravity_mac = geometric | eigenmac | gadget2 (src/Headers/Tree.h:413-432)                        */
@@ -167,13 +168,26 @@ int gsph_download(gsph_handle* h, const gsph_particle_view* view, uint32_t field
  * kernels issued so far and returns; later kernels (e.g. the force pass after a density download)
  * overlap them.  gsph_synchronize (or a plain gsph_download) waits for everything.               */
 int gsph_download_async(gsph_handle* h, const gsph_particle_view* view, uint32_t field_mask);
+/* Multi-process hosts (one process per GPU, each owning the host-order particles [lo, hi) of the
+ * N-particle set -- what an MPI rank owns in the reference, src/Mpi/MpiControl.cpp): ship / fetch only
+ * that share over PCIe; the other shares travel GPU-to-GPU (NCCL all-gather issued by the host layer
+ * on the arrays of gsph_device_array).  Contiguous (SoA) fields only.                               */
+int gsph_upload_range(gsph_handle* h, const gsph_particle_view* view, int64_t N, int64_t lo, int64_t hi);
+int gsph_download_range(gsph_handle* h, const gsph_particle_view* view, uint32_t field_mask,
+                        int64_t lo, int64_t hi, int wait);
+enum { GSPH_ARRAY_TREE_ORDER = 0, GSPH_ARRAY_STAGING = 1 /* host order */ };
+int gsph_device_array(gsph_handle* h, int which, const char* name, void** ptr, int64_t* capacity,
+                      int32_t* elem_size);
 
 /* ---- the operator surface ----------------------------------------------------------------------
  * gsph_build_tree           NeighbourSearch::BuildTree          HydroTree.cpp:310-372
  *                           (+ BuildGhostTree/SearchBoundaryGhostParticles, :382-441,:495-543,
  *                            which become no-ops: see gsph_upload)
  *     mode 0 = rebuild (KDTree::BuildTree, KDTree.cpp:220-313), 1 = restock (StockTree, :760-798),
- *     2 = extrapolate cell boxes by v*dt (Tree.cpp:172-198).
+ *     2 = extrapolate cell boxes by v*dt (Tree.cpp:172-198), 3 = restock but keep the cells'
+ *     gadget2 / eigenmac auxiliaries (amin, macfactor: the reference stocks them from the PREVIOUS
+ *     step's atree / gpot in BuildTree, before Sph::ZeroAccelerations; a host that re-uploads after
+ *     zeroing uses mode 3 so that they survive).
  * gsph_update_active_counters  KDTree::UpdateActiveParticleCounters   KDTree.cpp:1217-1254
  * gsph_update_properties    SphNeighbourSearch::UpdateAllSphProperties  GradhSphTree.cpp:83-271
  *                           (ComputeH GradhSph.cpp:142-326 + UpdateAllHmaxValues KDTree.cpp:1128-1208)

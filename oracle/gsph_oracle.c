@@ -301,6 +301,9 @@ static void thermal(const orc_params* p, double rho, double* u, double* sound, d
   const double gamma = p->gamma_eos, gammam1 = p->gamma_eos - 1.0;
   if (p->eos == 1) *u = p->temp0/gammam1/p->mu_bar;
   else if (p->eos == 2) *u = p->temp0*(1.0 + pow(rho*(1.0/p->rho_bary), gammam1))/gammam1/p->mu_bar;
+  else if (p->eos == 3)                      /* Barotropic2, src/Thermal/Barotropic2EOS.cpp:78-83 */
+    *u = rho < p->rho_bary ? p->temp0/gammam1/p->mu_bar
+                           : p->temp0*pow(rho*(1.0/p->rho_bary), gammam1)/gammam1/p->mu_bar;
   if (p->eos == 0) *sound = sqrt(gamma*gammam1*(*u));
   else *sound = sqrt(gammam1*(*u));
   *pressure = gammam1*rho*(*u);
@@ -657,6 +660,7 @@ typedef struct {
   int level, copen, cnext, c1, c2, ifirst, ilast, N;
   double bbmin[3], bbmax[3], hbmin[3], hbmax[3], rcell[3], r[3], v[3];
   double m, rmax, hmax, cdistsqd, mac, q[5];
+  double amin, macfactor;          /* gadget2 / eigenmac auxiliaries, KDTree.cpp:838-841,899-903,967-984 */
 } kdcell;
 
 struct orc_tree {
@@ -665,6 +669,7 @@ struct orc_tree {
   kdcell* cell;
   int *ids, *inext;
   const double *r, *v, *m, *h;
+  const double *atree, *gpot;      /* previous-step values read by the gadget2 / eigenmac criteria (may be NULL) */
 };
 
 static double quickselect(orc_tree* T, int left, int right, int jpivot, int k)
@@ -697,6 +702,7 @@ static void stock_cell(orc_tree* T, kdcell* c)
   double dr[3], drsqd, mi;
   int k, i;
   c->N = 0; c->m = 0; c->hmax = 0; c->rmax = 0; c->mac = 0; c->cdistsqd = BIG_NUMBER;
+  c->amin = BIG_NUMBER; c->macfactor = 0;
   for (k = 0; k < 5; k++) c->q[k] = 0;
   for (k = 0; k < nd; k++) {
     c->r[k] = 0; c->v[k] = 0; c->rcell[k] = 0;
@@ -718,6 +724,10 @@ static void stock_cell(orc_tree* T, kdcell* c)
         if (x - kr*T->h[i] < c->hbmin[k]) c->hbmin[k] = x - kr*T->h[i];
         if (x + kr*T->h[i] > c->hbmax[k]) c->hbmax[k] = x + kr*T->h[i];
       }
+      if (p->gravity_mac == 2 && T->atree)                                  /* KDTree.cpp:899-901 */
+        c->amin = fmin(c->amin, sqrt(dot(T->atree + (size_t)i*nd, T->atree + (size_t)i*nd, nd)));
+      else if (p->gravity_mac == 1 && T->gpot)                              /* KDTree.cpp:902-903 */
+        c->macfactor = fmax(c->macfactor, pow(T->gpot[i], -0.66666666666666666666666));
       if (i == c->ilast) break;
       i = T->inext[i];
     }
@@ -766,6 +776,8 @@ static void stock_cell(orc_tree* T, kdcell* c)
           c->hbmax[k] = fmax(ch[s]->hbmax[k], c->hbmax[k]);
         }
         c->hmax = fmax(c->hmax, ch[s]->hmax);
+        if (p->gravity_mac == 2) c->amin = fmin(c->amin, ch[s]->amin);
+        else if (p->gravity_mac == 1) c->macfactor = fmax(c->macfactor, ch[s]->macfactor);
       }
     }
     c->N = ch[0]->N + ch[1]->N;
@@ -805,6 +817,20 @@ static void stock_cell(orc_tree* T, kdcell* c)
         }
       }
     }
+  }
+  /* eigenvalue MAC, KDTree.cpp:1058-1079 */
+  if (p->gravity_mac == 1) {
+    double lambda, pp;
+    if (nd == 3) {
+      pp = c->q[0]*c->q[2] - (c->q[0] + c->q[2])*(c->q[0] + c->q[2]) - c->q[1]*c->q[1] - c->q[3]*c->q[3] - c->q[4]*c->q[4];
+      lambda = pp >= 0.0 ? 0.0 : 2.0*sqrt(-pp/3.0);
+    }
+    else if (nd == 2) {
+      pp = (c->q[0] - c->q[2])*(c->q[0] - c->q[2]) + 4*c->q[1]*c->q[1];
+      lambda = 0.5*fmax(c->q[0] + c->q[2] + sqrt(pp), 0.);
+    }
+    else lambda = fabs(c->q[0]);
+    c->mac = pow(0.5*lambda/p->macerror, 0.66666666666666);
   }
 }
 
@@ -852,9 +878,15 @@ static void divide_cell(orc_tree* T, int ifirst, int ilast, kdcell* cell)
 orc_tree* orc_tree_build(const orc_params* p, int N, const double* r, const double* v,
                          const double* m, const double* h)
 {
+  return orc_tree_build_mac(p, N, r, v, m, h, 0, 0);
+}
+
+orc_tree* orc_tree_build_mac(const orc_params* p, int N, const double* r, const double* v,
+                             const double* m, const double* h, const double* atree, const double* gpot)
+{
   orc_tree* T = (orc_tree*) calloc(1, sizeof(orc_tree));
   const int nd = p->ndim; const double kr = kern_range(p);
-  T->p = *p; T->N = N; T->r = r; T->v = v; T->m = m; T->h = h;
+  T->p = *p; T->N = N; T->r = r; T->v = v; T->m = m; T->h = h; T->atree = atree; T->gpot = gpot;
   T->ltot = 0;
   while (p->Nleafmax*pow(2, T->ltot) < N) T->ltot++;
   T->gtot = (int) pow(2, T->ltot);
@@ -1063,6 +1095,15 @@ static void fast_apply(int nd, const fastmp* F, const double* r, acc_t* A)
  *  cull  NeighbourManager::_EndSearch                 NeighbourManager.h:396-470
  *  trim  NeighbourManager::TrimNeighbourLists         NeighbourManager.h:503-542
  *-----------------------------------------------------------------------------------------------*/
+/* open_cell_for_gravity, src/Headers/Tree.h:413-432 */
+static int open_cell_for_gravity(const orc_params* p, const kdcell* c, double drsqd, double macfactor, double amag)
+{
+  if (drsqd < c->cdistsqd) return 1;
+  if (p->gravity_mac == 1) return drsqd < c->mac*macfactor;                               /* eigenmac */
+  if (p->gravity_mac == 2) return drsqd*drsqd*amag*p->macerror < c->rmax*c->rmax*c->m;   /* gadget2  */
+  return 0;
+}
+
 int orc_hydro_grav_forces_tree(const orc_params* p, const orc_tree* T, int N, const double* r,
                      const double* v, const double* m, const double* h, const double* rho,
                      const double* pressure, const double* invomega, const double* zeta,
@@ -1074,7 +1115,7 @@ int orc_hydro_grav_forces_tree(const orc_params* p, const orc_tree* T, int N, co
   const int nd = p->ndim; const double kr = kern_range(p);
   pview P = { r, v, m, h, rho, pressure, invomega, zeta, sound, u, alpha, hfactor, hrangesqd, level };
   (void) dalphadt; (void) N;
-  if (p->gravity_mac != 0) return -1;
+  if (p->gravity_mac != 0 && (!T->atree && !T->gpot)) return -1;
 
   #pragma omp parallel
   {
@@ -1116,7 +1157,7 @@ int orc_hydro_grav_forces_tree(const orc_params* p, const orc_tree* T, int N, co
           }
         }
         else if (c->N == 0) cc = c->cnext;
-        else if (!(drsqd < c->cdistsqd)) {
+        else if (!open_cell_for_gravity(p, c, drsqd, cell->macfactor, cell->amin)) {
           if (c->copen == -1 && c->N == 1) {
             if (Ntdir == capp) { capp *= 2;
               cand = (int*) realloc(cand, sizeof(int)*capp); tdir = (int*) realloc(tdir, sizeof(int)*capp);

@@ -31,7 +31,7 @@ typedef struct orc_params {
   int periodic[3];       /* 1: periodic in that dimension                                          */
   int self_gravity;
   double thetamaxsqd;
-  int gravity_mac;       /* 0 geometric (only one restated so far)                                 */
+  int gravity_mac;       /* 0 geometric, 1 eigenmac, 2 gadget2 (Tree.h:413-432)                    */
   double macerror;
   int multipole;         /* 0 monopole 1 quadrupole 2 fast_monopole 3 fast_quadrupole              */
   int Nleafmax;
@@ -94,6 +94,10 @@ int orc_hydro_grav_forces_direct(const orc_params* p, int N, const double* r, co
 typedef struct orc_tree orc_tree;
 orc_tree* orc_tree_build(const orc_params* p, int N, const double* r, const double* v,
                          const double* m, const double* h);
+/* same with the previous step's atree [N][ndim] and gpot [N], which the gadget2 / eigenmac opening
+ * criteria read when the cells are stocked (KDTree.cpp:899-903); either may be NULL */
+orc_tree* orc_tree_build_mac(const orc_params* p, int N, const double* r, const double* v,
+                             const double* m, const double* h, const double* atree, const double* gpot);
 void orc_tree_free(orc_tree* t);
 int  orc_tree_ncell(const orc_tree* t);
 int  orc_tree_ltot(const orc_tree* t);

@@ -159,6 +159,25 @@ def case_sphere_grav_mono():
     return p, d
 
 
+def case_sphere_grav_gadget2():
+    """Gadget-2 relative opening criterion (Tree.h:413-432): the cells' amin comes from the atree the
+    reference's own setup force pass left in the particles (dens_in.atree)."""
+    ic = sphere_ic(2027, 2200)
+    p = base_params(3, self_gravity=1, multipole="quadrupole", gravity_mac="gadget2", macerror=5.0e-4,
+                    thetamaxsqd=0.5)
+    d, _ = refio.run_harness(p, ic=ic, perturb_h=0.05, dumps="setup,density,forces,neib,tree,gravlists")
+    return p, d
+
+
+def case_sphere_grav_eigen():
+    """eigenvalue opening criterion: cell.mac from the quadrupole, macfactor from the previous gpot."""
+    ic = sphere_ic(2028, 2100)
+    p = base_params(3, self_gravity=1, multipole="fast_quadrupole", gravity_mac="eigenmac", macerror=1.0e-3,
+                    thetamaxsqd=0.5)
+    d, _ = refio.run_harness(p, ic=ic, perturb_h=0.05, dumps="setup,density,forces,neib,tree,gravlists")
+    return p, d
+
+
 def case_box3d_mm97():
     """analytic (untabulated) M4, mm97 time-dependent viscosity, price2008 conductivity."""
     rng = np.random.default_rng(4321)
@@ -185,6 +204,8 @@ CASES = {
     "sphere_grav_quad": case_sphere_grav_quad,
     "sphere_grav_fastmono": case_sphere_grav_fastmono,
     "sphere_grav_mono": case_sphere_grav_mono,
+    "sphere_grav_gadget2": case_sphere_grav_gadget2,
+    "sphere_grav_eigen": case_sphere_grav_eigen,
     "box3d_mm97": case_box3d_mm97,
 }
 
@@ -198,6 +219,9 @@ def pack(params, d, keep_direct=False):
             key = "%s.%s" % (stage, f)
             if key in d:
                 out[key] = d[key]
+    if str(params.get("gravity_mac", "geometric")) != "geometric":
+        for f in ("atree", "gpot"):          # what the cells' amin / macfactor were stocked from
+            out["dens_in." + f] = d["dens_in." + f]
     for f in KEEP_FORCE_OUT:
         key = "force_out.%s" % f
         if key in d:

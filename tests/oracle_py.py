@@ -66,6 +66,8 @@ def lib():
         _lib.orc_star_grav_forces.argtypes = [P, C.c_int, _dp, _dp, C.c_int, _dp, _dp, _dp, _dp]
         _lib.orc_tree_build.restype = C.c_void_p
         _lib.orc_tree_build.argtypes = [P, C.c_int, _dp, _dp, _dp, _dp]
+        _lib.orc_tree_build_mac.restype = C.c_void_p
+        _lib.orc_tree_build_mac.argtypes = [P, C.c_int, _dp, _dp, _dp, _dp, C.c_void_p, C.c_void_p]
         _lib.orc_tree_free.restype = None
         _lib.orc_tree_free.argtypes = [C.c_void_p]
         _lib.orc_tree_ncell.restype = C.c_int
@@ -86,7 +88,7 @@ _KERNELS = {"m4": 0, "quintic": 1}
 _AVISC = {"none": 0, "mon97": 1, "mon97mm97": 2, "mon97cd2010": 3}
 _ACOND = {"none": 0, "wadsley2008": 1, "price2008": 2}
 _TDAVISC = {"none": 0, "mm97": 1, "cd2010": 2}
-_EOS = {"energy_eqn": 0, "constant_temp": 0, "isothermal": 1, "barotropic": 2}
+_EOS = {"energy_eqn": 0, "constant_temp": 0, "isothermal": 1, "barotropic": 2, "barotropic2": 3}
 _MULTIPOLE = {"monopole": 0, "quadrupole": 1, "fast_monopole": 2, "fast_quadrupole": 3}
 _MAC = {"geometric": 0, "eigenmac": 1, "gadget2": 2}
 
@@ -218,14 +220,19 @@ def star_grav_forces(p, r, h, rstar, mstar, hstar):
 
 
 class Tree:
-    def __init__(self, p, r, v, m, h):
+    def __init__(self, p, r, v, m, h, atree=None, gpot=None):
+        """atree / gpot: the previous step's values the gadget2 / eigenmac criteria read at stock time"""
         N = len(m)
         self.p, self.N = p, N
         # keep the arrays alive: the C tree stores pointers
         self._r = _c(r).reshape(N, p.ndim)
         self._v = _c(v).reshape(N, p.ndim)
         self._m, self._h = _c(m), _c(h)
-        self.ptr = lib().orc_tree_build(C.byref(p), N, self._r, self._v, self._m, self._h)
+        self._atree = None if atree is None else _c(atree).reshape(N, p.ndim)
+        self._gpot = None if gpot is None else _c(gpot)
+        self.ptr = lib().orc_tree_build_mac(C.byref(p), N, self._r, self._v, self._m, self._h,
+                                            None if self._atree is None else self._atree.ctypes.data,
+                                            None if self._gpot is None else self._gpot.ctypes.data)
         self.ncell = lib().orc_tree_ncell(self.ptr)
         self.ltot = lib().orc_tree_ltot(self.ptr)
 

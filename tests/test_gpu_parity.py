@@ -119,10 +119,16 @@ def test_kdtree_matches_reference(name):
 
 @pytest.mark.parametrize("name", GRAV)
 def test_gravity_forces_match_reference(name):
-    """UpdateAllSphForces (hydro + tree gravity) vs the reference: same tree -> same lists -> 1e-9."""
+    """UpdateAllSphForces (hydro + tree gravity) vs the reference: same tree -> same lists -> 1e-9.
+    gadget2 / eigenmac cases: the cells' amin / macfactor are stocked from the atree / gpot the
+    particles carried when the reference built its tree (dens_in.*), as KDTree.cpp:899-903 does."""
     params, d = load_golden(name)
     si, so = _by_iorig(stage(d, "force_in")), _by_iorig(stage(d, "force_out"))
     ps, tree = _make(params, si)
+    if "dens_in.atree" in d:
+        order = np.argsort(d["dens_in.iorig"])
+        ps["atree"][...] = d["dens_in.atree"][order]
+        ps["gpot"][...] = d["dens_in.gpot"][order]
     tree.BuildTree(True, 0, 1, 1, 0.0, ps)
     tree.ZeroAccelerations()
     tree.UpdateAllSphForces()
@@ -174,6 +180,7 @@ def _box_params(ndim, **kw):
     (1, 300, {"kernel": "quintic"}),
     (3, 16, {"gas_eos": "isothermal", "temp0": 2.0, "mu_bar": 1.3}),
     (3, 16, {"gas_eos": "barotropic", "temp0": 1.5, "mu_bar": 2.35, "rho_bary": 1.2, "gamma_eos": 1.4}),
+    (3, 16, {"gas_eos": "barotropic2", "temp0": 1.5, "mu_bar": 2.35, "rho_bary": 1.0, "gamma_eos": 1.4}),
 ])
 def test_full_step_vs_oracle(ndim, n, kw):
     """density -> hydro forces on a periodic jittered lattice, all option families, vs the oracle."""

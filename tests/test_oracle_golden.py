@@ -66,6 +66,14 @@ def test_hydro_forces(name):
     assert np.array_equal(out["levelneib"], so["levelneib"])
 
 
+def _mac_inputs(d):
+    """atree / gpot at tree-build time (the reference stocks amin / macfactor from them) by iorig"""
+    if "dens_in.atree" not in d:
+        return None, None
+    order = np.argsort(d["dens_in.iorig"])
+    return d["dens_in.atree"][order], d["dens_in.gpot"][order]
+
+
 @pytest.mark.parametrize("name", [c for c in GOLDEN_CASES if c.startswith("sphere_grav")])
 def test_kdtree_matches_reference(name):
     params, d = load_golden(name)
@@ -93,7 +101,8 @@ def test_tree_gravity_forces(name):
     p = orc.params_from_dict(params)
     si = _state_by_iorig(stage(d, "force_in"))
     so = _state_by_iorig(stage(d, "force_out"))
-    t = orc.Tree(p, si["r"], si["v"], si["m"], si["h"])
+    atree, gpot = _mac_inputs(d)
+    t = orc.Tree(p, si["r"], si["v"], si["m"], si["h"], atree, gpot)
     out = t.hydro_grav_forces(si)
     # interaction-list sizes equal the reference's
     nd_ref = np.diff(d["grav_in.direct_off"])
