@@ -74,7 +74,7 @@ class Stats(C.Structure):
 EXPORTS = [
     "gsph_default_config", "gsph_create", "gsph_destroy", "gsph_last_error", "gsph_upload", "gsph_download",
     "gsph_download_async", "gsph_set_stars", "gsph_tree_shard_range", "gsph_build_tree_shard_begin",
-    "gsph_build_tree_shard_finish",
+    "gsph_build_tree_shard_finish", "gsph_upload_range", "gsph_download_range", "gsph_device_array",
     "gsph_build_tree", "gsph_update_active_counters", "gsph_update_properties", "gsph_zero_accelerations",
     "gsph_update_hydro_forces", "gsph_update_all_forces", "gsph_get_hmax", "gsph_synchronize",
     "gsph_timer_start", "gsph_timer_stop", "gsph_set_active_slice", "gsph_density_pass", "gsph_refresh_hmax",
@@ -115,6 +115,10 @@ def lib():
     L.gsph_tree_shard_range.argtypes = [H, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.gsph_build_tree_shard_begin.argtypes = [H, C.c_int, C.c_int]
     L.gsph_build_tree_shard_finish.argtypes = [H]
+    L.gsph_upload_range.argtypes = [H, C.POINTER(ParticleView), C.c_int64, C.c_int64, C.c_int64]
+    L.gsph_download_range.argtypes = [H, C.POINTER(ParticleView), C.c_uint32, C.c_int64, C.c_int64, C.c_int]
+    L.gsph_device_array.argtypes = [H, C.c_int, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
+                                    C.POINTER(C.c_int32)]
     L.gsph_build_tree.argtypes = [H, C.c_int, C.c_double]
     for n in ("gsph_update_active_counters", "gsph_update_properties", "gsph_zero_accelerations",
               "gsph_update_hydro_forces", "gsph_synchronize", "gsph_timer_start", "gsph_density_pass",

@@ -125,6 +125,52 @@ class DomainDriver(object):
         torch.cuda.current_stream().synchronize()
         self.tree.RefreshHmax()
 
+    # ---- host <-> device for a multi-process host: every rank owns the host-order chunk ---------------
+    #      [rank*ceil(N/R), ...) of the particle set (what an MPI rank owns in the reference); it ships
+    #      and fetches only that chunk over PCIe, the rest travels GPU to GPU over NVLink.
+    _COMPONENTS = {"r": ("rx", "ry", "rz"), "v": ("vx", "vy", "vz"), "a": ("ax", "ay", "az"),
+                   "atree": ("atx", "aty", "atz")}
+
+    def _array_names(self, fields, ndim):
+        out = []
+        for f in fields:
+            out += list(self._COMPONENTS[f][:ndim]) if f in self._COMPONENTS else [f]
+        return out
+
+    def _gather_inplace(self, names, staging, n_valid):
+        import torch
+        import torch.distributed as dist
+        chunk = -(-int(n_valid) // self.world)
+        for name in names:
+            ptr, cap, es = self.tree.DeviceArray(name, staging=staging)
+            if cap < chunk * self.world:
+                raise RuntimeError("device arrays too small for the padded all-gather")
+            t = torch.as_tensor(_CudaArray(ptr, chunk * self.world, "<f8" if es == 8 else "<i4"), device="cuda")
+            dist.all_gather_into_tensor(t, t[self.rank * chunk:(self.rank + 1) * chunk], group=self.group)
+        torch.cuda.current_stream().synchronize()
+
+    def Upload(self, parts, only):
+        """inputs of one step: this rank's chunk over PCIe + one NVLink all-gather per array"""
+        if self.world == 1:
+            self.tree.Upload(parts, only=only)
+            return
+        lo, hi, _ = slice_bounds(parts.N, self.world, self.rank)
+        self.tree.UploadRange(parts, lo, hi, only=only)
+        self.tree.Synchronize()
+        self._gather_inplace(self._array_names(only, parts.ndim), True, parts.N)
+
+    def Download(self, parts, mask, only, gather=True, wait=True):
+        """results of this rank's chunk; gather=True first all-gathers the tree-order result slices
+        (the force fields; the density fields are already complete on every rank)"""
+        if self.world == 1:
+            self.tree.Download(parts, mask=mask, only=only, wait=wait)
+            return
+        if gather:
+            self.tree.Synchronize()
+            self._gather_inplace(self._array_names(only, parts.ndim), False, parts.N)
+        lo, hi, _ = slice_bounds(parts.N, self.world, self.rank)
+        self.tree.DownloadRange(parts, lo, hi, mask=mask, only=only, wait=wait)
+
     def ZeroAccelerations(self):
         self.tree.ZeroAccelerations()
 

@@ -135,6 +135,23 @@ class GpuSphTree(object):
         fn = self._L.gsph_download if wait else self._L.gsph_download_async
         self._check(fn(self._h, C.byref(pv), mask))
 
+    def UploadRange(self, parts, lo, hi, only=None):
+        """ship only the host-order particles [lo, hi) (gsph_upload_range): the share of this rank"""
+        pv = parts.view(only)
+        self._check(self._L.gsph_upload_range(self._h, C.byref(pv), parts.N, int(lo), int(hi)))
+
+    def DownloadRange(self, parts, lo, hi, mask=_capi.F_ALL, only=None, wait=True):
+        pv = parts.view(only)
+        self._check(self._L.gsph_download_range(self._h, C.byref(pv), mask, int(lo), int(hi), 1 if wait else 0))
+
+    def DeviceArray(self, name, staging=False):
+        """-> (device pointer, capacity in elements, element size) of one particle array, tree order
+        or host-order staging (gsph_device_array)"""
+        ptr, cap, es = C.c_void_p(), C.c_int64(), C.c_int32()
+        self._check(self._L.gsph_device_array(self._h, 1 if staging else 0, name.encode(), C.byref(ptr),
+                                              C.byref(cap), C.byref(es)))
+        return ptr.value, cap.value, es.value
+
     # ---- NeighbourSearch / SphNeighbourSearch surface -----------------------------------------------
     def BuildTree(self, rebuild_tree, n, ntreebuildstep, ntreestockstep, timestep, parts=None):
         """NeighbourSearch::BuildTree (HydroTree.cpp:310-372): rebuild | restock | extrapolate."""

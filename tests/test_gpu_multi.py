@@ -42,6 +42,25 @@ for workload, NP in (("cloud", 150000), ("glass", 64**3)):
         tree.Download(ps)
         st = tree.Stats(); tree.close()
         return ps, st
+    def run_chunked(world_, rank_):
+        # multi-process host: each rank ships / fetches only its host-order chunk (gsph_upload_range,
+        # gsph_download_range), the rest travels over NCCL
+        ps = fresh()
+        lo, hi, _ = domain.slice_bounds(N, world_, rank_)
+        for k in ("r", "v", "m", "h", "u"):            # this rank only KNOWS its own chunk
+            keep = ps[k][lo:hi].copy(); ps[k][...] = np.nan; ps[k][lo:hi] = keep
+        tree = g.GpuSphTree(params, device=lr)
+        drv = domain.DomainDriver(tree, rank_, world_)
+        drv.Upload(ps, only=("r", "v", "m", "h", "u"))
+        drv.BuildTree(True, 0, 1, 1, 0.0)
+        drv.UpdateAllSphProperties()
+        drv.Download(ps, mask=1, only=("h", "rho", "hrangesqd"), gather=False, wait=False)
+        drv.ZeroAccelerations()
+        drv.UpdateAllSphForces() if grav else drv.UpdateAllSphHydroForces()
+        drv.Download(ps, mask=2, only=("a", "dudt", "div_v", "levelneib") + (("atree", "gpot") if grav else ()), gather=True)
+        tree.Synchronize(); tree.close()
+        return ps, lo, hi
+    chunked, clo, chi = run_chunked(world, rank)
     multi, st = run(world, rank)
     # forces: every rank only wrote its own slice (other particles keep the uploaded zeros): sum over ranks
     tot = {}
@@ -57,6 +76,8 @@ for workload, NP in (("cloud", 150000), ("glass", 64**3)):
             assert np.array_equal(multi[f], single[f]), (workload, f)
         for f in tot:
             assert np.array_equal(tot[f], single[f]), (workload, f, np.abs(tot[f] - single[f]).max())
+        for f in ("h", "rho", "hrangesqd", "a", "dudt", "div_v") + (("atree", "gpot") if grav else ()):
+            assert np.array_equal(chunked[f][clo:chi], single[f][clo:chi]), (workload, "chunked", f)
         print("multi-GPU parity ok:", workload, N, "particles, world", world)
 dist.barrier()
 """
