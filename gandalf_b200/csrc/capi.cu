@@ -354,7 +354,7 @@ void gsph_destroy(gsph_handle* h)
   auto fre = [](void* p) { if (p) cudaFree(p); };
   for (int f = 0; f < NF_DOUBLE; f++) { fre(h->H[f]); fre(h->P[f]); }
   for (int f = 0; f < NF_INT; f++) { fre(h->HI[f]); fre(h->PI[f]); }
-  fre(h->perm); fre(h->tables); fre(h->scratch); fre(h->cand); fre(h->gravlist); fre(h->status); fre(h->work_counter); fre(h->done); fre(h->geo4); fre(h->geoh); fre(h->frec); fre(h->nlist); fre(h->hnew); fre(h->stars);
+  fre(h->perm); fre(h->tables); fre(h->scratch); fre(h->cand); fre(h->gravlist); fre(h->status); fre(h->work_counter); fre(h->done); fre(h->geo4); fre(h->geoh); fre(h->frec); fre(h->nlist); fre(h->hnew); fre(h->stars); fre(h->gstack);
   TreeDev& T = h->tree;
   fre(T.first); fre(T.count); fre(T.nactive); fre(T.m); fre(T.rmax); fre(T.hmax); fre(T.cdistsqd);
   for (int k = 0; k < 3; k++) { fre(T.bbmin[k]); fre(T.bbmax[k]); fre(T.hbmin[k]); fre(T.hbmax[k]); fre(T.rcell[k]); fre(T.com[k]); fre(T.vcom[k]); }
@@ -713,6 +713,7 @@ int gsph_update_active_counters(gsph_handle* h)
   return GSPH_OK;
 }
 
+static int pass_gravity(gsph_handle* h, int);
 static int run_with_regrow(gsph_handle* h, const char* where, int (*pass)(gsph_handle*, int), int arg)
 {
   /* a cohort whose candidate list overflows its scratch slot is skipped and flagged (nothing of it
@@ -722,6 +723,23 @@ static int run_with_regrow(gsph_handle* h, const char* where, int (*pass)(gsph_h
   for (int attempt = 0; attempt < 8; attempt++) {
     int rc = pass(h, arg);
     if (rc) return rc;
+    if (pass == pass_gravity) {
+      /* a gravity walk that outgrew its shared-memory stack: redo the unfinished cohorts with stacks
+         in HBM (16 Ki entries per warp, quadrupled on every further overflow) */
+      rc = fetch_status(h);
+      if (rc) return rc;
+      if (h->status_host->err_stack_overflow && attempt < 5) {
+        if (!h->gstack_on && h->gstack_cap) h->gstack_on = true;        /* buffers of an earlier step */
+        else {
+          h->gstack_cap = h->gstack_cap ? h->gstack_cap*4 : 16384;
+          if (h->gstack) cudaFree(h->gstack);
+          h->gstack = nullptr; h->gstack_warps = 0;
+          h->gstack_on = true;
+        }
+        CUDA_TRY(h, cudaMemsetAsync(&h->status->err_stack_overflow, 0, sizeof(int), h->stream));
+        continue;
+      }
+    }
     rc = gsph_check_status(h, where);
     if (rc) return rc;
     const DevStatus& s = *h->status_host;
@@ -934,6 +952,7 @@ int gsph_update_all_forces(gsph_handle* h, const double* stars, int Nstar)
   if (rc) return rc;
   const DevStatus keep = *h->status_host;
   rc = gsph_prepare_done_flags(h); if (rc) return rc;
+  h->gstack_on = false;                               /* first launch: shared-memory stacks */
   rc = run_with_regrow(h, "gsph_update_all_forces(gravity)", pass_gravity, 0);
   if (rc) return rc;
   rc = gsph_run_star_forces(h);                       /* GradhSphTree.cpp:600-607 */

@@ -75,7 +75,7 @@ struct FastMp { double ac[3], q[6], pot; };   /* dphi == ac for HoT = false */
 template <int MULTIPOLE, int T, bool GEOMAC>
 __global__ void __launch_bounds__(GRAV_THREADS, (T == 1 && MULTIPOLE != GSPH_MULTIPOLE_FAST_QUADRUPOLE) ? GRAV_MINBLOCKS : 2)
 gravity_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* work_counter,
-               DevStatus* st, uint8_t* done)
+               DevStatus* st, uint8_t* done, int2* gstack, int gstack_cap, int smem_stack_cap)
 {
   extern __shared__ char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -84,6 +84,10 @@ gravity_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* wo
   const int leaf0 = (1 << tree.ltot) - 1;
   const int ncohort = 1 << cohort_level;
   const int nl = 1 << (tree.ltot - cohort_level);          /* leaves per cohort (<= 8) */
+  /* walk stack: shared memory; a cohort whose walk outgrows it is redone by a second launch whose
+     stacks live in HBM (gstack) -- deep, strongly clustered trees never fail, they only get slower */
+  int2* const stk = gstack ? gstack + (size_t)(blockIdx.x*GRAV_WARPS + warp)*gstack_cap : S.stack;
+  const int stkcap = gstack ? gstack_cap : smem_stack_cap;
   const int myl = lane >> 2, sub = lane & 3;               /* my leaf inside the cohort, my slot */
   constexpr int DIR_TILE = DIR_PART/(4*T);               /* direct leaves per tile (<= 4*T particles each) */
   static_assert(DIR_TILE <= DIR_TILE_MAX, "direct tile");
@@ -323,14 +327,14 @@ gravity_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* wo
     int sp = 0, ncb = 0, ndb = 0;
     bool failed = false;
     if (rootmask) {
-      if (lane == 0) S.stack[0] = make_int2(0, (int) rootmask);
+      if (lane == 0) stk[0] = make_int2(0, (int) rootmask);
       sp = 1;
     }
     __syncwarp();
     while (sp > 0) {
       const int take = sp < 32 ? sp : 32;
       int node = -1; unsigned mask = 0;
-      if (lane < take) { const int2 e = S.stack[sp - 1 - lane]; node = e.x; mask = (unsigned) e.y; }
+      if (lane < take) { const int2 e = stk[sp - 1 - lane]; node = e.x; mask = (unsigned) e.y; }
       sp -= take;
       __syncwarp();
       unsigned open_mask = 0, acc_mask = 0;
@@ -382,11 +386,11 @@ gravity_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* wo
       const bool push = open_mask && !isleaf;
       const unsigned pm = __ballot_sync(FULLMASK, push);
       const int npush = __popc(pm);
-      if (sp + 2*npush > GRAV_STACK) { failed = true; break; }
+      if (sp + 2*npush > stkcap) { failed = true; break; }
       if (push) {
         const int off = __popc(pm & ((1u << lane) - 1u));
-        S.stack[sp + 2*off] = make_int2(2*node + 2, (int) open_mask);
-        S.stack[sp + 2*off + 1] = make_int2(2*node + 1, (int) open_mask);
+        stk[sp + 2*off] = make_int2(2*node + 2, (int) open_mask);
+        stk[sp + 2*off + 1] = make_int2(2*node + 1, (int) open_mask);
       }
       sp += 2*npush;
       /* queue accepted cells / direct leaves */
@@ -487,7 +491,21 @@ int launch_gravity_t(gsph_handle* h)
   for (int k = 0; k < NF_DOUBLE; k++) P.f[k] = h->P[k];
   for (int k = 0; k < NF_INT; k++) P.i[k] = h->PI[k];
   KernelTimer kt(h, 2);
-  kern<<<blocks, GRAV_THREADS, smem, h->stream>>>(P, h->tree, h->dp, Lg, h->work_counter, h->status, h->done);
+  int2* gstack = nullptr;
+  /* GSPH_TEST_GRAV_STACK=n shrinks the shared-memory stack so that the tests can exercise the retry */
+  const char* tcap = getenv("GSPH_TEST_GRAV_STACK");
+  const int smem_stack_cap = tcap ? std::max(40, std::min(GRAV_STACK, atoi(tcap))) : GRAV_STACK;
+  if (h->gstack_on) {                                  /* retry after a stack overflow: stacks in HBM */
+    if (h->gstack_warps < blocks*GRAV_WARPS) {
+      if (h->gstack) cudaFree(h->gstack);
+      h->gstack = nullptr; h->gstack_warps = 0;
+      CUDA_TRY(h, cudaMalloc(&h->gstack, (size_t) blocks*GRAV_WARPS*h->gstack_cap*sizeof(int2)));
+      h->gstack_warps = blocks*GRAV_WARPS;
+    }
+    gstack = h->gstack;
+  }
+  kern<<<blocks, GRAV_THREADS, smem, h->stream>>>(P, h->tree, h->dp, Lg, h->work_counter, h->status, h->done,
+                                                  gstack, (int) h->gstack_cap, smem_stack_cap);
   h->stats.kernel_launches++;
   CUDA_TRY(h, cudaGetLastError());
   return GSPH_OK;

@@ -147,6 +147,9 @@ struct gsph_handle {
   int32_t* cand = nullptr; size_t cand_cap_per_warp = 0; int cand_warps = 0;
   int32_t* nlist = nullptr; size_t nlist_cap = 0; int nlist_warps = 0;   /* per warp: [cap][32] neighbour ids */
   int32_t* gravlist = nullptr; size_t grav_cap_cells = 0, grav_cap_direct = 0; int grav_warps = 0;
+  bool gstack_on = false;        /* this launch is a retry with the stacks in HBM */
+  int2* gstack = nullptr; size_t gstack_cap = 0; int gstack_warps = 0;   /* gravity walk stacks in HBM: only after a
+                                                                            shared-memory stack overflowed */
   DevStatus* status = nullptr;  /* device */
   DevStatus* status_host = nullptr; /* pinned */
   int* work_counter = nullptr;

@@ -446,3 +446,31 @@ def test_star_gravity_vs_oracle(grav, tab):
     assert np.abs((res[1]["atree"] - res[0]["atree"]) - atree).max() < 1e-9*scale
     assert np.abs((res[1]["a"] - res[0]["a"]) - a).max() < 1e-9*scale
     assert np.abs((res[1]["gpot"] - res[0]["gpot"]) - gpot).max() < 1e-9*np.abs(gpot).max()
+
+
+def test_gravity_walk_stack_overflow_retries_in_hbm(monkeypatch):
+    """a gravity walk that outgrows its shared-memory stack is redone with the stack in HBM: same
+    traversal, bit-identical forces (GSPH_TEST_GRAV_STACK shrinks the shared stack to force the retry)."""
+    import gandalf_b200 as g
+    rng = np.random.default_rng(21)
+    N = 30000
+    rad = rng.uniform(0, 1, N)**(1/2.5)
+    dirs = rng.normal(size=(N, 3)); dirs /= np.linalg.norm(dirs, axis=1)[:, None]
+    r = dirs*rad[:, None]
+    v = np.zeros((N, 3)); m = np.full(N, 1.0/N); u = np.full(N, 0.05); h = np.full(N, 0.07)
+    params = {"ndim": 3, "self_gravity": 1, "multipole": "fast_monopole", "thetamaxsqd": 0.15}
+    res = []
+    for cap in (None, "40"):
+        if cap is None:
+            monkeypatch.delenv("GSPH_TEST_GRAV_STACK", raising=False)
+        else:
+            monkeypatch.setenv("GSPH_TEST_GRAV_STACK", cap)
+        ps = g.ParticleSet(N, 3).set(r=r, v=v, m=m, h=h, u=u)
+        tree = g.GpuSphTree(params)
+        tree.BuildTree(True, 0, 1, 1, 0.0, ps)
+        tree.UpdateAllSphProperties(); tree.ZeroAccelerations(); tree.UpdateAllSphForces()
+        tree.Download(ps)
+        res.append({k: ps[k].copy() for k in ("a", "atree", "gpot")})
+        tree.close()
+    for k in res[0]:
+        assert np.array_equal(res[0][k], res[1][k]), k
