@@ -171,6 +171,13 @@ void fill_devparams(gsph_handle* h)
     d.periodic[k] = (k < c.ndim && c.boundary_lhs[k] == GSPH_BOUNDARY_PERIODIC) ? 1 : 0;
     d.any_periodic |= d.periodic[k];
   }
+  d.any_mirror = 0; d.nimg = 1;
+  for (int k = 0; k < 3; k++) {
+    d.mirror[k][0] = (k < c.ndim && c.boundary_lhs[k] == GSPH_BOUNDARY_MIRROR) ? 1 : 0;
+    d.mirror[k][1] = (k < c.ndim && c.boundary_rhs[k] == GSPH_BOUNDARY_MIRROR) ? 1 : 0;
+    d.any_mirror |= d.mirror[k][0] | d.mirror[k][1];
+    d.nimg *= 1 + d.mirror[k][0] + d.mirror[k][1];
+  }
   d.hydro_forces = c.hydro_forces; d.self_gravity = c.self_gravity; d.multipole = c.multipole;
   d.gravity_mac = c.gravity_mac; d.thetamaxsqd = c.thetamaxsqd; d.invthetamaxsqd = 1.0/c.thetamaxsqd;
   d.macerror = c.macerror; d.Nleafmax = c.Nleafmax; d.create_sinks = c.create_sinks;
@@ -186,8 +193,9 @@ int validate_config(const gsph_config* c, std::string& err)
   if (c->eos < GSPH_EOS_ADIABATIC || c->eos > GSPH_EOS_BAROTROPIC2) { err = "gas_eos is not on the accelerated path"; return GSPH_EINVAL; }
   if (c->tdavisc != GSPH_TDAVISC_NONE && c->tdavisc != GSPH_TDAVISC_MM97) { err = "time_dependent_avisc = cd2010 is not on the accelerated path"; return GSPH_EINVAL; }
   for (int k = 0; k < c->ndim; k++) {
-    if (c->boundary_lhs[k] == GSPH_BOUNDARY_MIRROR || c->boundary_rhs[k] == GSPH_BOUNDARY_MIRROR) {
-      err = "mirror boundaries are not on the accelerated path"; return GSPH_EINVAL;
+    if ((c->boundary_lhs[k] == GSPH_BOUNDARY_MIRROR || c->boundary_rhs[k] == GSPH_BOUNDARY_MIRROR)) {
+      if (c->self_gravity) { err = "self-gravity with mirror boundaries is not supported (the reference asserts it, Tree.cpp:636)"; return GSPH_EINVAL; }
+      if (!(c->boxmax[k] > c->boxmin[k])) { err = "mirror dimension needs boxmax > boxmin"; return GSPH_EINVAL; }
     }
     if ((c->boundary_lhs[k] == GSPH_BOUNDARY_PERIODIC) != (c->boundary_rhs[k] == GSPH_BOUNDARY_PERIODIC)) {
       err = "periodic boundaries must be set on both sides of a dimension"; return GSPH_EINVAL;
@@ -387,6 +395,7 @@ static int upload_impl(gsph_handle* h, const gsph_particle_view* view, int64_t N
   if (!h) return GSPH_EINVAL;
   if (!view || N <= 0 || N > 2000000000ll) { h->err = "gsph_upload: bad arguments"; return GSPH_EINVAL; }
   if (r0 < 0 || r1 < r0 || r1 > N) { h->err = "gsph_upload_range: bad range"; return GSPH_EINVAL; }
+  if (h->dp.any_mirror && N > (int64_t) 1 << 26) { h->err = "mirror boundaries support at most 2^26 particles (image codes live in the upper id bits)"; return GSPH_EINVAL; }
   const bool whole = (r0 == 0 && r1 == N);
   const int64_t nr = r1 - r0;
   cudaSetDevice(h->device);

@@ -32,6 +32,7 @@ struct GatherVisitorF {
   const float4* __restrict__ nodeb; const WalkBox& wb; CandList& cl;
   float smin[3], smax[3];
   int first, count;
+  int tag;                          /* image code << IMG_SHIFT of the walk (mirror boundaries) */
   __device__ __forceinline__ int test(int nd, bool)
   {
     const float4 lo = nodeb[2*(size_t) nd], hi = nodeb[2*(size_t) nd + 1];
@@ -40,7 +41,7 @@ struct GatherVisitorF {
     bool wrapped = false;
     return fboxes_overlap<NDIM>(wb, smin, smax, lo, hi, wrapped) ? 1 : 0;
   }
-  __device__ __forceinline__ bool emit(bool take, int lane) { return cand_append_range(cl, first, count, take, lane); }
+  __device__ __forceinline__ bool emit(bool take, int lane) { return cand_append_range(cl, first, count, take, lane, tag); }
 };
 
 /* EOS: src/Headers/EOS.h:156, src/Thermal/{Adiabatic,Isothermal,Barotropic}EOS.cpp */
@@ -80,7 +81,7 @@ template <int NDIM> __device__ __forceinline__ double pow_ndim(double x)
  *  phase 2  the ComputeH fixed-point iteration runs over the lane's own list only (gathering the
  *           32-byte records through L1/L2), so every lane does useful work in every instruction.
  *-----------------------------------------------------------------------------------------------*/
-template <int NDIM, int KERN, bool TAB>
+template <int NDIM, int KERN, bool TAB, bool MIRROR>
 __global__ void __launch_bounds__(DENS_THREADS, 3)
 density_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict__ gtables,
                const double2* __restrict__ geo4, int cohort_level, int* work_counter,
@@ -161,18 +162,38 @@ density_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict_
         if (!(hmax > 0.0)) break;                              /* every lane is finished */
         /* ---- walk: candidates whose leaf overlaps the grown cohort box --------------------------*/
         CandList cl{cand, cand_cap, 0, st};
-        GatherVisitorF<NDIM> V{tree.nodeb, wbx, cl, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, 0, 0};
+        GatherVisitorF<NDIM> V{tree.nodeb, wbx, cl, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, 0, 0, 0};
         const double R = dp.kernrange*hmax;
         bool crosses = false, wide = false;
 #pragma unroll
         for (int k = 0; k < NDIM; k++) {
           const double lo = cmin[k] - R, hi = cmax[k] + R;
-          V.smin[k] = __double2float_rd(lo); V.smax[k] = __double2float_ru(hi);
           if (dp.periodic[k] && (lo < dp.boxmin[k] || hi > dp.boxmax[k] || hi - lo > dp.boxhalf[k])) crosses = true;
           if (dp.periodic[k] && 0.5*(hi - lo) >= 0.49*dp.boxsize[k]) wide = true;
         }
-        __syncwarp();
-        if (!warp_walk_f<NB_WALK_STACK>(tree.ltot, stack, V, st)) { overflow = true; break; }
+        /* one walk per image code (mirror walls): the search box is reflected instead of the tree */
+        bool walk_ok = true;
+        for (int code = 0; code < (MIRROR ? dp.nimg : 1) && walk_ok; code++) {
+          const ImageOp op = image_op<NDIM>(dp, code);
+          bool reach = true;
+#pragma unroll
+          for (int k = 0; k < NDIM; k++) {
+            double lo = cmin[k] - R, hi = cmax[k] + R;
+            if (op.refl[k]) {
+              /* the image lies beyond the wall: only needed if the search box crosses that wall */
+              const double w = 0.5*op.wall2[k];
+              if (!(lo < w && hi > w) && !(lo <= w && hi >= w)) reach = false;
+              const double l2 = op.wall2[k] - hi, h2 = op.wall2[k] - lo;
+              lo = l2; hi = h2;
+            }
+            V.smin[k] = __double2float_rd(lo); V.smax[k] = __double2float_ru(hi);
+          }
+          if (!reach) continue;
+          V.tag = code << IMG_SHIFT;
+          __syncwarp();
+          walk_ok = warp_walk_f<NB_WALK_STACK>(tree.ltot, stack, V, st);
+        }
+        if (!walk_ok) { overflow = true; break; }
         const int ncand = cl.n;
 
         /* ---- phase 1: per-lane candidate lists on the FP32 pipe.  The list only has to be a SUPERSET
@@ -203,11 +224,18 @@ density_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict_
             float fx = __int_as_float(0x7f800000), fy = 0.f, fz = 0.f;
             if (jl < ncand) {
               j = cand[jl];
-              const double2 a = geo4[2*(size_t) j], b = geo4[2*(size_t) j + 1];
+              const int jp = MIRROR ? (j & IMG_MASK) : j;
+              const double2 a = geo4[2*(size_t) jp], b = geo4[2*(size_t) jp + 1];
+              double xs[3] = {a.x, a.y, b.x};
+              if (MIRROR && (j >> IMG_SHIFT)) {
+                const ImageOp op = image_op<NDIM>(dp, j >> IMG_SHIFT);
+#pragma unroll
+                for (int k = 0; k < NDIM; k++) xs[k] = reflect_coord(op, k, xs[k]);
+              }
               double dr[3] = {0, 0, 0};
-              dr[0] = a.x - 0.5*(cmin[0] + cmax[0]);
-              if (NDIM > 1) dr[1] = a.y - 0.5*(cmin[1] + cmax[1]);
-              if (NDIM > 2) dr[2] = b.x - 0.5*(cmin[2] + cmax[2]);
+              dr[0] = xs[0] - 0.5*(cmin[0] + cmax[0]);
+              if (NDIM > 1) dr[1] = xs[1] - 0.5*(cmin[1] + cmax[1]);
+              if (NDIM > 2) dr[2] = xs[2] - 0.5*(cmin[2] + cmax[2]);
               if (dp.any_periodic) wrap_dr<NDIM>(dp, dr);
               if (b.y > 0.0) fx = (float)(dr[0]*sc);
               fy = (float)(dr[1]*sc); fz = (float)(dr[2]*sc);
@@ -240,7 +268,7 @@ density_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict_
           for (int r = 0; r < 2; r++) {
             const int src = r*16 + (lane >> 1);
             const int jj = __shfl_sync(FULLMASK, jv, src);
-            if (jj >= 0) cp_async16(buf + DENS_UNIT(src, lane & 1), geo4 + 2*(size_t) jj + (lane & 1));
+            if (jj >= 0) cp_async16(buf + DENS_UNIT(src, lane & 1), geo4 + 2*(size_t)(MIRROR ? (jj & IMG_MASK) : jj) + (lane & 1));
           }
           cp_async_commit();
         };
@@ -265,10 +293,16 @@ density_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict_
             __syncwarp();
             if (jc >= 0) {
               const double2 a = buf[DENS_UNIT(lane, 0)], b = buf[DENS_UNIT(lane, 1)];
+              double xs[3] = {a.x, a.y, b.x};
+              if (MIRROR && (jc >> IMG_SHIFT)) {          /* a mirror image: 2*wall - r_k */
+                const ImageOp op = image_op<NDIM>(dp, jc >> IMG_SHIFT);
+#pragma unroll
+                for (int k = 0; k < NDIM; k++) xs[k] = reflect_coord(op, k, xs[k]);
+              }
               double dr[3] = {0, 0, 0};
-              dr[0] = a.x - x[0];
-              if (NDIM > 1) dr[1] = a.y - x[1];
-              if (NDIM > 2) dr[2] = b.x - x[2];
+              dr[0] = xs[0] - x[0];
+              if (NDIM > 1) dr[1] = xs[1] - x[1];
+              if (NDIM > 2) dr[2] = xs[2] - x[2];
               if (crosses) wrap_dr<NDIM>(dp, dr);
               const double ssqd = __dmul_rn(invhsqd, dot_exact<NDIM>(dr));
               if (ssqd < krs) {
@@ -358,13 +392,13 @@ density_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict_
   }
 }
 
-template <int NDIM, int KERN, bool TAB>
-int launch_density(gsph_handle* h)
+template <int NDIM, int KERN, bool TAB, bool MIRROR>
+int launch_density_m(gsph_handle* h)
 {
   const int Lc = cohort_level_for(h->N, h->tree.ltot, 32);
   static_assert(DENS_WARP_D2*sizeof(double2) >= NB_WALK_STACK*sizeof(int), "walk stack must fit the stage region");
   const size_t smem = (TAB ? 3*GSPH_TABLE_RES*sizeof(double) : 0) + DENS_WARPS*DENS_WARP_D2*sizeof(double2);
-  auto kern = density_kernel<NDIM, KERN, TAB>;
+  auto kern = density_kernel<NDIM, KERN, TAB, MIRROR>;
   CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   int bps = 0;
   CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, DENS_THREADS, smem));
@@ -388,6 +422,13 @@ int launch_density(gsph_handle* h)
   h->stats.kernel_launches++;
   CUDA_TRY(h, cudaGetLastError());
   return GSPH_OK;
+}
+
+template <int NDIM, int KERN, bool TAB>
+int launch_density(gsph_handle* h)
+{
+  /* mirror walls are a separate instantiation: boxes without them pay nothing for the image codes */
+  return h->dp.any_mirror ? launch_density_m<NDIM, KERN, TAB, true>(h) : launch_density_m<NDIM, KERN, TAB, false>(h);
 }
 
 template <int NDIM>

@@ -395,8 +395,48 @@ __device__ __forceinline__ bool warp_walk_f(int leaf_level, int* stack, Visitor&
   return true;
 }
 
+/*------------------------------------------------------------------------------------------------
+ * Mirror boundaries.  The reference materialises mirror images as ghost particles for the density
+ * pass (Hydrodynamics.cpp:217-290) and builds them on the fly in the force pass
+ * (GhostNeighbourFinder::ConstructGhostsScatterGather, GhostNeighbours.hpp:252-268,411-450):
+ * r_k -> 2*wall - r_k, v_k -> -v_k, images of images across dimensions.  Here an image is a
+ * candidate id tagged with an IMAGE CODE (mixed-radix digit per dimension: 0 none, then lhs, rhs as
+ * far as that wall is a mirror) in bits 26..30; code 0 is the real particle.  The walks are repeated
+ * with the reflected search boxes (a reflection is an isometry, so "image of the node meets the box"
+ * = "node meets the image of the box").
+ *-----------------------------------------------------------------------------------------------*/
+#define IMG_SHIFT 26
+#define IMG_MASK ((1 << IMG_SHIFT) - 1)
+
+struct ImageOp { int refl[3]; double wall2[3]; };       /* reflected in dimension k; 2*wall */
+
+template <int NDIM>
+__device__ __forceinline__ ImageOp image_op(const DevParams& dp, int code)
+{
+  ImageOp op;
+#pragma unroll
+  for (int k = 0; k < 3; k++) { op.refl[k] = 0; op.wall2[k] = 0.0; }
+#pragma unroll
+  for (int k = 0; k < NDIM; k++) {
+    const int radix = 1 + dp.mirror[k][0] + dp.mirror[k][1];
+    const int dgt = code % radix;
+    code /= radix;
+    if (dgt) {
+      op.refl[k] = 1;
+      op.wall2[k] = 2.0*((dgt == 1 && dp.mirror[k][0]) ? dp.boxmin[k] : dp.boxmax[k]);
+    }
+  }
+  return op;
+}
+
+/* 2*x_mirror - r, Particle.h:603-607 (one rounding, like the reference) */
+__device__ __forceinline__ double reflect_coord(const ImageOp& op, int k, double x)
+{
+  return op.refl[k] ? __dadd_rn(op.wall2[k], -x) : x;
+}
+
 /* append the slab [first, first+cnt) of every lane with take = true to the candidate list */
-__device__ __forceinline__ bool cand_append_range(CandList& cl, int first, int cnt, bool take, int lane)
+__device__ __forceinline__ bool cand_append_range(CandList& cl, int first, int cnt, bool take, int lane, int tag = 0)
 {
   if (!take) cnt = 0;
   int total;
@@ -406,7 +446,7 @@ __device__ __forceinline__ bool cand_append_range(CandList& cl, int first, int c
     if (lane == 0) { atomicExch(&cl.st->err_cand_overflow, 1); atomicMax(&cl.st->cand_need, (unsigned long long)(cl.n + total)); }
     return false;
   }
-  for (int i = 0; i < cnt; i++) cl.list[cl.n + off + i] = first + i;
+  for (int i = 0; i < cnt; i++) cl.list[cl.n + off + i] = (first + i) | tag;
   cl.n += total;
   return true;
 }

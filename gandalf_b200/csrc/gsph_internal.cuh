@@ -84,6 +84,8 @@ struct DevParams {
   double boxmin[3], boxmax[3], boxsize[3], boxhalf[3];
   int periodic[3];
   int any_periodic;
+  int mirror[3][2];          /* mirror wall on the lhs / rhs of dimension k                           */
+  int any_mirror, nimg;      /* nimg = prod_k (1 + mirror[k][0] + mirror[k][1]): image codes, 0 = the real particle */
   int hydro_forces, self_gravity, multipole, gravity_mac;
   double thetamaxsqd, invthetamaxsqd, macerror;
   int Nleafmax;

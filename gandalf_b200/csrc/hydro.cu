@@ -75,12 +75,25 @@ struct ScatterGatherVisitorF {
   float bmin[3], bmax[3], hmin[3], hmax[3];
   bool needwrap;
   int first, count;
+  int tag;                          /* image code << IMG_SHIFT of the walk (mirror boundaries) */
   __device__ __forceinline__ void set_boxes(int n)
   {
     const float4 lo = nodeb[2*(size_t) n], hi = nodeb[2*(size_t) n + 1];
     const float4 hlo = nodeh[2*(size_t) n], hhi = nodeh[2*(size_t) n + 1];
     bmin[0] = lo.x; bmin[1] = lo.y; bmin[2] = lo.z; bmax[0] = hi.x; bmax[1] = hi.y; bmax[2] = hi.z;
     hmin[0] = hlo.x; hmin[1] = hlo.y; hmin[2] = hlo.z; hmax[0] = hhi.x; hmax[1] = hhi.y; hmax[2] = hhi.z;
+  }
+  /* the cohort's boxes seen through a mirror: "image of a node meets the cohort" = "node meets the
+     image of the cohort" (outward rounding of the reflected float bounds) */
+  __device__ __forceinline__ void reflect_boxes(const ImageOp& op)
+  {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      if (!op.refl[k]) continue;
+      const float lo = __double2float_rd(op.wall2[k] - (double) bmax[k]), hi = __double2float_ru(op.wall2[k] - (double) bmin[k]);
+      const float hlo = __double2float_rd(op.wall2[k] - (double) hmax[k]), hhi = __double2float_ru(op.wall2[k] - (double) hmin[k]);
+      bmin[k] = lo; bmax[k] = hi; hmin[k] = hlo; hmax[k] = hhi;
+    }
   }
   __device__ __forceinline__ int test(int nd, bool leaf)
   {
@@ -96,7 +109,7 @@ struct ScatterGatherVisitorF {
     if (open && leaf && wrapped) needwrap = true;
     return open ? 1 : 0;
   }
-  __device__ __forceinline__ bool emit(bool take, int lane) { return cand_append_range(cl, first, count, take, lane); }
+  __device__ __forceinline__ bool emit(bool take, int lane) { return cand_append_range(cl, first, count, take, lane, tag); }
 };
 
 struct Target {
@@ -222,7 +235,7 @@ __device__ __forceinline__ void pair_terms(const DevParams& dp, const KE& K, Tar
  *           lane reads its own record, applies the reference's predicate (NeighbourManager.h:521)
  *           in exact FP64 arithmetic and evaluates the pair terms.
  *-----------------------------------------------------------------------------------------------*/
-template <int NDIM, int KERN, bool TAB, bool GRAV, bool HYDRO>
+template <int NDIM, int KERN, bool TAB, bool GRAV, bool HYDRO, bool MIRROR>
 __global__ void __launch_bounds__(HYD_THREADS, 2)
 hydro_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict__ gtables,
              const double2* __restrict__ frec, const double2* __restrict__ geoh, int aux_is_alpha,
@@ -267,7 +280,7 @@ hydro_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict__ 
     /* ---- walk ---------------------------------------------------------------------------------*/
     CandList cl{cand, cand_cap, 0, st};
     ScatterGatherVisitorF<NDIM> V{tree.nodeb, tree.nodeh, wbx, cl, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f},
-                                  {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, false, 0, 0};
+                                  {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, false, 0, 0, 0};
     double ctr[3] = {0, 0, 0}, diag2 = 0.0;
     bool wide = false;                /* periodic images not unique about the cohort centre: keep all */
     V.set_boxes(node);
@@ -280,7 +293,16 @@ hydro_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict__ 
       if (dp.periodic[k] && hw + rootR >= 0.49*dp.boxsize[k]) wide = true;
     }
     __syncwarp();
-    if (!warp_walk_f<NB_WALK_STACK>(tree.ltot, stack, V, st)) continue;
+    bool walk_ok = warp_walk_f<NB_WALK_STACK>(tree.ltot, stack, V, st);
+    /* mirror walls: one more walk per image code with the cohort's boxes reflected */
+    for (int code = 1; code < (MIRROR ? dp.nimg : 1) && walk_ok; code++) {
+      V.set_boxes(node);
+      V.reflect_boxes(image_op<NDIM>(dp, code));
+      V.tag = code << IMG_SHIFT;
+      __syncwarp();
+      walk_ok = warp_walk_f<NB_WALK_STACK>(tree.ltot, stack, V, st);
+    }
+    if (!walk_ok) continue;
     const int ncand = cl.n;
     const bool wrap = dp.any_periodic && __any_sync(FULLMASK, V.needwrap);
     bool overflow = false;
@@ -336,11 +358,18 @@ hydro_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict__ 
           float fx = __int_as_float(0x7f800000), fy = 0.f, fz = 0.f, fw = -1.0f;
           if (jl < ncand) {
             j = cand[jl];
-            const double2 a = geoh[2*(size_t) j], b = geoh[2*(size_t) j + 1];
+            const int jp = MIRROR ? (j & IMG_MASK) : j;
+            const double2 a = geoh[2*(size_t) jp], b = geoh[2*(size_t) jp + 1];
+            double xs[3] = {a.x, a.y, b.x};
+            if (MIRROR && (j >> IMG_SHIFT)) {
+              const ImageOp op = image_op<NDIM>(dp, j >> IMG_SHIFT);
+#pragma unroll
+              for (int k = 0; k < NDIM; k++) xs[k] = reflect_coord(op, k, xs[k]);
+            }
             double dr[3] = {0, 0, 0};
-            dr[0] = a.x - ctr[0];
-            if (NDIM > 1) dr[1] = a.y - ctr[1];
-            if (NDIM > 2) dr[2] = b.x - ctr[2];
+            dr[0] = xs[0] - ctr[0];
+            if (NDIM > 1) dr[1] = xs[1] - ctr[1];
+            if (NDIM > 2) dr[2] = xs[2] - ctr[2];
             if (dp.any_periodic) wrap_dr<NDIM>(dp, dr);
             if (b.y > 0.0) { fx = (float)(dr[0]*sc); fw = __double2float_ru(b.y*sc2); }
             fy = (float)(dr[1]*sc); fz = (float)(dr[2]*sc);
@@ -373,7 +402,7 @@ hydro_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict__ 
         for (int r = 0; r < 8; r++) {
           const int src = r*4 + (lane >> 3);
           const int jj = __shfl_sync(FULLMASK, jv, src);
-          if (jj >= 0) cp_async16(buf + src*REC_STRIDE + (lane & 7), frec + 8*(size_t) jj + (lane & 7));
+          if (jj >= 0) cp_async16(buf + src*REC_STRIDE + (lane & 7), frec + 8*(size_t)(MIRROR ? (jj & IMG_MASK) : jj) + (lane & 7));
         }
         cp_async_commit();
       };
@@ -390,22 +419,35 @@ hydro_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict__ 
         if (jc >= 0) {
           const double2* r = buf + lane*REC_STRIDE;
           const double2 r0 = r[0], r1 = r[1];
+          double xs[3] = {r0.x, r0.y, r1.x};
+          ImageOp op;
+          const bool img = MIRROR && (jc >> IMG_SHIFT);
+          if (img) {                                          /* a mirror image: r_k -> 2*wall - r_k */
+            op = image_op<NDIM>(dp, jc >> IMG_SHIFT);
+#pragma unroll
+            for (int k = 0; k < NDIM; k++) xs[k] = reflect_coord(op, k, xs[k]);
+          }
           double dr[3] = {0, 0, 0};
-          dr[0] = r0.x - g.x[0];
-          if (NDIM > 1) dr[1] = r0.y - g.x[1];
-          if (NDIM > 2) dr[2] = r1.x - g.x[2];
+          dr[0] = xs[0] - g.x[0];
+          if (NDIM > 1) dr[1] = xs[1] - g.x[1];
+          if (NDIM > 2) dr[2] = xs[2] - g.x[2];
           if (wrap) wrap_dr<NDIM>(dp, dr);
           const double drsqd = dot_exact<NDIM>(dr);
           if (drsqd < g.hr2 || drsqd < r1.y) {                  /* NeighbourManager.h:521 */
             const double2 r2 = r[2], r3 = r[3], r4 = r[4], r5 = r[5], r6 = r[6], r7 = r[7];
             Neib nb;
             nb.v[0] = r2.x; nb.v[1] = r2.y; nb.v[2] = r3.x;
+            if (img) {                                        /* ... and v_k -> -v_k (Particle.h:603-607) */
+#pragma unroll
+              for (int k = 0; k < NDIM; k++) if (op.refl[k]) nb.v[k] = -nb.v[k];
+            }
             nb.m = r3.y; nb.invh = r4.x; nb.hfac = r4.y; nb.invrho = r5.x; nb.pfac = r5.y;
             nb.sound = r6.x; nb.zeta = r6.y; nb.u = r7.x;
             nb.alpha = 0.0; nb.press = 0.0;
-            if (aux_is_alpha) { nb.alpha = r7.y; nb.level = P.i[I_LEVEL][jc]; }
+            const int jpart = MIRROR ? (jc & IMG_MASK) : jc;
+            if (aux_is_alpha) { nb.alpha = r7.y; nb.level = P.i[I_LEVEL][jpart]; }
             else nb.level = (int) r7.y;
-            if (price) nb.press = P.f[F_PRESS][jc];
+            if (price) nb.press = P.f[F_PRESS][jpart];
             pair_terms<NDIM, GRAV, HYDRO>(dp, K, g, dr, drsqd, nb);
           }
         }
@@ -542,14 +584,14 @@ neib_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* work_
   }
 }
 
-template <int NDIM, int KERN, bool TAB, bool GRAV, bool HYDRO>
-int launch_hydro(gsph_handle* h)
+template <int NDIM, int KERN, bool TAB, bool GRAV, bool HYDRO, bool MIRROR>
+int launch_hydro_m(gsph_handle* h)
 {
   const int Lc = cohort_level_for(h->N, h->tree.ltot, 32);
   constexpr int NTAB = TAB ? (GRAV ? 3 : 1) : 0;
   static_assert(2*32*REC_STRIDE*sizeof(double2) >= NB_WALK_STACK*sizeof(int), "walk stack must fit the stage region");
   const size_t smem = NTAB*GSPH_TABLE_RES*sizeof(double) + HYD_WARPS*2*32*REC_STRIDE*sizeof(double2);
-  auto kern = hydro_kernel<NDIM, KERN, TAB, GRAV, HYDRO>;
+  auto kern = hydro_kernel<NDIM, KERN, TAB, GRAV, HYDRO, MIRROR>;
   CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   int bps = 0;
   CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, HYD_THREADS, smem));
@@ -577,6 +619,14 @@ int launch_hydro(gsph_handle* h)
   h->stats.kernel_launches += 2;
   CUDA_TRY(h, cudaGetLastError());
   return GSPH_OK;
+}
+
+template <int NDIM, int KERN, bool TAB, bool GRAV, bool HYDRO>
+int launch_hydro(gsph_handle* h)
+{
+  /* mirror walls (never with self-gravity, Tree.cpp:636) are a separate instantiation */
+  if (!GRAV && h->dp.any_mirror) return launch_hydro_m<NDIM, KERN, TAB, false, true, true>(h);
+  return launch_hydro_m<NDIM, KERN, TAB, GRAV, HYDRO, false>(h);
 }
 
 template <int NDIM, int MODE>
@@ -626,8 +676,10 @@ int dispatch_hydro(gsph_handle* h, int with_gravity)
     rc = tab ? dispatch_mode<NDIM, GSPH_KERNEL_QUINTIC, true>(h, with_gravity)
              : dispatch_mode<NDIM, GSPH_KERNEL_QUINTIC, false>(h, with_gravity);
   if (rc) return rc;
-  if (!h->all_active && !h->slice_mode && (h->dp.hydro_forces || !with_gravity))
+  if (!h->all_active && !h->slice_mode && (h->dp.hydro_forces || !with_gravity)) {
+    if (h->dp.any_mirror) { h->err = "inactive particles (block time steps) with mirror boundaries are not on the accelerated path"; return GSPH_EINVAL; }
     rc = launch_neib<NDIM, 2>(h, nullptr, nullptr, nullptr);
+  }
   return rc;
 }
 
@@ -710,6 +762,7 @@ int gsph_run_hydro(gsph_handle* h, int with_gravity)
 
 int gsph_run_neiblist(gsph_handle* h, int32_t* counts, const int64_t* offsets, int32_t* idx)
 {
+  if (h->dp.any_mirror) { h->err = "neighbour-list inspection is not available with mirror boundaries"; return GSPH_EINVAL; }
   const bool fill = idx != nullptr;
   switch (h->dp.ndim) {
   case 1: return fill ? launch_neib<1, 1>(h, counts, offsets, idx) : launch_neib<1, 0>(h, counts, offsets, idx);

@@ -269,26 +269,27 @@ int64_t orc_neighbour_lists(const orc_params* p, int N, const double* r, const d
                             int64_t* offsets, int32_t* idx)
 {
   const int nd = p->ndim;
+  const int Nt = p->ntarget > 0 ? p->ntarget : N;     /* targets = the first Nt particles (the rest: mirror images) */
   if (!idx) {
     #pragma omp parallel for schedule(dynamic, 64)
-    for (int i = 0; i < N; i++) {
+    for (int i = 0; i < Nt; i++) {
       int64_t c = 0;
       for (int j = 0; j < N; j++)
         c += is_neighbour(p, r + (size_t)i*nd, r + (size_t)j*nd, hrangesqd[i], hrangesqd[j], 0, 0);
       offsets[i + 1] = c;
     }
     offsets[0] = 0;
-    for (int i = 0; i < N; i++) offsets[i + 1] += offsets[i];
-    return offsets[N];
+    for (int i = 0; i < Nt; i++) offsets[i + 1] += offsets[i];
+    return offsets[Nt];
   }
   #pragma omp parallel for schedule(dynamic, 64)
-  for (int i = 0; i < N; i++) {
+  for (int i = 0; i < Nt; i++) {
     int64_t o = offsets[i];
     for (int j = 0; j < N; j++)
       if (is_neighbour(p, r + (size_t)i*nd, r + (size_t)j*nd, hrangesqd[i], hrangesqd[j], 0, 0))
         idx[o++] = j;
   }
-  return offsets[N];
+  return offsets[Nt];
 }
 
 /*------------------------------------------------------------------------------------------------
@@ -386,6 +387,7 @@ int orc_density(const orc_params* p, int N, const double* r, const double* m, do
 {
   const int nd = p->ndim;
   const double krs = kern_range(p)*kern_range(p);
+  const int Nt = p->ntarget > 0 ? p->ntarget : N;     /* targets = the first Nt particles (the rest: mirror images) */
   int fail = 0;
   double* hnew = (double*) malloc(sizeof(double)*N);
 
@@ -395,7 +397,7 @@ int orc_density(const orc_params* p, int N, const double* r, const double* m, do
     double* d2 = (double*) malloc(sizeof(double)*cap);
     double* mj = (double*) malloc(sizeof(double)*cap);
     #pragma omp for schedule(dynamic, 32)
-    for (int i = 0; i < N; i++) {
+    for (int i = 0; i < Nt; i++) {
       double hmax = h[i];
       hres res; int ok;
       do {
@@ -426,7 +428,7 @@ int orc_density(const orc_params* p, int N, const double* r, const double* m, do
     }
     free(d2); free(mj);
   }
-  if (!fail) memcpy(h, hnew, sizeof(double)*N);
+  if (!fail) memcpy(h, hnew, sizeof(double)*Nt);
   free(hnew);
   return fail ? -1 : 0;
 }
@@ -589,8 +591,9 @@ int orc_hydro_forces(const orc_params* p, int N, const double* r, const double* 
 {
   const int nd = p->ndim;
   pview P = { r, v, m, h, rho, pressure, invomega, 0, sound, u, alpha, hfactor, hrangesqd, level };
+  const int Nt = p->ntarget > 0 ? p->ntarget : N;     /* targets = the first Nt particles (the rest: mirror images) */
   #pragma omp parallel for schedule(dynamic, 32)
-  for (int i = 0; i < N; i++) {
+  for (int i = 0; i < Nt; i++) {
     acc_t A; memset(&A, 0, sizeof A);
     for (int j = 0; j < N; j++) {
       double dr[3], drsqd;
@@ -605,9 +608,9 @@ int orc_hydro_forces(const orc_params* p, int N, const double* r, const double* 
     if (A.levelneib > levelneib[i]) levelneib[i] = A.levelneib;
   }
   /* scatter half of the levelneib update (GradhSph.cpp:446, GradhSphTree.cpp:376-382) */
-  for (int i = 0; i < N; i++) {
+  for (int i = 0; i < Nt; i++) {
     if (level[i] == 0) continue;
-    for (int j = 0; j < N; j++)
+    for (int j = 0; j < Nt; j++)
       if (is_neighbour(p, r + (size_t)i*nd, r + (size_t)j*nd, hrangesqd[i], hrangesqd[j], 0, 0))
         if (level[i] > levelneib[j]) levelneib[j] = level[i];
   }

@@ -36,6 +36,8 @@ typedef struct orc_params {
   int multipole;         /* 0 monopole 1 quadrupole 2 fast_monopole 3 fast_quadrupole              */
   int Nleafmax;
   int hydro_forces;
+  int ntarget;           /* > 0: only the first ntarget particles are targets; the others are sources only
+                            (materialised mirror-boundary images, Hydrodynamics.cpp:217-290)            */
 } orc_params;
 
 /* kernel functions, which: 0 w0, 1 w1, 2 womega, 3 wzeta, 4 wgrav, 5 wpot; s = r/h              */

@@ -122,6 +122,58 @@ def case_khi2d_quintic():
     return p, d
 
 
+def case_rti2d_mirror():
+    """2-D, periodic in x, MIRROR walls in y (the boundary set of tests/hydro_tests/rti.dat), quintic
+    tabulated: two layers of different density with a sheared, perturbed velocity field."""
+    rng = np.random.default_rng(4242)
+    nx, ny = 32, 64
+    gx = (np.arange(nx) + 0.5) / nx * 0.5
+    gy = (np.arange(ny) + 0.5) / ny
+    r = np.stack(np.meshgrid(gx, gy, indexing="ij"), -1).reshape(-1, 2)
+    r += 0.2 / ny * rng.uniform(-1, 1, r.shape)
+    r[:, 0] = r[:, 0] % 0.5
+    r[:, 1] = np.clip(r[:, 1], 1.0e-4, 1.0 - 1.0e-4)
+    N = len(r)
+    rho0 = np.where(r[:, 1] > 0.5, 2.0, 1.0)
+    m = rho0 * 0.5 / N / 1.5 * 1.5
+    v = np.stack([0.3 * np.sin(2 * np.pi * r[:, 1]), 0.1 * np.cos(4 * np.pi * r[:, 0]) * (1 + r[:, 1])], -1)
+    u = 2.5 / rho0 / (1.4 - 1.0)
+    h = 1.3 * np.sqrt(m / rho0)
+    p = base_params(2, kernel="quintic", gamma_eos=1.4, Nhydromax=12 * N)
+    periodic_box(p, 2, [0.0, 0.0], [0.5, 1.0])
+    p["boundary_lhs[1]"] = "mirror"
+    p["boundary_rhs[1]"] = "mirror"
+    d, _ = refio.run_harness(p, ic=dict(r=r, v=v, m=m, h=h, u=u), perturb_h=0.1, dumps="setup,density,forces")
+    return p, d
+
+
+def case_box3d_mirror():
+    """3-D: mirror walls on both x sides and the lower z side, open in y and above.  (Not periodic
+    in y: with a mix of periodic and non-periodic dimensions the reference's force walk reads an
+    uninitialised shift, GhostNeighbours.hpp:172-192 `dr_corr[k]` of the non-periodic dimensions, and
+    can miss neighbours across the periodic boundary -- observed with this very set-up.)"""
+    rng = np.random.default_rng(5151)
+    n = 11
+    g = (np.arange(n) + 0.5) / n
+    r = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    r += 0.25 / n * rng.uniform(-1, 1, r.shape)
+    r[:, 0] = np.clip(r[:, 0], 1.0e-4, 1.0 - 1.0e-4)
+    r[:, 2] = np.maximum(r[:, 2], 1.0e-4)
+    N = len(r)
+    v = smooth_field(rng, r, 3, 0.6, 1.0)
+    m = np.full(N, 1.0 / N)
+    u = 1.0 * (1.0 + 0.3 * smooth_field(rng, r, 1, 0.5, 1.0)[:, 0])
+    h = np.full(N, 1.2 / n)
+    p = base_params(3, Nhydromax=12 * N)
+    for k, (lo, hi) in enumerate((("mirror", "mirror"), ("open", "open"), ("mirror", "open"))):
+        p["boxmin[%d]" % k] = 0.0
+        p["boxmax[%d]" % k] = 1.0 if k < 2 else 2.0
+        p["boundary_lhs[%d]" % k] = lo
+        p["boundary_rhs[%d]" % k] = hi
+    d, _ = refio.run_harness(p, ic=dict(r=r, v=v, m=m, h=h, u=u), perturb_h=0.1, dumps="setup,density,forces")
+    return p, d
+
+
 def sphere_ic(seed, N):
     rng = np.random.default_rng(seed)
     # centrally condensed sphere rho ~ 1/r: r = R*sqrt(U)
@@ -201,6 +253,8 @@ CASES = {
     "adsod": case_adsod,
     "box3d_m4tab": case_box3d_m4tab,
     "khi2d_quintic": case_khi2d_quintic,
+    "rti2d_mirror": case_rti2d_mirror,
+    "box3d_mirror": case_box3d_mirror,
     "sphere_grav_quad": case_sphere_grav_quad,
     "sphere_grav_fastmono": case_sphere_grav_fastmono,
     "sphere_grav_mono": case_sphere_grav_mono,

@@ -26,7 +26,7 @@ class OrcParams(C.Structure):
         ("boxmin", C.c_double * 3), ("boxmax", C.c_double * 3), ("periodic", C.c_int * 3),
         ("self_gravity", C.c_int), ("thetamaxsqd", C.c_double), ("gravity_mac", C.c_int),
         ("macerror", C.c_double), ("multipole", C.c_int), ("Nleafmax", C.c_int),
-        ("hydro_forces", C.c_int),
+        ("hydro_forces", C.c_int), ("ntarget", C.c_int),
     ]
 
 
@@ -133,7 +133,52 @@ def params_from_dict(d):
     p.multipole = _MULTIPOLE[d.get("multipole", "quadrupole")]
     p.Nleafmax = int(d.get("Nleafmax", 6))
     p.hydro_forces = int(d.get("hydro_forces", 1))
+    p.ntarget = 0
+    # mirror walls: (dimension, wall position) for boundary_lhs/rhs[k] = mirror.  The oracle treats them
+    # the way the reference's density pass does: the mirror images are materialised as extra source
+    # particles (Hydrodynamics.cpp:217-290: r_k -> 2*wall - r_k, v_k -> -v_k, incl. images of images)
+    p.mirrors = []
+    for k in range(p.ndim):
+        if d.get("boundary_lhs[%d]" % k, "open") == "mirror":
+            p.mirrors.append((k, float(d.get("boxmin[%d]" % k, 0.0))))
+        if d.get("boundary_rhs[%d]" % k, "open") == "mirror":
+            p.mirrors.append((k, float(d.get("boxmax[%d]" % k, 0.0))))
     return p
+
+
+def mirror_images(p, fields):
+    """fields: dict name -> array with leading dimension N.  Returns (extended dict, N): the particles
+    followed by every mirror image (one wall per dimension at most per image; images of images across
+    dimensions), positions reflected as 2*wall - r_k and v_k flipped."""
+    mirrors = getattr(p, "mirrors", [])
+    N = len(fields["m"])
+    if not mirrors:
+        return fields, N
+    nd = p.ndim
+    combos = [[]]
+    for k in range(nd):
+        walls = [w for (kk, w) in mirrors if kk == k]
+        combos = [c + [opt] for c in combos for opt in [None] + walls]
+    ext = {k: [np.asarray(v)] for k, v in fields.items()}
+    for c in combos:
+        if all(w is None for w in c):
+            continue
+        r = np.array(fields["r"], dtype=np.float64).reshape(N, nd).copy()
+        v = np.array(fields["v"], dtype=np.float64).reshape(N, nd).copy() if "v" in fields else None
+        for k, w in enumerate(c):
+            if w is not None:
+                r[:, k] = 2*w - r[:, k]
+                if v is not None:
+                    v[:, k] = -v[:, k]
+        for name in fields:
+            if name == "r":
+                ext[name].append(r)
+            elif name == "v":
+                ext[name].append(v)
+            else:
+                ext[name].append(np.asarray(fields[name]))
+    return {k: np.concatenate([np.asarray(a).reshape((N,) + np.asarray(fields[k]).shape[1:]) for a in v], axis=0)
+            for k, v in ext.items()}, N
 
 
 def _c(a, dtype=np.float64):
@@ -158,32 +203,43 @@ def neighbour_lists(p, r, hrangesqd):
 
 
 def density(p, r, m, h, u):
-    N = len(m)
-    r = _c(r).reshape(N, -1)
+    Nt = len(m)
+    ext, _ = mirror_images(p, dict(r=_c(r).reshape(Nt, -1), m=_c(m), h=_c(h), u=_c(u)))
+    N = len(ext["m"])
+    r = _c(ext["r"]).reshape(N, -1)
     out = {k: np.zeros(N) for k in ("rho", "invomega", "zeta", "hfactor", "hrangesqd", "sound", "pressure")}
-    out["h"] = _c(h).copy()
-    out["u"] = _c(u).copy()
+    out["h"] = _c(ext["h"]).copy()
+    out["u"] = _c(ext["u"]).copy()
     out["niter"] = np.zeros(N, dtype=np.int32)
-    rc = lib().orc_density(C.byref(p), N, r, _c(m), out["h"], out["u"], out["rho"], out["invomega"],
+    p.ntarget = Nt if N != Nt else 0
+    rc = lib().orc_density(C.byref(p), N, r, _c(ext["m"]), out["h"], out["u"], out["rho"], out["invomega"],
                            out["zeta"], out["hfactor"], out["hrangesqd"], out["sound"], out["pressure"],
                            out["niter"])
+    p.ntarget = 0
     if rc != 0:
         raise RuntimeError("oracle: h-rho iteration did not converge")
-    return out
+    return {k: v[:Nt] for k, v in out.items()}
 
 
 def hydro_forces(p, s):
     """s: dict with r,v,m,h,rho,pressure,invomega,sound,u,alpha,hfactor,hrangesqd,level."""
-    N = len(s["m"])
+    Nt = len(s["m"])
     nd = p.ndim
+    names = ("r", "v", "m", "h", "rho", "pressure", "invomega", "sound", "u", "alpha", "hfactor", "hrangesqd", "level")
+    base = {k: np.asarray(s[k]) for k in names}
+    base["r"] = base["r"].reshape(Nt, nd); base["v"] = base["v"].reshape(Nt, nd)
+    s, _ = mirror_images(p, base)
+    N = len(s["m"])
     out = dict(a=np.zeros((N, nd)), dudt=np.zeros(N), div_v=np.zeros(N), dalphadt=np.zeros(N),
                levelneib=np.zeros(N, dtype=np.int32))
+    p.ntarget = Nt if N != Nt else 0
     lib().orc_hydro_forces(C.byref(p), N, _c(s["r"]).reshape(N, nd), _c(s["v"]).reshape(N, nd), _c(s["m"]),
                            _c(s["h"]), _c(s["rho"]), _c(s["pressure"]), _c(s["invomega"]), _c(s["sound"]),
                            _c(s["u"]), _c(s["alpha"]), _c(s["hfactor"]), _c(s["hrangesqd"]),
                            _c(s["level"], np.int32), out["a"], out["dudt"], out["div_v"], out["dalphadt"],
                            out["levelneib"])
-    return out
+    p.ntarget = 0
+    return {k: v[:Nt] for k, v in out.items()}
 
 
 def _grav_args(p, s):

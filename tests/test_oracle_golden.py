@@ -33,6 +33,8 @@ def test_kernel_tables_match_dumped_reference_fields(name):
 @pytest.mark.parametrize("name", GOLDEN_CASES)
 def test_neighbour_lists_bit_exact(name):
     params, d = load_golden(name)
+    if "force_in.neib_off" not in d:
+        pytest.skip("no neighbour lists dumped for mirror boundaries (the lists hold ghost images)")
     p = orc.params_from_dict(params)
     s = _state_by_iorig(stage(d, "force_in"))
     off, idx = orc.neighbour_lists(p, s["r"], s["hrangesqd"])
