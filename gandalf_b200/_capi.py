@@ -8,7 +8,7 @@ LIB_PATH = os.path.join(_HERE, "libgsph.so")
 
 GSPH_ABI_VERSION = 1
 NTYPES = 5
-KERNEL = {"m4": 0, "quintic": 1}
+KERNEL = {"m4": 0, "quintic": 1, "gaussian": 2}
 AVISC = {"none": 0, "mon97": 1, "mon97mm97": 2, "mon97cd2010": 3}
 ACOND = {"none": 0, "wadsley2008": 1, "price2008": 2}
 TDAVISC = {"none": 0, "mm97": 1}

@@ -187,7 +187,8 @@ int validate_config(const gsph_config* c, std::string& err)
 {
   if (c->abi_version != GSPH_ABI_VERSION) { err = "gsph_config.abi_version mismatch"; return GSPH_EINVAL; }
   if (c->ndim < 1 || c->ndim > 3) { err = "ndim must be 1, 2 or 3"; return GSPH_EINVAL; }
-  if (c->kernel != GSPH_KERNEL_M4 && c->kernel != GSPH_KERNEL_QUINTIC) { err = "kernel must be m4 or quintic"; return GSPH_EINVAL; }
+  if (c->kernel < GSPH_KERNEL_M4 || c->kernel > GSPH_KERNEL_GAUSSIAN) { err = "kernel must be m4, quintic or gaussian"; return GSPH_EINVAL; }
+  if (c->kernel == GSPH_KERNEL_GAUSSIAN && c->self_gravity) { err = "the gaussian kernel has no gravity softening (wgrav = wpot = 0, SmoothingKernel.h:497-521): not with self_gravity"; return GSPH_EINVAL; }
   if (!(c->h_fac > 0) || !(c->h_converge > 0)) { err = "h_fac and h_converge must be positive"; return GSPH_EINVAL; }
   if (c->Nleafmax < 1) { err = "Nleafmax must be >= 1"; return GSPH_EINVAL; }
   if (c->eos < GSPH_EOS_ADIABATIC || c->eos > GSPH_EOS_BAROTROPIC2) { err = "gas_eos is not on the accelerated path"; return GSPH_EINVAL; }
@@ -1152,7 +1153,7 @@ int gsph_get_stats(gsph_handle* h, gsph_stats* st)
 
 int gsph_kernel_table(int ndim, int kernel, int which, double* out)
 {
-  if (ndim < 1 || ndim > 3 || (kernel != GSPH_KERNEL_M4 && kernel != GSPH_KERNEL_QUINTIC) || which < 0 || which > 5 || !out)
+  if (ndim < 1 || ndim > 3 || (kernel < GSPH_KERNEL_M4 || kernel > GSPH_KERNEL_GAUSSIAN) || which < 0 || which > 5 || !out)
     return GSPH_EINVAL;
   std::vector<double> tab(6*GSPH_TABLE_RES);
   gsph_make_tables(ndim, kernel, tab.data());

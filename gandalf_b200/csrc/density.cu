@@ -437,6 +437,8 @@ int dispatch_density(gsph_handle* h)
   const bool tab = h->dp.tabulated != 0;
   if (h->dp.kernel == GSPH_KERNEL_M4)
     return tab ? launch_density<NDIM, GSPH_KERNEL_M4, true>(h) : launch_density<NDIM, GSPH_KERNEL_M4, false>(h);
+  if (h->dp.kernel == GSPH_KERNEL_GAUSSIAN)
+    return tab ? launch_density<NDIM, GSPH_KERNEL_GAUSSIAN, true>(h) : launch_density<NDIM, GSPH_KERNEL_GAUSSIAN, false>(h);
   return tab ? launch_density<NDIM, GSPH_KERNEL_QUINTIC, true>(h)
              : launch_density<NDIM, GSPH_KERNEL_QUINTIC, false>(h);
 }

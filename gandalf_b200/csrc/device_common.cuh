@@ -85,6 +85,15 @@ __host__ __device__ __forceinline__ double kern_analytic(int which, double s, do
       return 1.0/s;
     }
   }
+  else if (KERN == GSPH_KERNEL_GAUSSIAN) {             /* SmoothingKernel.h:447-521 */
+    if (!(s < 3.0)) return 0.0;
+    switch (which) {
+    case 0: return kn*exp(-s*s);
+    case 1: return -2.0*kn*s*exp(-s*s);
+    case 2: return kn*(2.0*s*exp(-s*s) - nd*exp(-s*s));
+    default: return 0.0;
+    }
+  }
   else {
     const double s6 = s3*s3, s7 = s6*s;
     switch (which) {

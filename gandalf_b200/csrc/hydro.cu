@@ -672,6 +672,12 @@ int dispatch_hydro(gsph_handle* h, int with_gravity)
   if (h->dp.kernel == GSPH_KERNEL_M4)
     rc = tab ? dispatch_mode<NDIM, GSPH_KERNEL_M4, true>(h, with_gravity)
              : dispatch_mode<NDIM, GSPH_KERNEL_M4, false>(h, with_gravity);
+  else if (h->dp.kernel == GSPH_KERNEL_GAUSSIAN) {
+    /* no self-gravity with this kernel (validated at create): hydro-only instantiations */
+    if (with_gravity) { h->err = "gaussian kernel with gravity"; return GSPH_EINVAL; }
+    rc = tab ? launch_hydro<NDIM, GSPH_KERNEL_GAUSSIAN, true, false, true>(h)
+             : launch_hydro<NDIM, GSPH_KERNEL_GAUSSIAN, false, false, true>(h);
+  }
   else
     rc = tab ? dispatch_mode<NDIM, GSPH_KERNEL_QUINTIC, true>(h, with_gravity)
              : dispatch_mode<NDIM, GSPH_KERNEL_QUINTIC, false>(h, with_gravity);
@@ -736,6 +742,7 @@ int dispatch_stars(gsph_handle* h)
 {
   const bool tab = h->dp.tabulated != 0;
   if (h->dp.kernel == GSPH_KERNEL_M4) return tab ? launch_stars<NDIM, GSPH_KERNEL_M4, true>(h) : launch_stars<NDIM, GSPH_KERNEL_M4, false>(h);
+  if (h->dp.kernel == GSPH_KERNEL_GAUSSIAN) return tab ? launch_stars<NDIM, GSPH_KERNEL_GAUSSIAN, true>(h) : launch_stars<NDIM, GSPH_KERNEL_GAUSSIAN, false>(h);
   return tab ? launch_stars<NDIM, GSPH_KERNEL_QUINTIC, true>(h) : launch_stars<NDIM, GSPH_KERNEL_QUINTIC, false>(h);
 }
 

@@ -18,6 +18,8 @@ static const double twothirds = 0.66666666666666666666666;
 double gsph_kernnorm(int ndim, int kernel)
 {
   if (kernel == GSPH_KERNEL_M4) return ndim == 1 ? twothirds : (ndim == 2 ? invpi*(10.0/7.0) : invpi);
+  if (kernel == GSPH_KERNEL_GAUSSIAN)                  /* GaussianKernel.cpp:39-58 */
+    return ndim == 1 ? sqrt(invpi) : (ndim == 2 ? invpi : invpi*sqrt(invpi));
   return ndim == 1 ? 1.0/120.0 : (ndim == 2 ? invpi*(7.0/478.0) : invpi*(1/120.));
 }
 
@@ -109,12 +111,24 @@ static double quintic(int which, double s, double kn, int nd)
   }
 }
 
+/* SmoothingKernel.h:447-521: the Gaussian has no gravity softening (wzeta = wgrav = wpot = 0) */
+static double gaussian(int which, double s, double kn, int nd)
+{
+  if (!(s < 3.0)) return 0.0;
+  switch (which) {
+  case 0: return kn*exp(-s*s);
+  case 1: return -2.0*kn*s*exp(-s*s);
+  case 2: return kn*(2.0*s*exp(-s*s) - nd*exp(-s*s));
+  default: return 0.0;
+  }
+}
+
 void gsph_make_tables(int ndim, int kernel, double* out)
 {
   const double kr = kernel == GSPH_KERNEL_M4 ? 2.0 : 3.0, krs = kr*kr;
   const double kn = gsph_kernnorm(ndim, kernel);
   const double step = kr/RES, step2 = krs/RES;
-  double (*f)(int, double, double, int) = kernel == GSPH_KERNEL_M4 ? m4 : quintic;
+  double (*f)(int, double, double, int) = kernel == GSPH_KERNEL_M4 ? m4 : (kernel == GSPH_KERNEL_GAUSSIAN ? gaussian : quintic);
   for (int i = 0; i < RES; i++) {
     out[0*RES + i] = f(0, sqrt(step2*i), kn, ndim);    /* w0_s2     */
     out[1*RES + i] = f(2, sqrt(step2*i), kn, ndim);    /* womega_s2 */

@@ -110,8 +110,8 @@ class GpuSphTree : public GradhSphTree<ndim, GradhSphParticle>
     gsph_config c;
     gsph_default_config(&c);
     c.ndim = ndim;
-    static const char* const kernels[] = {"m4", "quintic"};
-    c.kernel = lookup(sp["kernel"], kernels, 2, "kernel");
+    static const char* const kernels[] = {"m4", "quintic", "gaussian"};
+    c.kernel = lookup(sp["kernel"], kernels, 3, "kernel");
     c.tabulated_kernel = ip["tabulated_kernel"];
     c.h_fac = sph->h_fac; c.h_converge = sph->h_converge;
     c.avisc = (int) sph->avisc; c.acond = (int) sph->acond;           // same enum order, Sph.h:50-52

@@ -47,7 +47,7 @@ enum {
 
 /* ---- enumerations mirroring the reference's run-time parameters -------------------------------*/
 /* kernel = m4 | quintic            (src/Common/Parameters.cpp:253; SmoothingKernel.h:131,281)    */
-enum { GSPH_KERNEL_M4 = 0, GSPH_KERNEL_QUINTIC = 1 };
+enum { GSPH_KERNEL_M4 = 0, GSPH_KERNEL_QUINTIC = 1, GSPH_KERNEL_GAUSSIAN = 2 /* SmoothingKernel.h:410-545 */ };
 /* avisc  = none | mon97 | mon97mm97 | mon97cd2010   (src/Headers/Hydrodynamics.h aviscenum)      */
 enum { GSPH_AVISC_NONE = 0, GSPH_AVISC_MON97 = 1, GSPH_AVISC_MON97MM97 = 2, GSPH_AVISC_MON97CD2010 = 3 };
 /* acond  = none | wadsley2008 | price2008                                                         */

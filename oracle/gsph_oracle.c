@@ -25,7 +25,7 @@
  * Smoothing kernels.  M4: src/Headers/SmoothingKernel.h:131-240, norms src/Hydrodynamics/
  * M4Kernel.cpp:39-53.  Quintic: SmoothingKernel.h:281-408, norms QuinticKernel.cpp:39-53.
  *-----------------------------------------------------------------------------------------------*/
-static double kern_range(const orc_params* p) { return p->kernel == 0 ? 2.0 : 3.0; }
+static double kern_range(const orc_params* p) { return p->kernel == 0 ? 2.0 : 3.0; }   /* m4 | quintic, gaussian */
 
 static double kern_norm(const orc_params* p)
 {
@@ -33,6 +33,11 @@ static double kern_norm(const orc_params* p)
     if (p->ndim == 1) return TWOTHIRDS;
     if (p->ndim == 2) return INVPI*(10.0/7.0);
     return INVPI;
+  }
+  if (p->kernel == 2) {                          /* GaussianKernel.cpp:39-58 */
+    if (p->ndim == 1) return sqrt(INVPI);
+    if (p->ndim == 2) return INVPI;
+    return INVPI*sqrt(INVPI);
   }
   if (p->ndim == 1) return 1.0/120.0;
   if (p->ndim == 2) return INVPI*(7.0/478.0);
@@ -143,8 +148,21 @@ static double quintic_eval(int which, double s, double kernnorm, int ndim)
   }
 }
 
+/* GaussianKernel, src/Headers/SmoothingKernel.h:447-521 (wzeta = wgrav = wpot = 0) */
+static double gaussian_eval(int which, double s, double kn, int nd)
+{
+  if (!(s < 3.0)) return 0.0;
+  switch (which) {
+  case 0: return kn*exp(-s*s);
+  case 1: return -2.0*kn*s*exp(-s*s);
+  case 2: return kn*(2.0*s*exp(-s*s) - nd*exp(-s*s));
+  default: return 0.0;
+  }
+}
+
 static double analytic(const orc_params* p, int which, double s)
 {
+  if (p->kernel == 2) return gaussian_eval(which, s, kern_norm(p), p->ndim);
   return p->kernel == 0 ? m4_eval(which, s, kern_norm(p), p->ndim)
                         : quintic_eval(which, s, kern_norm(p), p->ndim);
 }
@@ -152,7 +170,7 @@ static double analytic(const orc_params* p, int which, double s)
 /* Tabulated kernel: tables built as src/Headers/SmoothingKernel.h:585-605 (initializeTable /
  * initializeTableSqd), looked up as :619-661 (truncating index, no interpolation).             */
 typedef struct { int ready; int ndim, kernel; double t[6][TABLE_RES]; } orc_tables;
-static orc_tables g_tab[6];   /* cache keyed by (kernel, ndim) */
+static orc_tables g_tab[9];   /* cache keyed by (kernel, ndim): 3 kernels x 3 dimensions */
 
 static const orc_tables* get_tables(const orc_params* p)
 {

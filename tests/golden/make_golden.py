@@ -122,6 +122,25 @@ def case_khi2d_quintic():
     return p, d
 
 
+def case_shock1d_gaussian():
+    """1-D periodic, GAUSSIAN kernel (analytic), the kernel of tests/hydro_tests/adshock.dat and
+    soundwave.dat: two states with a velocity jump."""
+    rng = np.random.default_rng(909)
+    n1, n2 = 320, 160
+    x = np.concatenate([-2.0 + 2.0*(np.arange(n1) + 0.5)/n1, 2.0*(np.arange(n2) + 0.5)/n2])
+    x += 0.05*rng.uniform(-1, 1, x.size)*np.concatenate([np.full(n1, 2.0/n1), np.full(n2, 2.0/n2)])
+    N = x.size
+    m = np.full(N, 2.0/n1)
+    rho0 = np.where(x < 0, 1.0, 0.5)
+    v = np.where(x < 0, 0.5, -0.5)[:, None]
+    u = np.where(x < 0, 2.5, 2.0)
+    h = 1.2*m/rho0
+    p = base_params(1, kernel="gaussian", tabulated_kernel=0, gamma_eos=1.4, Nhydromax=12*N)
+    periodic_box(p, 1, [-2.0], [2.0])
+    d, _ = refio.run_harness(p, ic=dict(r=x[:, None], v=v, m=m, h=h, u=u), perturb_h=0.1)
+    return p, d
+
+
 def case_rti2d_mirror():
     """2-D, periodic in x, MIRROR walls in y (the boundary set of tests/hydro_tests/rti.dat), quintic
     tabulated: two layers of different density with a sheared, perturbed velocity field."""
@@ -253,6 +272,7 @@ CASES = {
     "adsod": case_adsod,
     "box3d_m4tab": case_box3d_m4tab,
     "khi2d_quintic": case_khi2d_quintic,
+    "shock1d_gaussian": case_shock1d_gaussian,
     "rti2d_mirror": case_rti2d_mirror,
     "box3d_mirror": case_box3d_mirror,
     "sphere_grav_quad": case_sphere_grav_quad,

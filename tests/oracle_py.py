@@ -84,7 +84,7 @@ def lib():
     return _lib
 
 
-_KERNELS = {"m4": 0, "quintic": 1}
+_KERNELS = {"m4": 0, "quintic": 1, "gaussian": 2}
 _AVISC = {"none": 0, "mon97": 1, "mon97mm97": 2, "mon97cd2010": 3}
 _ACOND = {"none": 0, "wadsley2008": 1, "price2008": 2}
 _TDAVISC = {"none": 0, "mm97": 1, "cd2010": 2}

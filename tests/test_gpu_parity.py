@@ -183,6 +183,9 @@ def _box_params(ndim, **kw):
     (3, 16, {"gas_eos": "isothermal", "temp0": 2.0, "mu_bar": 1.3}),
     (3, 16, {"gas_eos": "barotropic", "temp0": 1.5, "mu_bar": 2.35, "rho_bary": 1.2, "gamma_eos": 1.4}),
     (3, 16, {"gas_eos": "barotropic2", "temp0": 1.5, "mu_bar": 2.35, "rho_bary": 1.0, "gamma_eos": 1.4}),
+    (3, 14, {"kernel": "gaussian"}),
+    (2, 48, {"kernel": "gaussian", "tabulated_kernel": 0}),
+    (1, 400, {"kernel": "gaussian", "tabulated_kernel": 0, "gamma_eos": 1.4}),
 ])
 def test_full_step_vs_oracle(ndim, n, kw):
     """density -> hydro forces on a periodic jittered lattice, all option families, vs the oracle."""
