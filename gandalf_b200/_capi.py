@@ -11,7 +11,7 @@ NTYPES = 5
 KERNEL = {"m4": 0, "quintic": 1, "gaussian": 2}
 AVISC = {"none": 0, "mon97": 1, "mon97mm97": 2, "mon97cd2010": 3}
 ACOND = {"none": 0, "wadsley2008": 1, "price2008": 2}
-TDAVISC = {"none": 0, "mm97": 1}
+TDAVISC = {"none": 0, "mm97": 1, "cd2010": 2}
 EOS = {"energy_eqn": 0, "constant_temp": 0, "isothermal": 1, "barotropic": 2, "barotropic2": 3}
 BOUNDARY = {"open": 0, "periodic": 1, "mirror": 2}
 MAC = {"geometric": 0, "eigenmac": 1, "gadget2": 2}

@@ -192,7 +192,12 @@ int validate_config(const gsph_config* c, std::string& err)
   if (!(c->h_fac > 0) || !(c->h_converge > 0)) { err = "h_fac and h_converge must be positive"; return GSPH_EINVAL; }
   if (c->Nleafmax < 1) { err = "Nleafmax must be >= 1"; return GSPH_EINVAL; }
   if (c->eos < GSPH_EOS_ADIABATIC || c->eos > GSPH_EOS_BAROTROPIC2) { err = "gas_eos is not on the accelerated path"; return GSPH_EINVAL; }
-  if (c->tdavisc != GSPH_TDAVISC_NONE && c->tdavisc != GSPH_TDAVISC_MM97) { err = "time_dependent_avisc = cd2010 is not on the accelerated path"; return GSPH_EINVAL; }
+  if (c->tdavisc < GSPH_TDAVISC_NONE || c->tdavisc > GSPH_TDAVISC_CD2010) { err = "unknown time_dependent_avisc"; return GSPH_EINVAL; }
+  if (c->tdavisc == GSPH_TDAVISC_CD2010)
+    for (int k = 0; k < c->ndim; k++)
+      if (c->boundary_lhs[k] == GSPH_BOUNDARY_MIRROR || c->boundary_rhs[k] == GSPH_BOUNDARY_MIRROR) {
+        err = "time_dependent_avisc = cd2010 with mirror boundaries is not on the accelerated path"; return GSPH_EINVAL;
+      }
   for (int k = 0; k < c->ndim; k++) {
     if ((c->boundary_lhs[k] == GSPH_BOUNDARY_MIRROR || c->boundary_rhs[k] == GSPH_BOUNDARY_MIRROR)) {
       if (c->self_gravity) { err = "self-gravity with mirror boundaries is not supported (the reference asserts it, Tree.cpp:636)"; return GSPH_EINVAL; }
@@ -531,7 +536,8 @@ static int download_impl(gsph_handle* h, const gsph_particle_view* view, uint32_
   auto want_d = [&](int pf) {
     if (field_mask == GSPH_F_ALL) return true;
     const bool dens = pf == F_H || pf == F_RHO || pf == F_HR2 || pf == F_HFAC || pf == F_INVOMEGA || pf == F_ZETA ||
-                      pf == F_U || pf == F_SOUND || pf == F_PRESS || pf == F_DIVV;
+                      pf == F_U || pf == F_SOUND || pf == F_PRESS || pf == F_DIVV ||
+                      ((pf == F_ALPHA || pf == F_DALPHADT) && h->dp.tdavisc == GSPH_TDAVISC_CD2010);
     const bool forc = (pf >= F_AX && pf <= F_ATZ) || pf == F_DUDT || pf == F_DIVV || pf == F_DALPHADT ||
                       pf == F_GPOT || pf == F_GPOTHYDRO;
     return ((field_mask & GSPH_F_DENSITY) && dens) || ((field_mask & GSPH_F_FORCES) && forc);

@@ -73,6 +73,129 @@ template <int NDIM> __device__ __forceinline__ double pow_ndim(double x)
 }
 
 /*------------------------------------------------------------------------------------------------
+ * Cullen & Dehnen (2010) viscosity switch, Sph<ndim>::ComputeCullenAndDehnenViscosity (Sph.h:364-456),
+ * called at the end of ComputeH (GradhSph.cpp:319-321): velocity- and acceleration-gradient matrices
+ * from the gather neighbours (their v and the PREVIOUS step's a), condition-number guard, Balsara-like
+ * limiter, alpha = max(alpha, alpha_loc) and dalphadt.  Rarely used and register hungry (27 sums):
+ * kept out of line, reading the lane's list and the records straight from global memory.
+ *-----------------------------------------------------------------------------------------------*/
+template <int NDIM, int KERN, bool TAB, bool MIRROR>
+__device__ __forceinline__ void cd2010_switch(const PartView& P, const DevParams& dp, const double* __restrict__ gtables,
+                                           const double2* __restrict__ geo4, const int32_t* nlist, int n, int lane,
+                                           int ti, bool crosses, double hf, double rho, double hfactor, double sound)
+{
+  const KernelEval<KERN, NDIM, TAB> K(dp, gtables);       /* all six tables, in global memory */
+  double rr[3][3], dv[3][3], da[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) rr[i][j] = dv[i][j] = da[i][j] = 0.0;
+  double xi[3] = {0, 0, 0}, vi[3] = {0, 0, 0}, ai[3] = {0, 0, 0};
+#pragma unroll
+  for (int k = 0; k < NDIM; k++) { xi[k] = P.f[F_RX + k][ti]; vi[k] = P.f[F_VX + k][ti]; ai[k] = P.f[F_AX + k][ti]; }
+  const double invh = 1.0/hf;
+  const double hfac = invh*hfactor/rho;
+  for (int kk = 0; kk < n; kk++) {
+    const int e = nlist[(size_t) kk*32 + lane];
+    const int j = MIRROR ? (e & IMG_MASK) : e;
+    const double2 g0 = geo4[2*(size_t) j], g1 = geo4[2*(size_t) j + 1];
+    if (!(g1.y > 0.0)) continue;                           /* dead */
+    double xs[3] = {g0.x, g0.y, g1.x}, vj[3] = {0, 0, 0}, aj[3] = {0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < NDIM; k++) { vj[k] = P.f[F_VX + k][j]; aj[k] = P.f[F_AX + k][j]; }
+    if (MIRROR && (e >> IMG_SHIFT)) {
+      const ImageOp op = image_op<NDIM>(dp, e >> IMG_SHIFT);
+#pragma unroll
+      for (int k = 0; k < NDIM; k++) {
+        xs[k] = reflect_coord(op, k, xs[k]);
+        if (op.refl[k]) { vj[k] = -vj[k]; aj[k] = -aj[k]; }
+      }
+    }
+    double dr[3] = {0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < NDIM; k++) dr[k] = xs[k] - xi[k];
+    if (crosses) wrap_dr<NDIM>(dp, dr);
+    const double w = g1.y*hfac*K.w1(invh*sqrt(dot_exact<NDIM>(dr)));
+    if (w == 0.0) continue;
+#pragma unroll
+    for (int a = 0; a < NDIM; a++)
+#pragma unroll
+      for (int b = 0; b < NDIM; b++) {
+        rr[a][b] += w*dr[a]*dr[b];
+        dv[a][b] += w*dr[a]*(vj[b] - vi[b]);
+        da[a][b] += w*dr[a]*(aj[b] - ai[b]);
+      }
+  }
+  /* InvertMatrix, InlineFuncs.h:573-612 */
+  double T[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) T[i][j] = 0.0;
+  if (NDIM == 1) T[0][0] = 1.0/rr[0][0];
+  else if (NDIM == 2) {
+    const double invdet = 1.0/(rr[0][0]*rr[1][1] - rr[0][1]*rr[1][0]);
+    T[0][0] = invdet*rr[1][1]; T[0][1] = -invdet*rr[0][1]; T[1][0] = -invdet*rr[1][0]; T[1][1] = invdet*rr[0][0];
+  }
+  else {
+    const double (&A)[3][3] = rr;
+    const double invdet = 1.0/(A[0][0]*(A[1][1]*A[2][2] - A[2][1]*A[1][2]) - A[0][1]*(A[1][0]*A[2][2] - A[1][2]*A[2][0]) +
+                               A[0][2]*(A[1][0]*A[2][1] - A[1][1]*A[2][0]));
+    T[0][0] = (A[1][1]*A[2][2] - A[2][1]*A[1][2])*invdet; T[0][1] = (A[0][2]*A[2][1] - A[0][1]*A[2][2])*invdet;
+    T[0][2] = (A[0][1]*A[1][2] - A[0][2]*A[1][1])*invdet; T[1][0] = (A[1][2]*A[2][0] - A[1][0]*A[2][2])*invdet;
+    T[1][1] = (A[0][0]*A[2][2] - A[0][2]*A[2][0])*invdet; T[1][2] = (A[1][0]*A[0][2] - A[0][0]*A[1][2])*invdet;
+    T[2][0] = (A[1][0]*A[2][1] - A[2][0]*A[1][1])*invdet; T[2][1] = (A[2][0]*A[0][1] - A[0][0]*A[2][1])*invdet;
+    T[2][2] = (A[0][0]*A[1][1] - A[1][0]*A[0][1])*invdet;
+  }
+  double modR = 0.0, modT = 0.0;
+#pragma unroll
+  for (int i = 0; i < NDIM; i++)
+#pragma unroll
+    for (int j = 0; j < NDIM; j++) { modR += rr[i][j]*rr[i][j]; modT += T[i][j]*T[i][j]; }
+  const double sqd_condition_number = modR*modT/(NDIM*NDIM);
+  double alpha_loc = 0.0;
+  if (sqd_condition_number > 1.0e4) alpha_loc = dp.alpha_visc;
+  else {
+    double dvdx[3][3], dadx[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) dvdx[i][j] = dadx[i][j] = 0.0;
+#pragma unroll
+    for (int i = 0; i < NDIM; i++)
+#pragma unroll
+      for (int j = 0; j < NDIM; j++)
+#pragma unroll
+        for (int k = 0; k < NDIM; k++) { dvdx[i][j] += T[j][k]*dv[k][i]; dadx[i][j] += T[j][k]*da[k][i]; }
+    double ddivdt = 0.0, divv2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < NDIM; i++) {
+      ddivdt += dadx[i][i];
+#pragma unroll
+      for (int j = 0; j < NDIM; j++) ddivdt -= dvdx[i][j]*dvdx[j][i];
+      divv2 += dvdx[i][i];
+    }
+    divv2 *= divv2;
+    double curlv2 = 0.0;                                   /* CurlVelSqd, Sph.h:340-357 */
+    if (NDIM == 2) { const double c = dvdx[1][0] - dvdx[0][1]; curlv2 = c*c; }
+    if (NDIM == 3) {
+      const double c0 = dvdx[1][2] - dvdx[2][1], c1 = dvdx[2][0] - dvdx[0][2], c2 = dvdx[0][1] - dvdx[1][0];
+      curlv2 = c0*c0 + c1*c1 + c2*c2;
+    }
+    double f_balsara = 1.0;
+    if (curlv2 > 0.0) f_balsara = divv2/(divv2 + curlv2);
+    if (ddivdt < 0.0) {
+      alpha_loc = (10.0*hf*hf/(sound*sound))*f_balsara*(-ddivdt);
+      alpha_loc = fmin(alpha_loc, dp.alpha_visc);
+    }
+  }
+  double alpha = P.f[F_ALPHA][ti];
+  if (alpha_loc > alpha) alpha = alpha_loc;
+  P.f[F_ALPHA][ti] = alpha;
+  P.f[F_DALPHADT][ti] = 0.1*sound*(fmax(dp.alpha_visc_min, alpha_loc) - alpha)*invh;
+}
+
+/*------------------------------------------------------------------------------------------------
  * One warp per cohort (KD-tree node of <= 32 particles), one target per lane.
  *  phase 1  the candidate slabs found by the walk are streamed once through a 32-entry shared
  *           tile of packed (x,y,z,m) records; every lane appends the candidates inside its search
@@ -81,8 +204,8 @@ template <int NDIM> __device__ __forceinline__ double pow_ndim(double x)
  *  phase 2  the ComputeH fixed-point iteration runs over the lane's own list only (gathering the
  *           32-byte records through L1/L2), so every lane does useful work in every instruction.
  *-----------------------------------------------------------------------------------------------*/
-template <int NDIM, int KERN, bool TAB, bool MIRROR>
-__global__ void __launch_bounds__(DENS_THREADS, 3)
+template <int NDIM, int KERN, bool TAB, bool MIRROR, bool CD2010>
+__global__ void __launch_bounds__(DENS_THREADS, CD2010 ? 2 : 3)
 density_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict__ gtables,
                const double2* __restrict__ geo4, int cohort_level, int* work_counter,
                int32_t* cand_all, int cand_cap, int32_t* nlist_all, int nlist_cap, DevStatus* st,
@@ -370,6 +493,36 @@ density_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict_
           double u = P.f[F_U][ti], cs, pr;
           thermal(dp, rho, u, cs, pr);
           P.f[F_U][ti] = u; P.f[F_SOUND][ti] = cs; P.f[F_PRESS][ti] = pr;
+          if (CD2010)
+            cd2010_switch<NDIM, KERN, TAB, MIRROR>(P, dp, gtables, geo4, nlist, n, lane, ti, crosses, hf, rho,
+                                                   pow_ndim<NDIM>(ih)*ih, cs);
+          if (dp.create_sinks) {
+            /* potential-minimum flag for the sink search (GradhSph.cpp:270-280): no neighbour inside the
+               kernel (of the last iterate of h) has a larger gpot.  The reference evaluates the distance
+               of the PREVIOUS neighbour of its list here, which makes its flag depend
+               on the list order; this is the intended test, with each neighbour's own distance.     */
+            const double gp = P.f[F_GPOT][ti], ihs = 1.0/(h*h);
+            bool pm = true;
+            for (int k = 0; k < n; k++) {
+              const int e = nlist[(size_t) k*32 + lane];
+              const int j = MIRROR ? (e & IMG_MASK) : e;
+              const double2 a = geo4[2*(size_t) j], b = geo4[2*(size_t) j + 1];
+              double xs[3] = {a.x, a.y, b.x};
+              if (MIRROR && (e >> IMG_SHIFT)) {
+                const ImageOp op = image_op<NDIM>(dp, e >> IMG_SHIFT);
+#pragma unroll
+                for (int kk = 0; kk < NDIM; kk++) xs[kk] = reflect_coord(op, kk, xs[kk]);
+              }
+              double dr[3] = {0, 0, 0};
+              dr[0] = xs[0] - x[0];
+              if (NDIM > 1) dr[1] = xs[1] - x[1];
+              if (NDIM > 2) dr[2] = xs[2] - x[2];
+              if (crosses) wrap_dr<NDIM>(dp, dr);
+              if (P.f[F_GPOT][j] > 1.000000001*gp && dot_exact<NDIM>(dr)*ihs < krs) pm = false;
+            }
+            const unsigned fl = (unsigned) P.i[I_FLAGS][ti];
+            P.i[I_FLAGS][ti] = (int32_t)(pm ? (fl | GSPH_FLAG_POTMIN) : (fl & ~(unsigned) GSPH_FLAG_POTMIN));
+          }
           loc_iter += iter; loc_targets++; loc_itmax = max(loc_itmax, iter);
           fin = true;
         }
@@ -392,13 +545,13 @@ density_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict_
   }
 }
 
-template <int NDIM, int KERN, bool TAB, bool MIRROR>
+template <int NDIM, int KERN, bool TAB, bool MIRROR, bool CD2010>
 int launch_density_m(gsph_handle* h)
 {
   const int Lc = cohort_level_for(h->N, h->tree.ltot, 32);
   static_assert(DENS_WARP_D2*sizeof(double2) >= NB_WALK_STACK*sizeof(int), "walk stack must fit the stage region");
   const size_t smem = (TAB ? 3*GSPH_TABLE_RES*sizeof(double) : 0) + DENS_WARPS*DENS_WARP_D2*sizeof(double2);
-  auto kern = density_kernel<NDIM, KERN, TAB, MIRROR>;
+  auto kern = density_kernel<NDIM, KERN, TAB, MIRROR, CD2010>;
   CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   int bps = 0;
   CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, DENS_THREADS, smem));
@@ -428,7 +581,11 @@ template <int NDIM, int KERN, bool TAB>
 int launch_density(gsph_handle* h)
 {
   /* mirror walls are a separate instantiation: boxes without them pay nothing for the image codes */
-  return h->dp.any_mirror ? launch_density_m<NDIM, KERN, TAB, true>(h) : launch_density_m<NDIM, KERN, TAB, false>(h);
+  if (h->dp.tdavisc == GSPH_TDAVISC_CD2010) {          /* the Cullen & Dehnen switch: its own (register hungry) instantiation */
+    if (h->dp.any_mirror) { h->err = "time_dependent_avisc = cd2010 with mirror boundaries is not on the accelerated path"; return GSPH_EINVAL; }
+    return launch_density_m<NDIM, KERN, TAB, false, true>(h);
+  }
+  return h->dp.any_mirror ? launch_density_m<NDIM, KERN, TAB, true, false>(h) : launch_density_m<NDIM, KERN, TAB, false, false>(h);
 }
 
 template <int NDIM>

@@ -115,7 +115,6 @@ class GpuSphTree : public GradhSphTree<ndim, GradhSphParticle>
     c.tabulated_kernel = ip["tabulated_kernel"];
     c.h_fac = sph->h_fac; c.h_converge = sph->h_converge;
     c.avisc = (int) sph->avisc; c.acond = (int) sph->acond;           // same enum order, Sph.h:50-52
-    if (sph->tdavisc == cd2010) ExceptionHandler::getIstance().raise("GpuSphTree: cd2010 viscosity is not accelerated");
     c.tdavisc = (int) sph->tdavisc;
     c.alpha_visc = sph->alpha_visc; c.beta_visc = sph->beta_visc; c.alpha_visc_min = sph->alpha_visc_min;
     static const char* const eos[] = {"energy_eqn", "isothermal", "barotropic", "barotropic2"};

@@ -82,6 +82,8 @@ def config_from_params(p, device=0):
     c.tdavisc = _capi.TDAVISC[td]
     if c.tdavisc == 1 and c.avisc == 1:
         c.avisc = 2                               # mon97 + mm97 -> mon97mm97 (GradhSphSimulation.cpp:69-88)
+    if c.tdavisc == 2 and c.avisc == 1:
+        c.avisc = 3                               # mon97 + cd2010 -> mon97cd2010
     c.alpha_visc, c.beta_visc = float(q["alpha_visc"]), float(q["beta_visc"])
     c.alpha_visc_min = float(q["alpha_visc_min"])
     c.eos = _capi.EOS[q["gas_eos"]]

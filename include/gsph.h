@@ -53,7 +53,7 @@ enum { GSPH_AVISC_NONE = 0, GSPH_AVISC_MON97 = 1, GSPH_AVISC_MON97MM97 = 2, GSPH
 /* acond  = none | wadsley2008 | price2008                                                         */
 enum { GSPH_ACOND_NONE = 0, GSPH_ACOND_WADSLEY2008 = 1, GSPH_ACOND_PRICE2008 = 2 };
 /* time_dependent_avisc = none | mm97 | cd2010 (cd2010 is not on the accelerated path)             */
-enum { GSPH_TDAVISC_NONE = 0, GSPH_TDAVISC_MM97 = 1 };
+enum { GSPH_TDAVISC_NONE = 0, GSPH_TDAVISC_MM97 = 1, GSPH_TDAVISC_CD2010 = 2 /* Sph.h:364-456 */ };
 /* gas_eos = energy_eqn|constant_temp (Adiabatic) | isothermal | barotropic
  *           (src/Hydrodynamics/Hydrodynamics.cpp:91-108; src/Thermal/{Adiabatic,Isothermal,Barotropic}EOS.cpp) */
 enum { GSPH_EOS_ADIABATIC = 0, GSPH_EOS_ISOTHERMAL = 1, GSPH_EOS_BAROTROPIC = 2,

@@ -574,6 +574,89 @@ static void finish_particle(const orc_params* p, const pview* P, int i, int grav
   }
 }
 
+/* InvertMatrix, src/Headers/InlineFuncs.h:573-612 */
+static void invert_matrix(int nd, double A[3][3], double B[3][3])
+{
+  if (nd == 1) B[0][0] = 1/A[0][0];
+  else if (nd == 2) {
+    const double invdet = 1.0/(A[0][0]*A[1][1] - A[0][1]*A[1][0]);
+    B[0][0] = invdet*A[1][1]; B[0][1] = -invdet*A[0][1]; B[1][0] = -invdet*A[1][0]; B[1][1] = invdet*A[0][0];
+  }
+  else {
+    const double invdet = 1.0/(A[0][0]*(A[1][1]*A[2][2] - A[2][1]*A[1][2]) - A[0][1]*(A[1][0]*A[2][2] - A[1][2]*A[2][0]) +
+                               A[0][2]*(A[1][0]*A[2][1] - A[1][1]*A[2][0]));
+    B[0][0] = (A[1][1]*A[2][2] - A[2][1]*A[1][2])*invdet; B[0][1] = (A[0][2]*A[2][1] - A[0][1]*A[2][2])*invdet;
+    B[0][2] = (A[0][1]*A[1][2] - A[0][2]*A[1][1])*invdet; B[1][0] = (A[1][2]*A[2][0] - A[1][0]*A[2][2])*invdet;
+    B[1][1] = (A[0][0]*A[2][2] - A[0][2]*A[2][0])*invdet; B[1][2] = (A[1][0]*A[0][2] - A[0][0]*A[1][2])*invdet;
+    B[2][0] = (A[1][0]*A[2][1] - A[2][0]*A[1][1])*invdet; B[2][1] = (A[2][0]*A[0][1] - A[0][0]*A[2][1])*invdet;
+    B[2][2] = (A[0][0]*A[1][1] - A[1][0]*A[0][1])*invdet;
+  }
+}
+
+/* Sph<ndim>::ComputeCullenAndDehnenViscosity, src/Headers/Sph.h:364-456.  The reference sums over the
+ * whole gather list of the cell; w1 vanishes outside the kernel of the final h, so any complete list
+ * gives the same sums (here: every particle, ascending index). */
+int orc_cd2010_switch(const orc_params* p, int N, const double* r, const double* v, const double* a,
+                      const double* m, const double* h, const double* rho, const double* hfactor,
+                      const double* sound, double* alpha, double* dalphadt)
+{
+  const int nd = p->ndim;
+  const int Nt = p->ntarget > 0 ? p->ntarget : N;
+  #pragma omp parallel for schedule(dynamic, 32)
+  for (int i = 0; i < Nt; i++) {
+    double rr[3][3] = {{0}}, dv[3][3] = {{0}}, da[3][3] = {{0}}, T[3][3] = {{0}}, dvdx[3][3] = {{0}}, dadx[3][3] = {{0}};
+    const double invh = 1/h[i];
+    const double hfac = invh*hfactor[i]/rho[i];
+    for (int j = 0; j < N; j++) {
+      double dr[3] = {0, 0, 0};
+      for (int k = 0; k < nd; k++) dr[k] = r[(size_t)j*nd + k] - r[(size_t)i*nd + k];
+      wrap(p, dr);
+      const double w = m[j]*hfac*orc_kernel(p, 1, invh*sqrt(dot(dr, dr, nd)));
+      if (w == 0.0) continue;
+      for (int jj = 0; jj < nd; jj++)
+        for (int k = 0; k < nd; k++) {
+          rr[jj][k] += w*dr[jj]*dr[k];
+          dv[jj][k] += w*dr[jj]*(v[(size_t)j*nd + k] - v[(size_t)i*nd + k]);
+          da[jj][k] += w*dr[jj]*(a[(size_t)j*nd + k] - a[(size_t)i*nd + k]);
+        }
+    }
+    invert_matrix(nd, rr, T);
+    double modR = 0, modT = 0;
+    for (int ii = 0; ii < nd; ii++)
+      for (int j = 0; j < nd; j++) { modR += rr[ii][j]*rr[ii][j]; modT += T[ii][j]*T[ii][j]; }
+    const double sqd_condition_number = modR*modT/(nd*nd);
+    double alpha_loc = 0;
+    if (sqd_condition_number > 1e4) alpha_loc = p->alpha_visc;
+    else {
+      for (int ii = 0; ii < nd; ii++)
+        for (int j = 0; j < nd; j++)
+          for (int k = 0; k < nd; k++) { dvdx[ii][j] += T[j][k]*dv[k][ii]; dadx[ii][j] += T[j][k]*da[k][ii]; }
+      double ddivdt = 0, divv2 = 0;
+      for (int ii = 0; ii < nd; ii++) {
+        ddivdt += dadx[ii][ii];
+        for (int j = 0; j < nd; j++) ddivdt -= dvdx[ii][j]*dvdx[j][ii];
+        divv2 += dvdx[ii][ii];
+      }
+      divv2 *= divv2;
+      double curlv2 = 0;
+      if (nd == 2) { const double c = dvdx[1][0] - dvdx[0][1]; curlv2 = c*c; }
+      if (nd == 3) {
+        const double c[3] = { dvdx[1][2] - dvdx[2][1], dvdx[2][0] - dvdx[0][2], dvdx[0][1] - dvdx[1][0] };
+        curlv2 = dot(c, c, 3);
+      }
+      double f_balsara = 1;
+      if (curlv2 > 0) f_balsara = divv2/(divv2 + curlv2);
+      if (ddivdt < 0) {
+        alpha_loc = (10*h[i]*h[i]/(sound[i]*sound[i]))*f_balsara*(-ddivdt);
+        alpha_loc = fmin(alpha_loc, p->alpha_visc);
+      }
+    }
+    if (alpha_loc > alpha[i]) alpha[i] = alpha_loc;
+    dalphadt[i] = 0.1*sound[i]*(fmax(p->alpha_visc_min, alpha_loc) - alpha[i])*invh;
+  }
+  return 0;
+}
+
 /* GradhSph::ComputeStarGravForces, src/GradhSph/GradhSph.cpp:699-743 (fixed_sink_mass = 0) */
 int orc_star_grav_forces(const orc_params* p, int N, const double* r, const double* h, int Nstar,
                          const double* stars, double* a, double* atree, double* gpot)

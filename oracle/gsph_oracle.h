@@ -70,6 +70,14 @@ int orc_hydro_forces(const orc_params* p, int N, const double* r, const double* 
                      const int32_t* level,
                      double* a, double* dudt, double* div_v, double* dalphadt, int32_t* levelneib);
 
+/* Sph<ndim>::ComputeCullenAndDehnenViscosity (src/Headers/Sph.h:364-456), called at the end of ComputeH
+ * when time_dependent_avisc = cd2010 (GradhSph.cpp:319-321): for every target, from the gather
+ * neighbours' v and a (the previous step's accelerations) and the FINAL h, rho, hfactor, sound of the
+ * density pass; alpha is updated in place (max with the local value), dalphadt is written.          */
+int orc_cd2010_switch(const orc_params* p, int N, const double* r, const double* v, const double* a,
+                      const double* m, const double* h, const double* rho, const double* hfactor,
+                      const double* sound, double* alpha, double* dalphadt);
+
 /* GradhSph::ComputeStarGravForces, src/GradhSph/GradhSph.cpp:699-743, for every particle: softened
  * gravity of Nstar stars {r[ndim], m, h} (stride ndim+2) with the mean-h kernel; adds to atree and,
  * like both force drivers do (GradhSphTree.cpp:396-399, :611-614), to a, and to gpot.

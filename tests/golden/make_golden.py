@@ -122,6 +122,25 @@ def case_khi2d_quintic():
     return p, d
 
 
+def case_box3d_cd2010():
+    """3-D periodic box with the Cullen & Dehnen (2010) viscosity switch (Sph.h:364-456): the density
+    pass reads the neighbours' v and the accelerations of the reference's own setup force pass."""
+    rng = np.random.default_rng(2010)
+    n = 11
+    g = (np.arange(n) + 0.5) / n
+    r = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3)
+    r = (r + 0.25 / n * rng.uniform(-1, 1, r.shape)) % 1.0
+    N = r.shape[0]
+    v = smooth_field(rng, r, 3, 1.5, 1.0)
+    m = np.full(N, 1.0 / N)
+    u = 1.0 * (1.0 + 0.4 * smooth_field(rng, r, 1, 0.5, 1.0)[:, 0])
+    h = np.full(N, 1.2 / n)
+    p = base_params(3, avisc="mon97", time_dependent_avisc="cd2010", alpha_visc_min=0.1, Nhydromax=8 * N)
+    periodic_box(p, 3, [0, 0, 0], [1, 1, 1])
+    d, _ = refio.run_harness(p, ic=dict(r=r, v=v, m=m, h=h, u=u), perturb_h=0.1)
+    return p, d
+
+
 def case_shock1d_gaussian():
     """1-D periodic, GAUSSIAN kernel (analytic), the kernel of tests/hydro_tests/adshock.dat and
     soundwave.dat: two states with a velocity jump."""
@@ -272,6 +291,7 @@ CASES = {
     "adsod": case_adsod,
     "box3d_m4tab": case_box3d_m4tab,
     "khi2d_quintic": case_khi2d_quintic,
+    "box3d_cd2010": case_box3d_cd2010,
     "shock1d_gaussian": case_shock1d_gaussian,
     "rti2d_mirror": case_rti2d_mirror,
     "box3d_mirror": case_box3d_mirror,
@@ -293,6 +313,10 @@ def pack(params, d, keep_direct=False):
             key = "%s.%s" % (stage, f)
             if key in d:
                 out[key] = d[key]
+    if str(params.get("time_dependent_avisc", "none")) == "cd2010":
+        for st in ("dens_in", "dens_out"):
+            for f in ("a", "dalphadt"):          # the switch reads a (previous step) and writes alpha, dalphadt
+                out["%s.%s" % (st, f)] = d["%s.%s" % (st, f)]
     if str(params.get("gravity_mac", "geometric")) != "geometric":
         for f in ("atree", "gpot"):          # what the cells' amin / macfactor were stocked from
             out["dens_in." + f] = d["dens_in." + f]

@@ -62,6 +62,8 @@ def lib():
         _lib.orc_hydro_forces.argtypes = [P, C.c_int] + [_dp] * 12 + [_ip] + [_dp] * 4 + [_ip]
         _lib.orc_hydro_grav_forces_direct.restype = C.c_int
         _lib.orc_hydro_grav_forces_direct.argtypes = [P, C.c_int] + [_dp] * 13 + [_ip] + [_dp] * 6 + [_ip]
+        _lib.orc_cd2010_switch.restype = C.c_int
+        _lib.orc_cd2010_switch.argtypes = [P, C.c_int] + [_dp] * 10
         _lib.orc_star_grav_forces.restype = C.c_int
         _lib.orc_star_grav_forces.argtypes = [P, C.c_int, _dp, _dp, C.c_int, _dp, _dp, _dp, _dp]
         _lib.orc_tree_build.restype = C.c_void_p
@@ -219,6 +221,17 @@ def density(p, r, m, h, u):
     if rc != 0:
         raise RuntimeError("oracle: h-rho iteration did not converge")
     return {k: v[:Nt] for k, v in out.items()}
+
+
+def cd2010_switch(p, r, v, a, m, dens, alpha):
+    """Cullen & Dehnen switch at the end of ComputeH: dens = output of density(); returns (alpha, dalphadt)"""
+    N = len(m)
+    nd = p.ndim
+    al = _c(alpha).copy()
+    da = np.zeros(N)
+    lib().orc_cd2010_switch(C.byref(p), N, _c(r).reshape(N, nd), _c(v).reshape(N, nd), _c(a).reshape(N, nd), _c(m),
+                            _c(dens["h"]), _c(dens["rho"]), _c(dens["hfactor"]), _c(dens["sound"]), al, da)
+    return al, da
 
 
 def hydro_forces(p, s):

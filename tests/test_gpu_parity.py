@@ -43,7 +43,8 @@ def test_density_matches_reference(name, layout):
     """UpdateAllSphProperties: dens_in -> dens_out of the reference."""
     params, d = load_golden(name)
     si, so = stage(d, "dens_in"), stage(d, "dens_out")
-    ps, tree = _make(params, si, layout, fields=("r", "v", "m", "h", "u", "alpha", "level"))
+    cd2010 = params.get("time_dependent_avisc", "none") == "cd2010"
+    ps, tree = _make(params, si, layout, fields=("r", "v", "m", "h", "u", "alpha", "level") + (("a",) if cd2010 else ()))
     tree.BuildTree(True, 0, 1, 1, 0.0, ps)
     tree.UpdateAllSphProperties()
     tree.Download(ps)
@@ -51,6 +52,9 @@ def test_density_matches_reference(name, layout):
         floor = np.abs(so[f]).max()*1e-6 if f == "zeta" else 0.0
         e = rel_err(ps[f], so[f], floor).max()
         assert e < TOL, "%s: %s rel err %.3e" % (name, f, e)
+    if cd2010:                                       # Cullen & Dehnen switch (Sph.h:364-456)
+        assert scaled_err(ps["alpha"], so["alpha"]).max() < TOL
+        assert scaled_err(ps["dalphadt"], so["dalphadt"]).max() < 1e-8
     assert np.all(ps["div_v"] == 0.0)
     st = tree.Stats()
     assert st.n_active == len(si["m"]) and 1.0 <= st.hiter_mean < 30
@@ -331,7 +335,10 @@ def test_restock_and_extrapolate_modes():
 def test_errors_are_loud():
     import gandalf_b200 as g
     with pytest.raises(ValueError):
-        g.GpuSphTree({"ndim": 3, "time_dependent_avisc": "cd2010"})
+        g.GpuSphTree({"ndim": 3, "time_dependent_avisc": "nosuchswitch"})
+    with pytest.raises(g.GsphError):                     # cd2010 has no mirror-image path
+        g.GpuSphTree({"ndim": 3, "time_dependent_avisc": "cd2010", "boundary_lhs[0]": "mirror",
+                      "boundary_rhs[0]": "mirror", "boxmax[0]": 1.0})
     with pytest.raises(g.GsphError):
         g.GpuSphTree({"ndim": 3, "self_gravity": 1, "boundary_lhs[0]": "mirror", "boundary_rhs[0]": "mirror",
                       "boxmax[0]": 1.0})                 # the reference asserts no mirrors with gravity
@@ -525,4 +532,33 @@ def test_mirror_boundaries_vs_oracle(ndim, n, walls):
     assert vec_rel_err(ps["a"], out["a"]).max() < TOL
     assert scaled_err(ps["dudt"], out["dudt"]).max() < TOL
     assert scaled_err(ps["div_v"], out["div_v"]).max() < TOL
+    tree.close()
+
+
+def test_potmin_flag_for_sink_search():
+    """create_sinks = 1: ComputeH flags the particles that sit at a potential minimum among their
+    kernel neighbours (GradhSph.cpp:270-280; the flag feeds Sinks::SearchForNewSinkParticles).  The GPU
+    evaluates the intended test (every neighbour with its own distance, see density.cu); checked against
+    a brute-force numpy statement of it -- neighbours within 0.5 % of the kernel edge are ambiguous
+    (the reference uses the last iterate of h there) and are excluded from the comparison."""
+    import gandalf_b200 as g
+    from gandalf_b200 import _capi
+    rng = np.random.default_rng(77)
+    N = 4000
+    r = rng.uniform(-1, 1, (N, 3)); r = r[np.linalg.norm(r, axis=1) < 1.0]; N = len(r)
+    m = np.full(N, 1.0/N); u = np.full(N, 0.05); h = np.full(N, 0.15)
+    gpot = 1.0/(0.05 + np.linalg.norm(r - np.array([0.2, -0.1, 0.1]), axis=1)) + 0.3*rng.uniform(size=N)
+    params = {"ndim": 3, "create_sinks": 1, "sink_particles": 1}
+    ps = g.ParticleSet(N, 3).set(r=r, v=np.zeros((N, 3)), m=m, h=h, u=u, gpot=gpot)
+    tree = g.GpuSphTree(params)
+    tree.BuildTree(True, 0, 1, 1, 0.0, ps)
+    tree.UpdateAllSphProperties()
+    tree.Download(ps)
+    got = (ps["flags"] & _capi.FLAG_POTMIN) != 0 if hasattr(_capi, "FLAG_POTMIN") else (ps["flags"] & 8) != 0
+    d2 = ((r[:, None, :] - r[None, :, :])**2).sum(-1)
+    hr2 = 4.0*ps["h"]**2
+    inside = d2 < hr2[:, None]
+    edge = (np.abs(d2/hr2[:, None] - 1.0) < 0.01).any(axis=1)
+    want = ~((gpot[None, :] > 1.000000001*gpot[:, None]) & inside).any(axis=1)
+    assert got.sum() > 0 and np.array_equal(got[~edge], want[~edge])
     tree.close()

@@ -53,6 +53,10 @@ def test_density(name):
         floor = np.abs(so[f]).max() * 1e-6 if f == "zeta" else 0.0
         e = rel_err(out[f], so[f], floor).max()
         assert e < TOL, "%s: %s rel err %.3e" % (name, f, e)
+    if params.get("time_dependent_avisc", "none") == "cd2010":
+        # the Cullen & Dehnen switch at the end of ComputeH (Sph.h:364-456)
+        al, da = orc.cd2010_switch(p, si["r"], si["v"], si["a"], si["m"], out, si["alpha"])
+        assert scaled_err(al, so["alpha"]).max() < TOL and scaled_err(da, so["dalphadt"]).max() < 1e-9
 
 
 @pytest.mark.parametrize("name", [c for c in GOLDEN_CASES if not c.startswith("sphere_grav")])
