@@ -36,7 +36,8 @@ class Config(C.Structure):
         ("gravity_mac", C.c_int32), ("macerror", C.c_double), ("multipole", C.c_int32),
         ("Nleafmax", C.c_int32), ("hmask", C.c_uint32 * NTYPES), ("hydromask", C.c_uint32 * NTYPES),
         ("gravmask", C.c_uint32), ("hydro_forces_type", C.c_uint32), ("self_gravity_type", C.c_uint32),
-        ("create_sinks", C.c_int32), ("device", C.c_int32), ("reserved", C.c_int32 * 7),
+        ("create_sinks", C.c_int32), ("device", C.c_int32), ("conservative_sph_star_gravity", C.c_int32), ("nbody_softening", C.c_int32),
+        ("reserved", C.c_int32 * 5),
     ]
 
 

@@ -171,6 +171,8 @@ void fill_devparams(gsph_handle* h)
     d.periodic[k] = (k < c.ndim && c.boundary_lhs[k] == GSPH_BOUNDARY_PERIODIC) ? 1 : 0;
     d.any_periodic |= d.periodic[k];
   }
+  d.star_zeta = c.conservative_sph_star_gravity != 0; d.nbody_softening = c.nbody_softening;
+  d.stars = nullptr; d.nstar = 0;
   d.any_mirror = 0; d.nimg = 1;
   for (int k = 0; k < 3; k++) {
     d.mirror[k][0] = (k < c.ndim && c.boundary_lhs[k] == GSPH_BOUNDARY_MIRROR) ? 1 : 0;
@@ -295,6 +297,7 @@ int gsph_default_config(gsph_config* c)
   c->ndim = 3; c->kernel = GSPH_KERNEL_M4; c->tabulated_kernel = 1;
   c->h_fac = 1.2; c->h_converge = 0.01;
   c->avisc = GSPH_AVISC_MON97; c->acond = GSPH_ACOND_NONE; c->tdavisc = GSPH_TDAVISC_NONE;
+  c->conservative_sph_star_gravity = 1; c->nbody_softening = 1;
   c->alpha_visc = 1.0; c->beta_visc = 2.0; c->alpha_visc_min = 0.1;
   c->eos = GSPH_EOS_ADIABATIC; c->gamma_eos = 1.6666666666666;
   c->temp0 = 1.0; c->mu_bar = 1.0; c->rho_bary = 1.0e-14;
@@ -934,6 +937,7 @@ int gsph_set_stars(gsph_handle* h, const double* stars, int Nstar)
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   }
   h->Nstar = Nstar;
+  h->dp.stars = h->stars; h->dp.nstar = Nstar;
   return GSPH_OK;
 }
 

@@ -486,7 +486,26 @@ density_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict_
           if (P.i[I_SINKID][ti] == -1) {
             const double deriv = -invndim*hf/rho;                /* h_rho_deriv, Sph.h:264-268 */
             io = 1.0/(1.0 - deriv*invom);
-            ze = deriv*zeta*io;
+            double zs = zeta;
+            if (dp.star_zeta && dp.nstar > 0) {
+              /* SPH-star conservative-gravity terms of zeta (Hubber et al. 2013, GradhSph.cpp:288-306):
+                 every star, with the mean of the two smoothing lengths or the particle's own          */
+              for (int j = 0; j < dp.nstar; j++) {
+                const double* s = dp.stars + (size_t) j*(NDIM + 2);
+                double ihm = dp.nbody_softening == 1 ? 2.0/(hf + s[NDIM + 1]) : 2.0*ih;
+                const double ihs2 = dp.nbody_softening == 1 ? ihm*ihm : 4.0*ih*ih;
+                double dr[3] = {0, 0, 0};
+#pragma unroll
+                for (int k = 0; k < NDIM; k++) dr[k] = s[k] - x[k];
+                const double ssqd = dot_exact<NDIM>(dr)*ihs2;
+                if (ssqd < krs) {
+                  double w0, wom, wze;
+                  K.density_terms(ssqd, w0, wom, wze);
+                  zs += s[NDIM]*ihs2*wze;
+                }
+              }
+            }
+            ze = deriv*zs*io;
           }
           P.f[F_INVOMEGA][ti] = io;
           P.f[F_ZETA][ti] = ze;

@@ -90,6 +90,8 @@ struct DevParams {
   double thetamaxsqd, invthetamaxsqd, macerror;
   int Nleafmax;
   int create_sinks;
+  int star_zeta, nbody_softening;   /* conservative_sph_star_gravity: star terms of zeta (GradhSph.cpp:288-306) */
+  const double* stars; int nstar;   /* device rows {r[ndim], m, h} of gsph_set_stars                    */
 };
 
 /* device-side error / statistics block */

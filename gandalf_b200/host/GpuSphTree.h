@@ -138,6 +138,8 @@ class GpuSphTree : public GradhSphTree<ndim, GradhSphParticle>
     c.multipole = lookup(multipole, mps, 4, "multipole");
     c.Nleafmax = Nleafmax;
     c.create_sinks = sph->create_sinks;
+    c.conservative_sph_star_gravity = sph->conservative_sph_star_gravity;
+    c.nbody_softening = params->intparams["nbody_softening"];
     int rc = gsph_create(&c, &handle);
     if (rc != GSPH_OK) ExceptionHandler::getIstance().raise(std::string("libgsph: ") + gsph_last_error(NULL));
   }
@@ -172,14 +174,28 @@ class GpuSphTree : public GradhSphTree<ndim, GradhSphParticle>
     check(gsph_set_stars(handle, Nstar > 0 ? rows.data() : NULL, Nstar));
   }
 
+  /// nbody->stardata -> the same rows for the star terms of zeta in the density pass
+  /// (GradhSph::ComputeH loops over stardata[0..Nstar), GradhSph.cpp:288-306)
+  void set_stars_for_zeta(Nbody<ndim>* nbody)
+  {
+    const int Nstar = nbody ? nbody->Nstar : 0;
+    std::vector<double> rows((size_t) Nstar*(ndim + 2));
+    for (int j = 0; j < Nstar; j++) {
+      for (int k = 0; k < ndim; k++) rows[(size_t) j*(ndim + 2) + k] = nbody->stardata[j].r[k];
+      rows[(size_t) j*(ndim + 2) + ndim] = nbody->stardata[j].m;
+      rows[(size_t) j*(ndim + 2) + ndim + 1] = nbody->stardata[j].h;
+    }
+    check(gsph_set_stars(handle, Nstar > 0 ? rows.data() : NULL, Nstar));
+  }
+
   virtual void UpdateAllSphProperties(Sph<ndim>* sph, Nbody<ndim>* nbody)
   {
     CodeTiming::BlockTimer timer = this->timing->StartNewTimer("SPH_PROPERTIES");
     if (!staged) { upload(sph); check(gsph_build_tree(handle, 1, 0.0)); }
+    set_stars_for_zeta(nbody);
     check(gsph_update_properties(handle));
     download(sph, GSPH_F_DENSITY);
     staged = false;                       // the host zeroes accelerations / moves data after this call
-    (void) nbody;
   }
 
   virtual void UpdateAllSphHydroForces(Sph<ndim>* sph, Nbody<ndim>* nbody, DomainBox<ndim>& simbox)

@@ -17,7 +17,7 @@ DEFAULTS = {
     "rho_bary": 1.0e-14, "avisc": "mon97", "acond": "none", "time_dependent_avisc": "none",
     "alpha_visc": 1.0, "alpha_visc_min": 0.1, "beta_visc": 2.0,
     "gravity_mac": "geometric", "multipole": "quadrupole", "thetamaxsqd": 0.1, "macerror": 0.0001,
-    "Nleafmax": 6, "ntreebuildstep": 1, "ntreestockstep": 1, "create_sinks": 0, "sink_particles": 0,
+    "Nleafmax": 6, "ntreebuildstep": 1, "ntreestockstep": 1, "create_sinks": 0, "conservative_sph_star_gravity": 1, "nbody_softening": 1, "sink_particles": 0,
     "Nlevels": 1,
 }
 for _k in range(3):
@@ -100,5 +100,7 @@ def config_from_params(p, device=0):
     c.multipole = _capi.MULTIPOLE[q["multipole"]]
     c.Nleafmax = int(q["Nleafmax"])
     c.create_sinks = int(q["create_sinks"])
+    c.conservative_sph_star_gravity = int(q["conservative_sph_star_gravity"])
+    c.nbody_softening = int(q["nbody_softening"])
     c.device = device
     return c

@@ -106,7 +106,10 @@ typedef struct gsph_config {
   uint32_t self_gravity_type; /* bit i: type i experiences gravity                                */
   int32_t create_sinks;       /* 1: compute the potmin flag in the density pass (GradhSph.cpp:271) */
   int32_t device;             /* CUDA device ordinal                                              */
-  int32_t reserved[7];
+  int32_t conservative_sph_star_gravity;  /* 1 (default, Parameters.cpp:253): the density pass adds the
+                                 stars of gsph_set_stars to zeta (GradhSph.cpp:288-306)             */
+  int32_t nbody_softening;    /* 1 (default, Parameters.cpp:321): mean-h softening in those terms   */
+  int32_t reserved[5];
 } gsph_config;
 
 /* Fill *cfg with the reference's defaults (Parameters::SetDefaultValues, Parameters.cpp:166-536):

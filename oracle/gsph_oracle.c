@@ -335,7 +335,7 @@ static void thermal(const orc_params* p, double rho, double* u, double* sound, d
  *-----------------------------------------------------------------------------------------------*/
 typedef struct { double h, rho, invomega, zeta, hfactor, hrangesqd; int niter; } hres;
 
-static int compute_h(const orc_params* p, double mi, double h0, double hmax, int Nneib,
+static int compute_h(const orc_params* p, const double* ri, double mi, double h0, double hmax, int Nneib,
                      const double* drsqd, const double* mj, hres* out)
 {
   const int ndim = p->ndim;
@@ -388,6 +388,17 @@ static int compute_h(const orc_params* p, double mi, double h0, double hmax, int
   invomega = 1.0 - deriv*invomega;
   invomega = 1.0/invomega;
   out->invomega = invomega;
+  if (p->star_zeta == 1 && p->nstar > 0) {          /* GradhSph.cpp:288-306 */
+    for (int j = 0; j < p->nstar; j++) {
+      const double* s = p->stars + (size_t) j*(ndim + 2);
+      double dr[3];
+      if (p->nbody_softening == 1) invhsqd = pow(2.0/(h + s[ndim + 1]), 2);
+      else invhsqd = 4.0*invh*invh;
+      for (int k = 0; k < ndim; k++) dr[k] = s[k] - ri[k];
+      const double ssqd = dot(dr, dr, ndim)*invhsqd;
+      zeta += s[ndim]*invhsqd*orc_kernel_s2(p, 2, ssqd);
+    }
+  }
   out->zeta = deriv*zeta*invomega;
   out->niter = iteration;
   return 1;
@@ -436,7 +447,7 @@ int orc_density(const orc_params* p, int N, const double* r, const double* m, do
             d2[Nneib] = drsqd; mj[Nneib] = m[j]; Nneib++;
           }
         }
-        ok = compute_h(p, m[i], h[i], hmax, Nneib, d2, mj, &res);
+        ok = compute_h(p, r + (size_t) i*nd, m[i], h[i], hmax, Nneib, d2, mj, &res);
       } while (ok == 0);
       if (ok < 0) { fail = 1; continue; }
       hnew[i] = res.h; rho[i] = res.rho; invomega[i] = res.invomega; zeta[i] = res.zeta;

@@ -38,6 +38,10 @@ typedef struct orc_params {
   int hydro_forces;
   int ntarget;           /* > 0: only the first ntarget particles are targets; the others are sources only
                             (materialised mirror-boundary images, Hydrodynamics.cpp:217-290)            */
+  /* stars for the zeta terms of the density pass (GradhSph.cpp:288-306): nstar rows {r[ndim], m, h};
+     star_zeta = conservative_sph_star_gravity, nbody_softening as in Parameters.cpp:321             */
+  int star_zeta, nbody_softening, nstar;
+  const double* stars;
 } orc_params;
 
 /* kernel functions, which: 0 w0, 1 w1, 2 womega, 3 wzeta, 4 wgrav, 5 wpot; s = r/h              */
@@ -81,7 +85,7 @@ int orc_cd2010_switch(const orc_params* p, int N, const double* r, const double*
 /* GradhSph::ComputeStarGravForces, src/GradhSph/GradhSph.cpp:699-743, for every particle: softened
  * gravity of Nstar stars {r[ndim], m, h} (stride ndim+2) with the mean-h kernel; adds to atree and,
  * like both force drivers do (GradhSphTree.cpp:396-399, :611-614), to a, and to gpot.
- * (parity unpinned: no golden vector of the reference with stars is shipped)                       */
+ * (pinned by tests/golden/sphere_grav_stars.npz)                                                    */
 int orc_star_grav_forces(const orc_params* p, int N, const double* r, const double* h, int Nstar,
                          const double* stars, double* a, double* atree, double* gpot);
 

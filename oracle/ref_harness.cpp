@@ -18,7 +18,7 @@
 //  NeighbourManager::EndSearch/GetParticleNeib, NeighbourManager.h:265-327,483-543).
 //
 //  usage:
-//    ref_harness PARAMS.dat OUTDIR [--in IC.bin] [--set key=value]... [--perturb-h AMP]
+//    ref_harness PARAMS.dat OUTDIR [--in IC.bin] [--stars STARS.bin] [--set key=value]... [--perturb-h AMP]
 //                [--dump setup,density,forces,neib,tree,gravlists] [--bench STEPS] [--quiet]
 //                [--mainloop N [--gpu]]
 //  --mainloop N : run N steps of the reference's own SphSimulation::MainLoop and dump the particles
@@ -72,6 +72,7 @@ using namespace std;
 static string g_outdir;
 static bool g_quiet = false;
 static int g_mainloop = 0;         // --mainloop N : run N steps of the reference's own MainLoop
+static string g_starfile;         // --stars FILE : int64 Nstar, then Nstar doubles each of x[,y[,z]], m, h
 static bool g_gpu = false;         // --gpu : swap sim->sphneib for GpuSphTree before doing so
 static FILE* g_out = NULL;          // the caller's stdout (the reference's chatter goes elsewhere)
 
@@ -367,6 +368,18 @@ static int run(Parameters* params, const string& icfile, double perturb, const s
     params->stringparams["ic"] = "python";
     params->intparams["Nhydro"] = (int) N;
   }
+  // star particles (at rest) through the reference's own python-IC import (Simulation.cpp:1325-1420)
+  int64_t Nstar = 0;
+  vector<vector<double> > starcols;
+  if (!g_starfile.empty()) {
+    FILE* fs = fopen(g_starfile.c_str(), "rb");
+    if (!fs || fread(&Nstar, 8, 1, fs) != 1) { fprintf(stderr, "cannot read %s\n", g_starfile.c_str()); return 2; }
+    starcols.assign(ndim + 2, vector<double>(Nstar));
+    for (int c = 0; c < ndim + 2; c++)
+      if (fread(starcols[c].data(), 8, Nstar, fs) != (size_t) Nstar) { fprintf(stderr, "short star file\n"); return 2; }
+    fclose(fs);
+    params->intparams["Nstar"] = (int) Nstar;
+  }
 
   SimulationBase* sb = SimulationBase::SimulationFactory(ndim, params->stringparams["sim"], params);
   SphSimulation<ndim>* sim = static_cast<SphSimulation<ndim>*>(sb);
@@ -388,6 +401,12 @@ static int run(Parameters* params, const string& icfile, double perturb, const s
       }
     }
     fclose(f);
+    static const char* snames[3] = {"x", "y", "z"};
+    for (int c = 0; c < ndim && Nstar > 0; c++) sb->ImportArray(starcols[c].data(), (int) Nstar, snames[c], "star");
+    if (Nstar > 0) {
+      sb->ImportArray(starcols[ndim].data(), (int) Nstar, "m", "star");
+      sb->ImportArray(starcols[ndim + 1].data(), (int) Nstar, "h", "star");
+    }
     sb->initial_h_provided = h_given;
   }
 
@@ -503,6 +522,7 @@ int main(int argc, char** argv)
   for (int i = 3; i < argc; i++) {
     string a = argv[i];
     if (a == "--in" && i + 1 < argc) icfile = argv[++i];
+    else if (a == "--stars" && i + 1 < argc) g_starfile = argv[++i];
     else if (a == "--set" && i + 1 < argc) {
       string kv = argv[++i];
       size_t eq = kv.find('=');
@@ -522,7 +542,7 @@ int main(int argc, char** argv)
   char cwd[4096];
   if (!getcwd(cwd, sizeof cwd)) return 2;
   auto absolutise = [&](string& p) { if (!p.empty() && p[0] != '/') p = string(cwd) + "/" + p; };
-  absolutise(paramfile); absolutise(g_outdir); absolutise(icfile);
+  absolutise(paramfile); absolutise(g_outdir); absolutise(icfile); absolutise(g_starfile);
   mkdir(g_outdir.c_str(), 0755);
   if (chdir(g_outdir.c_str()) != 0) { fprintf(stderr, "cannot chdir to %s\n", g_outdir.c_str()); return 2; }
 

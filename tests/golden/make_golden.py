@@ -249,6 +249,22 @@ def case_sphere_grav_mono():
     return p, d
 
 
+STARS = np.array([[0.05, -0.02, 0.03, 0.4, 0.08],      # {r, m, h}: one star inside the cloud (its mean-h kernel
+                  [1.3, 0.4, -0.2, 0.7, 0.05],         # overlaps many particles), one outside, one at the edge
+                  [-0.55, 0.5, 0.45, 0.2, 0.3]])
+
+
+def case_sphere_grav_stars():
+    """Star particles: their terms in zeta (GradhSph.cpp:288-306, conservative_sph_star_gravity = 1 and
+    nbody_softening = 1 are the defaults) and ComputeStarGravForces (GradhSph.cpp:699-743) in the force pass."""
+    ic = sphere_ic(2029, 2000)
+    p = base_params(3, self_gravity=1, multipole="quadrupole", gravity_mac="geometric", thetamaxsqd=0.15,
+                    Nstar=len(STARS), nbody="lfkdk")
+    d, _ = refio.run_harness(p, ic=ic, perturb_h=0.05, dumps="setup,density,forces,neib,tree,gravlists", stars=STARS)
+    d["stars"] = STARS
+    return p, d
+
+
 def case_sphere_grav_gadget2():
     """Gadget-2 relative opening criterion (Tree.h:413-432): the cells' amin comes from the atree the
     reference's own setup force pass left in the particles (dens_in.atree)."""
@@ -299,6 +315,7 @@ CASES = {
     "sphere_grav_fastmono": case_sphere_grav_fastmono,
     "sphere_grav_mono": case_sphere_grav_mono,
     "sphere_grav_gadget2": case_sphere_grav_gadget2,
+    "sphere_grav_stars": case_sphere_grav_stars,
     "sphere_grav_eigen": case_sphere_grav_eigen,
     "box3d_mm97": case_box3d_mm97,
 }
@@ -320,6 +337,8 @@ def pack(params, d, keep_direct=False):
     if str(params.get("gravity_mac", "geometric")) != "geometric":
         for f in ("atree", "gpot"):          # what the cells' amin / macfactor were stocked from
             out["dens_in." + f] = d["dens_in." + f]
+    if "stars" in d:
+        out["stars"] = d["stars"]
     for f in KEEP_FORCE_OUT:
         key = "force_out.%s" % f
         if key in d:

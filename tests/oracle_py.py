@@ -27,6 +27,7 @@ class OrcParams(C.Structure):
         ("self_gravity", C.c_int), ("thetamaxsqd", C.c_double), ("gravity_mac", C.c_int),
         ("macerror", C.c_double), ("multipole", C.c_int), ("Nleafmax", C.c_int),
         ("hydro_forces", C.c_int), ("ntarget", C.c_int),
+        ("star_zeta", C.c_int), ("nbody_softening", C.c_int), ("nstar", C.c_int), ("stars", C.c_void_p),
     ]
 
 
@@ -136,6 +137,9 @@ def params_from_dict(d):
     p.Nleafmax = int(d.get("Nleafmax", 6))
     p.hydro_forces = int(d.get("hydro_forces", 1))
     p.ntarget = 0
+    p.star_zeta = int(d.get("conservative_sph_star_gravity", 1))
+    p.nbody_softening = int(d.get("nbody_softening", 1))
+    p.nstar, p.stars = 0, None
     # mirror walls: (dimension, wall position) for boundary_lhs/rhs[k] = mirror.  The oracle treats them
     # the way the reference's density pass does: the mirror images are materialised as extra source
     # particles (Hydrodynamics.cpp:217-290: r_k -> 2*wall - r_k, v_k -> -v_k, incl. images of images)
@@ -204,8 +208,14 @@ def neighbour_lists(p, r, hrangesqd):
     return off, idx
 
 
-def density(p, r, m, h, u):
+def density(p, r, m, h, u, stars=None):
+    """stars = (Nstar, ndim + 2) rows {r, m, h}: star terms of zeta (conservative_sph_star_gravity)"""
     Nt = len(m)
+    if stars is not None and len(stars):
+        stars = _c(stars)
+        p.nstar, p.stars = len(stars), stars.ctypes.data
+    else:
+        p.nstar, p.stars = 0, None
     ext, _ = mirror_images(p, dict(r=_c(r).reshape(Nt, -1), m=_c(m), h=_c(h), u=_c(u)))
     N = len(ext["m"])
     r = _c(ext["r"]).reshape(N, -1)
@@ -218,6 +228,7 @@ def density(p, r, m, h, u):
                            out["zeta"], out["hfactor"], out["hrangesqd"], out["sound"], out["pressure"],
                            out["niter"])
     p.ntarget = 0
+    p.nstar, p.stars = 0, None
     if rc != 0:
         raise RuntimeError("oracle: h-rho iteration did not converge")
     return {k: v[:Nt] for k, v in out.items()}

@@ -55,7 +55,8 @@ def load_dump(outdir):
 
 
 def run_harness(params, ic=None, dumps="setup,density,forces,neib", perturb_h=0.0, kind="std",
-                bench_steps=0, threads=None, keep=None, datfile=None, extra_sets=None, timeout=3600):
+                bench_steps=0, threads=None, keep=None, datfile=None, extra_sets=None, timeout=3600,
+                stars=None):
     """Run the reference harness; returns (dict of dumped arrays, bench json or None).
 
     params : dict of .dat parameters (ignored if datfile is given)
@@ -77,6 +78,12 @@ def run_harness(params, ic=None, dumps="setup,density,forces,neib", perturb_h=0.
             icf = os.path.join(work, "ic.bin")
             write_ic(icf, ndim, ic["r"], ic["v"], ic["m"], ic["h"], ic["u"])
             cmd += ["--in", icf]
+        if stars is not None:            # (Nstar, ndim + 2) rows {r, m, h}: star particles at rest
+            sf = os.path.join(work, "stars.bin")
+            with open(sf, "wb") as fh:
+                fh.write(np.int64(len(stars)).tobytes())
+                fh.write(np.ascontiguousarray(np.asarray(stars, dtype=np.float64).T).tobytes())
+            cmd += ["--stars", sf]
         if perturb_h:
             cmd += ["--perturb-h", repr(float(perturb_h))]
         if bench_steps:

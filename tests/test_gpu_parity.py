@@ -46,6 +46,8 @@ def test_density_matches_reference(name, layout):
     cd2010 = params.get("time_dependent_avisc", "none") == "cd2010"
     ps, tree = _make(params, si, layout, fields=("r", "v", "m", "h", "u", "alpha", "level") + (("a",) if cd2010 else ()))
     tree.BuildTree(True, 0, 1, 1, 0.0, ps)
+    if "stars" in d:                                 # star terms of zeta (GradhSph.cpp:288-306)
+        tree.SetStars(d["stars"][:, :3], d["stars"][:, 3], d["stars"][:, 4])
     tree.UpdateAllSphProperties()
     tree.Download(ps)
     for f in ("h", "rho", "invomega", "zeta", "hfactor", "hrangesqd", "u", "sound", "pressure"):
@@ -136,6 +138,8 @@ def test_gravity_forces_match_reference(name):
         ps["atree"][...] = d["dens_in.atree"][order]
         ps["gpot"][...] = d["dens_in.gpot"][order]
     tree.BuildTree(True, 0, 1, 1, 0.0, ps)
+    if "stars" in d:                                 # ComputeStarGravForces (GradhSph.cpp:699-743)
+        tree.SetStars(d["stars"][:, :3], d["stars"][:, 3], d["stars"][:, 4])
     tree.ZeroAccelerations()
     tree.UpdateAllSphForces()
     tree.Download(ps)

@@ -48,7 +48,11 @@ def test_density(name):
     p = orc.params_from_dict(params)
     si = stage(d, "dens_in")
     so = stage(d, "dens_out")
-    out = orc.density(p, si["r"], si["m"], si["h"], si["u"])
+    out = orc.density(p, si["r"], si["m"], si["h"], si["u"], stars=d.get("stars"))
+    if "stars" in d:
+        # the star terms are a sizeable part of zeta near the stars (otherwise this case pins nothing)
+        plain = orc.density(p, si["r"], si["m"], si["h"], si["u"])
+        assert (np.abs(plain["zeta"] - out["zeta"]) > 1e-3*np.abs(out["zeta"])).sum() > 100
     for f in ("h", "rho", "invomega", "zeta", "hfactor", "hrangesqd", "u", "sound", "pressure"):
         floor = np.abs(so[f]).max() * 1e-6 if f == "zeta" else 0.0
         e = rel_err(out[f], so[f], floor).max()
@@ -110,6 +114,12 @@ def test_tree_gravity_forces(name):
     atree, gpot = _mac_inputs(d)
     t = orc.Tree(p, si["r"], si["v"], si["m"], si["h"], atree, gpot)
     out = t.hydro_grav_forces(si)
+    if "stars" in d:                 # ComputeStarGravForces after the tree forces (GradhSphTree.cpp:600-607)
+        st = d["stars"]
+        sa, sat, sg = orc.star_grav_forces(p, si["r"], si["h"], st[:, :3], st[:, 3], st[:, 4])
+        out["a"] = out["a"] + sa
+        out["atree"] = out["atree"] + sat
+        out["gpot"] = out["gpot"] + sg
     # interaction-list sizes equal the reference's
     nd_ref = np.diff(d["grav_in.direct_off"])
     assert np.array_equal(out["ndirect"], nd_ref)
@@ -128,5 +138,8 @@ def test_direct_gravity_close_to_tree(name):
     si = _state_by_iorig(stage(d, "force_in"))
     so = _state_by_iorig(stage(d, "force_out"))
     out = orc.hydro_grav_forces_direct(p, si)
+    if "stars" in d:
+        st = d["stars"]
+        out["atree"] = out["atree"] + orc.star_grav_forces(p, si["r"], si["h"], st[:, :3], st[:, 3], st[:, 4])[1]
     e = vec_rel_err(out["atree"], so["atree"])
     assert np.sqrt(np.mean(e ** 2)) < 2e-2
