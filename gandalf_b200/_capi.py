@@ -72,6 +72,13 @@ class Stats(C.Structure):
                 ("ms_tree_levels", C.c_float), ("ms_tree_stock", C.c_float)]
 
 
+class IntegratorConfig(C.Structure):
+    """gsph_integrator_config"""
+    _fields_ = [("accel_mult", C.c_double), ("courant_mult", C.c_double), ("energy_mult", C.c_double),
+                ("energy_integration", C.c_int32), ("ntreebuildstep", C.c_int32), ("ntreestockstep", C.c_int32),
+                ("reserved", C.c_int32 * 5)]
+
+
 EXPORTS = [
     "gsph_default_config", "gsph_create", "gsph_destroy", "gsph_last_error", "gsph_upload", "gsph_download",
     "gsph_download_async", "gsph_set_stars", "gsph_tree_shard_range", "gsph_build_tree_shard_begin",
@@ -82,6 +89,7 @@ EXPORTS = [
     "gsph_device_field",
     "gsph_neighbour_counts", "gsph_neighbour_lists", "gsph_tree_info_get", "gsph_tree_leaf_of",
     "gsph_tree_cells", "gsph_get_stats", "gsph_kernel_table", "gsph_measure_fp_peak",
+    "gsph_integrator_begin", "gsph_integrator_step", "gsph_integrator_state",
 ]
 
 _lib = None
@@ -121,6 +129,9 @@ def lib():
     L.gsph_device_array.argtypes = [H, C.c_int, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64),
                                     C.POINTER(C.c_int32)]
     L.gsph_build_tree.argtypes = [H, C.c_int, C.c_double]
+    L.gsph_integrator_begin.argtypes = [H, C.POINTER(IntegratorConfig), C.c_int, C.c_double]
+    L.gsph_integrator_step.argtypes = [H, C.c_int]
+    L.gsph_integrator_state.argtypes = [H, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     for n in ("gsph_update_active_counters", "gsph_update_properties", "gsph_zero_accelerations",
               "gsph_update_hydro_forces", "gsph_synchronize", "gsph_timer_start", "gsph_density_pass",
               "gsph_refresh_hmax"):

@@ -276,6 +276,140 @@ int gsph_ensure_nlist(gsph_handle* h, int warps, size_t cap)
   return GSPH_OK;
 }
 
+/*------------------------------------------------------------------------------------------------
+ * device-resident main loop: streaming kernels over the host-order (staging) arrays.  The
+ * arithmetic follows the reference's expressions operation by operation (no contraction), so a
+ * step reproduces the CPU integrator's rounding.
+ *-----------------------------------------------------------------------------------------------*/
+struct IntegPtrs { double* r0[3]; double* v0[3]; double* a0[3]; double* u0; double* dudt0; };
+
+IntegPtrs integ_ptrs(gsph_handle* h)
+{
+  IntegPtrs S;
+  for (int k = 0; k < 3; k++) { S.r0[k] = h->integ.s0[k]; S.v0[k] = h->integ.s0[3 + k]; S.a0[k] = h->integ.s0[6 + k]; }
+  S.u0 = h->integ.s0[9]; S.dudt0 = h->integ.s0[10];
+  return S;
+}
+
+/* SphLeapfrogKDK::AdvanceParticles (SphLeapfrogKDK.cpp:76-125) + TimeIntegration::CheckBoundaries
+ * (Integration.cpp:11-75).  dt = t - tlast, timestep = the global step (they differ by rounding). */
+template <int NDIM>
+__global__ void integ_advance_kernel(int N, DevPtrs H, IntegPtrs S, DevParams dp, double dt, double timestep,
+                                     int tdav, int energy)
+{
+  const int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  unsigned fl = (unsigned) H.i[I_FLAGS][i];
+  if (fl & GSPH_FLAG_DEAD) return;
+#pragma unroll
+  for (int k = 0; k < NDIM; k++) {
+    const double r0 = S.r0[k][i], v0 = S.v0[k][i], a0 = S.a0[k][i];
+    /* r0 + v0*dt + 0.5*a0*dt*dt */
+    H.f[F_RX + k][i] = __dadd_rn(__dadd_rn(r0, __dmul_rn(v0, dt)), __dmul_rn(__dmul_rn(__dmul_rn(0.5, a0), dt), dt));
+    H.f[F_VX + k][i] = __dadd_rn(v0, __dmul_rn(a0, dt));
+  }
+  if (tdav) H.f[F_ALPHA][i] = __dadd_rn(H.f[F_ALPHA][i], __dmul_rn(H.f[F_DALPHADT][i], timestep));
+  if (energy) H.f[F_U][i] = __dadd_rn(S.u0[i], __dmul_rn(S.dudt0[i], dt));
+  H.i[I_FLAGS][i] = (int32_t)(fl | GSPH_FLAG_ACTIVE);         /* dn == nstep for every particle */
+  /* boundaries */
+#pragma unroll
+  for (int k = 0; k < NDIM; k++) {
+    if (!dp.periodic[k] && !dp.mirror[k][0] && !dp.mirror[k][1]) continue;
+    if (H.f[F_RX + k][i] < dp.boxmin[k]) {
+      if (dp.periodic[k]) {
+        H.f[F_RX + k][i] = __dadd_rn(H.f[F_RX + k][i], dp.boxsize[k]);
+        S.r0[k][i] = __dadd_rn(S.r0[k][i], dp.boxsize[k]);
+      }
+      if (dp.mirror[k][0]) {
+        H.f[F_RX + k][i] = __dadd_rn(__dmul_rn(2.0, dp.boxmin[k]), -H.f[F_RX + k][i]);
+        S.r0[k][i] = __dadd_rn(__dmul_rn(2.0, dp.boxmin[k]), -S.r0[k][i]);
+        H.f[F_VX + k][i] = -H.f[F_VX + k][i]; S.v0[k][i] = -S.v0[k][i];
+        H.f[F_AX + k][i] = -H.f[F_AX + k][i]; S.a0[k][i] = -S.a0[k][i];
+      }
+    }
+    if (H.f[F_RX + k][i] > dp.boxmax[k]) {
+      if (dp.periodic[k]) {
+        H.f[F_RX + k][i] = __dadd_rn(H.f[F_RX + k][i], -dp.boxsize[k]);
+        S.r0[k][i] = __dadd_rn(S.r0[k][i], -dp.boxsize[k]);
+      }
+      if (dp.mirror[k][1]) {
+        H.f[F_RX + k][i] = __dadd_rn(__dmul_rn(2.0, dp.boxmax[k]), -H.f[F_RX + k][i]);
+        S.r0[k][i] = __dadd_rn(__dmul_rn(2.0, dp.boxmax[k]), -S.r0[k][i]);
+        H.f[F_VX + k][i] = -H.f[F_VX + k][i]; S.v0[k][i] = -S.v0[k][i];
+        H.f[F_AX + k][i] = -H.f[F_AX + k][i]; S.a0[k][i] = -S.a0[k][i];
+      }
+    }
+  }
+}
+
+/* SphIntegration::Timestep for every particle (SphIntegration.cpp:76-124) and the global minimum
+ * (Simulation::ComputeGlobalTimestep, Simulation.cpp:1690-1730).  Positive doubles order like their
+ * bit patterns, so the minimum is an integer atomicMin.                                            */
+template <int NDIM>
+__global__ void integ_timestep_kernel(int N, DevPtrs H, DevParams dp, gsph_integrator_config ic, unsigned long long* red)
+{
+  const int i = blockIdx.x*blockDim.x + threadIdx.x;
+  double ts = 9.9e50;
+  bool bad = false;
+  if (i < N) {
+    const double hh = H.f[F_H][i], dv = fabs(H.f[F_DIVV][i]);
+    if (dp.hydro_forces == 1) ts = __ddiv_rn(__dmul_rn(ic.courant_mult, hh), __dadd_rn(__dadd_rn(H.f[F_SOUND][i], __dmul_rn(hh, dv)), 1.0e-50));
+    else ts = __ddiv_rn(__dmul_rn(ic.courant_mult, hh), __dadd_rn(__dmul_rn(hh, dv), 1.0e-50));
+    double a2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < NDIM; k++) { const double a = H.f[F_AX + k][i]; a2 = k == 0 ? __dmul_rn(a, a) : __dadd_rn(a2, __dmul_rn(a, a)); }
+    const double amag = __dsqrt_rn(a2);
+    ts = fmin(ts, __dmul_rn(ic.accel_mult, __dsqrt_rn(__ddiv_rn(hh, __dadd_rn(amag, 1.0e-50)))));
+    if (ic.energy_integration && H.i[I_PTYPE][i] == 0)
+      ts = fmin(ts, __dmul_rn(ic.energy_mult, __ddiv_rn(H.f[F_U][i], __dadd_rn(fabs(H.f[F_DUDT][i]), 1.0e-20))));
+    bad = !(ts <= 1.0e20) || ts <= 0.0;
+  }
+  unsigned long long bits = bad ? 0x7ff0000000000000ull : (unsigned long long) __double_as_longlong(ts);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const unsigned long long other = __shfl_xor_sync(0xffffffffu, bits, o); bits = other < bits ? other : bits; }
+  const unsigned nbad = __ballot_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&red[0], bits);
+    if (nbad) atomicAdd(&red[1], (unsigned long long) __popc(nbad));
+  }
+}
+
+/* first half of PostInitialConditionsSetup's tail: r0 = r, v0 = v, a0 = a (SphSimulation.cpp:480-486) */
+template <int NDIM>
+__global__ void integ_init_kernel(int N, DevPtrs H, IntegPtrs S)
+{
+  const int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= N) return;
+#pragma unroll
+  for (int k = 0; k < NDIM; k++) { S.r0[k][i] = H.f[F_RX + k][i]; S.v0[k][i] = H.f[F_VX + k][i]; S.a0[k][i] = H.f[F_AX + k][i]; }
+  S.u0[i] = H.f[F_U][i]; S.dudt0[i] = 0.0;
+}
+
+/* SphLeapfrogKDK::EndTimestep (SphLeapfrogKDK.cpp:226-270); dtp = part.dt, the step just taken */
+template <int NDIM>
+__global__ void integ_end_kernel(int N, DevPtrs H, IntegPtrs S, double dtp, int energy)
+{
+  const int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const unsigned fl = (unsigned) H.i[I_FLAGS][i];
+  if (fl & GSPH_FLAG_DEAD) return;
+  const double hdt = __dmul_rn(0.5, dtp);
+#pragma unroll
+  for (int k = 0; k < NDIM; k++) {
+    const double a = H.f[F_AX + k][i];
+    const double v = __dadd_rn(H.f[F_VX + k][i], __dmul_rn(hdt, __dadd_rn(a, -S.a0[k][i])));
+    H.f[F_VX + k][i] = v;
+    S.r0[k][i] = H.f[F_RX + k][i]; S.v0[k][i] = v; S.a0[k][i] = a;
+  }
+  if (energy) {
+    const double dudt = H.f[F_DUDT][i];
+    double u = __dadd_rn(H.f[F_U][i], __dmul_rn(__dmul_rn(0.5, __dadd_rn(dudt, -S.dudt0[i])), dtp));
+    if (u <= 0.0) u = __dadd_rn(S.u0[i], __dmul_rn(S.dudt0[i], dtp));
+    H.f[F_U][i] = u; S.u0[i] = u; S.dudt0[i] = dudt;
+  }
+  H.i[I_FLAGS][i] = (int32_t)(fl & ~(unsigned) GSPH_FLAG_ACTIVE);
+}
+
 int gsph_check_status(gsph_handle* h, const char* where)
 {
   int rc = fetch_status(h);
@@ -371,7 +505,8 @@ void gsph_destroy(gsph_handle* h)
   auto fre = [](void* p) { if (p) cudaFree(p); };
   for (int f = 0; f < NF_DOUBLE; f++) { fre(h->H[f]); fre(h->P[f]); }
   for (int f = 0; f < NF_INT; f++) { fre(h->HI[f]); fre(h->PI[f]); }
-  fre(h->perm); fre(h->tables); fre(h->scratch); fre(h->cand); fre(h->gravlist); fre(h->status); fre(h->work_counter); fre(h->done); fre(h->geo4); fre(h->geoh); fre(h->frec); fre(h->nlist); fre(h->hnew); fre(h->stars); fre(h->gstack);
+  for (int k = 0; k < 11; k++) fre(h->integ.s0[k]);
+  fre(h->integ.red); fre(h->perm); fre(h->tables); fre(h->scratch); fre(h->cand); fre(h->gravlist); fre(h->status); fre(h->work_counter); fre(h->done); fre(h->geo4); fre(h->geoh); fre(h->frec); fre(h->nlist); fre(h->hnew); fre(h->stars); fre(h->gstack);
   TreeDev& T = h->tree;
   fre(T.first); fre(T.count); fre(T.nactive); fre(T.m); fre(T.rmax); fre(T.hmax); fre(T.cdistsqd);
   for (int k = 0; k < 3; k++) { fre(T.bbmin[k]); fre(T.bbmax[k]); fre(T.hbmin[k]); fre(T.hbmax[k]); fre(T.rcell[k]); fre(T.com[k]); fre(T.vcom[k]); }
@@ -507,6 +642,7 @@ static int upload_impl(gsph_handle* h, const gsph_particle_view* view, int64_t N
   CUDA_TRY(h, cudaGetLastError());
   if (N != h->N) h->have_tree = false;
   h->N = N; h->uploaded = true; h->sorted_valid = false; h->density_done = false; h->slice_mode = false;
+  h->integ.on = false;
   h->stats.Nhydro = N;
   tm.stop();
   return GSPH_OK;
@@ -527,7 +663,7 @@ static int download_impl(gsph_handle* h, const gsph_particle_view* view, uint32_
 {
   if (!h) return GSPH_EINVAL;
   if (!view) { h->err = "gsph_download: NULL view"; return GSPH_EINVAL; }
-  if (!h->sorted_valid) { h->err = "gsph_download before gsph_build_tree"; return GSPH_ESTATE; }
+  if (!h->sorted_valid && !h->integ.on) { h->err = "gsph_download before gsph_build_tree"; return GSPH_ESTATE; }
   cudaSetDevice(h->device);
   Timer tm(h, &h->stats.ms_download);
   const int64_t N = h->N;
@@ -555,10 +691,12 @@ static int download_impl(gsph_handle* h, const gsph_particle_view* view, uint32_
     if (vfield(view, kIntFields[k].off).base && want_i(kIntFields[k].pf)) imask |= 1u << kIntFields[k].pf;
   /* tree order -> host order on the compute stream, then the copies on the copy stream: they
      overlap whatever the compute stream does next (the force pass, for a density download) */
-  scatter_fields_kernel<<<(int)((N + 255)/256), 256, 0, h->stream>>>((int) N, h->perm, devptrs(h->P, h->PI),
-                                                                   devptrs(h->H, h->HI), dmask, imask);
-  h->stats.kernel_launches++;
-  CUDA_TRY(h, cudaGetLastError());
+  if (!h->integ.on) {       /* (the device-resident main loop keeps the state in host order already) */
+    scatter_fields_kernel<<<(int)((N + 255)/256), 256, 0, h->stream>>>((int) N, h->perm, devptrs(h->P, h->PI),
+                                                                     devptrs(h->H, h->HI), dmask, imask);
+    h->stats.kernel_launches++;
+    CUDA_TRY(h, cudaGetLastError());
+  }
   CUDA_TRY(h, cudaEventRecord(h->ev_compute, h->stream));
   CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->ev_compute, 0));
   cudaStream_t cs = h->copy_stream;
@@ -1127,6 +1265,147 @@ int gsph_tree_cells(gsph_handle* h, double* box, double* com, double* scalars, d
     CUDA_TRY(h, cudaMemcpy(cnt.data(), T.count, nc*sizeof(int), cudaMemcpyDeviceToHost));
     for (int n = 0; n < nc; n++) Nout[dfs[n]] = cnt[n];
   }
+  return GSPH_OK;
+}
+
+/*================================================================================================
+ * device-resident main loop
+ *================================================================================================*/
+#define INTEG_LAUNCH(KERN, ...)                                                                      \
+  do {                                                                                               \
+    const int nb_ = (int)((h->N + 255)/256);                                                         \
+    switch (h->cfg.ndim) {                                                                           \
+    case 1: KERN<1><<<nb_, 256, 0, h->stream>>>(__VA_ARGS__); break;                                \
+    case 2: KERN<2><<<nb_, 256, 0, h->stream>>>(__VA_ARGS__); break;                                \
+    default: KERN<3><<<nb_, 256, 0, h->stream>>>(__VA_ARGS__); break;                               \
+    }                                                                                                \
+    h->stats.kernel_launches++;                                                                      \
+    CUDA_TRY(h, cudaGetLastError());                                                                 \
+  } while (0)
+
+/* the particle state of the reference lives in the host-order arrays: bring the results of the
+   density and force passes back from tree order (r, v, m never change there) */
+static int integ_scatter_results(gsph_handle* h)
+{
+  unsigned long long dmask = 0;
+  const int fields[] = {F_H, F_U, F_RHO, F_HR2, F_HFAC, F_INVOMEGA, F_ZETA, F_SOUND, F_PRESS, F_DUDT, F_DIVV, F_ALPHA,
+                        F_DALPHADT, F_GPOT, F_GPOTHYDRO, F_AX, F_AY, F_AZ, F_ATX, F_ATY, F_ATZ};
+  for (int f : fields) dmask |= 1ull << f;
+  const unsigned imask = (1u << I_FLAGS) | (1u << I_LEVELNEIB);
+  scatter_fields_kernel<<<(int)((h->N + 255)/256), 256, 0, h->stream>>>((int) h->N, h->perm, devptrs(h->P, h->PI),
+                                                                      devptrs(h->H, h->HI), dmask, imask);
+  h->stats.kernel_launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return GSPH_OK;
+}
+
+static int integ_forces(gsph_handle* h)
+{
+  int rc = gsph_update_properties(h); if (rc) return rc;
+  rc = gsph_zero_accelerations(h); if (rc) return rc;
+  if (h->cfg.self_gravity) rc = gsph_update_all_forces(h, NULL, 0);
+  else if (h->cfg.hydro_forces) rc = gsph_update_hydro_forces(h);
+  else { h->err = "Error: No forces included in simulation"; return GSPH_EINVAL; }   /* SphSimulation.cpp:467 */
+  if (rc) return rc;
+  return integ_scatter_results(h);
+}
+
+/* Simulation::ComputeGlobalTimestep on the host-order state */
+static int integ_global_timestep(gsph_handle* h, double* out)
+{
+  const unsigned long long init[2] = {0x7ff0000000000000ull, 0ull};
+  CUDA_TRY(h, cudaMemcpyAsync(h->integ.red, init, sizeof init, cudaMemcpyHostToDevice, h->stream));
+  INTEG_LAUNCH(integ_timestep_kernel, (int) h->N, devptrs(h->H, h->HI), h->dp, h->integ.cfg, h->integ.red);
+  unsigned long long res[2];
+  CUDA_TRY(h, cudaMemcpyAsync(res, h->integ.red, sizeof res, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (res[1]) { h->err = "Error : Hydro timestep too large"; return GSPH_ESTATE; }     /* SphIntegration.cpp:113-120 */
+  double ts; memcpy(&ts, &res[0], sizeof ts);
+  *out = ts;
+  return GSPH_OK;
+}
+
+int gsph_integrator_begin(gsph_handle* h, const gsph_integrator_config* cfg, int compute_forces, double t0)
+{
+  if (!h) return GSPH_EINVAL;
+  if (!cfg) { h->err = "gsph_integrator_begin: NULL config"; return GSPH_EINVAL; }
+  if (!h->uploaded) { h->err = "gsph_integrator_begin before gsph_upload"; return GSPH_ESTATE; }
+  if (!(cfg->accel_mult > 0) || !(cfg->courant_mult > 0) || !(cfg->energy_mult > 0)) { h->err = "gsph_integrator_begin: the time-step multipliers must be positive"; return GSPH_EINVAL; }
+  if (cfg->ntreebuildstep < 1 || cfg->ntreestockstep < 1) { h->err = "gsph_integrator_begin: ntreebuildstep and ntreestockstep must be >= 1"; return GSPH_EINVAL; }
+  if (h->Nstar > 0) { h->err = "gsph_integrator_begin: star particles are not integrated on the device"; return GSPH_EINVAL; }
+  if (h->slice_mode) { h->err = "gsph_integrator_begin: not with an active slice (multi-GPU decomposition)"; return GSPH_EINVAL; }
+  cudaSetDevice(h->device);
+  IntegState& I = h->integ;
+  if (I.cap < h->Ncap) {
+    for (int k = 0; k < 11; k++) { if (I.s0[k]) cudaFree(I.s0[k]); I.s0[k] = nullptr; }
+    I.cap = 0;
+    for (int k = 0; k < 11; k++) CUDA_TRY(h, cudaMalloc(&I.s0[k], (size_t) h->Ncap*sizeof(double)));
+    I.cap = h->Ncap;
+  }
+  if (!I.red) CUDA_TRY(h, cudaMalloc(&I.red, 2*sizeof(unsigned long long)));
+  I.cfg = *cfg; I.t = I.tlast = t0; I.Nsteps = 0; I.rebuild = true; I.on = false;
+  CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_all, 0));          /* the upload has landed */
+  if (compute_forces) {
+    int rc = gsph_build_tree(h, 0, 0.0); if (rc) return rc;
+    rc = integ_forces(h); if (rc) return rc;
+  }
+  INTEG_LAUNCH(integ_init_kernel, (int) h->N, devptrs(h->H, h->HI), integ_ptrs(h));
+  int rc = integ_global_timestep(h, &I.timestep); if (rc) return rc;
+  /* EndTimestep with part.dt = 0 (SphSimulation.cpp:561): u0 = u, dudt0 = dudt */
+  INTEG_LAUNCH(integ_end_kernel, (int) h->N, devptrs(h->H, h->HI), integ_ptrs(h), 0.0, I.cfg.energy_integration);
+  I.on = true;
+  return GSPH_OK;
+}
+
+int gsph_integrator_step(gsph_handle* h, int nsteps)
+{
+  if (!h) return GSPH_EINVAL;
+  if (!h->integ.on) { h->err = "gsph_integrator_step before gsph_integrator_begin"; return GSPH_ESTATE; }
+  if (nsteps < 0) { h->err = "gsph_integrator_step: nsteps < 0"; return GSPH_EINVAL; }
+  cudaSetDevice(h->device);
+  IntegState& I = h->integ;
+  for (int s = 0; s < nsteps; s++) {
+    /* MainLoop, SphSimulation.cpp:586-606 */
+    I.Nsteps++;
+    const double ts = I.timestep;
+    I.t = I.t + ts;
+    const double dt = I.t - I.tlast;
+    INTEG_LAUNCH(integ_advance_kernel, (int) h->N, devptrs(h->H, h->HI), integ_ptrs(h), h->dp, dt, ts,
+                 h->dp.tdavisc != GSPH_TDAVISC_NONE ? 1 : 0, I.cfg.energy_integration);
+    /* the staging arrays now hold a fresh "upload" */
+    CUDA_TRY(h, cudaEventRecord(h->ev_geom, h->stream));
+    CUDA_TRY(h, cudaEventRecord(h->ev_all, h->stream));
+    for (int k = 0; k < 3; k++) CUDA_TRY(h, cudaEventRecord(h->ev_axis[k], h->stream));
+    h->sorted_valid = false; h->density_done = false;
+    /* sphneib->BuildTree(rebuild_tree, Nsteps, ntreebuildstep, ntreestockstep, timestep, sph) */
+    const bool full = I.rebuild || I.Nsteps % I.cfg.ntreebuildstep == 0;
+    const int mode = full ? 0 : (I.Nsteps % I.cfg.ntreestockstep == 0 ? 1 : 2);
+    int rc = gsph_build_tree(h, mode, ts); if (rc) return rc;
+    rc = integ_forces(h); if (rc) return rc;
+    if (h->dp.any_periodic) {                                         /* SphSimulation.cpp:757-767 */
+      double hmax = 0.0;
+      rc = gsph_get_hmax(h, &hmax); if (rc) return rc;
+      hmax *= h->dp.kernrange;
+      for (int k = 0; k < h->cfg.ndim; k++)
+        if (h->dp.periodic[k] && h->dp.boxhalf[k] < 2*hmax) { h->err = "Error: Smoothing length too large, self-interaction will occur"; return GSPH_ESTATE; }
+    }
+    double next = 0.0;
+    rc = integ_global_timestep(h, &next); if (rc) return rc;
+    I.rebuild = false;
+    INTEG_LAUNCH(integ_end_kernel, (int) h->N, devptrs(h->H, h->HI), integ_ptrs(h), ts, I.cfg.energy_integration);
+    I.tlast = I.t;
+    I.timestep = next;
+  }
+  return GSPH_OK;
+}
+
+int gsph_integrator_state(gsph_handle* h, double* t, double* timestep, int64_t* nsteps)
+{
+  if (!h) return GSPH_EINVAL;
+  if (!h->integ.on) { h->err = "gsph_integrator_state before gsph_integrator_begin"; return GSPH_ESTATE; }
+  if (t) *t = h->integ.t;
+  if (timestep) *timestep = h->integ.timestep;
+  if (nsteps) *nsteps = h->integ.Nsteps;
   return GSPH_OK;
 }
 

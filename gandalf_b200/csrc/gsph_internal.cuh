@@ -108,8 +108,21 @@ struct DevStatus {
   unsigned long long cand_need;   /* largest candidate count requested */
 };
 
+/* device-resident main loop (gsph_integrator_*): start-of-step copies in host order */
+struct IntegState {
+  bool on = false;
+  gsph_integrator_config cfg;
+  double* s0[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   /* r0[3], v0[3], a0[3], u0, dudt0              */
+  int64_t cap = 0;
+  unsigned long long* red = nullptr;   /* [0] min dt (bits of a positive double), [1] bad-timestep count */
+  double t = 0.0, tlast = 0.0, timestep = 0.0;
+  int64_t Nsteps = 0;
+  bool rebuild = true;
+};
+
 struct gsph_handle {
   gsph_config cfg;
+  IntegState integ;
   DevParams dp;
   int device = 0;
   int sm_count = 0;

@@ -18,7 +18,7 @@ DEFAULTS = {
     "alpha_visc": 1.0, "alpha_visc_min": 0.1, "beta_visc": 2.0,
     "gravity_mac": "geometric", "multipole": "quadrupole", "thetamaxsqd": 0.1, "macerror": 0.0001,
     "Nleafmax": 6, "ntreebuildstep": 1, "ntreestockstep": 1, "create_sinks": 0, "conservative_sph_star_gravity": 1, "nbody_softening": 1, "sink_particles": 0,
-    "Nlevels": 1,
+    "Nlevels": 1, "sph_integration": "lfkdk", "accel_mult": 0.3, "courant_mult": 0.15, "energy_mult": 0.4,
 }
 for _k in range(3):
     DEFAULTS["boundary_lhs[%d]" % _k] = "open"
@@ -61,6 +61,22 @@ class Parameters(dict):
             for line in f:
                 self.parse_line(line)
         return self
+
+
+def integrator_config_from_params(p):
+    """-> _capi.IntegratorConfig for gsph_integrator_begin (the device-resident main loop): lfkdk with one
+    global time step; energy_integration as GradhSphSimulation.cpp:110-123 derives it from gas_eos."""
+    q = Parameters(p)
+    if q["sph_integration"] != "lfkdk":
+        raise ValueError("sph_integration = %s is not on the accelerated path (lfkdk only)" % q["sph_integration"])
+    if int(q["Nlevels"]) != 1:
+        raise ValueError("the device-resident main loop uses one global time step (Nlevels = 1)")
+    c = _capi.IntegratorConfig()
+    c.accel_mult, c.courant_mult, c.energy_mult = (float(q["accel_mult"]), float(q["courant_mult"]),
+                                                   float(q["energy_mult"]))
+    c.energy_integration = 1 if q["gas_eos"] == "energy_eqn" else 0
+    c.ntreebuildstep, c.ntreestockstep = int(q["ntreebuildstep"]), int(q["ntreestockstep"])
+    return c
 
 
 def config_from_params(p, device=0):

@@ -189,6 +189,26 @@ class GpuSphTree(object):
     def UpdateAllSphForces(self):
         self._check(self._L.gsph_update_all_forces(self._h, None, 0))
 
+    # ---- device-resident main loop (SphSimulation::MainLoop with lfkdk, Nlevels = 1) --------------
+    def IntegratorBegin(self, parts=None, compute_forces=True, t=0.0):
+        """tail of PostInitialConditionsSetup (SphSimulation.cpp:390-563) on the particles of the last
+        Upload (or `parts`): optional first density + force pass, r0/v0/a0/u0, first global time step"""
+        from .params import integrator_config_from_params
+        if parts is not None:
+            self.Upload(parts)
+        ic = integrator_config_from_params(self.params)
+        self._check(self._L.gsph_integrator_begin(self._h, C.byref(ic), 1 if compute_forces else 0, float(t)))
+
+    def MainLoop(self, nsteps=1):
+        """nsteps x SphSimulation::MainLoop (SphSimulation.cpp:574-880) without leaving the device"""
+        self._check(self._L.gsph_integrator_step(self._h, int(nsteps)))
+
+    def IntegratorState(self):
+        """-> (t, timestep of the next step, steps done)"""
+        t, ts, n = C.c_double(), C.c_double(), C.c_int64()
+        self._check(self._L.gsph_integrator_state(self._h, C.byref(t), C.byref(ts), C.byref(n)))
+        return t.value, ts.value, n.value
+
     def SetStars(self, r=None, m=None, h=None):
         """nbody->nbodydata for GradhSph::ComputeStarGravForces (GradhSph.cpp:699-743): star positions
         (Nstar, ndim), masses and smoothing lengths; applied by both force passes until cleared

@@ -300,6 +300,41 @@ typedef struct gsph_stats {
 } gsph_stats;
 int gsph_get_stats(gsph_handle* h, gsph_stats* st);
 
+/*--------------------------------------------------------------------------------------------------
+ * Device-resident main loop: leapfrog kick-drift-kick with ONE global time step
+ * (Nlevels = 1), so that particles stay in HBM between steps instead of travelling over PCIe
+ * around every operator call.  Replaces, for that configuration,
+ *   SphSimulation::MainLoop                      src/Hydrodynamics/SphSimulation.cpp:574-880
+ *   SphLeapfrogKDK::AdvanceParticles/EndTimestep src/Hydrodynamics/SphLeapfrogKDK.cpp:76-125,226-270
+ *   SphIntegration::Timestep                     src/Hydrodynamics/SphIntegration.cpp:76-124
+ *   Simulation::ComputeGlobalTimestep            src/Common/Simulation.cpp:1669-1745
+ *   TimeIntegration::CheckBoundaries             src/Common/Integration.cpp:11-75
+ * around the operators above (BuildTree, UpdateAllSphProperties, ZeroAccelerations, force pass).
+ * Not covered (GSPH_EINVAL): block time steps, star / sink particles, external potentials, dust.   */
+typedef struct gsph_integrator_config {
+  double  accel_mult, courant_mult, energy_mult;   /* Parameters.cpp:239,240,263 (0.3, 0.15, 0.4)      */
+  int32_t energy_integration;   /* 1: u is integrated explicitly (gas_eos = energy_eqn,
+                                   GradhSphSimulation.cpp:110-123); 0: u follows from the EOS         */
+  int32_t ntreebuildstep;       /* full rebuild every this many steps (HydroTree.cpp BuildTree)       */
+  int32_t ntreestockstep;       /* otherwise restock every this many steps, else extrapolate          */
+  int32_t reserved[5];
+} gsph_integrator_config;
+
+/* Start from the particles of the last gsph_upload (host order is kept).
+ *   compute_forces = 1 : first run BuildTree, UpdateAllSphProperties, ZeroAccelerations and the
+ *                        force pass once (the tail of PostInitialConditionsSetup,
+ *                        SphSimulation.cpp:390-465);
+ *   compute_forces = 0 : take the uploaded h, sound, div_v, a, du/dt, alpha ... as they are
+ *                        (restart from a complete state, e.g. the reference's own setup).
+ * Then r0, v0, a0, u0, dudt0 are set and the first global time step is computed
+ * (SphSimulation.cpp:480-486, 544-563).                                                            */
+int gsph_integrator_begin(gsph_handle* h, const gsph_integrator_config* cfg, int compute_forces, double t0);
+/* nsteps x MainLoop.  Afterwards gsph_download(..., GSPH_F_ALL) returns the particle state as the
+ * reference holds it at the end of MainLoop (corrected v, u; r0 = r ...).                          */
+int gsph_integrator_step(gsph_handle* h, int nsteps);
+/* simulation time, the time step the NEXT MainLoop will take, steps done since begin             */
+int gsph_integrator_state(gsph_handle* h, double* t, double* timestep, int64_t* nsteps);
+
 /* Kernel tables exactly as TabulatedKernel builds them (TabulatedKernel.cpp:58-105,
  * SmoothingKernel.h:585-605): which = 0 w0_s2, 1 womega_s2, 2 wzeta_s2, 3 w1, 4 wgrav, 5 wpot;
  * out[1000].  Host-side, no device needed (parity stage P0).                                      */

@@ -462,11 +462,12 @@ static int run(Parameters* params, const string& icfile, double perturb, const s
 #endif
     }
     double t1 = now();
+    const double timestep0 = sim->timestep;          // the step PostInitialConditionsSetup chose
     for (int s = 0; s < g_mainloop; s++) sim->MainLoop();
     double t_loop = now() - t1;
     H.dump_particles("loop");
-    fprintf(g_out, "{\"ref_mainloop\": true, \"gpu\": %s, \"N\": %d, \"steps\": %d, \"t\": %.17g, \"wall_s\": %.4f}\n",
-            g_gpu ? "true" : "false", H.sph->Nhydro, g_mainloop, (double) sim->t, t_loop);
+    fprintf(g_out, "{\"ref_mainloop\": true, \"gpu\": %s, \"N\": %d, \"steps\": %d, \"t\": %.17g, \"timestep\": %.17g, \"timestep0\": %.17g, \"wall_s\": %.4f}\n",
+            g_gpu ? "true" : "false", H.sph->Nhydro, g_mainloop, (double) sim->t, (double) sim->timestep, timestep0, t_loop);
     fflush(g_out);
   }
 

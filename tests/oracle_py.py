@@ -143,12 +143,12 @@ def params_from_dict(d):
     # mirror walls: (dimension, wall position) for boundary_lhs/rhs[k] = mirror.  The oracle treats them
     # the way the reference's density pass does: the mirror images are materialised as extra source
     # particles (Hydrodynamics.cpp:217-290: r_k -> 2*wall - r_k, v_k -> -v_k, incl. images of images)
-    p.mirrors = []
+    p.mirrors, p.mirror_sides = [], []
     for k in range(p.ndim):
         if d.get("boundary_lhs[%d]" % k, "open") == "mirror":
-            p.mirrors.append((k, float(d.get("boxmin[%d]" % k, 0.0))))
+            p.mirrors.append((k, float(d.get("boxmin[%d]" % k, 0.0)))); p.mirror_sides.append("lhs")
         if d.get("boundary_rhs[%d]" % k, "open") == "mirror":
-            p.mirrors.append((k, float(d.get("boxmax[%d]" % k, 0.0))))
+            p.mirrors.append((k, float(d.get("boxmax[%d]" % k, 0.0)))); p.mirror_sides.append("rhs")
     return p
 
 
@@ -344,3 +344,102 @@ class Tree:
         if rc != 0:
             raise RuntimeError("oracle tree gravity: unsupported parameters")
         return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# main loop (lfkdk, one global time step): restatement of SphSimulation::MainLoop around the operator
+# functions above.  TEST INFRASTRUCTURE, the checker of gsph_integrator_*.
+# ---------------------------------------------------------------------------------------------------
+def global_timestep(p, s, courant_mult, accel_mult, energy_mult, energy_integration):
+    """SphIntegration::Timestep per particle (SphIntegration.cpp:76-124) and the minimum
+    (Simulation::ComputeGlobalTimestep, Simulation.cpp:1690-1730)"""
+    h, dv = s["h"], np.abs(s["div_v"])
+    if p.hydro_forces == 1:
+        ts = courant_mult*h/(s["sound"] + h*dv + 1.0e-50)
+    else:
+        ts = courant_mult*h/(h*dv + 1.0e-50)
+    a = s["a"].reshape(len(h), -1)
+    a2 = a[:, 0]*a[:, 0]
+    for k in range(1, a.shape[1]):
+        a2 = a2 + a[:, k]*a[:, k]
+    ts = np.minimum(ts, accel_mult*np.sqrt(h/(np.sqrt(a2) + 1.0e-50)))
+    if energy_integration:
+        te = energy_mult*(s["u"]/(np.abs(s["dudt"]) + 1.0e-20))
+        ts = np.where(s["ptype"] == 0, np.minimum(ts, te), ts)
+    return float(ts.min())
+
+
+def mainloop(params, setup, steps):
+    """`steps` x SphSimulation::MainLoop (SphSimulation.cpp:574-880; SphLeapfrogKDK.cpp:76-125,226-270;
+    Integration.cpp:11-75) from the reference's post-setup particle state; full tree rebuild every step.
+    -> (state dict, t, next timestep)"""
+    p = params_from_dict(params)
+    nd = p.ndim
+    cm, am, em = (float(params.get("courant_mult", 0.15)), float(params.get("accel_mult", 0.3)),
+                  float(params.get("energy_mult", 0.4)))
+    energy = params.get("gas_eos", "energy_eqn") == "energy_eqn"
+    tdav = params.get("time_dependent_avisc", "none") != "none"
+    s = {k: np.array(v, copy=True) for k, v in setup.items()}
+    N = len(s["m"])
+    for k in ("r", "v", "a", "atree"):
+        s[k] = s[k].reshape(N, nd)
+    r0, v0, a0 = s["r"].copy(), s["v"].copy(), s["a"].copy()
+    u0, dudt0 = s["u"].copy(), s["dudt"].copy()
+    timestep = global_timestep(p, s, cm, am, em, energy)
+    t = tlast = 0.0
+    size = [p.boxmax[k] - p.boxmin[k] for k in range(nd)]
+    for _ in range(steps):
+        t = t + timestep
+        dt = t - tlast
+        s["r"] = r0 + v0*dt + 0.5*a0*dt*dt
+        s["v"] = v0 + a0*dt
+        if tdav:
+            s["alpha"] = s["alpha"] + s["dalphadt"]*timestep
+        if energy:
+            s["u"] = u0 + dudt0*dt
+        for k in range(nd):                               # CheckBoundaries
+            walls = dict((side, w) for (kk, w), side in zip(getattr(p, "mirrors", []),
+                                                           getattr(p, "mirror_sides", [])) if kk == k)
+            lo = s["r"][:, k] < p.boxmin[k]
+            if p.periodic[k]:
+                s["r"][lo, k] += size[k]; r0[lo, k] += size[k]
+            if "lhs" in walls:
+                for arr in (s["r"], r0):
+                    arr[lo, k] = 2.0*p.boxmin[k] - arr[lo, k]
+                for arr in (s["v"], v0, s["a"], a0):
+                    arr[lo, k] = -arr[lo, k]
+            hi = s["r"][:, k] > p.boxmax[k]
+            if p.periodic[k]:
+                s["r"][hi, k] -= size[k]; r0[hi, k] -= size[k]
+            if "rhs" in walls:
+                for arr in (s["r"], r0):
+                    arr[hi, k] = 2.0*p.boxmax[k] - arr[hi, k]
+                for arr in (s["v"], v0, s["a"], a0):
+                    arr[hi, k] = -arr[hi, k]
+        dens = density(p, s["r"], s["m"], s["h"], s["u"])
+        for k in ("h", "rho", "invomega", "zeta", "hfactor", "hrangesqd", "u", "sound", "pressure"):
+            s[k] = dens[k]
+        if tdav and params.get("time_dependent_avisc") == "cd2010":
+            s["alpha"], s["dalphadt"] = cd2010_switch(p, s["r"], s["v"], s["a"], s["m"], dens, s["alpha"])
+        if p.self_gravity:
+            tr = Tree(p, s["r"], s["v"], s["m"], s["h"], s["atree"], s["gpot"])
+            f = tr.hydro_grav_forces(s)
+            s["atree"], s["gpot"] = f["atree"], f["gpot"]
+        else:
+            f = hydro_forces(p, s)
+        s["a"], s["dudt"], s["div_v"] = f["a"], f["dudt"], f["div_v"]
+        if params.get("time_dependent_avisc", "none") == "mm97":
+            # the force pass ADDS its dalphadt to the particle (GradhSphTree.cpp:403) and MainLoop's
+            # Sph::ZeroAccelerations (Sph.cpp:126-140) does not clear it: the reference accumulates it
+            s["dalphadt"] = s["dalphadt"] + f["dalphadt"]
+        nxt = global_timestep(p, s, cm, am, em, energy)
+        s["v"] = s["v"] + 0.5*timestep*(s["a"] - a0)          # EndTimestep, part.dt = the step just taken
+        r0, v0, a0 = s["r"].copy(), s["v"].copy(), s["a"].copy()
+        if energy:
+            u = s["u"] + 0.5*(s["dudt"] - dudt0)*timestep
+            u = np.where(u <= 0.0, u0 + dudt0*timestep, u)
+            s["u"] = u
+            u0, dudt0 = u.copy(), s["dudt"].copy()
+        tlast = t
+        timestep = nxt
+    return s, t, timestep

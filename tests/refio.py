@@ -111,19 +111,19 @@ def csr_rows(off, idx):
     return [idx[off[i]:off[i + 1]] for i in range(len(off) - 1)]
 
 
-def run_mainloop(params, ic, steps, gpu, timeout=1800):
+def run_mainloop(params, ic, steps, gpu, timeout=1800, kind="gpu", dumps=""):
     """N steps of the reference's own SphSimulation::MainLoop through oracle/_ref/ref_harness_gpu;
     gpu=True swaps sim->sphneib for gandalf_b200/host/GpuSphTree.h first.  -> (arrays, info json)"""
-    exe = harness_path("gpu")
+    exe = harness_path(kind)
     if exe is None:
-        raise FileNotFoundError("oracle/_ref/ref_harness_gpu not built (make -C oracle ref_gpu)")
+        raise FileNotFoundError("oracle/_ref/ref_harness_%s not built (make -C oracle ref_%s)" % (kind, kind))
     work = tempfile.mkdtemp(prefix="gsph_loop_")
     try:
         dat = os.path.join(work, "params.dat")
         write_dat(dat, params)
         icf = os.path.join(work, "ic.bin")
         write_ic(icf, int(params["ndim"]), ic["r"], ic["v"], ic["m"], ic["h"], ic["u"])
-        cmd = [exe, dat, os.path.join(work, "out"), "--dump", "", "--quiet", "--in", icf, "--mainloop", str(int(steps))]
+        cmd = [exe, dat, os.path.join(work, "out"), "--dump", dumps, "--quiet", "--in", icf, "--mainloop", str(int(steps))]
         if gpu:
             cmd.append("--gpu")
         res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=timeout)

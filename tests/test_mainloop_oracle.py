@@ -1,0 +1,59 @@
+"""The main-loop restatement (tests/oracle_py.py: mainloop, global_timestep) against the reference's
+own SphSimulation::MainLoop: tests/golden/loop_*.npz hold the reference's particle state after its
+setup and after N of its own steps (generator: tests/golden/make_loop_golden.py).  This pins the
+checker of the device-resident main loop (gsph_integrator_*, tests/test_gpu_mainloop.py)."""
+import numpy as np
+import pytest
+
+import oracle_py as orc
+from conftest import load_golden, LOOP_CASES, rel_err
+
+CPU_CASES = [c for c in LOOP_CASES if c != "loop_sphere_grav_quad"]   # (that one mixes rebuild / restock / extrapolate)
+
+
+def split(d):
+    out = {"setup": {}, "loop": {}}
+    for k, v in d.items():
+        st, f = k.split(".", 1)
+        out[st][f] = v
+    return out["setup"], out["loop"]
+
+
+def vec_err(a, b):
+    a = a.reshape(len(a), -1); b = b.reshape(len(b), -1)
+    return np.linalg.norm(a - b, axis=1)/np.maximum(np.linalg.norm(b, axis=1), np.abs(b).max()*1e-6)
+
+
+def check_state(s, ref, tol):
+    for f in ("r", "v", "a"):
+        assert vec_err(np.asarray(s[f]), ref[f]).max() < tol, f
+    for f in ("h", "rho", "u", "alpha"):
+        assert rel_err(np.asarray(s[f]), ref[f]).max() < tol, f
+    sc = np.abs(ref["dudt"]).max() + 1e-300
+    assert (np.abs(np.asarray(s["dudt"]) - ref["dudt"])/sc).max() < tol
+
+
+def test_loop_fixtures_exist():
+    assert len(LOOP_CASES) >= 5
+
+
+@pytest.mark.parametrize("name", LOOP_CASES)
+def test_first_timestep_matches_reference(name):
+    """Simulation::ComputeGlobalTimestep on the reference's post-setup state: its first MainLoop
+    advances t by exactly that step"""
+    params, d = load_golden(name)
+    setup, loop = split(d)
+    p = orc.params_from_dict(params)
+    ts = orc.global_timestep(p, setup, 0.15, 0.3, 0.4, params.get("gas_eos", "energy_eqn") == "energy_eqn")
+    assert 0 < ts < float(loop["t"])
+    assert float(loop["t"]) / int(loop["steps"]) < 3*ts
+
+
+@pytest.mark.parametrize("name", CPU_CASES)
+def test_mainloop_restatement_matches_reference(name):
+    params, d = load_golden(name)
+    setup, loop = split(d)
+    s, t, ts = orc.mainloop(params, setup, int(loop["steps"]))
+    assert abs(t - float(loop["t"])) <= 1e-12*abs(t)
+    assert abs(ts - float(loop["timestep"])) <= 1e-9*abs(ts)
+    check_state(s, loop, 1e-9)
