@@ -666,6 +666,96 @@ partition_v2_kernel(int N, int level, int cur, int plo, int phi, int klo, ListPt
   }
 }
 
+/*================================================================================================
+ * Multi-GPU build, phase 1, for NDIM > 1: a rank does not sort all particles to find its shard.
+ * The top log2(world) splits on the path to its node are found by SELECTION: the median entry of a
+ * node along its split axis is the (cnt/2)-th smallest (coordinate, id) pair -- a radix select over
+ * the 12 bytes of (order-preserving key of the double, particle id), one histogram pass per byte,
+ * ending early when one candidate is left.  (key, id) is exactly the order of the stable radix sort
+ * of iota ids that the single-GPU build uses, so the shard -- and therefore the tree -- is the
+ * same.  The rank then compacts its half, descends, and finally sorts and builds only its own
+ * N/world particles.
+ *================================================================================================*/
+__device__ __forceinline__ unsigned long long sort_key_of(double x)
+{
+  if (x == 0.0) x = 0.0;                                   /* -0.0 sorts with +0.0 */
+  const unsigned long long b = (unsigned long long) __double_as_longlong(x);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+/* first nb bytes (most significant first) of the 12-byte composite (key, id) equal to (pk, pid)? */
+__device__ __forceinline__ bool prefix_match(unsigned long long k, unsigned id, int nb, unsigned long long pk, unsigned pid)
+{
+  if (nb == 0) return true;
+  if (nb <= 8) return (k >> (64 - 8*nb)) == (pk >> (64 - 8*nb));
+  if (k != pk) return false;
+  if (nb >= 12) return id == pid;
+  return (id >> (32 - 8*(nb - 8))) == (pid >> (32 - 8*(nb - 8)));
+}
+
+/* histogram of byte nb of the composite over the candidates that match the prefix; cand == nullptr: ids 0..cnt-1 */
+__global__ void select_hist_kernel(int cnt, const int* __restrict__ cand, const double* __restrict__ r, int nb,
+                                   unsigned long long pk, unsigned pid, unsigned* __restrict__ hist)
+{
+  __shared__ unsigned sh[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) sh[i] = 0;
+  __syncthreads();
+  for (int i = blockIdx.x*blockDim.x + threadIdx.x; i < cnt; i += gridDim.x*blockDim.x) {
+    const unsigned id = cand ? (unsigned) cand[i] : (unsigned) i;
+    const unsigned long long k = sort_key_of(r[id]);
+    if (prefix_match(k, id, nb, pk, pid)) {
+      const unsigned dig = nb < 8 ? (unsigned)((k >> (56 - 8*nb)) & 255ull) : ((id >> (24 - 8*(nb - 8))) & 255u);
+      const unsigned peers = __match_any_sync(__activemask(), dig);
+      if ((int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&sh[dig], (unsigned) __popc(peers));
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+
+/* the (single) candidate that matches the first nb bytes */
+__global__ void select_find_kernel(int cnt, const int* __restrict__ cand, const double* __restrict__ r, int nb,
+                                   unsigned long long pk, unsigned pid, int* __restrict__ out_id, double* __restrict__ out_r)
+{
+  for (int i = blockIdx.x*blockDim.x + threadIdx.x; i < cnt; i += gridDim.x*blockDim.x) {
+    const unsigned id = cand ? (unsigned) cand[i] : (unsigned) i;
+    const double x = r[id];
+    if (prefix_match(sort_key_of(x), id, nb, pk, pid)) { *out_id = (int) id; *out_r = x; }
+  }
+}
+
+/* which side of the median entry (ks, ids) a particle lies on */
+struct SideOfMedian {
+  const double* r; unsigned long long ks; unsigned ids; bool right;
+  __device__ __forceinline__ bool operator()(const int& id) const
+  {
+    const unsigned long long k = sort_key_of(r[id]);
+    const bool ge = k > ks || (k == ks && (unsigned) id >= ids);
+    return ge == right;
+  }
+};
+
+__global__ void gather_keys_kernel(int n, const int* __restrict__ ids, const double* __restrict__ r, double* __restrict__ out)
+{
+  const int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i < n) out[i] = r[ids[i]];
+}
+
+/* first / count of EVERY node of the balanced tree: sizes N -> (N/2, N - N/2) do not depend on the data */
+__global__ void fill_topology_kernel(int N, int ltot, int* __restrict__ first, int* __restrict__ count)
+{
+  const int n = blockIdx.x*blockDim.x + threadIdx.x;
+  if (n >= (2 << ltot) - 1) return;
+  int l = 31 - __clz(n + 1);
+  const int k = n + 1 - (1 << l);
+  int a = 0, b = N;
+  for (int bit = l - 1; bit >= 0; bit--) {
+    const int left = (b - a)/2;
+    if ((k >> bit) & 1) a += left; else b = a + left;
+  }
+  first[n] = a; count[n] = b - a;
+}
+
 /* phase 0: whole build on this GPU.  phase 1 / 2: multi-GPU build -- every rank sorts and splits the
  * top log2(world) levels (they need all particles), then re-orders only the lists of ITS subtree
  * (1/world of the per-level work); phase 1 ends with this rank's slice of the tree order in
@@ -713,9 +803,18 @@ int build_tree_v2(gsph_handle* h, int phase, int shard_rank, int shard_world)
   cub::DeviceScan::ExclusiveSum(nullptr, cub_scan2, (const int*) nullptr, (int*) nullptr, nleaf, s);
   size_t cub_bytes = cub_sort > cub_scan ? cub_sort : cub_scan;
   if (cub_scan2 > cub_bytes) cub_bytes = cub_scan2;
+  const bool by_selection = phase == 1 && nd > 1;     /* multi-GPU shard found by selection, see above */
+  size_t extra = 0;
+  if (by_selection) {
+    size_t cub_sel = 0;
+    cub::DeviceSelect::If(nullptr, cub_sel, cub::CountingInputIterator<int>(0), (int*) nullptr, (int*) nullptr, N,
+                          SideOfMedian{nullptr, 0ull, 0u, false}, s);
+    if (cub_sel > cub_bytes) cub_bytes = cub_sel;
+    extra = 2*Npad*sizeof(int) + Npad*sizeof(double) + (size_t) 4*nleaf*sizeof(int) + 8192;
+  }
   const size_t need = Npad*sizeof(int)*(size_t)(nd*2*(1 + NR) + nd) + Npad*sizeof(double)
                       + (size_t) nleaf*(sizeof(double)*4*nd + 1 + 2*sizeof(int)) + (size_t) nd*ntile*sizeof(int)
-                      + cub_bytes + 256*64 + 4096*2*nd*sizeof(double);
+                      + cub_bytes + 256*64 + 4096*2*nd*sizeof(double) + extra;
   if (need > h->scratch_bytes) {
     if (h->scratch) cudaFree(h->scratch);
     h->scratch = nullptr; h->scratch_bytes = 0;
@@ -746,7 +845,121 @@ int build_tree_v2(gsph_handle* h, int phase, int shard_rank, int shard_world)
   const int rb_blocks = 1024;
   double* rbpart = B.get<double>((size_t) rb_blocks*2*nd);
   void* cubtmp = B.get<char>(cub_bytes);
+  int* candbuf[2] = {nullptr, nullptr}; double* keys_in = nullptr; int* lfirst = nullptr; int* lcount = nullptr;
+  unsigned* hist = nullptr; int* sel_i = nullptr; double* sel_r = nullptr;
+  if (by_selection) {
+    candbuf[0] = B.get<int>(Npad); candbuf[1] = B.get<int>(Npad);
+    keys_in = B.get<double>(Npad);
+    lfirst = B.get<int>((size_t) 2*nleaf); lcount = B.get<int>((size_t) 2*nleaf);
+    hist = B.get<unsigned>(256); sel_i = B.get<int>(2); sel_r = B.get<double>(1);
+  }
   if (B.off > B.cap) { h->err = "internal: tree scratch layout overflow"; return GSPH_ENOMEM; }
+
+  if (by_selection) {
+    int ltop = 0;
+    while ((1 << ltop) < shard_world) ltop++;
+    cudaEventRecord(h->evk[3][0], s);
+    for (int d = 0; d < nd; d++) cudaStreamWaitEvent(s, h->ev_axis[d], 0);
+    cudaStreamWaitEvent(s, h->ev_geom, 0);
+    root_box_kernel<NDIM><<<rb_blocks, 256, 0, s>>>(N, Hh, h->dp.kernrange, rbpart);
+    root_box_final<NDIM><<<1, 32, 0, s>>>(rb_blocks, rbpart, L.ib[0][0][0], L.ib[0][0][1], L.ib[0][0][2],
+                                          L.ib[0][1][0], L.ib[0][1][1], L.ib[0][1][2]);
+    h->stats.kernel_launches += 2;
+    double box[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    for (int b = 0; b < 2; b++) for (int d = 0; d < nd; d++)
+      CUDA_TRY(h, cudaMemcpyAsync(&box[b][d], L.ib[0][b][d], sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    /* descend the path to this rank's node of level ltop */
+    const int* cand = nullptr;                         /* nullptr: all particles, ids 0..N-1 */
+    int cnt = N, slo = 0, which = 0;
+    for (int l = 0; l < ltop; l++) {
+      int kd = 0; double rkmax = 0.0;                   /* split axis: widest side of the inherited box, KDTree.cpp:503-512 */
+      for (int d = 0; d < nd; d++) { const double w = box[1][d] - box[0][d]; if (w > rkmax) { rkmax = w; kd = d; } }
+      const int left = cnt/2;
+      const double* rk = h->H[F_RX + kd];
+      unsigned long long pk = 0ull; unsigned pid = 0u; int nb = 0; unsigned target = (unsigned) left;
+      bool single = false;
+      while (nb < 12 && !single) {
+        CUDA_TRY(h, cudaMemsetAsync(hist, 0, 256*sizeof(unsigned), s));
+        select_hist_kernel<<<h->sm_count*8, 256, 0, s>>>(cnt, cand, rk, nb, pk, pid, hist);
+        unsigned hh[256];
+        CUDA_TRY(h, cudaMemcpyAsync(hh, hist, sizeof hh, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(h, cudaStreamSynchronize(s));
+        h->stats.kernel_launches++;
+        int bin = 0;
+        while (bin < 255 && target >= hh[bin]) { target -= hh[bin]; bin++; }
+        if (target >= hh[bin]) { h->err = "internal: median selection lost its target"; return GSPH_ECUDA; }
+        if (nb < 8) pk |= (unsigned long long) bin << (56 - 8*nb);
+        else pid |= (unsigned) bin << (24 - 8*(nb - 8));
+        nb++;
+        single = hh[bin] == 1;
+      }
+      select_find_kernel<<<h->sm_count*8, 256, 0, s>>>(cnt, cand, rk, nb, pk, pid, sel_i, sel_r);
+      int idm = 0; double rdiv = 0.0;
+      CUDA_TRY(h, cudaMemcpyAsync(&idm, sel_i, sizeof(int), cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(h, cudaMemcpyAsync(&rdiv, sel_r, sizeof(double), cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(h, cudaStreamSynchronize(s));
+      unsigned long long ks; { double x = rdiv == 0.0 ? 0.0 : rdiv; unsigned long long b; memcpy(&b, &x, 8); ks = (b >> 63) ? ~b : (b | 0x8000000000000000ull); }
+      const bool right = (shard_rank >> (ltop - 1 - l)) & 1;
+      int* out = candbuf[which];
+      size_t tb = cub_bytes;
+      const SideOfMedian op{rk, ks, (unsigned) idm, right};
+      if (cand) cub::DeviceSelect::If(cubtmp, tb, cand, out, sel_i + 1, cnt, op, s);
+      else cub::DeviceSelect::If(cubtmp, tb, cub::CountingInputIterator<int>(0), out, sel_i + 1, cnt, op, s);
+      int got = 0;
+      CUDA_TRY(h, cudaMemcpyAsync(&got, sel_i + 1, sizeof(int), cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(h, cudaStreamSynchronize(s));
+      h->stats.kernel_launches += 3;
+      const int want = right ? cnt - left : left;
+      if (got != want) { h->err = "internal: shard selection size mismatch"; return GSPH_ECUDA; }
+      if (right) { slo += left; box[0][kd] = rdiv; } else box[1][kd] = rdiv;
+      cand = out; cnt = got; which ^= 1;
+    }
+    /* the local build: this shard's particles only, as a tree of ltot - ltop levels */
+    const int Nloc = cnt, lloc = ltot - ltop;
+    for (int b = 0; b < 2; b++) for (int d = 0; d < nd; d++)
+      CUDA_TRY(h, cudaMemcpyAsync(L.ib[0][b][d], &box[b][d], sizeof(double), cudaMemcpyHostToDevice, s));
+    for (int d = 0; d < nd; d++) {
+      gather_keys_kernel<<<(Nloc + 255)/256, 256, 0, s>>>(Nloc, cand, h->H[F_RX + d], keys_in);
+      size_t tb = cub_bytes;
+      cub::DeviceRadixSort::SortPairs(cubtmp, tb, (const double*) keys_in, keys_out, cand, L.ids[d][0], Nloc, 0, 64, s);
+      rank_scatter_kernel<<<(Nloc + 255)/256, 256, 0, s>>>(Nloc, L.ids[d][0], rank[d]);
+      h->stats.kernel_launches += 10;
+    }
+    fill_ranks_kernel<NDIM><<<(Nloc + 255)/256, 256, 0, s>>>(Nloc, L);
+    h->stats.kernel_launches++;
+    cudaEventRecord(h->evk[3][1], s); h->evk_used[3] = true;
+    cudaEventRecord(h->evk[4][0], s);
+    L.first = lfirst; L.count = lcount;
+    const int ntile_loc = (Nloc + TB_TILE - 1)/TB_TILE;
+    L.ntile = ntile_loc;
+    {
+      const int one[2] = {0, Nloc};
+      CUDA_TRY(h, cudaMemcpyAsync(lfirst, &one[0], sizeof(int), cudaMemcpyHostToDevice, s));
+      CUDA_TRY(h, cudaMemcpyAsync(lcount, &one[1], sizeof(int), cudaMemcpyHostToDevice, s));
+    }
+    int cur = 0;
+    for (int l = 0; l < lloc; l++) {
+      const int nn = 1 << l;
+      split_nodes_v2_kernel<NDIM><<<(nn + 127)/128, 128, 0, s>>>(l, cur, 0, nn, L);
+      size_t tb = cub_bytes;
+      cub::DeviceScan::ExclusiveSum(cubtmp, tb, L.noderb, L.noderb, nn, s);
+      const dim3 grid(ntile_loc, nd);
+      count_right_kernel<NDIM><<<grid, TB_THREADS, 0, s>>>(Nloc, l, cur, 0, Nloc, L);
+      tb = cub_bytes;
+      cub::DeviceScan::ExclusiveSum(cubtmp, tb, L.tilecnt, L.tilecnt, nd*ntile_loc, s);
+      partition_v2_kernel<NDIM><<<grid, TB_THREADS, 0, s>>>(Nloc, l, cur, 0, Nloc, 0, L);
+      cur ^= 1;
+      h->stats.kernel_launches += 7;
+    }
+    fill_topology_kernel<<<(T.ncell + 255)/256, 256, 0, s>>>(N, ltot, T.first, T.count);
+    h->stats.kernel_launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaMemcpyAsync(h->perm + slo, L.ids[0][cur], sizeof(int)*(size_t) Nloc, cudaMemcpyDeviceToDevice, s));
+    cudaEventRecord(h->evk[4][1], s); h->evk_used[4] = true;
+    h->have_tree = false; h->sorted_valid = false;
+    return GSPH_OK;
+  }
 
   /* the presorted lists: the sort of an axis starts as soon as that coordinate of the upload has landed */
   cudaEventRecord(h->evk[3][0], s);

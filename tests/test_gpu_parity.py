@@ -566,3 +566,54 @@ def test_potmin_flag_for_sink_search():
     want = ~((gpot[None, :] > 1.000000001*gpot[:, None]) & inside).any(axis=1)
     assert got.sum() > 0 and np.array_equal(got[~edge], want[~edge])
     tree.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# multi-GPU tree build on ONE GPU: every rank's shard is built in turn (selection of the top splits,
+# local sort + build of its N/world particles), the slices of the tree order are put together like
+# the host layer's all-gather does, and the finished tree must be the single-GPU tree bit for bit
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("ndim,world,lattice", [(3, 2, False), (3, 4, False), (3, 8, False), (3, 8, True), (2, 4, True),
+                                                (2, 8, False)])
+def test_sharded_tree_build_equals_single_gpu(ndim, world, lattice):
+    import torch
+    import gandalf_b200 as g
+    from gandalf_b200.domain import _CudaArray, shard_ranges
+    rng = np.random.default_rng(100*ndim + world)
+    n = 28 if ndim == 3 else 150
+    gx = (np.arange(n) + 0.5)/n
+    r = np.stack(np.meshgrid(*([gx]*ndim), indexing="ij"), -1).reshape(-1, ndim)
+    if not lattice:                                  # lattice: thousands of equal coordinates (ties -> particle id)
+        r = r + 0.4/n*rng.uniform(-1, 1, r.shape)
+    r = r[rng.permutation(len(r))][:len(r) - 37]     # ragged size, shuffled ids
+    r = r - 0.3                                      # some negative coordinates
+    N = len(r)
+    params = {"ndim": ndim, "Nleafmax": 6}
+    ps = g.ParticleSet(N, ndim).set(r=r, m=1.0/N, h=1.3/n, u=1.0)
+    ps["v"][...] = rng.normal(size=(N, ndim))
+    ref = g.GpuSphTree(params)
+    ref.BuildTree(True, 0, 1, 1, 0.0, ps)
+    leaf_ref, cells_ref = ref.TreeLeafOf(), ref.TreeCells()
+    ptr, _ = ref.DeviceField("perm")
+    perm_ref = torch.as_tensor(_CudaArray(ptr, N, "<i4"), device="cuda").cpu().numpy().copy()
+    ref.close()
+
+    tree = g.GpuSphTree(params)
+    tree.Upload(ps)
+    perm = np.full(N, -1, dtype=np.int32)
+    for rank in range(world):
+        tree.BuildTreeShardBegin(rank, world)
+        lo, hi = tree.TreeShardRange(rank, world)
+        assert (lo, hi) == shard_ranges(N, world)[rank]
+        ptr, _ = tree.DeviceField("perm")
+        dev = torch.as_tensor(_CudaArray(ptr, N, "<i4"), device="cuda")
+        perm[lo:hi] = dev[lo:hi].cpu().numpy()
+    assert np.array_equal(perm, perm_ref)
+    dev.copy_(torch.from_numpy(perm).cuda())
+    torch.cuda.synchronize()
+    tree.BuildTreeShardFinish()
+    assert np.array_equal(tree.TreeLeafOf(), leaf_ref)
+    cells = tree.TreeCells()
+    for k in cells_ref:
+        assert np.array_equal(cells[k], cells_ref[k]), k
+    tree.close()
