@@ -1096,29 +1096,56 @@ int gsph_update_hydro_forces(gsph_handle* h)
   return GSPH_OK;
 }
 
-int gsph_update_all_forces(gsph_handle* h, const double* stars, int Nstar)
+/* UpdateAllSphForces in two halves, so that a host can fetch what the first half already finished
+ * (du/dt, div_v, dalpha/dt, levelneib) while the second half runs:
+ *   begin  : the neighbour half -- hydro + smoothed-gravity pair terms (GradhSphTree.cpp:515-555);
+ *   finish : the tree-gravity half -- interaction lists, direct sums, cells (:557-598) -- and the stars. */
+int gsph_update_all_forces_begin(gsph_handle* h)
 {
   if (!h) return GSPH_EINVAL;
   if (!h->have_tree || !h->sorted_valid) { h->err = "gsph_update_all_forces before gsph_build_tree"; return GSPH_ESTATE; }
   if (!h->cfg.self_gravity) { h->err = "gsph_update_all_forces needs self_gravity = 1 in the config"; return GSPH_EINVAL; }
   cudaSetDevice(h->device);
-  if (stars || Nstar > 0) { const int rs = gsph_set_stars(h, stars, Nstar); if (rs) return rs; }
+  h->forces_half_done = false;
   Timer tm(h, &h->stats.ms_forces);
   int rc = reset_status(h); if (rc) return rc;
   rc = gsph_prepare_done_flags(h); if (rc) return rc;
   rc = run_with_regrow(h, "gsph_update_all_forces(neighbours)", pass_hydro, 1);
   if (rc) return rc;
-  const DevStatus keep = *h->status_host;
-  rc = gsph_prepare_done_flags(h); if (rc) return rc;
+  tm.stop();
+  force_stats(h);
+  h->forces_half_done = true;
+  return GSPH_OK;
+}
+
+int gsph_update_all_forces_finish(gsph_handle* h)
+{
+  if (!h) return GSPH_EINVAL;
+  if (!h->forces_half_done) { h->err = "gsph_update_all_forces_finish before gsph_update_all_forces_begin"; return GSPH_ESTATE; }
+  cudaSetDevice(h->device);
+  h->forces_half_done = false;
+  const gsph_stats first = h->stats;
+  Timer tm(h, &h->stats.ms_forces);
+  int rc = gsph_prepare_done_flags(h); if (rc) return rc;
   h->gstack_on = false;                               /* first launch: shared-memory stacks */
   rc = run_with_regrow(h, "gsph_update_all_forces(gravity)", pass_gravity, 0);
   if (rc) return rc;
   rc = gsph_run_star_forces(h);                       /* GradhSphTree.cpp:600-607 */
   if (rc) return rc;
   tm.stop();
-  (void) keep;
+  h->stats.ms_forces += first.ms_forces;
   force_stats(h);
   return GSPH_OK;
+}
+
+int gsph_update_all_forces(gsph_handle* h, const double* stars, int Nstar)
+{
+  if (!h) return GSPH_EINVAL;
+  cudaSetDevice(h->device);
+  if (stars || Nstar > 0) { const int rs = gsph_set_stars(h, stars, Nstar); if (rs) return rs; }
+  const int rc = gsph_update_all_forces_begin(h);
+  if (rc) return rc;
+  return gsph_update_all_forces_finish(h);
 }
 
 int gsph_get_hmax(gsph_handle* h, double* hmax)

@@ -123,6 +123,7 @@ struct IntegState {
 struct gsph_handle {
   gsph_config cfg;
   IntegState integ;
+  bool forces_half_done = false;       /* gsph_update_all_forces_begin done, _finish pending */
   DevParams dp;
   int device = 0;
   int sm_count = 0;

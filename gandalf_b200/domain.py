@@ -179,3 +179,9 @@ class DomainDriver(object):
 
     def UpdateAllSphForces(self):
         self.tree.UpdateAllSphForces()
+
+    def UpdateAllSphForcesBegin(self):
+        self.tree.UpdateAllSphForcesBegin()
+
+    def UpdateAllSphForcesFinish(self):
+        self.tree.UpdateAllSphForcesFinish()

@@ -189,6 +189,14 @@ class GpuSphTree(object):
     def UpdateAllSphForces(self):
         self._check(self._L.gsph_update_all_forces(self._h, None, 0))
 
+    def UpdateAllSphForcesBegin(self):
+        """neighbour half of UpdateAllSphForces; afterwards dudt, div_v, dalphadt, levelneib are final and
+        Download(..., wait=False) of them overlaps UpdateAllSphForcesFinish (tree gravity + stars)"""
+        self._check(self._L.gsph_update_all_forces_begin(self._h))
+
+    def UpdateAllSphForcesFinish(self):
+        self._check(self._L.gsph_update_all_forces_finish(self._h))
+
     # ---- device-resident main loop (SphSimulation::MainLoop with lfkdk, Nlevels = 1) --------------
     def IntegratorBegin(self, parts=None, compute_forces=True, t=0.0):
         """tail of PostInitialConditionsSetup (SphSimulation.cpp:390-563) on the particles of the last

@@ -206,6 +206,11 @@ int gsph_update_properties(gsph_handle* h);
 int gsph_zero_accelerations(gsph_handle* h);
 int gsph_update_hydro_forces(gsph_handle* h);
 int gsph_update_all_forces(gsph_handle* h, const double* stars, int Nstar);
+/* The same pass in two halves (stars: gsph_set_stars).  After _begin the neighbour half is done:
+ * du/dt, div_v, dalpha/dt and levelneib are final and may be fetched (gsph_download_async) while
+ * _finish runs the tree-gravity half and the stars; a, atree and gpot are final after _finish.     */
+int gsph_update_all_forces_begin(gsph_handle* h);
+int gsph_update_all_forces_finish(gsph_handle* h);
 /* Star particles for GradhSph::ComputeStarGravForces (GradhSph.cpp:699-743; called for every active
  * particle by both force drivers when nbody->Nnbody > 0, GradhSphTree.cpp:385-392, :600-607):
  * stars = Nstar x {r[ndim], m, h} doubles.  The list stays on the device and is applied by

@@ -617,3 +617,32 @@ def test_sharded_tree_build_equals_single_gpu(ndim, world, lattice):
     for k in cells_ref:
         assert np.array_equal(cells[k], cells_ref[k]), k
     tree.close()
+
+
+def test_all_forces_in_two_halves():
+    """gsph_update_all_forces_begin / _finish == gsph_update_all_forces bit for bit; du/dt, div_v and
+    levelneib fetched between the halves (asynchronously) are already final"""
+    import gandalf_b200 as g
+    from gandalf_b200 import _capi
+    params, d = load_golden("sphere_grav_quad")
+    si = _by_iorig(stage(d, "force_in"))
+    res = []
+    for split in (False, True):
+        ps, tree = _make(params, si)
+        tree.BuildTree(True, 0, 1, 1, 0.0, ps)
+        tree.ZeroAccelerations()
+        if split:
+            tree.UpdateAllSphForcesBegin()
+            tree.Download(ps, mask=_capi.F_FORCES, only=("dudt", "div_v", "levelneib"), wait=False)
+            tree.UpdateAllSphForcesFinish()
+            tree.Download(ps, mask=_capi.F_FORCES, only=("a", "atree", "gpot"))
+        else:
+            tree.UpdateAllSphForces()
+            tree.Download(ps)
+        res.append({k: ps[k].copy() for k in ("a", "atree", "gpot", "dudt", "div_v", "levelneib")})
+        if split:
+            with pytest.raises(g.GsphError):
+                tree.UpdateAllSphForcesFinish()          # no half pending
+        tree.close()
+    for k in res[0]:
+        assert np.array_equal(res[0][k], res[1][k]), k
