@@ -90,7 +90,8 @@ EXPORTS = [
     "gsph_neighbour_counts", "gsph_neighbour_lists", "gsph_tree_info_get", "gsph_tree_leaf_of",
     "gsph_tree_cells", "gsph_get_stats", "gsph_kernel_table", "gsph_measure_fp_peak",
     "gsph_integrator_begin", "gsph_integrator_step", "gsph_integrator_state",
-    "gsph_update_all_forces_begin", "gsph_update_all_forces_finish",
+    "gsph_update_all_forces_begin", "gsph_update_all_forces_finish", "gsph_integrator_advance",
+    "gsph_integrator_finish",
 ]
 
 _lib = None
@@ -132,6 +133,8 @@ def lib():
     L.gsph_build_tree.argtypes = [H, C.c_int, C.c_double]
     L.gsph_integrator_begin.argtypes = [H, C.POINTER(IntegratorConfig), C.c_int, C.c_double]
     L.gsph_integrator_step.argtypes = [H, C.c_int]
+    L.gsph_integrator_advance.argtypes = [H, C.POINTER(C.c_int), C.POINTER(C.c_double)]
+    L.gsph_integrator_finish.argtypes = [H]
     L.gsph_integrator_state.argtypes = [H, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     for n in ("gsph_update_active_counters", "gsph_update_properties", "gsph_zero_accelerations",
               "gsph_update_hydro_forces", "gsph_synchronize", "gsph_timer_start", "gsph_density_pass",

@@ -1333,8 +1333,7 @@ static int integ_forces(gsph_handle* h)
   if (h->cfg.self_gravity) rc = gsph_update_all_forces(h, NULL, 0);
   else if (h->cfg.hydro_forces) rc = gsph_update_hydro_forces(h);
   else { h->err = "Error: No forces included in simulation"; return GSPH_EINVAL; }   /* SphSimulation.cpp:467 */
-  if (rc) return rc;
-  return integ_scatter_results(h);
+  return rc;
 }
 
 /* Simulation::ComputeGlobalTimestep on the host-order state */
@@ -1360,7 +1359,9 @@ int gsph_integrator_begin(gsph_handle* h, const gsph_integrator_config* cfg, int
   if (!(cfg->accel_mult > 0) || !(cfg->courant_mult > 0) || !(cfg->energy_mult > 0)) { h->err = "gsph_integrator_begin: the time-step multipliers must be positive"; return GSPH_EINVAL; }
   if (cfg->ntreebuildstep < 1 || cfg->ntreestockstep < 1) { h->err = "gsph_integrator_begin: ntreebuildstep and ntreestockstep must be >= 1"; return GSPH_EINVAL; }
   if (h->Nstar > 0) { h->err = "gsph_integrator_begin: star particles are not integrated on the device"; return GSPH_EINVAL; }
-  if (h->slice_mode) { h->err = "gsph_integrator_begin: not with an active slice (multi-GPU decomposition)"; return GSPH_EINVAL; }
+  if (compute_forces < 0 || compute_forces > 2) { h->err = "gsph_integrator_begin: compute_forces must be 0, 1 or 2"; return GSPH_EINVAL; }
+  if (compute_forces == 1 && h->slice_mode) { h->err = "gsph_integrator_begin: compute_forces = 1 not with an active slice (the multi-GPU host layer runs the passes itself and passes 2)"; return GSPH_EINVAL; }
+  if (compute_forces == 2 && !h->sorted_valid) { h->err = "gsph_integrator_begin(compute_forces = 2) before the passes"; return GSPH_ESTATE; }
   cudaSetDevice(h->device);
   IntegState& I = h->integ;
   if (I.cap < h->Ncap) {
@@ -1370,12 +1371,13 @@ int gsph_integrator_begin(gsph_handle* h, const gsph_integrator_config* cfg, int
     I.cap = h->Ncap;
   }
   if (!I.red) CUDA_TRY(h, cudaMalloc(&I.red, 2*sizeof(unsigned long long)));
-  I.cfg = *cfg; I.t = I.tlast = t0; I.Nsteps = 0; I.rebuild = true; I.on = false;
+  I.cfg = *cfg; I.t = I.tlast = t0; I.Nsteps = 0; I.rebuild = true; I.on = false; I.mid_step = false;
   CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_all, 0));          /* the upload has landed */
-  if (compute_forces) {
+  if (compute_forces == 1) {
     int rc = gsph_build_tree(h, 0, 0.0); if (rc) return rc;
     rc = integ_forces(h); if (rc) return rc;
   }
+  if (compute_forces) { const int rc = integ_scatter_results(h); if (rc) return rc; }
   INTEG_LAUNCH(integ_init_kernel, (int) h->N, devptrs(h->H, h->HI), integ_ptrs(h));
   int rc = integ_global_timestep(h, &I.timestep); if (rc) return rc;
   /* EndTimestep with part.dt = 0 (SphSimulation.cpp:561): u0 = u, dudt0 = dudt */
@@ -1384,44 +1386,74 @@ int gsph_integrator_begin(gsph_handle* h, const gsph_integrator_config* cfg, int
   return GSPH_OK;
 }
 
+/* first half of one MainLoop: time advance, prediction, boundaries (SphSimulation.cpp:586-608); the
+ * host-order arrays then hold a fresh "upload".  *tree_mode = what BuildTree has to do (0 rebuild,
+ * 1 restock, 2 extrapolate), *timestep = the step being taken (the extrapolation interval).       */
+int gsph_integrator_advance(gsph_handle* h, int* tree_mode, double* timestep)
+{
+  if (!h) return GSPH_EINVAL;
+  if (!h->integ.on) { h->err = "gsph_integrator_advance before gsph_integrator_begin"; return GSPH_ESTATE; }
+  if (h->integ.mid_step) { h->err = "gsph_integrator_advance: the previous step was not finished"; return GSPH_ESTATE; }
+  cudaSetDevice(h->device);
+  IntegState& I = h->integ;
+  I.Nsteps++;
+  const double ts = I.timestep;
+  I.t = I.t + ts;
+  const double dt = I.t - I.tlast;
+  INTEG_LAUNCH(integ_advance_kernel, (int) h->N, devptrs(h->H, h->HI), integ_ptrs(h), h->dp, dt, ts,
+               h->dp.tdavisc != GSPH_TDAVISC_NONE ? 1 : 0, I.cfg.energy_integration);
+  CUDA_TRY(h, cudaEventRecord(h->ev_geom, h->stream));
+  CUDA_TRY(h, cudaEventRecord(h->ev_all, h->stream));
+  for (int k = 0; k < 3; k++) CUDA_TRY(h, cudaEventRecord(h->ev_axis[k], h->stream));
+  h->sorted_valid = false; h->density_done = false; h->slice_mode = false;
+  /* sphneib->BuildTree(rebuild_tree, Nsteps, ntreebuildstep, ntreestockstep, timestep, sph) */
+  const bool full = I.rebuild || I.Nsteps % I.cfg.ntreebuildstep == 0;
+  if (tree_mode) *tree_mode = full ? 0 : (I.Nsteps % I.cfg.ntreestockstep == 0 ? 1 : 2);
+  if (timestep) *timestep = ts;
+  I.mid_step = true;
+  return GSPH_OK;
+}
+
+/* second half, after BuildTree, UpdateAllSphProperties, ZeroAccelerations and the force pass (with
+ * several ranks: after the result slices were all-gathered in tree order): results back to host
+ * order, smoothing-length sanity check, next global time step, end-of-step terms
+ * (SphSimulation.cpp:757-767, 836-870).                                                           */
+int gsph_integrator_finish(gsph_handle* h)
+{
+  if (!h) return GSPH_EINVAL;
+  if (!h->integ.on || !h->integ.mid_step) { h->err = "gsph_integrator_finish before gsph_integrator_advance"; return GSPH_ESTATE; }
+  if (!h->sorted_valid) { h->err = "gsph_integrator_finish before the passes of this step"; return GSPH_ESTATE; }
+  cudaSetDevice(h->device);
+  IntegState& I = h->integ;
+  int rc = integ_scatter_results(h); if (rc) return rc;
+  if (h->dp.any_periodic) {
+    double hmax = 0.0;
+    rc = gsph_get_hmax(h, &hmax); if (rc) return rc;
+    hmax *= h->dp.kernrange;
+    for (int k = 0; k < h->cfg.ndim; k++)
+      if (h->dp.periodic[k] && h->dp.boxhalf[k] < 2*hmax) { h->err = "Error: Smoothing length too large, self-interaction will occur"; return GSPH_ESTATE; }
+  }
+  double next = 0.0;
+  rc = integ_global_timestep(h, &next); if (rc) return rc;
+  I.rebuild = false;
+  INTEG_LAUNCH(integ_end_kernel, (int) h->N, devptrs(h->H, h->HI), integ_ptrs(h), I.timestep, I.cfg.energy_integration);
+  I.tlast = I.t;
+  I.timestep = next;
+  I.mid_step = false;
+  return GSPH_OK;
+}
+
 int gsph_integrator_step(gsph_handle* h, int nsteps)
 {
   if (!h) return GSPH_EINVAL;
   if (!h->integ.on) { h->err = "gsph_integrator_step before gsph_integrator_begin"; return GSPH_ESTATE; }
   if (nsteps < 0) { h->err = "gsph_integrator_step: nsteps < 0"; return GSPH_EINVAL; }
-  cudaSetDevice(h->device);
-  IntegState& I = h->integ;
   for (int s = 0; s < nsteps; s++) {
-    /* MainLoop, SphSimulation.cpp:586-606 */
-    I.Nsteps++;
-    const double ts = I.timestep;
-    I.t = I.t + ts;
-    const double dt = I.t - I.tlast;
-    INTEG_LAUNCH(integ_advance_kernel, (int) h->N, devptrs(h->H, h->HI), integ_ptrs(h), h->dp, dt, ts,
-                 h->dp.tdavisc != GSPH_TDAVISC_NONE ? 1 : 0, I.cfg.energy_integration);
-    /* the staging arrays now hold a fresh "upload" */
-    CUDA_TRY(h, cudaEventRecord(h->ev_geom, h->stream));
-    CUDA_TRY(h, cudaEventRecord(h->ev_all, h->stream));
-    for (int k = 0; k < 3; k++) CUDA_TRY(h, cudaEventRecord(h->ev_axis[k], h->stream));
-    h->sorted_valid = false; h->density_done = false;
-    /* sphneib->BuildTree(rebuild_tree, Nsteps, ntreebuildstep, ntreestockstep, timestep, sph) */
-    const bool full = I.rebuild || I.Nsteps % I.cfg.ntreebuildstep == 0;
-    const int mode = full ? 0 : (I.Nsteps % I.cfg.ntreestockstep == 0 ? 1 : 2);
-    int rc = gsph_build_tree(h, mode, ts); if (rc) return rc;
+    int mode = 0; double ts = 0.0;
+    int rc = gsph_integrator_advance(h, &mode, &ts); if (rc) return rc;
+    rc = gsph_build_tree(h, mode, ts); if (rc) return rc;
     rc = integ_forces(h); if (rc) return rc;
-    if (h->dp.any_periodic) {                                         /* SphSimulation.cpp:757-767 */
-      double hmax = 0.0;
-      rc = gsph_get_hmax(h, &hmax); if (rc) return rc;
-      hmax *= h->dp.kernrange;
-      for (int k = 0; k < h->cfg.ndim; k++)
-        if (h->dp.periodic[k] && h->dp.boxhalf[k] < 2*hmax) { h->err = "Error: Smoothing length too large, self-interaction will occur"; return GSPH_ESTATE; }
-    }
-    double next = 0.0;
-    rc = integ_global_timestep(h, &next); if (rc) return rc;
-    I.rebuild = false;
-    INTEG_LAUNCH(integ_end_kernel, (int) h->N, devptrs(h->H, h->HI), integ_ptrs(h), ts, I.cfg.energy_integration);
-    I.tlast = I.t;
-    I.timestep = next;
+    rc = gsph_integrator_finish(h); if (rc) return rc;
   }
   return GSPH_OK;
 }

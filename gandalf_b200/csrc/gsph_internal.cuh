@@ -118,6 +118,7 @@ struct IntegState {
   double t = 0.0, tlast = 0.0, timestep = 0.0;
   int64_t Nsteps = 0;
   bool rebuild = true;
+  bool mid_step = false;     /* between gsph_integrator_advance and gsph_integrator_finish */
 };
 
 struct gsph_handle {

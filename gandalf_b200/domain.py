@@ -88,11 +88,16 @@ class DomainDriver(object):
 
     def BuildTree(self, rebuild, n, ntreebuildstep, ntreestockstep, timestep, parts=None):
         full = rebuild or n % ntreebuildstep == 0
+        self._build(0 if full else (1 if n % ntreestockstep == 0 else 2), timestep, parts)
+
+    def _build(self, mode, timestep, parts=None):
         pow2 = self.world > 1 and (self.world & (self.world - 1)) == 0
-        if full and pow2 and self.shard_build:
+        if mode == 0 and pow2 and self.shard_build:
             self._sharded_rebuild(parts)
         else:
-            self.tree.BuildTree(rebuild, n, ntreebuildstep, ntreestockstep, timestep, parts)
+            if parts is not None:
+                self.tree.Upload(parts)
+            self.tree.BuildTreeMode(mode, timestep)
         self.N = self.tree.Stats().Nhydro
         if self.world > 1:
             lo, hi, chunk = slice_bounds(self.N, self.world, self.rank)
@@ -170,6 +175,44 @@ class DomainDriver(object):
             self._gather_inplace(self._array_names(only, parts.ndim), False, parts.N)
         lo, hi, _ = slice_bounds(parts.N, self.world, self.rank)
         self.tree.DownloadRange(parts, lo, hi, mask=mask, only=only, wait=wait)
+
+    # ---- device-resident main loop across the ranks (gsph_integrator_*): the integrator state is
+    #      replicated (streaming kernels over all particles, identical on every rank: the global time
+    #      step is an order-independent minimum); between its two halves the ranks run the sharded
+    #      tree build, their slices of the passes and the exchanges.  Nothing crosses PCIe.
+    def _passes(self):
+        self.UpdateAllSphProperties()
+        self.ZeroAccelerations()
+        if self.tree.cfg.self_gravity:
+            self.UpdateAllSphForces()
+        else:
+            self.UpdateAllSphHydroForces()
+        if self.world > 1:
+            # the force results of the other slices (tree order): one in-place all-gather per array
+            fields = ["a", "atree", "gpot", "dudt", "div_v", "dalphadt", "alpha", "levelneib"]
+            self.tree.Synchronize()
+            self._gather_inplace(self._array_names(fields, self.tree.cfg.ndim), False, self.N)
+
+    def IntegratorBegin(self, parts=None, compute_forces=True, t=0.0):
+        if self.world == 1:
+            self.tree.IntegratorBegin(parts, compute_forces, t)
+            return
+        if parts is not None:
+            self.tree.Upload(parts)
+        if compute_forces:
+            self._build(0, 0.0)
+            self._passes()
+        self.tree.IntegratorBegin(compute_forces=2 if compute_forces else 0, t=t)
+
+    def MainLoop(self, nsteps=1):
+        if self.world == 1:
+            self.tree.MainLoop(nsteps)
+            return
+        for _ in range(int(nsteps)):
+            mode, ts = self.tree.IntegratorAdvance()
+            self._build(mode, ts)
+            self._passes()
+            self.tree.IntegratorFinish()
 
     def ZeroAccelerations(self):
         self.tree.ZeroAccelerations()

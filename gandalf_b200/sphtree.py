@@ -165,6 +165,10 @@ class GpuSphTree(object):
             mode = 2
         self._check(self._L.gsph_build_tree(self._h, mode, float(timestep)))
 
+    def BuildTreeMode(self, mode, timestep=0.0):
+        """gsph_build_tree with an explicit mode: 0 rebuild, 1 restock, 2 extrapolate, 3 restock keeping the MAC data"""
+        self._check(self._L.gsph_build_tree(self._h, int(mode), float(timestep)))
+
     def BuildGhostTree(self, *a, **kw):
         """Periodic images are taken on the fly in the walks: nothing to build (HydroTree.cpp:382-441)."""
 
@@ -205,7 +209,16 @@ class GpuSphTree(object):
         if parts is not None:
             self.Upload(parts)
         ic = integrator_config_from_params(self.params)
-        self._check(self._L.gsph_integrator_begin(self._h, C.byref(ic), 1 if compute_forces else 0, float(t)))
+        self._check(self._L.gsph_integrator_begin(self._h, C.byref(ic), int(compute_forces), float(t)))
+
+    def IntegratorAdvance(self):
+        """first half of a MainLoop -> (tree mode 0 rebuild / 1 restock / 2 extrapolate, time step)"""
+        mode, ts = C.c_int(), C.c_double()
+        self._check(self._L.gsph_integrator_advance(self._h, C.byref(mode), C.byref(ts)))
+        return mode.value, ts.value
+
+    def IntegratorFinish(self):
+        self._check(self._L.gsph_integrator_finish(self._h))
 
     def MainLoop(self, nsteps=1):
         """nsteps x SphSimulation::MainLoop (SphSimulation.cpp:574-880) without leaving the device"""

@@ -330,13 +330,25 @@ typedef struct gsph_integrator_config {
  *                        force pass once (the tail of PostInitialConditionsSetup,
  *                        SphSimulation.cpp:390-465);
  *   compute_forces = 0 : take the uploaded h, sound, div_v, a, du/dt, alpha ... as they are
- *                        (restart from a complete state, e.g. the reference's own setup).
+ *                        (restart from a complete state, e.g. the reference's own setup);
+ *   compute_forces = 2 : the caller has just run those passes itself (tree-order results present).
  * Then r0, v0, a0, u0, dudt0 are set and the first global time step is computed
  * (SphSimulation.cpp:480-486, 544-563).                                                            */
 int gsph_integrator_begin(gsph_handle* h, const gsph_integrator_config* cfg, int compute_forces, double t0);
 /* nsteps x MainLoop.  Afterwards gsph_download(..., GSPH_F_ALL) returns the particle state as the
  * reference holds it at the end of MainLoop (corrected v, u; r0 = r ...).                          */
 int gsph_integrator_step(gsph_handle* h, int nsteps);
+/* One MainLoop in two halves, for hosts that run the operators in between themselves (several
+ * ranks: sharded tree build, slice passes and the NCCL exchanges, see gandalf_b200/domain.py):
+ *   advance : t += timestep, prediction, boundaries; the host-order arrays are a fresh "upload";
+ *             *tree_mode = 0 rebuild / 1 restock / 2 extrapolate for BuildTree, *timestep = the step;
+ *   finish  : after BuildTree, UpdateAllSphProperties, ZeroAccelerations and the force pass, with the
+ *             tree-order result arrays complete on this device: results back to host order, next
+ *             global time step, end-of-step terms.
+ * gsph_integrator_begin(compute_forces = 2) is the matching start: the caller has just run the passes.
+ * gsph_integrator_step(h, 1) == advance + gsph_build_tree + the passes + finish.                     */
+int gsph_integrator_advance(gsph_handle* h, int* tree_mode, double* timestep);
+int gsph_integrator_finish(gsph_handle* h);
 /* simulation time, the time step the NEXT MainLoop will take, steps done since begin             */
 int gsph_integrator_state(gsph_handle* h, double* t, double* timestep, int64_t* nsteps);
 

@@ -60,6 +60,17 @@ for workload, NP in (("cloud", 150000), ("glass", 64**3)):
         drv.Download(ps, mask=2, only=("a", "dudt", "div_v", "levelneib") + (("atree", "gpot") if grav else ()), gather=True)
         tree.Synchronize(); tree.close()
         return ps, lo, hi
+    def run_loop(world_, rank_, steps):
+        # device-resident main loop: replicated integrator state, sharded passes (DomainDriver.MainLoop)
+        ps = fresh()
+        tree = g.GpuSphTree(params, device=lr)
+        drv = domain.DomainDriver(tree, rank_, world_)
+        drv.IntegratorBegin(ps, compute_forces=True)
+        drv.MainLoop(steps)
+        tree.Download(ps)
+        state = tree.IntegratorState(); tree.close()
+        return ps, state
+    loop, lstate = run_loop(world, rank, 3)
     chunked, clo, chi = run_chunked(world, rank)
     multi, st = run(world, rank)
     # forces: every rank only wrote its own slice (other particles keep the uploaded zeros): sum over ranks
@@ -78,6 +89,10 @@ for workload, NP in (("cloud", 150000), ("glass", 64**3)):
             assert np.array_equal(tot[f], single[f]), (workload, f, np.abs(tot[f] - single[f]).max())
         for f in ("h", "rho", "hrangesqd", "a", "dudt", "div_v") + (("atree", "gpot") if grav else ()):
             assert np.array_equal(chunked[f][clo:chi], single[f][clo:chi]), (workload, "chunked", f)
+        sloop, sstate = run_loop(1, 0, 3)
+        assert lstate == sstate, (lstate, sstate)
+        for f in ("r", "v", "a", "h", "rho", "u", "dudt") + (("atree", "gpot") if grav else ()):
+            assert np.array_equal(loop[f], sloop[f]), (workload, "mainloop", f, np.abs(loop[f] - sloop[f]).max())
         print("multi-GPU parity ok:", workload, N, "particles, world", world)
 dist.barrier()
 """
