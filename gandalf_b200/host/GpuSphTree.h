@@ -230,6 +230,55 @@ class GpuSphTree : public GradhSphTree<ndim, GradhSphParticle>
     return hmax;
   }
 
+  //-----------------------------------------------------------------------------------------------
+  // Device-resident main loop (include/gsph.h, gsph_integrator_*): for sph_integration = lfkdk,
+  // Nlevels = 1 and no star particles, SphSimulation::MainLoop itself (SphSimulation.cpp:574-880)
+  // runs on the device; the particle array crosses PCIe once in each direction.
+  //-----------------------------------------------------------------------------------------------
+  /// Call after PostInitialConditionsSetup (or any completed MainLoop): ships the complete particle
+  /// state and starts the device loop at simulation time t.
+  void ResidentBegin(Sph<ndim>* sph, Parameters* params, const double t)
+  {
+    std::map<std::string, int>& ip = params->intparams;
+    std::map<std::string, double>& fp = params->floatparams;
+    std::map<std::string, std::string>& sp = params->stringparams;
+    if (sp["sph_integration"] != "lfkdk" || ip["Nlevels"] != 1)
+      ExceptionHandler::getIstance().raise("GpuSphTree: the device-resident main loop needs sph_integration = lfkdk and Nlevels = 1");
+    gsph_integrator_config ic;
+    memset(&ic, 0, sizeof ic);
+    ic.accel_mult = fp["accel_mult"]; ic.courant_mult = fp["courant_mult"]; ic.energy_mult = fp["energy_mult"];
+    ic.energy_integration = sp["gas_eos"] == "energy_eqn" ? 1 : 0;      // GradhSphSimulation.cpp:110-123
+    ic.ntreebuildstep = ip["ntreebuildstep"]; ic.ntreestockstep = ip["ntreestockstep"];
+    check(gsph_set_stars(handle, NULL, 0));
+    upload(sph);
+    check(gsph_integrator_begin(handle, &ic, 0, t));
+    staged = false;
+  }
+
+  void ResidentMainLoop(const int nsteps) { check(gsph_integrator_step(handle, nsteps)); }
+
+  /// Brings the particles home in the state the reference holds at the end of MainLoop (r0 = r, v0 = v,
+  /// a0 = a, u0 = u, dudt0 = dudt, tlast = t, dt = the next step; SphLeapfrogKDK::EndTimestep,
+  /// Simulation::ComputeGlobalTimestep), so that its own MainLoop can carry on from there.
+  void ResidentFetch(Sph<ndim>* sph, double* t_out, double* timestep_out, long long* nsteps_out)
+  {
+    download(sph, GSPH_F_ALL);
+    double t = 0.0, ts = 0.0; int64_t n = 0;
+    check(gsph_integrator_state(handle, &t, &ts, &n));
+    Part* p = sph->template GetParticleArray<GradhSphParticle>();
+    for (int i = 0; i < sph->Nhydro; i++) {
+      if (p[i].flags.is_dead()) continue;
+      for (int k = 0; k < ndim; k++) { p[i].r0[k] = p[i].r[k]; p[i].v0[k] = p[i].v[k]; p[i].a0[k] = p[i].a[k]; }
+      p[i].u0 = p[i].u; p[i].dudt0 = p[i].dudt;
+      p[i].level = 0; p[i].levelneib = 0; p[i].nstep = 1; p[i].nlast = 0;
+      p[i].tlast = t; p[i].dt = ts; p[i].dt_next = 0;
+      p[i].flags.unset(active); p[i].flags.unset(end_timestep);
+    }
+    if (t_out) *t_out = t;
+    if (timestep_out) *timestep_out = ts;
+    if (nsteps_out) *nsteps_out = (long long) n;
+  }
+
   gsph_handle* GetHandle() { return handle; }
 };
 

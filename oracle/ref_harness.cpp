@@ -73,6 +73,7 @@ static string g_outdir;
 static bool g_quiet = false;
 static int g_mainloop = 0;         // --mainloop N : run N steps of the reference's own MainLoop
 static string g_starfile;         // --stars FILE : int64 Nstar, then Nstar doubles each of x[,y[,z]], m, h
+static int g_resident = 0;         // --resident K : (with --gpu) the first K of the --mainloop steps run in the device-resident loop
 static bool g_gpu = false;         // --gpu : swap sim->sphneib for GpuSphTree before doing so
 static FILE* g_out = NULL;          // the caller's stdout (the reference's chatter goes elsewhere)
 
@@ -463,7 +464,24 @@ static int run(Parameters* params, const string& icfile, double perturb, const s
     }
     double t1 = now();
     const double timestep0 = sim->timestep;          // the step PostInitialConditionsSetup chose
-    for (int s = 0; s < g_mainloop; s++) sim->MainLoop();
+    int done = 0;
+#ifdef WITH_GPU
+    if (g_gpu && g_resident > 0) {
+      // the device-resident main loop takes the first K steps, then hands the particles back to the
+      // reference's own MainLoop (gandalf_b200/host/GpuSphTree.h: ResidentBegin / MainLoop / Fetch)
+      GpuSphTree<ndim>* gt = static_cast<GpuSphTree<ndim>*>(sim->sphneib);
+      const int K = std::min(g_resident, g_mainloop);
+      gt->ResidentBegin(sim->sph, sim->simparams, sim->t);
+      gt->ResidentMainLoop(K);
+      double tt = 0.0, ts = 0.0; long long ns = 0;
+      gt->ResidentFetch(sim->sph, &tt, &ts, &ns);
+      sim->t = tt; sim->timestep = ts; sim->n = 0;
+      sim->Nsteps += K; sim->Nfullsteps += K; sim->Nblocksteps += K;
+      sim->rebuild_tree = false;
+      done = K;
+    }
+#endif
+    for (int s = done; s < g_mainloop; s++) sim->MainLoop();
     double t_loop = now() - t1;
     H.dump_particles("loop");
     fprintf(g_out, "{\"ref_mainloop\": true, \"gpu\": %s, \"N\": %d, \"steps\": %d, \"t\": %.17g, \"timestep\": %.17g, \"timestep0\": %.17g, \"wall_s\": %.4f}\n",
@@ -524,6 +542,7 @@ int main(int argc, char** argv)
     string a = argv[i];
     if (a == "--in" && i + 1 < argc) icfile = argv[++i];
     else if (a == "--stars" && i + 1 < argc) g_starfile = argv[++i];
+    else if (a == "--resident" && i + 1 < argc) g_resident = atoi(argv[++i]);
     else if (a == "--set" && i + 1 < argc) {
       string kv = argv[++i];
       size_t eq = kv.find('=');

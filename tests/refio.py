@@ -111,7 +111,7 @@ def csr_rows(off, idx):
     return [idx[off[i]:off[i + 1]] for i in range(len(off) - 1)]
 
 
-def run_mainloop(params, ic, steps, gpu, timeout=1800, kind="gpu", dumps=""):
+def run_mainloop(params, ic, steps, gpu, timeout=1800, kind="gpu", dumps="", resident=0):
     """N steps of the reference's own SphSimulation::MainLoop through oracle/_ref/ref_harness_gpu;
     gpu=True swaps sim->sphneib for gandalf_b200/host/GpuSphTree.h first.  -> (arrays, info json)"""
     exe = harness_path(kind)
@@ -126,6 +126,8 @@ def run_mainloop(params, ic, steps, gpu, timeout=1800, kind="gpu", dumps=""):
         cmd = [exe, dat, os.path.join(work, "out"), "--dump", dumps, "--quiet", "--in", icf, "--mainloop", str(int(steps))]
         if gpu:
             cmd.append("--gpu")
+        if resident:
+            cmd += ["--resident", str(int(resident))]      # the first `resident` steps in the device main loop
         res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=timeout)
         if res.returncode != 0:
             raise RuntimeError("ref_harness_gpu failed (%d): %s %s" % (res.returncode, res.stdout.decode()[-1000:],

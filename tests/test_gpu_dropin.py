@@ -52,3 +52,31 @@ def test_reference_mainloop_with_gpu_tree(name, steps):
     for f in ("h", "rho", "u"):
         assert rel_err(gpu["loop." + f][og], cpu["loop." + f][oc]).max() < tol, f
     assert scaled_err(gpu["loop.dudt"][og], cpu["loop.dudt"][oc]).max() < tol
+
+
+@pytest.mark.parametrize("name,steps,resident", [("adsod", 6, 6), ("box3d_mm97", 4, 2), ("sphere_grav_quad", 4, 3),
+                                                 ("khi2d_quintic", 4, 4)])
+def test_reference_hands_over_to_the_device_main_loop(name, steps, resident):
+    """C++ twin, MainLoop level: after the reference's own setup the particles go to the device once
+    (GpuSphTree::ResidentBegin), `resident` steps run in the device-resident main loop
+    (gsph_integrator_step), the particles come home (ResidentFetch restores r0, v0, a0, u0, dudt0, tlast,
+    dt as SphLeapfrogKDK::EndTimestep leaves them) and the reference's OWN MainLoop carries on for the
+    remaining steps.  The result must match the all-CPU run: same time-step sequence, state to 1e-6."""
+    if refio.harness_path("gpu") is None:
+        pytest.skip("oracle/_ref/ref_harness_gpu not built")
+    p, ic = _case(name)
+    cpu, ci = refio.run_mainloop(p, ic, steps, gpu=False)
+    dev, di = refio.run_mainloop(p, ic, steps, gpu=True, resident=resident)
+    assert ci["steps"] == di["steps"] == steps
+    assert abs(ci["t"] - di["t"]) <= 1e-12*abs(ci["t"])
+    assert abs(ci["timestep"] - di["timestep"]) <= 1e-9*abs(ci["timestep"])
+    oc, og = np.argsort(cpu["loop.iorig"]), np.argsort(dev["loop.iorig"])
+    tol = 1e-6
+    for f in ("r", "v", "a"):
+        a, b = dev["loop." + f][og], cpu["loop." + f][oc]
+        a = a.reshape(len(a), -1); b = b.reshape(len(b), -1)
+        e = np.linalg.norm(a - b, axis=1)/np.maximum(np.linalg.norm(b, axis=1), np.abs(b).max()*1e-6)
+        assert e.max() < tol, (f, e.max())
+    for f in ("h", "rho", "u", "alpha"):
+        assert rel_err(dev["loop." + f][og], cpu["loop." + f][oc]).max() < tol, f
+    assert scaled_err(dev["loop.dudt"][og], cpu["loop.dudt"][oc]).max() < tol
