@@ -230,6 +230,32 @@ class GpuSphTree(object):
         self._check(self._L.gsph_integrator_state(self._h, C.byref(t), C.byref(ts), C.byref(n)))
         return t.value, ts.value, n.value
 
+    # ---- snapshots in the reference's "su" wire format (gandalf_b200/snapshot.py) ------------------
+    def WriteSnapshot(self, path, alloc=None, **header):
+        """SEREN-unformatted snapshot of the particles on the device (SimulationIO.hpp:1655-2262): only
+        the seven arrays of the format come home, as contiguous SoA copies.  In a device-resident run the
+        header carries the loop's t and step count."""
+        from . import snapshot
+        N = self.Stats().Nhydro
+        fields = {"r", "v", "m", "h", "rho", "u", "iorig", "ptype", "flags"}
+        ps = ParticleSet(N, self.cfg.ndim, "soa", fields=fields, alloc=alloc)
+        self.Download(ps, only=tuple(fields))
+        hdr = dict(h_fac=self.cfg.h_fac)
+        try:
+            t, _, n = self.IntegratorState()
+            hdr.update(t=t, Nsteps=n)
+        except _capi.GsphError:
+            pass
+        hdr.update(header)
+        snapshot.write_su_from_particle_set(path, ps, **hdr)
+        return ps
+
+    @staticmethod
+    def ReadSnapshot(path, alloc=None):
+        """-> (ParticleSet, header) from a SEREN-unformatted snapshot (the reference's or ours)"""
+        from . import snapshot
+        return snapshot.particle_set_from_su(path, alloc=alloc)
+
     def SetStars(self, r=None, m=None, h=None):
         """nbody->nbodydata for GradhSph::ComputeStarGravForces (GradhSph.cpp:699-743): star positions
         (Nstar, ndim), masses and smoothing lengths; applied by both force passes until cleared

@@ -115,3 +115,36 @@ def test_device_mainloop_errors_are_loud():
     with pytest.raises(ValueError):
         g.GpuSphTree(dict(params, Nlevels=2)).IntegratorBegin(ps)
     tree.close(); tree2.close()
+
+
+def test_snapshot_of_a_device_resident_run_and_restart(tmp_path):
+    """su snapshot straight from the device (gandalf_b200/snapshot.py): equals the downloaded
+    state, carries t and the step count, and a run restarted from it (the reference's restart semantics:
+    the first density / force pass is redone from the snapshot's h) steps on"""
+    import gandalf_b200 as g
+    from gandalf_b200 import snapshot
+    params, d = load_golden("loop_box3d_mm97")
+    setup, loop = split(d)
+    ps, tree = _upload_setup(g, params, setup)
+    tree.IntegratorBegin(compute_forces=False)
+    tree.MainLoop(2)
+    path = str(tmp_path / "run.su.00002")
+    tree.WriteSnapshot(path)
+    tree.Download(ps)
+    t, ts, n = tree.IntegratorState()
+    s = snapshot.read_su(path)
+    assert s["t"] == t and s["Nsteps"] == n == 2 and s["N"] == len(setup["m"])
+    o = np.argsort(s["iorig"])
+    for f in ("m", "h", "rho", "u"):
+        assert np.array_equal(s[f][o], ps[f]), f
+    assert np.array_equal(s["r"][o], ps["r"]) and np.array_equal(s["v"][o], ps["v"])
+    tree.close()
+    ps2, hdr = g.GpuSphTree.ReadSnapshot(path)
+    tree2 = g.GpuSphTree(params)
+    tree2.IntegratorBegin(ps2, compute_forces=True, t=hdr["t"])
+    tree2.MainLoop(1)
+    t2, _, _ = tree2.IntegratorState()
+    assert t2 > hdr["t"]
+    tree2.Download(ps2)
+    assert rel_err(ps2["rho"], ps["rho"]).max() < 0.05          # one step later, same flow
+    tree2.close()

@@ -1,0 +1,102 @@
+"""gandalf_b200/snapshot.py (SEREN unformatted "su" snapshots) against the reference's own
+writer and reader: tests/golden/snap_*.su were written by Simulation::WriteSerenUnformSnapshotFile of
+the UNMODIFIED reference, snap_*.npz hold the same particles dumped at full precision."""
+import os
+
+import numpy as np
+import pytest
+
+import refio
+from conftest import GOLDEN_DIR, SNAP_CASES
+from gandalf_b200 import snapshot
+
+
+def _load(name):
+    z = np.load(os.path.join(GOLDEN_DIR, "snap_%s.npz" % name))
+    return {k: z[k] for k in z.files}, os.path.join(GOLDEN_DIR, "snap_%s.su" % name)
+
+
+def test_snapshot_fixtures_exist():
+    assert len(SNAP_CASES) >= 3
+
+
+@pytest.mark.parametrize("name", SNAP_CASES)
+def test_read_the_reference_snapshot(name):
+    d, path = _load(name)
+    s = snapshot.read_su(path)
+    nd = int(d["ndim"])
+    assert s["ndim"] == nd and s["N"] == len(d["m"]) and s["t"] == 0.0 and s["units"] == []
+    assert np.array_equal(s["iorig"], d["iorig"]) and np.array_equal(s["ptype"], d["ptype"])
+    for f in ("r", "v"):
+        assert np.array_equal(s[f].reshape(len(d["m"]), nd), d[f].reshape(len(d["m"]), nd)), f
+    for f in ("m", "h", "rho", "u"):
+        assert np.array_equal(s[f], d[f]), f
+    if "stars" in d:
+        st = d["stars"]
+        assert s["Nstar"] == len(st)
+        assert np.array_equal(s["stars"]["r"], st[:, :nd]) and np.array_equal(s["stars"]["m"], st[:, nd])
+        assert np.array_equal(s["stars"]["h"], st[:, nd + 1])
+    else:
+        assert s["Nstar"] == 0
+
+
+@pytest.mark.parametrize("name", SNAP_CASES)
+def test_written_file_is_byte_identical_to_the_reference(name, tmp_path):
+    d, path = _load(name)
+    hdr = snapshot.read_su(path)
+    out = str(tmp_path / "mine.su")
+    snapshot.write_su(out, d["r"], d["v"], d["m"], d["h"], d["rho"], d["u"], iorig=d["iorig"], ptype=d["ptype"],
+                      t=hdr["t"], Nsteps=hdr["Nsteps"], Noutsnap=hdr["Noutsnap"], h_fac=hdr["h_fac"],
+                      tsnaplast=hdr["tsnaplast"], mmean=hdr["mmean"], stars=hdr.get("stars"))
+    assert open(out, "rb").read() == open(path, "rb").read()
+
+
+def test_types_are_grouped_like_the_reference(tmp_path):
+    """particles of several types are written grouped icm, gas, cdm, dust, each group in array order
+    (WriteSerenUnformArrayScalar, SimulationIO.hpp:1962-1981)"""
+    rng = np.random.default_rng(5)
+    N = 50
+    ptype = rng.choice([0, 1, 2, 3], size=N)
+    r = rng.normal(size=(N, 3)); v = rng.normal(size=(N, 3))
+    m, h, rho, u = (rng.uniform(1, 2, N) for _ in range(4))
+    out = str(tmp_path / "t.su")
+    snapshot.write_su(out, r, v, m, h, rho, u, ptype=ptype, t=1.5, Nsteps=7)
+    s = snapshot.read_su(out)
+    order = np.concatenate([np.nonzero(ptype == pt)[0] for pt in (1, 0, 2, 3)])
+    assert np.array_equal(s["iorig"], order) and np.array_equal(s["ptype"], ptype[order])
+    assert np.array_equal(s["r"], r[order]) and np.array_equal(s["u"], u[order])
+    assert s["t"] == 1.5 and s["Nsteps"] == 7
+    with pytest.raises(ValueError):
+        snapshot.write_su(out, r, v, m, h, rho, u, ptype=np.full(N, 4))      # boundary_type is not a file type
+    open(out, "r+b").write(b"NOTASNAPSHOT")
+    with pytest.raises(ValueError):
+        snapshot.read_su(out)
+
+
+@pytest.mark.parametrize("name", ["adsod", "sphere_grav_stars"])
+def test_reference_reads_our_snapshot(name, tmp_path):
+    """the other direction: a file written by snapshot.write_su is the initial condition (ic = file,
+    in_file_form = su) of the unmodified reference; its particles after setup carry our r, v, m, u, iorig"""
+    if refio.harness_path("std") is None:
+        pytest.skip("oracle/_ref/ref_harness_std not built")
+    d, path = _load(name)
+    nd = int(d["ndim"])
+    mine = str(tmp_path / "ic.su")
+    st = None
+    if "stars" in d:
+        st = {"r": d["stars"][:, :nd], "m": d["stars"][:, nd], "h": d["stars"][:, nd + 1]}
+    snapshot.write_su(mine, d["r"], d["v"], d["m"], d["h"], d["rho"], d["u"], iorig=d["iorig"], ptype=d["ptype"], stars=st)
+    params = {"run_id": "SNAPIN", "sim": "gradhsph", "ic": "file", "in_file": mine, "in_file_form": "su", "ndim": nd,
+              "dimensionless": 1, "Nlevels": 1, "Nstepsmax": 1, "tend": 1.0e-10, "dt_snap": 1.0e10,
+              "noutputstep": 1000000, "ndiagstep": 1000000, "out_file_form": "su", "sink_particles": 0,
+              "sph_integration": "lfkdk", "neib_search": "kdtree", "Nhydromax": 8*len(d["m"]),
+              "self_gravity": 1 if "stars" in d else 0, "boundary_lhs[0]": "open", "boundary_rhs[0]": "open"}
+    out, _ = refio.run_harness(params, ic=None, dumps="setup")
+    o = np.argsort(out["setup.iorig"])
+    assert np.array_equal(out["setup.iorig"][o], np.sort(d["iorig"]))
+    mo = np.argsort(d["iorig"])
+    N = len(d["m"])
+    for f in ("r", "v"):
+        assert np.array_equal(out["setup." + f][o].reshape(N, nd), d[f].reshape(N, nd)[mo]), f
+    for f in ("m", "u"):
+        assert np.array_equal(out["setup." + f][o], d[f][mo]), f
