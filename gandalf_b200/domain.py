@@ -109,8 +109,11 @@ class DomainDriver(object):
         import torch
         if self._fields is None:
             out = []
-            for name in ("h", "rho", "hrangesqd", "hfactor", "invomega", "zeta", "sound", "pressure", "u"):
-                ptr, cap = self.tree.DeviceField(name)
+            names = ["h", "rho", "hrangesqd", "hfactor", "invomega", "zeta", "sound", "pressure", "u"]
+            if self.tree.cfg.tdavisc == 2:
+                names.append("alpha")        # the Cullen & Dehnen switch sets alpha in the density pass
+            for name in names:
+                ptr, cap, _ = self.tree.DeviceArray(name, staging=False)
                 if cap < self.chunk * self.world:
                     raise RuntimeError("device arrays too small for the padded all-gather")
                 out.append(torch.as_tensor(_CudaArray(ptr, self.chunk * self.world), device="cuda"))

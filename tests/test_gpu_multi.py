@@ -20,8 +20,10 @@ from gandalf_b200 import workloads, domain
 rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda:%d" % lr))
-for workload, NP in (("cloud", 150000), ("glass", 64**3)):
-    params, ic = workloads.WORKLOADS[workload](NP, device="cuda:%d" % lr)
+for workload, NP in (("cloud", 150000), ("glass", 64**3), ("glass+cd2010", 40**3)):
+    params, ic = workloads.WORKLOADS[workload.split("+")[0]](NP, device="cuda:%d" % lr)
+    if workload.endswith("cd2010"):                    # alpha is set in the density pass and read by the neighbours
+        params = dict(params, time_dependent_avisc="cd2010", alpha_visc_min=0.1)
     N = int(ic["m"].shape[0])
     grav = int(params["self_gravity"]) == 1
     def fresh():
@@ -83,7 +85,7 @@ for workload, NP in (("cloud", 150000), ("glass", 64**3)):
     assert int(nact.item()) == N, (int(nact.item()), N)
     if rank == 0:
         single, _ = run(1, 0)
-        for f in ("h", "rho", "invomega", "zeta", "pressure", "sound", "hrangesqd"):
+        for f in ("h", "rho", "invomega", "zeta", "pressure", "sound", "hrangesqd", "alpha"):
             assert np.array_equal(multi[f], single[f]), (workload, f)
         for f in tot:
             assert np.array_equal(tot[f], single[f]), (workload, f, np.abs(tot[f] - single[f]).max())
@@ -112,4 +114,4 @@ def test_two_gpu_results_identical_to_single_gpu(tmp_path):
                          timeout=1200)
     text = out.stdout.decode()
     assert out.returncode == 0, text[-3000:]
-    assert text.count("multi-GPU parity ok") == 2, text[-3000:]
+    assert text.count("multi-GPU parity ok") == 3, text[-3000:]
