@@ -112,11 +112,14 @@ class DomainDriver(object):
             names = ["h", "rho", "hrangesqd", "hfactor", "invomega", "zeta", "sound", "pressure", "u"]
             if self.tree.cfg.tdavisc == 2:
                 names.append("alpha")        # the Cullen & Dehnen switch sets alpha in the density pass
+            if self.tree.cfg.create_sinks:
+                names.append("flags")        # potmin flag of the sink search
             for name in names:
-                ptr, cap, _ = self.tree.DeviceArray(name, staging=False)
+                ptr, cap, es = self.tree.DeviceArray(name, staging=False)
                 if cap < self.chunk * self.world:
                     raise RuntimeError("device arrays too small for the padded all-gather")
-                out.append(torch.as_tensor(_CudaArray(ptr, self.chunk * self.world), device="cuda"))
+                out.append(torch.as_tensor(_CudaArray(ptr, self.chunk * self.world, "<f8" if es == 8 else "<i4"),
+                                           device="cuda"))
             self._fields = out
         return self._fields
 
