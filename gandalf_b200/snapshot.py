@@ -174,3 +174,44 @@ def write_su_from_particle_set(path, ps, **header):
     keep = ~dead
     write_su(path, ps["r"][keep], ps["v"][keep], ps["m"][keep], ps["h"][keep], ps["rho"][keep], ps["u"][keep],
              iorig=ps["iorig"][keep], ptype=ps["ptype"][keep], **header)
+
+
+# ---------------------------------------------------------------------------------------------------
+# "column" text snapshots (SimulationIO.hpp:162-545): Nhydro, Nstar, ndim, t on four lines, then one
+# row per particle  r[ndim] v[ndim] m h rho u  (three blanks between the numbers, C++ default stream
+# formatting = %g with 6 digits), then one row per star  r v m h 0 0.
+# ---------------------------------------------------------------------------------------------------
+def write_column(path, r, v, m, h, rho, u, t=0.0, stars=None):
+    r = np.asarray(r, dtype=np.float64)
+    N, ndim = r.shape
+    v = np.asarray(v, dtype=np.float64).reshape(N, ndim)
+    nstar = 0 if stars is None else len(stars["m"])
+    rows = np.column_stack([r, v, m, h, rho, u])
+    with open(path, "w") as f:
+        f.write("%d\n%d\n%d\n%g\n" % (N, nstar, ndim, t))
+        tail = "   \n" if ndim == 1 else "\n"       # the 1-D particle rows of the reference end with a separator (:466-472)
+        for row in rows:
+            f.write("   ".join("%g" % x for x in row) + tail)
+        if nstar:
+            sr = np.asarray(stars["r"], dtype=np.float64).reshape(nstar, ndim)
+            sv = np.asarray(stars.get("v", np.zeros((nstar, ndim))), dtype=np.float64).reshape(nstar, ndim)
+            for i in range(nstar):
+                row = list(sr[i]) + list(sv[i]) + [stars["m"][i], stars["h"][i], 0.0, 0.0]
+                f.write("   ".join("%g" % x for x in row) + "\n")
+
+
+def read_column(path):
+    """-> dict ndim N Nstar t r v m h rho u [stars]; values carry the 6 significant digits of the file"""
+    with open(path) as f:
+        N, nstar, ndim = int(f.readline()), int(f.readline()), int(f.readline())
+        t = float(f.readline())
+        body = np.loadtxt(f, ndmin=2) if N + nstar else np.zeros((0, 2*ndim + 4))
+    if body.shape != (N + nstar, 2*ndim + 4):
+        raise ValueError("column snapshot %s: expected %d rows of %d numbers" % (path, N + nstar, 2*ndim + 4))
+    p = body[:N]
+    out = {"ndim": ndim, "N": N, "Nstar": nstar, "t": t, "r": p[:, :ndim], "v": p[:, ndim:2*ndim],
+           "m": p[:, 2*ndim], "h": p[:, 2*ndim + 1], "rho": p[:, 2*ndim + 2], "u": p[:, 2*ndim + 3]}
+    if nstar:
+        s = body[N:]
+        out["stars"] = {"r": s[:, :ndim], "v": s[:, ndim:2*ndim], "m": s[:, 2*ndim], "h": s[:, 2*ndim + 1]}
+    return out

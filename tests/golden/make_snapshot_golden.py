@@ -41,6 +41,8 @@ def main():
             snap = os.path.join(HERE, "snap_%s.su" % name)
             cmd = [refio.harness_path("std"), dat, os.path.join(work, "out"), "--dump", "setup", "--quiet", "--in", icf,
                    "--snapshot", snap]
+            if name == "sphere_grav_stars" or name == "adsod":
+                cmd += ["--snapshot-column", os.path.join(HERE, "snap_%s.column" % name)]
             if stars is not None:
                 sf = os.path.join(work, "stars.bin")
                 with open(sf, "wb") as fh:
