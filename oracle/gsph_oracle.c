@@ -1371,3 +1371,83 @@ int orc_hydro_grav_forces_tree(const orc_params* p, const orc_tree* T, int N, co
   }
   return 0;
 }
+
+
+/*================================================================================================
+ * Gravity of the gas on the star particles: HydroTree::UpdateAllStarGasForces
+ * (src/Tree/HydroTree.cpp:552-654) = per star Tree::ComputeStarGravityInteractionList
+ * (src/Tree/Tree.cpp:748-885; the opening test is the GEOMETRIC one whatever gravity_mac says),
+ * then NbodyHermite4::CalculateDirectHydroForces (src/Nbody/NbodyHermite4.cpp:151-247; a and gpot are
+ * the same in the leapfrog classes, adot exists only for the Hermite schemes -- note the
+ * single-precision powf in wkern, :194) and ComputeCellMonopoleForces / ComputeCellQuadrupoleForces
+ * at the star's position.  Open boundaries only (no Ewald).  stars: rows {r[nd], v[nd], h};
+ * a, adot, gpot are ADDED to.
+ *===============================================================================================*/
+int orc_star_gas_forces(const orc_params* p, const orc_tree* T, int Nstar, const double* stars,
+                        double* a, double* adot, double* gpot, int32_t* counts /* [Nstar][3] neib, direct, cells or NULL */)
+{
+  const int nd = p->ndim; const double kr = kern_range(p);
+  const double twopi = 6.28318530717959;                  /* as spelled in src/Headers/Constants.h:62 */
+  for (int s = 0; s < Nstar; s++) {
+    const double* rs = stars + (size_t) s*(2*nd + 1);
+    const double* vs = rs + nd;
+    const double hs = rs[2*nd];
+    const double hrangemax = kr*hs;
+    acc_t A; memset(&A, 0, sizeof A);
+    double ad[3] = {0, 0, 0};
+    int Nneib = 0, Ndirect = 0, Ngravcell = 0;
+    int cc = 0;
+    while (cc < T->Ncell) {
+      const kdcell* c = &T->cell[cc];
+      double dr[3];
+      for (int k = 0; k < nd; k++) dr[k] = c->rcell[k] - rs[k];
+      const double drsqd = dot(dr, dr, nd);
+      int mode = 0;                                    /* 1: smoothed neighbours, 2: direct particles */
+      if (drsqd < pow(0.5*hrangemax + c->rmax + 0.5*kr*c->hmax, 2)) {
+        if (c->copen != -1) { cc = c->copen; continue; }
+        mode = 1;
+      }
+      else if (drsqd > c->cdistsqd && c->N > 0) {
+        if (c->copen == -1 && c->N == 1) mode = 2;
+        else { if (p->multipole == 0 || p->multipole == 2) cell_monopole(nd, c, rs, &A); else cell_quadrupole(nd, c, rs, &A);
+               Ngravcell++; cc = c->cnext; continue; }
+      }
+      else if (drsqd <= c->cdistsqd && c->N > 0) {
+        if (c->copen != -1) { cc = c->copen; continue; }
+        mode = 2;
+      }
+      else { cc = c->cnext; continue; }
+      int i = c->ifirst;
+      while (i != -1 && c->N > 0) {
+        double d[3], dv[3];
+        for (int k = 0; k < nd; k++) { d[k] = T->r[(size_t) i*nd + k] - rs[k]; dv[k] = T->v[(size_t) i*nd + k] - vs[k]; }
+        const double d2 = dot(d, d, nd), drmag = sqrt(d2), invdrmag = 1.0/drmag;
+        const double drdt = dot(dv, d, nd)*invdrmag;
+        const double mj = T->m[i];
+        if (mode == 1) {
+          const double invhmean = 2.0/(hs + T->h[i]);
+          const double paux = mj*invhmean*invhmean*orc_kernel(p, 4, drmag*invhmean)*invdrmag;
+          const double wkern = orc_kernel(p, 0, drmag*invhmean)*(double) powf((float) invhmean, (float) nd);
+          for (int k = 0; k < nd; k++) A.atree[k] += paux*d[k];
+          for (int k = 0; k < nd; k++)
+            ad[k] += paux*dv[k] - 3.0*paux*drdt*invdrmag*d[k] + 2.0*twopi*mj*drdt*wkern*invdrmag*d[k];
+          A.gpot += mj*invhmean*orc_kernel(p, 5, drmag*invhmean);
+          Nneib++;
+        }
+        else {
+          for (int k = 0; k < nd; k++) A.atree[k] += mj*d[k]*pow(invdrmag, 3);
+          for (int k = 0; k < nd; k++) ad[k] += mj*pow(invdrmag, 3)*(dv[k] - 3.0*drdt*invdrmag*d[k]);
+          A.gpot += mj*invdrmag;
+          Ndirect++;
+        }
+        if (i == c->ilast) break;
+        i = T->inext[i];
+      }
+      cc = c->cnext;
+    }
+    for (int k = 0; k < nd; k++) { a[(size_t) s*nd + k] += A.atree[k]; adot[(size_t) s*nd + k] += ad[k]; }
+    gpot[s] += A.gpot;
+    if (counts) { counts[3*s] = Nneib; counts[3*s + 1] = Ndirect; counts[3*s + 2] = Ngravcell; }
+  }
+  return 0;
+}

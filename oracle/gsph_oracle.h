@@ -132,6 +132,12 @@ int orc_hydro_grav_forces_tree(const orc_params* p, const orc_tree* t, int N, co
                      double* a, double* atree, double* gpot, double* dudt, double* div_v,
                      double* dalphadt, int32_t* levelneib, int32_t* ndirect, int32_t* ncell);
 
+/* gravity of the gas on star particles (HydroTree::UpdateAllStarGasForces, HydroTree.cpp:552-654):
+ * stars = Nstar rows {r[ndim], v[ndim], h}; a, adot (Hermite schemes), gpot are ADDED to;
+ * counts (may be NULL) = per star the sizes of its neighbour, direct and cell lists.              */
+int orc_star_gas_forces(const orc_params* p, const orc_tree* T, int Nstar, const double* stars,
+                        double* a, double* adot, double* gpot, int32_t* counts);
+
 #ifdef __cplusplus
 }
 #endif

@@ -427,7 +427,7 @@ static int run(Parameters* params, const string& icfile, double perturb, const s
   if (!g_snapshot_col.empty()) sb->WriteSnapshotFile(g_snapshot_col, "column");
 
   // ---------------------------------------------------------------- operator-level captures
-  if (want("density") || want("forces") || want("neib") || want("tree") || want("gravlists")) {
+  if (want("density") || want("forces") || want("neib") || want("tree") || want("gravlists") || want("stargas")) {
     H.set_all_active();
     if (perturb != 0.0) H.perturb_h(perturb);
     // gpot is an input of the density pass only through the sink potmin test; keep as is.
@@ -446,6 +446,29 @@ static int run(Parameters* params, const string& icfile, double perturb, const s
     if (want("forces")) H.dump_particles("force_in");
     H.run_forces();
     if (want("forces")) H.dump_particles("force_out");
+    // gravity of the gas on the stars (HydroTree::UpdateAllStarGasForces), as MainLoop calls it
+    // after the gas forces (SphSimulation.cpp:786-792)
+    if (want("stargas") && sim->nbody->Nstar > 0 && H.sph->self_gravity == 1) {
+      const int Ns = sim->nbody->Nstar;
+      vector<double> sa(Ns*ndim), sadot(Ns*ndim), sgpot(Ns), sr(Ns*ndim), sv(Ns*ndim), sh(Ns), sm(Ns);
+      for (int i = 0; i < Ns; i++) {
+        NbodyParticle<ndim>* st = sim->nbody->nbodydata[i];
+        st->flags.set(active);
+        for (int k = 0; k < ndim; k++) { st->a[k] = 0.0; st->adot[k] = 0.0; }
+        st->gpot = 0.0;
+      }
+      H.sphneib->UpdateAllStarGasForces(H.sph, sim->nbody, sim->simbox, sim->ewald);
+      for (int i = 0; i < Ns; i++) {
+        NbodyParticle<ndim>* st = sim->nbody->nbodydata[i];
+        for (int k = 0; k < ndim; k++) {
+          sa[i*ndim+k] = st->a[k]; sadot[i*ndim+k] = st->adot[k]; sr[i*ndim+k] = st->r[k]; sv[i*ndim+k] = st->v[k];
+        }
+        sgpot[i] = st->gpot; sh[i] = st->h; sm[i] = st->m;
+      }
+      dump_f64("stargas.a", sa, Ns, ndim); dump_f64("stargas.adot", sadot, Ns, ndim); dump_f64("stargas.gpot", sgpot, Ns);
+      dump_f64("stargas.r", sr, Ns, ndim); dump_f64("stargas.v", sv, Ns, ndim); dump_f64("stargas.h", sh, Ns);
+      dump_f64("stargas.m", sm, Ns);
+    }
   }
 
   // ---------------------------------------------------------------- drop-in check: the reference's

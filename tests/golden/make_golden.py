@@ -265,6 +265,20 @@ def case_sphere_grav_stars():
     return p, d
 
 
+def case_stargas_hermite4():
+    """HydroTree::UpdateAllStarGasForces (HydroTree.cpp:552-654): gravity of the gas on three stars, with the
+    Hermite-4 N-body class so that adot is filled too.  Only what that operator reads and writes is kept."""
+    ic = sphere_ic(2031, 1500)
+    p = base_params(3, self_gravity=1, multipole="quadrupole", gravity_mac="geometric", thetamaxsqd=0.15,
+                    Nstar=len(STARS), nbody="hermite4")
+    d, _ = refio.run_harness(p, ic=ic, perturb_h=0.05, dumps="forces,stargas", stars=STARS)
+    keep = {k: v for k, v in d.items() if k.startswith("stargas.")}
+    for f in ("r", "v", "m", "h", "iorig"):
+        keep["force_in." + f] = d["force_in." + f]
+    keep["stars"] = STARS
+    return p, keep
+
+
 def case_sphere_grav_gadget2():
     """Gadget-2 relative opening criterion (Tree.h:413-432): the cells' amin comes from the atree the
     reference's own setup force pass left in the particles (dens_in.atree)."""
@@ -316,6 +330,7 @@ CASES = {
     "sphere_grav_mono": case_sphere_grav_mono,
     "sphere_grav_gadget2": case_sphere_grav_gadget2,
     "sphere_grav_stars": case_sphere_grav_stars,
+    "stargas_hermite4": case_stargas_hermite4,
     "sphere_grav_eigen": case_sphere_grav_eigen,
     "box3d_mm97": case_box3d_mm97,
 }
@@ -344,6 +359,8 @@ def pack(params, d, keep_direct=False):
         if key in d:
             out[key] = d[key]
     for k, v in d.items():
+        if k.startswith("stargas."):
+            out[k] = v
         if ("neib_" in k or "tree_" in k or "direct_" in k or "smooth_" in k or "gravcell" in k
                 or "leaf_of" in k):
             if k.endswith("direct_idx") and not keep_direct:
@@ -364,7 +381,7 @@ def main():
         out = pack(params, d, keep_direct=(name == "sphere_grav_mono"))
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **out)
-        print("%-24s N=%-6d %7.1f kB  (%d arrays)" % (name, len(d["dens_in.m"]), os.path.getsize(path) / 1e3,
+        print("%-24s N=%-6d %7.1f kB  (%d arrays)" % (name, len(d["dens_in.m"] if "dens_in.m" in d else d["force_in.m"]), os.path.getsize(path) / 1e3,
                                                       len(out)))
 
 

@@ -333,6 +333,21 @@ class Tree:
         lib().orc_tree_cells(self.ptr, box, com, sc, q, n)
         return dict(box=box, com=com, scalars=sc, q=q, N=n)
 
+    def star_gas_forces(self, rstar, vstar, hstar):
+        """HydroTree::UpdateAllStarGasForces on this tree -> (a, adot, gpot, counts[Nstar][neib, direct, cells])"""
+        nd = self.p.ndim
+        ns = len(hstar)
+        rows = np.ascontiguousarray(np.concatenate([np.asarray(rstar, dtype=np.float64).reshape(ns, nd),
+                                                    np.asarray(vstar, dtype=np.float64).reshape(ns, nd),
+                                                    np.asarray(hstar, dtype=np.float64)[:, None]], axis=1))
+        a = np.zeros((ns, nd)); adot = np.zeros((ns, nd)); gpot = np.zeros(ns)
+        counts = np.zeros((ns, 3), dtype=np.int32)
+        L = lib()
+        L.orc_star_gas_forces.restype = C.c_int
+        L.orc_star_gas_forces.argtypes = [C.POINTER(OrcParams), C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _ip]
+        L.orc_star_gas_forces(C.byref(self.p), self.ptr, ns, rows, a, adot, gpot, counts.reshape(-1))
+        return a, adot, gpot, counts
+
     def hydro_grav_forces(self, s):
         N = self.N
         out = _grav_out(N, self.p.ndim)

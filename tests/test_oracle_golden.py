@@ -143,3 +143,18 @@ def test_direct_gravity_close_to_tree(name):
         out["atree"] = out["atree"] + orc.star_grav_forces(p, si["r"], si["h"], st[:, :3], st[:, 3], st[:, 4])[1]
     e = vec_rel_err(out["atree"], so["atree"])
     assert np.sqrt(np.mean(e ** 2)) < 2e-2
+
+
+def test_star_gas_forces_match_reference():
+    """HydroTree::UpdateAllStarGasForces: gravity of the gas on the star particles (a, gpot, and adot of
+    the Hermite-4 class) from the reference's own run (tests/golden/stargas_hermite4.npz)"""
+    params, d = load_golden("stargas_hermite4")
+    p = orc.params_from_dict(params)
+    o = np.argsort(d["force_in.iorig"])
+    r, v, m, h = (d["force_in." + f][o] for f in ("r", "v", "m", "h"))
+    t = orc.Tree(p, r, v, m, h)
+    a, adot, gpot, counts = t.star_gas_forces(d["stargas.r"], d["stargas.v"], d["stargas.h"])
+    assert (counts[:, 0] > 0).any() and (counts[:, 2] > 0).all()      # smoothed neighbours and cells both occur
+    assert vec_rel_err(a, d["stargas.a"]).max() < TOL
+    assert rel_err(gpot, d["stargas.gpot"]).max() < TOL
+    assert vec_rel_err(adot, d["stargas.adot"]).max() < 1e-6           # (single-precision powf in the reference)
