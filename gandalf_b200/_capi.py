@@ -91,7 +91,7 @@ EXPORTS = [
     "gsph_tree_cells", "gsph_get_stats", "gsph_kernel_table", "gsph_measure_fp_peak",
     "gsph_integrator_begin", "gsph_integrator_step", "gsph_integrator_state",
     "gsph_update_all_forces_begin", "gsph_update_all_forces_finish", "gsph_integrator_advance",
-    "gsph_integrator_finish",
+    "gsph_integrator_finish", "gsph_update_star_gas_forces",
 ]
 
 _lib = None
@@ -135,6 +135,7 @@ def lib():
     L.gsph_integrator_step.argtypes = [H, C.c_int]
     L.gsph_integrator_advance.argtypes = [H, C.POINTER(C.c_int), C.POINTER(C.c_double)]
     L.gsph_integrator_finish.argtypes = [H]
+    L.gsph_update_star_gas_forces.argtypes = [H, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.gsph_integrator_state.argtypes = [H, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     for n in ("gsph_update_active_counters", "gsph_update_properties", "gsph_zero_accelerations",
               "gsph_update_hydro_forces", "gsph_synchronize", "gsph_timer_start", "gsph_density_pass",

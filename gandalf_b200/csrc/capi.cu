@@ -1148,6 +1148,44 @@ int gsph_update_all_forces(gsph_handle* h, const double* stars, int Nstar)
   return gsph_update_all_forces_finish(h);
 }
 
+/* HydroTree::UpdateAllStarGasForces (HydroTree.cpp:552-654) */
+int gsph_update_star_gas_forces(gsph_handle* h, const double* stars, int Nstar, double* a, double* adot, double* gpot,
+                                int32_t* counts)
+{
+  if (!h) return GSPH_EINVAL;
+  if (!h->have_tree || !h->sorted_valid) { h->err = "gsph_update_star_gas_forces before gsph_build_tree"; return GSPH_ESTATE; }
+  if (Nstar < 0 || (Nstar > 0 && (!stars || !a || !gpot))) { h->err = "gsph_update_star_gas_forces: bad arguments"; return GSPH_EINVAL; }
+  if (h->cfg.kernel == GSPH_KERNEL_GAUSSIAN) { h->err = "gsph_update_star_gas_forces: the gaussian kernel has no gravity softening"; return GSPH_EINVAL; }
+  for (int k = 0; k < h->cfg.ndim; k++)
+    if (h->dp.periodic[k]) { h->err = "gsph_update_star_gas_forces: periodic (Ewald) gravity is not on the accelerated path"; return GSPH_EINVAL; }
+  if (Nstar == 0) return GSPH_OK;
+  cudaSetDevice(h->device);
+  const int nd = h->cfg.ndim, row = 2*nd + 1;
+  double* d = nullptr; int* di = nullptr;
+  CUDA_TRY(h, cudaMalloc(&d, (size_t) Nstar*row*2*sizeof(double)));
+  if (cudaMalloc(&di, ((size_t) Nstar*3 + 1)*sizeof(int)) != cudaSuccess) { cudaFree(d); h->err = "cudaMalloc failed"; return GSPH_ENOMEM; }
+  double* dout = d + (size_t) Nstar*row;
+  int rc = GSPH_OK;
+  std::vector<double> res((size_t) Nstar*row);
+  std::vector<int> cnt((size_t) Nstar*3 + 1);
+  auto fail = [&](cudaError_t e) { if (e != cudaSuccess && rc == GSPH_OK) { h->err = cudaGetErrorString(e); rc = GSPH_ECUDA; } };
+  fail(cudaMemcpyAsync(d, stars, (size_t) Nstar*row*sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  fail(cudaMemsetAsync(di, 0, ((size_t) Nstar*3 + 1)*sizeof(int), h->stream));
+  if (rc == GSPH_OK) rc = gsph_run_star_gas(h, d, Nstar, dout, di, di + (size_t) Nstar*3);
+  fail(cudaMemcpyAsync(res.data(), dout, res.size()*sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  fail(cudaMemcpyAsync(cnt.data(), di, cnt.size()*sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  fail(cudaStreamSynchronize(h->stream));
+  cudaFree(d); cudaFree(di);
+  if (rc) return rc;
+  if (cnt[(size_t) Nstar*3]) { h->err = "gsph_update_star_gas_forces: tree-walk stack overflow"; return GSPH_ENOMEM; }
+  for (int s = 0; s < Nstar; s++) {
+    for (int k = 0; k < nd; k++) { a[(size_t) s*nd + k] += res[(size_t) s*row + k]; if (adot) adot[(size_t) s*nd + k] += res[(size_t) s*row + nd + k]; }
+    gpot[s] += res[(size_t) s*row + 2*nd];
+    if (counts) for (int k = 0; k < 3; k++) counts[3*s + k] = cnt[(size_t) 3*s + k];
+  }
+  return GSPH_OK;
+}
+
 int gsph_get_hmax(gsph_handle* h, double* hmax)
 {
   if (!h || !hmax) return GSPH_EINVAL;

@@ -196,7 +196,8 @@ int gsph_run_density(gsph_handle* h);                                 /* density
 int gsph_run_hydro(gsph_handle* h, int with_gravity);                 /* hydro.cu   */
 int gsph_run_neiblist(gsph_handle* h, int32_t* counts_dev, const int64_t* offsets_dev, int32_t* idx_dev);
 int gsph_run_gravity(gsph_handle* h);                                 /* gravity.cu */
-int gsph_run_star_forces(gsph_handle* h);                             /* hydro.cu   */
+int gsph_run_star_forces(gsph_handle* h);
+int gsph_run_star_gas(gsph_handle* h, const double* dstars, int Nstar, double* dout, int* dcounts, int* derr);   /* hydro.cu */                             /* hydro.cu   */
 int gsph_check_status(gsph_handle* h, const char* where);             /* capi.cu    */
 int gsph_ensure_cand(gsph_handle* h, int warps, size_t cap_per_warp);
 int gsph_ensure_nlist(gsph_handle* h, int warps, size_t cap);

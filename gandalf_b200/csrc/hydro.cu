@@ -746,7 +746,198 @@ int dispatch_stars(gsph_handle* h)
   return tab ? launch_stars<NDIM, GSPH_KERNEL_QUINTIC, true>(h) : launch_stars<NDIM, GSPH_KERNEL_QUINTIC, false>(h);
 }
 
+/* HydroTree::UpdateAllStarGasForces (HydroTree.cpp:552-654): gravity of the gas on the star particles.
+ * One warp per star walks the tree from the root, 32 nodes per round (Tree::ComputeStarGravityInteractionList,
+ * Tree.cpp:748-885 -- the geometric opening test whatever gravity_mac says): leaves whose kernels may overlap
+ * the star's give smoothed pair terms with the mean h, accepted cells their monopole / quadrupole at the
+ * star's position, the remaining leaves unsoftened pair terms (NbodyHermite4::CalculateDirectHydroForces,
+ * NbodyHermite4.cpp:151-247; adot is what the Hermite schemes use, the leapfrog classes ignore it).
+ * stars: rows {r[NDIM], v[NDIM], h}; out: rows {a[NDIM], adot[NDIM], gpot} (sums, not added);
+ * counts: per star neighbours, direct particles, cells.                                            */
+#define STARGAS_STACK 4096
+template <int NDIM, int KERN, bool TAB>
+__global__ void __launch_bounds__(32)
+star_gas_kernel(TreeDev T, PartView P, DevParams dp, const double* __restrict__ gtables,
+                const double* __restrict__ stars, double* __restrict__ out, int* __restrict__ counts, int* __restrict__ err)
+{
+  __shared__ int stack[STARGAS_STACK];
+  const int lane = threadIdx.x, s = blockIdx.x;
+  const KernelEval<KERN, NDIM, TAB> K(dp, gtables);
+  const double* sp = stars + (size_t) s*(2*NDIM + 1);
+  double rs[3] = {0, 0, 0}, vs[3] = {0, 0, 0};
+#pragma unroll
+  for (int k = 0; k < NDIM; k++) { rs[k] = sp[k]; vs[k] = sp[NDIM + k]; }
+  const double hs = sp[2*NDIM];
+  const double halfrange = __dmul_rn(0.5, __dmul_rn(dp.kernrange, hs));
+  const double twopi = 6.28318530717959;                  /* src/Headers/Constants.h:62 */
+  const int leaf0 = (1 << T.ltot) - 1;
+  double acc[3] = {0, 0, 0}, ad[3] = {0, 0, 0}, pot = 0.0;
+  int nneib = 0, ndir = 0, ncell = 0;
+  int top = 0;
+  if (lane == 0) stack[0] = 0;
+  top = 1;
+  __syncwarp();
+  while (top > 0) {
+    const int take = min(top, 32);
+    const int n = lane < take ? stack[top - 1 - lane] : -1;
+    top -= take;
+    __syncwarp();
+    int mode = 0;                                         /* 1 smoothed leaf, 2 direct leaf, 3 cell, 4 open */
+    if (n >= 0 && T.count[n] > 0) {
+      double dr[3] = {0, 0, 0};
+#pragma unroll
+      for (int k = 0; k < NDIM; k++) dr[k] = T.rcell[k][n] - rs[k];
+      const double drsqd = dot_exact<NDIM>(dr);
+      const double thr = __dadd_rn(__dadd_rn(halfrange, T.rmax[n]), __dmul_rn(__dmul_rn(0.5, dp.kernrange), T.hmax[n]));
+      const bool leaf = n >= leaf0;
+      if (drsqd < __dmul_rn(thr, thr)) mode = leaf ? 1 : 4;
+      else if (drsqd > T.cdistsqd[n]) mode = (leaf && T.count[n] == 1) ? 2 : 3;
+      else mode = leaf ? 2 : 4;
+    }
+    /* children of the opened nodes */
+    const unsigned open = __ballot_sync(FULLMASK, mode == 4);
+    if (open) {
+      const int before = __popc(open & ((1u << lane) - 1u));
+      const int nopen = __popc(open);
+      if (top + 2*nopen > STARGAS_STACK) { if (lane == 0) atomicExch(err, 1); return; }
+      if (mode == 4) { stack[top + 2*before] = 2*n + 2; stack[top + 2*before + 1] = 2*n + 1; }
+      top += 2*nopen;
+    }
+    __syncwarp();
+    if (mode == 3) {
+      ncell++;
+      if (dp.multipole == GSPH_MULTIPOLE_MONOPOLE || dp.multipole == GSPH_MULTIPOLE_FAST_MONOPOLE) {
+        /* ComputeCellMonopoleForces, NeighbourSearch.h:349-380 */
+        double dr[3] = {0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < NDIM; k++) dr[k] = T.com[k][n] - rs[k];
+        const double drsqd = dot_exact<NDIM>(dr) + GSPH_SMALL;
+        const double invdrsqd = 1.0/drsqd, invdrmag = sqrt(invdrsqd), invdr3 = invdrsqd*invdrmag, mc = T.m[n];
+        pot += mc*invdrmag;
+#pragma unroll
+        for (int k = 0; k < NDIM; k++) acc[k] += mc*dr[k]*invdr3;
+      }
+      else {
+        /* ComputeCellQuadrupoleForces, NeighbourSearch.h:390-470 */
+        double dr[3] = {0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < NDIM; k++) dr[k] = rs[k] - T.com[k][n];
+        const double drsqd = dot_exact<NDIM>(dr) + GSPH_SMALL;
+        const double invdrsqd = 1.0/drsqd, invdrmag = sqrt(invdrsqd), invdr5 = invdrsqd*invdrsqd*invdrmag, mc = T.m[n];
+#pragma unroll
+        for (int k = 0; k < NDIM; k++) acc[k] -= mc*dr[k]*invdrsqd*invdrmag;
+        double q[5] = {0, 0, 0, 0, 0};
+        for (int k = 0; k < 5; k++) q[k] = T.q[k][n];
+        double qscalar, qfactor;
+        if (NDIM == 3) {
+          qscalar = q[0]*dr[0]*dr[0] + q[2]*dr[1]*dr[1] - (q[0] + q[2])*dr[2]*dr[2] +
+                    2.0*(q[1]*dr[0]*dr[1] + q[3]*dr[0]*dr[2] + q[4]*dr[1]*dr[2]);
+          qfactor = 2.5*qscalar*invdr5*invdrsqd;
+          acc[0] += (q[0]*dr[0] + q[1]*dr[1] + q[3]*dr[2])*invdr5 - qfactor*dr[0];
+          acc[1] += (q[1]*dr[0] + q[2]*dr[1] + q[4]*dr[2])*invdr5 - qfactor*dr[1];
+          acc[2] += (q[3]*dr[0] + q[4]*dr[1] - (q[0] + q[2])*dr[2])*invdr5 - qfactor*dr[2];
+        }
+        else if (NDIM == 2) {
+          qscalar = q[0]*dr[0]*dr[0] + q[2]*dr[1]*dr[1] + 2.0*q[1]*dr[0]*dr[1];
+          qfactor = 2.5*qscalar*invdr5*invdrsqd;
+          acc[0] += (q[0]*dr[0] + q[1]*dr[1])*invdr5 - qfactor*dr[0];
+          acc[1] += (q[1]*dr[0] + q[2]*dr[1])*invdr5 - qfactor*dr[1];
+        }
+        else {
+          qscalar = q[0]*dr[0]*dr[0];
+          qfactor = 2.5*qscalar*invdr5*invdrsqd;
+          acc[0] += (q[0]*dr[0])*invdr5 - qfactor*dr[0];
+        }
+        pot += mc*invdrmag + 0.5*qscalar*invdr5;
+      }
+    }
+    else if (mode == 1 || mode == 2) {
+      const int f = T.first[n], c = T.count[n];
+      for (int j = f; j < f + c; j++) {
+        if (((unsigned) P.i[I_FLAGS][j]) & GSPH_FLAG_DEAD) continue;
+        double dr[3] = {0, 0, 0}, dv[3] = {0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < NDIM; k++) { dr[k] = P.f[F_RX + k][j] - rs[k]; dv[k] = P.f[F_VX + k][j] - vs[k]; }
+        const double drsqd = dot_exact<NDIM>(dr), drmag = sqrt(drsqd), invdrmag = 1.0/drmag;
+        double dvdr = 0.0;
+#pragma unroll
+        for (int k = 0; k < NDIM; k++) dvdr += dv[k]*dr[k];
+        const double drdt = dvdr*invdrmag, mj = P.f[F_M][j];
+        if (mode == 1) {
+          nneib++;
+          const double invhmean = 2.0/(hs + P.f[F_H][j]);
+          const double sj = drmag*invhmean;
+          const double paux = mj*invhmean*invhmean*K.wgrav(sj)*invdrmag;
+          double w0;
+          if (TAB) w0 = sj >= K.kr ? 0.0 : kern_analytic<KERN, NDIM>(0, (K.kr/GSPH_TABLE_RES)*(int)(sj*K.res_invkr), K.kn);
+          else w0 = kern_analytic<KERN, NDIM>(0, sj, K.kn);
+          const double wkern = w0*(double) powf((float) invhmean, (float) NDIM);     /* powf: NbodyHermite4.cpp:194 */
+#pragma unroll
+          for (int k = 0; k < NDIM; k++) {
+            acc[k] += paux*dr[k];
+            ad[k] += paux*dv[k] - 3.0*paux*drdt*invdrmag*dr[k] + 2.0*twopi*mj*drdt*wkern*invdrmag*dr[k];
+          }
+          pot += mj*invhmean*K.wpot(sj);
+        }
+        else {
+          ndir++;
+          const double invdr3 = invdrmag*invdrmag*invdrmag;
+#pragma unroll
+          for (int k = 0; k < NDIM; k++) {
+            acc[k] += mj*dr[k]*invdr3;
+            ad[k] += mj*invdr3*(dv[k] - 3.0*drdt*invdrmag*dr[k]);
+          }
+          pot += mj*invdrmag;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < NDIM; k++) { acc[k] = warp_sum(acc[k]); ad[k] = warp_sum(ad[k]); }
+  pot = warp_sum(pot);
+  nneib = (int) warp_sum((double) nneib); ndir = (int) warp_sum((double) ndir); ncell = (int) warp_sum((double) ncell);
+  if (lane == 0) {
+    double* o = out + (size_t) s*(2*NDIM + 1);
+#pragma unroll
+    for (int k = 0; k < NDIM; k++) { o[k] = acc[k]; o[NDIM + k] = ad[k]; }
+    o[2*NDIM] = pot;
+    counts[3*s] = nneib; counts[3*s + 1] = ndir; counts[3*s + 2] = ncell;
+  }
+}
+
+template <int NDIM, int KERN, bool TAB>
+int launch_star_gas(gsph_handle* h, const double* dstars, int Nstar, double* dout, int* dcounts, int* derr)
+{
+  PartView P;
+  for (int k = 0; k < NF_DOUBLE; k++) P.f[k] = h->P[k];
+  for (int k = 0; k < NF_INT; k++) P.i[k] = h->PI[k];
+  star_gas_kernel<NDIM, KERN, TAB><<<Nstar, 32, 0, h->stream>>>(h->tree, P, h->dp, h->tables, dstars, dout, dcounts, derr);
+  h->stats.kernel_launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return GSPH_OK;
+}
+
+template <int NDIM>
+int dispatch_star_gas(gsph_handle* h, const double* dstars, int Nstar, double* dout, int* dcounts, int* derr)
+{
+  const bool tab = h->dp.tabulated != 0;
+  if (h->dp.kernel == GSPH_KERNEL_M4)
+    return tab ? launch_star_gas<NDIM, GSPH_KERNEL_M4, true>(h, dstars, Nstar, dout, dcounts, derr)
+               : launch_star_gas<NDIM, GSPH_KERNEL_M4, false>(h, dstars, Nstar, dout, dcounts, derr);
+  return tab ? launch_star_gas<NDIM, GSPH_KERNEL_QUINTIC, true>(h, dstars, Nstar, dout, dcounts, derr)
+             : launch_star_gas<NDIM, GSPH_KERNEL_QUINTIC, false>(h, dstars, Nstar, dout, dcounts, derr);
+}
+
 }  // namespace
+
+int gsph_run_star_gas(gsph_handle* h, const double* dstars, int Nstar, double* dout, int* dcounts, int* derr)
+{
+  switch (h->dp.ndim) {
+  case 1: return dispatch_star_gas<1>(h, dstars, Nstar, dout, dcounts, derr);
+  case 2: return dispatch_star_gas<2>(h, dstars, Nstar, dout, dcounts, derr);
+  default: return dispatch_star_gas<3>(h, dstars, Nstar, dout, dcounts, derr);
+  }
+}
 
 int gsph_run_star_forces(gsph_handle* h)
 {

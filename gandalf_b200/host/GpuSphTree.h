@@ -223,6 +223,32 @@ class GpuSphTree : public GradhSphTree<ndim, GradhSphParticle>
     (void) simbox; (void) ewald;
   }
 
+  /// Gravity of the gas on the active stars (HydroTree.cpp:552-654) from the device copy of the tree and
+  /// the particles of the force pass that MainLoop has just run (SphSimulation.cpp:786-792).
+  virtual void UpdateAllStarGasForces(Hydrodynamics<ndim>* hydro, Nbody<ndim>* nbody, DomainBox<ndim>& simbox,
+                                      Ewald<ndim>* ewald)
+  {
+    CodeTiming::BlockTimer timer = this->timing->StartNewTimer("STAR_GAS_GRAV_FORCES");
+    std::vector<int> act;
+    for (int i = 0; i < nbody->Nstar; i++) if (nbody->nbodydata[i]->flags.check(active)) act.push_back(i);
+    const int ns = (int) act.size();
+    if (ns == 0) return;
+    const int row = 2*ndim + 1;
+    std::vector<double> rows((size_t) ns*row), a((size_t) ns*ndim, 0.0), adot((size_t) ns*ndim, 0.0), gpot(ns, 0.0);
+    for (int j = 0; j < ns; j++) {
+      NbodyParticle<ndim>* st = nbody->nbodydata[act[j]];
+      for (int k = 0; k < ndim; k++) { rows[(size_t) j*row + k] = st->r[k]; rows[(size_t) j*row + ndim + k] = st->v[k]; }
+      rows[(size_t) j*row + 2*ndim] = st->h;
+    }
+    check(gsph_update_star_gas_forces(handle, rows.data(), ns, a.data(), adot.data(), gpot.data(), NULL));
+    for (int j = 0; j < ns; j++) {
+      NbodyParticle<ndim>* st = nbody->nbodydata[act[j]];
+      for (int k = 0; k < ndim; k++) { st->a[k] += a[(size_t) j*ndim + k]; st->adot[k] += adot[(size_t) j*ndim + k]; }
+      st->gpot += gpot[j];
+    }
+    (void) hydro; (void) simbox; (void) ewald;
+  }
+
   virtual double GetMaximumSmoothingLength() const
   {
     double hmax = 0.0;

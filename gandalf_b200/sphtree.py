@@ -256,6 +256,20 @@ class GpuSphTree(object):
         from . import snapshot
         return snapshot.particle_set_from_su(path, alloc=alloc)
 
+    def UpdateAllStarGasForces(self, rstar, vstar, hstar):
+        """NeighbourSearch::UpdateAllStarGasForces (HydroTree.cpp:552-654): gravity of the gas on the stars
+        -> (a, adot, gpot, counts[Nstar][neighbours, direct, cells]); uses the tree / particles of the last pass"""
+        nd = self.cfg.ndim
+        ns = len(hstar)
+        rows = np.ascontiguousarray(np.concatenate([np.asarray(rstar, dtype=np.float64).reshape(ns, nd),
+                                                    np.asarray(vstar, dtype=np.float64).reshape(ns, nd),
+                                                    np.asarray(hstar, dtype=np.float64)[:, None]], axis=1))
+        a = np.zeros((ns, nd)); adot = np.zeros((ns, nd)); gpot = np.zeros(ns)
+        counts = np.zeros((ns, 3), dtype=np.int32)
+        self._check(self._L.gsph_update_star_gas_forces(self._h, rows.ctypes.data, ns, a.ctypes.data, adot.ctypes.data,
+                                                        gpot.ctypes.data, counts.ctypes.data))
+        return a, adot, gpot, counts
+
     def SetStars(self, r=None, m=None, h=None):
         """nbody->nbodydata for GradhSph::ComputeStarGravForces (GradhSph.cpp:699-743): star positions
         (Nstar, ndim), masses and smoothing lengths; applied by both force passes until cleared

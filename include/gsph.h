@@ -216,6 +216,16 @@ int gsph_update_all_forces_finish(gsph_handle* h);
  * stars = Nstar x {r[ndim], m, h} doubles.  The list stays on the device and is applied by
  * gsph_update_hydro_forces and gsph_update_all_forces until replaced; Nstar = 0 clears it.         */
 int gsph_set_stars(gsph_handle* h, const double* stars, int Nstar);
+
+/* Gravity of the gas on the star particles -- NeighbourSearch::UpdateAllStarGasForces
+ * (src/Tree/HydroTree.cpp:552-654: Tree::ComputeStarGravityInteractionList Tree.cpp:748-885, then
+ * Nbody::CalculateDirectHydroForces and the cell multipoles at the star's position).  Uses the tree and
+ * the tree-order particles of the last passes.  stars = Nstar x {r[ndim], v[ndim], h}; a, adot
+ * (Nstar x ndim; adot may be NULL -- only the Hermite N-body schemes use it) and gpot (Nstar) are ADDED
+ * to, like the reference adds to star->a, star->adot, star->gpot; counts (may be NULL) = per star the
+ * number of smoothed neighbours, direct particles and cells.  Open boundaries only.                  */
+int gsph_update_star_gas_forces(gsph_handle* h, const double* stars, int Nstar, double* a, double* adot,
+                                double* gpot, int32_t* counts);
 int gsph_get_hmax(gsph_handle* h, double* hmax);
 int gsph_synchronize(gsph_handle* h);
 /* CUDA-event stopwatch on the handle's stream (torch.cuda.Event only sees torch's streams):

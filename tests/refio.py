@@ -111,7 +111,7 @@ def csr_rows(off, idx):
     return [idx[off[i]:off[i + 1]] for i in range(len(off) - 1)]
 
 
-def run_mainloop(params, ic, steps, gpu, timeout=1800, kind="gpu", dumps="", resident=0):
+def run_mainloop(params, ic, steps, gpu, timeout=1800, kind="gpu", dumps="", resident=0, stars=None):
     """N steps of the reference's own SphSimulation::MainLoop through oracle/_ref/ref_harness_gpu;
     gpu=True swaps sim->sphneib for gandalf_b200/host/GpuSphTree.h first.  -> (arrays, info json)"""
     exe = harness_path(kind)
@@ -128,6 +128,12 @@ def run_mainloop(params, ic, steps, gpu, timeout=1800, kind="gpu", dumps="", res
             cmd.append("--gpu")
         if resident:
             cmd += ["--resident", str(int(resident))]      # the first `resident` steps in the device main loop
+        if stars is not None:
+            sf = os.path.join(work, "stars.bin")
+            with open(sf, "wb") as fh:
+                fh.write(np.int64(len(stars)).tobytes())
+                fh.write(np.ascontiguousarray(np.asarray(stars, dtype=np.float64).T).tobytes())
+            cmd += ["--stars", sf]
         res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=timeout)
         if res.returncode != 0:
             raise RuntimeError("ref_harness_gpu failed (%d): %s %s" % (res.returncode, res.stdout.decode()[-1000:],

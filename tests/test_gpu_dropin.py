@@ -80,3 +80,23 @@ def test_reference_hands_over_to_the_device_main_loop(name, steps, resident):
     for f in ("h", "rho", "u", "alpha"):
         assert rel_err(dev["loop." + f][og], cpu["loop." + f][oc]).max() < tol, f
     assert scaled_err(dev["loop.dudt"][og], cpu["loop.dudt"][oc]).max() < tol
+
+
+def test_reference_mainloop_with_stars_and_gpu_tree():
+    """three star particles: the gas feels them (ComputeStarGravForces, star terms of zeta) and they feel
+    the gas through GpuSphTree::UpdateAllStarGasForces; the reference's own N-body integrator moves them.
+    Gas state after 3 steps == the all-CPU run."""
+    if refio.harness_path("gpu") is None:
+        pytest.skip("oracle/_ref/ref_harness_gpu not built")
+    p, ic = _case("sphere_grav_stars")
+    _, d = load_golden("sphere_grav_stars")
+    cpu, ci = refio.run_mainloop(p, ic, 3, gpu=False, stars=d["stars"])
+    gpu, gi = refio.run_mainloop(p, ic, 3, gpu=True, stars=d["stars"])
+    assert abs(ci["t"] - gi["t"]) <= 1e-12*abs(ci["t"])
+    oc, og = np.argsort(cpu["loop.iorig"]), np.argsort(gpu["loop.iorig"])
+    for f in ("r", "v", "a"):
+        a, b = gpu["loop." + f][og], cpu["loop." + f][oc]
+        e = np.linalg.norm(a - b, axis=1)/np.maximum(np.linalg.norm(b, axis=1), np.abs(b).max()*1e-6)
+        assert e.max() < 1e-6, (f, e.max())
+    for f in ("h", "rho", "u", "zeta", "gpot"):
+        assert rel_err(gpu["loop." + f][og], cpu["loop." + f][oc]).max() < 1e-6, f

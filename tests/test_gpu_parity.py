@@ -646,3 +646,27 @@ def test_all_forces_in_two_halves():
         tree.close()
     for k in res[0]:
         assert np.array_equal(res[0][k], res[1][k]), k
+
+
+def test_star_gas_forces_match_reference():
+    """NeighbourSearch::UpdateAllStarGasForces: gravity of the gas on three stars (inside, outside, at the
+    edge of the cloud) against the reference's own result (Hermite-4 class: a, adot, gpot) and the oracle's
+    interaction-list sizes"""
+    import gandalf_b200 as g
+    params, d = load_golden("stargas_hermite4")
+    o = np.argsort(d["force_in.iorig"])
+    N = len(o)
+    ps = g.ParticleSet(N, 3).set(r=d["force_in.r"][o], v=d["force_in.v"][o], m=d["force_in.m"][o], h=d["force_in.h"][o],
+                                 u=1.0)
+    tree = g.GpuSphTree(params)
+    tree.BuildTree(True, 0, 1, 1, 0.0, ps)
+    a, adot, gpot, counts = tree.UpdateAllStarGasForces(d["stargas.r"], d["stargas.v"], d["stargas.h"])
+    assert vec_rel_err(a, d["stargas.a"]).max() < TOL
+    assert rel_err(gpot, d["stargas.gpot"]).max() < TOL
+    assert vec_rel_err(adot, d["stargas.adot"]).max() < 1e-6           # single-precision powf in the reference
+    p = orc.params_from_dict(params)
+    t = orc.Tree(p, ps["r"], ps["v"], ps["m"], ps["h"])
+    oa, oad, og, ocounts = t.star_gas_forces(d["stargas.r"], d["stargas.v"], d["stargas.h"])
+    assert np.array_equal(counts, ocounts)
+    assert vec_rel_err(adot, oad).max() < 1e-7
+    tree.close()
