@@ -215,3 +215,124 @@ def read_column(path):
         s = body[N:]
         out["stars"] = {"r": s[:, :ndim], "v": s[:, ndim:2*ndim], "m": s[:, 2*ndim], "h": s[:, 2*ndim + 1]}
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# SEREN formatted ("sf") snapshots: the same records as "su" as text (SimulationIO.hpp:989-1240 writer,
+# :600-980 reader): tag line, precision 4 and ndim x3 in width 2, the four 50-word header blocks
+# (integers width 10, reals %18.10e), unit and array ids one per line, the type table (5 x width 10 per
+# line), then the arrays (one particle per line) and the star records (integers width 8 there).
+# ---------------------------------------------------------------------------------------------------
+ASCII_TAG = "SERENASCIIDUMPV2"
+
+
+def write_sf(path, r, v, m, h, rho, u, iorig=None, ptype=None, t=0.0, Nsteps=0, Noutsnap=0, h_fac=1.2,
+             tsnaplast=0.0, mmean=None, stars=None, units=None):
+    r = np.asarray(r, dtype=np.float64)
+    N, ndim = r.shape
+    v = np.asarray(v, dtype=np.float64).reshape(N, ndim)
+    cols = [np.asarray(a, dtype=np.float64).reshape(N) for a in (m, h, rho, u)]
+    iorig = np.arange(N, dtype=np.int32) if iorig is None else np.asarray(iorig, dtype=np.int32)
+    ptype = np.zeros(N, dtype=np.int32) if ptype is None else np.asarray(ptype, dtype=np.int32)
+    if not np.isin(ptype, FILE_ORDER).all():
+        raise ValueError("SerenFormReader: Type not recognised")
+    order = np.concatenate([np.nonzero(ptype == pt)[0] for pt in FILE_ORDER])
+    nstar = 0 if stars is None else len(stars["m"])
+    ids = (["porig", "r", "m", "h", "v", "rho", "u"] if N > 0 else []) + (["sink_v1"] if nstar else [])
+    typedata = []
+    if N > 0:
+        typedata += [[1, 1, N, 2, 0], [ndim, 1, N, 4, 1], [1, 1, N, 4, 2], [1, 1, N, 4, 1], [ndim, 1, N, 4, 4],
+                     [1, 1, N, 4, 6], [1, 1, N, 4, 20]]
+    if nstar:
+        typedata += [[1, 1, nstar, 7, 0]]
+    idata = [0]*50
+    idata[0], idata[1] = N, nstar
+    idata[3:7] = [int((ptype == pt).sum()) for pt in FILE_ORDER]
+    idata[19], idata[20] = (0 if units is None else len(units)), len(ids)
+    ilp = [0]*50; ilp[0], ilp[1] = Noutsnap, Nsteps
+    rdata = [0.0]*50; rdata[0] = h_fac
+    ddata = [0.0]*50
+    ddata[0], ddata[1] = t, tsnaplast
+    ddata[2] = (float(cols[0].mean()) if N else 0.0) if mmean is None else mmean
+    fl = "%18.10e"
+    with open(path, "w") as f:
+        f.write(ASCII_TAG + "\n")
+        f.write("%2d\n" % 4 + ("%2d\n" % ndim)*3)
+        for x in idata + ilp:
+            f.write("%10d\n" % x)
+        for x in rdata + ddata:
+            f.write(fl % x + "\n")
+        for s_ in (units or []):
+            f.write(s_ + "\n")
+        for s_ in ids:
+            f.write(s_ + "\n")
+        for td in typedata:
+            f.write("".join("%10d" % x for x in td) + "\n")
+        if N > 0:
+            f.write("".join("%10d\n" % x for x in iorig[order]))
+            f.write("".join("".join(fl % x for x in row) + "\n" for row in r[order]))
+            f.write("".join(fl % x + "\n" for x in cols[0][order]))
+            f.write("".join(fl % x + "\n" for x in cols[1][order]))
+            f.write("".join("".join(fl % x for x in row) + "\n" for row in v[order]))
+            f.write("".join(fl % x + "\n" for x in cols[2][order]))
+            f.write("".join(fl % x + "\n" for x in cols[3][order]))
+        if nstar:
+            L = 12 + 2*ndim
+            f.write("".join("%10d" % x for x in (2, 2, 0, L, 0, 0)) + "\n")
+            sr = np.asarray(stars["r"], dtype=np.float64).reshape(nstar, ndim)
+            sv = np.asarray(stars.get("v", np.zeros((nstar, ndim))), dtype=np.float64).reshape(nstar, ndim)
+            for i in range(nstar):
+                f.write("TT\n")
+                f.write("%8d%8d\n" % (i + 1, 0))
+                sd = np.zeros(L)
+                sd[1:1 + ndim] = sr[i]; sd[1 + ndim:1 + 2*ndim] = sv[i]
+                sd[1 + 2*ndim] = stars["m"][i]; sd[2 + 2*ndim] = stars["h"][i]
+                sd[3 + 2*ndim] = stars.get("radius", np.zeros(nstar))[i]
+                f.write("".join(fl % x for x in sd) + "\n")
+
+
+def read_sf(path):
+    """-> the same dict as read_su (values carry the 11 significant digits of the text)"""
+    with open(path) as f:
+        tok = f.read().split()
+    if tok[0] not in (ASCII_TAG, "SERENASCIIDUMPV3"):
+        raise ValueError("Incorrect format of snapshot file %s: %s" % (path, tok[0]))
+    pos = [1]
+
+    def take(n, conv):
+        out = [conv(x) for x in tok[pos[0]:pos[0] + n]]
+        if len(out) != n:
+            raise ValueError("snapshot file %s is truncated" % path)
+        pos[0] += n
+        return out
+    _, n1, n2, n3 = take(4, int)
+    if not (n1 == n2 == n3):
+        raise ValueError("Incorrect NDIM in file %s" % path)
+    ndim = n1
+    idata, ilp = take(50, int), take(50, int)
+    rdata, ddata = take(50, float), take(50, float)
+    N, nstar, nunit, ndata = idata[0], idata[1], idata[19], idata[20]
+    units, ids = take(nunit, str), take(ndata, str)
+    typedata = [take(5, int) for _ in range(ndata)]
+    out = {"ndim": ndim, "N": N, "Nstar": nstar, "t": ddata[0], "tsnaplast": ddata[1], "mmean": ddata[2],
+           "Nsteps": ilp[1], "Noutsnap": ilp[0], "h_fac": rdata[0], "units": units, "data_id": ids}
+    for name, td in zip(ids, typedata):
+        width, n, code = td[0], td[2] - td[1] + 1, td[3]
+        if code == 2:
+            out["iorig" if name == "porig" else name] = np.array(take(n*width, int), dtype=np.int32)
+        elif code == 4:
+            a = np.array(take(n*width, float))
+            out[name] = a.reshape(n, width) if width > 1 else a
+        elif code == 7:
+            L = take(6, int)[3]
+            st = {k: [] for k in ("r", "v", "m", "h", "radius")}
+            for _ in range(n):
+                take(1, str); take(2, int)
+                sd = np.array(take(L, float))
+                st["r"].append(sd[1:1 + ndim]); st["v"].append(sd[1 + ndim:1 + 2*ndim])
+                st["m"].append(sd[1 + 2*ndim]); st["h"].append(sd[2 + 2*ndim]); st["radius"].append(sd[3 + 2*ndim])
+            out["stars"] = {k: np.array(x) for k, x in st.items()}
+    counts = idata[3:7]
+    out["ptype"] = np.concatenate([np.full(int(c), pt, dtype=np.int32) for c, pt in zip(counts, FILE_ORDER)]) \
+        if sum(counts) == N else np.zeros(N, dtype=np.int32)
+    return out

@@ -74,6 +74,7 @@ static bool g_quiet = false;
 static int g_mainloop = 0;         // --mainloop N : run N steps of the reference's own MainLoop
 static string g_starfile;         // --stars FILE : int64 Nstar, then Nstar doubles each of x[,y[,z]], m, h
 static string g_snapshot;          // --snapshot FILE : write the post-setup state with the reference's own "su" writer
+static string g_snapshot_sf;       // --snapshot-sf FILE : the same in the formatted "sf" text format
 static string g_snapshot_col;      // --snapshot-column FILE : the same in the "column" text format
 static int g_resident = 0;         // --resident K : (with --gpu) the first K of the --mainloop steps run in the device-resident loop
 static bool g_gpu = false;         // --gpu : swap sim->sphneib for GpuSphTree before doing so
@@ -425,6 +426,7 @@ static int run(Parameters* params, const string& icfile, double perturb, const s
   if (want("setup")) H.dump_particles("setup");
   if (!g_snapshot.empty()) sb->WriteSnapshotFile(g_snapshot, "su");
   if (!g_snapshot_col.empty()) sb->WriteSnapshotFile(g_snapshot_col, "column");
+  if (!g_snapshot_sf.empty()) sb->WriteSnapshotFile(g_snapshot_sf, "sf");
 
   // ---------------------------------------------------------------- operator-level captures
   if (want("density") || want("forces") || want("neib") || want("tree") || want("gravlists") || want("stargas")) {
@@ -572,6 +574,7 @@ int main(int argc, char** argv)
     else if (a == "--resident" && i + 1 < argc) g_resident = atoi(argv[++i]);
     else if (a == "--snapshot" && i + 1 < argc) g_snapshot = argv[++i];
     else if (a == "--snapshot-column" && i + 1 < argc) g_snapshot_col = argv[++i];
+    else if (a == "--snapshot-sf" && i + 1 < argc) g_snapshot_sf = argv[++i];
     else if (a == "--set" && i + 1 < argc) {
       string kv = argv[++i];
       size_t eq = kv.find('=');
@@ -591,7 +594,7 @@ int main(int argc, char** argv)
   char cwd[4096];
   if (!getcwd(cwd, sizeof cwd)) return 2;
   auto absolutise = [&](string& p) { if (!p.empty() && p[0] != '/') p = string(cwd) + "/" + p; };
-  absolutise(paramfile); absolutise(g_outdir); absolutise(icfile); absolutise(g_starfile); absolutise(g_snapshot); absolutise(g_snapshot_col);
+  absolutise(paramfile); absolutise(g_outdir); absolutise(icfile); absolutise(g_starfile); absolutise(g_snapshot); absolutise(g_snapshot_col); absolutise(g_snapshot_sf);
   mkdir(g_outdir.c_str(), 0755);
   if (chdir(g_outdir.c_str()) != 0) { fprintf(stderr, "cannot chdir to %s\n", g_outdir.c_str()); return 2; }
 

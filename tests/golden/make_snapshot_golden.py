@@ -43,6 +43,7 @@ def main():
                    "--snapshot", snap]
             if name == "sphere_grav_stars" or name == "adsod":
                 cmd += ["--snapshot-column", os.path.join(HERE, "snap_%s.column" % name)]
+                cmd += ["--snapshot-sf", os.path.join(HERE, "snap_%s.sf" % name)]
             if stars is not None:
                 sf = os.path.join(work, "stars.bin")
                 with open(sf, "wb") as fh:

@@ -120,3 +120,22 @@ def test_column_format_matches_the_reference(name, tmp_path):
     assert s["N"] == N and s["ndim"] == nd and s["Nstar"] == (0 if st is None else len(st["m"]))
     assert np.allclose(s["r"], d["r"].reshape(N, nd), rtol=1e-5, atol=1e-12)
     assert np.allclose(s["rho"], d["rho"], rtol=1e-5) and np.allclose(s["u"], d["u"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["adsod", "sphere_grav_stars"])
+def test_formatted_sf_matches_the_reference(name, tmp_path):
+    """the formatted text twin of su: byte-identical to the reference's WriteSerenFormSnapshotFile, and
+    read back to the 11 digits it carries"""
+    d, _ = _load(name)
+    ref = os.path.join(GOLDEN_DIR, "snap_%s.sf" % name)
+    s = snapshot.read_sf(ref)
+    nd, N = int(d["ndim"]), len(d["m"])
+    assert s["N"] == N and s["ndim"] == nd and np.array_equal(s["iorig"], d["iorig"])
+    assert np.allclose(s["r"].reshape(N, nd), d["r"].reshape(N, nd), rtol=1e-10, atol=1e-14)
+    assert np.allclose(s["u"], d["u"], rtol=1e-10) and np.allclose(s["rho"], d["rho"], rtol=1e-10)
+    out = str(tmp_path / "mine.sf")
+    snapshot.write_sf(out, d["r"].reshape(N, nd), d["v"].reshape(N, nd), d["m"], d["h"], d["rho"], d["u"],
+                      iorig=d["iorig"], ptype=d["ptype"], t=s["t"], Nsteps=s["Nsteps"], Noutsnap=s["Noutsnap"],
+                      h_fac=s["h_fac"], tsnaplast=s["tsnaplast"], mmean=snapshot.read_su(os.path.join(
+                          GOLDEN_DIR, "snap_%s.su" % name))["mmean"], stars=s.get("stars"))
+    assert open(out).read() == open(ref).read()
