@@ -91,7 +91,7 @@ EXPORTS = [
     "gsph_tree_cells", "gsph_get_stats", "gsph_kernel_table", "gsph_measure_fp_peak",
     "gsph_integrator_begin", "gsph_integrator_step", "gsph_integrator_state",
     "gsph_update_all_forces_begin", "gsph_update_all_forces_finish", "gsph_integrator_advance",
-    "gsph_integrator_finish", "gsph_update_star_gas_forces",
+    "gsph_integrator_finish", "gsph_update_star_gas_forces", "gsph_derive_density_fields",
 ]
 
 _lib = None
@@ -144,6 +144,7 @@ def lib():
         getattr(L, n).argtypes = [H]
     L.gsph_update_all_forces.argtypes = [H, C.c_void_p, C.c_int]
     L.gsph_set_active_slice.argtypes = [H, C.c_int64, C.c_int64]
+    L.gsph_derive_density_fields.argtypes = [H, C.c_int64, C.c_int64]
     L.gsph_device_field.argtypes = [H, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     L.gsph_timer_stop.argtypes = [H, C.POINTER(C.c_float)]
     L.gsph_get_hmax.argtypes = [H, C.POINTER(C.c_double)]

@@ -989,6 +989,17 @@ int gsph_refresh_hmax(gsph_handle* h)
   return gsph_tree_update_hmax(h);
 }
 
+/* multi-GPU: after the exchange of h, rho, invomega, zeta -- the derived density fields of the tree-order
+   particles outside [lo, hi) (the other ranks' slices; all of them active, see gsph_set_active_slice) */
+int gsph_derive_density_fields(gsph_handle* h, int64_t lo, int64_t hi)
+{
+  if (!h) return GSPH_EINVAL;
+  if (!h->have_tree || !h->sorted_valid) { h->err = "gsph_derive_density_fields before gsph_build_tree"; return GSPH_ESTATE; }
+  if (lo < 0 || hi < lo || hi > h->N) { h->err = "gsph_derive_density_fields: bad range"; return GSPH_EINVAL; }
+  cudaSetDevice(h->device);
+  return gsph_derive_density_fields_impl(h, (int) lo, (int) hi);
+}
+
 __global__ void active_slice_kernel(int N, int lo, int hi, int32_t* flags)
 {
   const int p = blockIdx.x*blockDim.x + threadIdx.x;

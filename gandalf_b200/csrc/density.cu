@@ -619,7 +619,41 @@ int dispatch_density(gsph_handle* h)
              : launch_density<NDIM, GSPH_KERNEL_QUINTIC, false>(h);
 }
 
+/* Multi-GPU: hrangesqd, hfactor, u, sound and pressure of the particles of the OTHER slices follow from
+ * their exchanged h and rho exactly as the density kernel's store section computes them, so only h, rho,
+ * invomega and zeta have to cross NVLink.                                                            */
+template <int NDIM>
+__global__ void derive_density_fields_kernel(int N, int lo, int hi, PartView P, DevParams dp)
+{
+  const int ti = blockIdx.x*blockDim.x + threadIdx.x;
+  if (ti >= N || (ti >= lo && ti < hi)) return;
+  if (((unsigned) P.i[I_FLAGS][ti]) & GSPH_FLAG_DEAD) return;
+  const double hf = P.f[F_H][ti], rho = P.f[F_RHO][ti];
+  const double ih = 1.0/hf;
+  P.f[F_HFAC][ti] = pow_ndim<NDIM>(ih)*ih;
+  P.f[F_HR2][ti] = __dmul_rn(__dmul_rn(dp.kernrangesqd, hf), hf);
+  double u = P.f[F_U][ti], cs, pr;
+  thermal(dp, rho, u, cs, pr);
+  P.f[F_U][ti] = u; P.f[F_SOUND][ti] = cs; P.f[F_PRESS][ti] = pr;
+}
+
 }  // namespace
+
+int gsph_derive_density_fields_impl(gsph_handle* h, int lo, int hi)
+{
+  const int N = (int) h->N;
+  PartView P;
+  for (int k = 0; k < NF_DOUBLE; k++) P.f[k] = h->P[k];
+  for (int k = 0; k < NF_INT; k++) P.i[k] = h->PI[k];
+  switch (h->dp.ndim) {
+  case 1: derive_density_fields_kernel<1><<<(N + 255)/256, 256, 0, h->stream>>>(N, lo, hi, P, h->dp); break;
+  case 2: derive_density_fields_kernel<2><<<(N + 255)/256, 256, 0, h->stream>>>(N, lo, hi, P, h->dp); break;
+  default: derive_density_fields_kernel<3><<<(N + 255)/256, 256, 0, h->stream>>>(N, lo, hi, P, h->dp); break;
+  }
+  h->stats.kernel_launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return GSPH_OK;
+}
 
 int gsph_run_density(gsph_handle* h)
 {

@@ -192,6 +192,7 @@ int gsph_tree_build(gsph_handle* h, int mode, double dt);             /* tree.cu
 int gsph_tree_build_sharded(gsph_handle* h, int phase, int rank, int world);
 int gsph_tree_update_hmax(gsph_handle* h);
 int gsph_tree_update_active(gsph_handle* h);
+int gsph_derive_density_fields_impl(gsph_handle* h, int lo, int hi);   /* density.cu */
 int gsph_run_density(gsph_handle* h);                                 /* density.cu */
 int gsph_run_hydro(gsph_handle* h, int with_gravity);                 /* hydro.cu   */
 int gsph_run_neiblist(gsph_handle* h, int32_t* counts_dev, const int64_t* offsets_dev, int32_t* idx_dev);

@@ -9,7 +9,7 @@ src/Mpi/MpiKDTreeDecomposition.cpp:56-277 domain decomposition):
    domains, with no separate decomposition step;
  * every rank holds the (replicated) tree and all particle positions, so the density pass needs
    no halo import at all; the force pass needs the post-density fields of the other slices:
-   ONE in-place ``all_gather_into_tensor`` per field on the device SoA arrays (9 doubles per
+   ONE in-place ``all_gather_into_tensor`` per field on the device SoA arrays (4 doubles per
    particle instead of the reference's 448-byte structs);
  * results are identical to the single-GPU run (same tree, same kernels, same summation order).
 """
@@ -109,7 +109,8 @@ class DomainDriver(object):
         import torch
         if self._fields is None:
             out = []
-            names = ["h", "rho", "hrangesqd", "hfactor", "invomega", "zeta", "sound", "pressure", "u"]
+            # hrangesqd, hfactor, u, sound, pressure follow from these on the receiving side
+            names = ["h", "rho", "invomega", "zeta"]
             if self.tree.cfg.tdavisc == 2:
                 names.append("alpha")        # the Cullen & Dehnen switch sets alpha in the density pass
             if self.tree.cfg.create_sinks:
@@ -134,6 +135,7 @@ class DomainDriver(object):
             dist.all_gather_into_tensor(t, t[self.rank * self.chunk:(self.rank + 1) * self.chunk], group=self.group)
         import torch
         torch.cuda.current_stream().synchronize()
+        self.tree.DeriveDensityFields(self.lo, self.hi)
         self.tree.RefreshHmax()
 
     # ---- host <-> device for a multi-process host: every rank owns the host-order chunk ---------------

@@ -306,6 +306,9 @@ class GpuSphTree(object):
         self._check(self._L.gsph_tree_shard_range(self._h, rank, world, C.byref(lo), C.byref(hi)))
         return lo.value, hi.value
 
+    def DeriveDensityFields(self, lo, hi):
+        self._check(self._L.gsph_derive_density_fields(self._h, int(lo), int(hi)))
+
     def BuildTreeShardBegin(self, rank, world):
         self._check(self._L.gsph_build_tree_shard_begin(self._h, rank, world))
 

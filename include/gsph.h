@@ -243,6 +243,9 @@ int gsph_timer_stop(gsph_handle* h, float* ms);
  * the host layer on the device arrays exposed below.
  *   gsph_set_active_slice : particles at tree positions [lo, hi) become the active targets, all
  *                           others stay sources only (replaces the rank-ownership test).
+ *   gsph_derive_density_fields : after the exchange of h, rho, invomega, zeta: hrangesqd, hfactor, u,
+ *                           sound, pressure of the particles OUTSIDE [lo, hi) are recomputed from them
+ *                           exactly as the density pass stores them (4 instead of 9 arrays cross NVLink).
  *   gsph_density_pass     : gsph_update_properties without the tree refresh (h of the other
  *                           slices is not known yet);  gsph_refresh_hmax does that refresh
  *                           (KDTree::UpdateAllHmaxValues) after the exchange.
@@ -255,9 +258,10 @@ enum { GSPH_DF_H = 0, GSPH_DF_RHO, GSPH_DF_HRANGESQD, GSPH_DF_HFACTOR, GSPH_DF_I
 /* Sharded tree build.  The balanced KD-tree's top log2(world) levels ARE the reference's domain
  * decomposition (median splits, MpiKDTreeDecomposition.cpp:56-277): rank r owns the r-th node of that
  * level = tree positions [lo, hi) of gsph_tree_shard_range.
- *   gsph_build_tree_shard_begin  : sorts, splits the top levels (they need every particle) and then
- *                                  re-orders only this rank's subtree -- 1/world of the per-level
- *                                  work; leaves this rank's slice of GSPH_DF_PERM filled;
+ *   gsph_build_tree_shard_begin  : finds this rank's shard by selecting the medians of the top levels
+ *                                  (radix select over (coordinate, id); no sort of all particles), then
+ *                                  sorts and builds only this rank's subtree; leaves this rank's slice
+ *                                  of GSPH_DF_PERM filled (1-D: sorts everything, splits its part);
  *   (host layer)                 : all-gathers the GSPH_DF_PERM slices over NCCL;
  *   gsph_build_tree_shard_finish : permutes the particle fields into tree order and stocks the cells
  *                                  (KDTree::StockTree) -- the tree is then identical on every rank
@@ -268,6 +272,7 @@ int gsph_build_tree_shard_finish(gsph_handle* h);
 int gsph_set_active_slice(gsph_handle* h, int64_t lo, int64_t hi);
 int gsph_density_pass(gsph_handle* h);
 int gsph_refresh_hmax(gsph_handle* h);
+int gsph_derive_density_fields(gsph_handle* h, int64_t lo, int64_t hi);
 int gsph_device_field(gsph_handle* h, int field, void** ptr, int64_t* capacity);
 
 /* ---- parity / debug access ---------------------------------------------------------------------
