@@ -173,3 +173,44 @@ def test_reference_perturbation_hash():
         x ^= x >> 16; x = (x*2246822519) & 0xFFFFFFFF; x ^= x >> 13
         want.append(1.0 + 0.1*(2.0*((x & 0xFFFFFF)/float(0x1000000)) - 1.0))
     assert np.allclose(f, want, rtol=0, atol=0)
+
+
+def test_integrator_config_follows_the_reference_parameters():
+    """the device main loop's configuration from .dat parameters: multipliers (Parameters.cpp:239-263),
+    energy integration from gas_eos (GradhSphSimulation.cpp:110-123), tree schedule; only lfkdk with one
+    global time step is accepted"""
+    import pytest
+    from gandalf_b200.params import integrator_config_from_params
+    c = integrator_config_from_params({"ndim": 3})
+    assert (c.accel_mult, c.courant_mult, c.energy_mult) == (0.3, 0.15, 0.4)
+    assert c.energy_integration == 1 and c.ntreebuildstep == 1 and c.ntreestockstep == 1
+    c = integrator_config_from_params({"gas_eos": "isothermal", "courant_mult": 0.2, "ntreebuildstep": 8,
+                                       "ntreestockstep": 2})
+    assert c.energy_integration == 0 and c.courant_mult == 0.2 and (c.ntreebuildstep, c.ntreestockstep) == (8, 2)
+    for eos in ("barotropic", "barotropic2", "constant_temp"):
+        assert integrator_config_from_params({"gas_eos": eos}).energy_integration == 0
+    with pytest.raises(ValueError):
+        integrator_config_from_params({"Nlevels": 5})
+    with pytest.raises(ValueError):
+        integrator_config_from_params({"sph_integration": "lfdkd"})
+
+
+def test_c_abi_structs_match_the_header_sizes(tmp_path):
+    """ctypes mirrors of the C structs: sizes as the C compiler lays out include/gsph.h"""
+    import ctypes as C
+    import os
+    import subprocess
+    from gandalf_b200 import _capi
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "gsph.h"\nint main(void) { printf("%zu %zu %zu %zu\\n", '
+                   'sizeof(gsph_config), sizeof(gsph_integrator_config), sizeof(gsph_stats), sizeof(gsph_particle_view)); '
+                   'return 0; }\n')
+    exe = str(tmp_path / "sz")
+    subprocess.check_call(["gcc", "-I", os.path.join(root, "include"), "-o", exe, str(src)])
+    sizes = [int(x) for x in subprocess.check_output([exe]).split()]
+    assert sizes == [C.sizeof(_capi.Config), C.sizeof(_capi.IntegratorConfig), C.sizeof(_capi.Stats),
+                     C.sizeof(_capi.ParticleView)]
+    cfg = _capi.Config()
+    assert _capi.lib().gsph_default_config(C.byref(cfg)) == 0
+    assert cfg.conservative_sph_star_gravity == 1 and cfg.nbody_softening == 1 and list(cfg.reserved) == [0]*5
