@@ -166,6 +166,21 @@ struct Harness
     dump_i32(stage + ".iorig", iorig, N); dump_i32(stage + ".ptype", ptype, N);
     dump_i32(stage + ".flags", flags, N); dump_i32(stage + ".level", level, N);
     dump_i32(stage + ".levelneib", levelneib, N);
+    // star particles (the N-body side of the main loop)
+    const int Ns = sim->nbody->Nstar;
+    if (Ns > 0) {
+      vector<double> sr(Ns*ndim), sv(Ns*ndim), sa(Ns*ndim), sm(Ns), sh(Ns), sg(Ns);
+      for (int i = 0; i < Ns; i++) {
+        for (int k = 0; k < ndim; k++) {
+          sr[i*ndim+k] = sim->nbody->stardata[i].r[k]; sv[i*ndim+k] = sim->nbody->stardata[i].v[k];
+          sa[i*ndim+k] = sim->nbody->stardata[i].a[k];
+        }
+        sm[i] = sim->nbody->stardata[i].m; sh[i] = sim->nbody->stardata[i].h; sg[i] = sim->nbody->stardata[i].gpot;
+      }
+      dump_f64(stage + ".star_r", sr, Ns, ndim); dump_f64(stage + ".star_v", sv, Ns, ndim);
+      dump_f64(stage + ".star_a", sa, Ns, ndim); dump_f64(stage + ".star_m", sm, Ns);
+      dump_f64(stage + ".star_h", sh, Ns); dump_f64(stage + ".star_gpot", sg, Ns);
+    }
   }
 
   //-----------------------------------------------------------------------------------------------

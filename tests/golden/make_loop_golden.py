@@ -33,6 +33,7 @@ CASES = {
     "box3d_mirror": (4, {}),
     "sphere_grav_fastmono": (4, {}),                         # barotropic: u follows from the EOS
     "sphere_grav_quad": (5, {"ntreebuildstep": 3, "ntreestockstep": 2}),   # rebuild / extrapolate / restock mix
+    "sphere_grav_stars": (4, {}),                            # three star particles moved by the N-body leapfrog
 }
 
 # setup: what a restart needs (the first step recomputes every density-pass field); loop: what is compared
@@ -53,13 +54,16 @@ def main():
         order = np.argsort(s["iorig"])
         ic = {k: s[k][order] for k in ("r", "v", "m", "h", "u")}
         p.setdefault("Nhydromax", 8*len(ic["m"]))
-        out, info = refio.run_mainloop(p, ic, steps, gpu=False, kind="std", dumps="setup")
+        out, info = refio.run_mainloop(p, ic, steps, gpu=False, kind="std", dumps="setup", stars=d.get("stars"))
         assert info["steps"] == steps
         fix = {"param." + k: np.array(str(v)) for k, v in p.items()}
         for st in ("setup", "loop"):
             o = np.argsort(out[st + ".iorig"])
             for f in FIELDS[st]:
                 fix["%s.%s" % (st, f)] = out["%s.%s" % (st, f)][o]
+            for k in out:
+                if k.startswith(st + ".star_"):
+                    fix[k] = out[k]
         fix["loop.t"] = np.float64(info["t"])
         fix["loop.timestep"] = np.float64(info["timestep"])
         fix["loop.steps"] = np.int64(steps)

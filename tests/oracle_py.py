@@ -384,6 +384,26 @@ def global_timestep(p, s, courant_mult, accel_mult, energy_mult, energy_integrat
     return float(ts.min())
 
 
+def star_star_forces(p, sr, sm, sh):
+    """NbodyLeapfrogKDK::CalculateDirectSmoothedGravForces (NbodyLeapfrogKDK.cpp): softened gravity between
+    the stars with the mean-h kernel -> (a, gpot)"""
+    L = lib()
+    ns, nd = sr.shape
+    a = np.zeros((ns, nd)); gpot = np.zeros(ns)
+    for i in range(ns):
+        for j in range(ns):
+            if i == j:
+                continue
+            dr = sr[j] - sr[i]
+            drmag = np.sqrt(float(np.dot(dr, dr))) + 1.0e-20
+            invdrmag = 1.0/drmag
+            invhmean = 2.0/(sh[i] + sh[j])
+            paux = sm[j]*invhmean*invhmean*L.orc_kernel(C.byref(p), 4, drmag*invhmean)*invdrmag
+            gpot[i] += sm[j]*invhmean*L.orc_kernel(C.byref(p), 5, drmag*invhmean)
+            a[i] += paux*dr
+    return a, gpot
+
+
 def mainloop(params, setup, steps):
     """`steps` x SphSimulation::MainLoop (SphSimulation.cpp:574-880; SphLeapfrogKDK.cpp:76-125,226-270;
     Integration.cpp:11-75) from the reference's post-setup particle state; full tree rebuild every step.
@@ -401,6 +421,19 @@ def mainloop(params, setup, steps):
     r0, v0, a0 = s["r"].copy(), s["v"].copy(), s["a"].copy()
     u0, dudt0 = s["u"].copy(), s["dudt"].copy()
     timestep = global_timestep(p, s, cm, am, em, energy)
+    # star particles: the reference's N-body leapfrog (NbodyLeapfrogKDK.cpp) around the same step
+    stars = "star_r" in s
+    if stars:
+        nm = float(params.get("nbody_mult", 0.1))
+        sr, sv, sa = (s[k].reshape(-1, nd).copy() for k in ("star_r", "star_v", "star_a"))
+        sm, sh = s["star_m"], s["star_h"]
+        sr0, sv0, sa0 = sr.copy(), sv.copy(), sa.copy()
+        sgpot = np.zeros(len(sm))
+
+        def star_timestep():
+            amag = np.sqrt((sa*sa).sum(1))
+            return float((nm*np.sqrt(sh/(amag + 1.0e-50))).min())
+        timestep = min(timestep, star_timestep())
     t = tlast = 0.0
     size = [p.boxmax[k] - p.boxmin[k] for k in range(nd)]
     for _ in range(steps):
@@ -408,6 +441,10 @@ def mainloop(params, setup, steps):
         dt = t - tlast
         s["r"] = r0 + v0*dt + 0.5*a0*dt*dt
         s["v"] = v0 + a0*dt
+        if stars:
+            sr = sr0 + sv0*dt + 0.5*sa0*dt*dt
+            sv = sv0 + sa0*dt
+            rows = np.concatenate([sr, sm[:, None], sh[:, None]], axis=1)
         if tdav:
             s["alpha"] = s["alpha"] + s["dalphadt"]*timestep
         if energy:
@@ -431,7 +468,7 @@ def mainloop(params, setup, steps):
                     arr[hi, k] = 2.0*p.boxmax[k] - arr[hi, k]
                 for arr in (s["v"], v0, s["a"], a0):
                     arr[hi, k] = -arr[hi, k]
-        dens = density(p, s["r"], s["m"], s["h"], s["u"])
+        dens = density(p, s["r"], s["m"], s["h"], s["u"], stars=rows if stars else None)
         for k in ("h", "rho", "invomega", "zeta", "hfactor", "hrangesqd", "u", "sound", "pressure"):
             s[k] = dens[k]
         if tdav and params.get("time_dependent_avisc") == "cd2010":
@@ -439,6 +476,13 @@ def mainloop(params, setup, steps):
         if p.self_gravity:
             tr = Tree(p, s["r"], s["v"], s["m"], s["h"], s["atree"], s["gpot"])
             f = tr.hydro_grav_forces(s)
+            if stars:                                   # ComputeStarGravForces, then the stars' own forces
+                ga, gat, gg = star_grav_forces(p, s["r"], s["h"], sr, sm, sh)
+                f["a"] = f["a"] + ga; f["atree"] = f["atree"] + gat; f["gpot"] = f["gpot"] + gg
+                sa, _, sgpot, _ = tr.star_gas_forces(sr, sv, sh)
+                ssa, ssg = star_star_forces(p, sr, sm, sh)
+                sa = sa + ssa; sgpot = sgpot + ssg
+                sv = sv + 0.5*(sa - sa0)*(t - tlast)    # NbodyLeapfrogKDK::CorrectionTerms
             s["atree"], s["gpot"] = f["atree"], f["gpot"]
         else:
             f = hydro_forces(p, s)
@@ -448,6 +492,9 @@ def mainloop(params, setup, steps):
             # Sph::ZeroAccelerations (Sph.cpp:126-140) does not clear it: the reference accumulates it
             s["dalphadt"] = s["dalphadt"] + f["dalphadt"]
         nxt = global_timestep(p, s, cm, am, em, energy)
+        if stars:
+            nxt = min(nxt, star_timestep())
+            sr0, sv0, sa0 = sr.copy(), sv.copy(), sa.copy()
         s["v"] = s["v"] + 0.5*timestep*(s["a"] - a0)          # EndTimestep, part.dt = the step just taken
         r0, v0, a0 = s["r"].copy(), s["v"].copy(), s["a"].copy()
         if energy:
@@ -457,4 +504,6 @@ def mainloop(params, setup, steps):
             u0, dudt0 = u.copy(), s["dudt"].copy()
         tlast = t
         timestep = nxt
+    if stars:
+        s["star_r"], s["star_v"], s["star_a"], s["star_gpot"] = sr, sv, sa, sgpot
     return s, t, timestep

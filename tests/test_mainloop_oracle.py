@@ -57,3 +57,6 @@ def test_mainloop_restatement_matches_reference(name):
     assert abs(t - float(loop["t"])) <= 1e-12*abs(t)
     assert abs(ts - float(loop["timestep"])) <= 1e-9*abs(ts)
     check_state(s, loop, 1e-9)
+    if "star_r" in loop:                     # star particles moved by the N-body leapfrog
+        for k in ("star_r", "star_v", "star_a"):
+            assert vec_err(np.asarray(s[k]), loop[k]).max() < 1e-9, k
