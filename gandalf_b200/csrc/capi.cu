@@ -1400,6 +1400,106 @@ static int integ_global_timestep(gsph_handle* h, double* out)
   return GSPH_OK;
 }
 
+/* ---- star particles of the device-resident loop: the reference's N-body leapfrog, host side ---------- */
+static int integ_push_stars(gsph_handle* h)
+{
+  IntegState& I = h->integ;
+  const int nd = h->cfg.ndim;
+  std::vector<double> rows((size_t) I.nstar*(nd + 2));
+  for (int s = 0; s < I.nstar; s++) {
+    for (int k = 0; k < nd; k++) rows[(size_t) s*(nd + 2) + k] = I.sr[(size_t) s*nd + k];
+    rows[(size_t) s*(nd + 2) + nd] = I.sm[s]; rows[(size_t) s*(nd + 2) + nd + 1] = I.sh[s];
+  }
+  return gsph_set_stars(h, rows.data(), I.nstar);
+}
+
+/* MainLoop's N-body block (SphSimulation.cpp:771-812, Npec = 1): zero, gravity of the gas
+   (UpdateAllStarGasForces), softened star-star gravity (NbodyLeapfrogKDK::CalculateDirectSmoothedGravForces) */
+static int integ_star_forces(gsph_handle* h)
+{
+  IntegState& I = h->integ;
+  const int nd = h->cfg.ndim, ns = I.nstar;
+  std::fill(I.sa.begin(), I.sa.end(), 0.0); std::fill(I.sgpot.begin(), I.sgpot.end(), 0.0);
+  if (h->cfg.self_gravity) {
+    std::vector<double> rows((size_t) ns*(2*nd + 1));
+    for (int s = 0; s < ns; s++) {
+      for (int k = 0; k < nd; k++) { rows[(size_t) s*(2*nd + 1) + k] = I.sr[(size_t) s*nd + k]; rows[(size_t) s*(2*nd + 1) + nd + k] = I.sv[(size_t) s*nd + k]; }
+      rows[(size_t) s*(2*nd + 1) + 2*nd] = I.sh[s];
+    }
+    const int rc = gsph_update_star_gas_forces(h, rows.data(), ns, I.sa.data(), NULL, I.sgpot.data(), NULL);
+    if (rc) return rc;
+  }
+  for (int i = 0; i < ns; i++)
+    for (int j = 0; j < ns; j++) {
+      if (i == j) continue;
+      double dr[3] = {0, 0, 0}, drsqd = 0.0;
+      for (int k = 0; k < nd; k++) { dr[k] = I.sr[(size_t) j*nd + k] - I.sr[(size_t) i*nd + k]; }
+      for (int k = 0; k < nd; k++) drsqd = k == 0 ? dr[0]*dr[0] : drsqd + dr[k]*dr[k];
+      const double drmag = sqrt(drsqd) + 1.0e-20, invdrmag = 1.0/drmag;
+      const double invhmean = 2.0/(I.sh[i] + I.sh[j]);
+      const double paux = I.sm[j]*invhmean*invhmean*
+                          gsph_kernel_grav_host(nd, h->cfg.kernel, h->cfg.tabulated_kernel, 4, drmag*invhmean)*invdrmag;
+      I.sgpot[i] += I.sm[j]*invhmean*gsph_kernel_grav_host(nd, h->cfg.kernel, h->cfg.tabulated_kernel, 5, drmag*invhmean);
+      for (int k = 0; k < nd; k++) I.sa[(size_t) i*nd + k] += paux*dr[k];
+    }
+  return GSPH_OK;
+}
+
+/* NbodyLeapfrogKDK::Timestep over the stars */
+static double integ_star_timestep(const gsph_handle* h)
+{
+  const IntegState& I = h->integ;
+  const int nd = h->cfg.ndim;
+  double ts = 9.9e50;
+  for (int s = 0; s < I.nstar; s++) {
+    double a2 = 0.0;
+    for (int k = 0; k < nd; k++) { const double a = I.sa[(size_t) s*nd + k]; a2 = k == 0 ? a*a : a2 + a*a; }
+    ts = std::min(ts, I.nbody_mult*sqrt(I.sh[s]/(sqrt(a2) + 1.0e-50)));
+  }
+  return ts;
+}
+
+/* rows = Nstar x {r[ndim], v[ndim], a[ndim], m, h}: the stars the next gsph_integrator_begin starts with
+   (a is only read by compute_forces = 0).  Nstar = 0 removes them.                                    */
+int gsph_integrator_set_stars(gsph_handle* h, const double* rows, int Nstar, double nbody_mult)
+{
+  if (!h) return GSPH_EINVAL;
+  if (Nstar < 0 || (Nstar > 0 && !rows) || (Nstar > 0 && !(nbody_mult > 0))) { h->err = "gsph_integrator_set_stars: bad arguments"; return GSPH_EINVAL; }
+  IntegState& I = h->integ;
+  const int nd = h->cfg.ndim, row = 3*nd + 2;
+  I.on = false;
+  I.nstar = Nstar; I.nbody_mult = nbody_mult;
+  I.sr.assign((size_t) Nstar*nd, 0.0); I.sv = I.sr; I.sa = I.sr;
+  I.sm.assign(Nstar, 0.0); I.sh = I.sm; I.sgpot = I.sm;
+  for (int s = 0; s < Nstar; s++) {
+    for (int k = 0; k < nd; k++) {
+      I.sr[(size_t) s*nd + k] = rows[(size_t) s*row + k]; I.sv[(size_t) s*nd + k] = rows[(size_t) s*row + nd + k];
+      I.sa[(size_t) s*nd + k] = rows[(size_t) s*row + 2*nd + k];
+    }
+    I.sm[s] = rows[(size_t) s*row + 3*nd]; I.sh[s] = rows[(size_t) s*row + 3*nd + 1];
+  }
+  I.sr0 = I.sr; I.sv0 = I.sv; I.sa0 = I.sa;
+  /* the gas passes see them from now on (a host layer may run the first passes itself, compute_forces = 2) */
+  return Nstar > 0 ? integ_push_stars(h) : gsph_set_stars(h, NULL, 0);
+}
+
+/* rows = Nstar x {r[ndim], v[ndim], a[ndim], m, h, gpot} as they stand after the last step */
+int gsph_integrator_get_stars(gsph_handle* h, double* rows, int Nstar)
+{
+  if (!h) return GSPH_EINVAL;
+  const IntegState& I = h->integ;
+  if (Nstar != I.nstar || (Nstar > 0 && !rows)) { h->err = "gsph_integrator_get_stars: bad arguments"; return GSPH_EINVAL; }
+  const int nd = h->cfg.ndim, row = 3*nd + 3;
+  for (int s = 0; s < Nstar; s++) {
+    for (int k = 0; k < nd; k++) {
+      rows[(size_t) s*row + k] = I.sr[(size_t) s*nd + k]; rows[(size_t) s*row + nd + k] = I.sv[(size_t) s*nd + k];
+      rows[(size_t) s*row + 2*nd + k] = I.sa[(size_t) s*nd + k];
+    }
+    rows[(size_t) s*row + 3*nd] = I.sm[s]; rows[(size_t) s*row + 3*nd + 1] = I.sh[s]; rows[(size_t) s*row + 3*nd + 2] = I.sgpot[s];
+  }
+  return GSPH_OK;
+}
+
 int gsph_integrator_begin(gsph_handle* h, const gsph_integrator_config* cfg, int compute_forces, double t0)
 {
   if (!h) return GSPH_EINVAL;
@@ -1407,7 +1507,10 @@ int gsph_integrator_begin(gsph_handle* h, const gsph_integrator_config* cfg, int
   if (!h->uploaded) { h->err = "gsph_integrator_begin before gsph_upload"; return GSPH_ESTATE; }
   if (!(cfg->accel_mult > 0) || !(cfg->courant_mult > 0) || !(cfg->energy_mult > 0)) { h->err = "gsph_integrator_begin: the time-step multipliers must be positive"; return GSPH_EINVAL; }
   if (cfg->ntreebuildstep < 1 || cfg->ntreestockstep < 1) { h->err = "gsph_integrator_begin: ntreebuildstep and ntreestockstep must be >= 1"; return GSPH_EINVAL; }
-  if (h->Nstar > 0) { h->err = "gsph_integrator_begin: star particles are not integrated on the device"; return GSPH_EINVAL; }
+  if (h->Nstar > 0 && h->integ.nstar == 0) { h->err = "gsph_integrator_begin: star particles of gsph_set_stars are not integrated (hand them to gsph_integrator_set_stars)"; return GSPH_EINVAL; }
+  if (h->integ.nstar > 0 && h->cfg.nbody_softening != 1) { h->err = "gsph_integrator_begin: star particles need nbody_softening = 1"; return GSPH_EINVAL; }
+  if (h->integ.nstar > 0) for (int k = 0; k < h->cfg.ndim; k++)
+    if (h->dp.periodic[k] || h->dp.mirror[k][0] || h->dp.mirror[k][1]) { h->err = "gsph_integrator_begin: star particles need open boundaries"; return GSPH_EINVAL; }
   if (compute_forces < 0 || compute_forces > 2) { h->err = "gsph_integrator_begin: compute_forces must be 0, 1 or 2"; return GSPH_EINVAL; }
   if (compute_forces == 1 && h->slice_mode) { h->err = "gsph_integrator_begin: compute_forces = 1 not with an active slice (the multi-GPU host layer runs the passes itself and passes 2)"; return GSPH_EINVAL; }
   if (compute_forces == 2 && !h->sorted_valid) { h->err = "gsph_integrator_begin(compute_forces = 2) before the passes"; return GSPH_ESTATE; }
@@ -1422,13 +1525,19 @@ int gsph_integrator_begin(gsph_handle* h, const gsph_integrator_config* cfg, int
   if (!I.red) CUDA_TRY(h, cudaMalloc(&I.red, 2*sizeof(unsigned long long)));
   I.cfg = *cfg; I.t = I.tlast = t0; I.Nsteps = 0; I.rebuild = true; I.on = false; I.mid_step = false;
   CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_all, 0));          /* the upload has landed */
+  if (I.nstar > 0) { const int rs = integ_push_stars(h); if (rs) return rs; }
   if (compute_forces == 1) {
     int rc = gsph_build_tree(h, 0, 0.0); if (rc) return rc;
     rc = integ_forces(h); if (rc) return rc;
   }
   if (compute_forces) { const int rc = integ_scatter_results(h); if (rc) return rc; }
+  if (I.nstar > 0) {
+    if (compute_forces) { const int rs = integ_star_forces(h); if (rs) return rs; }
+    I.sr0 = I.sr; I.sv0 = I.sv; I.sa0 = I.sa;
+  }
   INTEG_LAUNCH(integ_init_kernel, (int) h->N, devptrs(h->H, h->HI), integ_ptrs(h));
   int rc = integ_global_timestep(h, &I.timestep); if (rc) return rc;
+  if (I.nstar > 0) I.timestep = std::min(I.timestep, integ_star_timestep(h));
   /* EndTimestep with part.dt = 0 (SphSimulation.cpp:561): u0 = u, dudt0 = dudt */
   INTEG_LAUNCH(integ_end_kernel, (int) h->N, devptrs(h->H, h->HI), integ_ptrs(h), 0.0, I.cfg.energy_integration);
   I.on = true;
@@ -1451,6 +1560,13 @@ int gsph_integrator_advance(gsph_handle* h, int* tree_mode, double* timestep)
   const double dt = I.t - I.tlast;
   INTEG_LAUNCH(integ_advance_kernel, (int) h->N, devptrs(h->H, h->HI), integ_ptrs(h), h->dp, dt, ts,
                h->dp.tdavisc != GSPH_TDAVISC_NONE ? 1 : 0, I.cfg.energy_integration);
+  if (I.nstar > 0) {                                   /* NbodyLeapfrogKDK::AdvanceParticles */
+    for (size_t q = 0; q < I.sr.size(); q++) {
+      I.sr[q] = I.sr0[q] + I.sv0[q]*dt + 0.5*I.sa0[q]*dt*dt;
+      I.sv[q] = I.sv0[q] + I.sa0[q]*dt;
+    }
+    const int rs = integ_push_stars(h); if (rs) return rs;
+  }
   CUDA_TRY(h, cudaEventRecord(h->ev_geom, h->stream));
   CUDA_TRY(h, cudaEventRecord(h->ev_all, h->stream));
   for (int k = 0; k < 3; k++) CUDA_TRY(h, cudaEventRecord(h->ev_axis[k], h->stream));
@@ -1482,8 +1598,17 @@ int gsph_integrator_finish(gsph_handle* h)
     for (int k = 0; k < h->cfg.ndim; k++)
       if (h->dp.periodic[k] && h->dp.boxhalf[k] < 2*hmax) { h->err = "Error: Smoothing length too large, self-interaction will occur"; return GSPH_ESTATE; }
   }
+  if (I.nstar > 0) {
+    rc = integ_star_forces(h); if (rc) return rc;
+    const double dts = I.t - I.tlast;                  /* NbodyLeapfrogKDK::CorrectionTerms */
+    for (size_t q = 0; q < I.sv.size(); q++) I.sv[q] += 0.5*(I.sa[q] - I.sa0[q])*dts;
+  }
   double next = 0.0;
   rc = integ_global_timestep(h, &next); if (rc) return rc;
+  if (I.nstar > 0) {
+    next = std::min(next, integ_star_timestep(h));
+    I.sr0 = I.sr; I.sv0 = I.sv; I.sa0 = I.sa;          /* NbodyLeapfrogKDK::EndTimestep */
+  }
   I.rebuild = false;
   INTEG_LAUNCH(integ_end_kernel, (int) h->N, devptrs(h->H, h->HI), integ_ptrs(h), I.timestep, I.cfg.energy_integration);
   I.tlast = I.t;

@@ -119,6 +119,10 @@ struct IntegState {
   int64_t Nsteps = 0;
   bool rebuild = true;
   bool mid_step = false;     /* between gsph_integrator_advance and gsph_integrator_finish */
+  /* star particles: the N-body leapfrog (NbodyLeapfrogKDK.cpp) runs on the host around the device passes */
+  int nstar = 0;
+  double nbody_mult = 0.1;
+  std::vector<double> sr, sv, sa, sr0, sv0, sa0, sm, sh, sgpot;
 };
 
 struct gsph_handle {
@@ -186,7 +190,8 @@ struct gsph_handle {
   (h)->err = std::string(#call) + ": " + cudaGetErrorString(e__); return GSPH_ECUDA; } } while (0)
 
 /* ---- module entry points (host side) -----------------------------------------------------------*/
-void gsph_make_tables(int ndim, int kernel, double* out6x1000);       /* tables.cu  */
+void gsph_make_tables(int ndim, int kernel, double* out6x1000);
+double gsph_kernel_grav_host(int ndim, int kernel, int tabulated, int which, double s);   /* tables.cpp */       /* tables.cu  */
 double gsph_kernnorm(int ndim, int kernel);
 int gsph_tree_build(gsph_handle* h, int mode, double dt);             /* tree.cu    */
 int gsph_tree_build_sharded(gsph_handle* h, int phase, int rank, int world);

@@ -138,3 +138,17 @@ void gsph_make_tables(int ndim, int kernel, double* out)
     out[5*RES + i] = f(5, step*i, kn, ndim);           /* wpot      */
   }
 }
+
+/* host-side wgrav (which = 4) / wpot (which = 5) with the reference's look-up semantics
+   (TabulatedKernel GravTableLookup / GravPotTableLookup, SmoothingKernel.h:645-662) or the analytic form:
+   used by the N-body side of the device-resident main loop, where the stars are a handful */
+double gsph_kernel_grav_host(int ndim, int kernel, int tabulated, int which, double s)
+{
+  const double kr = kernel == GSPH_KERNEL_M4 ? 2.0 : 3.0;
+  const double kn = gsph_kernnorm(ndim, kernel);
+  double (*f)(int, double, double, int) = kernel == GSPH_KERNEL_M4 ? m4 : (kernel == GSPH_KERNEL_GAUSSIAN ? gaussian : quintic);
+  if (!tabulated) return f(which, s, kn, ndim);
+  if (s >= kr) return which == 4 ? 1.0/(s*s) : 1.0/s;
+  const int idx = (int)(s*((double) RES/kr));
+  return f(which, (kr/RES)*idx, kn, ndim);
+}

@@ -19,6 +19,7 @@ DEFAULTS = {
     "gravity_mac": "geometric", "multipole": "quadrupole", "thetamaxsqd": 0.1, "macerror": 0.0001,
     "Nleafmax": 6, "ntreebuildstep": 1, "ntreestockstep": 1, "create_sinks": 0, "conservative_sph_star_gravity": 1, "nbody_softening": 1, "sink_particles": 0,
     "Nlevels": 1, "sph_integration": "lfkdk", "accel_mult": 0.3, "courant_mult": 0.15, "energy_mult": 0.4,
+    "nbody": "lfkdk", "nbody_mult": 0.1,
 }
 for _k in range(3):
     DEFAULTS["boundary_lhs[%d]" % _k] = "open"

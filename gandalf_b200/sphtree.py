@@ -211,6 +211,32 @@ class GpuSphTree(object):
         ic = integrator_config_from_params(self.params)
         self._check(self._L.gsph_integrator_begin(self._h, C.byref(ic), int(compute_forces), float(t)))
 
+    def IntegratorSetStars(self, r=None, v=None, m=None, h=None, a=None):
+        """star particles of the device-resident loop (nbody = lfkdk: the reference's N-body leapfrog runs on
+        the host around the device passes); call before IntegratorBegin; r=None removes them"""
+        if r is None or len(m) == 0:
+            self._check(self._L.gsph_integrator_set_stars(self._h, None, 0, 0.1))
+            self._nstar = 0
+            return
+        if self.params["nbody"] != "lfkdk":
+            raise ValueError("nbody = %s is not on the accelerated path (lfkdk only)" % self.params["nbody"])
+        nd, ns = self.cfg.ndim, len(m)
+        z = np.zeros((ns, nd))
+        rows = np.ascontiguousarray(np.concatenate([
+            np.asarray(r, dtype=np.float64).reshape(ns, nd), z if v is None else np.asarray(v, dtype=np.float64).reshape(ns, nd),
+            z if a is None else np.asarray(a, dtype=np.float64).reshape(ns, nd),
+            np.asarray(m, dtype=np.float64)[:, None], np.asarray(h, dtype=np.float64)[:, None]], axis=1))
+        self._check(self._L.gsph_integrator_set_stars(self._h, rows.ctypes.data, ns, float(self.params["nbody_mult"])))
+        self._nstar = ns
+
+    def IntegratorGetStars(self):
+        """-> dict r, v, a, m, h, gpot of the stars after the last step"""
+        nd, ns = self.cfg.ndim, getattr(self, "_nstar", 0)
+        rows = np.zeros((ns, 3*nd + 3))
+        self._check(self._L.gsph_integrator_get_stars(self._h, rows.ctypes.data, ns))
+        return {"r": rows[:, :nd].copy(), "v": rows[:, nd:2*nd].copy(), "a": rows[:, 2*nd:3*nd].copy(),
+                "m": rows[:, 3*nd].copy(), "h": rows[:, 3*nd + 1].copy(), "gpot": rows[:, 3*nd + 2].copy()}
+
     def IntegratorAdvance(self):
         """first half of a MainLoop -> (tree mode 0 rebuild / 1 restock / 2 extrapolate, time step)"""
         mode, ts = C.c_int(), C.c_double()

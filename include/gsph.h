@@ -362,6 +362,16 @@ int gsph_integrator_step(gsph_handle* h, int nsteps);
  *             global time step, end-of-step terms.
  * gsph_integrator_begin(compute_forces = 2) is the matching start: the caller has just run the passes.
  * gsph_integrator_step(h, 1) == advance + gsph_build_tree + the passes + finish.                     */
+/* Star particles in the device-resident loop.  Their N-body side is the reference's leapfrog
+ * (NbodyLeapfrogKDK.cpp: AdvanceParticles, CalculateDirectSmoothedGravForces, CorrectionTerms, Timestep,
+ * EndTimestep; nbody = lfkdk, nbody_softening = 1, Npec = 1, open boundaries), run on the host -- the stars
+ * are a handful -- around gsph_update_star_gas_forces; the gas feels them through the star terms of the
+ * density and force passes, and their time step enters the global minimum.
+ *   set_stars : rows = Nstar x {r[ndim], v[ndim], a[ndim], m, h}, before gsph_integrator_begin (a is read
+ *               only with compute_forces = 0); nbody_mult as Parameters.cpp:241 (0.1)
+ *   get_stars : rows = Nstar x {r[ndim], v[ndim], a[ndim], m, h, gpot} after the last step          */
+int gsph_integrator_set_stars(gsph_handle* h, const double* rows, int Nstar, double nbody_mult);
+int gsph_integrator_get_stars(gsph_handle* h, double* rows, int Nstar);
 int gsph_integrator_advance(gsph_handle* h, int* tree_mode, double* timestep);
 int gsph_integrator_finish(gsph_handle* h);
 /* simulation time, the time step the NEXT MainLoop will take, steps done since begin             */

@@ -9,7 +9,7 @@ import pytest
 
 import oracle_py as orc
 from conftest import load_golden, LOOP_CASES, rel_err
-from test_mainloop_oracle import split, check_state
+from test_mainloop_oracle import split, check_state, vec_err
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-8          # asserted after 4-6 steps (rounding differences of the force sums feed back through the
@@ -37,6 +37,8 @@ def test_device_mainloop_matches_reference(name):
     params, d = load_golden(name)
     setup, loop = split(d)
     ps, tree = _upload_setup(g, params, setup)
+    if "star_r" in setup:                    # star particles: the N-body leapfrog around the device passes
+        tree.IntegratorSetStars(setup["star_r"], setup["star_v"], setup["star_m"], setup["star_h"], a=setup["star_a"])
     tree.IntegratorBegin(compute_forces=False)
     t0, ts0, n0 = tree.IntegratorState()
     assert t0 == 0.0 and n0 == 0 and ts0 > 0
@@ -48,6 +50,11 @@ def test_device_mainloop_matches_reference(name):
     assert abs(ts - float(loop["timestep"])) <= 1e-9*abs(ts)
     tree.Download(ps)
     check_state({k: ps[k] for k in ("r", "v", "a", "h", "rho", "u", "alpha", "dudt")}, loop, TOL)
+    if "star_r" in setup:
+        st = tree.IntegratorGetStars()
+        for k in ("r", "v", "a"):
+            assert vec_err(st[k], loop["star_" + k]).max() < TOL, k
+        assert rel_err(st["gpot"], loop["star_gpot"]).max() < TOL
     tree.close()
 
 
