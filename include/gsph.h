@@ -330,7 +330,8 @@ int gsph_get_stats(gsph_handle* h, gsph_stats* st);
  *   Simulation::ComputeGlobalTimestep            src/Common/Simulation.cpp:1669-1745
  *   TimeIntegration::CheckBoundaries             src/Common/Integration.cpp:11-75
  * around the operators above (BuildTree, UpdateAllSphProperties, ZeroAccelerations, force pass).
- * Not covered (GSPH_EINVAL): block time steps, star / sink particles, external potentials, dust.   */
+ * Star particles: gsph_integrator_set_stars below.  Not covered (GSPH_EINVAL): block time steps, sinks,
+ * external potentials, dust.                                                                       */
 typedef struct gsph_integrator_config {
   double  accel_mult, courant_mult, energy_mult;   /* Parameters.cpp:239,240,263 (0.3, 0.15, 0.4)      */
   int32_t energy_integration;   /* 1: u is integrated explicitly (gas_eos = energy_eqn,
