@@ -214,3 +214,81 @@ def test_c_abi_structs_match_the_header_sizes(tmp_path):
     cfg = _capi.Config()
     assert _capi.lib().gsph_default_config(C.byref(cfg)) == 0
     assert cfg.conservative_sph_star_gravity == 1 and cfg.nbody_softening == 1 and list(cfg.reserved) == [0]*5
+
+
+def test_domain_driver_main_loop_sequence():
+    """host logic of the multi-rank device main loop (gandalf_b200/domain.py) with a recording stub in
+    place of the device tree: per step advance -> (sharded) build -> slice -> density + exchange ->
+    zero -> forces -> exchange of the force results -> finish; restock / extrapolate steps do not shard"""
+    from gandalf_b200 import domain
+
+    class Cfg:
+        ndim, self_gravity, tdavisc, create_sinks = 3, 1, 0, 0
+
+    class Stats:
+        Nhydro = 1001
+
+    class Stub:
+        cfg = Cfg()
+
+        def __init__(self, modes):
+            self.calls, self.modes = [], list(modes)
+
+        def __getattr__(self, name):
+            def f(*a, **k):
+                self.calls.append(name)
+            return f
+
+        def Stats(self):
+            return Stats()
+
+        def IntegratorAdvance(self):
+            self.calls.append("IntegratorAdvance")
+            return self.modes.pop(0), 0.01
+
+        def SetActiveSlice(self, lo, hi):
+            self.calls.append(("SetActiveSlice", lo, hi))
+
+        def BuildTreeMode(self, mode, ts):
+            self.calls.append(("BuildTreeMode", mode))
+
+        def DeriveDensityFields(self, lo, hi):
+            self.calls.append(("DeriveDensityFields", lo, hi))
+
+    class Driver(domain.DomainDriver):
+        def _sharded_rebuild(self, parts):
+            self.tree.calls.append("sharded_rebuild")
+
+        def _wrap_fields(self):
+            self.tree.calls.append("exchange_density")
+            return []
+
+        def _gather_inplace(self, names, staging, n_valid):
+            self.tree.calls.append(("gather", tuple(names), staging))
+
+    import sys
+    import types
+    fake = types.ModuleType("torch")                      # UpdateAllSphProperties synchronises torch's stream
+    fake.cuda = types.SimpleNamespace(current_stream=lambda: types.SimpleNamespace(synchronize=lambda: None))
+    fake.distributed = types.ModuleType("torch.distributed")
+    saved = {k: sys.modules.get(k) for k in ("torch", "torch.distributed")}
+    sys.modules["torch"], sys.modules["torch.distributed"] = fake, fake.distributed
+    try:
+        stub = Stub([0, 1, 2])
+        drv = Driver(stub, rank=1, world_size=2)
+        drv.MainLoop(3)
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    lo, hi, _ = domain.slice_bounds(1001, 2, 1)
+    step = ["DensityPass", "Synchronize", "exchange_density", ("DeriveDensityFields", lo, hi), "RefreshHmax",
+            "ZeroAccelerations", "UpdateAllSphForces", "Synchronize",
+            ("gather", ("ax", "ay", "az", "atx", "aty", "atz", "gpot", "dudt", "div_v", "dalphadt", "alpha", "levelneib"),
+             False), "IntegratorFinish"]
+    expect = []
+    for build in ("sharded_rebuild", ("BuildTreeMode", 1), ("BuildTreeMode", 2)):
+        expect += ["IntegratorAdvance", build, ("SetActiveSlice", lo, hi)] + step
+    assert stub.calls == expect, stub.calls
