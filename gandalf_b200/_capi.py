@@ -76,7 +76,7 @@ class IntegratorConfig(C.Structure):
     """gsph_integrator_config"""
     _fields_ = [("accel_mult", C.c_double), ("courant_mult", C.c_double), ("energy_mult", C.c_double),
                 ("energy_integration", C.c_int32), ("ntreebuildstep", C.c_int32), ("ntreestockstep", C.c_int32),
-                ("reserved", C.c_int32 * 5)]
+                ("sink_particles", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
 EXPORTS = [

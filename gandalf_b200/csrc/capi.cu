@@ -113,6 +113,11 @@ int ensure_capacity(gsph_handle* h, int64_t N)
 {
   if (N <= h->Ncap) return GSPH_OK;
   const int64_t cap = N + N/16 + 1024;
+  /* nothing of the old state survives a regrow: invalidate it BEFORE the first free, so that a failed
+     cudaMalloc half-way leaves a handle that refuses work instead of one that launches on freed arrays */
+  h->Ncap = 0; h->integ.cap = 0;
+  h->uploaded = h->have_tree = h->sorted_valid = h->density_done = false;
+  h->integ.on = false; h->results_newer = false;
   for (int f = 0; f < NF_DOUBLE; f++) {
     if (h->H[f]) cudaFree(h->H[f]); if (h->P[f]) cudaFree(h->P[f]);
     h->H[f] = h->P[f] = nullptr;
@@ -642,7 +647,7 @@ static int upload_impl(gsph_handle* h, const gsph_particle_view* view, int64_t N
   CUDA_TRY(h, cudaGetLastError());
   if (N != h->N) h->have_tree = false;
   h->N = N; h->uploaded = true; h->sorted_valid = false; h->density_done = false; h->slice_mode = false;
-  h->integ.on = false;
+  h->integ.on = false; h->results_newer = false; h->p_stale = false;
   h->stats.Nhydro = N;
   tm.stop();
   return GSPH_OK;
@@ -691,7 +696,9 @@ static int download_impl(gsph_handle* h, const gsph_particle_view* view, uint32_
     if (vfield(view, kIntFields[k].off).base && want_i(kIntFields[k].pf)) imask |= 1u << kIntFields[k].pf;
   /* tree order -> host order on the compute stream, then the copies on the copy stream: they
      overlap whatever the compute stream does next (the force pass, for a density download) */
-  if (!h->integ.on) {       /* (the device-resident main loop keeps the state in host order already) */
+  /* (the device-resident main loop keeps the state in host order already: there only results of passes
+     that ran since the last scatter -- operator calls between the halves of a step -- have to come back) */
+  if (!h->integ.on || h->results_newer) {
     scatter_fields_kernel<<<(int)((N + 255)/256), 256, 0, h->stream>>>((int) N, h->perm, devptrs(h->P, h->PI),
                                                                      devptrs(h->H, h->HI), dmask, imask);
     h->stats.kernel_launches++;
@@ -801,6 +808,7 @@ int gsph_build_tree(gsph_handle* h, int mode, double dt)
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   h->all_active = (nact == h->N);
   h->stats.n_active = nact;
+  h->p_stale = false;
   return GSPH_OK;
 }
 
@@ -853,6 +861,7 @@ int gsph_build_tree_shard_finish(gsph_handle* h)
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   h->all_active = (nact == h->N);
   h->stats.n_active = nact;
+  h->p_stale = false;
   return GSPH_OK;
 }
 
@@ -950,6 +959,8 @@ static int update_properties_impl(gsph_handle* h, bool refresh)
 {
   if (!h) return GSPH_EINVAL;
   if (!h->have_tree || !h->sorted_valid) { h->err = "gsph_update_properties before gsph_build_tree"; return GSPH_ESTATE; }
+  if (h->integ.on && h->p_stale) { h->err = "gsph_update_properties: the device-resident main loop changed v, u after the last BuildTree; call gsph_build_tree (or gsph_upload) first"; return GSPH_ESTATE; }
+  h->results_newer = true;
   cudaSetDevice(h->device);
   Timer tm(h, &h->stats.ms_properties);
   int rc = reset_status(h); if (rc) return rc;
@@ -1044,6 +1055,8 @@ int gsph_zero_accelerations(gsph_handle* h)
 {
   if (!h) return GSPH_EINVAL;
   if (!h->sorted_valid) { h->err = "gsph_zero_accelerations before gsph_build_tree"; return GSPH_ESTATE; }
+  if (h->integ.on && h->p_stale) { h->err = "gsph_zero_accelerations: the device-resident main loop changed v, u after the last BuildTree; call gsph_build_tree (or gsph_upload) first"; return GSPH_ESTATE; }
+  h->results_newer = true;
   cudaSetDevice(h->device);
   const int N = (int) h->N;
   DevPtrs P = devptrs(h->P, h->PI);
@@ -1094,6 +1107,8 @@ int gsph_update_hydro_forces(gsph_handle* h)
 {
   if (!h) return GSPH_EINVAL;
   if (!h->have_tree || !h->sorted_valid) { h->err = "gsph_update_hydro_forces before gsph_build_tree"; return GSPH_ESTATE; }
+  if (h->integ.on && h->p_stale) { h->err = "gsph_update_hydro_forces: the device-resident main loop changed v, u after the last BuildTree; call gsph_build_tree (or gsph_upload) first"; return GSPH_ESTATE; }
+  h->results_newer = true;
   cudaSetDevice(h->device);
   Timer tm(h, &h->stats.ms_forces);
   int rc = reset_status(h); if (rc) return rc;
@@ -1116,6 +1131,8 @@ int gsph_update_all_forces_begin(gsph_handle* h)
   if (!h) return GSPH_EINVAL;
   if (!h->have_tree || !h->sorted_valid) { h->err = "gsph_update_all_forces before gsph_build_tree"; return GSPH_ESTATE; }
   if (!h->cfg.self_gravity) { h->err = "gsph_update_all_forces needs self_gravity = 1 in the config"; return GSPH_EINVAL; }
+  if (h->integ.on && h->p_stale) { h->err = "gsph_update_all_forces: the device-resident main loop changed v, u after the last BuildTree; call gsph_build_tree (or gsph_upload) first"; return GSPH_ESTATE; }
+  h->results_newer = true;
   cudaSetDevice(h->device);
   h->forces_half_done = false;
   Timer tm(h, &h->stats.ms_forces);
@@ -1372,6 +1389,7 @@ static int integ_scatter_results(gsph_handle* h)
                                                                       devptrs(h->H, h->HI), dmask, imask);
   h->stats.kernel_launches++;
   CUDA_TRY(h, cudaGetLastError());
+  h->results_newer = false;
   return GSPH_OK;
 }
 
@@ -1511,6 +1529,12 @@ int gsph_integrator_begin(gsph_handle* h, const gsph_integrator_config* cfg, int
   if (h->integ.nstar > 0 && h->cfg.nbody_softening != 1) { h->err = "gsph_integrator_begin: star particles need nbody_softening = 1"; return GSPH_EINVAL; }
   if (h->integ.nstar > 0) for (int k = 0; k < h->cfg.ndim; k++)
     if (h->dp.periodic[k] || h->dp.mirror[k][0] || h->dp.mirror[k][1]) { h->err = "gsph_integrator_begin: star particles need open boundaries"; return GSPH_EINVAL; }
+  if (cfg->sink_particles != 0 || h->cfg.create_sinks != 0) {
+    /* the reference's MainLoop would search for new sinks, accrete and update the stellar properties
+       (SphSimulation.cpp:815-833); stepping on without them would silently diverge */
+    h->err = "gsph_integrator_begin: sink_particles / create_sinks are not on the accelerated path of the device-resident main loop";
+    return GSPH_EINVAL;
+  }
   if (compute_forces < 0 || compute_forces > 2) { h->err = "gsph_integrator_begin: compute_forces must be 0, 1 or 2"; return GSPH_EINVAL; }
   if (compute_forces == 1 && h->slice_mode) { h->err = "gsph_integrator_begin: compute_forces = 1 not with an active slice (the multi-GPU host layer runs the passes itself and passes 2)"; return GSPH_EINVAL; }
   if (compute_forces == 2 && !h->sorted_valid) { h->err = "gsph_integrator_begin(compute_forces = 2) before the passes"; return GSPH_ESTATE; }
@@ -1570,7 +1594,7 @@ int gsph_integrator_advance(gsph_handle* h, int* tree_mode, double* timestep)
   CUDA_TRY(h, cudaEventRecord(h->ev_geom, h->stream));
   CUDA_TRY(h, cudaEventRecord(h->ev_all, h->stream));
   for (int k = 0; k < 3; k++) CUDA_TRY(h, cudaEventRecord(h->ev_axis[k], h->stream));
-  h->sorted_valid = false; h->density_done = false; h->slice_mode = false;
+  h->sorted_valid = false; h->density_done = false; h->slice_mode = false; h->results_newer = false;
   /* sphneib->BuildTree(rebuild_tree, Nsteps, ntreebuildstep, ntreestockstep, timestep, sph) */
   const bool full = I.rebuild || I.Nsteps % I.cfg.ntreebuildstep == 0;
   if (tree_mode) *tree_mode = full ? 0 : (I.Nsteps % I.cfg.ntreestockstep == 0 ? 1 : 2);
@@ -1614,6 +1638,7 @@ int gsph_integrator_finish(gsph_handle* h)
   I.tlast = I.t;
   I.timestep = next;
   I.mid_step = false;
+  h->p_stale = true;                                    /* v, u were corrected in host order only */
   return GSPH_OK;
 }
 

@@ -453,7 +453,9 @@ gravity_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* wo
       if ((fl & GSPH_FLAG_ACTIVE) && !(fl & GSPH_FLAG_DEAD)) {
         P.f[F_AX][i] += ax[t]; P.f[F_AY][i] += ay[t]; P.f[F_AZ][i] += az[t];
         P.f[F_ATX][i] += ax[t]; P.f[F_ATY][i] += ay[t]; P.f[F_ATZ][i] += az[t];
-        P.f[F_GPOT][i] += pot[t];
+        const double gp = P.f[F_GPOT][i] + pot[t];
+        P.f[F_GPOT][i] = gp;
+        P.f[F_GPOTHYDRO][i] = gp;        /* gpot before the star terms (GradhSphTree.cpp:595-597, :616) */
       }
     }
     if (leaf_live && sub == 0) {

@@ -159,6 +159,11 @@ struct gsph_handle {
   bool uploaded = false, have_tree = false, sorted_valid = false, all_active = true;
   bool density_done = false;
   bool slice_mode = false;   /* gsph_set_active_slice: inactive particles belong to other ranks */
+  /* device-resident runs keep the particle state in HOST order (H*) and the passes write tree order (P*):
+       results_newer : a pass wrote tree-order results that have not been scattered back to host order yet
+       p_stale       : the integrator changed host-order inputs (v, u at the end of a step) after the last
+                       BuildTree, so an operator call would work on outdated tree-order copies          */
+  bool results_newer = false, p_stale = false;
 
   double* stars = nullptr; int Nstar = 0, stars_cap = 0;   /* device copy of {r[ndim], m, h} per star (gsph_set_stars) */
 

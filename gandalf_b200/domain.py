@@ -197,7 +197,7 @@ class DomainDriver(object):
             self.UpdateAllSphHydroForces()
         if self.world > 1:
             # the force results of the other slices (tree order): one in-place all-gather per array
-            fields = ["a", "atree", "gpot", "dudt", "div_v", "dalphadt", "alpha", "levelneib"]
+            fields = ["a", "atree", "gpot", "gpot_hydro", "dudt", "div_v", "dalphadt", "alpha", "levelneib"]
             self.tree.Synchronize()
             self._gather_inplace(self._array_names(fields, self.tree.cfg.ndim), False, self.N)
 

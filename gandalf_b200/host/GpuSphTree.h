@@ -270,11 +270,15 @@ class GpuSphTree : public GradhSphTree<ndim, GradhSphParticle>
     std::map<std::string, std::string>& sp = params->stringparams;
     if (sp["sph_integration"] != "lfkdk" || ip["Nlevels"] != 1)
       ExceptionHandler::getIstance().raise("GpuSphTree: the device-resident main loop needs sph_integration = lfkdk and Nlevels = 1");
+    // MainLoop's sink search / accretion / stellar-property update (SphSimulation.cpp:815-833) is not on this path
+    if (ip["sink_particles"] != 0 || ip["create_sinks"] != 0)
+      ExceptionHandler::getIstance().raise("GpuSphTree: sink_particles / create_sinks are not on the accelerated path of the device-resident main loop");
     gsph_integrator_config ic;
     memset(&ic, 0, sizeof ic);
     ic.accel_mult = fp["accel_mult"]; ic.courant_mult = fp["courant_mult"]; ic.energy_mult = fp["energy_mult"];
     ic.energy_integration = sp["gas_eos"] == "energy_eqn" ? 1 : 0;      // GradhSphSimulation.cpp:110-123
     ic.ntreebuildstep = ip["ntreebuildstep"]; ic.ntreestockstep = ip["ntreestockstep"];
+    ic.sink_particles = ip["sink_particles"];
     check(gsph_set_stars(handle, NULL, 0));
     upload(sph);
     check(gsph_integrator_begin(handle, &ic, 0, t));

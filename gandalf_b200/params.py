@@ -11,7 +11,7 @@ from . import _capi
 
 # defaults of the knobs on the path (Parameters.cpp:252-314, :373-384, :409)
 DEFAULTS = {
-    "ndim": 3, "sim": "gradhsph", "neib_search": "kdtree", "kernel": "m4", "tabulated_kernel": 1,
+    "ndim": 3, "sim": "sph", "neib_search": "kdtree", "kernel": "m4", "tabulated_kernel": 1,
     "h_fac": 1.2, "h_converge": 0.01, "hydro_forces": 1, "self_gravity": 0,
     "gas_eos": "energy_eqn", "gamma_eos": 1.66666666666666, "temp0": 1.0, "mu_bar": 1.0,
     "rho_bary": 1.0e-14, "avisc": "mon97", "acond": "none", "time_dependent_avisc": "none",
@@ -19,7 +19,7 @@ DEFAULTS = {
     "gravity_mac": "geometric", "multipole": "quadrupole", "thetamaxsqd": 0.1, "macerror": 0.0001,
     "Nleafmax": 6, "ntreebuildstep": 1, "ntreestockstep": 1, "create_sinks": 0, "conservative_sph_star_gravity": 1, "nbody_softening": 1, "sink_particles": 0,
     "Nlevels": 1, "sph_integration": "lfkdk", "accel_mult": 0.3, "courant_mult": 0.15, "energy_mult": 0.4,
-    "nbody": "lfkdk", "nbody_mult": 0.1,
+    "nbody": "hermite4", "nbody_mult": 0.1,
 }
 for _k in range(3):
     DEFAULTS["boundary_lhs[%d]" % _k] = "open"
@@ -72,11 +72,17 @@ def integrator_config_from_params(p):
         raise ValueError("sph_integration = %s is not on the accelerated path (lfkdk only)" % q["sph_integration"])
     if int(q["Nlevels"]) != 1:
         raise ValueError("the device-resident main loop uses one global time step (Nlevels = 1)")
+    if int(q["sink_particles"]) != 0 or int(q["create_sinks"]) != 0:
+        # MainLoop would run SearchForNewSinkParticles / AccreteMassToSinks / UpdateStellarProperties
+        # (SphSimulation.cpp:815-833): not on the accelerated path
+        raise ValueError("sink_particles / create_sinks are not on the accelerated path of the device-resident "
+                         "main loop (no sink search or accretion)")
     c = _capi.IntegratorConfig()
     c.accel_mult, c.courant_mult, c.energy_mult = (float(q["accel_mult"]), float(q["courant_mult"]),
                                                    float(q["energy_mult"]))
     c.energy_integration = 1 if q["gas_eos"] == "energy_eqn" else 0
     c.ntreebuildstep, c.ntreestockstep = int(q["ntreebuildstep"]), int(q["ntreestockstep"])
+    c.sink_particles = int(q["sink_particles"])
     return c
 
 

@@ -272,13 +272,19 @@ class GpuSphTree(object):
             hdr.update(t=t, Nsteps=n)
         except _capi.GsphError:
             pass
+        if getattr(self, "_nstar", 0) > 0 and "stars" not in header:
+            # the reference always writes nbody->stardata (WriteSerenUnformSnapshotFile, SimulationIO.hpp:2212-2250):
+            # without them a restart from our own snapshot would lose the star particles
+            st = self.IntegratorGetStars()
+            hdr["stars"] = dict(r=st["r"], v=st["v"], m=st["m"], h=st["h"])
         hdr.update(header)
         snapshot.write_su_from_particle_set(path, ps, **hdr)
         return ps
 
     @staticmethod
     def ReadSnapshot(path, alloc=None):
-        """-> (ParticleSet, header) from a SEREN-unformatted snapshot (the reference's or ours)"""
+        """-> (ParticleSet, header) from a SEREN-unformatted snapshot (the reference's or ours); star particles,
+        if the file has any, are header["stars"] = dict r, v, m, h, radius (feed them to IntegratorSetStars)"""
         from . import snapshot
         return snapshot.particle_set_from_su(path, alloc=alloc)
 

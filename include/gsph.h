@@ -338,7 +338,9 @@ typedef struct gsph_integrator_config {
                                    GradhSphSimulation.cpp:110-123); 0: u follows from the EOS         */
   int32_t ntreebuildstep;       /* full rebuild every this many steps (HydroTree.cpp BuildTree)       */
   int32_t ntreestockstep;       /* otherwise restock every this many steps, else extrapolate          */
-  int32_t reserved[5];
+  int32_t sink_particles;       /* Parameters.cpp "sink_particles": must be 0 -- MainLoop's sink search, accretion
+                                   and stellar-property update (SphSimulation.cpp:815-833) are not on this path   */
+  int32_t reserved[4];
 } gsph_integrator_config;
 
 /* Start from the particles of the last gsph_upload (host order is kept).

@@ -160,3 +160,60 @@ def test_snapshot_of_a_device_resident_run_and_restart(tmp_path):
     assert rel_err(ps2["rho"], ps["rho"]).max() < 0.05
     assert np.abs(ps2["r"] - ps["r"]).max() < 0.1*ps["h"].min()
     tree2.close()
+
+
+def test_snapshot_keeps_the_star_particles(tmp_path):
+    """a device-resident run with star particles writes them into its su snapshot (the reference always writes
+    nbody->stardata, SimulationIO.hpp:2212-2250) and a restart from that file carries them on"""
+    import gandalf_b200 as g
+    params, d = load_golden("loop_sphere_grav_stars")
+    setup, loop = split(d)
+    ps, tree = _upload_setup(g, params, setup)
+    tree.IntegratorSetStars(setup["star_r"], setup["star_v"], setup["star_m"], setup["star_h"], a=setup["star_a"])
+    tree.IntegratorBegin(compute_forces=False)
+    tree.MainLoop(2)
+    path = str(tmp_path / "stars.su.00002")
+    tree.WriteSnapshot(path)
+    st = tree.IntegratorGetStars()
+    tree.close()
+    ps2, hdr = g.GpuSphTree.ReadSnapshot(path)
+    assert "stars" in hdr and len(hdr["stars"]["m"]) == len(setup["star_m"])
+    for k in ("r", "v", "m", "h"):
+        assert np.array_equal(np.asarray(hdr["stars"][k]).reshape(np.asarray(st[k]).shape), st[k]), k
+    tree2 = g.GpuSphTree(params)
+    tree2.Upload(ps2)
+    tree2.IntegratorSetStars(hdr["stars"]["r"], hdr["stars"]["v"], hdr["stars"]["m"], hdr["stars"]["h"])
+    tree2.IntegratorBegin(compute_forces=True, t=hdr["t"])
+    tree2.MainLoop(1)
+    st2 = tree2.IntegratorGetStars()
+    assert len(st2["m"]) == len(st["m"]) and np.all(np.isfinite(st2["r"]))
+    assert np.abs(st2["r"] - st["r"]).max() < 0.1*np.abs(st["r"]).max()        # they moved on from where they were
+    tree2.close()
+
+
+def test_operator_calls_inside_a_resident_run_are_consistent():
+    """after MainLoop the tree-order copies are older than the host-order state (v, u were corrected):
+    an operator call without a new BuildTree is refused; after BuildTree its results do come back through
+    Download (they used to be dropped because the resident loop skips the tree-order -> host-order scatter);
+    sinks are refused up front"""
+    import gandalf_b200 as g
+    params, d = load_golden("loop_box3d_mm97")
+    setup, loop = split(d)
+    ps, tree = _upload_setup(g, params, setup)
+    tree.IntegratorBegin(compute_forces=False)
+    tree.MainLoop(1)
+    with pytest.raises(g.GsphError):
+        tree.UpdateAllSphProperties()
+    tree.Download(ps)
+    rho1 = ps["rho"].copy()
+    tree.BuildTree(True, 0, 1, 1, 0.0)                 # tree-order copies of the CURRENT host-order state
+    tree.UpdateAllSphProperties()
+    ps["rho"][...] = -1.0
+    tree.Download(ps)
+    assert rel_err(ps["rho"], rho1).max() < 1e-12      # same positions, h converged -> same density, and it arrived
+    tree.MainLoop(1)                                   # the loop carries on
+    tree.close()
+    with pytest.raises(ValueError):
+        g.GpuSphTree(dict(params, sink_particles=1)).IntegratorBegin(ps)
+    with pytest.raises(ValueError):
+        g.GpuSphTree(dict(params, create_sinks=1)).IntegratorBegin(ps)

@@ -670,3 +670,25 @@ def test_star_gas_forces_match_reference():
     assert np.array_equal(counts, ocounts)
     assert vec_rel_err(adot, oad).max() < 1e-7
     tree.close()
+
+
+def test_gpot_hydro_is_gpot_before_the_star_terms():
+    """UpdateAllSphForces sets gpot_hydro = gpot before the star contribution (GradhSphTree.cpp:595-597, :616):
+    without stars the two are equal bit for bit, with stars gpot_hydro stays what it was without them"""
+    import gandalf_b200 as g
+    params, d = load_golden("sphere_grav_stars")
+    si = _by_iorig(stage(d, "force_in"))
+    res = []
+    for stars in (False, True):
+        ps, tree = _make(params, si)
+        tree.BuildTree(True, 0, 1, 1, 0.0, ps)
+        if stars:
+            tree.SetStars(d["stars"][:, :3], d["stars"][:, 3], d["stars"][:, 4])
+        tree.ZeroAccelerations()
+        tree.UpdateAllSphForces()
+        tree.Download(ps)
+        res.append((ps["gpot"].copy(), ps["gpot_hydro"].copy()))
+        tree.close()
+    assert np.array_equal(res[0][0], res[0][1])
+    assert np.array_equal(res[1][1], res[0][1])
+    assert np.all(res[1][0] > res[1][1])

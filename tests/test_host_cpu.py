@@ -286,9 +286,33 @@ def test_domain_driver_main_loop_sequence():
     lo, hi, _ = domain.slice_bounds(1001, 2, 1)
     step = ["DensityPass", "Synchronize", "exchange_density", ("DeriveDensityFields", lo, hi), "RefreshHmax",
             "ZeroAccelerations", "UpdateAllSphForces", "Synchronize",
-            ("gather", ("ax", "ay", "az", "atx", "aty", "atz", "gpot", "dudt", "div_v", "dalphadt", "alpha", "levelneib"),
+            ("gather", ("ax", "ay", "az", "atx", "aty", "atz", "gpot", "gpot_hydro", "dudt", "div_v", "dalphadt", "alpha", "levelneib"),
              False), "IntegratorFinish"]
     expect = []
     for build in ("sharded_rebuild", ("BuildTreeMode", 1), ("BuildTreeMode", 2)):
         expect += ["IntegratorAdvance", build, ("SetActiveSlice", lo, hi)] + step
     assert stub.calls == expect, stub.calls
+
+
+def test_defaults_equal_the_reference():
+    """every key gandalf_b200.params.DEFAULTS mirrors has the value Parameters::SetDefaultValues assigns
+    (Parameters.cpp:166-536; tests/golden/ref_defaults.json, generator make_defaults_golden.py) -- a
+    .dat file that leaves a key out must mean the same run in both codes (e.g. nbody = hermite4)"""
+    import json
+    from gandalf_b200.params import DEFAULTS
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "ref_defaults.json")))
+    for k, v in DEFAULTS.items():
+        assert k in ref, "%s is not a parameter of the reference" % k
+        assert ref[k] == v and type(ref[k]) is type(v), "%s: %r, reference %r" % (k, v, ref[k])
+    assert DEFAULTS["nbody"] == "hermite4"
+
+
+def test_device_loop_rejects_what_it_does_not_run():
+    """the device-resident main loop has no sink search / accretion, block time steps or Hermite stars:
+    parameter sets that ask for them are refused instead of silently running something else"""
+    from gandalf_b200.params import integrator_config_from_params
+    c = integrator_config_from_params({"ndim": 3})
+    assert c.sink_particles == 0 and c.ntreebuildstep == 1
+    for bad in ({"sink_particles": 1}, {"create_sinks": 1}, {"Nlevels": 5}, {"sph_integration": "lfdkd"}):
+        with pytest.raises(ValueError):
+            integrator_config_from_params(dict({"ndim": 3}, **bad))
