@@ -77,9 +77,9 @@ __global__ void scatter_fields_kernel(int N, const int32_t* perm, DevPtrs P, Dev
 }
 
 template <int NDIM>
-__global__ void zero_acc_kernel(int N, DevPtrs P)
+__global__ void zero_acc_kernel(int lo, int N, DevPtrs P)
 {
-  const int i = blockIdx.x*blockDim.x + threadIdx.x;
+  const int i = lo + blockIdx.x*blockDim.x + threadIdx.x;
   if (i >= N) return;
   if (!(((unsigned) P.i[I_FLAGS][i]) & GSPH_FLAG_ACTIVE)) return;
   P.i[I_LEVELNEIB][i] = 0;
@@ -118,17 +118,22 @@ int ensure_capacity(gsph_handle* h, int64_t N)
   h->Ncap = 0; h->integ.cap = 0;
   h->uploaded = h->have_tree = h->sorted_valid = h->density_done = false;
   h->integ.on = false; h->results_newer = false;
+  h->present_d = h->hdef_d = h->pvalid_d = 0ull; h->present_i = h->hdef_i = h->pvalid_i = 0u;
   for (int f = 0; f < NF_DOUBLE; f++) {
     if (h->H[f]) cudaFree(h->H[f]); if (h->P[f]) cudaFree(h->P[f]);
     h->H[f] = h->P[f] = nullptr;
     CUDA_TRY(h, cudaMalloc(&h->H[f], cap*sizeof(double)));
     CUDA_TRY(h, cudaMalloc(&h->P[f], cap*sizeof(double)));
+    /* defined contents from the start: a device that only ever writes its slice of a result array (multi-GPU)
+       leaves zeros, not heap garbage, in the rest */
+    CUDA_TRY(h, cudaMemsetAsync(h->P[f], 0, cap*sizeof(double), h->stream));
   }
   for (int f = 0; f < NF_INT; f++) {
     if (h->HI[f]) cudaFree(h->HI[f]); if (h->PI[f]) cudaFree(h->PI[f]);
     h->HI[f] = h->PI[f] = nullptr;
     CUDA_TRY(h, cudaMalloc(&h->HI[f], cap*sizeof(int32_t)));
     CUDA_TRY(h, cudaMalloc(&h->PI[f], cap*sizeof(int32_t)));
+    CUDA_TRY(h, cudaMemsetAsync(h->PI[f], 0, cap*sizeof(int32_t), h->stream));
   }
   if (h->perm) cudaFree(h->perm);
   h->perm = nullptr;
@@ -178,6 +183,7 @@ void fill_devparams(gsph_handle* h)
   }
   d.star_zeta = c.conservative_sph_star_gravity != 0; d.nbody_softening = c.nbody_softening;
   d.stars = nullptr; d.nstar = 0;
+  d.slice_lo = 0; d.slice_hi = 0x7fffffff;
   d.any_mirror = 0; d.nimg = 1;
   for (int k = 0; k < 3; k++) {
     d.mirror[k][0] = (k < c.ndim && c.boundary_lhs[k] == GSPH_BOUNDARY_MIRROR) ? 1 : 0;
@@ -511,7 +517,7 @@ void gsph_destroy(gsph_handle* h)
   for (int f = 0; f < NF_DOUBLE; f++) { fre(h->H[f]); fre(h->P[f]); }
   for (int f = 0; f < NF_INT; f++) { fre(h->HI[f]); fre(h->PI[f]); }
   for (int k = 0; k < 11; k++) fre(h->integ.s0[k]);
-  fre(h->integ.red); fre(h->perm); fre(h->tables); fre(h->scratch); fre(h->cand); fre(h->gravlist); fre(h->status); fre(h->work_counter); fre(h->done); fre(h->geo4); fre(h->geoh); fre(h->frec); fre(h->nlist); fre(h->hnew); fre(h->stars); fre(h->gstack);
+  fre(h->integ.red); fre(h->perm); fre(h->tables); fre(h->scratch); fre(h->cand); fre(h->gravlist); fre(h->status); fre(h->work_counter); fre(h->done); fre(h->needed); fre(h->geo4); fre(h->geoh); fre(h->frec); fre(h->nlist); fre(h->hnew); fre(h->stars); fre(h->gstack);
   TreeDev& T = h->tree;
   fre(T.first); fre(T.count); fre(T.nactive); fre(T.m); fre(T.rmax); fre(T.hmax); fre(T.cdistsqd);
   for (int k = 0; k < 3; k++) { fre(T.bbmin[k]); fre(T.bbmax[k]); fre(T.hbmin[k]); fre(T.hbmax[k]); fre(T.rcell[k]); fre(T.com[k]); fre(T.vcom[k]); }
@@ -582,8 +588,16 @@ static int upload_impl(gsph_handle* h, const gsph_particle_view* view, int64_t N
       if (geom != (pass == 0)) continue;
       const gsph_field& f = vfield(view, kDoubleFields[k].off);
       const bool unused_dim = (pf >= F_RX && pf <= F_ATZ) && ((pf - F_RX) % 3 >= nd);
-      if (!f.base || unused_dim) fill_kernel<double><<<nb, 256, 0, h->copy_stream>>>(N, h->H[pf], default_double(pf));
-      else if (f.stride == sizeof(double)) {
+      if (!f.base || unused_dim) {
+        /* absent: the reference's constructor default; the staging array keeps it until something writes there */
+        if (!((h->hdef_d >> pf) & 1ull)) fill_kernel<double><<<nb, 256, 0, h->copy_stream>>>(N, h->H[pf], default_double(pf));
+        h->hdef_d |= 1ull << pf; h->present_d &= ~(1ull << pf);
+        if (pf >= F_RX && pf <= F_RZ && !(bulk_ok && (plan.nf || plan.ni)))
+          CUDA_TRY(h, cudaEventRecord(h->ev_axis[pf - F_RX], h->copy_stream));
+        continue;
+      }
+      h->present_d |= 1ull << pf; h->hdef_d &= ~(1ull << pf);
+      if (f.stride == sizeof(double)) {
         if (nr > 0) CUDA_TRY(h, cudaMemcpyAsync(h->H[pf] + r0, (const double*) f.base + r0, nr*sizeof(double), cudaMemcpyHostToDevice, h->copy_stream));
       }
       else if (!whole) { h->err = "gsph_upload_range needs contiguous (SoA) fields"; return GSPH_EINVAL; }
@@ -603,8 +617,13 @@ static int upload_impl(gsph_handle* h, const gsph_particle_view* view, int64_t N
     for (int k = 0; k < kNIntFields; k++) {
       const int pf = kIntFields[k].pf;
       const gsph_field& f = vfield(view, kIntFields[k].off);
-      if (!f.base) fill_kernel<int32_t><<<nb, 256, 0, h->copy_stream>>>(N, h->HI[pf], default_int(pf));
-      else if (f.stride == sizeof(int32_t)) {
+      if (!f.base) {
+        if (!((h->hdef_i >> pf) & 1u)) fill_kernel<int32_t><<<nb, 256, 0, h->copy_stream>>>(N, h->HI[pf], default_int(pf));
+        h->hdef_i |= 1u << pf; h->present_i &= ~(1u << pf);
+        continue;
+      }
+      h->present_i |= 1u << pf; h->hdef_i &= ~(1u << pf);
+      if (f.stride == sizeof(int32_t)) {
         if (nr > 0) CUDA_TRY(h, cudaMemcpyAsync(h->HI[pf] + r0, (const int32_t*) f.base + r0, nr*sizeof(int32_t), cudaMemcpyHostToDevice, h->copy_stream));
       }
       else if (!whole) { h->err = "gsph_upload_range needs contiguous (SoA) fields"; return GSPH_EINVAL; }
@@ -646,7 +665,8 @@ static int upload_impl(gsph_handle* h, const gsph_particle_view* view, int64_t N
   h->upload_pending = true;
   CUDA_TRY(h, cudaGetLastError());
   if (N != h->N) h->have_tree = false;
-  h->N = N; h->uploaded = true; h->sorted_valid = false; h->density_done = false; h->slice_mode = false;
+  h->N = N; h->uploaded = true; h->sorted_valid = false; h->density_done = false;
+  h->slice_mode = false; h->dp.slice_lo = 0; h->dp.slice_hi = 0x7fffffff;
   h->integ.on = false; h->results_newer = false; h->p_stale = false;
   h->stats.Nhydro = N;
   tm.stop();
@@ -699,10 +719,16 @@ static int download_impl(gsph_handle* h, const gsph_particle_view* view, uint32_
   /* (the device-resident main loop keeps the state in host order already: there only results of passes
      that ran since the last scatter -- operator calls between the halves of a step -- have to come back) */
   if (!h->integ.on || h->results_newer) {
-    scatter_fields_kernel<<<(int)((N + 255)/256), 256, 0, h->stream>>>((int) N, h->perm, devptrs(h->P, h->PI),
-                                                                     devptrs(h->H, h->HI), dmask, imask);
-    h->stats.kernel_launches++;
-    CUDA_TRY(h, cudaGetLastError());
+    /* only the fields whose tree-order copy carries information (permuted inputs, results of the passes);
+       the others are still exactly what the host uploaded (or the defaults) in host order */
+    const unsigned long long sd = dmask & h->pvalid_d; const unsigned si = imask & h->pvalid_i;
+    if (sd || si) {
+      scatter_fields_kernel<<<(int)((N + 255)/256), 256, 0, h->stream>>>((int) N, h->perm, devptrs(h->P, h->PI),
+                                                                       devptrs(h->H, h->HI), sd, si);
+      h->stats.kernel_launches++;
+      CUDA_TRY(h, cudaGetLastError());
+      h->hdef_d &= ~sd; h->hdef_i &= ~si;
+    }
   }
   CUDA_TRY(h, cudaEventRecord(h->ev_compute, h->stream));
   CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->ev_compute, 0));
@@ -947,9 +973,9 @@ int gsph_prepare_done_flags(gsph_handle* h)
   return GSPH_OK;
 }
 
-__global__ void commit_h_kernel(int N, const int32_t* flags, const double* __restrict__ hnew, double* __restrict__ h)
+__global__ void commit_h_kernel(int lo, int N, const int32_t* flags, const double* __restrict__ hnew, double* __restrict__ h)
 {
-  const int i = blockIdx.x*blockDim.x + threadIdx.x;
+  const int i = lo + blockIdx.x*blockDim.x + threadIdx.x;
   if (i >= N) return;
   const unsigned f = (unsigned) flags[i];
   if ((f & GSPH_FLAG_ACTIVE) && !(f & GSPH_FLAG_DEAD)) h[i] = hnew[i];
@@ -970,8 +996,8 @@ static int update_properties_impl(gsph_handle* h, bool refresh)
   {
     /* the kernel leaves h untouched (a cohort may have to be redone with larger scratch and must
        then start from the same guess): commit the new smoothing lengths now */
-    const int N = (int) h->N;
-    commit_h_kernel<<<(N + 255)/256, 256, 0, h->stream>>>(N, h->PI[I_FLAGS], h->hnew, h->P[F_H]);
+    const int lo = h->dp.slice_lo, N = (int) std::min<int64_t>(h->N, h->dp.slice_hi);
+    commit_h_kernel<<<std::max(1, (N - lo + 255)/256), 256, 0, h->stream>>>(lo, N, h->PI[I_FLAGS], h->hnew, h->P[F_H]);
     h->stats.kernel_launches++;
     CUDA_TRY(h, cudaGetLastError());
   }
@@ -986,6 +1012,7 @@ static int update_properties_impl(gsph_handle* h, bool refresh)
   h->stats.hiter_max = s.hiter_max;
   h->stats.density_retries = s.density_retries;
   h->density_done = true;
+  h->pvalid_d |= GSPH_OUT_DENSITY; h->pvalid_i |= 1u << I_FLAGS;
   return GSPH_OK;
 }
 
@@ -1011,27 +1038,17 @@ int gsph_derive_density_fields(gsph_handle* h, int64_t lo, int64_t hi)
   return gsph_derive_density_fields_impl(h, (int) lo, (int) hi);
 }
 
-__global__ void active_slice_kernel(int N, int lo, int hi, int32_t* flags)
-{
-  const int p = blockIdx.x*blockDim.x + threadIdx.x;
-  if (p >= N) return;
-  unsigned f = (unsigned) flags[p];
-  if (p >= lo && p < hi) f |= GSPH_FLAG_ACTIVE; else f &= ~(unsigned) GSPH_FLAG_ACTIVE;
-  flags[p] = (int32_t) f;
-}
-
+/* multi-GPU: this device updates only the tree-order particles [lo, hi); the others are sources.  The
+   kernels test the range themselves (DevParams::slice_lo / slice_hi): no flag is rewritten and the
+   active counters of the tree stay those of the particle flags.                                        */
 int gsph_set_active_slice(gsph_handle* h, int64_t lo, int64_t hi)
 {
   if (!h) return GSPH_EINVAL;
   if (!h->have_tree || !h->sorted_valid) { h->err = "gsph_set_active_slice before gsph_build_tree"; return GSPH_ESTATE; }
   if (lo < 0 || hi < lo || hi > h->N) { h->err = "gsph_set_active_slice: bad range"; return GSPH_EINVAL; }
-  cudaSetDevice(h->device);
-  const int N = (int) h->N;
-  active_slice_kernel<<<(N + 255)/256, 256, 0, h->stream>>>(N, (int) lo, (int) hi, h->PI[I_FLAGS]);
-  h->stats.kernel_launches++;
+  h->dp.slice_lo = (int) lo; h->dp.slice_hi = (int) hi;
   h->slice_mode = true;
-  CUDA_TRY(h, cudaGetLastError());
-  return gsph_update_active_counters(h);
+  return GSPH_OK;
 }
 
 int gsph_device_field(gsph_handle* h, int field, void** ptr, int64_t* capacity)
@@ -1058,15 +1075,43 @@ int gsph_zero_accelerations(gsph_handle* h)
   if (h->integ.on && h->p_stale) { h->err = "gsph_zero_accelerations: the device-resident main loop changed v, u after the last BuildTree; call gsph_build_tree (or gsph_upload) first"; return GSPH_ESTATE; }
   h->results_newer = true;
   cudaSetDevice(h->device);
-  const int N = (int) h->N;
+  const int lo = h->dp.slice_lo, N = (int) std::min<int64_t>(h->N, h->dp.slice_hi);   /* this device's targets */
   DevPtrs P = devptrs(h->P, h->PI);
+  const int nb = std::max(1, (N - lo + 255)/256);
   switch (h->cfg.ndim) {
-  case 1: zero_acc_kernel<1><<<(N + 255)/256, 256, 0, h->stream>>>(N, P); break;
-  case 2: zero_acc_kernel<2><<<(N + 255)/256, 256, 0, h->stream>>>(N, P); break;
-  default: zero_acc_kernel<3><<<(N + 255)/256, 256, 0, h->stream>>>(N, P); break;
+  case 1: zero_acc_kernel<1><<<nb, 256, 0, h->stream>>>(lo, N, P); break;
+  case 2: zero_acc_kernel<2><<<nb, 256, 0, h->stream>>>(lo, N, P); break;
+  default: zero_acc_kernel<3><<<nb, 256, 0, h->stream>>>(lo, N, P); break;
   }
   h->stats.kernel_launches++;
   CUDA_TRY(h, cudaGetLastError());
+  h->pvalid_d |= GSPH_OUT_FORCES & ~GSPH_DMASK(F_DALPHADT); h->pvalid_i |= 1u << I_LEVELNEIB;
+  h->acc_zeroed = true;
+  return GSPH_OK;
+}
+
+/* Accumulators the host did not supply start from their default 0 (what the reference's constructors give):
+   if no gsph_zero_accelerations ran since BuildTree, clear the ones the tree-order arrays do not hold yet. */
+__global__ void zero_fields_kernel(int N, DevPtrs P, unsigned long long dmask, unsigned imask)
+{
+  const int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  for (int f = 0; f < NF_DOUBLE; f++) if ((dmask >> f) & 1ull) P.f[f][i] = 0.0;
+  for (int f = 0; f < NF_INT; f++) if ((imask >> f) & 1u) P.i[f][i] = 0;
+}
+
+static int prepare_accumulators(gsph_handle* h)
+{
+  unsigned long long acc = GSPH_OUT_FORCES;
+  if (h->dp.tdavisc == GSPH_TDAVISC_CD2010) acc &= ~GSPH_DMASK(F_DALPHADT);      /* set by the density pass */
+  const unsigned long long zd = acc & ~h->pvalid_d; const unsigned zi = (1u << I_LEVELNEIB) & ~h->pvalid_i;
+  if (zd || zi) {
+    const int N = (int) h->N;
+    zero_fields_kernel<<<(N + 255)/256, 256, 0, h->stream>>>(N, devptrs(h->P, h->PI), zd, zi);
+    h->stats.kernel_launches++;
+    CUDA_TRY(h, cudaGetLastError());
+  }
+  h->pvalid_d |= GSPH_OUT_FORCES; h->pvalid_i |= 1u << I_LEVELNEIB;
   return GSPH_OK;
 }
 
@@ -1112,6 +1157,7 @@ int gsph_update_hydro_forces(gsph_handle* h)
   cudaSetDevice(h->device);
   Timer tm(h, &h->stats.ms_forces);
   int rc = reset_status(h); if (rc) return rc;
+  rc = prepare_accumulators(h); if (rc) return rc;
   rc = gsph_prepare_done_flags(h); if (rc) return rc;
   rc = run_with_regrow(h, "gsph_update_hydro_forces", pass_hydro, 0);
   if (rc) return rc;
@@ -1137,6 +1183,7 @@ int gsph_update_all_forces_begin(gsph_handle* h)
   h->forces_half_done = false;
   Timer tm(h, &h->stats.ms_forces);
   int rc = reset_status(h); if (rc) return rc;
+  rc = prepare_accumulators(h); if (rc) return rc;
   rc = gsph_prepare_done_flags(h); if (rc) return rc;
   rc = run_with_regrow(h, "gsph_update_all_forces(neighbours)", pass_hydro, 1);
   if (rc) return rc;
@@ -1384,12 +1431,14 @@ static int integ_scatter_results(gsph_handle* h)
   const int fields[] = {F_H, F_U, F_RHO, F_HR2, F_HFAC, F_INVOMEGA, F_ZETA, F_SOUND, F_PRESS, F_DUDT, F_DIVV, F_ALPHA,
                         F_DALPHADT, F_GPOT, F_GPOTHYDRO, F_AX, F_AY, F_AZ, F_ATX, F_ATY, F_ATZ};
   for (int f : fields) dmask |= 1ull << f;
-  const unsigned imask = (1u << I_FLAGS) | (1u << I_LEVELNEIB);
+  dmask &= h->pvalid_d;
+  const unsigned imask = ((1u << I_FLAGS) | (1u << I_LEVELNEIB)) & h->pvalid_i;
   scatter_fields_kernel<<<(int)((h->N + 255)/256), 256, 0, h->stream>>>((int) h->N, h->perm, devptrs(h->P, h->PI),
                                                                       devptrs(h->H, h->HI), dmask, imask);
   h->stats.kernel_launches++;
   CUDA_TRY(h, cudaGetLastError());
   h->results_newer = false;
+  h->hdef_d = 0ull; h->hdef_i = 0u;                     /* the host-order arrays are the particle state now */
   return GSPH_OK;
 }
 
@@ -1548,6 +1597,7 @@ int gsph_integrator_begin(gsph_handle* h, const gsph_integrator_config* cfg, int
   }
   if (!I.red) CUDA_TRY(h, cudaMalloc(&I.red, 2*sizeof(unsigned long long)));
   I.cfg = *cfg; I.t = I.tlast = t0; I.Nsteps = 0; I.rebuild = true; I.on = false; I.mid_step = false;
+  h->hdef_d = 0ull; h->hdef_i = 0u;                     /* the integrator writes the host-order arrays */
   CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_all, 0));          /* the upload has landed */
   if (I.nstar > 0) { const int rs = integ_push_stars(h); if (rs) return rs; }
   if (compute_forces == 1) {
@@ -1594,7 +1644,8 @@ int gsph_integrator_advance(gsph_handle* h, int* tree_mode, double* timestep)
   CUDA_TRY(h, cudaEventRecord(h->ev_geom, h->stream));
   CUDA_TRY(h, cudaEventRecord(h->ev_all, h->stream));
   for (int k = 0; k < 3; k++) CUDA_TRY(h, cudaEventRecord(h->ev_axis[k], h->stream));
-  h->sorted_valid = false; h->density_done = false; h->slice_mode = false; h->results_newer = false;
+  h->sorted_valid = false; h->density_done = false; h->results_newer = false;
+  h->slice_mode = false; h->dp.slice_lo = 0; h->dp.slice_hi = 0x7fffffff;
   /* sphneib->BuildTree(rebuild_tree, Nsteps, ntreebuildstep, ntreestockstep, timestep, sph) */
   const bool full = I.rebuild || I.Nsteps % I.cfg.ntreebuildstep == 0;
   if (tree_mode) *tree_mode = full ? 0 : (I.Nsteps % I.cfg.ntreestockstep == 0 ? 1 : 2);

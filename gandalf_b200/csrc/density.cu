@@ -242,7 +242,7 @@ density_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict_
     if (c >= ncohort) break;
     const int node = ncohort - 1 + c;
     const int cfirst = tree.first[node], ccount = tree.count[node];
-    if (ccount == 0 || tree.nactive[node] == 0 || done[c]) continue;
+    if (ccount == 0 || tree.nactive[node] == 0 || done[c] || GSPH_RANGE_OUTSIDE_SLICE(dp, cfirst, ccount)) continue;
     bool overflow = false;
     double cmin[3], cmax[3];
 #pragma unroll
@@ -251,7 +251,7 @@ density_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict_
     for (int t0 = 0; t0 < ccount && !overflow; t0 += 32) {
       /* ---- the target of this lane ---------------------------------------------------------------*/
       const int ti = cfirst + t0 + lane;
-      bool live = t0 + lane < ccount;
+      bool live = t0 + lane < ccount && GSPH_IN_SLICE(dp, ti);
       if (live) {
         const unsigned fl = (unsigned) P.i[I_FLAGS][ti];
         live = (fl & GSPH_FLAG_ACTIVE) && !(fl & GSPH_FLAG_DEAD);

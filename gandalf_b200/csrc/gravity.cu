@@ -101,7 +101,8 @@ gravity_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* wo
     c = __shfl_sync(FULLMASK, c, 0);
     if (c >= ncohort) break;
     const int cnode = ncohort - 1 + c;
-    if (tree.count[cnode] == 0 || tree.nactive[cnode] == 0 || done[c]) continue;
+    if (tree.count[cnode] == 0 || tree.nactive[cnode] == 0 || done[c] ||
+        GSPH_RANGE_OUTSIDE_SLICE(dp, tree.first[cnode], tree.count[cnode])) continue;
 
     /* ---- this lane's leaf and target particles ------------------------------------------------------*/
     const int myleaf = ((cnode + 1) << (tree.ltot - cohort_level)) - 1 + myl;    /* heap id */
@@ -109,14 +110,14 @@ gravity_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* wo
     bool leaf_live = false;
     if (myl < nl) {
       first = tree.first[myleaf]; cnt = tree.count[myleaf];
-      leaf_live = cnt > 0 && tree.nactive[myleaf] > 0;
+      leaf_live = cnt > 0 && tree.nactive[myleaf] > 0 && !GSPH_RANGE_OUTSIDE_SLICE(dp, first, cnt);
     }
     double x[T][3], hr2[T], ax[T], ay[T], az[T], pot[T];
     bool tlive[T];
 #pragma unroll
     for (int t = 0; t < T; t++) {
       const int o = sub + 4*t;
-      tlive[t] = leaf_live && o < cnt;
+      tlive[t] = leaf_live && o < cnt && GSPH_IN_SLICE(dp, first + o);
       x[t][0] = x[t][1] = x[t][2] = 0.0; hr2[t] = 0.0; ax[t] = ay[t] = az[t] = pot[t] = 0.0;
       if (tlive[t]) {
         x[t][0] = P.f[F_RX][first + o]; x[t][1] = P.f[F_RY][first + o]; x[t][2] = P.f[F_RZ][first + o];

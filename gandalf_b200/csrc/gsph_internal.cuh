@@ -92,7 +92,11 @@ struct DevParams {
   int create_sinks;
   int star_zeta, nbody_softening;   /* conservative_sph_star_gravity: star terms of zeta (GradhSph.cpp:288-306) */
   const double* stars; int nstar;   /* device rows {r[ndim], m, h} of gsph_set_stars                    */
+  int slice_lo, slice_hi;           /* multi-GPU: only the tree-order particles [slice_lo, slice_hi) are targets of
+                                       this device (gsph_set_active_slice); [0, INT_MAX) otherwise             */
 };
+#define GSPH_IN_SLICE(dp, p) ((p) >= (dp).slice_lo && (p) < (dp).slice_hi)
+#define GSPH_RANGE_OUTSIDE_SLICE(dp, first, count) ((first) >= (dp).slice_hi || (first) + (count) <= (dp).slice_lo)
 
 /* device-side error / statistics block */
 struct DevStatus {
@@ -164,6 +168,16 @@ struct gsph_handle {
        p_stale       : the integrator changed host-order inputs (v, u at the end of a step) after the last
                        BuildTree, so an operator call would work on outdated tree-order copies          */
   bool results_newer = false, p_stale = false;
+  /* which particle arrays carry information (bit = PField / IField index):
+       present_* : the host handed the field to the last gsph_upload (absent ones hold the defaults)
+       hdef_*    : the host-order staging array currently holds the default fill (no need to refill)
+       pvalid_*  : the tree-order array is up to date (permuted by BuildTree or written by a pass); a
+                   download takes the other fields straight from host order
+     lazy_fields : every particle is active and alive in this step, so pure outputs need not be permuted
+     acc_zeroed  : gsph_zero_accelerations ran since the last BuildTree                                   */
+  unsigned long long present_d = 0, hdef_d = 0, pvalid_d = 0;
+  unsigned present_i = 0, hdef_i = 0, pvalid_i = 0;
+  bool lazy_fields = false, acc_zeroed = false;
 
   double* stars = nullptr; int Nstar = 0, stars_cap = 0;   /* device copy of {r[ndim], m, h} per star (gsph_set_stars) */
 
@@ -182,6 +196,7 @@ struct gsph_handle {
   DevStatus* status_host = nullptr; /* pinned */
   int* work_counter = nullptr;
   uint8_t* done = nullptr; size_t done_cap = 0;   /* per cohort / leaf: finished in this pass */
+  uint8_t* needed = nullptr; size_t needed_cap = 0;   /* per cohort node: may hold a neighbour of this device's slice */
   void* pinned = nullptr; size_t pinned_bytes = 0;             /* host staging for strided views  */
 
   gsph_stats stats;
@@ -213,6 +228,15 @@ int gsph_check_status(gsph_handle* h, const char* where);             /* capi.cu
 int gsph_ensure_cand(gsph_handle* h, int warps, size_t cap_per_warp);
 int gsph_ensure_nlist(gsph_handle* h, int warps, size_t cap);
 int gsph_pack_geo4(gsph_handle* h);                                   /* tree.cu */
+int gsph_gather_fields(gsph_handle* h);                               /* tree.cu: host order -> tree order */
+/* fields written by the passes (for pvalid_*) */
+#define GSPH_DMASK(f) (1ull << (f))
+static const unsigned long long GSPH_OUT_DENSITY =
+  GSPH_DMASK(F_H) | GSPH_DMASK(F_RHO) | GSPH_DMASK(F_HR2) | GSPH_DMASK(F_HFAC) | GSPH_DMASK(F_INVOMEGA) | GSPH_DMASK(F_ZETA) |
+  GSPH_DMASK(F_SOUND) | GSPH_DMASK(F_PRESS) | GSPH_DMASK(F_U) | GSPH_DMASK(F_DIVV) | GSPH_DMASK(F_ALPHA) | GSPH_DMASK(F_DALPHADT);
+static const unsigned long long GSPH_OUT_FORCES =
+  GSPH_DMASK(F_AX) | GSPH_DMASK(F_AY) | GSPH_DMASK(F_AZ) | GSPH_DMASK(F_ATX) | GSPH_DMASK(F_ATY) | GSPH_DMASK(F_ATZ) |
+  GSPH_DMASK(F_GPOT) | GSPH_DMASK(F_GPOTHYDRO) | GSPH_DMASK(F_DUDT) | GSPH_DMASK(F_DIVV) | GSPH_DMASK(F_DALPHADT);
 
 struct KernelTimer {          /* brackets one launch (or group) with events; read back later */
   gsph_handle* h; int k;

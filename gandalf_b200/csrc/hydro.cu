@@ -132,11 +132,35 @@ struct Neib {            /* one gathered force record (frec, 128 B) */
  * Chunks 0-1 double as the geometry record of the candidate filter.  Dead particles get x = BIG and
  * hrangesqd = -1 so that no predicate ever accepts them.                                            */
 template <int NDIM>
+__device__ __forceinline__ void pack_force_one(int p, const PartView& P, int aux_is_alpha, double* __restrict__ frec,
+                                               double* __restrict__ geoh);
+
+/* only the particles of the cohort nodes flagged by needed_cohorts_kernel: one warp per cohort node */
+template <int NDIM>
+__global__ void pack_force_needed_kernel(TreeDev tree, int cohort_level, const uint8_t* __restrict__ needed, PartView P,
+                                         int aux_is_alpha, double* __restrict__ frec, double* __restrict__ geoh)
+{
+  const int c = (blockIdx.x*blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int ncohort = 1 << cohort_level;
+  if (c >= ncohort || !needed[c]) return;
+  const int node = ncohort - 1 + c;
+  const int first = tree.first[node], count = tree.count[node];
+  for (int o = lane; o < count; o += 32) pack_force_one<NDIM>(first + o, P, aux_is_alpha, frec, geoh);
+}
+
+template <int NDIM>
 __global__ void pack_force_kernel(int N, PartView P, int aux_is_alpha, double* __restrict__ frec,
                                   double* __restrict__ geoh)
 {
   const int p = blockIdx.x*blockDim.x + threadIdx.x;
   if (p >= N) return;
+  pack_force_one<NDIM>(p, P, aux_is_alpha, frec, geoh);
+}
+
+template <int NDIM>
+__device__ __forceinline__ void pack_force_one(int p, const PartView& P, int aux_is_alpha, double* __restrict__ frec,
+                                               double* __restrict__ geoh)
+{
   const bool dead = ((unsigned) P.i[I_FLAGS][p]) & GSPH_FLAG_DEAD;
   const double x = P.f[F_RX][p], y = NDIM > 1 ? P.f[F_RY][p] : 0.0, z = NDIM > 2 ? P.f[F_RZ][p] : 0.0;
   const double h = P.f[F_H][p], rho = P.f[F_RHO][p], pr = P.f[F_PRESS][p];
@@ -151,6 +175,55 @@ __global__ void pack_force_kernel(int N, PartView P, int aux_is_alpha, double* _
   r[5] = make_double2(1.0/rho, (pr*P.f[F_INVOMEGA][p])/(rho*rho));
   r[6] = make_double2(P.f[F_SOUND][p], P.f[F_ZETA][p]);
   r[7] = make_double2(P.f[F_U][p], aux_is_alpha ? P.f[F_ALPHA][p] : (double) P.i[I_LEVEL][p]);
+}
+
+/* Multi-GPU (gsph_set_active_slice): a device only evaluates the targets of its tree-order slice, so it only
+ * needs the force records of the cohort nodes that can hold a neighbour of the slice.  The slice is covered by
+ * a few tree nodes K (host side, from the data-independent topology of the balanced tree); a cohort node c is
+ * NEEDED if it intersects the slice or  c.hbox meets K.bb  or  c.bb meets K.hbox  for some K -- the walk's own
+ * scatter-gather test on the same outward-rounded float boxes, applied to super-sets of the boxes it compares,
+ * hence a super-set of every candidate the slice's cohorts can find.                                        */
+#define SLICE_COVER_MAX 64
+struct SliceCover { int n; int node[SLICE_COVER_MAX]; };
+
+template <int NDIM>
+__global__ void needed_cohorts_kernel(TreeDev tree, DevParams dp, int cohort_level, SliceCover cov, uint8_t* __restrict__ needed)
+{
+  const int c = blockIdx.x*blockDim.x + threadIdx.x;
+  const int ncohort = 1 << cohort_level;
+  if (c >= ncohort) return;
+  const int node = ncohort - 1 + c;
+  const float4 blo = tree.nodeb[2*(size_t) node], bhi = tree.nodeb[2*(size_t) node + 1];
+  const int first = __float_as_int(blo.w), count = __float_as_int(bhi.w);
+  bool need = false;
+  if (count > 0) {
+    need = !GSPH_RANGE_OUTSIDE_SLICE(dp, first, count);
+    if (!need) {
+      const WalkBox wb(dp);
+      const float4 hlo = tree.nodeh[2*(size_t) node], hhi = tree.nodeh[2*(size_t) node + 1];
+      const float cb0[3] = {blo.x, blo.y, blo.z}, cb1[3] = {bhi.x, bhi.y, bhi.z};
+      const float ch0[3] = {hlo.x, hlo.y, hlo.z}, ch1[3] = {hhi.x, hhi.y, hhi.z};
+      for (int k = 0; k < cov.n && !need; k++) {
+        const int kn = cov.node[k];
+        bool wrapped = false;
+        need = fboxes_overlap<NDIM>(wb, ch0, ch1, tree.nodeb[2*(size_t) kn], tree.nodeb[2*(size_t) kn + 1], wrapped) ||
+               fboxes_overlap<NDIM>(wb, cb0, cb1, tree.nodeh[2*(size_t) kn], tree.nodeh[2*(size_t) kn + 1], wrapped);
+      }
+    }
+  }
+  needed[c] = need ? 1 : 0;
+}
+
+static void slice_cover(int node, int64_t a, int64_t b, int64_t lo, int64_t hi, int level, int stop_level, SliceCover& out, bool& overflow)
+{
+  if (a >= hi || b <= lo || a == b) return;
+  if ((lo <= a && b <= hi) || level == stop_level) {
+    if (out.n < SLICE_COVER_MAX) out.node[out.n++] = node; else overflow = true;
+    return;
+  }
+  const int64_t left = (b - a)/2;                       /* node sizes N -> (N/2, N - N/2), KDTree.cpp:545-560 */
+  slice_cover(2*node + 1, a, a + left, lo, hi, level + 1, stop_level, out, overflow);
+  slice_cover(2*node + 2, a + left, b, lo, hi, level + 1, stop_level, out, overflow);
 }
 
 #define REC_STRIDE 9      /* double2 units per staged record: 144 B, conflict-free for 16-byte accesses */
@@ -275,7 +348,7 @@ hydro_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict__ 
     if (c >= ncohort) break;
     const int node = ncohort - 1 + c;
     const int cfirst = tree.first[node], ccount = tree.count[node];
-    if (ccount == 0 || tree.nactive[node] == 0 || done[c]) continue;
+    if (ccount == 0 || tree.nactive[node] == 0 || done[c] || GSPH_RANGE_OUTSIDE_SLICE(dp, cfirst, ccount)) continue;
 
     /* ---- walk ---------------------------------------------------------------------------------*/
     CandList cl{cand, cand_cap, 0, st};
@@ -310,7 +383,7 @@ hydro_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict__ 
     for (int t0 = 0; t0 < ccount; t0 += 32) {
       Target g;
       const int ti = cfirst + t0 + lane;
-      bool live = t0 + lane < ccount;
+      bool live = t0 + lane < ccount && GSPH_IN_SLICE(dp, ti);
       if (live) {
         const unsigned fl = (unsigned) P.i[I_FLAGS][ti];
         live = (fl & GSPH_FLAG_ACTIVE) && !(fl & GSPH_FLAG_DEAD);
@@ -610,7 +683,26 @@ int launch_hydro_m(gsph_handle* h)
   for (int k = 0; k < NF_INT; k++) P.i[k] = h->PI[k];
   const int N = (int) h->N;
   const int aux_is_alpha = (h->dp.avisc == GSPH_AVISC_MON97MM97 || h->dp.avisc == GSPH_AVISC_MON97CD2010) ? 1 : 0;
-  pack_force_kernel<NDIM><<<(N + 255)/256, 256, 0, h->stream>>>(N, P, aux_is_alpha, h->frec, h->geoh);
+  bool packed = false;
+  if (h->slice_mode && !h->dp.any_mirror) {
+    /* multi-GPU: records only where a neighbour of this device's slice can live */
+    SliceCover cov; cov.n = 0; bool overflow = false;
+    slice_cover(0, 0, h->N, h->dp.slice_lo, h->dp.slice_hi, 0, Lc, cov, overflow);
+    if (!overflow && cov.n > 0) {
+      if ((size_t) ncohort > h->needed_cap) {
+        if (h->needed) cudaFree(h->needed);
+        h->needed = nullptr; h->needed_cap = 0;
+        CUDA_TRY(h, cudaMalloc(&h->needed, (size_t) ncohort));
+        h->needed_cap = (size_t) ncohort;
+      }
+      needed_cohorts_kernel<NDIM><<<(ncohort + 255)/256, 256, 0, h->stream>>>(h->tree, h->dp, Lc, cov, h->needed);
+      pack_force_needed_kernel<NDIM><<<(int)(((size_t) ncohort*32 + 255)/256), 256, 0, h->stream>>>(h->tree, Lc, h->needed, P, aux_is_alpha,
+                                                                                               h->frec, h->geoh);
+      h->stats.kernel_launches++;
+      packed = true;
+    }
+  }
+  if (!packed) pack_force_kernel<NDIM><<<(N + 255)/256, 256, 0, h->stream>>>(N, P, aux_is_alpha, h->frec, h->geoh);
   KernelTimer kt(h, 1);
   kern<<<blocks, HYD_THREADS, smem, h->stream>>>(P, h->tree, h->dp, h->tables, (const double2*) h->frec,
                                                  (const double2*) h->geoh, aux_is_alpha, Lc, h->work_counter, h->cand,
@@ -697,7 +789,7 @@ __global__ void star_forces_kernel(int N, PartView P, DevParams dp, const double
                                    const double* __restrict__ stars, int Nstar)
 {
   const int i = blockIdx.x*blockDim.x + threadIdx.x;
-  if (i >= N) return;
+  if (i >= N || !GSPH_IN_SLICE(dp, i)) return;
   const unsigned fl = (unsigned) P.i[I_FLAGS][i];
   if (!(fl & GSPH_FLAG_ACTIVE) || (fl & GSPH_FLAG_DEAD)) return;
   const KernelEval<KERN, NDIM, TAB> K(dp, gtables);

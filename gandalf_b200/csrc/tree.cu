@@ -83,16 +83,25 @@ __global__ void iota_kernel(int N, int* a)
   if (i < N) a[i] = i;
 }
 
-/* ---- permute all particle fields from host order into tree order -------------------------------*/
-__global__ void gather_kernel(int N, const int32_t* perm, PartView Hh, PartView Pp)
+/* ---- permute particle fields from host order into tree order: the fields of dmask / imask are
+ *      permuted, those of dfill / ifill (absent on the host: all particles hold the default) are set --*/
+struct FillVals { double d[NF_DOUBLE]; int i[NF_INT]; };
+__global__ void gather_kernel(int N, const int32_t* perm, PartView Hh, PartView Pp, unsigned long long dmask,
+                              unsigned imask, unsigned long long dfill, unsigned ifill, FillVals fv)
 {
   const int p = blockIdx.x*blockDim.x + threadIdx.x;
   if (p >= N) return;
   const int i = perm[p];
 #pragma unroll 4
-  for (int f = 0; f < NF_DOUBLE; f++) Pp.f[f][p] = Hh.f[f][i];
+  for (int f = 0; f < NF_DOUBLE; f++) {
+    if ((dmask >> f) & 1ull) Pp.f[f][p] = Hh.f[f][i];
+    else if ((dfill >> f) & 1ull) Pp.f[f][p] = fv.d[f];
+  }
 #pragma unroll
-  for (int f = 0; f < NF_INT; f++) Pp.i[f][p] = Hh.i[f][i];
+  for (int f = 0; f < NF_INT; f++) {
+    if ((imask >> f) & 1u) Pp.i[f][p] = Hh.i[f][i];
+    else if ((ifill >> f) & 1u) Pp.i[f][p] = fv.i[f];
+  }
 }
 
 /* packed (x, y, z, m) records for the density gather phase; dead particles get m = 0 */
@@ -436,8 +445,7 @@ int build_tree_nd(gsph_handle* h, int mode, double dt)
     if (!h->have_tree) { h->err = "gsph_build_tree(extrapolate) before the first rebuild"; return GSPH_ESTATE; }
     if (!h->sorted_valid) {
       cudaStreamWaitEvent(s, h->ev_all, 0);      /* every uploaded field has landed */
-  gather_kernel<<<(N + 255)/256, 256, 0, s>>>(N, h->perm, Hh, Pp);
-      h->sorted_valid = true; h->stats.kernel_launches++;
+      { const int rg = gsph_gather_fields(h); if (rg) return rg; }
     }
     extrapolate_kernel<NDIM><<<(h->tree.ncell + 255)/256, 256, 0, s>>>(h->tree, dt);
     pack_nodes_kernel<NDIM><<<(h->tree.ncell + 255)/256, 256, 0, s>>>(h->tree, 1, h->dp.kernrange, h->dp.gravity_mac, h->dp.macerror);
@@ -448,8 +456,7 @@ int build_tree_nd(gsph_handle* h, int mode, double dt)
   if (mode == 1 || mode == 3) {                      /* restock: KDTree::StockTree (3: keep amin / macfactor) */
     if (!h->have_tree) { h->err = "gsph_build_tree(restock) before the first rebuild"; return GSPH_ESTATE; }
     cudaStreamWaitEvent(s, h->ev_all, 0);      /* every uploaded field has landed */
-  gather_kernel<<<(N + 255)/256, 256, 0, s>>>(N, h->perm, Hh, Pp);
-    h->sorted_valid = true; h->stats.kernel_launches++;
+    { const int rg = gsph_gather_fields(h); if (rg) return rg; }
     return stock_tree<NDIM>(h, mode == 3 ? 2 : 1);
   }
 
@@ -770,9 +777,7 @@ int build_tree_v2(gsph_handle* h, int phase, int shard_rank, int shard_world)
     cudaStream_t s2 = h->stream;
     cudaEventRecord(h->evk[4][0], s2);
     cudaStreamWaitEvent(s2, h->ev_all, 0);      /* every uploaded field has landed */
-    gather_kernel<<<(N + 255)/256, 256, 0, s2>>>(N, h->perm, view_of(h->H, h->HI), view_of(h->P, h->PI));
-    h->stats.kernel_launches++;
-    h->sorted_valid = true;
+    { const int rg = gsph_gather_fields(h); if (rg) return rg; }
     h->have_tree = true;
     cudaEventRecord(h->evk[4][1], s2); h->evk_used[4] = true;
     cudaEventRecord(h->evk[5][0], s2);
@@ -1024,9 +1029,7 @@ int build_tree_v2(gsph_handle* h, int phase, int shard_rank, int shard_world)
   }
   CUDA_TRY(h, cudaMemcpyAsync(h->perm, L.ids[0][cur], sizeof(int)*(size_t) N, cudaMemcpyDeviceToDevice, s));
   cudaStreamWaitEvent(s, h->ev_all, 0);      /* every uploaded field has landed */
-  gather_kernel<<<(N + 255)/256, 256, 0, s>>>(N, h->perm, Hh, Pp);
-  h->stats.kernel_launches++;
-  h->sorted_valid = true;
+  { const int rg = gsph_gather_fields(h); if (rg) return rg; }
   h->have_tree = true;
   cudaEventRecord(h->evk[4][1], s); h->evk_used[4] = true;
   cudaEventRecord(h->evk[5][0], s);
@@ -1036,6 +1039,56 @@ int build_tree_v2(gsph_handle* h, int phase, int shard_rank, int shard_world)
 }
 
 }  // namespace
+
+/* Host order -> tree order.  When every particle is active and alive in this step (no flags from the
+ * host, or the device-resident loop with one global time step) the passes overwrite their outputs for
+ * every particle, so only the INPUTS of the step are permuted: r, v, m, h, u, alpha, level, sinkid, the
+ * MAC / switch inputs of the previous step where the configuration reads them, and accumulators the
+ * host supplied.  Otherwise (block time steps, dead particles) every field is permuted, because the
+ * old values of inactive particles are inputs.                                                       */
+int gsph_gather_fields(gsph_handle* h)
+{
+  const int N = (int) h->N;
+  const int nd = h->dp.ndim;
+  /* inside a step of the resident loop every particle was just made active (one global time step); a
+     BuildTree between steps sees the flags EndTimestep left (inactive): everything is permuted then */
+  const bool integ = h->integ.on && h->integ.mid_step;
+  const unsigned long long ALLD = (1ull << NF_DOUBLE) - 1ull; const unsigned ALLI = (1u << NF_INT) - 1u;
+  unsigned long long dmask, dfill = 0ull; unsigned imask, ifill = 0u;
+  h->lazy_fields = integ || (!h->integ.on && !((h->present_i >> I_FLAGS) & 1u));
+  if (!h->lazy_fields) { dmask = ALLD; imask = ALLI; }
+  else {
+    unsigned long long core = GSPH_DMASK(F_M) | GSPH_DMASK(F_H) | GSPH_DMASK(F_U) | GSPH_DMASK(F_ALPHA);
+    for (int k = 0; k < nd; k++) core |= GSPH_DMASK(F_RX + k) | GSPH_DMASK(F_VX + k);
+    if (h->dp.tdavisc == GSPH_TDAVISC_MM97) core |= GSPH_DMASK(F_DALPHADT);          /* accumulated across steps */
+    if (h->dp.tdavisc == GSPH_TDAVISC_CD2010) for (int k = 0; k < nd; k++) core |= GSPH_DMASK(F_AX + k);
+    if (h->dp.self_gravity && h->dp.gravity_mac != GSPH_MAC_GEOMETRIC) {              /* KDTree.cpp:899-903 */
+      core |= GSPH_DMASK(F_GPOT);
+      for (int k = 0; k < nd; k++) core |= GSPH_DMASK(F_ATX + k);
+    }
+    if (h->dp.create_sinks) core |= GSPH_DMASK(F_GPOT);                               /* potmin test, GradhSph.cpp:270-280 */
+    unsigned icore = (1u << I_FLAGS) | (1u << I_LEVEL) | (1u << I_SINKID) | (1u << I_PTYPE);
+    /* accumulators: the force passes add to them; what the host supplied counts (the resident loop always
+       zeroes them, gsph_zero_accelerations) */
+    unsigned long long acc = 0ull; unsigned iacc = 0u;
+    if (!integ) {
+      acc = GSPH_OUT_FORCES & h->present_d; iacc = (1u << I_LEVELNEIB) & h->present_i;
+    }
+    const unsigned long long pres_d = integ ? ALLD : h->present_d; const unsigned pres_i = integ ? ALLI : h->present_i;
+    dmask = (core | acc) & pres_d; imask = (icore | iacc) & pres_i;
+    dfill = core & ~pres_d; ifill = icore & ~pres_i;
+  }
+  FillVals fv;
+  for (int f = 0; f < NF_DOUBLE; f++) fv.d[f] = (f == F_H || f == F_INVOMEGA) ? 1.0 : 0.0;
+  for (int f = 0; f < NF_INT; f++) fv.i[f] = f == I_FLAGS ? (int) GSPH_FLAG_ACTIVE : ((f == I_SINKID || f == I_IORIG) ? -1 : 0);
+  gather_kernel<<<(N + 255)/256, 256, 0, h->stream>>>(N, h->perm, view_of(h->H, h->HI), view_of(h->P, h->PI),
+                                                     dmask, imask, dfill, ifill, fv);
+  h->stats.kernel_launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  h->pvalid_d = dmask | dfill; h->pvalid_i = imask | ifill;
+  h->sorted_valid = true; h->acc_zeroed = false;
+  return GSPH_OK;
+}
 
 int gsph_pack_geo4(gsph_handle* h)
 {

@@ -241,8 +241,12 @@ int gsph_timer_stop(gsph_handle* h, float* ms);
  * the top log2(R) levels of the balanced KD-tree are exactly its median splits -- and the one
  * exchange step per pass (post-density fields of the other slices) is an NCCL all-gather issued by
  * the host layer on the device arrays exposed below.
- *   gsph_set_active_slice : particles at tree positions [lo, hi) become the active targets, all
- *                           others stay sources only (replaces the rank-ownership test).
+ *   gsph_set_active_slice : particles at tree positions [lo, hi) become the targets of this device, all
+ *                           others stay sources only (replaces the rank-ownership test).  No flag is
+ *                           rewritten: the kernels test the range.  Result arrays are written inside
+ *                           [lo, hi) only; outside they hold what the last exchange (or allocation: zeros)
+ *                           left there.  The force records of the force pass are packed only for the cohort
+ *                           nodes that can hold a neighbour of the slice.  Cleared by the next gsph_upload.
  *   gsph_derive_density_fields : after the exchange of h, rho, invomega, zeta: hrangesqd, hfactor, u,
  *                           sound, pressure of the particles OUTSIDE [lo, hi) are recomputed from them
  *                           exactly as the density pass stores them (4 instead of 9 arrays cross NVLink).
