@@ -533,6 +533,8 @@ void gsph_destroy(gsph_handle* h)
   if (h->ev_compute) cudaEventDestroy(h->ev_compute);
   for (int k = 0; k < 3; k++) if (h->ev_axis[k]) cudaEventDestroy(h->ev_axis[k]);
   fre(h->tree.nodeb); fre(h->tree.nodeh); fre(h->tree.gnode); fre(h->tree.mnode);
+  for (int k = 0; k < 5; k++) if (h->ev_grav[k]) cudaEventDestroy(h->ev_grav[k]);
+  if (h->aux_stream) cudaStreamDestroy(h->aux_stream);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -959,7 +961,7 @@ static int run_with_regrow(gsph_handle* h, const char* where, int (*pass)(gsph_h
 
 static int pass_density(gsph_handle* h, int) { return gsph_run_density(h); }
 static int pass_hydro(gsph_handle* h, int g) { return gsph_run_hydro(h, g); }
-static int pass_gravity(gsph_handle* h, int) { return gsph_run_gravity(h); }
+static int pass_gravity(gsph_handle* h, int) { return gsph_run_gravity(h, 0); }
 int gsph_prepare_done_flags(gsph_handle* h)
 {
   const size_t need = (size_t) 1 << h->tree.ltot;
@@ -1203,7 +1205,20 @@ int gsph_update_all_forces_finish(gsph_handle* h)
   Timer tm(h, &h->stats.ms_forces);
   int rc = gsph_prepare_done_flags(h); if (rc) return rc;
   h->gstack_on = false;                               /* first launch: shared-memory stacks */
-  rc = run_with_regrow(h, "gsph_update_all_forces(gravity)", pass_gravity, 0);
+  /* first the decoupled walk / consume kernels; the fused kernel then finishes what they left (cohorts whose
+     lists or walk stacks outgrew their slots), with its own retry ladder.  GSPH_GRAV_FUSED=1: fused only. */
+  const char* fused_only = getenv("GSPH_GRAV_FUSED");
+  bool need_fused = fused_only && atoi(fused_only) != 0;
+  if (!need_fused) {
+    rc = gsph_run_gravity(h, 1); if (rc) return rc;
+    rc = fetch_status(h); if (rc) return rc;
+    need_fused = h->status_host->grav_left != 0;
+    if (getenv("GSPH_DEBUG"))
+      fprintf(stderr, "gsph: decoupled gravity pass left %d cohorts to the fused kernel; longest lists %d cells, %d direct leaves, deepest stack %d\n",
+              h->status_host->grav_left, h->status_host->grav_cell_max, h->status_host->grav_dir_max, h->status_host->grav_stack_max);
+  }
+  if (need_fused) rc = run_with_regrow(h, "gsph_update_all_forces(gravity)", pass_gravity, 0);
+  else rc = gsph_check_status(h, "gsph_update_all_forces(gravity)");
   if (rc) return rc;
   rc = gsph_run_star_forces(h);                       /* GradhSphTree.cpp:600-607 */
   if (rc) return rc;

@@ -66,7 +66,8 @@ struct TreeDev {
   float4* nodeh = nullptr;
   /* exact double-precision node records of the gravity walk (one 64-byte line / one 32-byte sector
      per node instead of seven / four separate arrays):
-       gnode[4n..4n+3] = (rcell.x, rcell.y) (rcell.z, rmax) (cdistsqd, kernrange*hmax) (count, mac)
+       gnode[4n..4n+3] = (rcell.x, rcell.y) (rcell.z, rmax) (cdistsqd, kernrange*hmax) (count:first, mac)
+                         count:first = the two int32 halves of one double (high: count, low: first)
                          mac = rmax^2*m for gadget2, TreeCell::mac for eigenmac (Tree.h:413-432)
        mnode[2n..2n+1] = (com.x, com.y) (com.z, m)                                               */
   double2* gnode = nullptr;
@@ -110,6 +111,8 @@ struct DevStatus {
   int ngb_max;
   unsigned long long hiter_sum, ngb_sum, cand_sum, ntarget, ndirect_sum, ncell_sum, nleaf_grav;
   unsigned long long cand_need;   /* largest candidate count requested */
+  int grav_left;             /* cohorts the decoupled gravity pass left to the fused kernel */
+  int grav_cell_max, grav_dir_max, grav_stack_max;   /* longest interaction lists / deepest walk stack of a cohort (decoupled gravity pass) */
 };
 
 /* device-resident main loop (gsph_integrator_*): start-of-step copies in host order */
@@ -188,7 +191,9 @@ struct gsph_handle {
   void* scratch = nullptr; size_t scratch_bytes = 0;          /* tree build temporaries          */
   int32_t* cand = nullptr; size_t cand_cap_per_warp = 0; int cand_warps = 0;
   int32_t* nlist = nullptr; size_t nlist_cap = 0; int nlist_warps = 0;   /* per warp: [cap][32] neighbour ids */
-  int32_t* gravlist = nullptr; size_t grav_cap_cells = 0, grav_cap_direct = 0; int grav_warps = 0;
+  void* gravlist = nullptr; size_t gravlist_bytes = 0;   /* interaction lists of the decoupled gravity pass (two batches) */
+  cudaStream_t aux_stream = nullptr;                      /* the walk kernels of the decoupled gravity pass */
+  cudaEvent_t ev_grav[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   /* walked[2], consumed[2], fork */
   bool gstack_on = false;        /* this launch is a retry with the stacks in HBM */
   int2* gstack = nullptr; size_t gstack_cap = 0; int gstack_warps = 0;   /* gravity walk stacks in HBM: only after a
                                                                             shared-memory stack overflowed */
@@ -221,7 +226,7 @@ int gsph_derive_density_fields_impl(gsph_handle* h, int lo, int hi);   /* densit
 int gsph_run_density(gsph_handle* h);                                 /* density.cu */
 int gsph_run_hydro(gsph_handle* h, int with_gravity);                 /* hydro.cu   */
 int gsph_run_neiblist(gsph_handle* h, int32_t* counts_dev, const int64_t* offsets_dev, int32_t* idx_dev);
-int gsph_run_gravity(gsph_handle* h);                                 /* gravity.cu */
+int gsph_run_gravity(gsph_handle* h, int decoupled);                  /* gravity.cu */
 int gsph_run_star_forces(gsph_handle* h);
 int gsph_run_star_gas(gsph_handle* h, const double* dstars, int Nstar, double* dout, int* dcounts, int* derr);   /* hydro.cu */                             /* hydro.cu   */
 int gsph_check_status(gsph_handle* h, const char* where);             /* capi.cu    */

@@ -328,7 +328,8 @@ __global__ void pack_nodes_kernel(TreeDev T, int with_bb, double kernrange, int 
         else lambda = fabs(q0);
         mac = pow(0.5*lambda/macerror, 0.66666666666666);
       }
-      T.gnode[4*(size_t) n + 3] = make_double2((double) cnt, mac);
+      /* (first, count) travel as the two 32-bit halves of one double: never used in arithmetic */
+      T.gnode[4*(size_t) n + 3] = make_double2(__hiloint2double(cnt, T.first[n]), mac);
       T.mnode[2*(size_t) n] = make_double2(T.com[0][n], NDIM > 1 ? T.com[1][n] : 0.0);
       T.mnode[2*(size_t) n + 1] = make_double2(NDIM > 2 ? T.com[2][n] : 0.0, T.m[n]);
     }

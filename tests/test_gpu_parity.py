@@ -466,8 +466,10 @@ def test_star_gravity_vs_oracle(grav, tab):
 
 
 def test_gravity_walk_stack_overflow_retries_in_hbm(monkeypatch):
-    """a gravity walk that outgrows its shared-memory stack is redone with the stack in HBM: same
-    traversal, bit-identical forces (GSPH_TEST_GRAV_STACK shrinks the shared stack to force the retry)."""
+    """a gravity walk that outgrows its shared-memory stack is left to the fused kernel and redone there with the
+    stack in HBM: same traversal and interaction lists, forces equal up to the summation order of the two kernels
+    (GSPH_TEST_GRAV_STACK shrinks the shared stacks to force the retry).  The fused kernel alone
+    (GSPH_GRAV_FUSED=1) gives the same bits with shared-memory and HBM stacks."""
     import gandalf_b200 as g
     rng = np.random.default_rng(21)
     N = 30000
@@ -477,11 +479,12 @@ def test_gravity_walk_stack_overflow_retries_in_hbm(monkeypatch):
     v = np.zeros((N, 3)); m = np.full(N, 1.0/N); u = np.full(N, 0.05); h = np.full(N, 0.07)
     params = {"ndim": 3, "self_gravity": 1, "multipole": "fast_monopole", "thetamaxsqd": 0.15}
     res = []
-    for cap in (None, "40"):
-        if cap is None:
-            monkeypatch.delenv("GSPH_TEST_GRAV_STACK", raising=False)
-        else:
-            monkeypatch.setenv("GSPH_TEST_GRAV_STACK", cap)
+    for cap, fused in ((None, None), ("40", None), (None, "1"), ("40", "1")):
+        for name, val in (("GSPH_TEST_GRAV_STACK", cap), ("GSPH_GRAV_FUSED", fused)):
+            if val is None:
+                monkeypatch.delenv(name, raising=False)
+            else:
+                monkeypatch.setenv(name, val)
         ps = g.ParticleSet(N, 3).set(r=r, v=v, m=m, h=h, u=u)
         tree = g.GpuSphTree(params)
         tree.BuildTree(True, 0, 1, 1, 0.0, ps)
@@ -490,7 +493,40 @@ def test_gravity_walk_stack_overflow_retries_in_hbm(monkeypatch):
         res.append({k: ps[k].copy() for k in ("a", "atree", "gpot")})
         tree.close()
     for k in res[0]:
-        assert np.array_equal(res[0][k], res[1][k]), k
+        assert np.array_equal(res[2][k], res[3][k]), k                 # fused kernel: shared vs HBM stacks
+        assert np.array_equal(res[1][k], res[3][k]), k                 # every cohort was left to the fused kernel
+        scale = np.abs(res[0][k]).max()
+        assert np.abs(res[0][k] - res[2][k]).max() < 1e-13*scale, k    # decoupled vs fused: summation order only
+
+
+def test_gravity_list_overflow_falls_back_to_the_fused_kernel(monkeypatch):
+    """cohorts whose interaction lists outgrow their slots in the decoupled pass are finished by the fused kernel"""
+    import gandalf_b200 as g
+    rng = np.random.default_rng(22)
+    N = 20000
+    r = rng.uniform(-1, 1, (N, 3)); r = r[np.linalg.norm(r, axis=1) < 1.0]
+    N = len(r)
+    v = np.zeros((N, 3)); m = np.full(N, 1.0/N); u = np.full(N, 0.05); h = np.full(N, 0.1)
+    params = {"ndim": 3, "self_gravity": 1, "multipole": "quadrupole", "thetamaxsqd": 0.15}
+    res = []
+    for cell_cap, list_mb in ((None, None), ("64", None), (None, "1")):
+        for name, val in (("GSPH_GRAV_CELL_CAP", cell_cap), ("GSPH_GRAV_LIST_MB", list_mb)):
+            if val is None:
+                monkeypatch.delenv(name, raising=False)
+            else:
+                monkeypatch.setenv(name, val)
+        ps = g.ParticleSet(N, 3).set(r=r, v=v, m=m, h=h, u=u)
+        tree = g.GpuSphTree(params)
+        tree.BuildTree(True, 0, 1, 1, 0.0, ps)
+        tree.UpdateAllSphProperties(); tree.ZeroAccelerations(); tree.UpdateAllSphForces()
+        tree.Download(ps)
+        res.append({k: ps[k].copy() for k in ("a", "atree", "gpot")})
+        assert tree.Stats().ncell_mean > 0
+        tree.close()
+    for k in res[0]:
+        scale = np.abs(res[0][k]).max()
+        assert np.abs(res[0][k] - res[1][k]).max() < 1e-13*scale, k    # tiny slots: mostly the fused kernel
+        assert np.array_equal(res[0][k], res[2][k]), k                 # many small batches: same kernels, same bits
 
 
 @pytest.mark.parametrize("ndim,n,walls", [
