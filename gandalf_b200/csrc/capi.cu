@@ -271,6 +271,57 @@ int gsph_ensure_cand(gsph_handle* h, int warps, size_t cap_per_warp)
   return GSPH_OK;
 }
 
+/* cohort range [c_lo, c_hi) of `level` that can hold targets of this device: all of them, or (multi-GPU) those
+   meeting the tree-order slice -- from the data-independent topology of the balanced tree */
+static void cohort_range(const gsph_handle* h, int level, int& c_lo, int& c_hi)
+{
+  const int ncohort = 1 << level;
+  c_lo = 0; c_hi = ncohort;
+  if (!h->slice_mode) return;
+  auto range = [&](int k, int64_t& a, int64_t& b) {
+    a = 0; b = h->N;
+    for (int bit = level - 1; bit >= 0; bit--) { const int64_t left = (b - a)/2; if ((k >> bit) & 1) a += left; else b = a + left; }
+  };
+  int lo = 0, hi = ncohort;
+  while (lo < hi) { const int mid = (lo + hi)/2; int64_t a, b; range(mid, a, b); if (b <= h->dp.slice_lo) lo = mid + 1; else hi = mid; }
+  c_lo = lo; hi = ncohort;
+  while (lo < hi) { const int mid = (lo + hi)/2; int64_t a, b; range(mid, a, b); if (a < h->dp.slice_hi) lo = mid + 1; else hi = mid; }
+  c_hi = lo;
+}
+
+/* Buffers of the pre-walk kernels for the cohorts of this device.  GSPH_PREWALK=0 disables them (the main kernels
+   walk themselves), GSPH_PREWALK_CAP = candidate ids per cohort, GSPH_PREWALK_MB = memory budget.            */
+int gsph_prewalk_prepare(gsph_handle* h, int cohort_level)
+{
+  h->pre_n = 0;
+  const char* e0 = getenv("GSPH_PREWALK");
+  if (e0 && atoi(e0) == 0) return GSPH_OK;
+  int c_lo, c_hi;
+  cohort_range(h, cohort_level, c_lo, c_hi);
+  const int n = c_hi - c_lo;
+  if (n <= 0) return GSPH_OK;
+  const char* e1 = getenv("GSPH_PREWALK_CAP"); const char* e2 = getenv("GSPH_PREWALK_MB");
+  size_t cap = e1 ? (size_t) std::max(64, atoi(e1)) : (h->cfg.kernel == GSPH_KERNEL_M4 ? 2048 : 4096);
+  const size_t budget = (e2 ? (size_t) atol(e2) : (size_t) 24576) << 20;
+  while (cap > 512 && (size_t) n*cap*sizeof(int32_t) > budget) cap /= 2;
+  if ((size_t) n*cap*sizeof(int32_t) > budget) return GSPH_OK;           /* too many cohorts: in-kernel walks */
+  const size_t need = (size_t) n*cap*sizeof(int32_t);
+  if (need > h->pre_bytes) {
+    if (h->pre_cand) cudaFree(h->pre_cand);
+    h->pre_cand = nullptr; h->pre_bytes = 0;
+    if (cudaMalloc(&h->pre_cand, need) != cudaSuccess) { cudaGetLastError(); return GSPH_OK; }   /* no room: in-kernel walks */
+    h->pre_bytes = need;
+  }
+  if ((size_t) n > h->pre_count_cap) {
+    if (h->pre_count) cudaFree(h->pre_count);
+    h->pre_count = nullptr; h->pre_count_cap = 0;
+    CUDA_TRY(h, cudaMalloc(&h->pre_count, (size_t) n*sizeof(int)));
+    h->pre_count_cap = (size_t) n;
+  }
+  h->pre_c0 = c_lo; h->pre_n = n; h->pre_cap = (int) cap;
+  return GSPH_OK;
+}
+
 int gsph_ensure_nlist(gsph_handle* h, int warps, size_t cap)
 {
   if (cap == 0) cap = h->nlist_cap;
@@ -517,7 +568,7 @@ void gsph_destroy(gsph_handle* h)
   for (int f = 0; f < NF_DOUBLE; f++) { fre(h->H[f]); fre(h->P[f]); }
   for (int f = 0; f < NF_INT; f++) { fre(h->HI[f]); fre(h->PI[f]); }
   for (int k = 0; k < 11; k++) fre(h->integ.s0[k]);
-  fre(h->integ.red); fre(h->perm); fre(h->tables); fre(h->scratch); fre(h->cand); fre(h->gravlist); fre(h->status); fre(h->work_counter); fre(h->done); fre(h->needed); fre(h->geo4); fre(h->geoh); fre(h->frec); fre(h->nlist); fre(h->hnew); fre(h->stars); fre(h->gstack);
+  fre(h->integ.red); fre(h->perm); fre(h->tables); fre(h->scratch); fre(h->cand); fre(h->gravlist); fre(h->status); fre(h->work_counter); fre(h->done); fre(h->needed); fre(h->pre_cand); fre(h->pre_count); fre(h->geo4); fre(h->geoh); fre(h->frec); fre(h->nlist); fre(h->hnew); fre(h->stars); fre(h->gstack);
   TreeDev& T = h->tree;
   fre(T.first); fre(T.count); fre(T.nactive); fre(T.m); fre(T.rmax); fre(T.hmax); fre(T.cdistsqd);
   for (int k = 0; k < 3; k++) { fre(T.bbmin[k]); fre(T.bbmax[k]); fre(T.hbmin[k]); fre(T.hbmax[k]); fre(T.rcell[k]); fre(T.com[k]); fre(T.vcom[k]); }

@@ -44,6 +44,75 @@ struct GatherVisitorF {
   __device__ __forceinline__ bool emit(bool take, int lane) { return cand_append_range(cl, first, count, take, lane, tag); }
 };
 
+/* the gather walk(s) of one cohort: its box grown by R, once per image code (mirror walls: the search box is
+   reflected instead of the tree); candidates are appended to cl */
+template <int NDIM, bool MIRROR>
+__device__ __forceinline__ bool density_cohort_walk(const TreeDev& tree, const DevParams& dp, const WalkBox& wbx, CandList& cl,
+                                                    int* stack, const double (&cmin)[3], const double (&cmax)[3], double R,
+                                                    DevStatus* st)
+{
+  GatherVisitorF<NDIM> V{tree.nodeb, wbx, cl, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, 0, 0, 0};
+  bool walk_ok = true;
+  for (int code = 0; code < (MIRROR ? dp.nimg : 1) && walk_ok; code++) {
+    const ImageOp op = image_op<NDIM>(dp, code);
+    bool reach = true;
+#pragma unroll
+    for (int k = 0; k < NDIM; k++) {
+      double lo = cmin[k] - R, hi = cmax[k] + R;
+      if (op.refl[k]) {
+        /* the image lies beyond the wall: only needed if the search box crosses that wall */
+        const double w = 0.5*op.wall2[k];
+        if (!(lo < w && hi > w) && !(lo <= w && hi >= w)) reach = false;
+        const double l2 = op.wall2[k] - hi, h2 = op.wall2[k] - lo;
+        lo = l2; hi = h2;
+      }
+      V.smin[k] = __double2float_rd(lo); V.smax[k] = __double2float_ru(hi);
+    }
+    if (!reach) continue;
+    V.tag = code << IMG_SHIFT;
+    __syncwarp();
+    walk_ok = warp_walk_f<NB_WALK_STACK>(tree.ltot, stack, V, st);
+  }
+  return walk_ok;
+}
+
+/* Pre-walk (see hydro_walk_kernel): the gather walks of the first attempt of every cohort in a lean kernel of
+   their own.  Search radius = kernrange * 1.05 * hmax of the cohort node, which is the largest first-attempt
+   radius of its leaves (GradhSphTree.cpp:154); a cohort with inactive particles may get a few candidates more
+   than density_kernel would collect -- the list only has to be a superset.                                   */
+template <int NDIM, bool MIRROR>
+__global__ void __launch_bounds__(DENS_THREADS)
+density_walk_kernel(TreeDev tree, DevParams dp, int cohort_level, int c0, int nc, int* work_counter,
+                    int32_t* __restrict__ pre_cand, int pre_cap, int* __restrict__ pre_count, const uint8_t* __restrict__ done)
+{
+  __shared__ int stacks[DENS_WARPS][NB_WALK_STACK];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const WalkBox wbx(dp);
+  const int ncohort = 1 << cohort_level;
+  while (true) {
+    int b = 0;
+    if (lane == 0) b = atomicAdd(work_counter, 1);
+    b = __shfl_sync(FULLMASK, b, 0);
+    if (b >= nc) break;
+    const int c = c0 + b;
+    const int node = ncohort - 1 + c;
+    const int cfirst = tree.first[node], ccount = tree.count[node];
+    if (ccount == 0 || ccount > 32 || tree.nactive[node] == 0 || done[c] || GSPH_RANGE_OUTSIDE_SLICE(dp, cfirst, ccount)) {
+      if (lane == 0) pre_count[b] = -1;
+      continue;
+    }
+    double cmin[3] = {0, 0, 0}, cmax[3] = {0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < NDIM; k++) { cmin[k] = tree.bbmin[k][node]; cmax[k] = tree.bbmax[k][node]; }
+    const double hmax = 1.05*tree.hmax[node];
+    const double R = dp.kernrange*hmax;
+    CandList cl{pre_cand + (size_t) b*pre_cap, pre_cap, 0, nullptr, true};
+    const bool ok = density_cohort_walk<NDIM, MIRROR>(tree, dp, wbx, cl, stacks[warp], cmin, cmax, R, nullptr);
+    __syncwarp();
+    if (lane == 0) pre_count[b] = ok ? cl.n : -1;
+  }
+}
+
 /* EOS: src/Headers/EOS.h:156, src/Thermal/{Adiabatic,Isothermal,Barotropic}EOS.cpp */
 __device__ __forceinline__ void thermal(const DevParams& dp, double rho, double& u, double& sound,
                                         double& press)
@@ -209,7 +278,8 @@ __global__ void __launch_bounds__(DENS_THREADS, CD2010 ? 2 : 3)
 density_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict__ gtables,
                const double2* __restrict__ geo4, int cohort_level, int* work_counter,
                int32_t* cand_all, int cand_cap, int32_t* nlist_all, int nlist_cap, DevStatus* st,
-               uint8_t* done, double* __restrict__ hnew)
+               uint8_t* done, double* __restrict__ hnew,
+               const int32_t* __restrict__ pre_cand, int pre_cap, const int* __restrict__ pre_count, int pre_c0, int pre_n)
 {
   extern __shared__ double smem[];
   double* tab = smem;                                          /* 3 x 1000 (tabulated only) */
@@ -226,7 +296,7 @@ density_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict_
   const int warp = threadIdx.x >> 5;
   const WalkBox wbx(dp);
   const int gwarp = blockIdx.x*DENS_WARPS + warp;
-  int32_t* cand = cand_all + (size_t) gwarp*cand_cap;
+  int32_t* const mycand = cand_all + (size_t) gwarp*cand_cap;
   int32_t* nlist = nlist_all + (size_t) gwarp*nlist_cap*32;
   const KernelEval<KERN, NDIM, TAB> K(dp, tab);
   const int ncohort = 1 << cohort_level;
@@ -283,9 +353,8 @@ density_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict_
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) hmax = fmax(hmax, __shfl_xor_sync(FULLMASK, hmax, o));
         if (!(hmax > 0.0)) break;                              /* every lane is finished */
-        /* ---- walk: candidates whose leaf overlaps the grown cohort box --------------------------*/
-        CandList cl{cand, cand_cap, 0, st};
-        GatherVisitorF<NDIM> V{tree.nodeb, wbx, cl, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, 0, 0, 0};
+        /* ---- candidates whose leaf overlaps the grown cohort box: first attempt from the pre-walk kernel,
+         *      otherwise (no pre-walk, its slot overflowed, or a larger radius is needed) walked here -------*/
         const double R = dp.kernrange*hmax;
         bool crosses = false, wide = false;
 #pragma unroll
@@ -294,30 +363,15 @@ density_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict_
           if (dp.periodic[k] && (lo < dp.boxmin[k] || hi > dp.boxmax[k] || hi - lo > dp.boxhalf[k])) crosses = true;
           if (dp.periodic[k] && 0.5*(hi - lo) >= 0.49*dp.boxsize[k]) wide = true;
         }
-        /* one walk per image code (mirror walls): the search box is reflected instead of the tree */
-        bool walk_ok = true;
-        for (int code = 0; code < (MIRROR ? dp.nimg : 1) && walk_ok; code++) {
-          const ImageOp op = image_op<NDIM>(dp, code);
-          bool reach = true;
-#pragma unroll
-          for (int k = 0; k < NDIM; k++) {
-            double lo = cmin[k] - R, hi = cmax[k] + R;
-            if (op.refl[k]) {
-              /* the image lies beyond the wall: only needed if the search box crosses that wall */
-              const double w = 0.5*op.wall2[k];
-              if (!(lo < w && hi > w) && !(lo <= w && hi >= w)) reach = false;
-              const double l2 = op.wall2[k] - hi, h2 = op.wall2[k] - lo;
-              lo = l2; hi = h2;
-            }
-            V.smin[k] = __double2float_rd(lo); V.smax[k] = __double2float_ru(hi);
-          }
-          if (!reach) continue;
-          V.tag = code << IMG_SHIFT;
-          __syncwarp();
-          walk_ok = warp_walk_f<NB_WALK_STACK>(tree.ltot, stack, V, st);
+        const int32_t* cand = mycand;
+        int ncand = 0;
+        const int pre = (attempt == 0 && t0 == 0 && c >= pre_c0 && c < pre_c0 + pre_n) ? pre_count[c - pre_c0] : -1;
+        if (pre >= 0) { ncand = pre; cand = pre_cand + (size_t)(c - pre_c0)*pre_cap; }
+        else {
+          CandList cl{mycand, cand_cap, 0, st};
+          if (!density_cohort_walk<NDIM, MIRROR>(tree, dp, wbx, cl, stack, cmin, cmax, R, st)) { overflow = true; break; }
+          ncand = cl.n;
         }
-        if (!walk_ok) { overflow = true; break; }
-        const int ncand = cl.n;
 
         /* ---- phase 1: per-lane candidate lists on the FP32 pipe.  The list only has to be a SUPERSET
          *      of the particles inside kernrange*h for every h <= hmax_l (membership is decided in
@@ -588,9 +642,23 @@ int launch_density_m(gsph_handle* h)
   for (int k = 0; k < NF_DOUBLE; k++) P.f[k] = h->P[k];
   for (int k = 0; k < NF_INT; k++) P.i[k] = h->PI[k];
   KernelTimer kt(h, 0);
+  /* the first-attempt walks in their own lean kernel (density_walk_kernel) */
+  rc = gsph_prewalk_prepare(h, Lc);
+  if (rc) return rc;
+  if (h->pre_n > 0) {
+    CUDA_TRY(h, cudaMemsetAsync(h->work_counter + 1, 0, sizeof(int), h->stream));
+    auto wk = density_walk_kernel<NDIM, MIRROR>;
+    int wbps = 0;
+    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wbps, wk, DENS_THREADS, 0));
+    const int wblocks = std::min(h->sm_count*std::max(wbps, 1), (h->pre_n + DENS_WARPS - 1)/DENS_WARPS);
+    wk<<<wblocks, DENS_THREADS, 0, h->stream>>>(h->tree, h->dp, Lc, h->pre_c0, h->pre_n, h->work_counter + 1, h->pre_cand,
+                                                h->pre_cap, h->pre_count, h->done);
+    h->stats.kernel_launches++;
+  }
   kern<<<blocks, DENS_THREADS, smem, h->stream>>>(P, h->tree, h->dp, h->tables, (const double2*) h->geo4, Lc,
                                                   h->work_counter, h->cand, (int) h->cand_cap_per_warp,
-                                                  h->nlist, (int) h->nlist_cap, h->status, h->done, h->hnew);
+                                                  h->nlist, (int) h->nlist_cap, h->status, h->done, h->hnew,
+                                                  h->pre_cand, h->pre_cap, h->pre_count, h->pre_c0, h->pre_n);
   h->stats.kernel_launches++;
   CUDA_TRY(h, cudaGetLastError());
   return GSPH_OK;

@@ -297,6 +297,7 @@ __device__ __forceinline__ bool warp_walk(const TreeDev& T, int* stack, Visitor&
 struct CandList {
   int32_t* list; int cap; int n;
   DevStatus* st;
+  bool quiet = false;        /* overflow is not an error (pre-walk kernels: the cohort is simply left to the main kernel) */
   __device__ __forceinline__ bool append_leaf(const TreeDev& T, int node, bool take, int lane)
   {
     int cnt = 0, first = 0;
@@ -389,7 +390,7 @@ __device__ __forceinline__ bool warp_walk_f(int leaf_level, int* stack, Visitor&
     const unsigned pm = __ballot_sync(FULLMASK, push);
     const int npush = __popc(pm);
     if (sp + 2*npush > STACKCAP) {
-      if (lane == 0) atomicExch(&st->err_stack_overflow, 1);
+      if (lane == 0 && st) atomicExch(&st->err_stack_overflow, 1);
       return false;
     }
     if (push) {
@@ -452,7 +453,7 @@ __device__ __forceinline__ bool cand_append_range(CandList& cl, int first, int c
   const int off = warp_excl_scan(cnt, lane, total);
   if (total == 0) return true;
   if (cl.n + total > cl.cap) {
-    if (lane == 0) { atomicExch(&cl.st->err_cand_overflow, 1); atomicMax(&cl.st->cand_need, (unsigned long long)(cl.n + total)); }
+    if (lane == 0 && !cl.quiet) { atomicExch(&cl.st->err_cand_overflow, 1); atomicMax(&cl.st->cand_need, (unsigned long long)(cl.n + total)); }
     return false;
   }
   for (int i = 0; i < cnt; i++) cl.list[cl.n + off + i] = (first + i) | tag;

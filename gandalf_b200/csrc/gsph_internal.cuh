@@ -201,6 +201,11 @@ struct gsph_handle {
   DevStatus* status_host = nullptr; /* pinned */
   int* work_counter = nullptr;
   uint8_t* done = nullptr; size_t done_cap = 0;   /* per cohort / leaf: finished in this pass */
+  /* candidate lists of the neighbour passes, produced by lean pre-walk kernels (density_walk_kernel,
+     hydro_walk_kernel) for the cohorts [pre_c0, pre_c0 + pre_n): pre_count[b] = candidates of cohort pre_c0 + b
+     (bit 30: a periodic wrap was seen), -1 = the main kernel walks itself; ids at pre_cand + b*pre_cap */
+  int32_t* pre_cand = nullptr; int* pre_count = nullptr; size_t pre_bytes = 0, pre_count_cap = 0;
+  int pre_c0 = 0, pre_n = 0, pre_cap = 0;
   uint8_t* needed = nullptr; size_t needed_cap = 0;   /* per cohort node: may hold a neighbour of this device's slice */
   void* pinned = nullptr; size_t pinned_bytes = 0;             /* host staging for strided views  */
 
@@ -234,6 +239,7 @@ int gsph_ensure_cand(gsph_handle* h, int warps, size_t cap_per_warp);
 int gsph_ensure_nlist(gsph_handle* h, int warps, size_t cap);
 int gsph_pack_geo4(gsph_handle* h);                                   /* tree.cu */
 int gsph_gather_fields(gsph_handle* h);                               /* tree.cu: host order -> tree order */
+int gsph_prewalk_prepare(gsph_handle* h, int cohort_level);           /* capi.cu: sizes pre_cand / pre_count; pre_n = 0: disabled */
 /* fields written by the passes (for pvalid_*) */
 #define GSPH_DMASK(f) (1ull << (f))
 static const unsigned long long GSPH_OUT_DENSITY =

@@ -295,6 +295,54 @@ __device__ __forceinline__ void pair_terms(const DevParams& dp, const KE& K, Tar
 }
 
 /*------------------------------------------------------------------------------------------------
+ * Pre-walk: the scatter-gather walks of the cohorts, in a kernel of their own.  A walk is a chain of dependent
+ * node loads -- latency bound -- and needs few registers; inside hydro_kernel (128 registers per thread, 16 warps
+ * per SM) it cannot hide that latency.  Here every SM holds 48+ walking warps; the candidate ids go to HBM
+ * (pre_cand, a few KB per cohort) and hydro_kernel starts with its FP32 filter.  A cohort whose list outgrows
+ * its slot gets count -1 and is walked by hydro_kernel itself, as before.
+ *-----------------------------------------------------------------------------------------------*/
+template <int NDIM, bool MIRROR>
+__global__ void __launch_bounds__(HYD_THREADS)
+hydro_walk_kernel(TreeDev tree, DevParams dp, int cohort_level, int c0, int nc, int* work_counter,
+                  int32_t* __restrict__ pre_cand, int pre_cap, int* __restrict__ pre_count, const uint8_t* __restrict__ done)
+{
+  __shared__ int stacks[HYD_WARPS][NB_WALK_STACK];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int* stack = stacks[warp];
+  const WalkBox wbx(dp);
+  const int ncohort = 1 << cohort_level;
+  while (true) {
+    int b = 0;
+    if (lane == 0) b = atomicAdd(work_counter, 1);
+    b = __shfl_sync(FULLMASK, b, 0);
+    if (b >= nc) break;
+    const int c = c0 + b;
+    const int node = ncohort - 1 + c;
+    const int cfirst = tree.first[node], ccount = tree.count[node];
+    if (ccount == 0 || tree.nactive[node] == 0 || done[c] || GSPH_RANGE_OUTSIDE_SLICE(dp, cfirst, ccount)) {
+      if (lane == 0) pre_count[b] = -1;
+      continue;
+    }
+    CandList cl{pre_cand + (size_t) b*pre_cap, pre_cap, 0, nullptr, true};
+    ScatterGatherVisitorF<NDIM> V{tree.nodeb, tree.nodeh, wbx, cl, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f},
+                                  {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, false, 0, 0, 0};
+    V.set_boxes(node);
+    __syncwarp();
+    bool walk_ok = warp_walk_f<NB_WALK_STACK>(tree.ltot, stack, V, (DevStatus*) nullptr);
+    for (int code = 1; code < (MIRROR ? dp.nimg : 1) && walk_ok; code++) {
+      V.set_boxes(node);
+      V.reflect_boxes(image_op<NDIM>(dp, code));
+      V.tag = code << IMG_SHIFT;
+      __syncwarp();
+      walk_ok = warp_walk_f<NB_WALK_STACK>(tree.ltot, stack, V, (DevStatus*) nullptr);
+    }
+    const bool wrapped = __any_sync(FULLMASK, V.needwrap);
+    __syncwarp();
+    if (lane == 0) pre_count[b] = walk_ok ? (cl.n | (wrapped ? (1 << 30) : 0)) : -1;
+  }
+}
+
+/*------------------------------------------------------------------------------------------------
  * One warp per cohort (KD-tree node of <= 32 particles), one target per lane.
  *  phase 1  candidate filter on the FP32 pipe: the candidate slabs are streamed through a shared
  *           tile of float4 records (position relative to the cohort centre, scaled by the largest
@@ -313,7 +361,8 @@ __global__ void __launch_bounds__(HYD_THREADS, 2)
 hydro_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict__ gtables,
              const double2* __restrict__ frec, const double2* __restrict__ geoh, int aux_is_alpha,
              int cohort_level, int* work_counter, int32_t* cand_all, int cand_cap,
-             int32_t* nlist_all, int nlist_cap, DevStatus* st, uint8_t* done)
+             int32_t* nlist_all, int nlist_cap, DevStatus* st, uint8_t* done,
+             const int32_t* __restrict__ pre_cand, int pre_cap, const int* __restrict__ pre_count, int pre_c0, int pre_n)
 {
   extern __shared__ double smem[];
   constexpr int NTAB = TAB ? (GRAV ? 3 : 1) : 0;
@@ -332,7 +381,7 @@ hydro_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict__ 
   int* tj = reinterpret_cast<int*>(ftile + 128);
   const WalkBox wbx(dp);
   const int gwarp = blockIdx.x*HYD_WARPS + warp;
-  int32_t* cand = cand_all + (size_t) gwarp*cand_cap;
+  int32_t* const mycand = cand_all + (size_t) gwarp*cand_cap;
   int32_t* nlist = nlist_all + (size_t) gwarp*nlist_cap*32;
   /* evaluator indexes tables as 3=w1, 4=wgrav, 5=wpot: rebase so that slot 3 is tab[0] */
   const KernelEval<KERN, NDIM, TAB> K(dp, tab - 3*GSPH_TABLE_RES);
@@ -350,13 +399,9 @@ hydro_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict__ 
     const int cfirst = tree.first[node], ccount = tree.count[node];
     if (ccount == 0 || tree.nactive[node] == 0 || done[c] || GSPH_RANGE_OUTSIDE_SLICE(dp, cfirst, ccount)) continue;
 
-    /* ---- walk ---------------------------------------------------------------------------------*/
-    CandList cl{cand, cand_cap, 0, st};
-    ScatterGatherVisitorF<NDIM> V{tree.nodeb, tree.nodeh, wbx, cl, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f},
-                                  {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, false, 0, 0, 0};
+    /* ---- candidates: from the pre-walk kernel, or (no pre-walk / its slot overflowed) walked here ---------*/
     double ctr[3] = {0, 0, 0}, diag2 = 0.0;
     bool wide = false;                /* periodic images not unique about the cohort centre: keep all */
-    V.set_boxes(node);
 #pragma unroll
     for (int k = 0; k < NDIM; k++) {
       const double b0 = tree.bbmin[k][node], b1 = tree.bbmax[k][node];
@@ -365,19 +410,32 @@ hydro_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict__ 
       diag2 += hw*hw;
       if (dp.periodic[k] && hw + rootR >= 0.49*dp.boxsize[k]) wide = true;
     }
-    __syncwarp();
-    bool walk_ok = warp_walk_f<NB_WALK_STACK>(tree.ltot, stack, V, st);
-    /* mirror walls: one more walk per image code with the cohort's boxes reflected */
-    for (int code = 1; code < (MIRROR ? dp.nimg : 1) && walk_ok; code++) {
-      V.set_boxes(node);
-      V.reflect_boxes(image_op<NDIM>(dp, code));
-      V.tag = code << IMG_SHIFT;
-      __syncwarp();
-      walk_ok = warp_walk_f<NB_WALK_STACK>(tree.ltot, stack, V, st);
+    const int32_t* cand = mycand;
+    int ncand = 0; bool wrap = false;
+    const int pre = (c >= pre_c0 && c < pre_c0 + pre_n) ? pre_count[c - pre_c0] : -1;
+    if (pre >= 0) {
+      ncand = pre & 0x3fffffff; wrap = dp.any_periodic && (pre >> 30);
+      cand = pre_cand + (size_t)(c - pre_c0)*pre_cap;
     }
-    if (!walk_ok) continue;
-    const int ncand = cl.n;
-    const bool wrap = dp.any_periodic && __any_sync(FULLMASK, V.needwrap);
+    else {
+      CandList cl{mycand, cand_cap, 0, st};
+      ScatterGatherVisitorF<NDIM> V{tree.nodeb, tree.nodeh, wbx, cl, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f},
+                                    {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, false, 0, 0, 0};
+      V.set_boxes(node);
+      __syncwarp();
+      bool walk_ok = warp_walk_f<NB_WALK_STACK>(tree.ltot, stack, V, st);
+      /* mirror walls: one more walk per image code with the cohort's boxes reflected */
+      for (int code = 1; code < (MIRROR ? dp.nimg : 1) && walk_ok; code++) {
+        V.set_boxes(node);
+        V.reflect_boxes(image_op<NDIM>(dp, code));
+        V.tag = code << IMG_SHIFT;
+        __syncwarp();
+        walk_ok = warp_walk_f<NB_WALK_STACK>(tree.ltot, stack, V, st);
+      }
+      if (!walk_ok) continue;
+      ncand = cl.n;
+      wrap = dp.any_periodic && __any_sync(FULLMASK, V.needwrap);
+    }
     bool overflow = false;
 
     for (int t0 = 0; t0 < ccount; t0 += 32) {
@@ -704,10 +762,23 @@ int launch_hydro_m(gsph_handle* h)
   }
   if (!packed) pack_force_kernel<NDIM><<<(N + 255)/256, 256, 0, h->stream>>>(N, P, aux_is_alpha, h->frec, h->geoh);
   KernelTimer kt(h, 1);
+  /* the walks first, in their own lean kernel (hydro_walk_kernel) */
+  rc = gsph_prewalk_prepare(h, Lc);
+  if (rc) return rc;
+  if (h->pre_n > 0) {
+    CUDA_TRY(h, cudaMemsetAsync(h->work_counter + 1, 0, sizeof(int), h->stream));
+    auto wk = hydro_walk_kernel<NDIM, MIRROR>;
+    int wbps = 0;
+    CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wbps, wk, HYD_THREADS, 0));
+    const int wblocks = std::min(h->sm_count*std::max(wbps, 1), (h->pre_n + HYD_WARPS - 1)/HYD_WARPS);
+    wk<<<wblocks, HYD_THREADS, 0, h->stream>>>(h->tree, h->dp, Lc, h->pre_c0, h->pre_n, h->work_counter + 1, h->pre_cand,
+                                               h->pre_cap, h->pre_count, h->done);
+    h->stats.kernel_launches++;
+  }
   kern<<<blocks, HYD_THREADS, smem, h->stream>>>(P, h->tree, h->dp, h->tables, (const double2*) h->frec,
                                                  (const double2*) h->geoh, aux_is_alpha, Lc, h->work_counter, h->cand,
                                                  (int) h->cand_cap_per_warp, h->nlist, (int) h->nlist_cap,
-                                                 h->status, h->done);
+                                                 h->status, h->done, h->pre_cand, h->pre_cap, h->pre_count, h->pre_c0, h->pre_n);
   h->stats.kernel_launches += 2;
   CUDA_TRY(h, cudaGetLastError());
   return GSPH_OK;
