@@ -237,7 +237,6 @@ int gsph_run_star_gas(gsph_handle* h, const double* dstars, int Nstar, double* d
 int gsph_check_status(gsph_handle* h, const char* where);             /* capi.cu    */
 int gsph_ensure_cand(gsph_handle* h, int warps, size_t cap_per_warp);
 int gsph_ensure_nlist(gsph_handle* h, int warps, size_t cap);
-int gsph_pack_geo4(gsph_handle* h);                                   /* tree.cu */
 int gsph_gather_fields(gsph_handle* h);                               /* tree.cu: host order -> tree order */
 int gsph_prewalk_prepare(gsph_handle* h, int cohort_level);           /* capi.cu: sizes pre_cand / pre_count; pre_n = 0: disabled */
 /* fields written by the passes (for pvalid_*) */

@@ -87,11 +87,21 @@ __global__ void iota_kernel(int N, int* a)
  *      permuted, those of dfill / ifill (absent on the host: all particles hold the default) are set --*/
 struct FillVals { double d[NF_DOUBLE]; int i[NF_INT]; };
 __global__ void gather_kernel(int N, const int32_t* perm, PartView Hh, PartView Pp, unsigned long long dmask,
-                              unsigned imask, unsigned long long dfill, unsigned ifill, FillVals fv)
+                              unsigned imask, unsigned long long dfill, unsigned ifill, FillVals fv,
+                              double* __restrict__ geo4, int ndim)
 {
   const int p = blockIdx.x*blockDim.x + threadIdx.x;
   if (p >= N) return;
   const int i = perm[p];
+  {
+    /* packed (x, y, z, m) record of the density gather phase and the gravity sums; dead particles get m = 0 */
+    const bool dead = ((imask >> I_FLAGS) & 1u) ? ((((unsigned) Hh.i[I_FLAGS][i]) & GSPH_FLAG_DEAD) != 0) : false;
+    double2 a, b;
+    a.x = Hh.f[F_RX][i]; a.y = ndim > 1 ? Hh.f[F_RY][i] : 0.0;
+    b.x = ndim > 2 ? Hh.f[F_RZ][i] : 0.0; b.y = dead ? 0.0 : Hh.f[F_M][i];
+    reinterpret_cast<double2*>(geo4)[2*(size_t) p] = a;
+    reinterpret_cast<double2*>(geo4)[2*(size_t) p + 1] = b;
+  }
 #pragma unroll 4
   for (int f = 0; f < NF_DOUBLE; f++) {
     if ((dmask >> f) & 1ull) Pp.f[f][p] = Hh.f[f][i];
@@ -104,18 +114,55 @@ __global__ void gather_kernel(int N, const int32_t* perm, PartView Hh, PartView 
   }
 }
 
-/* packed (x, y, z, m) records for the density gather phase; dead particles get m = 0 */
+/* The packed walk records of one node (TreeDev::nodeb / nodeh / gnode / mnode), written by the stocking kernels
+ * straight from their registers (pack_nodes_kernel below does the same from the SoA arrays, for the extrapolation
+ * mode).  full = 0 (hmax refresh after the density pass): only hmax / hbox changed.                          */
 template <int NDIM>
-__global__ void pack_geo4_kernel(int N, PartView P, double* __restrict__ geo4)
+__device__ __forceinline__ void pack_node_from_regs(const TreeDev& T, int n, int cnt, int full, const DevParams& dp,
+                                                    const double (&bmin)[3], const double (&bmax)[3],
+                                                    const double (&hbmin)[3], const double (&hbmax)[3],
+                                                    const double (&rc)[3], const double (&com)[3], double m, double rmax,
+                                                    double hmax, double cdist, const double (&q)[5])
 {
-  const int p = blockIdx.x*blockDim.x + threadIdx.x;
-  if (p >= N) return;
-  const bool dead = ((unsigned) P.i[I_FLAGS][p]) & GSPH_FLAG_DEAD;
-  double2 a, b;
-  a.x = P.f[F_RX][p]; a.y = NDIM > 1 ? P.f[F_RY][p] : 0.0;
-  b.x = NDIM > 2 ? P.f[F_RZ][p] : 0.0; b.y = dead ? 0.0 : P.f[F_M][p];
-  reinterpret_cast<double2*>(geo4)[2*(size_t) p] = a;
-  reinterpret_cast<double2*>(geo4)[2*(size_t) p + 1] = b;
+  if (T.gnode) {
+    if (full) {
+      T.gnode[4*(size_t) n] = make_double2(rc[0], NDIM > 1 ? rc[1] : 0.0);
+      T.gnode[4*(size_t) n + 1] = make_double2(NDIM > 2 ? rc[2] : 0.0, rmax);
+      double mac = 0.0;
+      if (dp.gravity_mac == GSPH_MAC_GADGET2) mac = __dmul_rn(__dmul_rn(rmax, rmax), m);
+      else if (dp.gravity_mac == GSPH_MAC_EIGEN) {                   /* KDTree.cpp:1058-1079 */
+        double lambda, pp;
+        if (NDIM == 3) {
+          pp = q[0]*q[2] - (q[0] + q[2])*(q[0] + q[2]) - q[1]*q[1] - q[3]*q[3] - q[4]*q[4];
+          lambda = pp >= 0.0 ? 0.0 : 2.0*sqrt(-pp/3.0);
+        }
+        else if (NDIM == 2) { pp = (q[0] - q[2])*(q[0] - q[2]) + 4*q[1]*q[1]; lambda = 0.5*fmax(q[0] + q[2] + sqrt(pp), 0.); }
+        else lambda = fabs(q[0]);
+        mac = pow(0.5*lambda/dp.macerror, 0.66666666666666);
+      }
+      T.gnode[4*(size_t) n + 3] = make_double2(__hiloint2double(cnt, T.first[n]), mac);
+      T.mnode[2*(size_t) n] = make_double2(com[0], NDIM > 1 ? com[1] : 0.0);
+      T.mnode[2*(size_t) n + 1] = make_double2(NDIM > 2 ? com[2] : 0.0, m);
+    }
+    T.gnode[4*(size_t) n + 2] = make_double2(cdist, __dmul_rn(dp.kernrange, hmax));
+  }
+  float lo[3] = {0.f, 0.f, 0.f}, hi[3] = {0.f, 0.f, 0.f};
+  if (full) {
+#pragma unroll
+    for (int k = 0; k < NDIM; k++) {
+      lo[k] = cnt > 0 ? __double2float_rd(bmin[k]) : 3.0e38f;
+      hi[k] = cnt > 0 ? __double2float_ru(bmax[k]) : -3.0e38f;
+    }
+    T.nodeb[2*(size_t) n] = make_float4(lo[0], lo[1], lo[2], __int_as_float(T.first[n]));
+    T.nodeb[2*(size_t) n + 1] = make_float4(hi[0], hi[1], hi[2], __int_as_float(cnt));
+  }
+#pragma unroll
+  for (int k = 0; k < NDIM; k++) {
+    lo[k] = cnt > 0 ? __double2float_rd(hbmin[k]) : 3.0e38f;
+    hi[k] = cnt > 0 ? __double2float_ru(hbmax[k]) : -3.0e38f;
+  }
+  T.nodeh[2*(size_t) n] = make_float4(lo[0], lo[1], lo[2], 0.f);
+  T.nodeh[2*(size_t) n + 1] = make_float4(hi[0], hi[1], hi[2], 0.f);
 }
 
 /* ---- StockCellProperties for the leaves, KDTree.cpp:841-1010 -----------------------------------*/
@@ -154,7 +201,11 @@ __global__ void stock_leaves_kernel(TreeDev T, PartView P, DevParams dp, int ful
   T.hmax[n] = hmax;
 #pragma unroll
   for (int k = 0; k < NDIM; k++) { T.hbmin[k][n] = hbmin[k]; T.hbmax[k][n] = hbmax[k]; }
-  if (!full) return;
+  if (!full) {
+    const double z3[3] = {0, 0, 0}, z5[5] = {0, 0, 0, 0, 0};
+    pack_node_from_regs<NDIM>(T, n, cnt, 0, dp, z3, z3, hbmin, hbmax, z3, z3, 0.0, 0.0, hmax, T.cdistsqd[n], z5);
+    return;
+  }
   if (T.macaux && full == 1) {                     /* KDTree.cpp:838-841, 899-903 */
     double aux = dp.gravity_mac == GSPH_MAC_GADGET2 ? GSPH_BIG : 0.0;
     for (int i = fst; i < fst + cnt; i++) {
@@ -204,6 +255,7 @@ __global__ void stock_leaves_kernel(TreeDev T, PartView P, DevParams dp, int ful
   }
 #pragma unroll
   for (int k = 0; k < 5; k++) T.q[k][n] = q[k];
+  pack_node_from_regs<NDIM>(T, n, cnt, 1, dp, bmin, bmax, hbmin, hbmax, rc, com, m, rmax, hmax, cdist, q);
 }
 
 /* ---- StockCellProperties for one internal level, KDTree.cpp:1013-1080 ---------------------------*/
@@ -233,7 +285,11 @@ __global__ void stock_level_kernel(TreeDev T, DevParams dp, int level, int full)
   T.hmax[n] = hmax;
 #pragma unroll
   for (int d = 0; d < NDIM; d++) { T.hbmin[d][n] = hbmin[d]; T.hbmax[d][n] = hbmax[d]; }
-  if (!full) return;
+  if (!full) {
+    const double z3[3] = {0, 0, 0}, z5[5] = {0, 0, 0, 0, 0};
+    pack_node_from_regs<NDIM>(T, n, cnt, 0, dp, z3, z3, hbmin, hbmax, z3, z3, 0.0, 0.0, hmax, T.cdistsqd[n], z5);
+    return;
+  }
   if (T.macaux && full == 1) {                     /* KDTree.cpp:967-984 */
     const bool gad = dp.gravity_mac == GSPH_MAC_GADGET2;
     double aux = gad ? GSPH_BIG : 0.0;
@@ -288,6 +344,7 @@ __global__ void stock_level_kernel(TreeDev T, DevParams dp, int level, int full)
   }
 #pragma unroll
   for (int j = 0; j < 5; j++) T.q[j][n] = q[j];
+  pack_node_from_regs<NDIM>(T, n, cnt, 1, dp, bmin, bmax, hbmin, hbmax, rc, com, m, rmax, hmax, cdist, q);
 }
 
 /* Tree::ExtrapolateCellProperties, Tree.cpp:172-198 */
@@ -422,8 +479,8 @@ int stock_tree(gsph_handle* h, int full)
     const int nn = 1 << l;
     stock_level_kernel<NDIM><<<(nn + 127)/128, 128, 0, h->stream>>>(T, h->dp, l, full);
   }
-  pack_nodes_kernel<NDIM><<<(T.ncell + 255)/256, 256, 0, h->stream>>>(T, full, h->dp.kernrange, h->dp.gravity_mac, h->dp.macerror);
-  h->stats.kernel_launches += 2 + T.ltot;
+  /* (the packed walk records are written by the stocking kernels themselves, pack_node_from_regs) */
+  h->stats.kernel_launches += 1 + T.ltot;
   CUDA_TRY(h, cudaGetLastError());
   return GSPH_OK;
 }
@@ -1083,25 +1140,11 @@ int gsph_gather_fields(gsph_handle* h)
   for (int f = 0; f < NF_DOUBLE; f++) fv.d[f] = (f == F_H || f == F_INVOMEGA) ? 1.0 : 0.0;
   for (int f = 0; f < NF_INT; f++) fv.i[f] = f == I_FLAGS ? (int) GSPH_FLAG_ACTIVE : ((f == I_SINKID || f == I_IORIG) ? -1 : 0);
   gather_kernel<<<(N + 255)/256, 256, 0, h->stream>>>(N, h->perm, view_of(h->H, h->HI), view_of(h->P, h->PI),
-                                                     dmask, imask, dfill, ifill, fv);
+                                                     dmask, imask, dfill, ifill, fv, h->geo4, nd);
   h->stats.kernel_launches++;
   CUDA_TRY(h, cudaGetLastError());
   h->pvalid_d = dmask | dfill; h->pvalid_i = imask | ifill;
   h->sorted_valid = true; h->acc_zeroed = false;
-  return GSPH_OK;
-}
-
-int gsph_pack_geo4(gsph_handle* h)
-{
-  const int N = (int) h->N;
-  const PartView P = view_of(h->P, h->PI);
-  switch (h->dp.ndim) {
-  case 1: pack_geo4_kernel<1><<<(N + 255)/256, 256, 0, h->stream>>>(N, P, h->geo4); break;
-  case 2: pack_geo4_kernel<2><<<(N + 255)/256, 256, 0, h->stream>>>(N, P, h->geo4); break;
-  default: pack_geo4_kernel<3><<<(N + 255)/256, 256, 0, h->stream>>>(N, P, h->geo4); break;
-  }
-  h->stats.kernel_launches++;
-  CUDA_TRY(h, cudaGetLastError());
   return GSPH_OK;
 }
 
@@ -1113,8 +1156,7 @@ int gsph_tree_build_sharded(gsph_handle* h, int phase, int rank, int world)
   case 2: rc = build_tree_v2<2>(h, phase, rank, world); break;
   default: rc = build_tree_v2<3>(h, phase, rank, world); break;
   }
-  if (rc || phase == 1) return rc;
-  return gsph_pack_geo4(h);
+  return rc;                         /* (geo4 is packed by the permutation kernel, gsph_gather_fields) */
 }
 
 int gsph_tree_build(gsph_handle* h, int mode, double dt)
@@ -1125,8 +1167,7 @@ int gsph_tree_build(gsph_handle* h, int mode, double dt)
   case 2: rc = build_tree_nd<2>(h, mode, dt); break;
   default: rc = build_tree_nd<3>(h, mode, dt); break;
   }
-  if (rc) return rc;
-  return gsph_pack_geo4(h);
+  return rc;                         /* (geo4 is packed by the permutation kernel, gsph_gather_fields) */
 }
 
 /* KDTree::UpdateAllHmaxValues after the density pass: only hmax and hbox change (cdistsqd keeps
