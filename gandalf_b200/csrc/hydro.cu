@@ -481,14 +481,18 @@ hydro_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict__ 
         if (wide || diag2 > 1.0e6*g.hr2) thr = __int_as_float(0x7f800000);   /* keep every candidate */
       }
       int n = 0; bool full = false;
+      /* the candidate ids are fetched one tile ahead: the record load of a tile never waits for its address */
+      int jpre = lane < ncand ? cand[lane] : -1;
       for (int base = 0; base < ncand; base += 32) {
         const int jl = base + lane;
+        const int jcur = jpre;
+        jpre = (jl + 32 < ncand) ? cand[jl + 32] : -1;
         __syncwarp();
         {
           int j = -1;
           float fx = __int_as_float(0x7f800000), fy = 0.f, fz = 0.f, fw = -1.0f;
           if (jl < ncand) {
-            j = cand[jl];
+            j = jcur;
             const int jp = MIRROR ? (j & IMG_MASK) : j;
             const double2 a = geoh[2*(size_t) jp], b = geoh[2*(size_t) jp + 1];
             double xs[3] = {a.x, a.y, b.x};

@@ -728,3 +728,36 @@ def test_gpot_hydro_is_gpot_before_the_star_terms():
     assert np.array_equal(res[0][0], res[0][1])
     assert np.array_equal(res[1][1], res[0][1])
     assert np.all(res[1][0] > res[1][1])
+
+
+@pytest.mark.parametrize("grav", [0, 1])
+def test_prewalk_kernels_give_the_same_bits_as_the_in_kernel_walks(monkeypatch, grav):
+    """the lean pre-walk kernels (density_walk_kernel / hydro_walk_kernel) hand the main kernels the same candidate
+    lists, in the same order, as the walks the main kernels do themselves: switched off (GSPH_PREWALK=0) or with
+    slots so small that almost every cohort falls back to the in-kernel walk (GSPH_PREWALK_CAP), the results are
+    bit-identical"""
+    import gandalf_b200 as g
+    rng = np.random.default_rng(31)
+    N = 20000
+    r = rng.uniform(-1, 1, (N, 3)); r = r[np.linalg.norm(r, axis=1) < 1.0]
+    N = len(r)
+    v = 0.1*rng.normal(size=(N, 3)); m = np.full(N, 1.0/N); u = np.full(N, 0.05); h = np.full(N, 0.1)
+    params = {"ndim": 3, "self_gravity": grav, "multipole": "fast_monopole", "thetamaxsqd": 0.15}
+    res = []
+    for pre, cap in ((None, None), ("0", None), (None, "64")):
+        for name, val in (("GSPH_PREWALK", pre), ("GSPH_PREWALK_CAP", cap)):
+            if val is None:
+                monkeypatch.delenv(name, raising=False)
+            else:
+                monkeypatch.setenv(name, val)
+        ps = g.ParticleSet(N, 3).set(r=r, v=v, m=m, h=h, u=u)
+        tree = g.GpuSphTree(params)
+        tree.BuildTree(True, 0, 1, 1, 0.0, ps)
+        tree.UpdateAllSphProperties(); tree.ZeroAccelerations()
+        tree.UpdateAllSphForces() if grav else tree.UpdateAllSphHydroForces()
+        tree.Download(ps)
+        res.append({k: ps[k].copy() for k in ("h", "rho", "a", "dudt", "div_v", "levelneib")})
+        tree.close()
+    for k in res[0]:
+        assert np.array_equal(res[0][k], res[1][k]), k
+        assert np.array_equal(res[0][k], res[2][k]), k
