@@ -990,6 +990,45 @@ static void divide_cell(orc_tree* T, int ifirst, int ilast, kdcell* cell)
   stock_cell(T, cell);
 }
 
+/* KDTree::UpdateHmaxValues (KDTree.cpp:1128-1208): after the density pass only hmax and hbox of the cells follow
+ * the new smoothing lengths; cdistsqd keeps the value of the last stock.  h replaces the tree's h array. */
+static void update_hmax_cell(orc_tree* T, kdcell* c)
+{
+  const int nd = T->p.ndim; const double kr = kern_range(&T->p);
+  int k;
+  if (c->level != T->ltot) { update_hmax_cell(T, &T->cell[c->c1]); update_hmax_cell(T, &T->cell[c->c2]); }
+  c->hmax = 0.0;
+  for (k = 0; k < nd; k++) { c->hbmin[k] = BIG_NUMBER; c->hbmax[k] = -BIG_NUMBER; }
+  if (c->level == T->ltot) {
+    int i = c->ifirst;
+    while (i != -1) {
+      c->hmax = fmax(c->hmax, T->h[i]);
+      for (k = 0; k < nd; k++) {
+        const double x = T->r[(size_t)i*nd + k];
+        if (x - kr*T->h[i] < c->hbmin[k]) c->hbmin[k] = x - kr*T->h[i];
+        if (x + kr*T->h[i] > c->hbmax[k]) c->hbmax[k] = x + kr*T->h[i];
+      }
+      if (i == c->ilast) break;
+      i = T->inext[i];
+    }
+  }
+  else {
+    kdcell* ch[2] = { &T->cell[c->c1], &T->cell[c->c2] };
+    for (int s = 0; s < 2; s++) {
+      if (ch[s]->N > 0) {
+        c->hmax = fmax(c->hmax, ch[s]->hmax);
+        for (k = 0; k < nd; k++) { c->hbmin[k] = fmin(ch[s]->hbmin[k], c->hbmin[k]); c->hbmax[k] = fmax(ch[s]->hbmax[k], c->hbmax[k]); }
+      }
+    }
+  }
+}
+
+void orc_tree_update_hmax(orc_tree* T, const double* h)
+{
+  T->h = h;
+  update_hmax_cell(T, &T->cell[0]);
+}
+
 orc_tree* orc_tree_build(const orc_params* p, int N, const double* r, const double* v,
                          const double* m, const double* h)
 {

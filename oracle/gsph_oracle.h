@@ -112,6 +112,9 @@ orc_tree* orc_tree_build(const orc_params* p, int N, const double* r, const doub
  * criteria read when the cells are stocked (KDTree.cpp:899-903); either may be NULL */
 orc_tree* orc_tree_build_mac(const orc_params* p, int N, const double* r, const double* v,
                              const double* m, const double* h, const double* atree, const double* gpot);
+/* KDTree::UpdateHmaxValues (KDTree.cpp:1128-1208): hmax / hbox of the cells from new smoothing lengths h (the array
+ * must stay alive); cdistsqd keeps the value of the last stock, as in the reference */
+void orc_tree_update_hmax(orc_tree* t, const double* h);
 void orc_tree_free(orc_tree* t);
 int  orc_tree_ncell(const orc_tree* t);
 int  orc_tree_ltot(const orc_tree* t);

@@ -140,8 +140,12 @@ struct Harness
     vector<double> r(N*ndim), v(N*ndim), a(N*ndim), atree(N*ndim);
     vector<double> m(N), h(N), hrangesqd(N), hfactor(N), sound(N), rho(N), pressure(N), u(N),
                    dudt(N), gpot(N), div_v(N), alpha(N), dalphadt(N), invomega(N), zeta(N);
-    vector<int> iorig(N), ptype(N), flags(N), level(N), levelneib(N);
+    vector<int> iorig(N), ptype(N), flags(N), level(N), levelneib(N), nstep(N), nlast(N);
+    vector<double> r0(N*ndim), v0(N*ndim), a0(N*ndim), u0(N), dudt0(N), pdt(N), dt_next(N), tlast(N);
     for (int i = 0; i < N; i++) {
+      for (int k = 0; k < ndim; k++) { r0[i*ndim+k] = p[i].r0[k]; v0[i*ndim+k] = p[i].v0[k]; a0[i*ndim+k] = p[i].a0[k]; }
+      u0[i] = p[i].u0; dudt0[i] = p[i].dudt0; pdt[i] = p[i].dt; dt_next[i] = p[i].dt_next; tlast[i] = p[i].tlast;
+      nstep[i] = p[i].nstep; nlast[i] = p[i].nlast;
       for (int k = 0; k < ndim; k++) {
         r[i*ndim+k] = p[i].r[k]; v[i*ndim+k] = p[i].v[k];
         a[i*ndim+k] = p[i].a[k]; atree[i*ndim+k] = p[i].atree[k];
@@ -166,6 +170,11 @@ struct Harness
     dump_i32(stage + ".iorig", iorig, N); dump_i32(stage + ".ptype", ptype, N);
     dump_i32(stage + ".flags", flags, N); dump_i32(stage + ".level", level, N);
     dump_i32(stage + ".levelneib", levelneib, N);
+    // integrator state (block time steps, Particle.h: nstep, nlast, dt, dt_next, tlast, r0, v0, a0, u0, dudt0)
+    dump_i32(stage + ".nstep", nstep, N); dump_i32(stage + ".nlast", nlast, N);
+    dump_f64(stage + ".dt", pdt, N); dump_f64(stage + ".dt_next", dt_next, N); dump_f64(stage + ".tlast", tlast, N);
+    dump_f64(stage + ".r0", r0, N, ndim); dump_f64(stage + ".v0", v0, N, ndim); dump_f64(stage + ".a0", a0, N, ndim);
+    dump_f64(stage + ".u0", u0, N); dump_f64(stage + ".dudt0", dudt0, N);
     // star particles (the N-body side of the main loop)
     const int Ns = sim->nbody->Nstar;
     if (Ns > 0) {
@@ -438,7 +447,13 @@ static int run(Parameters* params, const string& icfile, double perturb, const s
   if (!g_quiet) fprintf(stderr, "[ref_harness] setup done: Nhydro=%d Ntot=%d (%.2fs)\n",
                         H.sph->Nhydro, H.sph->Ntot, t_setup);
 
-  if (want("setup")) H.dump_particles("setup");
+  if (want("setup")) {
+    H.dump_particles("setup");
+    fprintf(g_out, "{\"ref_setup\": true, \"n\": %d, \"nresync\": %d, \"level_max\": %d, \"level_step\": %d, \"dt_max\": %.17g, "
+            "\"timestep\": %.17g, \"t\": %.17g, \"Nlevels\": %d}\n", (int) sim->n, (int) sim->nresync, (int) sim->level_max,
+            (int) sim->level_step, (double) sim->dt_max, (double) sim->timestep, (double) sim->t, (int) sim->Nlevels);
+    fflush(g_out);
+  }
   if (!g_snapshot.empty()) sb->WriteSnapshotFile(g_snapshot, "su");
   if (!g_snapshot_col.empty()) sb->WriteSnapshotFile(g_snapshot_col, "column");
   if (!g_snapshot_sf.empty()) sb->WriteSnapshotFile(g_snapshot_sf, "sf");
@@ -528,8 +543,10 @@ static int run(Parameters* params, const string& icfile, double perturb, const s
     for (int s = done; s < g_mainloop; s++) sim->MainLoop();
     double t_loop = now() - t1;
     H.dump_particles("loop");
-    fprintf(g_out, "{\"ref_mainloop\": true, \"gpu\": %s, \"N\": %d, \"steps\": %d, \"t\": %.17g, \"timestep\": %.17g, \"timestep0\": %.17g, \"wall_s\": %.4f}\n",
-            g_gpu ? "true" : "false", H.sph->Nhydro, g_mainloop, (double) sim->t, (double) sim->timestep, timestep0, t_loop);
+    fprintf(g_out, "{\"ref_mainloop\": true, \"gpu\": %s, \"N\": %d, \"steps\": %d, \"t\": %.17g, \"timestep\": %.17g, \"timestep0\": %.17g, \"wall_s\": %.4f, "
+            "\"n\": %d, \"nresync\": %d, \"level_max\": %d, \"level_step\": %d, \"dt_max\": %.17g, \"Nlevels\": %d}\n",
+            g_gpu ? "true" : "false", H.sph->Nhydro, g_mainloop, (double) sim->t, (double) sim->timestep, timestep0, t_loop,
+            (int) sim->n, (int) sim->nresync, (int) sim->level_max, (int) sim->level_step, (double) sim->dt_max, (int) sim->Nlevels);
     fflush(g_out);
   }
 

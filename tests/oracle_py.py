@@ -321,6 +321,14 @@ class Tree:
             lib().orc_tree_free(self.ptr)
             self.ptr = None
 
+    def update_hmax(self, h):
+        """KDTree::UpdateHmaxValues after a density pass (cdistsqd keeps the value of the stock)"""
+        self._h = _c(h).copy()
+        L = lib()
+        L.orc_tree_update_hmax.restype = None
+        L.orc_tree_update_hmax.argtypes = [C.c_void_p, _dp]
+        L.orc_tree_update_hmax(self.ptr, self._h)
+
     def leaf_of(self):
         out = np.full(self.N, -1, dtype=np.int32)
         lib().orc_tree_leaf_of(self.ptr, out)
@@ -366,8 +374,13 @@ class Tree:
 # functions above.  TEST INFRASTRUCTURE, the checker of gsph_integrator_*.
 # ---------------------------------------------------------------------------------------------------
 def global_timestep(p, s, courant_mult, accel_mult, energy_mult, energy_integration):
-    """SphIntegration::Timestep per particle (SphIntegration.cpp:76-124) and the minimum
-    (Simulation::ComputeGlobalTimestep, Simulation.cpp:1690-1730)"""
+    """the minimum of SphIntegration::Timestep over the particles (Simulation::ComputeGlobalTimestep,
+    Simulation.cpp:1690-1730)"""
+    return float(particle_timesteps(p, s, courant_mult, accel_mult, energy_mult, energy_integration).min())
+
+
+def particle_timesteps(p, s, courant_mult, accel_mult, energy_mult, energy_integration):
+    """SphIntegration::Timestep per particle (SphIntegration.cpp:76-124)"""
     h, dv = s["h"], np.abs(s["div_v"])
     if p.hydro_forces == 1:
         ts = courant_mult*h/(s["sound"] + h*dv + 1.0e-50)
@@ -381,7 +394,7 @@ def global_timestep(p, s, courant_mult, accel_mult, energy_mult, energy_integrat
     if energy_integration:
         te = energy_mult*(s["u"]/(np.abs(s["dudt"]) + 1.0e-20))
         ts = np.where(s["ptype"] == 0, np.minimum(ts, te), ts)
-    return float(ts.min())
+    return ts
 
 
 def star_star_forces(p, sr, sm, sh):
@@ -507,3 +520,216 @@ def mainloop(params, setup, steps):
     if stars:
         s["star_r"], s["star_v"], s["star_a"], s["star_gpot"] = sr, sv, sa, sgpot
     return s, t, timestep
+
+
+
+# ---------------------------------------------------------------------------------------------------
+# block time steps (Nlevels > 1)
+# ---------------------------------------------------------------------------------------------------
+INVLOGETWO = 1.44269504088896          # src/Headers/Constants.h:81
+
+
+def timestep_level(dt, dt_max):
+    """ComputeTimestepLevel (InlineFuncs.h:550-558), elementwise"""
+    return np.maximum((INVLOGETWO*np.log(dt_max/dt)).astype(np.int64) + 1, 0)
+
+
+def thermal_all(p, rho, u):
+    """GradhSph::ComputeThermalProperties for every particle (GradhSph.cpp:335-347; EOS classes as in
+    oracle/gsph_oracle.c thermal()) -> (u, sound, pressure)"""
+    g = p.gamma_eos; gm1 = g - 1.0
+    u = np.array(u, copy=True)
+    if p.eos == 1:
+        u = np.full_like(u, p.temp0/gm1/p.mu_bar)
+    elif p.eos == 2:
+        u = p.temp0*(1.0 + np.power(rho*(1.0/p.rho_bary), gm1))/gm1/p.mu_bar
+    elif p.eos == 3:
+        u = np.where(rho < p.rho_bary, p.temp0/gm1/p.mu_bar, p.temp0*np.power(rho*(1.0/p.rho_bary), gm1)/gm1/p.mu_bar)
+    sound = np.sqrt(g*gm1*u) if p.eos == 0 else np.sqrt(gm1*u)
+    return u, sound, gm1*rho*u
+
+
+def _pow2int(e):
+    """(int) pow(2, e) as the reference evaluates it: 0 for negative exponents (a particle that has just moved below
+    the deepest level gets nstep = 0 and dt_next = 0 for one step, Simulation.cpp:1990-1992 -- kept)"""
+    e = np.asarray(e)
+    return np.where(e >= 0, 2**np.clip(e, 0, 62), 0)
+
+
+def mainloop_block(params, setup, sim, steps, trace=None):
+    """`steps` x SphSimulation::MainLoop with hierarchical block time steps (Nlevels > 1): SphSimulation.cpp:574-880,
+    SphLeapfrogKDK::AdvanceParticles / CheckTimesteps / EndTimestep (SphLeapfrogKDK.cpp:76-125, 226-339),
+    Simulation::ComputeBlockTimesteps (Simulation.cpp:1764-2199), from the reference's post-setup state.
+    setup: particle arrays incl. level, levelneib, nstep, nlast, dt, dt_next, tlast, r0, v0, a0, u0, dudt0;
+    sim: dict n, nresync, level_max, level_step, dt_max, timestep, t (after the reference's setup).
+    No stars, no sinks, lfkdk (integration_step = 1), sph_single_timestep = 0.  -> (state, sim)"""
+    p = params_from_dict(params)
+    nd = p.ndim
+    cm, am, em = (float(params.get("courant_mult", 0.15)), float(params.get("accel_mult", 0.3)),
+                  float(params.get("energy_mult", 0.4)))
+    energy = params.get("gas_eos", "energy_eqn") == "energy_eqn"
+    tdav = params.get("time_dependent_avisc", "none") != "none"
+    Nlevels = int(params["Nlevels"])
+    ldm = int(params.get("level_diff_max", 1))
+    s = {k: np.array(v, copy=True) for k, v in setup.items()}
+    N = len(s["m"])
+    for k in ("r", "v", "a", "atree", "r0", "v0", "a0"):
+        s[k] = s[k].reshape(N, nd)
+    for k in ("level", "levelneib", "nstep", "nlast"):
+        s[k] = s[k].astype(np.int64)
+    n, nresync, level_max, level_step = (int(sim[k]) for k in ("n", "nresync", "level_max", "level_step"))
+    dt_max, timestep, t = float(sim["dt_max"]), float(sim["timestep"]), float(sim["t"])
+    size = [p.boxmax[k] - p.boxmin[k] for k in range(nd)]
+    end_ts = np.zeros(N, dtype=bool)
+
+    def passes(active, tr):
+        """UpdateAllSphProperties, ZeroAccelerations and the force pass for the active particles; tr = the tree
+        BuildTree stocked with the smoothing lengths of the start of the step (cdistsqd!), refreshed here with the
+        new ones like tree->UpdateAllHmaxValues (GradhSphTree.cpp:268)"""
+        dens = density(p, s["r"], s["m"], s["h"], s["u"])
+        for k in ("h", "rho", "invomega", "zeta", "hfactor", "hrangesqd", "u", "sound", "pressure"):
+            s[k] = np.where(active, dens[k], s[k])
+        if tr is not None:
+            tr.update_hmax(s["h"])
+        if params.get("time_dependent_avisc") == "cd2010":
+            raise NotImplementedError("cd2010 with block time steps")
+        s["levelneib"] = np.where(active, 0, s["levelneib"])
+        for k in ("div_v", "dudt", "gpot"):
+            s[k] = np.where(active, 0.0, s[k])
+        # nradstep = 1 (the default): MainLoop refreshes the thermal properties of EVERY particle, active or not,
+        # before the force pass (SphSimulation.cpp:669-679) -- inactive neighbours enter with the pressure of their
+        # predicted u
+        s["u"], s["sound"], s["pressure"] = thermal_all(p, s["rho"], s["u"])
+        if p.self_gravity:
+            f = tr.hydro_grav_forces(s)
+            s["atree"] = np.where(active[:, None], f["atree"], s["atree"])
+            s["gpot"] = np.where(active, f["gpot"], s["gpot"])
+        else:
+            f = hydro_forces(p, s)
+        s["a"] = np.where(active[:, None], f["a"], s["a"])
+        s["dudt"] = np.where(active, f["dudt"], s["dudt"])
+        s["div_v"] = np.where(active, f["div_v"], s["div_v"])
+        if params.get("time_dependent_avisc", "none") == "mm97":
+            s["dalphadt"] = np.where(active, s["dalphadt"] + f["dalphadt"], s["dalphadt"])
+        # levelneib: every (active i, neighbour j) pair raises both (GradhSph.cpp:446, GradhSphTree.cpp:376-382)
+        off, idx = neighbour_lists(p, s["r"], s["hrangesqd"])
+        lev, ln = s["level"], s["levelneib"].copy()
+        for i in np.nonzero(active)[0]:
+            nb = idx[off[i]:off[i + 1]]
+            if len(nb):
+                ln[i] = max(ln[i], lev[nb].max())
+                np.maximum.at(ln, nb, lev[i])
+        s["levelneib"] = ln
+
+    for _ in range(steps):
+        n += 1
+        t = t + timestep
+        # ---- AdvanceParticles
+        dn = n - s["nlast"]
+        dtp = t - s["tlast"]
+        s["r"] = s["r0"] + s["v0"]*dtp[:, None] + 0.5*s["a0"]*dtp[:, None]*dtp[:, None]
+        s["v"] = s["v0"] + s["a0"]*dtp[:, None]
+        if tdav:
+            s["alpha"] = s["alpha"] + s["dalphadt"]*timestep
+        if energy:
+            s["u"] = s["u0"] + s["dudt0"]*dtp
+        active = dn == s["nstep"]
+        # ---- CheckBoundaries (periodic wrap only here)
+        for k in range(nd):
+            if p.periodic[k]:
+                lo = s["r"][:, k] < p.boxmin[k]
+                s["r"][lo, k] += size[k]; s["r0"][lo, k] += size[k]
+                hi = s["r"][:, k] > p.boxmax[k]
+                s["r"][hi, k] -= size[k]; s["r0"][hi, k] -= size[k]
+        # ---- passes, repeated while CheckTimesteps activates more particles
+        nredo = 0
+        tr = Tree(p, s["r"], s["v"], s["m"], s["h"], s["atree"], s["gpot"]) if p.self_gravity else None
+        while True:
+            passes(active, tr)
+            active = np.zeros(N, dtype=bool)
+            dn = n - s["nlast"]
+            cand = (dn != s["nstep"]) & (s["levelneib"] - s["level"] > ldm)
+            level_new = s["levelneib"] - ldm
+            nnewstep = _pow2int(level_step - level_new)
+            ok = cand & (nnewstep > 0) & (dn % np.maximum(nnewstep, 1) == 0)
+            s["nstep"] = np.where(ok & (dn > 0), dn, s["nstep"])
+            s["level"] = np.where(ok, level_new, s["level"])
+            active = ok
+            if not ok.any():
+                break
+            nredo += 1
+        # ---- ComputeBlockTimesteps
+        ts = particle_timesteps(p, s, cm, am, em, energy)
+        if n == nresync:
+            n = 0
+            s["dt_next"] = ts.copy()
+            timestep = float(ts.min())
+            level_max = Nlevels - 1
+            level_step = level_max
+            dt_max = timestep*2.0**level_max
+            lev = np.minimum(timestep_level(ts, dt_max), level_max)
+            s["level"] = lev; s["levelneib"] = lev.copy()
+            s["nstep"] = _pow2int(level_step - lev)
+            s["nlast"] = np.full(N, n, dtype=np.int64)
+            s["dt_next"] = s["nstep"]*timestep
+            end_ts[:] = True
+            nresync = 2**level_step
+            timestep = dt_max/float(nresync)
+        else:
+            level_max_old = level_max
+            atend = (n - s["nlast"]) == s["nstep"]
+            reduced = atend & (s["nstep"] != _pow2int(level_step - s["level"]))
+            natural = atend & ~reduced
+            lev_dt = timestep_level(ts, dt_max)
+            level = np.maximum(lev_dt, s["levelneib"] - ldm)
+            # Saitoh & Makino reduced steps
+            newl = np.maximum(s["level"], level)
+            s["level"] = np.where(reduced, newl, s["level"])
+            s["levelneib"] = np.where(reduced, newl, s["levelneib"])
+            # natural end of step: up one level if synchronised, down any number
+            last = s["level"]
+            up = natural & (level < last) & (last > 1) & (n % (2*s["nstep"]) == 0)
+            down = natural & (level > last)
+            s["level"] = np.where(up, last - 1, np.where(down, level, last))
+            s["levelneib"] = np.where(natural, level, s["levelneib"])
+            s["nlast"] = np.where(atend, n, s["nlast"])
+            s["nstep"] = np.where(atend, _pow2int(level_step - s["level"]), s["nstep"])
+            s["dt_next"] = np.where(atend, s["nstep"]*timestep, s["dt_next"])
+            end_ts |= atend
+            level_max = int(s["level"].max())
+            istep = 2**(level_step - level_max_old + 1)
+            if level_max > level_max_old:
+                nfactor = 2**(level_max - level_max_old)
+                n *= nfactor
+                s["nstep"] = s["nstep"]*nfactor; s["nlast"] = s["nlast"]*nfactor
+            elif level_max <= level_max_old - 1 and level_max_old > 1 and n % istep == 0:
+                level_max = level_max_old - 1
+                nfactor = 2**(level_max_old - level_max)
+                n //= nfactor
+                s["nlast"] = s["nlast"]//nfactor; s["nstep"] = s["nstep"]//nfactor
+            else:
+                level_max = level_max_old
+            level_step = level_max
+            nresync = 2**level_step
+            timestep = dt_max/float(nresync)
+            s["nstep"] = np.where(s["nlast"] == n, _pow2int(level_step - s["level"]), s["nstep"])
+        # ---- EndTimestep
+        e = end_ts
+        s["v"] = np.where(e[:, None], s["v"] + 0.5*s["dt"][:, None]*(s["a"] - s["a0"]), s["v"])
+        for k0, k1 in (("r0", "r"), ("v0", "v"), ("a0", "a")):
+            s[k0] = np.where(e[:, None], s[k1], s[k0])
+        if energy:
+            u = s["u"] + 0.5*(s["dudt"] - s["dudt0"])*s["dt"]
+            u = np.where(u <= 0.0, s["u0"] + s["dudt0"]*s["dt"], u)
+            s["u"] = np.where(e, u, s["u"])
+            s["u0"] = np.where(e, s["u"], s["u0"])
+            s["dudt0"] = np.where(e, s["dudt"], s["dudt0"])
+        s["nlast"] = np.where(e, n, s["nlast"])
+        s["tlast"] = np.where(e, t, s["tlast"])
+        s["dt"] = np.where(e, s["dt_next"], s["dt"])
+        s["dt_next"] = np.where(e, 0.0, s["dt_next"])
+        end_ts[:] = False
+        if trace is not None:
+            trace.append(dict(n=n, nresync=nresync, level_max=level_max, timestep=timestep, t=t, nredo=nredo))
+    sim_out = dict(n=n, nresync=nresync, level_max=level_max, level_step=level_step, dt_max=dt_max, timestep=timestep, t=t)
+    return s, sim_out

@@ -139,9 +139,14 @@ def run_mainloop(params, ic, steps, gpu, timeout=1800, kind="gpu", dumps="", res
             raise RuntimeError("ref_harness_gpu failed (%d): %s %s" % (res.returncode, res.stdout.decode()[-1000:],
                                                                      res.stderr.decode()[-2000:]))
         info = None
+        setup_info = None
         for line in res.stdout.decode().splitlines():
             if line.startswith("{\"ref_mainloop\""):
                 info = json.loads(line)
+            if line.startswith("{\"ref_setup\""):
+                setup_info = json.loads(line)
+        if info is not None and setup_info is not None:
+            info["setup"] = setup_info                     # n, nresync, level_max, ... right after the reference's setup
         return load_dump(os.path.join(work, "out")), info
     finally:
         shutil.rmtree(work, ignore_errors=True)

@@ -60,3 +60,56 @@ def test_mainloop_restatement_matches_reference(name):
     if "star_r" in loop:                     # star particles moved by the N-body leapfrog
         for k in ("star_r", "star_v", "star_a"):
             assert vec_err(np.asarray(s[k]), loop[k]).max() < 1e-9, k
+
+
+# ---------------------------------------------------------------------------------------------------
+# hierarchical block time steps (Nlevels > 1): tests/golden/loopblk_*.npz, make_loopblk_golden.py
+# ---------------------------------------------------------------------------------------------------
+from conftest import LOOPBLK_CASES  # noqa: E402
+
+SIM_KEYS = ("n", "nresync", "level_max", "level_step", "dt_max", "timestep", "t")
+INT_STATE = ("level", "levelneib", "nstep", "nlast")
+
+
+def split_blk(d):
+    """-> (setup arrays, setup scalars, loop arrays, loop scalars)"""
+    arr = {"setup": {}, "loop": {}}
+    sim = {"setup": {}, "loop": {}}
+    for k, v in d.items():
+        st, f = k.split(".", 1)
+        if f.startswith("sim_"):
+            sim[st][f[4:]] = v.item()
+        elif f != "steps":
+            arr[st][f] = v
+    return arr["setup"], sim["setup"], arr["loop"], sim["loop"]
+
+
+def check_block_state(s, sim, ref, refsim, tol):
+    for k in ("n", "nresync", "level_max", "level_step"):
+        assert int(sim[k]) == int(refsim[k]), k
+    for k in ("dt_max", "timestep", "t"):
+        assert abs(float(sim[k]) - float(refsim[k])) <= 1e-11*abs(float(refsim[k])), k
+    for f in INT_STATE:
+        assert np.array_equal(np.asarray(s[f]).astype(np.int64), ref[f].astype(np.int64)), f
+    check_state(s, ref, tol)
+    for f in ("dt", "tlast"):
+        assert np.abs(np.asarray(s[f]) - ref[f]).max() <= 1e-11*np.abs(ref[f]).max(), f
+
+
+def test_block_fixtures_exist():
+    assert len(LOOPBLK_CASES) >= 3
+
+
+@pytest.mark.parametrize("name", LOOPBLK_CASES)
+def test_block_timestep_restatement_matches_reference(name):
+    """oracle_py.mainloop_block (AdvanceParticles / CheckTimesteps / ComputeBlockTimesteps / EndTimestep with
+    Nlevels = 4) reproduces 20 of the reference's own MainLoop calls: the same levels, integer times and step
+    sizes for every particle -- through added and removed levels and a resynchronisation -- and the same state"""
+    params, d = load_golden(name)
+    setup, sim0, loop, sim1 = split_blk(d)
+    assert int(params["Nlevels"]) > 1 and len(np.unique(loop["level"])) >= 3
+    steps = int(d["loop.steps"])
+    if name != "loopblk_adsod":
+        steps = 20                     # (kept: about 10 s each)
+    s, sim = orc.mainloop_block(params, setup, sim0, steps)
+    check_block_state(s, sim, loop, sim1, 1e-9)
