@@ -76,7 +76,14 @@ class IntegratorConfig(C.Structure):
     """gsph_integrator_config"""
     _fields_ = [("accel_mult", C.c_double), ("courant_mult", C.c_double), ("energy_mult", C.c_double),
                 ("energy_integration", C.c_int32), ("ntreebuildstep", C.c_int32), ("ntreestockstep", C.c_int32),
-                ("sink_particles", C.c_int32), ("reserved", C.c_int32 * 4)]
+                ("sink_particles", C.c_int32), ("Nlevels", C.c_int32), ("level_diff_max", C.c_int32),
+                ("reserved", C.c_int32 * 2)]
+
+
+class BlockState(C.Structure):
+    """gsph_block_state"""
+    _fields_ = [("n", C.c_int64), ("nresync", C.c_int64), ("level_max", C.c_int32), ("level_step", C.c_int32),
+                ("dt_max", C.c_double)]
 
 
 EXPORTS = [
@@ -89,7 +96,7 @@ EXPORTS = [
     "gsph_device_field",
     "gsph_neighbour_counts", "gsph_neighbour_lists", "gsph_tree_info_get", "gsph_tree_leaf_of",
     "gsph_tree_cells", "gsph_get_stats", "gsph_kernel_table", "gsph_measure_fp_peak",
-    "gsph_integrator_begin", "gsph_integrator_step", "gsph_integrator_state",
+    "gsph_integrator_begin", "gsph_integrator_step", "gsph_integrator_state", "gsph_integrator_block_state",
     "gsph_update_all_forces_begin", "gsph_update_all_forces_finish", "gsph_integrator_advance",
     "gsph_integrator_finish", "gsph_update_star_gas_forces", "gsph_derive_density_fields",
     "gsph_integrator_set_stars", "gsph_integrator_get_stars",
@@ -140,6 +147,7 @@ def lib():
     L.gsph_integrator_get_stars.argtypes = [H, C.c_void_p, C.c_int]
     L.gsph_update_star_gas_forces.argtypes = [H, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.gsph_integrator_state.argtypes = [H, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
+    L.gsph_integrator_block_state.argtypes = [H, C.POINTER(BlockState), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     for n in ("gsph_update_active_counters", "gsph_update_properties", "gsph_zero_accelerations",
               "gsph_update_hydro_forces", "gsph_synchronize", "gsph_timer_start", "gsph_density_pass",
               "gsph_update_all_forces_begin", "gsph_update_all_forces_finish",

@@ -355,14 +355,21 @@ IntegPtrs integ_ptrs(gsph_handle* h)
 
 /* SphLeapfrogKDK::AdvanceParticles (SphLeapfrogKDK.cpp:76-125) + TimeIntegration::CheckBoundaries
  * (Integration.cpp:11-75).  dt = t - tlast, timestep = the global step (they differ by rounding). */
+struct BlkPtrs;
 template <int NDIM>
 __global__ void integ_advance_kernel(int N, DevPtrs H, IntegPtrs S, DevParams dp, double dt, double timestep,
-                                     int tdav, int energy)
+                                     int tdav, int energy, int block, double t, int n, const int32_t* __restrict__ nstep,
+                                     const int32_t* __restrict__ nlast, const double* __restrict__ tlast)
 {
   const int i = blockIdx.x*blockDim.x + threadIdx.x;
   if (i >= N) return;
   unsigned fl = (unsigned) H.i[I_FLAGS][i];
   if (fl & GSPH_FLAG_DEAD) return;
+  bool act = true;                                          /* one global step: dn == nstep for every particle */
+  if (block) {                                              /* time since the start of THIS particle's step */
+    dt = __dadd_rn(t, -tlast[i]);
+    act = (n - nlast[i]) == nstep[i];
+  }
 #pragma unroll
   for (int k = 0; k < NDIM; k++) {
     const double r0 = S.r0[k][i], v0 = S.v0[k][i], a0 = S.a0[k][i];
@@ -372,7 +379,7 @@ __global__ void integ_advance_kernel(int N, DevPtrs H, IntegPtrs S, DevParams dp
   }
   if (tdav) H.f[F_ALPHA][i] = __dadd_rn(H.f[F_ALPHA][i], __dmul_rn(H.f[F_DALPHADT][i], timestep));
   if (energy) H.f[F_U][i] = __dadd_rn(S.u0[i], __dmul_rn(S.dudt0[i], dt));
-  H.i[I_FLAGS][i] = (int32_t)(fl | GSPH_FLAG_ACTIVE);         /* dn == nstep for every particle */
+  H.i[I_FLAGS][i] = (int32_t)(act ? (fl | GSPH_FLAG_ACTIVE) : (fl & ~(unsigned) GSPH_FLAG_ACTIVE));
   /* boundaries */
 #pragma unroll
   for (int k = 0; k < NDIM; k++) {
@@ -404,28 +411,34 @@ __global__ void integ_advance_kernel(int N, DevPtrs H, IntegPtrs S, DevParams dp
   }
 }
 
-/* SphIntegration::Timestep for every particle (SphIntegration.cpp:76-124) and the global minimum
- * (Simulation::ComputeGlobalTimestep, Simulation.cpp:1690-1730).  Positive doubles order like their
- * bit patterns, so the minimum is an integer atomicMin.                                            */
+/* SphIntegration::Timestep of one particle (SphIntegration.cpp:76-124), host-order state */
+template <int NDIM>
+__device__ __forceinline__ double particle_timestep(int i, const DevPtrs& H, const DevParams& dp, const gsph_integrator_config& ic, bool& bad)
+{
+  double ts;
+  const double hh = H.f[F_H][i], dv = fabs(H.f[F_DIVV][i]);
+  if (dp.hydro_forces == 1) ts = __ddiv_rn(__dmul_rn(ic.courant_mult, hh), __dadd_rn(__dadd_rn(H.f[F_SOUND][i], __dmul_rn(hh, dv)), 1.0e-50));
+  else ts = __ddiv_rn(__dmul_rn(ic.courant_mult, hh), __dadd_rn(__dmul_rn(hh, dv), 1.0e-50));
+  double a2 = 0.0;
+#pragma unroll
+  for (int k = 0; k < NDIM; k++) { const double a = H.f[F_AX + k][i]; a2 = k == 0 ? __dmul_rn(a, a) : __dadd_rn(a2, __dmul_rn(a, a)); }
+  const double amag = __dsqrt_rn(a2);
+  ts = fmin(ts, __dmul_rn(ic.accel_mult, __dsqrt_rn(__ddiv_rn(hh, __dadd_rn(amag, 1.0e-50)))));
+  if (ic.energy_integration && H.i[I_PTYPE][i] == 0)
+    ts = fmin(ts, __dmul_rn(ic.energy_mult, __ddiv_rn(H.f[F_U][i], __dadd_rn(fabs(H.f[F_DUDT][i]), 1.0e-20))));
+  bad = !(ts <= 1.0e20) || ts <= 0.0;
+  return ts;
+}
+
+/* every particle's time step and the global minimum (Simulation::ComputeGlobalTimestep, Simulation.cpp:1690-1730).
+ * Positive doubles order like their bit patterns, so the minimum is an integer atomicMin.                */
 template <int NDIM>
 __global__ void integ_timestep_kernel(int N, DevPtrs H, DevParams dp, gsph_integrator_config ic, unsigned long long* red)
 {
   const int i = blockIdx.x*blockDim.x + threadIdx.x;
   double ts = 9.9e50;
   bool bad = false;
-  if (i < N) {
-    const double hh = H.f[F_H][i], dv = fabs(H.f[F_DIVV][i]);
-    if (dp.hydro_forces == 1) ts = __ddiv_rn(__dmul_rn(ic.courant_mult, hh), __dadd_rn(__dadd_rn(H.f[F_SOUND][i], __dmul_rn(hh, dv)), 1.0e-50));
-    else ts = __ddiv_rn(__dmul_rn(ic.courant_mult, hh), __dadd_rn(__dmul_rn(hh, dv), 1.0e-50));
-    double a2 = 0.0;
-#pragma unroll
-    for (int k = 0; k < NDIM; k++) { const double a = H.f[F_AX + k][i]; a2 = k == 0 ? __dmul_rn(a, a) : __dadd_rn(a2, __dmul_rn(a, a)); }
-    const double amag = __dsqrt_rn(a2);
-    ts = fmin(ts, __dmul_rn(ic.accel_mult, __dsqrt_rn(__ddiv_rn(hh, __dadd_rn(amag, 1.0e-50)))));
-    if (ic.energy_integration && H.i[I_PTYPE][i] == 0)
-      ts = fmin(ts, __dmul_rn(ic.energy_mult, __ddiv_rn(H.f[F_U][i], __dadd_rn(fabs(H.f[F_DUDT][i]), 1.0e-20))));
-    bad = !(ts <= 1.0e20) || ts <= 0.0;
-  }
+  if (i < N) ts = particle_timestep<NDIM>(i, H, dp, ic, bad);
   unsigned long long bits = bad ? 0x7ff0000000000000ull : (unsigned long long) __double_as_longlong(ts);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { const unsigned long long other = __shfl_xor_sync(0xffffffffu, bits, o); bits = other < bits ? other : bits; }
@@ -433,6 +446,133 @@ __global__ void integ_timestep_kernel(int N, DevPtrs H, DevParams dp, gsph_integ
   if ((threadIdx.x & 31) == 0) {
     atomicMin(&red[0], bits);
     if (nbad) atomicAdd(&red[1], (unsigned long long) __popc(nbad));
+  }
+}
+
+/*------------------------------------------------------------------------------------------------
+ * Hierarchical block time steps (gsph_integrator_config::Nlevels > 1).  Per-particle integer step data live in
+ * host order next to r0, v0, ...; the level logic follows Simulation::ComputeBlockTimesteps
+ * (Simulation.cpp:1764-2199) statement by statement, incl. (int) pow(2, negative) = 0 for a particle that has just
+ * moved below the deepest level (its dt_next is 0 for that step, as in the reference).
+ *-----------------------------------------------------------------------------------------------*/
+struct BlkPtrs { int32_t* nstep; int32_t* nlast; double* dt; double* dt_next; double* tlast; };
+#define GSPH_INVLOGETWO 1.44269504088896            /* src/Headers/Constants.h:81 */
+
+__host__ __device__ __forceinline__ int pow2int(int e) { return e >= 0 ? (e < 31 ? (1 << e) : 0x40000000) : 0; }
+
+/* ComputeTimestepLevel, InlineFuncs.h:550-558 */
+__device__ __forceinline__ int timestep_level(double dt, double dt_max)
+{
+  const int l = (int)(GSPH_INVLOGETWO*log(__ddiv_rn(dt_max, dt))) + 1;
+  return l > 0 ? l : 0;
+}
+
+/* SphLeapfrogKDK::CheckTimesteps (SphLeapfrogKDK.cpp:284-339) after "unset active for every particle"
+ * (SphSimulation.cpp:735-738): red[1] += particles woken up */
+__global__ void blk_check_kernel(int N, DevPtrs H, BlkPtrs B, int n, int level_step, int ldm, unsigned long long* red)
+{
+  const int i = blockIdx.x*blockDim.x + threadIdx.x;
+  bool woke = false;
+  if (i < N) {
+    unsigned fl = ((unsigned) H.i[I_FLAGS][i]) & ~(unsigned) GSPH_FLAG_ACTIVE;
+    if (!(fl & GSPH_FLAG_DEAD)) {
+      const int dn = n - B.nlast[i];
+      const int level = H.i[I_LEVEL][i], levelneib = H.i[I_LEVELNEIB][i];
+      if (dn != B.nstep[i] && levelneib - level > ldm) {
+        const int level_new = levelneib - ldm;
+        const int nnew = pow2int(level_step - level_new);
+        if (nnew > 0 && dn % nnew == 0) {
+          if (dn > 0) B.nstep[i] = dn;
+          H.i[I_LEVEL][i] = level_new;
+          fl |= GSPH_FLAG_ACTIVE;
+          woke = true;
+        }
+      }
+    }
+    H.i[I_FLAGS][i] = (int32_t) fl;
+  }
+  const unsigned w = __ballot_sync(0xffffffffu, woke);
+  if ((threadIdx.x & 31) == 0 && w) atomicAdd(&red[1], (unsigned long long) __popc(w));
+}
+
+/* mode 0  resynchronisation, first half: dt_next = Timestep(part), global minimum           (Simulation.cpp:1808-1818)
+ * mode 1  resynchronisation, second half: levels from dt_next                                   (:1905-1917)
+ * mode 2  regular step: particles at the end of their step choose their new level; red[2] = max level (:1947-2009)
+ * mode 3  integer time rescaled by nfactor (op 1 multiply, 2 divide), then nstep of the particles that start a
+ *         step now                                                                              (:2113-2155)  */
+template <int NDIM>
+__global__ void blk_timestep_kernel(int N, DevPtrs H, BlkPtrs B, DevParams dp, gsph_integrator_config ic, int mode, int n,
+                                    int level_step, int level_max, double dt_max, double timestep, int op, int nfactor,
+                                    unsigned long long* red)
+{
+  const int i = blockIdx.x*blockDim.x + threadIdx.x;
+  const int ldm = ic.level_diff_max > 0 ? ic.level_diff_max : 1;
+  bool bad = false;
+  unsigned long long bits = 0x7ff0000000000000ull;
+  int lev_here = 0;
+  const bool alive = i < N && !(((unsigned) H.i[I_FLAGS][i]) & GSPH_FLAG_DEAD);
+  if (alive) {
+    if (mode == 0) {
+      const double ts = particle_timestep<NDIM>(i, H, dp, ic, bad);
+      B.dt_next[i] = ts;
+      if (!bad) bits = (unsigned long long) __double_as_longlong(ts);
+    }
+    else if (mode == 1) {
+      int level = timestep_level(B.dt_next[i], dt_max);
+      if (level > level_max) level = level_max;
+      H.i[I_LEVEL][i] = level; H.i[I_LEVELNEIB][i] = level;
+      const int ns = pow2int(level_step - level);
+      B.nstep[i] = ns; B.nlast[i] = n;
+      B.dt_next[i] = __dmul_rn((double) ns, timestep);
+      H.i[I_FLAGS][i] = (int32_t)(((unsigned) H.i[I_FLAGS][i]) | GSPH_FLAG_END_TIMESTEP);
+    }
+    else if (mode == 2) {
+      const int nstep = B.nstep[i];
+      int plevel = H.i[I_LEVEL][i];
+      if (n - B.nlast[i] == nstep) {
+        const double ts = particle_timestep<NDIM>(i, H, dp, ic, bad);
+        int level = timestep_level(ts, dt_max);
+        const int lnb = H.i[I_LEVELNEIB][i] - ldm;
+        if (lnb > level) level = lnb;
+        if (nstep != pow2int(level_step - plevel)) {          /* step cut short by the neighbour-level limiter */
+          if (level > plevel) plevel = level;
+          H.i[I_LEVELNEIB][i] = plevel;
+        }
+        else {                                               /* natural end of the step */
+          const int last_level = plevel;
+          if (level < last_level && last_level > 1 && n % (2*nstep) == 0) plevel = last_level - 1;
+          else if (level > last_level) plevel = level;
+          H.i[I_LEVELNEIB][i] = level;
+        }
+        H.i[I_LEVEL][i] = plevel;
+        B.nlast[i] = n;
+        const int ns = pow2int(level_step - plevel);
+        B.nstep[i] = ns;
+        B.dt_next[i] = __dmul_rn((double) ns, timestep);
+        H.i[I_FLAGS][i] = (int32_t)(((unsigned) H.i[I_FLAGS][i]) | GSPH_FLAG_END_TIMESTEP);
+      }
+      lev_here = plevel;
+    }
+    else {
+      int ns = B.nstep[i], nl = B.nlast[i];
+      if (op == 1) { ns *= nfactor; nl *= nfactor; }
+      else if (op == 2) { ns /= nfactor; nl /= nfactor; }
+      if (nl == n) ns = pow2int(level_step - H.i[I_LEVEL][i]);
+      B.nstep[i] = ns; B.nlast[i] = nl;
+    }
+  }
+  if (mode == 0 || mode == 2) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, bits, o); bits = other < bits ? other : bits;
+      lev_here = max(lev_here, __shfl_xor_sync(0xffffffffu, lev_here, o));
+    }
+    const unsigned nbad = __ballot_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0) {
+      if (mode == 0) atomicMin(&red[0], bits);
+      if (nbad) atomicAdd(&red[1], (unsigned long long) __popc(nbad));
+      if (mode == 2) atomicMax(&red[2], (unsigned long long) lev_here);
+    }
   }
 }
 
@@ -449,12 +589,19 @@ __global__ void integ_init_kernel(int N, DevPtrs H, IntegPtrs S)
 
 /* SphLeapfrogKDK::EndTimestep (SphLeapfrogKDK.cpp:226-270); dtp = part.dt, the step just taken */
 template <int NDIM>
-__global__ void integ_end_kernel(int N, DevPtrs H, IntegPtrs S, double dtp, int energy)
+__global__ void integ_end_kernel(int N, DevPtrs H, IntegPtrs S, double dtp, int energy, int block, int n, double t,
+                                 int32_t* __restrict__ nlast, double* __restrict__ pdt, double* __restrict__ dt_next,
+                                 double* __restrict__ tlast)
 {
   const int i = blockIdx.x*blockDim.x + threadIdx.x;
   if (i >= N) return;
   const unsigned fl = (unsigned) H.i[I_FLAGS][i];
   if (fl & GSPH_FLAG_DEAD) return;
+  if (block) {                                              /* only the particles whose step ends now */
+    if (!(fl & GSPH_FLAG_END_TIMESTEP)) return;
+    dtp = pdt[i];                                           /* part.dt: the step just taken */
+    nlast[i] = n; tlast[i] = t; pdt[i] = dt_next[i]; dt_next[i] = 0.0;
+  }
   const double hdt = __dmul_rn(0.5, dtp);
 #pragma unroll
   for (int k = 0; k < NDIM; k++) {
@@ -469,7 +616,7 @@ __global__ void integ_end_kernel(int N, DevPtrs H, IntegPtrs S, double dtp, int 
     if (u <= 0.0) u = __dadd_rn(S.u0[i], __dmul_rn(S.dudt0[i], dtp));
     H.f[F_U][i] = u; S.u0[i] = u; S.dudt0[i] = dudt;
   }
-  H.i[I_FLAGS][i] = (int32_t)(fl & ~(unsigned) GSPH_FLAG_ACTIVE);
+  H.i[I_FLAGS][i] = (int32_t)(fl & ~(unsigned)(GSPH_FLAG_ACTIVE | GSPH_FLAG_END_TIMESTEP));
 }
 
 int gsph_check_status(gsph_handle* h, const char* where)
@@ -568,6 +715,7 @@ void gsph_destroy(gsph_handle* h)
   for (int f = 0; f < NF_DOUBLE; f++) { fre(h->H[f]); fre(h->P[f]); }
   for (int f = 0; f < NF_INT; f++) { fre(h->HI[f]); fre(h->PI[f]); }
   for (int k = 0; k < 11; k++) fre(h->integ.s0[k]);
+  fre(h->integ.nstep); fre(h->integ.nlast); fre(h->integ.pdt); fre(h->integ.dt_next); fre(h->integ.ptlast);
   fre(h->integ.red); fre(h->perm); fre(h->tables); fre(h->scratch); fre(h->cand); fre(h->gravlist); fre(h->status); fre(h->work_counter); fre(h->done); fre(h->needed); fre(h->pre_cand); fre(h->pre_count); fre(h->geo4); fre(h->geoh); fre(h->frec); fre(h->nlist); fre(h->hnew); fre(h->stars); fre(h->gstack);
   TreeDev& T = h->tree;
   fre(T.first); fre(T.count); fre(T.nactive); fre(T.m); fre(T.rmax); fre(T.hmax); fre(T.cdistsqd);
@@ -1512,6 +1660,9 @@ static int integ_forces(gsph_handle* h)
 {
   int rc = gsph_update_properties(h); if (rc) return rc;
   rc = gsph_zero_accelerations(h); if (rc) return rc;
+  /* nradstep = 1: MainLoop refreshes the thermal properties of every particle here (SphSimulation.cpp:669-679);
+     with one global step the density pass has just done exactly that for all of them */
+  if (h->integ.cfg.Nlevels > 1 && (h->integ.on || h->integ.starting)) { rc = gsph_thermal_all_impl(h); if (rc) return rc; }
   if (h->cfg.self_gravity) rc = gsph_update_all_forces(h, NULL, 0);
   else if (h->cfg.hydro_forces) rc = gsph_update_hydro_forces(h);
   else { h->err = "Error: No forces included in simulation"; return GSPH_EINVAL; }   /* SphSimulation.cpp:467 */
@@ -1592,6 +1743,102 @@ static double integ_star_timestep(const gsph_handle* h)
   return ts;
 }
 
+/* ---- block time steps: host side of Simulation::ComputeBlockTimesteps (Simulation.cpp:1764-2199) ------------ */
+static BlkPtrs blk_ptrs(gsph_handle* h)
+{
+  BlkPtrs B; B.nstep = h->integ.nstep; B.nlast = h->integ.nlast; B.dt = h->integ.pdt; B.dt_next = h->integ.dt_next; B.tlast = h->integ.ptlast;
+  return B;
+}
+static inline bool integ_block(const gsph_handle* h) { return h->integ.cfg.Nlevels > 1; }
+
+#define BLK_LAUNCH(MODE, OP, NFACTOR)                                                                        \
+  INTEG_LAUNCH(blk_timestep_kernel, (int) h->N, devptrs(h->H, h->HI), blk_ptrs(h), h->dp, I.cfg, MODE, (int) I.n, I.level_step, \
+               I.level_max, I.dt_max, I.timestep, OP, NFACTOR, I.red)
+
+static int blk_compute_timesteps(gsph_handle* h)
+{
+  IntegState& I = h->integ;
+  const unsigned long long init[3] = {0x7ff0000000000000ull, 0ull, 0ull};
+  unsigned long long res[3];
+  CUDA_TRY(h, cudaMemcpyAsync(I.red, init, sizeof init, cudaMemcpyHostToDevice, h->stream));
+  if (I.n == I.nresync) {                                 /* synchronise every step and rebuild the hierarchy */
+    I.n = 0;
+    BLK_LAUNCH(0, 0, 1);
+    CUDA_TRY(h, cudaMemcpyAsync(res, I.red, sizeof res, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (res[1]) { h->err = "Error : Hydro timestep too large"; return GSPH_ESTATE; }
+    double ts; memcpy(&ts, &res[0], sizeof ts);
+    I.timestep = ts;
+    I.level_max = I.cfg.Nlevels - 1;
+    I.level_step = I.level_max;                            /* + integration_step - 1, = 0 for the KDK leapfrog */
+    I.dt_max = I.timestep*pow(2.0, I.level_max);
+    BLK_LAUNCH(1, 0, 1);
+    I.nresync = (long long) pow2int(I.level_step);
+    I.timestep = I.dt_max/(double) I.nresync;
+  }
+  else {
+    const int level_max_old = I.level_max;
+    BLK_LAUNCH(2, 0, 1);
+    CUDA_TRY(h, cudaMemcpyAsync(res, I.red, sizeof res, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (res[1]) { h->err = "Error : Hydro timestep too large"; return GSPH_ESTATE; }
+    I.level_max = (int) res[2];
+    const long long istep = pow2int(I.level_step - level_max_old + 1);
+    int op = 0, nfactor = 1;
+    if (I.level_max > level_max_old) {                     /* levels added: finer integer time */
+      nfactor = pow2int(I.level_max - level_max_old); op = 1;
+      I.n *= nfactor;
+    }
+    else if (I.level_max <= level_max_old - 1 && level_max_old > 1 && istep > 0 && I.n % istep == 0) {
+      I.level_max = level_max_old - 1;                     /* one level removed */
+      nfactor = pow2int(level_max_old - I.level_max); op = 2;
+      I.n /= nfactor;
+    }
+    else I.level_max = level_max_old;
+    I.level_step = I.level_max;
+    I.nresync = (long long) pow2int(I.level_step);
+    I.timestep = I.dt_max/(double) I.nresync;
+    BLK_LAUNCH(3, op, nfactor);
+  }
+  if (!(I.timestep > 0.0)) { h->err = "Error : timestep fallen to zero"; return GSPH_ESTATE; }
+  return GSPH_OK;
+}
+
+/* after a pass of a block-time-step MainLoop: results back to host order, every active flag cleared,
+   SphLeapfrogKDK::CheckTimesteps; *woken = particles whose step was cut short (they need the passes now) */
+static int blk_check_timesteps(gsph_handle* h, int* woken)
+{
+  IntegState& I = h->integ;
+  int rc = integ_scatter_results(h); if (rc) return rc;
+  const unsigned long long init[3] = {0x7ff0000000000000ull, 0ull, 0ull};
+  unsigned long long res[3];
+  CUDA_TRY(h, cudaMemcpyAsync(I.red, init, sizeof init, cudaMemcpyHostToDevice, h->stream));
+  const int ldm = I.cfg.level_diff_max > 0 ? I.cfg.level_diff_max : 1;
+  blk_check_kernel<<<(int)((h->N + 255)/256), 256, 0, h->stream>>>((int) h->N, devptrs(h->H, h->HI), blk_ptrs(h), (int) I.n, I.level_step, ldm, I.red);
+  h->stats.kernel_launches++;
+  CUDA_TRY(h, cudaMemcpyAsync(res, I.red, sizeof res, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  *woken = (int) res[1];
+  return GSPH_OK;
+}
+
+/* the woken particles' flags and levels reach the tree-order arrays; active counters of the cells
+   (sphneib->UpdateActiveParticleCounters, SphSimulation.cpp:661) */
+__global__ void blk_push_flags_kernel(int N, const int32_t* __restrict__ perm, DevPtrs H, DevPtrs P)
+{
+  const int p = blockIdx.x*blockDim.x + threadIdx.x;
+  if (p >= N) return;
+  const int i = perm[p];
+  P.i[I_FLAGS][p] = H.i[I_FLAGS][i]; P.i[I_LEVEL][p] = H.i[I_LEVEL][i];
+}
+static int blk_push_flags(gsph_handle* h)
+{
+  blk_push_flags_kernel<<<(int)((h->N + 255)/256), 256, 0, h->stream>>>((int) h->N, h->perm, devptrs(h->H, h->HI), devptrs(h->P, h->PI));
+  h->stats.kernel_launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return gsph_update_active_counters(h);
+}
+
 /* rows = Nstar x {r[ndim], v[ndim], a[ndim], m, h}: the stars the next gsph_integrator_begin starts with
    (a is only read by compute_forces = 0).  Nstar = 0 removes them.                                    */
 int gsph_integrator_set_stars(gsph_handle* h, const double* rows, int Nstar, double nbody_mult)
@@ -1661,14 +1908,36 @@ int gsph_integrator_begin(gsph_handle* h, const gsph_integrator_config* cfg, int
     for (int k = 0; k < 11; k++) CUDA_TRY(h, cudaMalloc(&I.s0[k], (size_t) h->Ncap*sizeof(double)));
     I.cap = h->Ncap;
   }
-  if (!I.red) CUDA_TRY(h, cudaMalloc(&I.red, 2*sizeof(unsigned long long)));
+  if (!I.red) CUDA_TRY(h, cudaMalloc(&I.red, 4*sizeof(unsigned long long)));
+  if (cfg->Nlevels > 1) {
+    if (I.nstar > 0) { h->err = "gsph_integrator_begin: star particles with block time steps (Nlevels > 1) are not on the accelerated path"; return GSPH_EINVAL; }
+    if (h->dp.any_mirror) { h->err = "gsph_integrator_begin: block time steps with mirror boundaries are not on the accelerated path"; return GSPH_EINVAL; }
+    if (h->dp.tdavisc == GSPH_TDAVISC_CD2010) { h->err = "gsph_integrator_begin: block time steps with time_dependent_avisc = cd2010 are not on the accelerated path"; return GSPH_EINVAL; }
+    if (compute_forces == 2 || h->slice_mode) { h->err = "gsph_integrator_begin: block time steps run on one device (gsph_integrator_step)"; return GSPH_EINVAL; }
+    if (cfg->Nlevels > 30) { h->err = "gsph_integrator_begin: Nlevels must be <= 30"; return GSPH_EINVAL; }
+    if (I.blk_cap < h->Ncap) {
+      auto fre = [](void* p) { if (p) cudaFree(p); };
+      fre(I.nstep); fre(I.nlast); fre(I.pdt); fre(I.dt_next); fre(I.ptlast);
+      I.nstep = I.nlast = nullptr; I.pdt = I.dt_next = I.ptlast = nullptr; I.blk_cap = 0;
+      CUDA_TRY(h, cudaMalloc(&I.nstep, (size_t) h->Ncap*sizeof(int32_t)));
+      CUDA_TRY(h, cudaMalloc(&I.nlast, (size_t) h->Ncap*sizeof(int32_t)));
+      CUDA_TRY(h, cudaMalloc(&I.pdt, (size_t) h->Ncap*sizeof(double)));
+      CUDA_TRY(h, cudaMalloc(&I.dt_next, (size_t) h->Ncap*sizeof(double)));
+      CUDA_TRY(h, cudaMalloc(&I.ptlast, (size_t) h->Ncap*sizeof(double)));
+      I.blk_cap = h->Ncap;
+    }
+  }
   I.cfg = *cfg; I.t = I.tlast = t0; I.Nsteps = 0; I.rebuild = true; I.on = false; I.mid_step = false;
+  I.n = I.nresync = 0; I.level_max = I.level_step = 0; I.dt_max = 0.0;
   h->hdef_d = 0ull; h->hdef_i = 0u;                     /* the integrator writes the host-order arrays */
   CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_all, 0));          /* the upload has landed */
   if (I.nstar > 0) { const int rs = integ_push_stars(h); if (rs) return rs; }
   if (compute_forces == 1) {
     int rc = gsph_build_tree(h, 0, 0.0); if (rc) return rc;
-    rc = integ_forces(h); if (rc) return rc;
+    I.starting = true;
+    rc = integ_forces(h);
+    I.starting = false;
+    if (rc) return rc;
   }
   if (compute_forces) { const int rc = integ_scatter_results(h); if (rc) return rc; }
   if (I.nstar > 0) {
@@ -1676,10 +1945,26 @@ int gsph_integrator_begin(gsph_handle* h, const gsph_integrator_config* cfg, int
     I.sr0 = I.sr; I.sv0 = I.sv; I.sa0 = I.sa;
   }
   INTEG_LAUNCH(integ_init_kernel, (int) h->N, devptrs(h->H, h->HI), integ_ptrs(h));
-  int rc = integ_global_timestep(h, &I.timestep); if (rc) return rc;
+  int rc;
+  if (integ_block(h)) {
+    /* PostInitialConditionsSetup: ComputeBlockTimesteps with n = nresync = 0 (a resynchronisation), then
+       EndTimestep with part.dt = 0 (SphSimulation.cpp:544-563) */
+    CUDA_TRY(h, cudaMemsetAsync(I.nstep, 0, (size_t) h->N*sizeof(int32_t), h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(I.nlast, 0, (size_t) h->N*sizeof(int32_t), h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(I.pdt, 0, (size_t) h->N*sizeof(double), h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(I.dt_next, 0, (size_t) h->N*sizeof(double), h->stream));
+    fill_kernel<double><<<(int)((h->N + 255)/256), 256, 0, h->stream>>>(h->N, I.ptlast, t0);
+    rc = blk_compute_timesteps(h); if (rc) return rc;
+    INTEG_LAUNCH(integ_end_kernel, (int) h->N, devptrs(h->H, h->HI), integ_ptrs(h), 0.0, I.cfg.energy_integration, 1,
+                 (int) I.n, I.t, I.nlast, I.pdt, I.dt_next, I.ptlast);
+    I.on = true;
+    return GSPH_OK;
+  }
+  rc = integ_global_timestep(h, &I.timestep); if (rc) return rc;
   if (I.nstar > 0) I.timestep = std::min(I.timestep, integ_star_timestep(h));
   /* EndTimestep with part.dt = 0 (SphSimulation.cpp:561): u0 = u, dudt0 = dudt */
-  INTEG_LAUNCH(integ_end_kernel, (int) h->N, devptrs(h->H, h->HI), integ_ptrs(h), 0.0, I.cfg.energy_integration);
+  INTEG_LAUNCH(integ_end_kernel, (int) h->N, devptrs(h->H, h->HI), integ_ptrs(h), 0.0, I.cfg.energy_integration, 0, 0, 0.0,
+               (int32_t*) nullptr, (double*) nullptr, (double*) nullptr, (double*) nullptr);
   I.on = true;
   return GSPH_OK;
 }
@@ -1694,12 +1979,15 @@ int gsph_integrator_advance(gsph_handle* h, int* tree_mode, double* timestep)
   if (h->integ.mid_step) { h->err = "gsph_integrator_advance: the previous step was not finished"; return GSPH_ESTATE; }
   cudaSetDevice(h->device);
   IntegState& I = h->integ;
+  if (integ_block(h) && !I.in_step) { h->err = "gsph_integrator_advance: block time steps (Nlevels > 1) run through gsph_integrator_step on one device"; return GSPH_EINVAL; }
   I.Nsteps++;
+  I.n++;
   const double ts = I.timestep;
   I.t = I.t + ts;
   const double dt = I.t - I.tlast;
   INTEG_LAUNCH(integ_advance_kernel, (int) h->N, devptrs(h->H, h->HI), integ_ptrs(h), h->dp, dt, ts,
-               h->dp.tdavisc != GSPH_TDAVISC_NONE ? 1 : 0, I.cfg.energy_integration);
+               h->dp.tdavisc != GSPH_TDAVISC_NONE ? 1 : 0, I.cfg.energy_integration, integ_block(h) ? 1 : 0, I.t, (int) I.n,
+               (const int32_t*) I.nstep, (const int32_t*) I.nlast, (const double*) I.ptlast);
   if (I.nstar > 0) {                                   /* NbodyLeapfrogKDK::AdvanceParticles */
     for (size_t q = 0; q < I.sr.size(); q++) {
       I.sr[q] = I.sr0[q] + I.sv0[q]*dt + 0.5*I.sa0[q]*dt*dt;
@@ -1728,10 +2016,12 @@ int gsph_integrator_finish(gsph_handle* h)
 {
   if (!h) return GSPH_EINVAL;
   if (!h->integ.on || !h->integ.mid_step) { h->err = "gsph_integrator_finish before gsph_integrator_advance"; return GSPH_ESTATE; }
+  if (integ_block(h) && !h->integ.in_step) { h->err = "gsph_integrator_finish: block time steps (Nlevels > 1) run through gsph_integrator_step on one device"; return GSPH_EINVAL; }
   if (!h->sorted_valid) { h->err = "gsph_integrator_finish before the passes of this step"; return GSPH_ESTATE; }
   cudaSetDevice(h->device);
   IntegState& I = h->integ;
-  int rc = integ_scatter_results(h); if (rc) return rc;
+  int rc = GSPH_OK;
+  if (!integ_block(h)) { rc = integ_scatter_results(h); if (rc) return rc; }      /* (block steps: blk_check_timesteps did) */
   if (h->dp.any_periodic) {
     double hmax = 0.0;
     rc = gsph_get_hmax(h, &hmax); if (rc) return rc;
@@ -1744,6 +2034,16 @@ int gsph_integrator_finish(gsph_handle* h)
     const double dts = I.t - I.tlast;                  /* NbodyLeapfrogKDK::CorrectionTerms */
     for (size_t q = 0; q < I.sv.size(); q++) I.sv[q] += 0.5*(I.sa[q] - I.sa0[q])*dts;
   }
+  if (integ_block(h)) {
+    rc = blk_compute_timesteps(h); if (rc) return rc;   /* new levels; I.n, I.timestep of the next step */
+    I.rebuild = false;
+    INTEG_LAUNCH(integ_end_kernel, (int) h->N, devptrs(h->H, h->HI), integ_ptrs(h), 0.0, I.cfg.energy_integration, 1,
+                 (int) I.n, I.t, I.nlast, I.pdt, I.dt_next, I.ptlast);
+    I.tlast = I.t;
+    I.mid_step = false;
+    h->p_stale = true;
+    return GSPH_OK;
+  }
   double next = 0.0;
   rc = integ_global_timestep(h, &next); if (rc) return rc;
   if (I.nstar > 0) {
@@ -1751,7 +2051,8 @@ int gsph_integrator_finish(gsph_handle* h)
     I.sr0 = I.sr; I.sv0 = I.sv; I.sa0 = I.sa;          /* NbodyLeapfrogKDK::EndTimestep */
   }
   I.rebuild = false;
-  INTEG_LAUNCH(integ_end_kernel, (int) h->N, devptrs(h->H, h->HI), integ_ptrs(h), I.timestep, I.cfg.energy_integration);
+  INTEG_LAUNCH(integ_end_kernel, (int) h->N, devptrs(h->H, h->HI), integ_ptrs(h), I.timestep, I.cfg.energy_integration, 0, 0, 0.0,
+               (int32_t*) nullptr, (double*) nullptr, (double*) nullptr, (double*) nullptr);
   I.tlast = I.t;
   I.timestep = next;
   I.mid_step = false;
@@ -1766,10 +2067,27 @@ int gsph_integrator_step(gsph_handle* h, int nsteps)
   if (nsteps < 0) { h->err = "gsph_integrator_step: nsteps < 0"; return GSPH_EINVAL; }
   for (int s = 0; s < nsteps; s++) {
     int mode = 0; double ts = 0.0;
-    int rc = gsph_integrator_advance(h, &mode, &ts); if (rc) return rc;
+    h->integ.in_step = true;
+    int rc = gsph_integrator_advance(h, &mode, &ts);
+    h->integ.in_step = false;
+    if (rc) return rc;
     rc = gsph_build_tree(h, mode, ts); if (rc) return rc;
     rc = integ_forces(h); if (rc) return rc;
-    rc = gsph_integrator_finish(h); if (rc) return rc;
+    if (integ_block(h)) {
+      /* the passes are repeated for the particles whose step CheckTimesteps cuts short (SphSimulation.cpp:658-756) */
+      for (int it = 0; ; it++) {
+        int woken = 0;
+        rc = blk_check_timesteps(h, &woken); if (rc) return rc;
+        if (woken == 0) break;
+        if (it > 64) { h->err = "gsph_integrator_step: the neighbour time-step limiter does not settle"; return GSPH_ESTATE; }
+        rc = blk_push_flags(h); if (rc) return rc;
+        rc = integ_forces(h); if (rc) return rc;
+      }
+    }
+    h->integ.in_step = true;
+    rc = gsph_integrator_finish(h);
+    h->integ.in_step = false;
+    if (rc) return rc;
   }
   return GSPH_OK;
 }
@@ -1781,6 +2099,25 @@ int gsph_integrator_state(gsph_handle* h, double* t, double* timestep, int64_t* 
   if (t) *t = h->integ.t;
   if (timestep) *timestep = h->integ.timestep;
   if (nsteps) *nsteps = h->integ.Nsteps;
+  return GSPH_OK;
+}
+
+int gsph_integrator_block_state(gsph_handle* h, gsph_block_state* st, int32_t* nstep, int32_t* nlast, double* dt, double* tlast)
+{
+  if (!h) return GSPH_EINVAL;
+  if (!h->integ.on) { h->err = "gsph_integrator_block_state before gsph_integrator_begin"; return GSPH_ESTATE; }
+  const IntegState& I = h->integ;
+  if (st) { st->n = I.n; st->nresync = I.nresync; st->level_max = I.level_max; st->level_step = I.level_step; st->dt_max = I.dt_max; }
+  if (nstep || nlast || dt || tlast) {
+    if (I.cfg.Nlevels <= 1) { h->err = "gsph_integrator_block_state: per-particle step data exist with Nlevels > 1 only"; return GSPH_EINVAL; }
+    cudaSetDevice(h->device);
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    const size_t N = (size_t) h->N;
+    if (nstep) CUDA_TRY(h, cudaMemcpy(nstep, I.nstep, N*sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (nlast) CUDA_TRY(h, cudaMemcpy(nlast, I.nlast, N*sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (dt) CUDA_TRY(h, cudaMemcpy(dt, I.pdt, N*sizeof(double), cudaMemcpyDeviceToHost));
+    if (tlast) CUDA_TRY(h, cudaMemcpy(tlast, I.ptlast, N*sizeof(double), cudaMemcpyDeviceToHost));
+  }
   return GSPH_OK;
 }
 

@@ -709,7 +709,32 @@ __global__ void derive_density_fields_kernel(int N, int lo, int hi, PartView P, 
   P.f[F_U][ti] = u; P.f[F_SOUND][ti] = cs; P.f[F_PRESS][ti] = pr;
 }
 
+/* GradhSph::ComputeThermalProperties (GradhSph.cpp:335-347) for EVERY particle, active or not: what MainLoop does
+ * before the force pass when nradstep = 1 (SphSimulation.cpp:669-679).  With block time steps the inactive
+ * neighbours then enter the force sums with the sound speed and pressure of their PREDICTED u.            */
+__global__ void thermal_all_kernel(int N, PartView P, DevParams dp)
+{
+  const int ti = blockIdx.x*blockDim.x + threadIdx.x;
+  if (ti >= N) return;
+  if (((unsigned) P.i[I_FLAGS][ti]) & GSPH_FLAG_DEAD) return;
+  double u = P.f[F_U][ti], cs, pr;
+  thermal(dp, P.f[F_RHO][ti], u, cs, pr);
+  P.f[F_U][ti] = u; P.f[F_SOUND][ti] = cs; P.f[F_PRESS][ti] = pr;
+}
+
 }  // namespace
+
+int gsph_thermal_all_impl(gsph_handle* h)
+{
+  const int N = (int) h->N;
+  PartView P;
+  for (int k = 0; k < NF_DOUBLE; k++) P.f[k] = h->P[k];
+  for (int k = 0; k < NF_INT; k++) P.i[k] = h->PI[k];
+  thermal_all_kernel<<<(N + 255)/256, 256, 0, h->stream>>>(N, P, h->dp);
+  h->stats.kernel_launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return GSPH_OK;
+}
 
 int gsph_derive_density_fields_impl(gsph_handle* h, int lo, int hi)
 {

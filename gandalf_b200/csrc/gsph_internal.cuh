@@ -126,6 +126,16 @@ struct IntegState {
   int64_t Nsteps = 0;
   bool rebuild = true;
   bool mid_step = false;     /* between gsph_integrator_advance and gsph_integrator_finish */
+  bool in_step = false;      /* inside gsph_integrator_step (block time steps only run there) */
+  bool starting = false;     /* inside gsph_integrator_begin's first force pass */
+  /* hierarchical block time steps (cfg.Nlevels > 1): per-particle integer step / start of step (host order) and the
+     scalars of Simulation::ComputeBlockTimesteps */
+  int32_t* nstep = nullptr; int32_t* nlast = nullptr;
+  double* pdt = nullptr; double* dt_next = nullptr; double* ptlast = nullptr;     /* Particle::dt, dt_next, tlast */
+  int64_t blk_cap = 0;
+  long long n = 0, nresync = 0;
+  int level_max = 0, level_step = 0;
+  double dt_max = 0.0;
   /* star particles: the N-body leapfrog (NbodyLeapfrogKDK.cpp) runs on the host around the device passes */
   int nstar = 0;
   double nbody_mult = 0.1;
@@ -228,6 +238,7 @@ int gsph_tree_build_sharded(gsph_handle* h, int phase, int rank, int world);
 int gsph_tree_update_hmax(gsph_handle* h);
 int gsph_tree_update_active(gsph_handle* h);
 int gsph_derive_density_fields_impl(gsph_handle* h, int lo, int hi);   /* density.cu */
+int gsph_thermal_all_impl(gsph_handle* h);                            /* density.cu: ComputeThermalProperties of every particle */
 int gsph_run_density(gsph_handle* h);                                 /* density.cu */
 int gsph_run_hydro(gsph_handle* h, int with_gravity);                 /* hydro.cu   */
 int gsph_run_neiblist(gsph_handle* h, int32_t* counts_dev, const int64_t* offsets_dev, int32_t* idx_dev);

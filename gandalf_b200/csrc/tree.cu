@@ -1110,10 +1110,10 @@ int gsph_gather_fields(gsph_handle* h)
   const int nd = h->dp.ndim;
   /* inside a step of the resident loop every particle was just made active (one global time step); a
      BuildTree between steps sees the flags EndTimestep left (inactive): everything is permuted then */
-  const bool integ = h->integ.on && h->integ.mid_step;
+  const bool integ = h->integ.on && h->integ.mid_step && h->integ.cfg.Nlevels <= 1;
   const unsigned long long ALLD = (1ull << NF_DOUBLE) - 1ull; const unsigned ALLI = (1u << NF_INT) - 1u;
   unsigned long long dmask, dfill = 0ull; unsigned imask, ifill = 0u;
-  h->lazy_fields = integ || (!h->integ.on && !((h->present_i >> I_FLAGS) & 1u));
+  h->lazy_fields = integ || (!h->integ.on && !h->integ.starting && !((h->present_i >> I_FLAGS) & 1u));
   if (!h->lazy_fields) { dmask = ALLD; imask = ALLI; }
   else {
     unsigned long long core = GSPH_DMASK(F_M) | GSPH_DMASK(F_H) | GSPH_DMASK(F_U) | GSPH_DMASK(F_ALPHA);

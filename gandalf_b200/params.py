@@ -19,7 +19,7 @@ DEFAULTS = {
     "gravity_mac": "geometric", "multipole": "quadrupole", "thetamaxsqd": 0.1, "macerror": 0.0001,
     "Nleafmax": 6, "ntreebuildstep": 1, "ntreestockstep": 1, "create_sinks": 0, "conservative_sph_star_gravity": 1, "nbody_softening": 1, "sink_particles": 0,
     "Nlevels": 1, "sph_integration": "lfkdk", "accel_mult": 0.3, "courant_mult": 0.15, "energy_mult": 0.4,
-    "nbody": "hermite4", "nbody_mult": 0.1,
+    "nbody": "hermite4", "nbody_mult": 0.1, "level_diff_max": 1, "sph_single_timestep": 0,
 }
 for _k in range(3):
     DEFAULTS["boundary_lhs[%d]" % _k] = "open"
@@ -66,12 +66,15 @@ class Parameters(dict):
 
 def integrator_config_from_params(p):
     """-> _capi.IntegratorConfig for gsph_integrator_begin (the device-resident main loop): lfkdk with one
-    global time step; energy_integration as GradhSphSimulation.cpp:110-123 derives it from gas_eos."""
+    global time step or (Nlevels > 1) hierarchical block time steps; energy_integration as
+    GradhSphSimulation.cpp:110-123 derives it from gas_eos."""
     q = Parameters(p)
     if q["sph_integration"] != "lfkdk":
         raise ValueError("sph_integration = %s is not on the accelerated path (lfkdk only)" % q["sph_integration"])
-    if int(q["Nlevels"]) != 1:
-        raise ValueError("the device-resident main loop uses one global time step (Nlevels = 1)")
+    if int(q["Nlevels"]) < 1:
+        raise ValueError("Nlevels must be >= 1")
+    if int(q["Nlevels"]) > 1 and int(q["sph_single_timestep"]) != 0:
+        raise ValueError("sph_single_timestep = 1 is not on the accelerated path of the device-resident main loop")
     if int(q["sink_particles"]) != 0 or int(q["create_sinks"]) != 0:
         # MainLoop would run SearchForNewSinkParticles / AccreteMassToSinks / UpdateStellarProperties
         # (SphSimulation.cpp:815-833): not on the accelerated path
@@ -83,6 +86,8 @@ def integrator_config_from_params(p):
     c.energy_integration = 1 if q["gas_eos"] == "energy_eqn" else 0
     c.ntreebuildstep, c.ntreestockstep = int(q["ntreebuildstep"]), int(q["ntreestockstep"])
     c.sink_particles = int(q["sink_particles"])
+    c.Nlevels = int(q["Nlevels"])
+    c.level_diff_max = int(q["level_diff_max"])
     return c
 
 

@@ -256,6 +256,21 @@ class GpuSphTree(object):
         self._check(self._L.gsph_integrator_state(self._h, C.byref(t), C.byref(ts), C.byref(n)))
         return t.value, ts.value, n.value
 
+    def IntegratorBlockState(self, arrays=False):
+        """block time steps (Nlevels > 1): dict n, nresync, level_max, level_step, dt_max of the hierarchy
+        (Simulation::ComputeBlockTimesteps) and, with arrays=True, nstep, nlast, dt, tlast of every particle"""
+        st = _capi.BlockState()
+        out = {}
+        if arrays:
+            N = self.Stats().Nhydro
+            out = {"nstep": np.zeros(N, dtype=np.int32), "nlast": np.zeros(N, dtype=np.int32), "dt": np.zeros(N), "tlast": np.zeros(N)}
+            self._check(self._L.gsph_integrator_block_state(self._h, C.byref(st), out["nstep"].ctypes.data, out["nlast"].ctypes.data,
+                                                            out["dt"].ctypes.data, out["tlast"].ctypes.data))
+        else:
+            self._check(self._L.gsph_integrator_block_state(self._h, C.byref(st), None, None, None, None))
+        out.update(n=st.n, nresync=st.nresync, level_max=st.level_max, level_step=st.level_step, dt_max=st.dt_max)
+        return out
+
     # ---- snapshots in the reference's "su" wire format (gandalf_b200/snapshot.py) ------------------
     def WriteSnapshot(self, path, alloc=None, **header):
         """SEREN-unformatted snapshot of the particles on the device (SimulationIO.hpp:1655-2262): only

@@ -70,7 +70,8 @@ enum { GSPH_MULTIPOLE_MONOPOLE = 0, GSPH_MULTIPOLE_QUADRUPOLE = 1,
 enum { GSPH_TYPE_GAS = 0, GSPH_TYPE_ICM = 1, GSPH_TYPE_CDM = 2, GSPH_TYPE_DUST = 3,
        GSPH_TYPE_BOUNDARY = 4, GSPH_NTYPES = 5 };
 /* flag bits of Particle::flags used by the path (src/Headers/Flags.h:93-136)                       */
-enum { GSPH_FLAG_DEAD = 1u << 0, GSPH_FLAG_ACTIVE = 1u << 1, GSPH_FLAG_POTMIN = 1u << 3 };
+enum { GSPH_FLAG_DEAD = 1u << 0, GSPH_FLAG_ACTIVE = 1u << 1, GSPH_FLAG_POTMIN = 1u << 3,
+       GSPH_FLAG_END_TIMESTEP = 1u << 4   /* device-resident loop: the particle ends its step now (Particle.h end_timestep) */ };
 
 /* ---- configuration ----------------------------------------------------------------------------
  * Everything the reference passes to GradhSph / GradhSphTree constructors
@@ -334,8 +335,14 @@ int gsph_get_stats(gsph_handle* h, gsph_stats* st);
  *   Simulation::ComputeGlobalTimestep            src/Common/Simulation.cpp:1669-1745
  *   TimeIntegration::CheckBoundaries             src/Common/Integration.cpp:11-75
  * around the operators above (BuildTree, UpdateAllSphProperties, ZeroAccelerations, force pass).
- * Star particles: gsph_integrator_set_stars below.  Not covered (GSPH_EINVAL): block time steps, sinks,
- * external potentials, dust.                                                                       */
+ * Block time steps (gsph_integrator_config::Nlevels > 1, single device): additionally
+ *   Simulation::ComputeBlockTimesteps            src/Common/Simulation.cpp:1764-2199
+ *   SphLeapfrogKDK::CheckTimesteps               src/Hydrodynamics/SphLeapfrogKDK.cpp:284-339 (neighbour-level limiter; the
+ *                                                passes are repeated for the particles it wakes, SphSimulation.cpp:658-756)
+ *   the thermal refresh of every particle before the force pass (nradstep = 1, SphSimulation.cpp:669-679).
+ * gsph_integrator_begin then sets up the hierarchy like PostInitialConditionsSetup (a resynchronisation at n = 0).
+ * Star particles: gsph_integrator_set_stars below (one global time step only).  Not covered (GSPH_EINVAL): sinks,
+ * external potentials, dust, sph_single_timestep, block time steps on several ranks or with stars.     */
 typedef struct gsph_integrator_config {
   double  accel_mult, courant_mult, energy_mult;   /* Parameters.cpp:239,240,263 (0.3, 0.15, 0.4)      */
   int32_t energy_integration;   /* 1: u is integrated explicitly (gas_eos = energy_eqn,
@@ -344,7 +351,11 @@ typedef struct gsph_integrator_config {
   int32_t ntreestockstep;       /* otherwise restock every this many steps, else extrapolate          */
   int32_t sink_particles;       /* Parameters.cpp "sink_particles": must be 0 -- MainLoop's sink search, accretion
                                    and stellar-property update (SphSimulation.cpp:815-833) are not on this path   */
-  int32_t reserved[4];
+  int32_t Nlevels;              /* 0 or 1: one global time step; > 1: hierarchical block time steps
+                                   (Simulation::ComputeBlockTimesteps, Simulation.cpp:1764-2199)                   */
+  int32_t level_diff_max;       /* largest level difference between neighbours (Parameters.cpp:245, 1);
+                                   0 is read as the default 1                                                     */
+  int32_t reserved[2];
 } gsph_integrator_config;
 
 /* Start from the particles of the last gsph_upload (host order is kept).
@@ -383,6 +394,11 @@ int gsph_integrator_advance(gsph_handle* h, int* tree_mode, double* timestep);
 int gsph_integrator_finish(gsph_handle* h);
 /* simulation time, the time step the NEXT MainLoop will take, steps done since begin             */
 int gsph_integrator_state(gsph_handle* h, double* t, double* timestep, int64_t* nsteps);
+/* block time steps: the scalars of the hierarchy (Simulation::n, nresync, level_max, level_step, dt_max) and, where
+ * the pointers are not NULL, the integrator state of every particle in host order: nstep, nlast (int32[N]), dt, tlast
+ * (double[N]).  level and levelneib come with gsph_download.                                          */
+typedef struct gsph_block_state { int64_t n, nresync; int32_t level_max, level_step; double dt_max; } gsph_block_state;
+int gsph_integrator_block_state(gsph_handle* h, gsph_block_state* st, int32_t* nstep, int32_t* nlast, double* dt, double* tlast);
 
 /* Kernel tables exactly as TabulatedKernel builds them (TabulatedKernel.cpp:58-105,
  * SmoothingKernel.h:585-605): which = 0 w0_s2, 1 womega_s2, 2 wzeta_s2, 3 w1, 4 wgrav, 5 wpot;

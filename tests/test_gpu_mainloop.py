@@ -24,6 +24,9 @@ def _upload_setup(g, params, setup):
         ps[f][...] = setup[f].reshape(N, nd)
     for f in ("m", "h", "u", "sound", "dudt", "div_v", "alpha", "dalphadt", "gpot"):
         ps[f][...] = setup[f]
+    for f in ("rho", "invomega", "zeta", "hfactor", "hrangesqd", "pressure"):
+        if f in setup:                                       # block time steps: inactive particles keep these
+            ps[f][...] = setup[f]
     ps["ptype"][...] = setup["ptype"]
     ps["level"][...] = setup["level"]
     tree = g.GpuSphTree(params)
@@ -120,7 +123,7 @@ def test_device_mainloop_errors_are_loud():
     with pytest.raises(g.GsphError):
         tree2.IntegratorBegin(compute_forces=False)        # stars are not integrated on the device
     with pytest.raises(ValueError):
-        g.GpuSphTree(dict(params, Nlevels=2)).IntegratorBegin(ps)
+        g.GpuSphTree(dict(params, Nlevels=2, sph_single_timestep=1)).IntegratorBegin(ps)
     tree.close(); tree2.close()
 
 
@@ -217,3 +220,71 @@ def test_operator_calls_inside_a_resident_run_are_consistent():
         g.GpuSphTree(dict(params, sink_particles=1)).IntegratorBegin(ps)
     with pytest.raises(ValueError):
         g.GpuSphTree(dict(params, create_sinks=1)).IntegratorBegin(ps)
+
+
+# ---------------------------------------------------------------------------------------------------
+# hierarchical block time steps (Nlevels > 1)
+# ---------------------------------------------------------------------------------------------------
+from conftest import LOOPBLK_CASES  # noqa: E402
+from test_mainloop_oracle import split_blk, check_block_state  # noqa: E402
+
+
+@pytest.mark.parametrize("name", LOOPBLK_CASES)
+def test_device_block_timesteps_match_reference(name):
+    """the device-resident loop with Nlevels = 4 against 20 of the reference's own MainLoop calls: IntegratorBegin
+    rebuilds the hierarchy the reference's setup chose (same level / nstep / dt for every particle), then levels are
+    added and removed, steps are cut short by the neighbour-level limiter, the hierarchy is resynchronised -- the
+    integer state of every particle is the reference's, the physical state agrees to rounding"""
+    import gandalf_b200 as g
+    params, d = load_golden(name)
+    setup, sim0, loop, sim1 = split_blk(d)
+    ps, tree = _upload_setup(g, params, setup)
+    tree.IntegratorBegin(compute_forces=False)
+    b0 = tree.IntegratorBlockState(arrays=True)
+    tree.Download(ps, only=("level", "levelneib"))
+    for k in ("n", "nresync", "level_max", "level_step"):
+        assert int(b0[k]) == int(sim0[k]), k
+    assert abs(b0["dt_max"] - sim0["dt_max"]) <= 1e-12*sim0["dt_max"]
+    assert np.array_equal(ps["level"], setup["level"]) and np.array_equal(b0["nstep"], setup["nstep"])
+    assert np.abs(b0["dt"] - setup["dt"]).max() <= 1e-12*np.abs(setup["dt"]).max()
+    steps = int(d["loop.steps"])
+    tree.MainLoop(steps)
+    t, ts, n = tree.IntegratorState()
+    assert n == steps
+    b1 = tree.IntegratorBlockState(arrays=True)
+    tree.Download(ps)
+    state = {k: ps[k] for k in ("r", "v", "a", "h", "rho", "u", "alpha", "dudt", "level", "levelneib")}
+    state.update(nstep=b1["nstep"], nlast=b1["nlast"], dt=b1["dt"], tlast=b1["tlast"])
+    sim = dict(b1, timestep=ts, t=t)
+    # integer state exact; physical state to the north-star bar after 20 steps (per-particle relative errors of
+    # vector components that pass through zero in the shock tube reach 7e-8; scaled by the field maximum: 1e-11)
+    check_block_state(state, sim, loop, sim1, 1e-6)
+    for f in ("r", "v", "a", "h", "rho", "u"):
+        assert np.abs(np.asarray(state[f]).reshape(-1) - loop[f].reshape(-1)).max() <= 1e-9*np.abs(loop[f]).max(), f
+    tree.close()
+
+
+def test_device_block_timesteps_step_by_step_and_one_level():
+    """MainLoop(1) x N == MainLoop(N) bit for bit with block time steps, and Nlevels = 1 still takes the global-step
+    path (levels all 0)"""
+    import gandalf_b200 as g
+    params, d = load_golden("loopblk_adsod")
+    setup, sim0, loop, sim1 = split_blk(d)
+    res = []
+    for chunks in ((12,), (5, 1, 6)):
+        ps, tree = _upload_setup(g, params, setup)
+        tree.IntegratorBegin(compute_forces=False)
+        for c in chunks:
+            tree.MainLoop(c)
+            tree.Download(ps)
+        res.append(({k: ps[k].copy() for k in ("r", "v", "a", "h", "u", "level")}, tree.IntegratorState(),
+                    tree.IntegratorBlockState()))
+        tree.close()
+    assert res[0][1] == res[1][1] and res[0][2] == res[1][2]
+    for k in res[0][0]:
+        assert np.array_equal(res[0][0][k], res[1][0][k]), k
+    ps, tree = _upload_setup(g, dict(params, Nlevels=1), setup)
+    tree.IntegratorBegin(compute_forces=False)
+    tree.MainLoop(2)
+    assert tree.IntegratorBlockState()["level_max"] == 0
+    tree.close()

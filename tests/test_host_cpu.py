@@ -189,8 +189,8 @@ def test_integrator_config_follows_the_reference_parameters():
     assert c.energy_integration == 0 and c.courant_mult == 0.2 and (c.ntreebuildstep, c.ntreestockstep) == (8, 2)
     for eos in ("barotropic", "barotropic2", "constant_temp"):
         assert integrator_config_from_params({"gas_eos": eos}).energy_integration == 0
-    with pytest.raises(ValueError):
-        integrator_config_from_params({"Nlevels": 5})
+    c = integrator_config_from_params({"Nlevels": 5})
+    assert c.Nlevels == 5 and c.level_diff_max == 1            # block time steps, Parameters.cpp:245
     with pytest.raises(ValueError):
         integrator_config_from_params({"sph_integration": "lfdkd"})
 
@@ -313,6 +313,7 @@ def test_device_loop_rejects_what_it_does_not_run():
     from gandalf_b200.params import integrator_config_from_params
     c = integrator_config_from_params({"ndim": 3})
     assert c.sink_particles == 0 and c.ntreebuildstep == 1
-    for bad in ({"sink_particles": 1}, {"create_sinks": 1}, {"Nlevels": 5}, {"sph_integration": "lfdkd"}):
+    assert integrator_config_from_params({"ndim": 3, "Nlevels": 5}).Nlevels == 5          # block time steps are on the path
+    for bad in ({"sink_particles": 1}, {"create_sinks": 1}, {"Nlevels": 5, "sph_single_timestep": 1}, {"sph_integration": "lfdkd"}):
         with pytest.raises(ValueError):
             integrator_config_from_params(dict({"ndim": 3}, **bad))
