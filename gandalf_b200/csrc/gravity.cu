@@ -1032,6 +1032,7 @@ gravity_direct_kernel(PartView P, TreeDev tree, DevParams dp, const double2* __r
           __syncwarp();
         }
         if (qn > 0) advance(qn);
+        __syncwarp();                                       /* the ring is rewritten from slot 0 by the next leaf */
         if (pend) evaluate();
         /* sum over the lanes; the even lane L holds value v(L) = (target, component) */
         const double tot = warp_reduce16(acc, lane);

@@ -732,6 +732,177 @@ partition_v2_kernel(int N, int level, int cur, int plo, int phi, int klo, ListPt
 }
 
 /*================================================================================================
+ * Bottom of the build: once a node holds at most BT_CAP particles, its whole subtree is finished by ONE thread
+ * block in shared memory -- the same per-level algorithm (split axis from the inherited box, median entry of the
+ * split-axis list, stable partition of the lists by global rank), but the lists are 16-bit local indices and no
+ * level touches HBM.  Replaces the last 8-9 level passes (each re-reads and re-writes all three lists).
+ * The result (order of list 0 below the node) is bit-identical to the level passes.
+ *================================================================================================*/
+#define BT_CAP 1024
+#define BT_THREADS 256
+#define BT_ITEMS (BT_CAP/BT_THREADS)
+#define BT_MAXSPLIT 256                 /* nodes that still split at the deepest in-block level: nlev <= 9 */
+
+template <int NDIM>
+struct BottomShared {
+  int id[BT_CAP];
+  int rank[NDIM][BT_CAP];               /* global rank of local particle j along every axis */
+  unsigned short lst[2][NDIM][BT_CAP];  /* the lists as local indices, double buffered */
+  unsigned short scan[BT_CAP];
+  unsigned short nodeof[BT_CAP];
+  int nfirst[2][2*BT_MAXSPLIT], ncount[2][2*BT_MAXSPLIT];
+  int mr[2*BT_MAXSPLIT], mid[2*BT_MAXSPLIT];
+  signed char kd[2*BT_MAXSPLIT];
+  double box[2][2][NDIM][BT_MAXSPLIT];  /* [buffer][min|max][axis][node]: inherited boxes of the nodes that split */
+  typename cub::BlockScan<int, BT_THREADS>::TempStorage scan_tmp;
+};
+
+template <int NDIM>
+__global__ void __launch_bounds__(BT_THREADS)
+bottom_levels_kernel(int level0, int nlev, int cur, int klo, ListPtrs<NDIM> L)
+{
+  extern __shared__ __align__(16) unsigned char bt_smem[];
+  BottomShared<NDIM>& S = *reinterpret_cast<BottomShared<NDIM>*>(bt_smem);
+  typedef cub::BlockScan<int, BT_THREADS> BS;
+  const int tid = threadIdx.x;
+  const int k = klo + blockIdx.x;
+  const int n0 = (1 << level0) - 1 + k;
+  const int fst = L.first[n0], cnt = L.count[n0];
+  if (cnt <= 0) return;
+  /* ---- local numbering = order of list 0; ranks along the other axes travel with the entries, the rank along
+   *      axis 0 comes from the global table; lists 1, 2 find their particles by that rank (binary search) -------*/
+  for (int j = tid; j < cnt; j += BT_THREADS) {
+    const int id = L.ids[0][cur][fst + j];
+    S.id[j] = id;
+    S.rank[0][j] = L.rank[0][id];
+#pragma unroll
+    for (int q = 0; q < NDIM - 1; q++) S.rank[1 + q][j] = L.rk[0][q][cur][fst + j];     /* axis (0 + 1 + q) */
+    S.lst[0][0][j] = (unsigned short) j;
+    S.nodeof[j] = 0;
+  }
+  if (tid == 0) {
+    S.nfirst[0][0] = 0; S.ncount[0][0] = cnt;
+#pragma unroll
+    for (int d = 0; d < NDIM; d++) { S.box[0][0][d][0] = L.ib[level0 & 1][0][d][k]; S.box[0][1][d][0] = L.ib[level0 & 1][1][d][k]; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int d = 1; d < NDIM; d++) {
+    const int q = NDIM - 1 - d;                              /* (d + 1 + q) % NDIM == 0: the carried rank along axis 0 */
+    for (int p = tid; p < cnt; p += BT_THREADS) {
+      const int rx = L.rk[d][q][cur][fst + p];
+      int lo = 0, hi = cnt;
+      while (lo < hi) { const int m = (lo + hi) >> 1; if (S.rank[0][m] < rx) lo = m + 1; else hi = m; }
+      S.lst[0][d][p] = (unsigned short) lo;
+    }
+  }
+  __syncthreads();
+  int cb = 0, bb = 0;                                       /* list buffer, node / box buffer */
+  for (int s = 0; s < nlev; s++) {
+    const int nn = 1 << s;
+    /* ---- DivideTreeCell for every node of the level (split_nodes_v2_kernel) ---------------------------------*/
+    for (int i = tid; i < nn; i += BT_THREADS) {
+      const int f = S.nfirst[bb][i], c = S.ncount[bb][i];
+      int kd = 0; double rkmax = 0.0;
+#pragma unroll
+      for (int d = 0; d < NDIM; d++) {
+        const double w = __dadd_rn(S.box[bb][1][d][i], -S.box[bb][0][d][i]);
+        if (w > rkmax) { rkmax = w; kd = d; }
+      }
+      const int left = c/2;
+      double rdiv = 0.0; int mr = 0x7fffffff;
+      if (c > 0) {
+        const int jm = S.lst[cb][kd][f + left];
+        rdiv = L.r[kd][S.id[jm]];
+        mr = S.rank[kd][jm];
+      }
+      S.nfirst[bb ^ 1][2*i] = f;            S.ncount[bb ^ 1][2*i] = left;
+      S.nfirst[bb ^ 1][2*i + 1] = f + left; S.ncount[bb ^ 1][2*i + 1] = c - left;
+      if (s + 1 < nlev) {                                   /* the children split again: their inherited boxes */
+#pragma unroll
+        for (int d = 0; d < NDIM; d++) {
+          const double mn = S.box[bb][0][d][i], mx = S.box[bb][1][d][i];
+          S.box[bb ^ 1][0][d][2*i] = mn;                       S.box[bb ^ 1][1][d][2*i] = (d == kd) ? rdiv : mx;
+          S.box[bb ^ 1][0][d][2*i + 1] = (d == kd) ? rdiv : mn; S.box[bb ^ 1][1][d][2*i + 1] = mx;
+        }
+      }
+      S.kd[i] = (signed char) kd; S.mr[i] = mr; S.mid[i] = f + left;
+    }
+    __syncthreads();
+    /* ---- stable partition of every list inside every node (count_right + partition_v2 kernels) ---------------*/
+#pragma unroll
+    for (int d = 0; d < NDIM; d++) {
+      int fl[BT_ITEMS], jj[BT_ITEMS], nd[BT_ITEMS];
+      int c = 0;
+#pragma unroll
+      for (int i = 0; i < BT_ITEMS; i++) {
+        const int p = tid*BT_ITEMS + i;
+        fl[i] = 0; jj[i] = 0; nd[i] = 0;
+        if (p < cnt) {
+          jj[i] = S.lst[cb][d][p]; nd[i] = S.nodeof[p];
+          const int kd = S.kd[nd[i]];
+          fl[i] = (d == kd) ? (p >= S.mid[nd[i]]) : (S.rank[kd][jj[i]] >= S.mr[nd[i]]);
+        }
+        c += fl[i];
+      }
+      int pre;
+      BS(S.scan_tmp).ExclusiveSum(c, pre);
+#pragma unroll
+      for (int i = 0; i < BT_ITEMS; i++) {
+        const int p = tid*BT_ITEMS + i;
+        if (p < cnt) S.scan[p] = (unsigned short) pre;
+        pre += fl[i];
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < BT_ITEMS; i++) {
+        const int p = tid*BT_ITEMS + i;
+        if (p < cnt) {
+          const int rb = (int) S.scan[p] - (int) S.scan[S.nfirst[bb][nd[i]]];   /* right-going entries before p in its node */
+          const int dest = fl[i] ? S.mid[nd[i]] + rb : p - rb;
+          S.lst[cb ^ 1][d][dest] = (unsigned short) jj[i];
+        }
+      }
+      __syncthreads();
+    }
+    for (int p = tid; p < cnt; p += BT_THREADS) {
+      const int nd = S.nodeof[p];
+      S.nodeof[p] = (unsigned short)(2*nd + (p >= S.mid[nd] ? 1 : 0));
+    }
+    cb ^= 1; bb ^= 1;
+    __syncthreads();
+  }
+  /* the tree order below this node: list 0 */
+  for (int p = tid; p < cnt; p += BT_THREADS) L.ids[0][cur ^ 1][fst + p] = S.id[S.lst[cb][0][p]];
+}
+
+/* level from which the bottom kernel takes over: the shallowest one whose nodes hold <= BT_CAP particles, but not
+   more than 9 levels above the leaves; ltot (= no bottom kernel) for 1-D and for trees that are too small */
+static int bottom_start_level(int64_t N, int ltot, int ndim)
+{
+  if (ndim == 1) return ltot;
+  const char* e = getenv("GSPH_TREE_BOTTOM");
+  if (e && atoi(e) == 0) return ltot;
+  int l = 0;
+  while (l < ltot && ((N + ((int64_t) 1 << l) - 1) >> l) > BT_CAP) l++;
+  if (l < ltot - 9) l = ltot - 9;
+  if (ltot - l < 2) return ltot;                            /* not worth a launch */
+  return l;
+}
+
+template <int NDIM>
+static int launch_bottom_levels(gsph_handle* h, int level0, int ltot, int cur, int klo, int nblocks, const ListPtrs<NDIM>& L, cudaStream_t s)
+{
+  auto kern = bottom_levels_kernel<NDIM>;
+  const size_t smem = sizeof(BottomShared<NDIM>);
+  CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+  kern<<<nblocks, BT_THREADS, smem, s>>>(level0, ltot - level0, cur, klo, L);
+  h->stats.kernel_launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return GSPH_OK;
+}
+
+/*================================================================================================
  * Multi-GPU build, phase 1, for NDIM > 1: a rank does not sort all particles to find its shard.
  * The top log2(world) splits on the path to its node are found by SELECTION: the median entry of a
  * node along its split axis is the (cnt/2)-th smallest (coordinate, id) pair -- a radix select over
@@ -1002,7 +1173,13 @@ int build_tree_v2(gsph_handle* h, int phase, int shard_rank, int shard_world)
       CUDA_TRY(h, cudaMemcpyAsync(lcount, &one[1], sizeof(int), cudaMemcpyHostToDevice, s));
     }
     int cur = 0;
+    const int lbot = bottom_start_level(Nloc, lloc, nd);   /* levels >= lbot: one block per node, in shared memory */
     for (int l = 0; l < lloc; l++) {
+      if (l == lbot) {
+        const int rb = launch_bottom_levels<NDIM>(h, lbot, lloc, cur, 0, 1 << lbot, L, s); if (rb) return rb;
+        cur ^= 1;
+        break;
+      }
       const int nn = 1 << l;
       split_nodes_v2_kernel<NDIM><<<(nn + 127)/128, 128, 0, s>>>(l, cur, 0, nn, L);
       size_t tb = cub_bytes;
@@ -1058,11 +1235,19 @@ int build_tree_v2(gsph_handle* h, int phase, int shard_rank, int shard_world)
     if ((shard_rank >> b) & 1) slo += left; else shi = slo + left;
   }
   int cur = 0;
+  const int lbot = bottom_start_level(N, ltot, nd);        /* levels >= lbot: one block per node, in shared memory */
   for (int l = 0; l < ltot; l++) {
     const int nn = 1 << l;
     const bool mine_only = phase == 1 && l >= ltop;
     const int klo = mine_only ? shard_rank << (l - ltop) : 0;
     const int khi = mine_only ? (shard_rank + 1) << (l - ltop) : nn;
+    if (l == lbot) {
+      const int rb = launch_bottom_levels<NDIM>(h, lbot, ltot, cur, klo, khi - klo, L, s); if (rb) return rb;
+      cur ^= 1;
+      fill_topology_kernel<<<(T.ncell + 255)/256, 256, 0, s>>>(N, ltot, T.first, T.count);   /* first / count of the levels below */
+      h->stats.kernel_launches++;
+      break;
+    }
     const int plo = mine_only ? slo : 0, phi = mine_only ? shi : N;
     split_nodes_v2_kernel<NDIM><<<(nn + 127)/128, 128, 0, s>>>(l, cur, klo, khi, L);
     h->stats.kernel_launches++;
