@@ -98,7 +98,8 @@ EXPORTS = [
     "gsph_tree_cells", "gsph_get_stats", "gsph_kernel_table", "gsph_measure_fp_peak",
     "gsph_integrator_begin", "gsph_integrator_step", "gsph_integrator_state", "gsph_integrator_block_state",
     "gsph_update_all_forces_begin", "gsph_update_all_forces_finish", "gsph_integrator_advance",
-    "gsph_integrator_finish", "gsph_update_star_gas_forces", "gsph_derive_density_fields",
+    "gsph_integrator_finish", "gsph_integrator_check_timesteps", "gsph_update_thermal_properties",
+    "gsph_update_star_gas_forces", "gsph_derive_density_fields",
     "gsph_integrator_set_stars", "gsph_integrator_get_stars",
 ]
 
@@ -143,6 +144,8 @@ def lib():
     L.gsph_integrator_step.argtypes = [H, C.c_int]
     L.gsph_integrator_advance.argtypes = [H, C.POINTER(C.c_int), C.POINTER(C.c_double)]
     L.gsph_integrator_finish.argtypes = [H]
+    L.gsph_integrator_check_timesteps.argtypes = [H, C.POINTER(C.c_int)]
+    L.gsph_update_thermal_properties.argtypes = [H]
     L.gsph_integrator_set_stars.argtypes = [H, C.c_void_p, C.c_int, C.c_double]
     L.gsph_integrator_get_stars.argtypes = [H, C.c_void_p, C.c_int]
     L.gsph_update_star_gas_forces.argtypes = [H, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -88,6 +88,16 @@ __global__ void zero_acc_kernel(int lo, int N, DevPtrs P)
   for (int k = 0; k < NDIM; k++) { P.f[F_AX + k][i] = 0.0; P.f[F_ATX + k][i] = 0.0; }
 }
 
+/* with an active slice and inactive particles the devices' levelneib arrays are combined by a MAX reduction
+   (the scatter half of the force pass lands on every slice): the active particles of the OTHER slices start
+   from 0 here as they do on their own device */
+__global__ void zero_levelneib_outside_kernel(int N, int lo, int hi, DevPtrs P)
+{
+  const int i = blockIdx.x*blockDim.x + threadIdx.x;
+  if (i >= N || (i >= lo && i < hi)) return;
+  if (((unsigned) P.i[I_FLAGS][i]) & GSPH_FLAG_ACTIVE) P.i[I_LEVELNEIB][i] = 0;
+}
+
 /* register-resident FMA chains for the FP roofline denominators */
 template <class T>
 __global__ void fma_peak_kernel(T* out, int iters)
@@ -1286,6 +1296,11 @@ int gsph_zero_accelerations(gsph_handle* h)
   }
   h->stats.kernel_launches++;
   CUDA_TRY(h, cudaGetLastError());
+  if (h->slice_mode && !h->all_active) {
+    zero_levelneib_outside_kernel<<<(int)((h->N + 255)/256), 256, 0, h->stream>>>((int) h->N, lo, N, P);
+    h->stats.kernel_launches++;
+    CUDA_TRY(h, cudaGetLastError());
+  }
   h->pvalid_d |= GSPH_OUT_FORCES & ~GSPH_DMASK(F_DALPHADT); h->pvalid_i |= 1u << I_LEVELNEIB;
   h->acc_zeroed = true;
   return GSPH_OK;
@@ -1913,7 +1928,6 @@ int gsph_integrator_begin(gsph_handle* h, const gsph_integrator_config* cfg, int
     if (I.nstar > 0) { h->err = "gsph_integrator_begin: star particles with block time steps (Nlevels > 1) are not on the accelerated path"; return GSPH_EINVAL; }
     if (h->dp.any_mirror) { h->err = "gsph_integrator_begin: block time steps with mirror boundaries are not on the accelerated path"; return GSPH_EINVAL; }
     if (h->dp.tdavisc == GSPH_TDAVISC_CD2010) { h->err = "gsph_integrator_begin: block time steps with time_dependent_avisc = cd2010 are not on the accelerated path"; return GSPH_EINVAL; }
-    if (compute_forces == 2 || h->slice_mode) { h->err = "gsph_integrator_begin: block time steps run on one device (gsph_integrator_step)"; return GSPH_EINVAL; }
     if (cfg->Nlevels > 30) { h->err = "gsph_integrator_begin: Nlevels must be <= 30"; return GSPH_EINVAL; }
     if (I.blk_cap < h->Ncap) {
       auto fre = [](void* p) { if (p) cudaFree(p); };
@@ -1979,7 +1993,6 @@ int gsph_integrator_advance(gsph_handle* h, int* tree_mode, double* timestep)
   if (h->integ.mid_step) { h->err = "gsph_integrator_advance: the previous step was not finished"; return GSPH_ESTATE; }
   cudaSetDevice(h->device);
   IntegState& I = h->integ;
-  if (integ_block(h) && !I.in_step) { h->err = "gsph_integrator_advance: block time steps (Nlevels > 1) run through gsph_integrator_step on one device"; return GSPH_EINVAL; }
   I.Nsteps++;
   I.n++;
   const double ts = I.timestep;
@@ -2016,7 +2029,7 @@ int gsph_integrator_finish(gsph_handle* h)
 {
   if (!h) return GSPH_EINVAL;
   if (!h->integ.on || !h->integ.mid_step) { h->err = "gsph_integrator_finish before gsph_integrator_advance"; return GSPH_ESTATE; }
-  if (integ_block(h) && !h->integ.in_step) { h->err = "gsph_integrator_finish: block time steps (Nlevels > 1) run through gsph_integrator_step on one device"; return GSPH_EINVAL; }
+  if (integ_block(h) && h->results_newer) { h->err = "gsph_integrator_finish: block time steps (Nlevels > 1) need gsph_integrator_check_timesteps after the passes (until it reports 0)"; return GSPH_ESTATE; }
   if (!h->sorted_valid) { h->err = "gsph_integrator_finish before the passes of this step"; return GSPH_ESTATE; }
   cudaSetDevice(h->device);
   IntegState& I = h->integ;
@@ -2060,6 +2073,35 @@ int gsph_integrator_finish(gsph_handle* h)
   return GSPH_OK;
 }
 
+/* block time steps, host-driven loop (several devices): SphLeapfrogKDK::CheckTimesteps after the passes of
+ * this step (with several ranks: after the result slices were combined).  *woken = particles whose step is
+ * cut short; when > 0 their active flags and new levels are in place and the passes have to run again
+ * (the do-while loop of MainLoop, SphSimulation.cpp:658-756).                                        */
+int gsph_integrator_check_timesteps(gsph_handle* h, int* woken)
+{
+  if (!h) return GSPH_EINVAL;
+  if (!h->integ.on || !h->integ.mid_step) { h->err = "gsph_integrator_check_timesteps before gsph_integrator_advance"; return GSPH_ESTATE; }
+  if (!woken) { h->err = "gsph_integrator_check_timesteps: NULL argument"; return GSPH_EINVAL; }
+  if (!h->sorted_valid) { h->err = "gsph_integrator_check_timesteps before the passes of this step"; return GSPH_ESTATE; }
+  cudaSetDevice(h->device);
+  *woken = 0;
+  if (!integ_block(h)) return GSPH_OK;                 /* one global step: nothing to check */
+  int rc = blk_check_timesteps(h, woken); if (rc) return rc;
+  if (*woken > 0) rc = blk_push_flags(h);
+  return rc;
+}
+
+/* GradhSph::ComputeThermalProperties for every particle, active or not, in tree order: what MainLoop does
+ * between the density and the force pass when nradstep = 1 (SphSimulation.cpp:669-679).  gsph_integrator_step
+ * does it itself; a host layer that drives the passes of a block-time-step run calls this.          */
+int gsph_update_thermal_properties(gsph_handle* h)
+{
+  if (!h) return GSPH_EINVAL;
+  if (!h->sorted_valid) { h->err = "gsph_update_thermal_properties before gsph_build_tree"; return GSPH_ESTATE; }
+  cudaSetDevice(h->device);
+  return gsph_thermal_all_impl(h);
+}
+
 int gsph_integrator_step(gsph_handle* h, int nsteps)
 {
   if (!h) return GSPH_EINVAL;
@@ -2067,9 +2109,7 @@ int gsph_integrator_step(gsph_handle* h, int nsteps)
   if (nsteps < 0) { h->err = "gsph_integrator_step: nsteps < 0"; return GSPH_EINVAL; }
   for (int s = 0; s < nsteps; s++) {
     int mode = 0; double ts = 0.0;
-    h->integ.in_step = true;
     int rc = gsph_integrator_advance(h, &mode, &ts);
-    h->integ.in_step = false;
     if (rc) return rc;
     rc = gsph_build_tree(h, mode, ts); if (rc) return rc;
     rc = integ_forces(h); if (rc) return rc;
@@ -2084,9 +2124,7 @@ int gsph_integrator_step(gsph_handle* h, int nsteps)
         rc = integ_forces(h); if (rc) return rc;
       }
     }
-    h->integ.in_step = true;
     rc = gsph_integrator_finish(h);
-    h->integ.in_step = false;
     if (rc) return rc;
   }
   return GSPH_OK;

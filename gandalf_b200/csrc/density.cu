@@ -699,7 +699,8 @@ __global__ void derive_density_fields_kernel(int N, int lo, int hi, PartView P, 
 {
   const int ti = blockIdx.x*blockDim.x + threadIdx.x;
   if (ti >= N || (ti >= lo && ti < hi)) return;
-  if (((unsigned) P.i[I_FLAGS][ti]) & GSPH_FLAG_DEAD) return;
+  const unsigned fl = (unsigned) P.i[I_FLAGS][ti];
+  if ((fl & GSPH_FLAG_DEAD) || !(fl & GSPH_FLAG_ACTIVE)) return;     /* (the density pass left the inactive ones alone) */
   const double hf = P.f[F_H][ti], rho = P.f[F_RHO][ti];
   const double ih = 1.0/hf;
   P.f[F_HFAC][ti] = pow_ndim<NDIM>(ih)*ih;

@@ -126,7 +126,6 @@ struct IntegState {
   int64_t Nsteps = 0;
   bool rebuild = true;
   bool mid_step = false;     /* between gsph_integrator_advance and gsph_integrator_finish */
-  bool in_step = false;      /* inside gsph_integrator_step (block time steps only run there) */
   bool starting = false;     /* inside gsph_integrator_begin's first force pass */
   /* hierarchical block time steps (cfg.Nlevels > 1): per-particle integer step / start of step (host order) and the
      scalars of Simulation::ComputeBlockTimesteps */

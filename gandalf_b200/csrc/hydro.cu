@@ -657,7 +657,7 @@ neib_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* work_
     const int node = ncohort - 1 + c;
     const int cfirst = tree.first[node], ccount = tree.count[node];
     if (ccount == 0) continue;
-    if (MODE == 2 && tree.nactive[node] == 0) continue;
+    if (MODE == 2 && (tree.nactive[node] == 0 || GSPH_RANGE_OUTSIDE_SLICE(dp, cfirst, ccount))) continue;
     CandList cl{cand, cand_cap, 0, st};
     ScatterGatherVisitor<NDIM> V{tree, dp, cl, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, false};
 #pragma unroll
@@ -676,7 +676,7 @@ neib_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* work_
       if (live) {
         const unsigned fl = (unsigned) P.i[I_FLAGS][i];
         if (fl & GSPH_FLAG_DEAD) live = false;
-        if (MODE == 2 && !(fl & GSPH_FLAG_ACTIVE)) live = false;
+        if (MODE == 2 && (!(fl & GSPH_FLAG_ACTIVE) || !GSPH_IN_SLICE(dp, i))) live = false;
       }
       if (live) {
 #pragma unroll
@@ -849,7 +849,9 @@ int dispatch_hydro(gsph_handle* h, int with_gravity)
     rc = tab ? dispatch_mode<NDIM, GSPH_KERNEL_QUINTIC, true>(h, with_gravity)
              : dispatch_mode<NDIM, GSPH_KERNEL_QUINTIC, false>(h, with_gravity);
   if (rc) return rc;
-  if (!h->all_active && !h->slice_mode && (h->dp.hydro_forces || !with_gravity)) {
+  /* (with an active slice the scatter of this device's targets lands on particles of every slice: the host
+     layer combines the devices' levelneib arrays with a MAX reduction instead of gathering slices) */
+  if (!h->all_active && (h->dp.hydro_forces || !with_gravity)) {
     if (h->dp.any_mirror) { h->err = "inactive particles (block time steps) with mirror boundaries are not on the accelerated path"; return GSPH_EINVAL; }
     rc = launch_neib<NDIM, 2>(h, nullptr, nullptr, nullptr);
   }

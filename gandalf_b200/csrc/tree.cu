@@ -748,13 +748,13 @@ struct BottomShared {
   int id[BT_CAP];
   int rank[NDIM][BT_CAP];               /* global rank of local particle j along every axis */
   unsigned short lst[2][NDIM][BT_CAP];  /* the lists as local indices, double buffered */
-  unsigned short scan[BT_CAP];
+  unsigned short scan[NDIM][BT_CAP];
   unsigned short nodeof[BT_CAP];
   int nfirst[2][2*BT_MAXSPLIT], ncount[2][2*BT_MAXSPLIT];
   int mr[2*BT_MAXSPLIT], mid[2*BT_MAXSPLIT];
   signed char kd[2*BT_MAXSPLIT];
   double box[2][2][NDIM][BT_MAXSPLIT];  /* [buffer][min|max][axis][node]: inherited boxes of the nodes that split */
-  typename cub::BlockScan<int, BT_THREADS>::TempStorage scan_tmp;
+  typename cub::BlockScan<unsigned long long, BT_THREADS>::TempStorage scan_tmp;
 };
 
 template <int NDIM>
@@ -763,7 +763,7 @@ bottom_levels_kernel(int level0, int nlev, int cur, int klo, ListPtrs<NDIM> L)
 {
   extern __shared__ __align__(16) unsigned char bt_smem[];
   BottomShared<NDIM>& S = *reinterpret_cast<BottomShared<NDIM>*>(bt_smem);
-  typedef cub::BlockScan<int, BT_THREADS> BS;
+  typedef cub::BlockScan<unsigned long long, BT_THREADS> BS;
   const int tid = threadIdx.x;
   const int k = klo + blockIdx.x;
   const int n0 = (1 << level0) - 1 + k;
@@ -829,45 +829,55 @@ bottom_levels_kernel(int level0, int nlev, int cur, int klo, ListPtrs<NDIM> L)
       S.kd[i] = (signed char) kd; S.mr[i] = mr; S.mid[i] = f + left;
     }
     __syncthreads();
-    /* ---- stable partition of every list inside every node (count_right + partition_v2 kernels) ---------------*/
-#pragma unroll
-    for (int d = 0; d < NDIM; d++) {
-      int fl[BT_ITEMS], jj[BT_ITEMS], nd[BT_ITEMS];
-      int c = 0;
+    /* ---- stable partition of every list inside every node (count_right + partition_v2 kernels): the right-going
+     *      counts of the NDIM lists ride in one 64-bit scan, 21 bits each ------------------------------------------*/
+    {
+      int jj[NDIM][BT_ITEMS], nd[BT_ITEMS];
+      unsigned fl = 0u;
+      unsigned long long c = 0ull;
 #pragma unroll
       for (int i = 0; i < BT_ITEMS; i++) {
         const int p = tid*BT_ITEMS + i;
-        fl[i] = 0; jj[i] = 0; nd[i] = 0;
+        nd[i] = 0;
         if (p < cnt) {
-          jj[i] = S.lst[cb][d][p]; nd[i] = S.nodeof[p];
-          const int kd = S.kd[nd[i]];
-          fl[i] = (d == kd) ? (p >= S.mid[nd[i]]) : (S.rank[kd][jj[i]] >= S.mr[nd[i]]);
+          nd[i] = S.nodeof[p];
+          const int kd = S.kd[nd[i]], mid = S.mid[nd[i]], mr = S.mr[nd[i]];
+#pragma unroll
+          for (int d = 0; d < NDIM; d++) {
+            jj[d][i] = S.lst[cb][d][p];
+            const bool f = (d == kd) ? (p >= mid) : (S.rank[kd][jj[d][i]] >= mr);
+            if (f) { fl |= 1u << (d*BT_ITEMS + i); c += 1ull << (21*d); }
+          }
         }
-        c += fl[i];
       }
-      int pre;
+      unsigned long long pre;
       BS(S.scan_tmp).ExclusiveSum(c, pre);
 #pragma unroll
       for (int i = 0; i < BT_ITEMS; i++) {
         const int p = tid*BT_ITEMS + i;
-        if (p < cnt) S.scan[p] = (unsigned short) pre;
-        pre += fl[i];
+        if (p < cnt) {
+#pragma unroll
+          for (int d = 0; d < NDIM; d++) {
+            S.scan[d][p] = (unsigned short)((pre >> (21*d)) & 0x1fffffull);
+            if ((fl >> (d*BT_ITEMS + i)) & 1u) pre += 1ull << (21*d);
+          }
+        }
       }
       __syncthreads();
 #pragma unroll
       for (int i = 0; i < BT_ITEMS; i++) {
         const int p = tid*BT_ITEMS + i;
         if (p < cnt) {
-          const int rb = (int) S.scan[p] - (int) S.scan[S.nfirst[bb][nd[i]]];   /* right-going entries before p in its node */
-          const int dest = fl[i] ? S.mid[nd[i]] + rb : p - rb;
-          S.lst[cb ^ 1][d][dest] = (unsigned short) jj[i];
+          const int nf = S.nfirst[bb][nd[i]], mid = S.mid[nd[i]];
+#pragma unroll
+          for (int d = 0; d < NDIM; d++) {
+            const int rb = (int) S.scan[d][p] - (int) S.scan[d][nf];          /* right-going entries before p in its node */
+            const int dest = ((fl >> (d*BT_ITEMS + i)) & 1u) ? mid + rb : p - rb;
+            S.lst[cb ^ 1][d][dest] = (unsigned short) jj[d][i];
+          }
+          S.nodeof[p] = (unsigned short)(2*nd[i] + (p >= mid ? 1 : 0));
         }
       }
-      __syncthreads();
-    }
-    for (int p = tid; p < cnt; p += BT_THREADS) {
-      const int nd = S.nodeof[p];
-      S.nodeof[p] = (unsigned short)(2*nd + (p >= S.mid[nd] ? 1 : 0));
     }
     cb ^= 1; bb ^= 1;
     __syncthreads();

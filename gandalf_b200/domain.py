@@ -188,18 +188,40 @@ class DomainDriver(object):
     #      replicated (streaming kernels over all particles, identical on every rank: the global time
     #      step is an order-independent minimum); between its two halves the ranks run the sharded
     #      tree build, their slices of the passes and the exchanges.  Nothing crosses PCIe.
+    def _block(self):
+        """hierarchical block time steps (Nlevels > 1, Simulation::ComputeBlockTimesteps)?"""
+        return int(self.tree.params["Nlevels"]) > 1
+
     def _passes(self):
+        block = self._block()
         self.UpdateAllSphProperties()
         self.ZeroAccelerations()
+        if block:
+            # nradstep = 1: thermal properties of every particle, active or not (SphSimulation.cpp:669-679)
+            self.tree.UpdateThermalProperties()
         if self.tree.cfg.self_gravity:
             self.UpdateAllSphForces()
         else:
             self.UpdateAllSphHydroForces()
         if self.world > 1:
             # the force results of the other slices (tree order): one in-place all-gather per array
-            fields = ["a", "atree", "gpot", "gpot_hydro", "dudt", "div_v", "dalphadt", "alpha", "levelneib"]
+            fields = ["a", "atree", "gpot", "gpot_hydro", "dudt", "div_v", "dalphadt", "alpha"]
+            if not block:
+                fields.append("levelneib")
             self.tree.Synchronize()
             self._gather_inplace(self._array_names(fields, self.tree.cfg.ndim), False, self.N)
+            if block:
+                # with inactive particles the levelneib scatter of a rank's targets lands on every slice
+                # (GradhSph.cpp:446, GradhSphTree.cpp:376-382): MAX over the ranks instead of a gather
+                self._reduce_max_inplace("levelneib", self.N)
+
+    def _reduce_max_inplace(self, name, n_valid):
+        import torch
+        import torch.distributed as dist
+        ptr, cap, es = self.tree.DeviceArray(name, staging=False)
+        t = torch.as_tensor(_CudaArray(ptr, int(n_valid), "<i4" if es == 4 else "<f8"), device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        torch.cuda.current_stream().synchronize()
 
     def IntegratorBegin(self, parts=None, compute_forces=True, t=0.0):
         if self.world == 1:
@@ -220,6 +242,16 @@ class DomainDriver(object):
             mode, ts = self.tree.IntegratorAdvance()
             self._build(mode, ts)
             self._passes()
+            if self._block():
+                # the passes are repeated for the particles whose step SphLeapfrogKDK::CheckTimesteps cuts
+                # short (the do-while loop of MainLoop, SphSimulation.cpp:658-756); the check runs on the
+                # replicated host-order state, so every rank sees the same count
+                for it in range(66):
+                    if self.tree.IntegratorCheckTimesteps() == 0:
+                        break
+                    if it == 65:
+                        raise RuntimeError("the neighbour time-step limiter does not settle")
+                    self._passes()
             self.tree.IntegratorFinish()
 
     def ZeroAccelerations(self):

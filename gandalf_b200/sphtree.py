@@ -246,6 +246,17 @@ class GpuSphTree(object):
     def IntegratorFinish(self):
         self._check(self._L.gsph_integrator_finish(self._h))
 
+    def IntegratorCheckTimesteps(self):
+        """SphLeapfrogKDK::CheckTimesteps after the passes of a block-time-step MainLoop -> number of particles
+        whose step was cut short (> 0: the passes have to run again for them)"""
+        woken = C.c_int()
+        self._check(self._L.gsph_integrator_check_timesteps(self._h, C.byref(woken)))
+        return woken.value
+
+    def UpdateThermalProperties(self):
+        """ComputeThermalProperties of every particle (MainLoop with nradstep = 1, SphSimulation.cpp:669-679)"""
+        self._check(self._L.gsph_update_thermal_properties(self._h))
+
     def MainLoop(self, nsteps=1):
         """nsteps x SphSimulation::MainLoop (SphSimulation.cpp:574-880) without leaving the device"""
         self._check(self._L.gsph_integrator_step(self._h, int(nsteps)))

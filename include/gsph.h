@@ -392,6 +392,18 @@ int gsph_integrator_set_stars(gsph_handle* h, const double* rows, int Nstar, dou
 int gsph_integrator_get_stars(gsph_handle* h, double* rows, int Nstar);
 int gsph_integrator_advance(gsph_handle* h, int* tree_mode, double* timestep);
 int gsph_integrator_finish(gsph_handle* h);
+/* Block time steps (Nlevels > 1) in a host-driven loop (several devices): between the passes and
+ * gsph_integrator_finish the host layer calls gsph_integrator_check_timesteps (SphLeapfrogKDK::CheckTimesteps,
+ * SphLeapfrogKDK.cpp:283-348): *woken = particles whose step the neighbour limiter cuts short.  While it is > 0
+ * their active flags and levels are in place and the passes run again (the do-while loop of MainLoop,
+ * SphSimulation.cpp:658-756); gsph_integrator_finish refuses to run before it has reported 0.
+ * gsph_update_thermal_properties = GradhSph::ComputeThermalProperties of EVERY particle (active or not), which
+ * MainLoop does between the density and the force pass with nradstep = 1 (SphSimulation.cpp:669-679); only the
+ * passes of a block-time-step run need it (with one global step the density pass has just done the same).
+ * With an active slice and inactive particles the levelneib scatter of the force pass reaches particles of
+ * every slice: combine the devices' levelneib arrays with a MAX reduction, not with a gather of slices.      */
+int gsph_integrator_check_timesteps(gsph_handle* h, int* woken);
+int gsph_update_thermal_properties(gsph_handle* h);
 /* simulation time, the time step the NEXT MainLoop will take, steps done since begin             */
 int gsph_integrator_state(gsph_handle* h, double* t, double* timestep, int64_t* nsteps);
 /* block time steps: the scalars of the hierarchy (Simulation::n, nresync, level_max, level_step, dt_max) and, where

@@ -72,6 +72,21 @@ for workload, NP in (("cloud", 150000), ("glass", 64**3), ("glass+cd2010", 40**3
         tree.Download(ps)
         state = tree.IntegratorState(); tree.close()
         return ps, state
+    def run_block(world_, rank_, steps):
+        # hierarchical block time steps across the ranks: replicated hierarchy, sharded passes repeated for the
+        # particles CheckTimesteps wakes, levelneib combined by a MAX reduction
+        ps = fresh()
+        tree = g.GpuSphTree(dict(params, Nlevels=5), device=lr)
+        drv = domain.DomainDriver(tree, rank_, world_)
+        drv.IntegratorBegin(ps, compute_forces=True)
+        drv.MainLoop(steps)
+        tree.Download(ps)
+        state, blk = tree.IntegratorState(), tree.IntegratorBlockState(arrays=True)
+        nact = tree.Stats().n_active
+        tree.close()
+        return ps, state, blk
+    if workload in ("cloud", "glass"):
+        bloop, bstate, bblk = run_block(world, rank, 7)
     loop, lstate = run_loop(world, rank, 3)
     chunked, clo, chi = run_chunked(world, rank)
     multi, st = run(world, rank)
@@ -95,6 +110,17 @@ for workload, NP in (("cloud", 150000), ("glass", 64**3), ("glass+cd2010", 40**3
         assert lstate == sstate, (lstate, sstate)
         for f in ("r", "v", "a", "h", "rho", "u", "dudt") + (("atree", "gpot") if grav else ()):
             assert np.array_equal(loop[f], sloop[f]), (workload, "mainloop", f, np.abs(loop[f] - sloop[f]).max())
+        if workload in ("cloud", "glass"):
+            sb, sbstate, sbblk = run_block(1, 0, 7)
+            assert bstate == sbstate, (bstate, sbstate)
+            for k in ("n", "nresync", "level_max", "level_step", "dt_max"):
+                assert bblk[k] == sbblk[k], (workload, "block", k, bblk[k], sbblk[k])
+            assert len(np.unique(sb["level"])) > 1, "the block-step case has one level only"
+            for k in ("nstep", "nlast", "dt", "tlast"):
+                assert np.array_equal(bblk[k], sbblk[k]), (workload, "block", k)
+            for f in ("r", "v", "a", "h", "rho", "u", "dudt", "level", "levelneib") + (("atree", "gpot") if grav else ()):
+                assert np.array_equal(bloop[f], sb[f]), (workload, "block", f, np.abs(bloop[f] - sb[f]).max())
+            print("multi-GPU block time steps ok:", workload, "levels", np.unique(sb["level"]).tolist(), "n", sbblk["n"])
         print("multi-GPU parity ok:", workload, N, "particles, world", world)
 dist.barrier()
 """

@@ -231,8 +231,13 @@ def test_domain_driver_main_loop_sequence():
     class Stub:
         cfg = Cfg()
 
-        def __init__(self, modes):
+        def __init__(self, modes, Nlevels=1, woken=()):
             self.calls, self.modes = [], list(modes)
+            self.params, self.woken = {"Nlevels": Nlevels}, list(woken)
+
+        def IntegratorCheckTimesteps(self):
+            self.calls.append("IntegratorCheckTimesteps")
+            return self.woken.pop(0)
 
         def __getattr__(self, name):
             def f(*a, **k):
@@ -266,6 +271,9 @@ def test_domain_driver_main_loop_sequence():
         def _gather_inplace(self, names, staging, n_valid):
             self.tree.calls.append(("gather", tuple(names), staging))
 
+        def _reduce_max_inplace(self, name, n_valid):
+            self.tree.calls.append(("reduce_max", name))
+
     import sys
     import types
     fake = types.ModuleType("torch")                      # UpdateAllSphProperties synchronises torch's stream
@@ -277,6 +285,10 @@ def test_domain_driver_main_loop_sequence():
         stub = Stub([0, 1, 2])
         drv = Driver(stub, rank=1, world_size=2)
         drv.MainLoop(3)
+        # block time steps: thermal refresh of every particle before the forces, levelneib by a MAX reduction,
+        # the passes repeated while CheckTimesteps wakes particles (here: once in the first step)
+        bstub = Stub([0, 2], Nlevels=4, woken=[3, 0, 0])
+        Driver(bstub, rank=1, world_size=2).MainLoop(2)
     finally:
         for k, v in saved.items():
             if v is None:
@@ -292,6 +304,15 @@ def test_domain_driver_main_loop_sequence():
     for build in ("sharded_rebuild", ("BuildTreeMode", 1), ("BuildTreeMode", 2)):
         expect += ["IntegratorAdvance", build, ("SetActiveSlice", lo, hi)] + step
     assert stub.calls == expect, stub.calls
+    bpass = ["DensityPass", "Synchronize", "exchange_density", ("DeriveDensityFields", lo, hi), "RefreshHmax",
+             "ZeroAccelerations", "UpdateThermalProperties", "UpdateAllSphForces", "Synchronize",
+             ("gather", ("ax", "ay", "az", "atx", "aty", "atz", "gpot", "gpot_hydro", "dudt", "div_v", "dalphadt", "alpha"), False),
+             ("reduce_max", "levelneib")]
+    bexpect = (["IntegratorAdvance", "sharded_rebuild", ("SetActiveSlice", lo, hi)] + bpass + ["IntegratorCheckTimesteps"] + bpass
+               + ["IntegratorCheckTimesteps", "IntegratorFinish"]
+               + ["IntegratorAdvance", ("BuildTreeMode", 2), ("SetActiveSlice", lo, hi)] + bpass
+               + ["IntegratorCheckTimesteps", "IntegratorFinish"])
+    assert bstub.calls == bexpect, bstub.calls
 
 
 def test_defaults_equal_the_reference():
