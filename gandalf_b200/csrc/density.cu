@@ -449,7 +449,7 @@ density_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict_
           for (int r = 0; r < 2; r++) {
             const int src = r*16 + (lane >> 1);
             const int jj = __shfl_sync(FULLMASK, jv, src);
-            if (jj >= 0) cp_async16(buf + DENS_UNIT(src, lane & 1), geo4 + 2*(size_t)(MIRROR ? (jj & IMG_MASK) : jj) + (lane & 1));
+            if (jj >= 0) cp_async16_cg(buf + DENS_UNIT(src, lane & 1), geo4 + 2*(size_t)(MIRROR ? (jj & IMG_MASK) : jj) + (lane & 1));
           }
           cp_async_commit();
         };

@@ -537,7 +537,7 @@ hydro_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict__ 
         for (int r = 0; r < 8; r++) {
           const int src = r*4 + (lane >> 3);
           const int jj = __shfl_sync(FULLMASK, jv, src);
-          if (jj >= 0) cp_async16(buf + src*REC_STRIDE + (lane & 7), frec + 8*(size_t)(MIRROR ? (jj & IMG_MASK) : jj) + (lane & 7));
+          if (jj >= 0) cp_async16_cg(buf + src*REC_STRIDE + (lane & 7), frec + 8*(size_t)(MIRROR ? (jj & IMG_MASK) : jj) + (lane & 7));
         }
         cp_async_commit();
       };
