@@ -499,12 +499,15 @@ gravity_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* wo
 #define GW_THREADS 256
 #define GW_WARPS (GW_THREADS/32)
 #define GW_STACK 448
-#define GW_NODE_STRIDE 5               /* double2 units per staged node record: 80 B, conflict-free 16-byte reads */
+/* staged node records: 64 bytes = four 16-byte chunks, chunk c of record r at unit 4r + (c ^ ((r >> 1) & 3)):
+   both the cooperative writes (four lanes per record, two records per quarter warp) and the per-lane reads of one
+   chunk (eight records per quarter warp) touch every bank once */
+#define GW_NODE_UNIT(r, c) (4*(r) + ((c) ^ (((r) >> 1) & 3)))
 
 struct WalkShared {
   int2 stack[GW_STACK];
-  double leafgeom[GRAV_LEAVES][6];
-  double2 nodes[32*GW_NODE_STRIDE];    /* the 64-byte records of the 32 nodes of a round, gathered cooperatively */
+  double2 leafgeom[GRAV_LEAVES][3];    /* (x, y) (z, rmax) (kernrange*hmax, MAC auxiliary): three broadcast 16-byte reads per test */
+  double2 nodes[32*4];                 /* the 64-byte records of the 32 nodes of a round, gathered cooperatively */
 };
 
 /* counts[2b], counts[2b+1] of batch slot b: cells, direct leaves; -1 = nothing to do here, -2 = left to the fused kernel */
@@ -543,11 +546,10 @@ gravity_walk_kernel(TreeDev tree, DevParams dp, int cohort_level, int c0, int nc
         const int first = tree.first[myleaf], cnt = tree.count[myleaf];
         leaf_live = cnt > 0 && tree.nactive[myleaf] > 0 && !GSPH_RANGE_OUTSIDE_SLICE(dp, first, cnt);
       }
-#pragma unroll
-      for (int k = 0; k < 3; k++) S.leafgeom[lane][k] = leaf_live ? tree.rcell[k][myleaf] : 0.0;
-      S.leafgeom[lane][3] = leaf_live ? tree.rmax[myleaf] : 0.0;
-      S.leafgeom[lane][4] = leaf_live ? __dmul_rn(dp.kernrange, tree.hmax[myleaf]) : 0.0;
-      S.leafgeom[lane][5] = (!GEOMAC && leaf_live && tree.macaux) ? tree.macaux[myleaf] : 0.0;
+      S.leafgeom[lane][0] = leaf_live ? make_double2(tree.rcell[0][myleaf], tree.rcell[1][myleaf]) : make_double2(0.0, 0.0);
+      S.leafgeom[lane][1] = leaf_live ? make_double2(tree.rcell[2][myleaf], tree.rmax[myleaf]) : make_double2(0.0, 0.0);
+      S.leafgeom[lane][2] = make_double2(leaf_live ? __dmul_rn(dp.kernrange, tree.hmax[myleaf]) : 0.0,
+                                         (!GEOMAC && leaf_live && tree.macaux) ? tree.macaux[myleaf] : 0.0);
     }
     const unsigned rootmask = __ballot_sync(FULLMASK, leaf_live) & 0xffu;
     int sp = 0, ncb = 0, ndb = 0, spmax = 0;
@@ -571,33 +573,33 @@ gravity_walk_kernel(TreeDev tree, DevParams dp, int cohort_level, int c0, int nc
       for (int r = 0; r < 4; r++) {
         const int src = r*8 + (lane >> 2);
         const int nsrc = __shfl_sync(FULLMASK, node, src);
-        if (nsrc >= 0) cp_async16(&S.nodes[src*GW_NODE_STRIDE + (lane & 3)], tree.gnode + 4*(size_t) nsrc + (lane & 3));
+        if (nsrc >= 0) cp_async16_cg(&S.nodes[GW_NODE_UNIT(src, lane & 3)], tree.gnode + 4*(size_t) nsrc + (lane & 3));
       }
       cp_async_commit();
       cp_async_wait<0>();
       __syncwarp();
-      const double2* const rec = &S.nodes[lane*GW_NODE_STRIDE];
       unsigned open_mask = 0, acc_mask = 0, live_mask = 0;
       bool isleaf = false; int ncount = 0, nfirst = 0;
       double rx = 0.0, ry = 0.0, rz = 0.0, crmax = 0.0, cdist = 0.0, chr = 0.0, cmac = 0.0;
       const int mac = dp.gravity_mac; const double macerror = dp.macerror;
       /* the reference's opening test per leaf (Tree.cpp:660-731, Tree.h:413-432), as in gravity_kernel */
       auto opens = [&](int l) -> bool {
-        const double* lg = S.leafgeom[l];
+        const double2 la = S.leafgeom[l][0], lb = S.leafgeom[l][1], lc = S.leafgeom[l][2];
         double dr[3];
-        dr[0] = __dadd_rn(rx, -lg[0]); dr[1] = __dadd_rn(ry, -lg[1]); dr[2] = __dadd_rn(rz, -lg[2]);
+        dr[0] = __dadd_rn(rx, -la.x); dr[1] = __dadd_rn(ry, -la.y); dr[2] = __dadd_rn(rz, -lb.x);
         const double drsqd = dot_exact<3>(dr);
-        const double rmax = lg[3];
-        const double a = __dadd_rn(__dadd_rn(crmax, rmax), lg[4]);
+        const double rmax = lb.y;
+        const double a = __dadd_rn(__dadd_rn(crmax, rmax), lc.x);
         const double bb = __dadd_rn(__dadd_rn(rmax, crmax), chr);
         if (drsqd <= __dmul_rn(a, a) || drsqd <= __dmul_rn(bb, bb) || drsqd < cdist) return true;
         if (GEOMAC) return false;
-        if (mac == GSPH_MAC_EIGEN) return drsqd < __dmul_rn(cmac, lg[5]);
-        if (mac == GSPH_MAC_GADGET2) return __dmul_rn(__dmul_rn(__dmul_rn(drsqd, drsqd), lg[5]), macerror) < cmac;
+        if (mac == GSPH_MAC_EIGEN) return drsqd < __dmul_rn(cmac, lc.y);
+        if (mac == GSPH_MAC_GADGET2) return __dmul_rn(__dmul_rn(__dmul_rn(drsqd, drsqd), lc.y), macerror) < cmac;
         return false;
       };
       if (node >= 0) {
-        const double2 g0 = rec[0], g1 = rec[1], g2 = rec[2], g3 = rec[3];
+        const double2 g0 = S.nodes[GW_NODE_UNIT(lane, 0)], g1 = S.nodes[GW_NODE_UNIT(lane, 1)],
+                      g2 = S.nodes[GW_NODE_UNIT(lane, 2)], g3 = S.nodes[GW_NODE_UNIT(lane, 3)];
         ncount = __double2hiint(g3.x); nfirst = __double2loint(g3.x);
         isleaf = node >= leaf0;
         if (ncount > 0) {
