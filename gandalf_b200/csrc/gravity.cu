@@ -896,13 +896,15 @@ gravity_cells_kernel(PartView P, TreeDev tree, DevParams dp, const double2* __re
 }
 
 /* The direct leaves; runs after gravity_cells_kernel of the same batch (same stream) and closes the cohort
- * (gpot_hydro, done flag, statistics).  Leaf by leaf: the LANES ARE THE SOURCE PARTICLES.  The entries of the
- * cohort's list that name the leaf are expanded into a queue of source particle ids; every group of 32 sources is
- * loaded once (consecutive lanes = consecutive particles of a leaf: coalesced) and each lane evaluates its source
- * against the (up to) four target particles of the leaf, four independent chains; the per-lane partial sums are
- * added up over the warp at the end of the leaf.  Every lane is busy whatever the leaf masks of the entries
- * look like -- with lanes as targets the warp waits for the leaf with most entries in every tile.           */
-#define GD_QUEUE 512                     /* ring of source ids per warp (a chunk of 32 entries adds <= 32*8) */
+ * (gpot_hydro, done flag, statistics).  Target leaf by target leaf: the LANES ARE THE SOURCE PARTICLES.  The entries
+ * of the cohort's list that name the target leaf are compacted (one ballot per chunk of 32 entries) into a ring of
+ * (first particle, count); a round takes the next 32 / W of them, W lanes per source leaf (W = particles of the
+ * largest leaf: consecutive lanes read consecutive particles, coalesced), and each lane evaluates its source against
+ * the (up to) four target particles of the leaf, four independent chains; the per-lane partial sums are added up
+ * over the warp at the end of the target leaf.  Every lane is busy whatever the leaf masks of the entries look
+ * like -- with lanes as targets the warp waits for the leaf with most entries in every tile.  (Expanding the entries
+ * into a ring of particle ids first cost a scan and a divergent fill loop per chunk and leaf, a quarter of the
+ * kernel's instructions; one lane per source LEAF instead was measured too: its loads do not coalesce, +13 ms.) */
 
 /* sum of 16 per-lane values over the warp in 16 exchanges instead of 80: every step halves the number of values a
    lane carries (it keeps one half and hands the other to its partner).  Afterwards a[0] of lane L is the warp
@@ -925,14 +927,16 @@ template <int NTG>                       /* target groups of 4 particles per lea
 __global__ void __launch_bounds__(GRAV_THREADS, 3)
 gravity_direct_kernel(PartView P, TreeDev tree, DevParams dp, const double2* __restrict__ geo4, int cohort_level,
                       int c0, int nc, int* work_counter, const int2* __restrict__ dirs, int dir_cap,
-                      const int* __restrict__ counts, DevStatus* st, uint8_t* done)
+                      const int* __restrict__ counts, DevStatus* st, uint8_t* done, int W)
 {
   constexpr int NP = 32*NTG;                                /* particles of a cohort: 8 leaves x 4 NTG */
-  __shared__ int queue_s[GRAV_WARPS][GD_QUEUE];
+  __shared__ int2 queue_s[GRAV_WARPS][64];                  /* compacted (first, count) entries of the current leaf */
   __shared__ double2 tgt_s[GRAV_WARPS][NP][2];              /* (x, y) (z, hrangesqd) of the cohort's particles: broadcast reads */
   __shared__ double res_s[GRAV_WARPS][NP][4];               /* their sums ax, ay, az, pot */
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int* const queue = queue_s[warp];
+  int2* const queue = queue_s[warp];
+  /* W = particles of the largest leaf: a round serves EPR = 32 / W source leaves with W lanes each */
+  const int EPR = 32/W, myslot = lane/W, myk = lane - myslot*W;
   double2 (&tgt)[NP][2] = tgt_s[warp];
   double (&res)[NP][4] = res_s[warp];
   const int ncohort = 1 << cohort_level;
@@ -992,7 +996,7 @@ gravity_direct_kernel(PartView P, TreeDev tree, DevParams dp, const double2* __r
 #pragma unroll
         for (int k = 0; k < 16; k++) acc[k] = 0.0;
         int qhead = 0, qn = 0, nsrc = 0;
-        /* software pipeline: the sources of the next group are loaded while the current group is evaluated */
+        /* software pipeline: the sources of the next round are loaded while the current ones are evaluated */
         double px = 0.0, py = 0.0, pz = 0.0, pm = 0.0, ph = -1.0;
         bool pend = false;
         auto evaluate = [&]() {
@@ -1008,14 +1012,20 @@ gravity_direct_kernel(PartView P, TreeDev tree, DevParams dp, const double2* __r
             acc[4*t + 3] += mmj*inv;
           }
         };
-        auto advance = [&](int n) {                         /* load the first n <= 32 queued sources, evaluate the pending ones */
+        /* one round: the next (up to) EPR queued source leaves, W lanes each -- lane -> (leaf myslot, particle myk):
+           consecutive lanes read consecutive particles, coalesced like a slab; a leaf with fewer than W particles
+           leaves lanes idle (none in a tree with full leaves) */
+        auto round = [&](int n) {
           double xj = 0.0, yj = 0.0, zj = 0.0, mj = 0.0, hj = -1.0;
-          if (lane < n) {
-            const int j = queue[(qhead + lane) & (GD_QUEUE - 1)];
-            const double2 a = geo4[2*(size_t) j], bb = geo4[2*(size_t) j + 1];      /* m = 0 for dead particles */
-            xj = a.x; yj = a.y; zj = bb.x; mj = bb.y; hj = hr2a[j];
+          if (myslot < n) {
+            const int2 q = queue[(qhead + myslot) & 63];
+            if (myk < q.y) {
+              const int j = q.x + myk;
+              const double2 a = geo4[2*(size_t) j], bb = geo4[2*(size_t) j + 1];      /* m = 0 for dead particles */
+              xj = a.x; yj = a.y; zj = bb.x; mj = bb.y; hj = hr2a[j];
+            }
           }
-          qhead = (qhead + n) & (GD_QUEUE - 1); qn -= n;
+          qhead = (qhead + n) & 63; qn -= n;
           if (pend) evaluate();
           px = xj; py = yj; pz = zj; pm = mj; ph = hj; pend = true;
         };
@@ -1024,18 +1034,21 @@ gravity_direct_kernel(PartView P, TreeDev tree, DevParams dp, const double2* __r
           const int2 e = enext;
           enext = make_int2(0, 0);
           if (base + 32 + lane < ndir) enext = mydirs[base + 32 + lane];        /* next chunk of entries on its way */
-          const int cj = ((e.y >> l) & 1) ? ((e.y >> 8) & 0xff) : 0;
-          int tot;
-          const int off = warp_excl_scan(cj, lane, tot);
-          for (int k = 0; k < cj; k++) queue[(qhead + qn + off + k) & (GD_QUEUE - 1)] = e.x + k;
-          qn += tot; nsrc += tot;
+          const bool take = (e.y >> l) & 1;                                       /* (zero beyond the list) */
+          const unsigned tbal = __ballot_sync(FULLMASK, take);
+          if (take) {
+            queue[(qhead + qn + __popc(tbal & ((1u << lane) - 1u))) & 63] = make_int2(e.x, (e.y >> 8) & 0xff);
+            nsrc += (e.y >> 8) & 0xff;
+          }
+          qn += __popc(tbal);
           __syncwarp();
-          while (qn >= 32) advance(32);
+          while (qn >= EPR) round(EPR);
           __syncwarp();
         }
-        if (qn > 0) advance(qn);
-        __syncwarp();                                       /* the ring is rewritten from slot 0 by the next leaf */
+        if (qn > 0) round(qn);
+        __syncwarp();                                       /* the ring is rewritten by the next leaf */
         if (pend) evaluate();
+        nsrc = __reduce_add_sync(FULLMASK, nsrc);
         /* sum over the lanes; the even lane L holds value v(L) = (target, component) */
         const double tot = warp_reduce16(acc, lane);
         const int v = ((lane >> 4) & 1)*8 + ((lane >> 3) & 1)*4 + ((lane >> 2) & 1)*2 + ((lane >> 1) & 1);
@@ -1154,7 +1167,8 @@ int launch_gravity_decoupled(gsph_handle* h)
                                              cells, cell_cap, counts, h->status);
     const int dblocks = std::min(h->sm_count*dbps, (nc + GRAV_WARPS - 1)/GRAV_WARPS);
     kdirect<<<dblocks, GRAV_THREADS, 0, sc>>>(P, h->tree, h->dp, (const double2*) h->geo4, Lg, c0, nc, h->work_counter + 3,
-                                              dirs, dir_cap, counts, h->status, h->done);
+                                              dirs, dir_cap, counts, h->status, h->done,
+                                              (int) std::max<int64_t>(1, (h->N + ((int64_t) 1 << h->tree.ltot) - 1) >> h->tree.ltot));
     CUDA_TRY(h, cudaEventRecord(h->ev_grav[2 + buf], sc));
     h->stats.kernel_launches += 3;
   }
