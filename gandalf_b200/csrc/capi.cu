@@ -127,7 +127,7 @@ int ensure_capacity(gsph_handle* h, int64_t N)
      cudaMalloc half-way leaves a handle that refuses work instead of one that launches on freed arrays */
   h->Ncap = 0; h->integ.cap = 0;
   h->uploaded = h->have_tree = h->sorted_valid = h->density_done = false;
-  h->integ.on = false; h->results_newer = false;
+  h->integ.on = false; h->results_newer = false; h->v_pending = false; h->vcom_valid = false;
   h->present_d = h->hdef_d = h->pvalid_d = 0ull; h->present_i = h->hdef_i = h->pvalid_i = 0u;
   for (int f = 0; f < NF_DOUBLE; f++) {
     if (h->H[f]) cudaFree(h->H[f]); if (h->P[f]) cudaFree(h->P[f]);
@@ -695,6 +695,7 @@ int gsph_create(const gsph_config* cfg, gsph_handle** out)
   if ((e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
   if ((e = cudaEventCreateWithFlags(&h->ev_geom, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
   if ((e = cudaEventCreateWithFlags(&h->ev_all, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+  if ((e = cudaEventCreateWithFlags(&h->ev_early, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
   if ((e = cudaEventCreateWithFlags(&h->ev_compute, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
   for (int k = 0; k < 3; k++)
     if ((e = cudaEventCreateWithFlags(&h->ev_axis[k], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
@@ -739,6 +740,7 @@ void gsph_destroy(gsph_handle* h)
   for (int k = 0; k < 6; k++) for (int j = 0; j < 2; j++) if (h->evk[k][j]) cudaEventDestroy(h->evk[k][j]);
   if (h->ev_geom) cudaEventDestroy(h->ev_geom);
   if (h->ev_all) cudaEventDestroy(h->ev_all);
+  if (h->ev_early) cudaEventDestroy(h->ev_early);
   if (h->ev_compute) cudaEventDestroy(h->ev_compute);
   for (int k = 0; k < 3; k++) if (h->ev_axis[k]) cudaEventDestroy(h->ev_axis[k]);
   fre(h->tree.nodeb); fre(h->tree.nodeh); fre(h->tree.gnode); fre(h->tree.mnode);
@@ -766,7 +768,11 @@ static int upload_impl(gsph_handle* h, const gsph_particle_view* view, int64_t N
   const int64_t nr = r1 - r0;
   cudaSetDevice(h->device);
   Timer tm(h, &h->stats.ms_upload);
-  int rc = ensure_capacity(h, N);
+  int rc = GSPH_OK;
+  if (h->v_pending && N == h->N) rc = gsph_ensure_velocities(h);   /* before the staging copy of v is overwritten */
+  if (rc) return rc;
+  h->v_pending = false;
+  rc = ensure_capacity(h, N);
   if (rc) return rc;
   const int nd = h->cfg.ndim;
   if (!vfield(view, VOFF(r[0])).base || !vfield(view, VOFF(m)).base || !vfield(view, VOFF(h)).base) {
@@ -792,11 +798,14 @@ static int upload_impl(gsph_handle* h, const gsph_particle_view* view, int64_t N
      waits for the compute stream, which may still be reading the staging arrays of the last step. */
   CUDA_TRY(h, cudaEventRecord(h->ev_compute, h->stream));
   CUDA_TRY(h, cudaStreamWaitEvent(h->copy_stream, h->ev_compute, 0));
-  for (int pass = 0; pass < 2; pass++) {
+  /* pass 0: geometry, 1: everything else but the velocities, 2: the velocities (first needed by the force pass) */
+  for (int pass = 0; pass < 3; pass++) {
+    if (pass == 2) CUDA_TRY(h, cudaEventRecord(h->ev_early, h->copy_stream));
     for (int k = 0; k < kNDoubleFields; k++) {
       const int pf = kDoubleFields[k].pf;
       const bool geom = (pf >= F_RX && pf <= F_RZ) || pf == F_H;
-      if (geom != (pass == 0)) continue;
+      const bool vel = pf >= F_VX && pf <= F_VZ;
+      if ((geom ? 0 : (vel ? 2 : 1)) != pass) continue;
       const gsph_field& f = vfield(view, kDoubleFields[k].off);
       const bool unused_dim = (pf >= F_RX && pf <= F_ATZ) && ((pf - F_RX) % 3 >= nd);
       if (!f.base || unused_dim) {
@@ -824,7 +833,7 @@ static int upload_impl(gsph_handle* h, const gsph_particle_view* view, int64_t N
       if (pf >= F_RX && pf <= F_RZ && !(bulk_ok && (plan.nf || plan.ni)))
         CUDA_TRY(h, cudaEventRecord(h->ev_axis[pf - F_RX], h->copy_stream));
     }
-    if (pass == 1) break;
+    if (pass >= 1) continue;
     for (int k = 0; k < kNIntFields; k++) {
       const int pf = kIntFields[k].pf;
       const gsph_field& f = vfield(view, kIntFields[k].off);
@@ -871,6 +880,7 @@ static int upload_impl(gsph_handle* h, const gsph_particle_view* view, int64_t N
     }
     CUDA_TRY(h, cudaEventRecord(h->ev_geom, h->copy_stream));
     for (int k = 0; k < 3; k++) CUDA_TRY(h, cudaEventRecord(h->ev_axis[k], h->copy_stream));
+    CUDA_TRY(h, cudaEventRecord(h->ev_early, h->copy_stream));
   }
   CUDA_TRY(h, cudaEventRecord(h->ev_all, h->copy_stream));
   h->upload_pending = true;
@@ -1372,7 +1382,8 @@ int gsph_update_hydro_forces(gsph_handle* h)
   h->results_newer = true;
   cudaSetDevice(h->device);
   Timer tm(h, &h->stats.ms_forces);
-  int rc = reset_status(h); if (rc) return rc;
+  int rc = gsph_ensure_velocities(h); if (rc) return rc;
+  rc = reset_status(h); if (rc) return rc;
   rc = prepare_accumulators(h); if (rc) return rc;
   rc = gsph_prepare_done_flags(h); if (rc) return rc;
   rc = run_with_regrow(h, "gsph_update_hydro_forces", pass_hydro, 0);
@@ -1398,7 +1409,8 @@ int gsph_update_all_forces_begin(gsph_handle* h)
   cudaSetDevice(h->device);
   h->forces_half_done = false;
   Timer tm(h, &h->stats.ms_forces);
-  int rc = reset_status(h); if (rc) return rc;
+  int rc = gsph_ensure_velocities(h); if (rc) return rc;
+  rc = reset_status(h); if (rc) return rc;
   rc = prepare_accumulators(h); if (rc) return rc;
   rc = gsph_prepare_done_flags(h); if (rc) return rc;
   rc = run_with_regrow(h, "gsph_update_all_forces(neighbours)", pass_hydro, 1);
@@ -1464,6 +1476,7 @@ int gsph_update_star_gas_forces(gsph_handle* h, const double* stars, int Nstar, 
     if (h->dp.periodic[k]) { h->err = "gsph_update_star_gas_forces: periodic (Ewald) gravity is not on the accelerated path"; return GSPH_EINVAL; }
   if (Nstar == 0) return GSPH_OK;
   cudaSetDevice(h->device);
+  { const int rv = gsph_ensure_velocities(h); if (rv) return rv; }       /* adot reads the gas velocities */
   const int nd = h->cfg.ndim, row = 2*nd + 1;
   double* d = nullptr; int* di = nullptr;
   CUDA_TRY(h, cudaMalloc(&d, (size_t) Nstar*row*2*sizeof(double)));
@@ -1595,6 +1608,7 @@ int gsph_tree_cells(gsph_handle* h, double* box, double* com, double* scalars, d
   if (!h) return GSPH_EINVAL;
   if (!h->have_tree) { h->err = "gsph_tree_cells before gsph_build_tree"; return GSPH_ESTATE; }
   cudaSetDevice(h->device);
+  { const int rv = gsph_ensure_vcom(h); if (rv) return rv; }
   const TreeDev& T = h->tree;
   const int nd = h->cfg.ndim, nc = T.ncell;
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -2010,6 +2024,7 @@ int gsph_integrator_advance(gsph_handle* h, int* tree_mode, double* timestep)
   }
   CUDA_TRY(h, cudaEventRecord(h->ev_geom, h->stream));
   CUDA_TRY(h, cudaEventRecord(h->ev_all, h->stream));
+  CUDA_TRY(h, cudaEventRecord(h->ev_early, h->stream));
   for (int k = 0; k < 3; k++) CUDA_TRY(h, cudaEventRecord(h->ev_axis[k], h->stream));
   h->sorted_valid = false; h->density_done = false; h->results_newer = false;
   h->slice_mode = false; h->dp.slice_lo = 0; h->dp.slice_hi = 0x7fffffff;

@@ -155,6 +155,10 @@ struct gsph_handle {
        ev_compute: the compute stream reached the point where a copy may touch the staging arrays  */
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_geom = nullptr, ev_all = nullptr, ev_compute = nullptr;
+  cudaEvent_t ev_early = nullptr;   /* everything but the velocities has landed (they are uploaded last) */
+  /* the velocities are not needed before the force pass: a full rebuild leaves their permutation (and the cells'
+     vcom) for later, so that their upload overlaps the tree build and the density pass */
+  bool v_pending = false, vcom_valid = true;
   cudaEvent_t ev_axis[3] = {nullptr, nullptr, nullptr};   /* coordinate k of the last upload has landed (its sort may start) */
   bool upload_pending = false;   /* ev_geom / ev_all still have to be waited for by the compute stream */
   std::string err;
@@ -247,7 +251,9 @@ int gsph_run_star_gas(gsph_handle* h, const double* dstars, int Nstar, double* d
 int gsph_check_status(gsph_handle* h, const char* where);             /* capi.cu    */
 int gsph_ensure_cand(gsph_handle* h, int warps, size_t cap_per_warp);
 int gsph_ensure_nlist(gsph_handle* h, int warps, size_t cap);
-int gsph_gather_fields(gsph_handle* h);                               /* tree.cu: host order -> tree order */
+int gsph_gather_fields(gsph_handle* h, bool defer_v = false);         /* tree.cu: host order -> tree order */
+int gsph_ensure_velocities(gsph_handle* h);                           /* tree.cu: the deferred part of it */
+int gsph_ensure_vcom(gsph_handle* h);                                 /* tree.cu: ... and the cells' vcom */
 int gsph_prewalk_prepare(gsph_handle* h, int cohort_level);           /* capi.cu: sizes pre_cand / pre_count; pre_n = 0: disabled */
 /* fields written by the passes (for pvalid_*) */
 #define GSPH_DMASK(f) (1ull << (f))

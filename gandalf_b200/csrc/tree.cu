@@ -93,7 +93,7 @@ __global__ void gather_kernel(int N, const int32_t* perm, PartView Hh, PartView 
   const int p = blockIdx.x*blockDim.x + threadIdx.x;
   if (p >= N) return;
   const int i = perm[p];
-  {
+  if (geo4) {
     /* packed (x, y, z, m) record of the density gather phase and the gravity sums; dead particles get m = 0 */
     const bool dead = ((imask >> I_FLAGS) & 1u) ? ((((unsigned) Hh.i[I_FLAGS][i]) & GSPH_FLAG_DEAD) != 0) : false;
     double2 a, b;
@@ -167,8 +167,10 @@ __device__ __forceinline__ void pack_node_from_regs(const TreeDev& T, int n, int
 
 /* ---- StockCellProperties for the leaves, KDTree.cpp:841-1010 -----------------------------------*/
 template <int NDIM>
-__global__ void stock_leaves_kernel(TreeDev T, PartView P, DevParams dp, int full)
+__global__ void stock_leaves_kernel(TreeDev T, PartView P, DevParams dp, int full_in)
 {
+  const int full = full_in & 3;
+  const bool with_v = !(full_in & 4);              /* 4: the velocities are not in tree order yet (stock_vcom later) */
   const int g = blockIdx.x*blockDim.x + threadIdx.x;
   const int nleaf = 1 << T.ltot;
   if (g >= nleaf) return;
@@ -192,7 +194,7 @@ __global__ void stock_leaves_kernel(TreeDev T, PartView P, DevParams dp, int ful
     for (int k = 0; k < NDIM; k++) {
       const double x = P.f[F_RX + k][i];
       com[k] += mi*x;
-      vc[k] += mi*P.f[F_VX + k][i];
+      if (with_v) vc[k] += mi*P.f[F_VX + k][i];
       bmin[k] = fmin(bmin[k], x); bmax[k] = fmax(bmax[k], x);
       hbmin[k] = fmin(hbmin[k], __dadd_rn(x, -hr)); hbmax[k] = fmax(hbmax[k], __dadd_rn(x, hr));
     }
@@ -238,7 +240,8 @@ __global__ void stock_leaves_kernel(TreeDev T, PartView P, DevParams dp, int ful
 #pragma unroll
   for (int k = 0; k < NDIM; k++) {
     T.bbmin[k][n] = bmin[k]; T.bbmax[k][n] = bmax[k];
-    T.rcell[k][n] = rc[k]; T.com[k][n] = com[k]; T.vcom[k][n] = vc[k];
+    T.rcell[k][n] = rc[k]; T.com[k][n] = com[k];
+    if (with_v) T.vcom[k][n] = vc[k];
   }
   /* quadrupole about the centre of mass, KDTree.cpp:937-1000 */
   double q[5] = {0, 0, 0, 0, 0};
@@ -260,8 +263,10 @@ __global__ void stock_leaves_kernel(TreeDev T, PartView P, DevParams dp, int ful
 
 /* ---- StockCellProperties for one internal level, KDTree.cpp:1013-1080 ---------------------------*/
 template <int NDIM>
-__global__ void stock_level_kernel(TreeDev T, DevParams dp, int level, int full)
+__global__ void stock_level_kernel(TreeDev T, DevParams dp, int level, int full_in)
 {
+  const int full = full_in & 3;
+  const bool with_v = !(full_in & 4);
   const int k = blockIdx.x*blockDim.x + threadIdx.x;
   if (k >= (1 << level)) return;
   const int n = (1 << level) - 1 + k;
@@ -305,7 +310,7 @@ __global__ void stock_level_kernel(TreeDev T, DevParams dp, int level, int full)
 #pragma unroll
     for (int d = 0; d < NDIM; d++) {
       com[d] = (m0*T.com[d][c[0]] + m1*T.com[d][c[1]])/m;
-      vc[d] = (m0*T.vcom[d][c[0]] + m1*T.vcom[d][c[1]])/m;
+      if (with_v) vc[d] = (m0*T.vcom[d][c[0]] + m1*T.vcom[d][c[1]])/m;
     }
   }
   double rc[3] = {0, 0, 0}, rmax = 0.0, cdist = GSPH_BIG;
@@ -324,7 +329,8 @@ __global__ void stock_level_kernel(TreeDev T, DevParams dp, int level, int full)
 #pragma unroll
   for (int d = 0; d < NDIM; d++) {
     T.bbmin[d][n] = bmin[d]; T.bbmax[d][n] = bmax[d];
-    T.rcell[d][n] = rc[d]; T.com[d][n] = com[d]; T.vcom[d][n] = vc[d];
+    T.rcell[d][n] = rc[d]; T.com[d][n] = com[d];
+    if (with_v) T.vcom[d][n] = vc[d];
   }
   double q[5] = {0, 0, 0, 0, 0};
 #pragma unroll
@@ -359,6 +365,39 @@ __global__ void extrapolate_kernel(TreeDev T, double dt)
     T.com[d][n] += s; T.rcell[d][n] += s;
     T.bbmin[d][n] += s; T.bbmax[d][n] += s; T.hbmin[d][n] += s; T.hbmax[d][n] += s;
   }
+}
+
+/* the cells' centre-of-mass velocities alone (same sums as the stocking kernels above): run when the velocities
+   reached tree order after the tree was stocked (deferred permutation) and an extrapolation asks for them */
+template <int NDIM>
+__global__ void stock_vcom_leaves_kernel(TreeDev T, PartView P)
+{
+  const int g = blockIdx.x*blockDim.x + threadIdx.x;
+  const int nleaf = 1 << T.ltot;
+  if (g >= nleaf) return;
+  const int n = nleaf - 1 + g;
+  const int fst = T.first[n], cnt = T.count[n];
+  double m = 0.0, vc[3] = {0, 0, 0};
+  for (int i = fst; i < fst + cnt; i++) {
+    if (((unsigned) P.i[I_FLAGS][i]) & GSPH_FLAG_DEAD) continue;
+    const double mi = P.f[F_M][i];
+    m += mi;
+#pragma unroll
+    for (int k = 0; k < NDIM; k++) vc[k] += mi*P.f[F_VX + k][i];
+  }
+#pragma unroll
+  for (int k = 0; k < NDIM; k++) T.vcom[k][n] = m > 0.0 ? vc[k]/m : vc[k];
+}
+template <int NDIM>
+__global__ void stock_vcom_level_kernel(TreeDev T, int level)
+{
+  const int k = blockIdx.x*blockDim.x + threadIdx.x;
+  if (k >= (1 << level)) return;
+  const int n = (1 << level) - 1 + k;
+  const int c0 = 2*n + 1, c1 = 2*n + 2;
+  const double m0 = T.m[c0], m1 = T.m[c1], m = m0 + m1;
+#pragma unroll
+  for (int d = 0; d < NDIM; d++) T.vcom[d][n] = m > 0.0 ? (m0*T.vcom[d][c0] + m1*T.vcom[d][c1])/m : 0.0;
 }
 
 /* outward-rounded single-precision node records for the neighbour walks (TreeDev::nodeb / nodeh) */
@@ -474,10 +513,12 @@ int stock_tree(gsph_handle* h, int full)
   TreeDev& T = h->tree;
   const PartView P = view_of(h->P, h->PI);
   const int nleaf = 1 << T.ltot;
-  stock_leaves_kernel<NDIM><<<(nleaf + 127)/128, 128, 0, h->stream>>>(T, P, h->dp, full);
+  const int fl = full | ((full && h->v_pending) ? 4 : 0);
+  if (full) h->vcom_valid = !h->v_pending;
+  stock_leaves_kernel<NDIM><<<(nleaf + 127)/128, 128, 0, h->stream>>>(T, P, h->dp, fl);
   for (int l = T.ltot - 1; l >= 0; l--) {
     const int nn = 1 << l;
-    stock_level_kernel<NDIM><<<(nn + 127)/128, 128, 0, h->stream>>>(T, h->dp, l, full);
+    stock_level_kernel<NDIM><<<(nn + 127)/128, 128, 0, h->stream>>>(T, h->dp, l, fl);
   }
   /* (the packed walk records are written by the stocking kernels themselves, pack_node_from_regs) */
   h->stats.kernel_launches += 1 + T.ltot;
@@ -501,6 +542,8 @@ int build_tree_nd(gsph_handle* h, int mode, double dt)
 
   if (mode == 2) {                                   /* extrapolate: Tree.cpp:172-198 */
     if (!h->have_tree) { h->err = "gsph_build_tree(extrapolate) before the first rebuild"; return GSPH_ESTATE; }
+    /* (gsph_upload has flushed a deferred velocity permutation) the cells move with the vcom of the last stock */
+    { const int rv = gsph_ensure_vcom(h); if (rv) return rv; }
     if (!h->sorted_valid) {
       cudaStreamWaitEvent(s, h->ev_all, 0);      /* every uploaded field has landed */
       { const int rg = gsph_gather_fields(h); if (rg) return rg; }
@@ -1281,8 +1324,11 @@ int build_tree_v2(gsph_handle* h, int phase, int shard_rank, int shard_world)
     return GSPH_OK;
   }
   CUDA_TRY(h, cudaMemcpyAsync(h->perm, L.ids[0][cur], sizeof(int)*(size_t) N, cudaMemcpyDeviceToDevice, s));
-  cudaStreamWaitEvent(s, h->ev_all, 0);      /* every uploaded field has landed */
-  { const int rg = gsph_gather_fields(h); if (rg) return rg; }
+  /* single-device rebuild straight after an upload: the velocities (uploaded last) are permuted when the force
+     pass asks for them -- the build and the density pass do not read them (the cd2010 switch does) */
+  const bool defer_v = phase == 0 && h->upload_pending && !h->integ.on && !h->integ.starting && h->dp.tdavisc != GSPH_TDAVISC_CD2010;
+  cudaStreamWaitEvent(s, defer_v ? h->ev_early : h->ev_all, 0);      /* the uploaded fields have landed */
+  { const int rg = gsph_gather_fields(h, defer_v); if (rg) return rg; }
   h->have_tree = true;
   cudaEventRecord(h->evk[4][1], s); h->evk_used[4] = true;
   cudaEventRecord(h->evk[5][0], s);
@@ -1299,10 +1345,11 @@ int build_tree_v2(gsph_handle* h, int phase, int shard_rank, int shard_world)
  * MAC / switch inputs of the previous step where the configuration reads them, and accumulators the
  * host supplied.  Otherwise (block time steps, dead particles) every field is permuted, because the
  * old values of inactive particles are inputs.                                                       */
-int gsph_gather_fields(gsph_handle* h)
+int gsph_gather_fields(gsph_handle* h, bool defer_v)
 {
   const int N = (int) h->N;
   const int nd = h->dp.ndim;
+  h->v_pending = false;
   /* inside a step of the resident loop every particle was just made active (one global time step); a
      BuildTree between steps sees the flags EndTimestep left (inactive): everything is permuted then */
   const bool integ = h->integ.on && h->integ.mid_step && h->integ.cfg.Nlevels <= 1;
@@ -1331,6 +1378,11 @@ int gsph_gather_fields(gsph_handle* h)
     dmask = (core | acc) & pres_d; imask = (icore | iacc) & pres_i;
     dfill = core & ~pres_d; ifill = icore & ~pres_i;
   }
+  if (defer_v && h->lazy_fields) {
+    unsigned long long vmask = 0ull;
+    for (int k = 0; k < nd; k++) vmask |= GSPH_DMASK(F_VX + k);
+    if ((dmask & vmask) == vmask) { dmask &= ~vmask; h->v_pending = true; }
+  }
   FillVals fv;
   for (int f = 0; f < NF_DOUBLE; f++) fv.d[f] = (f == F_H || f == F_INVOMEGA) ? 1.0 : 0.0;
   for (int f = 0; f < NF_INT; f++) fv.i[f] = f == I_FLAGS ? (int) GSPH_FLAG_ACTIVE : ((f == I_SINKID || f == I_IORIG) ? -1 : 0);
@@ -1340,6 +1392,53 @@ int gsph_gather_fields(gsph_handle* h)
   CUDA_TRY(h, cudaGetLastError());
   h->pvalid_d = dmask | dfill; h->pvalid_i = imask | ifill;
   h->sorted_valid = true; h->acc_zeroed = false;
+  return GSPH_OK;
+}
+
+/* the deferred part of the permutation: the velocities of the last upload into tree order */
+int gsph_ensure_velocities(gsph_handle* h)
+{
+  if (!h->v_pending) return GSPH_OK;
+  const int N = (int) h->N;
+  unsigned long long vmask = 0ull;
+  for (int k = 0; k < h->dp.ndim; k++) vmask |= GSPH_DMASK(F_VX + k);
+  CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_all, 0));
+  FillVals fv;
+  for (int f = 0; f < NF_DOUBLE; f++) fv.d[f] = 0.0;
+  for (int f = 0; f < NF_INT; f++) fv.i[f] = 0;
+  gather_kernel<<<(N + 255)/256, 256, 0, h->stream>>>(N, h->perm, view_of(h->H, h->HI), view_of(h->P, h->PI),
+                                                     vmask, 0u, 0ull, 0u, fv, (double*) nullptr, h->dp.ndim);
+  h->stats.kernel_launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  h->pvalid_d |= vmask;
+  h->v_pending = false;
+  return GSPH_OK;
+}
+
+/* the cells' centre-of-mass velocities, if the last stock ran before the velocities were in tree order */
+int gsph_ensure_vcom(gsph_handle* h)
+{
+  int rc = gsph_ensure_velocities(h); if (rc) return rc;
+  if (h->vcom_valid || !h->have_tree) return GSPH_OK;
+  const PartView Pv = view_of(h->P, h->PI);
+  const int nleaf = 1 << h->tree.ltot;
+  cudaStream_t s = h->stream;
+  switch (h->dp.ndim) {
+  case 1: stock_vcom_leaves_kernel<1><<<(nleaf + 127)/128, 128, 0, s>>>(h->tree, Pv); break;
+  case 2: stock_vcom_leaves_kernel<2><<<(nleaf + 127)/128, 128, 0, s>>>(h->tree, Pv); break;
+  default: stock_vcom_leaves_kernel<3><<<(nleaf + 127)/128, 128, 0, s>>>(h->tree, Pv); break;
+  }
+  for (int l = h->tree.ltot - 1; l >= 0; l--) {
+    const int nb = ((1 << l) + 127)/128;
+    switch (h->dp.ndim) {
+    case 1: stock_vcom_level_kernel<1><<<nb, 128, 0, s>>>(h->tree, l); break;
+    case 2: stock_vcom_level_kernel<2><<<nb, 128, 0, s>>>(h->tree, l); break;
+    default: stock_vcom_level_kernel<3><<<nb, 128, 0, s>>>(h->tree, l); break;
+    }
+  }
+  h->stats.kernel_launches += 1 + h->tree.ltot;
+  CUDA_TRY(h, cudaGetLastError());
+  h->vcom_valid = true;
   return GSPH_OK;
 }
 
