@@ -97,6 +97,7 @@ EXPORTS = [
     "gsph_neighbour_counts", "gsph_neighbour_lists", "gsph_tree_info_get", "gsph_tree_leaf_of",
     "gsph_tree_cells", "gsph_get_stats", "gsph_kernel_table", "gsph_measure_fp_peak",
     "gsph_integrator_begin", "gsph_integrator_step", "gsph_integrator_state", "gsph_integrator_block_state",
+    "gsph_integrator_start_state",
     "gsph_update_all_forces_begin", "gsph_update_all_forces_finish", "gsph_integrator_advance",
     "gsph_integrator_finish", "gsph_integrator_check_timesteps", "gsph_update_thermal_properties",
     "gsph_update_star_gas_forces", "gsph_derive_density_fields",
@@ -151,6 +152,7 @@ def lib():
     L.gsph_update_star_gas_forces.argtypes = [H, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.gsph_integrator_state.argtypes = [H, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     L.gsph_integrator_block_state.argtypes = [H, C.POINTER(BlockState), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.gsph_integrator_start_state.argtypes = [H] + [C.c_void_p]*6
     for n in ("gsph_update_active_counters", "gsph_update_properties", "gsph_zero_accelerations",
               "gsph_update_hydro_forces", "gsph_synchronize", "gsph_timer_start", "gsph_density_pass",
               "gsph_update_all_forces_begin", "gsph_update_all_forces_finish",

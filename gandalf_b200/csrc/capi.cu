@@ -2174,6 +2174,29 @@ int gsph_integrator_block_state(gsph_handle* h, gsph_block_state* st, int32_t* n
   return GSPH_OK;
 }
 
+/* the start-of-step state of every particle in host order (SphLeapfrogKDK keeps it in the particle: r0, v0, a0,
+   u0, dudt0; with block time steps also dt_next): what a host needs to carry a run on in the reference's own
+   MainLoop.  r0, v0, a0: ndim arrays of N doubles one after the other (component-major); NULL = not wanted. */
+int gsph_integrator_start_state(gsph_handle* h, double* r0, double* v0, double* a0, double* u0, double* dudt0, double* dt_next)
+{
+  if (!h) return GSPH_EINVAL;
+  if (!h->integ.on) { h->err = "gsph_integrator_start_state before gsph_integrator_begin"; return GSPH_ESTATE; }
+  const IntegState& I = h->integ;
+  if (dt_next && I.cfg.Nlevels <= 1) { h->err = "gsph_integrator_start_state: dt_next exists with Nlevels > 1 only"; return GSPH_EINVAL; }
+  cudaSetDevice(h->device);
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  const size_t N = (size_t) h->N;
+  const int nd = h->cfg.ndim;
+  double* const out3[3] = {r0, v0, a0};
+  for (int g = 0; g < 3; g++)
+    if (out3[g]) for (int k = 0; k < nd; k++)
+      CUDA_TRY(h, cudaMemcpy(out3[g] + (size_t) k*N, I.s0[3*g + k], N*sizeof(double), cudaMemcpyDeviceToHost));
+  if (u0) CUDA_TRY(h, cudaMemcpy(u0, I.s0[9], N*sizeof(double), cudaMemcpyDeviceToHost));
+  if (dudt0) CUDA_TRY(h, cudaMemcpy(dudt0, I.s0[10], N*sizeof(double), cudaMemcpyDeviceToHost));
+  if (dt_next) CUDA_TRY(h, cudaMemcpy(dt_next, I.dt_next, N*sizeof(double), cudaMemcpyDeviceToHost));
+  return GSPH_OK;
+}
+
 int gsph_timer_start(gsph_handle* h)
 {
   if (!h) return GSPH_EINVAL;

@@ -47,6 +47,8 @@ class GpuSphTree : public GradhSphTree<ndim, GradhSphParticle>
   gsph_handle* handle;
   bool keep_host_tree;        ///< also maintain the CPU tree for the non-accelerated consumers
   bool staged;                ///< device copy matches the host array of this step
+  int resident_levels = 1;    ///< Nlevels of the device-resident loop started by ResidentBegin
+  bool resident_energy = true; ///< ... and whether it integrates u (SphLeapfrogKDK touches u0, dudt0 only then)
 
   static int lookup(const std::string& v, const char* const* names, int n, const char* what) {
     for (int i = 0; i < n; i++) if (v == names[i]) return i;
@@ -257,9 +259,9 @@ class GpuSphTree : public GradhSphTree<ndim, GradhSphParticle>
   }
 
   //-----------------------------------------------------------------------------------------------
-  // Device-resident main loop (include/gsph.h, gsph_integrator_*): for sph_integration = lfkdk,
-  // Nlevels = 1 and no star particles, SphSimulation::MainLoop itself (SphSimulation.cpp:574-880)
-  // runs on the device; the particle array crosses PCIe once in each direction.
+  // Device-resident main loop (include/gsph.h, gsph_integrator_*): for sph_integration = lfkdk (one global
+  // time step or hierarchical block time steps) and no star particles, SphSimulation::MainLoop itself
+  // (SphSimulation.cpp:574-880) runs on the device; the particle array crosses PCIe once in each direction.
   //-----------------------------------------------------------------------------------------------
   /// Call after PostInitialConditionsSetup (or any completed MainLoop): ships the complete particle
   /// state and starts the device loop at simulation time t.
@@ -268,8 +270,12 @@ class GpuSphTree : public GradhSphTree<ndim, GradhSphParticle>
     std::map<std::string, int>& ip = params->intparams;
     std::map<std::string, double>& fp = params->floatparams;
     std::map<std::string, std::string>& sp = params->stringparams;
-    if (sp["sph_integration"] != "lfkdk" || ip["Nlevels"] != 1)
-      ExceptionHandler::getIstance().raise("GpuSphTree: the device-resident main loop needs sph_integration = lfkdk and Nlevels = 1");
+    if (sp["sph_integration"] != "lfkdk" || ip["Nlevels"] < 1)
+      ExceptionHandler::getIstance().raise("GpuSphTree: the device-resident main loop needs sph_integration = lfkdk");
+    // hierarchical block time steps (Nlevels > 1): the device loop starts with a resynchronisation of the hierarchy like
+    // PostInitialConditionsSetup, so begin there (or at a step with n == nresync); the single-step switch is not built
+    if (ip["Nlevels"] > 1 && ip["sph_single_timestep"] != 0)
+      ExceptionHandler::getIstance().raise("GpuSphTree: sph_single_timestep with Nlevels > 1 is not on the accelerated path");
     // MainLoop's sink search / accretion / stellar-property update (SphSimulation.cpp:815-833) is not on this path
     if (ip["sink_particles"] != 0 || ip["create_sinks"] != 0)
       ExceptionHandler::getIstance().raise("GpuSphTree: sink_particles / create_sinks are not on the accelerated path of the device-resident main loop");
@@ -279,6 +285,8 @@ class GpuSphTree : public GradhSphTree<ndim, GradhSphParticle>
     ic.energy_integration = sp["gas_eos"] == "energy_eqn" ? 1 : 0;      // GradhSphSimulation.cpp:110-123
     ic.ntreebuildstep = ip["ntreebuildstep"]; ic.ntreestockstep = ip["ntreestockstep"];
     ic.sink_particles = ip["sink_particles"];
+    ic.Nlevels = ip["Nlevels"]; ic.level_diff_max = ip["level_diff_max"];
+    resident_levels = ic.Nlevels; resident_energy = ic.energy_integration != 0;
     check(gsph_set_stars(handle, NULL, 0));
     upload(sph);
     check(gsph_integrator_begin(handle, &ic, 0, t));
@@ -289,20 +297,43 @@ class GpuSphTree : public GradhSphTree<ndim, GradhSphParticle>
 
   /// Brings the particles home in the state the reference holds at the end of MainLoop (r0 = r, v0 = v,
   /// a0 = a, u0 = u, dudt0 = dudt, tlast = t, dt = the next step; SphLeapfrogKDK::EndTimestep,
-  /// Simulation::ComputeGlobalTimestep), so that its own MainLoop can carry on from there.
-  void ResidentFetch(Sph<ndim>* sph, double* t_out, double* timestep_out, long long* nsteps_out)
+  /// Simulation::ComputeGlobalTimestep), so that its own MainLoop can carry on from there.  With block time
+  /// steps every particle sits somewhere inside its own step: its level, nstep, nlast, dt, dt_next, tlast and the
+  /// start-of-step state r0, v0, a0, u0, dudt0 come from the device as they are, and *blk receives the scalars of
+  /// the hierarchy (Simulation::n, nresync, level_max, level_step, dt_max).
+  void ResidentFetch(Sph<ndim>* sph, double* t_out, double* timestep_out, long long* nsteps_out, gsph_block_state* blk = NULL)
   {
     download(sph, GSPH_F_ALL);
     double t = 0.0, ts = 0.0; int64_t n = 0;
     check(gsph_integrator_state(handle, &t, &ts, &n));
     Part* p = sph->template GetParticleArray<GradhSphParticle>();
-    for (int i = 0; i < sph->Nhydro; i++) {
-      if (p[i].flags.is_dead()) continue;
-      for (int k = 0; k < ndim; k++) { p[i].r0[k] = p[i].r[k]; p[i].v0[k] = p[i].v[k]; p[i].a0[k] = p[i].a[k]; }
-      p[i].u0 = p[i].u; p[i].dudt0 = p[i].dudt;
-      p[i].level = 0; p[i].levelneib = 0; p[i].nstep = 1; p[i].nlast = 0;
-      p[i].tlast = t; p[i].dt = ts; p[i].dt_next = 0;
-      p[i].flags.unset(active); p[i].flags.unset(end_timestep);
+    const size_t N = (size_t) sph->Nhydro;
+    if (resident_levels > 1) {
+      std::vector<int32_t> nstep(N), nlast(N);
+      std::vector<double> dt(N), tlast(N), dtn(N), u0(N), dudt0(N), r0(ndim*N), v0(ndim*N), a0(ndim*N);
+      gsph_block_state st;
+      check(gsph_integrator_block_state(handle, &st, nstep.data(), nlast.data(), dt.data(), tlast.data()));
+      check(gsph_integrator_start_state(handle, r0.data(), v0.data(), a0.data(), u0.data(), dudt0.data(), dtn.data()));
+      for (size_t i = 0; i < N; i++) {
+        if (p[i].flags.is_dead()) continue;
+        for (int k = 0; k < ndim; k++) { p[i].r0[k] = r0[k*N + i]; p[i].v0[k] = v0[k*N + i]; p[i].a0[k] = a0[k*N + i]; }
+        if (resident_energy) { p[i].u0 = u0[i]; p[i].dudt0 = dudt0[i]; }
+        p[i].nstep = nstep[i]; p[i].nlast = nlast[i];            // (level, levelneib came with the download)
+        p[i].tlast = tlast[i]; p[i].dt = dt[i]; p[i].dt_next = dtn[i];
+        p[i].flags.unset(active); p[i].flags.unset(end_timestep);
+      }
+      if (blk) *blk = st;
+    }
+    else {
+      for (size_t i = 0; i < N; i++) {
+        if (p[i].flags.is_dead()) continue;
+        for (int k = 0; k < ndim; k++) { p[i].r0[k] = p[i].r[k]; p[i].v0[k] = p[i].v[k]; p[i].a0[k] = p[i].a[k]; }
+        p[i].u0 = p[i].u; p[i].dudt0 = p[i].dudt;
+        p[i].level = 0; p[i].levelneib = 0; p[i].nstep = 1; p[i].nlast = 0;
+        p[i].tlast = t; p[i].dt = ts; p[i].dt_next = 0;
+        p[i].flags.unset(active); p[i].flags.unset(end_timestep);
+      }
+      if (blk) { blk->n = 0; blk->nresync = 0; blk->level_max = 0; blk->level_step = 0; blk->dt_max = ts; }
     }
     if (t_out) *t_out = t;
     if (timestep_out) *timestep_out = ts;

@@ -282,6 +282,20 @@ class GpuSphTree(object):
         out.update(n=st.n, nresync=st.nresync, level_max=st.level_max, level_step=st.level_step, dt_max=st.dt_max)
         return out
 
+    def IntegratorStartState(self):
+        """start-of-step state of every particle (r0, v0, a0, u0, dudt0 of SphLeapfrogKDK; dt_next with block steps)"""
+        N, nd = self.Stats().Nhydro, self.cfg.ndim
+        out = {"r0": np.zeros((nd, N)), "v0": np.zeros((nd, N)), "a0": np.zeros((nd, N)), "u0": np.zeros(N), "dudt0": np.zeros(N)}
+        blk = int(self.params["Nlevels"]) > 1
+        if blk:
+            out["dt_next"] = np.zeros(N)
+        self._check(self._L.gsph_integrator_start_state(self._h, out["r0"].ctypes.data, out["v0"].ctypes.data, out["a0"].ctypes.data,
+                                                        out["u0"].ctypes.data, out["dudt0"].ctypes.data,
+                                                        out["dt_next"].ctypes.data if blk else None))
+        for k in ("r0", "v0", "a0"):
+            out[k] = np.ascontiguousarray(out[k].T)
+        return out
+
     # ---- snapshots in the reference's "su" wire format (gandalf_b200/snapshot.py) ------------------
     def WriteSnapshot(self, path, alloc=None, **header):
         """SEREN-unformatted snapshot of the particles on the device (SimulationIO.hpp:1655-2262): only

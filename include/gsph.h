@@ -411,6 +411,11 @@ int gsph_integrator_state(gsph_handle* h, double* t, double* timestep, int64_t* 
  * (double[N]).  level and levelneib come with gsph_download.                                          */
 typedef struct gsph_block_state { int64_t n, nresync; int32_t level_max, level_step; double dt_max; } gsph_block_state;
 int gsph_integrator_block_state(gsph_handle* h, gsph_block_state* st, int32_t* nstep, int32_t* nlast, double* dt, double* tlast);
+/* the start-of-step state SphLeapfrogKDK keeps in every particle (r0, v0, a0, u0, dudt0, Particle.h:150-165; with
+ * block time steps also dt_next), host order; r0, v0, a0 = ndim arrays of N doubles one after the other.  Together with
+ * gsph_download and gsph_integrator_block_state this is everything the reference's own MainLoop needs to carry a
+ * device-resident run on (GpuSphTree::ResidentFetch).  NULL = not wanted.                                       */
+int gsph_integrator_start_state(gsph_handle* h, double* r0, double* v0, double* a0, double* u0, double* dudt0, double* dt_next);
 
 /* Kernel tables exactly as TabulatedKernel builds them (TabulatedKernel.cpp:58-105,
  * SmoothingKernel.h:585-605): which = 0 w0_s2, 1 womega_s2, 2 wzeta_s2, 3 w1, 4 wgrav, 5 wpot;

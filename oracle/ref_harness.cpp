@@ -533,8 +533,13 @@ static int run(Parameters* params, const string& icfile, double perturb, const s
       gt->ResidentBegin(sim->sph, sim->simparams, sim->t);
       gt->ResidentMainLoop(K);
       double tt = 0.0, ts = 0.0; long long ns = 0;
-      gt->ResidentFetch(sim->sph, &tt, &ts, &ns);
+      gsph_block_state bs;
+      gt->ResidentFetch(sim->sph, &tt, &ts, &ns, &bs);
       sim->t = tt; sim->timestep = ts; sim->n = 0;
+      if (sim->Nlevels > 1) {                         // the hierarchy of the block time steps as the device left it
+        sim->n = (int) bs.n; sim->nresync = (int) bs.nresync; sim->level_max = bs.level_max;
+        sim->level_step = bs.level_step; sim->dt_max = bs.dt_max;
+      }
       sim->Nsteps += K; sim->Nfullsteps += K; sim->Nblocksteps += K;
       sim->rebuild_tree = false;
       done = K;

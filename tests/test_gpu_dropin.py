@@ -82,6 +82,40 @@ def test_reference_hands_over_to_the_device_main_loop(name, steps, resident):
     assert scaled_err(dev["loop.dudt"][og], cpu["loop.dudt"][oc]).max() < tol
 
 
+@pytest.mark.parametrize("name,steps,resident", [("adsod", 14, 9), ("box3d_mm97", 10, 5), ("sphere_grav_fastmono", 10, 7)])
+def test_reference_hands_over_with_block_time_steps(name, steps, resident):
+    """the same hand-over with hierarchical block time steps (Nlevels = 4): the device loop starts the hierarchy like
+    PostInitialConditionsSetup, runs `resident` steps, and ResidentFetch brings home every particle in the middle
+    of its own step -- level, nstep, nlast, dt, dt_next, tlast, r0, v0, a0, u0, dudt0 -- plus n, nresync, level_max,
+    level_step, dt_max of the hierarchy; the reference's own MainLoop carries on.  Must equal the all-CPU run:
+    identical integer state, values to 1e-6."""
+    if refio.harness_path("gpu") is None:
+        pytest.skip("oracle/_ref/ref_harness_gpu not built")
+    p, ic = _case(name)
+    p = dict(p, Nlevels=4)
+    cpu, ci = refio.run_mainloop(p, ic, steps, gpu=False)
+    dev, di = refio.run_mainloop(p, ic, steps, gpu=True, resident=resident)
+    assert ci["steps"] == di["steps"] == steps
+    for k in ("n", "nresync", "level_max", "level_step"):
+        assert ci[k] == di[k], (k, ci[k], di[k])
+    assert abs(ci["t"] - di["t"]) <= 1e-12*abs(ci["t"])
+    assert abs(ci["dt_max"] - di["dt_max"]) <= 1e-9*abs(ci["dt_max"])
+    oc, og = np.argsort(cpu["loop.iorig"]), np.argsort(dev["loop.iorig"])
+    assert len(np.unique(cpu["loop.level"])) > 1, "one level only: not a block-step case"
+    for f in ("level", "nstep", "nlast"):
+        assert np.array_equal(dev["loop." + f][og], cpu["loop." + f][oc]), f
+    tol = 1e-6
+    for f in ("r", "v", "a", "r0", "v0", "a0"):
+        a, b = dev["loop." + f][og], cpu["loop." + f][oc]
+        a = a.reshape(len(a), -1); b = b.reshape(len(b), -1)
+        e = np.linalg.norm(a - b, axis=1)/np.maximum(np.linalg.norm(b, axis=1), np.abs(b).max()*1e-6)
+        assert e.max() < tol, (f, e.max())
+    energy = p.get("gas_eos", "energy_eqn") == "energy_eqn"       # (SphLeapfrogKDK touches u0 only then)
+    for f in ("h", "rho", "u", "dt", "tlast") + (("u0",) if energy else ()):
+        assert rel_err(dev["loop." + f][og], cpu["loop." + f][oc]).max() < tol, f
+    assert scaled_err(dev["loop.dudt"][og], cpu["loop.dudt"][oc]).max() < tol
+
+
 def test_reference_mainloop_with_stars_and_gpu_tree():
     """three star particles: the gas feels them (ComputeStarGravForces, star terms of zeta) and they feel
     the gas through GpuSphTree::UpdateAllStarGasForces; the reference's own N-body integrator moves them.

@@ -261,6 +261,12 @@ def test_device_block_timesteps_match_reference(name):
     check_block_state(state, sim, loop, sim1, 1e-6)
     for f in ("r", "v", "a", "h", "rho", "u"):
         assert np.abs(np.asarray(state[f]).reshape(-1) - loop[f].reshape(-1)).max() <= 1e-9*np.abs(loop[f]).max(), f
+    # the start-of-step state of every particle (most of them in the middle of their own step) is the reference's
+    s0 = tree.IntegratorStartState()
+    energy = params.get("gas_eos", "energy_eqn") == "energy_eqn"       # (SphLeapfrogKDK touches u0, dudt0 only then)
+    for f in ("r0", "v0", "a0", "dt_next") + (("u0", "dudt0") if energy else ()):
+        if f in loop:
+            assert np.abs(s0[f].reshape(-1) - loop[f].reshape(-1)).max() <= 1e-9*max(np.abs(loop[f]).max(), 1e-300), f
     tree.close()
 
 
