@@ -8,5 +8,6 @@
 | FP64 roofline (measured peak 34.7 TFLOP/s) | 2.85 TFLOP/s = 8.2 % | @FP@ TFLOP/s = @FPF@ % |
 | HBM roofline of the dominant pass (gravity, 180 B/particle algorithmic) | 50.7 GB/s = 0.77 % | @HB@ GB/s = @HBF@ % of 6552 (by construction: the pass is FP64 / issue bound); ncu DRAM traffic 1.1 kB per particle -- the interaction lists now travel through HBM on purpose, 380 GB/s while the pass runs |
 | 2 GPUs (64 Mi) | value 2.18e+08, e2e 1.5e+08 | value @V2@ /s (@MS2@ ms), e2e @E2@, resident @R2@ |
+| 4 GPUs (64 Mi) | value 3.86e+08, e2e 2.18e+08, resident 3.45e+08 | value @V4@ /s (@MS4@ ms), e2e @E4@, resident @R4@ |
 | 8 GPUs (64 Mi) | value 6.09e+08 (110 ms), e2e 2.68e+08, resident 4.96e+08 | value @V8@ /s (@MS8@ ms), e2e @E8@ (PCIe bound: every rank still ships its chunk in and out), resident @R8@ |
 

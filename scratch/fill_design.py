@@ -3,6 +3,7 @@ import json, re
 def last(f):
     return json.loads(open("profiles/" + f).read().strip().splitlines()[-1])
 d1, d2, d8, ref = last("r2_bench_cloud64m.json"), last("r2_bench_cloud64m_2gpu.json"), last("r2_bench_cloud64m_8gpu.json"), last("r2_bench_reference_arm.json")
+d4 = last("r2_bench_cloud64m_4gpu.json")
 e = lambda v: "%.3g" % v if v < 1e4 else ("%.2fe+08" % (v/1e8))
 b = d1.get("blocks_ms") or d1.get("kernel_ms") or {}
 blk = d1.get("breakdown_ms", {})
@@ -13,6 +14,7 @@ vals = {
  "FP": "%.2f" % d1["roofline_fp64"]["achieved"], "FPF": "%.1f" % (100*d1["roofline_fp64"]["frac"]),
  "HB": "%.1f" % d1["roofline"]["achieved"], "HBF": "%.2f" % (100*d1["roofline"]["frac"]),
  "V2": e(d2["value"]), "MS2": "%.0f" % d2["ms_per_step"], "E2": e(d2["e2e"]["value"]), "R2": e(d2["resident"]["value"]),
+ "V4": e(d4["value"]), "MS4": "%.0f" % d4["ms_per_step"], "E4": e(d4["e2e"]["value"]), "R4": e(d4["resident"]["value"]),
  "V8": e(d8["value"]), "MS8": "%.1f" % d8["ms_per_step"], "E8": e(d8["e2e"]["value"]), "R8": e(d8["resident"]["value"]),
 }
 km = d1.get("kernels_ms") or {}
