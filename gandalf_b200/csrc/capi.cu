@@ -1941,7 +1941,6 @@ int gsph_integrator_begin(gsph_handle* h, const gsph_integrator_config* cfg, int
   if (cfg->Nlevels > 1) {
     if (I.nstar > 0) { h->err = "gsph_integrator_begin: star particles with block time steps (Nlevels > 1) are not on the accelerated path"; return GSPH_EINVAL; }
     if (h->dp.any_mirror) { h->err = "gsph_integrator_begin: block time steps with mirror boundaries are not on the accelerated path"; return GSPH_EINVAL; }
-    if (h->dp.tdavisc == GSPH_TDAVISC_CD2010) { h->err = "gsph_integrator_begin: block time steps with time_dependent_avisc = cd2010 are not on the accelerated path"; return GSPH_EINVAL; }
     if (cfg->Nlevels > 30) { h->err = "gsph_integrator_begin: Nlevels must be <= 30"; return GSPH_EINVAL; }
     if (I.blk_cap < h->Ncap) {
       auto fre = [](void* p) { if (p) cudaFree(p); };

@@ -21,7 +21,7 @@ import refio  # noqa: E402
 from conftest import load_golden, stage  # noqa: E402
 from make_loop_golden import BASE  # noqa: E402
 
-CASES = {"adsod": (20, 4), "box3d_mm97": (20, 4), "sphere_grav_fastmono": (20, 4)}       # name -> (steps, Nlevels)
+CASES = {"adsod": (20, 4), "box3d_mm97": (20, 4), "sphere_grav_fastmono": (20, 4), "adsod+cd2010": (20, 4)}       # name -> (steps, Nlevels)
 FIELDS = ["r", "v", "a", "atree", "m", "h", "u", "rho", "invomega", "zeta", "hfactor", "hrangesqd", "sound", "pressure",
           "alpha", "dalphadt", "dudt", "div_v", "gpot", "ptype", "level", "levelneib", "nstep", "nlast", "dt", "dt_next",
           "tlast", "r0", "v0", "a0", "u0", "dudt0"]
@@ -31,9 +31,11 @@ SIM = ["n", "nresync", "level_max", "level_step", "dt_max", "timestep", "t"]
 def main():
     for name in (sys.argv[1:] or list(CASES)):
         steps, nlev = CASES[name]
-        params, d = load_golden(name)
+        params, d = load_golden(name.split("+")[0])
         p = dict(BASE)
         p.update(params)
+        if name.endswith("+cd2010"):                         # the Cullen & Dehnen switch on the same initial conditions
+            p.update(time_dependent_avisc="cd2010", alpha_visc_min=0.1)
         p.update({k: BASE[k] for k in ("run_id", "ic", "Nstepsmax", "tend", "neib_search")})
         p["Nlevels"] = nlev
         s = stage(d, "dens_in")
@@ -51,7 +53,7 @@ def main():
             for k in SIM:
                 fix["%s.sim_%s" % (st, k)] = np.float64(src[k]) if k in ("dt_max", "timestep", "t") else np.int64(src[k])
         fix["loop.steps"] = np.int64(steps)
-        path = os.path.join(HERE, "loopblk_" + name + ".npz")
+        path = os.path.join(HERE, "loopblk_" + name.replace("+", "_") + ".npz")
         np.savez_compressed(path, **fix)
         print("%-32s N=%-6d steps=%d n=%d nresync=%d level_max=%d  %7.1f kB" % (
             "loopblk_" + name, len(ic["m"]), steps, info["n"], info["nresync"], info["level_max"], os.path.getsize(path)/1e3))

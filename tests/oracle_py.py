@@ -592,7 +592,10 @@ def mainloop_block(params, setup, sim, steps, trace=None):
         if tr is not None:
             tr.update_hmax(s["h"])
         if params.get("time_dependent_avisc") == "cd2010":
-            raise NotImplementedError("cd2010 with block time steps")
+            # the switch at the end of ComputeH, for the active particles; neighbours enter as they stand
+            al, dal = cd2010_switch(p, s["r"], s["v"], s["a"], s["m"], s, s["alpha"])
+            s["alpha"] = np.where(active, al, s["alpha"])
+            s["dalphadt"] = np.where(active, dal, s["dalphadt"])
         s["levelneib"] = np.where(active, 0, s["levelneib"])
         for k in ("div_v", "dudt", "gpot"):
             s[k] = np.where(active, 0.0, s[k])
