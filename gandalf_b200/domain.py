@@ -76,6 +76,12 @@ class DomainDriver(object):
         ptr, cap = self.tree.DeviceField("perm")
         perm = torch.as_tensor(_CudaArray(ptr, N, "<i4"), device="cuda")
         lo, hi = ranges[self.rank]
+        if all(b - a == maxc for a, b in ranges):
+            # equal shards (N divisible by the rank count): gather straight into the tree order, in place
+            dist.all_gather_into_tensor(perm, perm[lo:hi], group=self.group)
+            torch.cuda.current_stream().synchronize()
+            self.tree.BuildTreeShardFinish()
+            return
         send = torch.zeros(maxc, dtype=torch.int32, device=perm.device)
         send[:hi - lo] = perm[lo:hi]
         recv = torch.empty(maxc * self.world, dtype=torch.int32, device=perm.device)
@@ -129,14 +135,21 @@ class DomainDriver(object):
             self.tree.UpdateAllSphProperties()
             return
         import torch.distributed as dist
+        import torch
         self.tree.DensityPass()
         self.tree.Synchronize()
-        for t in self._wrap_fields():          # in-place all-gather: input = this rank's chunk of the output
-            dist.all_gather_into_tensor(t, t[self.rank * self.chunk:(self.rank + 1) * self.chunk], group=self.group)
-        import torch
+        fields = self._wrap_fields()           # h first
+        sl = slice(self.rank * self.chunk, (self.rank + 1) * self.chunk)
+        # in-place all-gathers (input = this rank's chunk of the output).  The smoothing lengths go first: the
+        # hmax / h-box refresh of the tree (KDTree::UpdateAllHmaxValues) only needs them and runs on the library's
+        # stream while rho, invomega, zeta are still crossing NVLink
+        dist.all_gather_into_tensor(fields[0], fields[0][sl], group=self.group)
+        torch.cuda.current_stream().synchronize()
+        self.tree.RefreshHmax()
+        for t in fields[1:]:
+            dist.all_gather_into_tensor(t, t[sl], group=self.group)
         torch.cuda.current_stream().synchronize()
         self.tree.DeriveDensityFields(self.lo, self.hi)
-        self.tree.RefreshHmax()
 
     # ---- host <-> device for a multi-process host: every rank owns the host-order chunk ---------------
     #      [rank*ceil(N/R), ...) of the particle set (what an MPI rank owns in the reference); it ships

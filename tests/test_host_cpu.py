@@ -265,8 +265,8 @@ def test_domain_driver_main_loop_sequence():
             self.tree.calls.append("sharded_rebuild")
 
         def _wrap_fields(self):
-            self.tree.calls.append("exchange_density")
-            return []
+            import numpy as np
+            return [np.zeros(self.chunk*self.world) for _ in range(4)]      # h, rho, invomega, zeta
 
         def _gather_inplace(self, names, staging, n_valid):
             self.tree.calls.append(("gather", tuple(names), staging))
@@ -279,15 +279,19 @@ def test_domain_driver_main_loop_sequence():
     fake = types.ModuleType("torch")                      # UpdateAllSphProperties synchronises torch's stream
     fake.cuda = types.SimpleNamespace(current_stream=lambda: types.SimpleNamespace(synchronize=lambda: None))
     fake.distributed = types.ModuleType("torch.distributed")
+    gathers = []
+    fake.distributed.all_gather_into_tensor = lambda out, inp, group=None: gathers[-1].calls.append("all_gather")
     saved = {k: sys.modules.get(k) for k in ("torch", "torch.distributed")}
     sys.modules["torch"], sys.modules["torch.distributed"] = fake, fake.distributed
     try:
         stub = Stub([0, 1, 2])
+        gathers.append(stub)
         drv = Driver(stub, rank=1, world_size=2)
         drv.MainLoop(3)
         # block time steps: thermal refresh of every particle before the forces, levelneib by a MAX reduction,
         # the passes repeated while CheckTimesteps wakes particles (here: once in the first step)
         bstub = Stub([0, 2], Nlevels=4, woken=[3, 0, 0])
+        gathers.append(bstub)
         Driver(bstub, rank=1, world_size=2).MainLoop(2)
     finally:
         for k, v in saved.items():
@@ -296,16 +300,16 @@ def test_domain_driver_main_loop_sequence():
             else:
                 sys.modules[k] = v
     lo, hi, _ = domain.slice_bounds(1001, 2, 1)
-    step = ["DensityPass", "Synchronize", "exchange_density", ("DeriveDensityFields", lo, hi), "RefreshHmax",
-            "ZeroAccelerations", "UpdateAllSphForces", "Synchronize",
+    dens = ["DensityPass", "Synchronize", "all_gather", "RefreshHmax", "all_gather", "all_gather", "all_gather",
+            ("DeriveDensityFields", lo, hi)]
+    step = dens + ["ZeroAccelerations", "UpdateAllSphForces", "Synchronize",
             ("gather", ("ax", "ay", "az", "atx", "aty", "atz", "gpot", "gpot_hydro", "dudt", "div_v", "dalphadt", "alpha", "levelneib"),
              False), "IntegratorFinish"]
     expect = []
     for build in ("sharded_rebuild", ("BuildTreeMode", 1), ("BuildTreeMode", 2)):
         expect += ["IntegratorAdvance", build, ("SetActiveSlice", lo, hi)] + step
     assert stub.calls == expect, stub.calls
-    bpass = ["DensityPass", "Synchronize", "exchange_density", ("DeriveDensityFields", lo, hi), "RefreshHmax",
-             "ZeroAccelerations", "UpdateThermalProperties", "UpdateAllSphForces", "Synchronize",
+    bpass = dens + ["ZeroAccelerations", "UpdateThermalProperties", "UpdateAllSphForces", "Synchronize",
              ("gather", ("ax", "ay", "az", "atx", "aty", "atz", "gpot", "gpot_hydro", "dudt", "div_v", "dalphadt", "alpha"), False),
              ("reduce_max", "levelneib")]
     bexpect = (["IntegratorAdvance", "sharded_rebuild", ("SetActiveSlice", lo, hi)] + bpass + ["IntegratorCheckTimesteps"] + bpass
