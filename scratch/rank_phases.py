@@ -6,7 +6,7 @@ import gandalf_b200 as g
 from gandalf_b200 import workloads, domain
 NP = int(sys.argv[1]) if len(sys.argv) > 1 else 67108864
 world = int(sys.argv[2]) if len(sys.argv) > 2 else 8
-rank = world - 1
+rank = int(sys.argv[3]) if len(sys.argv) > 3 else world - 1
 params, ic = workloads.WORKLOADS["cloud"](NP, device="cuda:0")
 N = int(ic["m"].shape[0])
 ps = g.ParticleSet(N, 3, "soa", fields={"r", "v", "m", "h", "u"})
