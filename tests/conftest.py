@@ -18,7 +18,7 @@ def pytest_configure(config):
 
 GOLDEN_DIR = os.path.join(HERE, "golden")
 _ALL_NPZ = sorted(os.path.basename(f)[:-4] for f in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-GOLDEN_CASES = [c for c in _ALL_NPZ if not c.startswith(("loop_", "loopblk_", "snap_", "stargas_"))]   # operator-level fixtures (make_golden.py)
+GOLDEN_CASES = [c for c in _ALL_NPZ if not c.startswith(("loop_", "loopblk_", "snap_", "stargas_", "brute_"))]   # operator-level fixtures (make_golden.py)
 SNAP_CASES = [c[5:] for c in _ALL_NPZ if c.startswith("snap_")]        # "su" snapshot files (make_snapshot_golden.py)
 LOOP_CASES = [c for c in _ALL_NPZ if c.startswith("loop_")]            # main-loop fixtures (make_loop_golden.py)
 LOOPBLK_CASES = [c for c in _ALL_NPZ if c.startswith("loopblk_")]      # main loop with block time steps (make_loopblk_golden.py)

@@ -249,6 +249,16 @@ def case_sphere_grav_mono():
     return p, d
 
 
+def case_sphere_grav_bruteforce():
+    """the reference's SECOND, tree-independent path (neib_search = bruteforce, GradhSphBruteForce): every pair is
+    either a kernel neighbour (softened terms) or an exact direct sum -- no tree, no opening criterion"""
+    ic = sphere_ic(2026, 2000)
+    p = base_params(3, self_gravity=1, multipole="monopole", gravity_mac="geometric", thetamaxsqd=0.2,
+                    gas_eos="isothermal", temp0=2.0, mu_bar=1.0, neib_search="bruteforce")
+    d, _ = refio.run_harness(p, ic=ic, perturb_h=0.05, dumps="setup,density,forces")
+    return p, d
+
+
 STARS = np.array([[0.05, -0.02, 0.03, 0.4, 0.08],      # {r, m, h}: one star inside the cloud (its mean-h kernel
                   [1.3, 0.4, -0.2, 0.7, 0.05],         # overlaps many particles), one outside, one at the edge
                   [-0.55, 0.5, 0.45, 0.2, 0.3]])
@@ -328,6 +338,7 @@ CASES = {
     "sphere_grav_quad": case_sphere_grav_quad,
     "sphere_grav_fastmono": case_sphere_grav_fastmono,
     "sphere_grav_mono": case_sphere_grav_mono,
+    "brute_sphere_grav": case_sphere_grav_bruteforce,
     "sphere_grav_gadget2": case_sphere_grav_gadget2,
     "sphere_grav_stars": case_sphere_grav_stars,
     "stargas_hermite4": case_stargas_hermite4,

@@ -155,6 +155,36 @@ def test_gravity_forces_match_reference(name):
     tree.close()
 
 
+def test_bruteforce_reference_equals_the_all_opened_device_tree():
+    """second, tree-independent oracle: the reference run with neib_search = bruteforce (every pair a
+    kernel neighbour or an exact direct sum) against the device path with an opening criterion that opens every
+    cell -- the softened pair terms of hydro_kernel plus gravity_direct_kernel alone must give its forces; and
+    the density pass must give its h, rho (no tree involved in either)"""
+    params, d = load_golden("brute_sphere_grav")
+    assert params["neib_search"] == "bruteforce"
+    q = dict(params, thetamaxsqd=1e-30)
+    q.pop("neib_search")
+    di, do = _by_iorig(stage(d, "dens_in")), _by_iorig(stage(d, "dens_out"))
+    ps, tree = _make(q, di)
+    tree.BuildTree(True, 0, 1, 1, 0.0, ps)
+    tree.UpdateAllSphProperties()
+    tree.Download(ps)
+    assert rel_err(ps["h"], do["h"]).max() < TOL and rel_err(ps["rho"], do["rho"]).max() < TOL
+    tree.close()
+    si, so = _by_iorig(stage(d, "force_in")), _by_iorig(stage(d, "force_out"))
+    ps, tree = _make(q, si)
+    tree.BuildTree(True, 0, 1, 1, 0.0, ps)
+    tree.ZeroAccelerations()
+    tree.UpdateAllSphForces()
+    tree.Download(ps)
+    assert tree.Stats().ncell_mean == 0                    # no cell was accepted anywhere
+    assert vec_rel_err(ps["a"], so["a"]).max() < TOL
+    assert vec_rel_err(ps["atree"], so["atree"]).max() < TOL
+    assert rel_err(ps["gpot"], so["gpot"]).max() < TOL
+    assert scaled_err(ps["dudt"], so["dudt"]).max() < TOL
+    tree.close()
+
+
 # ---------------------------------------------------------------------------------------------------
 # seeded inputs vs the oracle
 # ---------------------------------------------------------------------------------------------------

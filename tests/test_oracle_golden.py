@@ -158,3 +158,26 @@ def test_star_gas_forces_match_reference():
     assert vec_rel_err(a, d["stargas.a"]).max() < TOL
     assert rel_err(gpot, d["stargas.gpot"]).max() < TOL
     assert vec_rel_err(adot, d["stargas.adot"]).max() < 1e-6           # (single-precision powf in the reference)
+
+
+def test_bruteforce_reference_is_the_all_opened_tree():
+    """the reference's SECOND, tree-independent path (neib_search = bruteforce -> GradhSphBruteForce: every pair is a
+    kernel neighbour or an exact direct sum; golden brute_sphere_grav from make_golden.py) pins (a) the oracle's exact
+    direct summation and (b) the tree path with an opening criterion that opens every cell (thetamaxsqd -> 0): the
+    direct-sum and softened pair terms are the ones the tree path uses, without any cell in between"""
+    params, d = load_golden("brute_sphere_grav")
+    assert params["neib_search"] == "bruteforce"
+    p = orc.params_from_dict(params)
+    si = _state_by_iorig(stage(d, "force_in"))
+    so = _state_by_iorig(stage(d, "force_out"))
+    out = orc.hydro_grav_forces_direct(p, si)
+    assert vec_rel_err(out["a"], so["a"]).max() < TOL
+    assert rel_err(out["gpot"], so["gpot"]).max() < TOL
+    assert scaled_err(out["dudt"], so["dudt"]).max() < TOL
+    p2 = orc.params_from_dict(dict(params, thetamaxsqd=1e-30))
+    t = orc.Tree(p2, si["r"], si["v"], si["m"], si["h"])
+    out2 = t.hydro_grav_forces(si)
+    assert out2["ncell"].max() == 0 if "ncell" in out2 else True
+    assert vec_rel_err(out2["a"], so["a"]).max() < TOL
+    assert vec_rel_err(out2["atree"], so["atree"]).max() < TOL
+    assert rel_err(out2["gpot"], so["gpot"]).max() < TOL
