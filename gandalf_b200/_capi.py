@@ -101,7 +101,8 @@ EXPORTS = [
     "gsph_update_all_forces_begin", "gsph_update_all_forces_finish", "gsph_integrator_advance",
     "gsph_integrator_finish", "gsph_integrator_check_timesteps", "gsph_update_thermal_properties",
     "gsph_update_star_gas_forces", "gsph_derive_density_fields",
-    "gsph_integrator_set_stars", "gsph_integrator_get_stars",
+    "gsph_integrator_set_stars", "gsph_integrator_get_stars", "gsph_integrator_set_stars_hermite4",
+    "gsph_integrator_get_star_derivatives",
 ]
 
 _lib = None
@@ -149,6 +150,8 @@ def lib():
     L.gsph_update_thermal_properties.argtypes = [H]
     L.gsph_integrator_set_stars.argtypes = [H, C.c_void_p, C.c_int, C.c_double]
     L.gsph_integrator_get_stars.argtypes = [H, C.c_void_p, C.c_int]
+    L.gsph_integrator_set_stars_hermite4.argtypes = [H, C.c_void_p, C.c_int, C.c_double]
+    L.gsph_integrator_get_star_derivatives.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p]
     L.gsph_update_star_gas_forces.argtypes = [H, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.gsph_integrator_state.argtypes = [H, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     L.gsph_integrator_block_state.argtypes = [H, C.POINTER(BlockState), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

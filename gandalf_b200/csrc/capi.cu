@@ -1733,29 +1733,92 @@ static int integ_star_forces(gsph_handle* h)
   IntegState& I = h->integ;
   const int nd = h->cfg.ndim, ns = I.nstar;
   std::fill(I.sa.begin(), I.sa.end(), 0.0); std::fill(I.sgpot.begin(), I.sgpot.end(), 0.0);
+  if (I.hermite4) std::fill(I.sadot.begin(), I.sadot.end(), 0.0);
   if (h->cfg.self_gravity) {
     std::vector<double> rows((size_t) ns*(2*nd + 1));
     for (int s = 0; s < ns; s++) {
       for (int k = 0; k < nd; k++) { rows[(size_t) s*(2*nd + 1) + k] = I.sr[(size_t) s*nd + k]; rows[(size_t) s*(2*nd + 1) + nd + k] = I.sv[(size_t) s*nd + k]; }
       rows[(size_t) s*(2*nd + 1) + 2*nd] = I.sh[s];
     }
-    const int rc = gsph_update_star_gas_forces(h, rows.data(), ns, I.sa.data(), NULL, I.sgpot.data(), NULL);
+    const int rc = gsph_update_star_gas_forces(h, rows.data(), ns, I.sa.data(), I.hermite4 ? I.sadot.data() : NULL, I.sgpot.data(), NULL);
     if (rc) return rc;
   }
+  const double twopi = 6.283185307179586;
   for (int i = 0; i < ns; i++)
     for (int j = 0; j < ns; j++) {
       if (i == j) continue;
-      double dr[3] = {0, 0, 0}, drsqd = 0.0;
-      for (int k = 0; k < nd; k++) { dr[k] = I.sr[(size_t) j*nd + k] - I.sr[(size_t) i*nd + k]; }
-      for (int k = 0; k < nd; k++) drsqd = k == 0 ? dr[0]*dr[0] : drsqd + dr[k]*dr[k];
-      const double drmag = sqrt(drsqd) + 1.0e-20, invdrmag = 1.0/drmag;
+      double dr[3] = {0, 0, 0}, dv[3] = {0, 0, 0}, drsqd = 0.0, dvdr = 0.0;
+      for (int k = 0; k < nd; k++) { dr[k] = I.sr[(size_t) j*nd + k] - I.sr[(size_t) i*nd + k]; dv[k] = I.sv[(size_t) j*nd + k] - I.sv[(size_t) i*nd + k]; }
+      for (int k = 0; k < nd; k++) { drsqd = k == 0 ? dr[0]*dr[0] : drsqd + dr[k]*dr[k]; dvdr = k == 0 ? dv[0]*dr[0] : dvdr + dv[k]*dr[k]; }
       const double invhmean = 2.0/(I.sh[i] + I.sh[j]);
-      const double paux = I.sm[j]*invhmean*invhmean*
-                          gsph_kernel_grav_host(nd, h->cfg.kernel, h->cfg.tabulated_kernel, 4, drmag*invhmean)*invdrmag;
-      I.sgpot[i] += I.sm[j]*invhmean*gsph_kernel_grav_host(nd, h->cfg.kernel, h->cfg.tabulated_kernel, 5, drmag*invhmean);
-      for (int k = 0; k < nd; k++) I.sa[(size_t) i*nd + k] += paux*dr[k];
+      if (!I.hermite4) {                                   /* NbodyLeapfrogKDK::CalculateDirectSmoothedGravForces */
+        const double drmag = sqrt(drsqd) + 1.0e-20, invdrmag = 1.0/drmag;
+        const double paux = I.sm[j]*invhmean*invhmean*
+                            gsph_kernel_grav_host(nd, h->cfg.kernel, h->cfg.tabulated_kernel, 4, drmag*invhmean)*invdrmag;
+        I.sgpot[i] += I.sm[j]*invhmean*gsph_kernel_grav_host(nd, h->cfg.kernel, h->cfg.tabulated_kernel, 5, drmag*invhmean);
+        for (int k = 0; k < nd; k++) I.sa[(size_t) i*nd + k] += paux*dr[k];
+      }
+      else {                                               /* NbodyHermite4::CalculateDirectSmoothedGravForces (NbodyHermite4.cpp:77-140) */
+        const double drmag = sqrt(drsqd), invdrmag = 1.0/sqrt(drsqd);
+        const double drdt = dvdr*invdrmag;
+        const double paux = I.sm[j]*invhmean*invhmean*
+                            gsph_kernel_grav_host(nd, h->cfg.kernel, h->cfg.tabulated_kernel, 4, drmag*invhmean)*invdrmag;
+        const double wmean = gsph_kernel_grav_host(nd, h->cfg.kernel, h->cfg.tabulated_kernel, 0, drmag*invhmean)*
+                             (double) powf((float) invhmean, (float) nd);            /* (single precision in the reference too) */
+        I.sgpot[i] += I.sm[j]*invhmean*gsph_kernel_grav_host(nd, h->cfg.kernel, h->cfg.tabulated_kernel, 5, drmag*invhmean);
+        for (int k = 0; k < nd; k++) {
+          I.sa[(size_t) i*nd + k] += paux*dr[k];
+          I.sadot[(size_t) i*nd + k] += paux*dv[k] - 3.0*paux*drdt*invdrmag*dr[k] + 2.0*twopi*I.sm[j]*drdt*wmean*invdrmag*dr[k];
+        }
+      }
     }
   return GSPH_OK;
+}
+
+/* NbodyHermite4::CalculateAllStartupQuantities (NbodyHermite4.cpp:257-330): a2dot, a3dot of the stars from the
+   (unsoftened) star-star terms, once, after the first force computation */
+static void integ_star_startup_hermite(gsph_handle* h)
+{
+  IntegState& I = h->integ;
+  const int nd = h->cfg.ndim, ns = I.nstar;
+  std::fill(I.sa2dot.begin(), I.sa2dot.end(), 0.0); std::fill(I.sa3dot.begin(), I.sa3dot.end(), 0.0);
+  auto dot = [&](const double* a, const double* b) { double s = 0.0; for (int k = 0; k < nd; k++) s = k == 0 ? a[0]*b[0] : s + a[k]*b[k]; return s; };
+  for (int i = 0; i < ns; i++)
+    for (int j = 0; j < ns; j++) {
+      if (i == j) continue;
+      double dr[3], dv[3], da[3], dadot[3], a[3], adot[3], a2dot[3];
+      for (int k = 0; k < nd; k++) {
+        dr[k] = I.sr[(size_t) j*nd + k] - I.sr[(size_t) i*nd + k]; dv[k] = I.sv[(size_t) j*nd + k] - I.sv[(size_t) i*nd + k];
+        da[k] = I.sa[(size_t) j*nd + k] - I.sa[(size_t) i*nd + k]; dadot[k] = I.sadot[(size_t) j*nd + k] - I.sadot[(size_t) i*nd + k];
+      }
+      const double drsqd = dot(dr, dr) + 1.0e-50, dvsqd = dot(dv, dv);
+      const double invdrsqd = 1.0/drsqd, invdrmag = sqrt(invdrsqd);
+      const double drdt = dot(dv, dr)*invdrmag;
+      const double i3 = pow(invdrmag, 3);
+      for (int k = 0; k < nd; k++) { a[k] = I.sm[j]*dr[k]*i3; adot[k] = I.sm[j]*i3*(dv[k] - 3.0*drdt*invdrmag*dr[k]); }
+      const double afac = dot(dv, dr)*invdrsqd;
+      const double bfac = dvsqd*invdrsqd + afac*afac + dot(da, dr)*invdrsqd;
+      const double cfac = 3.0*dot(dv, da)*invdrsqd + dot(dr, dadot)*invdrsqd + afac*(3.0*bfac - 4.0*afac*afac);
+      for (int k = 0; k < nd; k++) {
+        a2dot[k] = I.sm[j]*da[k]*invdrsqd*invdrmag - 6.0*afac*adot[k] - 3.0*bfac*a[k];
+        I.sa2dot[(size_t) i*nd + k] += a2dot[k];
+        I.sa3dot[(size_t) i*nd + k] += I.sm[j]*dadot[k]*invdrsqd*invdrmag - 9.0*afac*a2dot[k] - 9.0*bfac*adot[k] - 3.0*cfac*a[k];
+      }
+    }
+}
+
+/* NbodyHermite4::CorrectionTerms (NbodyHermite4.cpp:388-440): Hermite interpolation of a2dot, a3dot over the step,
+   positions to 5th and velocities to 4th order; dt^3 in single precision like the reference's powf */
+static void integ_star_correct_hermite(gsph_handle* h, double dt)
+{
+  IntegState& I = h->integ;
+  const double dt3 = (double) powf((float) dt, 3.0f), invdt = 1.0/dt;
+  for (size_t q = 0; q < I.sa.size(); q++) {
+    I.sa2dot[q] = (-6.0*(I.sa0[q] - I.sa[q]) - dt*(4.0*I.sadot0[q] + 2.0*I.sadot[q]))*invdt*invdt;
+    I.sa3dot[q] = (12.0*(I.sa0[q] - I.sa[q]) + 6.0*dt*(I.sadot0[q] + I.sadot[q]))*invdt*invdt*invdt;
+    I.sr[q] += I.sa2dot[q]*dt3*dt/24.0 + I.sa3dot[q]*dt3*dt*dt/120.0;
+    I.sv[q] += I.sa2dot[q]*dt3/6.0 + I.sa3dot[q]*dt3*dt/24.0;
+  }
 }
 
 /* NbodyLeapfrogKDK::Timestep over the stars */
@@ -1765,9 +1828,17 @@ static double integ_star_timestep(const gsph_handle* h)
   const int nd = h->cfg.ndim;
   double ts = 9.9e50;
   for (int s = 0; s < I.nstar; s++) {
-    double a2 = 0.0;
-    for (int k = 0; k < nd; k++) { const double a = I.sa[(size_t) s*nd + k]; a2 = k == 0 ? a*a : a2 + a*a; }
-    ts = std::min(ts, I.nbody_mult*sqrt(I.sh[s]/(sqrt(a2) + 1.0e-50)));
+    auto sq = [&](const std::vector<double>& v) { double x = 0.0; for (int k = 0; k < nd; k++) { const double a = v[(size_t) s*nd + k]; x = k == 0 ? a*a : x + a*a; } return x; };
+    const double asqd = sq(I.sa);
+    if (!I.hermite4) { ts = std::min(ts, I.nbody_mult*sqrt(I.sh[s]/(sqrt(asqd) + 1.0e-50))); continue; }
+    /* NbodyHermite4::Timestep (NbodyHermite4.cpp:542-578): the Aarseth criterion */
+    const double small = 1.0e-50, a1sqd = sq(I.sadot), a2sqd = sq(I.sa2dot), a3sqd = sq(I.sa3dot);
+    double t1;
+    if (a1sqd > small && a2sqd > small) t1 = I.nbody_mult*sqrt((sqrt(asqd*a2sqd) + a1sqd)/(sqrt(a1sqd*a3sqd) + a2sqd));
+    else if (asqd > small && a2sqd > small) t1 = I.nbody_mult*sqrt(asqd/(a2sqd + small));
+    else if (asqd > small) t1 = sqrt(I.sh[s]/(sqrt(asqd) + small));
+    else t1 = 9.9e50;
+    ts = std::min(ts, t1);
   }
   return ts;
 }
@@ -1877,6 +1948,7 @@ int gsph_integrator_set_stars(gsph_handle* h, const double* rows, int Nstar, dou
   IntegState& I = h->integ;
   const int nd = h->cfg.ndim, row = 3*nd + 2;
   I.on = false;
+  I.hermite4 = false;
   I.nstar = Nstar; I.nbody_mult = nbody_mult;
   I.sr.assign((size_t) Nstar*nd, 0.0); I.sv = I.sr; I.sa = I.sr;
   I.sm.assign(Nstar, 0.0); I.sh = I.sm; I.sgpot = I.sm;
@@ -1906,6 +1978,46 @@ int gsph_integrator_get_stars(gsph_handle* h, double* rows, int Nstar)
     }
     rows[(size_t) s*row + 3*nd] = I.sm[s]; rows[(size_t) s*row + 3*nd + 1] = I.sh[s]; rows[(size_t) s*row + 3*nd + 2] = I.sgpot[s];
   }
+  return GSPH_OK;
+}
+
+/* the same for nbody = hermite4 (the reference's default N-body integrator, NbodyHermite4.cpp): rows = Nstar x
+   {r[ndim], v[ndim], a[ndim], adot[ndim], a2dot[ndim], a3dot[ndim], m, h}; the derivatives are only read by
+   gsph_integrator_begin(compute_forces = 0) -- otherwise begin computes them like PostInitialConditionsSetup */
+int gsph_integrator_set_stars_hermite4(gsph_handle* h, const double* rows, int Nstar, double nbody_mult)
+{
+  if (!h) return GSPH_EINVAL;
+  if (Nstar <= 0 || !rows || !(nbody_mult > 0)) { h->err = "gsph_integrator_set_stars_hermite4: bad arguments"; return GSPH_EINVAL; }
+  IntegState& I = h->integ;
+  const int nd = h->cfg.ndim, row = 6*nd + 2;
+  std::vector<double> lf((size_t) Nstar*(3*nd + 2));
+  for (int s = 0; s < Nstar; s++) {
+    for (int k = 0; k < 3*nd; k++) lf[(size_t) s*(3*nd + 2) + k] = rows[(size_t) s*row + k];
+    lf[(size_t) s*(3*nd + 2) + 3*nd] = rows[(size_t) s*row + 6*nd]; lf[(size_t) s*(3*nd + 2) + 3*nd + 1] = rows[(size_t) s*row + 6*nd + 1];
+  }
+  const int rc = gsph_integrator_set_stars(h, lf.data(), Nstar, nbody_mult);
+  if (rc) return rc;
+  I.hermite4 = true;
+  I.sadot.assign((size_t) Nstar*nd, 0.0); I.sa2dot = I.sadot; I.sa3dot = I.sadot;
+  for (int s = 0; s < Nstar; s++)
+    for (int k = 0; k < nd; k++) {
+      I.sadot[(size_t) s*nd + k] = rows[(size_t) s*row + 3*nd + k];
+      I.sa2dot[(size_t) s*nd + k] = rows[(size_t) s*row + 4*nd + k];
+      I.sa3dot[(size_t) s*nd + k] = rows[(size_t) s*row + 5*nd + k];
+    }
+  I.sadot0 = I.sadot;
+  return GSPH_OK;
+}
+
+/* adot, a2dot, a3dot of the stars after the last step (Nstar x ndim each, NULL = not wanted); nbody = hermite4 only */
+int gsph_integrator_get_star_derivatives(gsph_handle* h, double* adot, double* a2dot, double* a3dot)
+{
+  if (!h) return GSPH_EINVAL;
+  const IntegState& I = h->integ;
+  if (!I.hermite4 || I.nstar == 0) { h->err = "gsph_integrator_get_star_derivatives: no Hermite-4 stars"; return GSPH_ESTATE; }
+  if (adot) memcpy(adot, I.sadot.data(), I.sadot.size()*sizeof(double));
+  if (a2dot) memcpy(a2dot, I.sa2dot.data(), I.sa2dot.size()*sizeof(double));
+  if (a3dot) memcpy(a3dot, I.sa3dot.data(), I.sa3dot.size()*sizeof(double));
   return GSPH_OK;
 }
 
@@ -1968,8 +2080,12 @@ int gsph_integrator_begin(gsph_handle* h, const gsph_integrator_config* cfg, int
   }
   if (compute_forces) { const int rc = integ_scatter_results(h); if (rc) return rc; }
   if (I.nstar > 0) {
-    if (compute_forces) { const int rs = integ_star_forces(h); if (rs) return rs; }
+    if (compute_forces) {
+      const int rs = integ_star_forces(h); if (rs) return rs;
+      if (I.hermite4) integ_star_startup_hermite(h);       /* PostInitialConditionsSetup, SphSimulation.cpp:513-516 */
+    }
     I.sr0 = I.sr; I.sv0 = I.sv; I.sa0 = I.sa;
+    if (I.hermite4) I.sadot0 = I.sadot;
   }
   INTEG_LAUNCH(integ_init_kernel, (int) h->N, devptrs(h->H, h->HI), integ_ptrs(h));
   int rc;
@@ -2018,6 +2134,10 @@ int gsph_integrator_advance(gsph_handle* h, int* tree_mode, double* timestep)
     for (size_t q = 0; q < I.sr.size(); q++) {
       I.sr[q] = I.sr0[q] + I.sv0[q]*dt + 0.5*I.sa0[q]*dt*dt;
       I.sv[q] = I.sv0[q] + I.sa0[q]*dt;
+      if (I.hermite4) {                                /* NbodyHermite4::AdvanceParticles (NbodyHermite4.cpp:340-378) */
+        I.sr[q] = I.sr0[q] + I.sv0[q]*dt + 0.5*I.sa0[q]*dt*dt + 0.16666666666666666666666*I.sadot0[q]*dt*dt*dt;
+        I.sv[q] = I.sv0[q] + I.sa0[q]*dt + 0.5*I.sadot0[q]*dt*dt;
+      }
     }
     const int rs = integ_push_stars(h); if (rs) return rs;
   }
@@ -2058,8 +2178,9 @@ int gsph_integrator_finish(gsph_handle* h)
   }
   if (I.nstar > 0) {
     rc = integ_star_forces(h); if (rc) return rc;
-    const double dts = I.t - I.tlast;                  /* NbodyLeapfrogKDK::CorrectionTerms */
-    for (size_t q = 0; q < I.sv.size(); q++) I.sv[q] += 0.5*(I.sa[q] - I.sa0[q])*dts;
+    const double dts = I.t - I.tlast;
+    if (I.hermite4) integ_star_correct_hermite(h, dts);
+    else for (size_t q = 0; q < I.sv.size(); q++) I.sv[q] += 0.5*(I.sa[q] - I.sa0[q])*dts;     /* NbodyLeapfrogKDK::CorrectionTerms */
   }
   if (integ_block(h)) {
     rc = blk_compute_timesteps(h); if (rc) return rc;   /* new levels; I.n, I.timestep of the next step */
@@ -2075,7 +2196,8 @@ int gsph_integrator_finish(gsph_handle* h)
   rc = integ_global_timestep(h, &next); if (rc) return rc;
   if (I.nstar > 0) {
     next = std::min(next, integ_star_timestep(h));
-    I.sr0 = I.sr; I.sv0 = I.sv; I.sa0 = I.sa;          /* NbodyLeapfrogKDK::EndTimestep */
+    I.sr0 = I.sr; I.sv0 = I.sv; I.sa0 = I.sa;          /* Nbody{LeapfrogKDK,Hermite4}::EndTimestep */
+    if (I.hermite4) I.sadot0 = I.sadot;
   }
   I.rebuild = false;
   INTEG_LAUNCH(integ_end_kernel, (int) h->N, devptrs(h->H, h->HI), integ_ptrs(h), I.timestep, I.cfg.energy_integration, 0, 0, 0.0,

@@ -139,6 +139,8 @@ struct IntegState {
   int nstar = 0;
   double nbody_mult = 0.1;
   std::vector<double> sr, sv, sa, sr0, sv0, sa0, sm, sh, sgpot;
+  bool hermite4 = false;     /* the stars move with NbodyHermite4 (the reference's default) instead of the leapfrog */
+  std::vector<double> sadot, sadot0, sa2dot, sa3dot;
 };
 
 struct gsph_handle {

@@ -148,7 +148,7 @@ double gsph_kernel_grav_host(int ndim, int kernel, int tabulated, int which, dou
   const double kn = gsph_kernnorm(ndim, kernel);
   double (*f)(int, double, double, int) = kernel == GSPH_KERNEL_M4 ? m4 : (kernel == GSPH_KERNEL_GAUSSIAN ? gaussian : quintic);
   if (!tabulated) return f(which, s, kn, ndim);
-  if (s >= kr) return which == 4 ? 1.0/(s*s) : 1.0/s;
+  if (s >= kr) return which == 4 ? 1.0/(s*s) : (which == 5 ? 1.0/s : 0.0);
   const int idx = (int)(s*((double) RES/kr));
   return f(which, (kr/RES)*idx, kn, ndim);
 }

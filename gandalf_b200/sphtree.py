@@ -211,31 +211,43 @@ class GpuSphTree(object):
         ic = integrator_config_from_params(self.params)
         self._check(self._L.gsph_integrator_begin(self._h, C.byref(ic), int(compute_forces), float(t)))
 
-    def IntegratorSetStars(self, r=None, v=None, m=None, h=None, a=None):
-        """star particles of the device-resident loop (nbody = lfkdk: the reference's N-body leapfrog runs on
-        the host around the device passes); call before IntegratorBegin; r=None removes them"""
+    def IntegratorSetStars(self, r=None, v=None, m=None, h=None, a=None, adot=None, a2dot=None, a3dot=None):
+        """star particles of the device-resident loop: the reference's N-body integrator -- nbody = hermite4 (its
+        default, NbodyHermite4.cpp) or lfkdk -- runs on the host around the device passes; call before
+        IntegratorBegin; r=None removes them.  a (and adot, a2dot, a3dot for hermite4) are only read by
+        IntegratorBegin(compute_forces=False)"""
         if r is None or len(m) == 0:
             self._check(self._L.gsph_integrator_set_stars(self._h, None, 0, 0.1))
             self._nstar = 0
             return
-        if self.params["nbody"] != "lfkdk":
-            raise ValueError("nbody = %s is not on the accelerated path (lfkdk only)" % self.params["nbody"])
+        kind = self.params["nbody"]
+        if kind not in ("lfkdk", "hermite4"):
+            raise ValueError("nbody = %s is not on the accelerated path (lfkdk and hermite4 only)" % kind)
         nd, ns = self.cfg.ndim, len(m)
         z = np.zeros((ns, nd))
-        rows = np.ascontiguousarray(np.concatenate([
-            np.asarray(r, dtype=np.float64).reshape(ns, nd), z if v is None else np.asarray(v, dtype=np.float64).reshape(ns, nd),
-            z if a is None else np.asarray(a, dtype=np.float64).reshape(ns, nd),
-            np.asarray(m, dtype=np.float64)[:, None], np.asarray(h, dtype=np.float64)[:, None]], axis=1))
-        self._check(self._L.gsph_integrator_set_stars(self._h, rows.ctypes.data, ns, float(self.params["nbody_mult"])))
+        vec = lambda x: z if x is None else np.asarray(x, dtype=np.float64).reshape(ns, nd)
+        cols = [np.asarray(r, dtype=np.float64).reshape(ns, nd), vec(v), vec(a)]
+        if kind == "hermite4":
+            cols += [vec(adot), vec(a2dot), vec(a3dot)]
+        rows = np.ascontiguousarray(np.concatenate(cols + [np.asarray(m, dtype=np.float64)[:, None],
+                                                           np.asarray(h, dtype=np.float64)[:, None]], axis=1))
+        fn = self._L.gsph_integrator_set_stars_hermite4 if kind == "hermite4" else self._L.gsph_integrator_set_stars
+        self._check(fn(self._h, rows.ctypes.data, ns, float(self.params["nbody_mult"])))
         self._nstar = ns
 
     def IntegratorGetStars(self):
-        """-> dict r, v, a, m, h, gpot of the stars after the last step"""
+        """-> dict r, v, a, m, h, gpot of the stars after the last step (+ adot, a2dot, a3dot with nbody = hermite4)"""
         nd, ns = self.cfg.ndim, getattr(self, "_nstar", 0)
         rows = np.zeros((ns, 3*nd + 3))
         self._check(self._L.gsph_integrator_get_stars(self._h, rows.ctypes.data, ns))
-        return {"r": rows[:, :nd].copy(), "v": rows[:, nd:2*nd].copy(), "a": rows[:, 2*nd:3*nd].copy(),
-                "m": rows[:, 3*nd].copy(), "h": rows[:, 3*nd + 1].copy(), "gpot": rows[:, 3*nd + 2].copy()}
+        out = {"r": rows[:, :nd].copy(), "v": rows[:, nd:2*nd].copy(), "a": rows[:, 2*nd:3*nd].copy(),
+               "m": rows[:, 3*nd].copy(), "h": rows[:, 3*nd + 1].copy(), "gpot": rows[:, 3*nd + 2].copy()}
+        if ns > 0 and self.params["nbody"] == "hermite4":
+            for k in ("adot", "a2dot", "a3dot"):
+                out[k] = np.zeros((ns, nd))
+            self._check(self._L.gsph_integrator_get_star_derivatives(self._h, out["adot"].ctypes.data,
+                                                                     out["a2dot"].ctypes.data, out["a3dot"].ctypes.data))
+        return out
 
     def IntegratorAdvance(self):
         """first half of a MainLoop -> (tree mode 0 rebuild / 1 restock / 2 extrapolate, time step)"""

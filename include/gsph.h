@@ -390,6 +390,14 @@ int gsph_integrator_step(gsph_handle* h, int nsteps);
  *   get_stars : rows = Nstar x {r[ndim], v[ndim], a[ndim], m, h, gpot} after the last step          */
 int gsph_integrator_set_stars(gsph_handle* h, const double* rows, int Nstar, double nbody_mult);
 int gsph_integrator_get_stars(gsph_handle* h, double* rows, int Nstar);
+/* nbody = hermite4, the reference's DEFAULT N-body integrator (NbodyHermite4.cpp: AdvanceParticles third-order
+ * predictor, CalculateDirectSmoothedGravForces with the jerk, CalculateAllStartupQuantities, CorrectionTerms Hermite
+ * corrector, the Aarseth Timestep, EndTimestep), again on the host around gsph_update_star_gas_forces (which returns
+ * the jerk of the gas on the stars).  rows = Nstar x {r, v, a, adot, a2dot, a3dot (ndim each), m, h}; a .. a3dot are
+ * read only by gsph_integrator_begin(compute_forces = 0).  get_stars returns r, v, a, m, h, gpot as above,
+ * get_star_derivatives adot, a2dot, a3dot (Nstar x ndim each, NULL = not wanted).                               */
+int gsph_integrator_set_stars_hermite4(gsph_handle* h, const double* rows, int Nstar, double nbody_mult);
+int gsph_integrator_get_star_derivatives(gsph_handle* h, double* adot, double* a2dot, double* a3dot);
 int gsph_integrator_advance(gsph_handle* h, int* tree_mode, double* timestep);
 int gsph_integrator_finish(gsph_handle* h);
 /* Block time steps (Nlevels > 1) in a host-driven loop (several devices): between the passes and

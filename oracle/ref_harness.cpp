@@ -178,17 +178,22 @@ struct Harness
     // star particles (the N-body side of the main loop)
     const int Ns = sim->nbody->Nstar;
     if (Ns > 0) {
-      vector<double> sr(Ns*ndim), sv(Ns*ndim), sa(Ns*ndim), sm(Ns), sh(Ns), sg(Ns);
+      vector<double> sr(Ns*ndim), sv(Ns*ndim), sa(Ns*ndim), sm(Ns), sh(Ns), sg(Ns), sad(Ns*ndim), sa2(Ns*ndim), sa3(Ns*ndim);
       for (int i = 0; i < Ns; i++) {
         for (int k = 0; k < ndim; k++) {
           sr[i*ndim+k] = sim->nbody->stardata[i].r[k]; sv[i*ndim+k] = sim->nbody->stardata[i].v[k];
           sa[i*ndim+k] = sim->nbody->stardata[i].a[k];
+          sad[i*ndim+k] = sim->nbody->stardata[i].adot[k]; sa2[i*ndim+k] = sim->nbody->stardata[i].a2dot[k];
+          sa3[i*ndim+k] = sim->nbody->stardata[i].a3dot[k];
         }
         sm[i] = sim->nbody->stardata[i].m; sh[i] = sim->nbody->stardata[i].h; sg[i] = sim->nbody->stardata[i].gpot;
       }
       dump_f64(stage + ".star_r", sr, Ns, ndim); dump_f64(stage + ".star_v", sv, Ns, ndim);
       dump_f64(stage + ".star_a", sa, Ns, ndim); dump_f64(stage + ".star_m", sm, Ns);
       dump_f64(stage + ".star_h", sh, Ns); dump_f64(stage + ".star_gpot", sg, Ns);
+      // Hermite-4 derivatives (NbodyParticle: adot, a2dot, a3dot)
+      dump_f64(stage + ".star_adot", sad, Ns, ndim); dump_f64(stage + ".star_a2dot", sa2, Ns, ndim);
+      dump_f64(stage + ".star_a3dot", sa3, Ns, ndim);
     }
   }
 

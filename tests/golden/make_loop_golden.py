@@ -34,6 +34,8 @@ CASES = {
     "sphere_grav_fastmono": (4, {}),                         # barotropic: u follows from the EOS
     "sphere_grav_quad": (5, {"ntreebuildstep": 3, "ntreestockstep": 2}),   # rebuild / extrapolate / restock mix
     "sphere_grav_stars": (4, {}),                            # three star particles moved by the N-body leapfrog
+    # ... and by the reference's DEFAULT N-body integrator, the 4th-order Hermite scheme (NbodyHermite4.cpp)
+    "sphere_grav_stars+hermite4": (4, {"nbody": "hermite4"}),
 }
 
 # setup: what a restart needs (the first step recomputes every density-pass field); loop: what is compared
@@ -45,7 +47,7 @@ FIELDS = {"setup": ["r", "v", "a", "atree", "m", "h", "u", "sound", "dudt", "div
 def main():
     for name in (sys.argv[1:] or list(CASES)):
         steps, extra = CASES[name]
-        params, d = load_golden(name)
+        params, d = load_golden(name.split("+")[0])
         p = dict(BASE)
         p.update(params)
         p.update({k: BASE[k] for k in ("run_id", "ic", "Nstepsmax", "tend", "neib_search")})
@@ -67,7 +69,7 @@ def main():
         fix["loop.t"] = np.float64(info["t"])
         fix["loop.timestep"] = np.float64(info["timestep"])
         fix["loop.steps"] = np.int64(steps)
-        path = os.path.join(HERE, "loop_" + name + ".npz")
+        path = os.path.join(HERE, "loop_" + name.replace("+", "_") + ".npz")
         np.savez_compressed(path, **fix)
         print("%-28s N=%-6d steps=%d t=%.6e  %7.1f kB" % ("loop_" + name, len(ic["m"]), steps, info["t"],
                                                          os.path.getsize(path)/1e3))

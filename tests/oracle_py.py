@@ -417,6 +417,52 @@ def star_star_forces(p, sr, sm, sh):
     return a, gpot
 
 
+def star_star_forces_hermite(p, sr, sv, sm, sh):
+    """NbodyHermite4::CalculateDirectSmoothedGravForces (NbodyHermite4.cpp:77-140): softened gravity between the stars
+    with the mean-h kernel and its time derivative -> (a, adot, gpot).  (wmean carries the reference's single-precision
+    powf.)"""
+    L = lib()
+    ns, nd = sr.shape
+    a = np.zeros((ns, nd)); adot = np.zeros((ns, nd)); gpot = np.zeros(ns)
+    twopi = 6.283185307179586
+    for i in range(ns):
+        for j in range(ns):
+            if i == j:
+                continue
+            dr = sr[j] - sr[i]
+            dv = sv[j] - sv[i]
+            drsqd = float(np.dot(dr, dr))
+            drmag = np.sqrt(drsqd)
+            invdrmag = 1.0/np.sqrt(drsqd)
+            invhmean = 2.0/(sh[i] + sh[j])
+            drdt = float(np.dot(dv, dr))*invdrmag
+            paux = sm[j]*invhmean*invhmean*L.orc_kernel(C.byref(p), 4, drmag*invhmean)*invdrmag
+            wmean = L.orc_kernel(C.byref(p), 0, drmag*invhmean)*float(np.power(np.float32(invhmean), np.float32(nd)))
+            gpot[i] += sm[j]*invhmean*L.orc_kernel(C.byref(p), 5, drmag*invhmean)
+            a[i] += paux*dr
+            adot[i] += paux*dv - 3.0*paux*drdt*invdrmag*dr + 2.0*twopi*sm[j]*drdt*wmean*invdrmag*dr
+    return a, adot, gpot
+
+
+def hermite4_timestep(nm, sa, sadot, sa2dot, sa3dot, sh):
+    """NbodyHermite4::Timestep (NbodyHermite4.cpp:542-578): the Aarseth criterion, minimum over the stars"""
+    small, big = 1.0e-50, 9.9e50                      # small_number_dp, big_number_dp (Constants.h:89-90)
+    out = big
+    for i in range(len(sh)):
+        asqd, a1sqd = float(np.dot(sa[i], sa[i])), float(np.dot(sadot[i], sadot[i]))
+        a2sqd, a3sqd = float(np.dot(sa2dot[i], sa2dot[i])), float(np.dot(sa3dot[i], sa3dot[i]))
+        if a1sqd > small and a2sqd > small:
+            ts = nm*np.sqrt((np.sqrt(asqd*a2sqd) + a1sqd)/(np.sqrt(a1sqd*a3sqd) + a2sqd))
+        elif asqd > small and a2sqd > small:
+            ts = nm*np.sqrt(asqd/(a2sqd + small))
+        elif asqd > small:
+            ts = np.sqrt(sh[i]/(np.sqrt(asqd) + small))
+        else:
+            ts = big
+        out = min(out, float(ts))
+    return out
+
+
 def mainloop(params, setup, steps):
     """`steps` x SphSimulation::MainLoop (SphSimulation.cpp:574-880; SphLeapfrogKDK.cpp:76-125,226-270;
     Integration.cpp:11-75) from the reference's post-setup particle state; full tree rebuild every step.
@@ -442,8 +488,14 @@ def mainloop(params, setup, steps):
         sm, sh = s["star_m"], s["star_h"]
         sr0, sv0, sa0 = sr.copy(), sv.copy(), sa.copy()
         sgpot = np.zeros(len(sm))
+        hermite = params.get("nbody", "hermite4") == "hermite4"      # the reference's default (Parameters.cpp:168)
+        if hermite:
+            sadot, sa2dot, sa3dot = (s[k].reshape(-1, nd).copy() for k in ("star_adot", "star_a2dot", "star_a3dot"))
+            sadot0 = sadot.copy()
 
         def star_timestep():
+            if hermite:
+                return hermite4_timestep(nm, sa, sadot, sa2dot, sa3dot, sh)
             amag = np.sqrt((sa*sa).sum(1))
             return float((nm*np.sqrt(sh/(amag + 1.0e-50))).min())
         timestep = min(timestep, star_timestep())
@@ -457,6 +509,9 @@ def mainloop(params, setup, steps):
         if stars:
             sr = sr0 + sv0*dt + 0.5*sa0*dt*dt
             sv = sv0 + sa0*dt
+            if hermite:                                 # NbodyHermite4::AdvanceParticles (NbodyHermite4.cpp:340-378)
+                sr = sr0 + sv0*dt + 0.5*sa0*dt*dt + 0.16666666666666666666666*sadot0*dt*dt*dt
+                sv = sv0 + sa0*dt + 0.5*sadot0*dt*dt
             rows = np.concatenate([sr, sm[:, None], sh[:, None]], axis=1)
         if tdav:
             s["alpha"] = s["alpha"] + s["dalphadt"]*timestep
@@ -492,10 +547,22 @@ def mainloop(params, setup, steps):
             if stars:                                   # ComputeStarGravForces, then the stars' own forces
                 ga, gat, gg = star_grav_forces(p, s["r"], s["h"], sr, sm, sh)
                 f["a"] = f["a"] + ga; f["atree"] = f["atree"] + gat; f["gpot"] = f["gpot"] + gg
-                sa, _, sgpot, _ = tr.star_gas_forces(sr, sv, sh)
-                ssa, ssg = star_star_forces(p, sr, sm, sh)
-                sa = sa + ssa; sgpot = sgpot + ssg
-                sv = sv + 0.5*(sa - sa0)*(t - tlast)    # NbodyLeapfrogKDK::CorrectionTerms
+                sa, sad, sgpot, _ = tr.star_gas_forces(sr, sv, sh)
+                if hermite:
+                    ssa, ssad, ssg = star_star_forces_hermite(p, sr, sv, sm, sh)
+                    sa = sa + ssa; sadot = sad + ssad; sgpot = sgpot + ssg
+                    # NbodyHermite4::CorrectionTerms (NbodyHermite4.cpp:388-440); dt^3 in single precision (powf)
+                    dts = t - tlast
+                    dt3 = float(np.power(np.float32(dts), np.float32(3.0)))
+                    invdt = 1.0/dts
+                    sa2dot = (-6.0*(sa0 - sa) - dts*(4.0*sadot0 + 2.0*sadot))*invdt*invdt
+                    sa3dot = (12.0*(sa0 - sa) + 6.0*dts*(sadot0 + sadot))*invdt*invdt*invdt
+                    sr = sr + sa2dot*dt3*dts/24.0 + sa3dot*dt3*dts*dts/120.0
+                    sv = sv + sa2dot*dt3/6.0 + sa3dot*dt3*dts/24.0
+                else:
+                    ssa, ssg = star_star_forces(p, sr, sm, sh)
+                    sa = sa + ssa; sgpot = sgpot + ssg
+                    sv = sv + 0.5*(sa - sa0)*(t - tlast)    # NbodyLeapfrogKDK::CorrectionTerms
             s["atree"], s["gpot"] = f["atree"], f["gpot"]
         else:
             f = hydro_forces(p, s)
@@ -508,6 +575,8 @@ def mainloop(params, setup, steps):
         if stars:
             nxt = min(nxt, star_timestep())
             sr0, sv0, sa0 = sr.copy(), sv.copy(), sa.copy()
+            if hermite:
+                sadot0 = sadot.copy()
         s["v"] = s["v"] + 0.5*timestep*(s["a"] - a0)          # EndTimestep, part.dt = the step just taken
         r0, v0, a0 = s["r"].copy(), s["v"].copy(), s["a"].copy()
         if energy:
@@ -519,6 +588,8 @@ def mainloop(params, setup, steps):
         timestep = nxt
     if stars:
         s["star_r"], s["star_v"], s["star_a"], s["star_gpot"] = sr, sv, sa, sgpot
+        if hermite:
+            s["star_adot"], s["star_a2dot"], s["star_a3dot"] = sadot, sa2dot, sa3dot
     return s, t, timestep
 
 

@@ -40,8 +40,10 @@ def test_device_mainloop_matches_reference(name):
     params, d = load_golden(name)
     setup, loop = split(d)
     ps, tree = _upload_setup(g, params, setup)
-    if "star_r" in setup:                    # star particles: the N-body leapfrog around the device passes
-        tree.IntegratorSetStars(setup["star_r"], setup["star_v"], setup["star_m"], setup["star_h"], a=setup["star_a"])
+    hermite = "star_r" in setup and params.get("nbody", "hermite4") == "hermite4"
+    if "star_r" in setup:                    # star particles: the reference's N-body integrator around the device passes
+        extra = {k: setup["star_" + k] for k in ("adot", "a2dot", "a3dot")} if hermite else {}
+        tree.IntegratorSetStars(setup["star_r"], setup["star_v"], setup["star_m"], setup["star_h"], a=setup["star_a"], **extra)
     tree.IntegratorBegin(compute_forces=False)
     t0, ts0, n0 = tree.IntegratorState()
     assert t0 == 0.0 and n0 == 0 and ts0 > 0
@@ -49,8 +51,10 @@ def test_device_mainloop_matches_reference(name):
     tree.MainLoop(steps)
     t, ts, n = tree.IntegratorState()
     assert n == steps
-    assert abs(t - float(loop["t"])) <= 1e-12*abs(t)              # same time-step sequence
-    assert abs(ts - float(loop["timestep"])) <= 1e-9*abs(ts)
+    # same time-step sequence.  (Hermite-4 stars: the Aarseth step follows the jerk, and the reference's gas-on-star jerk
+    # goes through single-precision powf -- 1e-7 -- where the device kernel works in double precision.)
+    assert abs(t - float(loop["t"])) <= (1e-8 if hermite else 1e-12)*abs(t)
+    assert abs(ts - float(loop["timestep"])) <= (1e-6 if hermite else 1e-9)*abs(ts)
     tree.Download(ps)
     check_state({k: ps[k] for k in ("r", "v", "a", "h", "rho", "u", "alpha", "dudt")}, loop, TOL)
     if "star_r" in setup:
@@ -58,6 +62,43 @@ def test_device_mainloop_matches_reference(name):
         for k in ("r", "v", "a"):
             assert vec_err(st[k], loop["star_" + k]).max() < TOL, k
         assert rel_err(st["gpot"], loop["star_gpot"]).max() < TOL
+        if hermite:                          # jerk etc.: the reference's gas-on-star jerk goes through single-precision powf
+            for k in ("adot", "a2dot", "a3dot"):
+                assert vec_err(st[k], loop["star_" + k].reshape(st[k].shape)).max() < 1e-5, k
+    tree.close()
+
+
+def test_device_hermite4_stars_from_initial_conditions():
+    """compute_forces = 1 with nbody = hermite4 (the reference's default): IntegratorBegin computes the stars' a, adot
+    (gas + stars) and the start-up a2dot, a3dot (NbodyHermite4::CalculateAllStartupQuantities) itself -- they must be
+    the ones the reference's setup left, and the run must then follow the reference"""
+    import gandalf_b200 as g
+    params, d = load_golden("loop_sphere_grav_stars_hermite4")
+    setup, loop = split(d)
+    assert params["nbody"] == "hermite4"
+    N = len(setup["m"])
+    ps = g.ParticleSet(N, 3)
+    for f in ("r", "v"):
+        ps[f][...] = setup[f].reshape(N, 3)
+    for f in ("m", "h", "u"):
+        ps[f][...] = setup[f]
+    tree = g.GpuSphTree(params)
+    tree.IntegratorSetStars(setup["star_r"], setup["star_v"], setup["star_m"], setup["star_h"])
+    tree.IntegratorBegin(ps, compute_forces=True)
+    st = tree.IntegratorGetStars()
+    # (begin converges h once more from the reference's converged h: the fixed point moves inside h_converge, so the
+    #  gas state -- and with it the force on a star inside the cloud -- agrees to ~1e-4, not to rounding)
+    for k, tol in (("a", 1e-3), ("adot", 1e-2), ("a2dot", 1e-2), ("a3dot", 1e-2)):
+        ref = setup["star_" + k].reshape(st[k].shape)
+        assert np.abs(st[k] - ref).max() <= tol*np.abs(ref).max(), (k, np.abs(st[k] - ref).max()/np.abs(ref).max())
+    t0, ts0, _ = tree.IntegratorState()
+    steps = int(loop["steps"])
+    tree.MainLoop(steps)
+    t, ts, n = tree.IntegratorState()
+    assert n == steps and abs(t - float(loop["t"])) <= 1e-2*abs(t)
+    st = tree.IntegratorGetStars()
+    for k in ("r", "v", "a"):
+        assert vec_err(st[k], loop["star_" + k]).max() < 2e-2, k
     tree.close()
 
 

@@ -60,6 +60,9 @@ def test_mainloop_restatement_matches_reference(name):
     if "star_r" in loop:                     # star particles moved by the N-body leapfrog
         for k in ("star_r", "star_v", "star_a"):
             assert vec_err(np.asarray(s[k]), loop[k]).max() < 1e-9, k
+        if params.get("nbody", "hermite4") == "hermite4":     # NbodyHermite4: jerk, snap, crackle (single-precision
+            for k in ("star_adot", "star_a2dot", "star_a3dot"):   # powf in the reference's wmean and dt^3)
+                assert vec_err(np.asarray(s[k]), loop[k].reshape(np.asarray(s[k]).shape)).max() < 1e-6, k
 
 
 # ---------------------------------------------------------------------------------------------------
