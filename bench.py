@@ -32,8 +32,8 @@ sys.path.insert(0, ROOT)
 METRIC = "SPH particle-updates/sec (density+hydro+grav force)"
 UNIT = "particle-updates/s"
 H_PERTURB = 0.03          # both arms restart the h-rho iteration from the converged h perturbed by +-3 %
-DEFAULT_PARTICLES = {"cloud": 64 * 2 ** 20, "glass": 252 ** 3}
-CPU_SAMPLE = {"cloud": 400000, "glass": 400000}
+DEFAULT_PARTICLES = {"cloud": 64 * 2 ** 20, "glass": 252 ** 3, "khi": 983552, "bossbodenheimer": 4000000}
+CPU_SAMPLE = {"cloud": 400000, "glass": 400000, "khi": 245888, "bossbodenheimer": 400000}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -126,7 +126,7 @@ def run_reference_sample(workload, n_sample, steps, threads):
     dat = {"run_id": "BENCHREF", "sim": "gradhsph", "ic": "python", "dimensionless": 1, "Nlevels": 1,
            "Nstepsmax": 1, "tend": 1.0e-10, "dt_snap": 1.0e10, "noutputstep": 1000000, "ndiagstep": 1000000,
            "out_file_form": "su", "sink_particles": 0, "sph_integration": "lfkdk", "neib_search": "kdtree",
-           "Nhydromax": 4 * N if workload == "glass" else N + 1000}
+           "Nhydromax": 4 * N if workload in ("glass", "khi") else N + 1000}
     dat.update(params)
     t0 = time.time()
     _, bench = refio.run_harness(dat, ic=dict(r=ic["r"].T.copy(), v=ic["v"].T.copy(), m=ic["m"], h=ic["h"], u=ic["u"]),
@@ -179,6 +179,11 @@ def main_reference(args, rank, world):
 
 
 def workload_name(w, N):
+    if w == "khi":
+        return "2D Kelvin-Helmholtz (khi.dat scaled), %d particles, quintic tabulated, Nleafmax 12, wadsley2008" % N
+    if w == "bossbodenheimer":
+        return ("rotating sphere with m=2 perturbation (bossbodenheimer.dat scaled), %d particles, barotropic, "
+                "fast_monopole theta^2=0.15, M4 tabulated" % N)
     if w == "cloud":
         return "turbulent self-gravitating cloud, %d particles, fast_monopole theta^2=0.15, M4 tabulated" % N
     return "3D periodic jittered-lattice (glass) box, hydro only, %d particles, M4 tabulated" % N
@@ -198,7 +203,7 @@ def main_ours(args, rank, world, local_rank):
     NP = args.particles or DEFAULT_PARTICLES[args.workload]
     params, ic = workloads.WORKLOADS[args.workload](NP, device=dev)
     N = int(ic["m"].shape[0])
-    ndim = 3
+    ndim = int(params["ndim"])
     grav = int(params["self_gravity"]) == 1
 
     alloc = pinned_alloc()
@@ -370,7 +375,9 @@ def main_ours(args, rank, world, local_rank):
     # ---- roofline of the dominant kernel (DESIGN.md "Kernels"): algorithmic bytes per particle ---------
     K = args.steps
     kms = {k: ksum[k] / K for k in ("density", "hydro", "gravity")}
-    balg = {"density": 120.0, "hydro": 248.0 if grav else 208.0, "gravity": 180.0}
+    # density (d+2)s+8 in + 9s out; forces (2d+11)s+20 in + (d+3)s+4 out (+ (d+2)s with gravity); s = 8
+    balg = {"density": (ndim + 2)*8.0 + 8 + 72, "hydro": (2*ndim + 11)*8.0 + 20 + (ndim + 3)*8 + 4 + ((ndim + 2)*8 if grav else 0),
+            "gravity": 180.0}
     # dram__bytes_read+write per particle from the committed ncu --set full capture
     # (profiles/r2_ncu_full_cloud16m_summary.txt, 16 Mi-particle cloud), scaled to this launch.  Every entry is the
     # whole pass: the pre-walk kernel + the main kernel for density / hydro; for gravity the walk, cells and direct
@@ -445,7 +452,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cloud", choices=["cloud", "glass"])
+    ap.add_argument("--workload", default="cloud", choices=["cloud", "glass", "khi", "bossbodenheimer"])
     ap.add_argument("--particles", type=int, default=0)
     ap.add_argument("--cpu-particles", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
