@@ -102,7 +102,7 @@ EXPORTS = [
     "gsph_integrator_finish", "gsph_integrator_check_timesteps", "gsph_update_thermal_properties",
     "gsph_update_star_gas_forces", "gsph_derive_density_fields",
     "gsph_integrator_set_stars", "gsph_integrator_get_stars", "gsph_integrator_set_stars_hermite4",
-    "gsph_integrator_get_star_derivatives",
+    "gsph_integrator_get_star_derivatives", "gsph_integrator_get_star_levels",
 ]
 
 _lib = None
@@ -152,6 +152,7 @@ def lib():
     L.gsph_integrator_get_stars.argtypes = [H, C.c_void_p, C.c_int]
     L.gsph_integrator_set_stars_hermite4.argtypes = [H, C.c_void_p, C.c_int, C.c_double]
     L.gsph_integrator_get_star_derivatives.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.gsph_integrator_get_star_levels.argtypes = [H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.gsph_update_star_gas_forces.argtypes = [H, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.gsph_integrator_state.argtypes = [H, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     L.gsph_integrator_block_state.argtypes = [H, C.POINTER(BlockState), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -1732,19 +1732,34 @@ static int integ_star_forces(gsph_handle* h)
 {
   IntegState& I = h->integ;
   const int nd = h->cfg.ndim, ns = I.nstar;
-  std::fill(I.sa.begin(), I.sa.end(), 0.0); std::fill(I.sgpot.begin(), I.sgpot.end(), 0.0);
-  if (I.hermite4) std::fill(I.sadot.begin(), I.sadot.end(), 0.0);
+  /* with block time steps only the stars at the end of their own step get new forces (the `active` flag of
+     Nbody*::AdvanceParticles); the others keep a, adot, gpot */
+  const bool blk = I.cfg.Nlevels > 1 && (int) I.sact.size() == ns;
+  std::vector<int> act;
+  for (int s = 0; s < ns; s++) if (!blk || I.sact[s]) act.push_back(s);
+  const int na = (int) act.size();
+  if (na == 0) return GSPH_OK;
+  for (int s : act) {
+    for (int k = 0; k < nd; k++) { I.sa[(size_t) s*nd + k] = 0.0; if (I.hermite4) I.sadot[(size_t) s*nd + k] = 0.0; }
+    I.sgpot[s] = 0.0;
+  }
   if (h->cfg.self_gravity) {
-    std::vector<double> rows((size_t) ns*(2*nd + 1));
-    for (int s = 0; s < ns; s++) {
-      for (int k = 0; k < nd; k++) { rows[(size_t) s*(2*nd + 1) + k] = I.sr[(size_t) s*nd + k]; rows[(size_t) s*(2*nd + 1) + nd + k] = I.sv[(size_t) s*nd + k]; }
-      rows[(size_t) s*(2*nd + 1) + 2*nd] = I.sh[s];
+    std::vector<double> rows((size_t) na*(2*nd + 1)), ga((size_t) na*nd), gad((size_t) na*nd), gg(na);
+    for (int q = 0; q < na; q++) {
+      const int s = act[q];
+      for (int k = 0; k < nd; k++) { rows[(size_t) q*(2*nd + 1) + k] = I.sr[(size_t) s*nd + k]; rows[(size_t) q*(2*nd + 1) + nd + k] = I.sv[(size_t) s*nd + k]; }
+      rows[(size_t) q*(2*nd + 1) + 2*nd] = I.sh[s];
     }
-    const int rc = gsph_update_star_gas_forces(h, rows.data(), ns, I.sa.data(), I.hermite4 ? I.sadot.data() : NULL, I.sgpot.data(), NULL);
+    const int rc = gsph_update_star_gas_forces(h, rows.data(), na, ga.data(), I.hermite4 ? gad.data() : NULL, gg.data(), NULL);
     if (rc) return rc;
+    for (int q = 0; q < na; q++) {
+      const int s = act[q];
+      for (int k = 0; k < nd; k++) { I.sa[(size_t) s*nd + k] = ga[(size_t) q*nd + k]; if (I.hermite4) I.sadot[(size_t) s*nd + k] = gad[(size_t) q*nd + k]; }
+      I.sgpot[s] = gg[q];
+    }
   }
   const double twopi = 6.283185307179586;
-  for (int i = 0; i < ns; i++)
+  for (int i : act)
     for (int j = 0; j < ns; j++) {
       if (i == j) continue;
       double dr[3] = {0, 0, 0}, dv[3] = {0, 0, 0}, drsqd = 0.0, dvdr = 0.0;
@@ -1809,11 +1824,13 @@ static void integ_star_startup_hermite(gsph_handle* h)
 
 /* NbodyHermite4::CorrectionTerms (NbodyHermite4.cpp:388-440): Hermite interpolation of a2dot, a3dot over the step,
    positions to 5th and velocities to 4th order; dt^3 in single precision like the reference's powf */
-static void integ_star_correct_hermite(gsph_handle* h, double dt)
+static void integ_star_correct_hermite(gsph_handle* h, double dt, int star = -1)
 {
   IntegState& I = h->integ;
+  const int nd = h->cfg.ndim;
   const double dt3 = (double) powf((float) dt, 3.0f), invdt = 1.0/dt;
-  for (size_t q = 0; q < I.sa.size(); q++) {
+  const size_t q0 = star < 0 ? 0 : (size_t) star*nd, q1 = star < 0 ? I.sa.size() : (size_t)(star + 1)*nd;
+  for (size_t q = q0; q < q1; q++) {
     I.sa2dot[q] = (-6.0*(I.sa0[q] - I.sa[q]) - dt*(4.0*I.sadot0[q] + 2.0*I.sadot[q]))*invdt*invdt;
     I.sa3dot[q] = (12.0*(I.sa0[q] - I.sa[q]) + 6.0*dt*(I.sadot0[q] + I.sadot[q]))*invdt*invdt*invdt;
     I.sr[q] += I.sa2dot[q]*dt3*dt/24.0 + I.sa3dot[q]*dt3*dt*dt/120.0;
@@ -1822,12 +1839,13 @@ static void integ_star_correct_hermite(gsph_handle* h, double dt)
 }
 
 /* NbodyLeapfrogKDK::Timestep over the stars */
-static double integ_star_timestep(const gsph_handle* h)
+static double integ_star_timestep(const gsph_handle* h, int only = -1)
 {
   const IntegState& I = h->integ;
   const int nd = h->cfg.ndim;
   double ts = 9.9e50;
   for (int s = 0; s < I.nstar; s++) {
+    if (only >= 0 && s != only) continue;
     auto sq = [&](const std::vector<double>& v) { double x = 0.0; for (int k = 0; k < nd; k++) { const double a = v[(size_t) s*nd + k]; x = k == 0 ? a*a : x + a*a; } return x; };
     const double asqd = sq(I.sa);
     if (!I.hermite4) { ts = std::min(ts, I.nbody_mult*sqrt(I.sh[s]/(sqrt(asqd) + 1.0e-50))); continue; }
@@ -1851,6 +1869,13 @@ static BlkPtrs blk_ptrs(gsph_handle* h)
 }
 static inline bool integ_block(const gsph_handle* h) { return h->integ.cfg.Nlevels > 1; }
 
+/* ComputeTimestepLevel (InlineFuncs.h:550-558) on the host, for the stars */
+static inline int timestep_level_host(double dt, double dt_max)
+{
+  const int lv = (int)(1.44269504088896*log(dt_max/dt)) + 1;
+  return lv > 0 ? lv : 0;
+}
+
 #define BLK_LAUNCH(MODE, OP, NFACTOR)                                                                        \
   INTEG_LAUNCH(blk_timestep_kernel, (int) h->N, devptrs(h->H, h->HI), blk_ptrs(h), h->dp, I.cfg, MODE, (int) I.n, I.level_step, \
                I.level_max, I.dt_max, I.timestep, OP, NFACTOR, I.red)
@@ -1869,9 +1894,19 @@ static int blk_compute_timesteps(gsph_handle* h)
     if (res[1]) { h->err = "Error : Hydro timestep too large"; return GSPH_ESTATE; }
     double ts; memcpy(&ts, &res[0], sizeof ts);
     I.timestep = ts;
+    std::vector<double> sdt(I.nstar);
+    for (int s = 0; s < I.nstar; s++) { sdt[s] = integ_star_timestep(h, s); I.timestep = std::min(I.timestep, sdt[s]); }
     I.level_max = I.cfg.Nlevels - 1;
     I.level_step = I.level_max;                            /* + integration_step - 1, = 0 for the KDK leapfrog */
     I.dt_max = I.timestep*pow(2.0, I.level_max);
+    if (I.nstar > 0) {
+      /* the stars sit at least on the deepest level the gas occupies (Simulation.cpp:1858-1872) */
+      const int lmh = std::min(timestep_level_host(ts, I.dt_max), I.level_max);
+      for (int s = 0; s < I.nstar; s++) {
+        I.slevel[s] = std::max(std::min(timestep_level_host(sdt[s], I.dt_max), I.level_max), lmh);
+        I.snlast[s] = I.n; I.snstep[s] = pow2int(I.level_step - (int) I.slevel[s]); I.stlast[s] = I.t; I.send[s] = 1;
+      }
+    }
     BLK_LAUNCH(1, 0, 1);
     I.nresync = (long long) pow2int(I.level_step);
     I.timestep = I.dt_max/(double) I.nresync;
@@ -1883,21 +1918,37 @@ static int blk_compute_timesteps(gsph_handle* h)
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     if (res[1]) { h->err = "Error : Hydro timestep too large"; return GSPH_ESTATE; }
     I.level_max = (int) res[2];
+    if (I.nstar > 0) {                                     /* the stars at the end of their step (Simulation.cpp:2024-2068) */
+      const int lmh = I.level_max;                         /* level_max_hydro */
+      for (int s = 0; s < I.nstar; s++) {
+        if (I.n - I.snlast[s] == I.snstep[s]) {
+          const long long nstep = I.snstep[s]; const int last = (int) I.slevel[s];
+          const int lv = std::max(timestep_level_host(integ_star_timestep(h, s), I.dt_max), lmh);
+          if (lv < last && lv > lmh && last > 1 && I.n % (2*nstep) == 0) I.slevel[s] = last - 1;
+          else if (lv > last) I.slevel[s] = lv;
+          I.snlast[s] = I.n; I.snstep[s] = pow2int(I.level_step - (int) I.slevel[s]); I.stlast[s] = I.t; I.send[s] = 1;
+        }
+        I.level_max = std::max(I.level_max, (int) I.slevel[s]);
+      }
+    }
     const long long istep = pow2int(I.level_step - level_max_old + 1);
     int op = 0, nfactor = 1;
     if (I.level_max > level_max_old) {                     /* levels added: finer integer time */
       nfactor = pow2int(I.level_max - level_max_old); op = 1;
       I.n *= nfactor;
+      for (int s = 0; s < I.nstar; s++) { I.snstep[s] *= nfactor; I.snlast[s] *= nfactor; }
     }
     else if (I.level_max <= level_max_old - 1 && level_max_old > 1 && istep > 0 && I.n % istep == 0) {
       I.level_max = level_max_old - 1;                     /* one level removed */
       nfactor = pow2int(level_max_old - I.level_max); op = 2;
       I.n /= nfactor;
+      for (int s = 0; s < I.nstar; s++) { I.snlast[s] /= nfactor; I.snstep[s] /= nfactor; }
     }
     else I.level_max = level_max_old;
     I.level_step = I.level_max;
     I.nresync = (long long) pow2int(I.level_step);
     I.timestep = I.dt_max/(double) I.nresync;
+    for (int s = 0; s < I.nstar; s++) if (I.snlast[s] == I.n) I.snstep[s] = pow2int(I.level_step - (int) I.slevel[s]);
     BLK_LAUNCH(3, op, nfactor);
   }
   if (!(I.timestep > 0.0)) { h->err = "Error : timestep fallen to zero"; return GSPH_ESTATE; }
@@ -2021,6 +2072,21 @@ int gsph_integrator_get_star_derivatives(gsph_handle* h, double* adot, double* a
   return GSPH_OK;
 }
 
+/* block time steps of the stars: level, nstep, nlast (int64[Nstar]) and tlast (double[Nstar]); NULL = not wanted */
+int gsph_integrator_get_star_levels(gsph_handle* h, int64_t* level, int64_t* nstep, int64_t* nlast, double* tlast)
+{
+  if (!h) return GSPH_EINVAL;
+  const IntegState& I = h->integ;
+  if (!I.on || I.cfg.Nlevels <= 1 || (int) I.slevel.size() != I.nstar) { h->err = "gsph_integrator_get_star_levels: no star particles on block time steps"; return GSPH_ESTATE; }
+  for (int s = 0; s < I.nstar; s++) {
+    if (level) level[s] = I.slevel[s];
+    if (nstep) nstep[s] = I.snstep[s];
+    if (nlast) nlast[s] = I.snlast[s];
+    if (tlast) tlast[s] = I.stlast[s];
+  }
+  return GSPH_OK;
+}
+
 int gsph_integrator_begin(gsph_handle* h, const gsph_integrator_config* cfg, int compute_forces, double t0)
 {
   if (!h) return GSPH_EINVAL;
@@ -2051,7 +2117,6 @@ int gsph_integrator_begin(gsph_handle* h, const gsph_integrator_config* cfg, int
   }
   if (!I.red) CUDA_TRY(h, cudaMalloc(&I.red, 4*sizeof(unsigned long long)));
   if (cfg->Nlevels > 1) {
-    if (I.nstar > 0) { h->err = "gsph_integrator_begin: star particles with block time steps (Nlevels > 1) are not on the accelerated path"; return GSPH_EINVAL; }
     if (h->dp.any_mirror) { h->err = "gsph_integrator_begin: block time steps with mirror boundaries are not on the accelerated path"; return GSPH_EINVAL; }
     if (cfg->Nlevels > 30) { h->err = "gsph_integrator_begin: Nlevels must be <= 30"; return GSPH_EINVAL; }
     if (I.blk_cap < h->Ncap) {
@@ -2067,6 +2132,7 @@ int gsph_integrator_begin(gsph_handle* h, const gsph_integrator_config* cfg, int
     }
   }
   I.cfg = *cfg; I.t = I.tlast = t0; I.Nsteps = 0; I.rebuild = true; I.on = false; I.mid_step = false;
+  I.sact.clear(); I.send.clear();                        /* (no star is "inactive" before the hierarchy exists) */
   I.n = I.nresync = 0; I.level_max = I.level_step = 0; I.dt_max = 0.0;
   h->hdef_d = 0ull; h->hdef_i = 0u;                     /* the integrator writes the host-order arrays */
   CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_all, 0));          /* the upload has landed */
@@ -2097,7 +2163,10 @@ int gsph_integrator_begin(gsph_handle* h, const gsph_integrator_config* cfg, int
     CUDA_TRY(h, cudaMemsetAsync(I.pdt, 0, (size_t) h->N*sizeof(double), h->stream));
     CUDA_TRY(h, cudaMemsetAsync(I.dt_next, 0, (size_t) h->N*sizeof(double), h->stream));
     fill_kernel<double><<<(int)((h->N + 255)/256), 256, 0, h->stream>>>(h->N, I.ptlast, t0);
+    I.slevel.assign(I.nstar, 0); I.snstep.assign(I.nstar, 0); I.snlast.assign(I.nstar, 0); I.stlast.assign(I.nstar, t0);
+    I.send.assign(I.nstar, 0); I.sact.assign(I.nstar, 0);
     rc = blk_compute_timesteps(h); if (rc) return rc;
+    std::fill(I.send.begin(), I.send.end(), 0);             /* nbody->EndTimestep: r0 = r ... was set above */
     INTEG_LAUNCH(integ_end_kernel, (int) h->N, devptrs(h->H, h->HI), integ_ptrs(h), 0.0, I.cfg.energy_integration, 1,
                  (int) I.n, I.t, I.nlast, I.pdt, I.dt_next, I.ptlast);
     I.on = true;
@@ -2130,7 +2199,24 @@ int gsph_integrator_advance(gsph_handle* h, int* tree_mode, double* timestep)
   INTEG_LAUNCH(integ_advance_kernel, (int) h->N, devptrs(h->H, h->HI), integ_ptrs(h), h->dp, dt, ts,
                h->dp.tdavisc != GSPH_TDAVISC_NONE ? 1 : 0, I.cfg.energy_integration, integ_block(h) ? 1 : 0, I.t, (int) I.n,
                (const int32_t*) I.nstep, (const int32_t*) I.nlast, (const double*) I.ptlast);
-  if (I.nstar > 0) {                                   /* NbodyLeapfrogKDK::AdvanceParticles */
+  if (I.nstar > 0 && integ_block(h)) {                 /* Nbody*::AdvanceParticles, every star from the start of ITS step */
+    const int nd = h->cfg.ndim;
+    for (int s = 0; s < I.nstar; s++) {
+      const double ds = I.t - I.stlast[s];
+      for (int k = 0; k < nd; k++) {
+        const size_t q = (size_t) s*nd + k;
+        I.sr[q] = I.sr0[q] + I.sv0[q]*ds + 0.5*I.sa0[q]*ds*ds;
+        I.sv[q] = I.sv0[q] + I.sa0[q]*ds;
+        if (I.hermite4) {
+          I.sr[q] = I.sr0[q] + I.sv0[q]*ds + 0.5*I.sa0[q]*ds*ds + 0.16666666666666666666666*I.sadot0[q]*ds*ds*ds;
+          I.sv[q] = I.sv0[q] + I.sa0[q]*ds + 0.5*I.sadot0[q]*ds*ds;
+        }
+      }
+      I.sact[s] = (I.n - I.snlast[s] == I.snstep[s]) ? 1 : 0;
+    }
+    const int rs = integ_push_stars(h); if (rs) return rs;
+  }
+  else if (I.nstar > 0) {                              /* NbodyLeapfrogKDK::AdvanceParticles */
     for (size_t q = 0; q < I.sr.size(); q++) {
       I.sr[q] = I.sr0[q] + I.sv0[q]*dt + 0.5*I.sa0[q]*dt*dt;
       I.sv[q] = I.sv0[q] + I.sa0[q]*dt;
@@ -2179,7 +2265,16 @@ int gsph_integrator_finish(gsph_handle* h)
   if (I.nstar > 0) {
     rc = integ_star_forces(h); if (rc) return rc;
     const double dts = I.t - I.tlast;
-    if (I.hermite4) integ_star_correct_hermite(h, dts);
+    if (integ_block(h)) {                              /* Nbody*::CorrectionTerms for the stars at the end of their step */
+      const int nd = h->cfg.ndim;
+      for (int s = 0; s < I.nstar; s++) {
+        if (!I.sact[s]) continue;
+        const double ds = I.t - I.stlast[s];
+        if (I.hermite4) integ_star_correct_hermite(h, ds, s);
+        else for (int k = 0; k < nd; k++) { const size_t q = (size_t) s*nd + k; I.sv[q] += 0.5*(I.sa[q] - I.sa0[q])*ds; }
+      }
+    }
+    else if (I.hermite4) integ_star_correct_hermite(h, dts);
     else for (size_t q = 0; q < I.sv.size(); q++) I.sv[q] += 0.5*(I.sa[q] - I.sa0[q])*dts;     /* NbodyLeapfrogKDK::CorrectionTerms */
   }
   if (integ_block(h)) {
@@ -2187,6 +2282,16 @@ int gsph_integrator_finish(gsph_handle* h)
     I.rebuild = false;
     INTEG_LAUNCH(integ_end_kernel, (int) h->N, devptrs(h->H, h->HI), integ_ptrs(h), 0.0, I.cfg.energy_integration, 1,
                  (int) I.n, I.t, I.nlast, I.pdt, I.dt_next, I.ptlast);
+    for (int s = 0; s < I.nstar; s++) {                 /* Nbody*::EndTimestep for the stars flagged end_timestep */
+      if (!I.send[s]) continue;
+      const int nd = h->cfg.ndim;
+      for (int k = 0; k < nd; k++) {
+        const size_t q = (size_t) s*nd + k;
+        I.sr0[q] = I.sr[q]; I.sv0[q] = I.sv[q]; I.sa0[q] = I.sa[q];
+        if (I.hermite4) I.sadot0[q] = I.sadot[q];
+      }
+      I.snlast[s] = I.n; I.stlast[s] = I.t; I.send[s] = 0;
+    }
     I.tlast = I.t;
     I.mid_step = false;
     h->p_stale = true;

@@ -141,6 +141,11 @@ struct IntegState {
   std::vector<double> sr, sv, sa, sr0, sv0, sa0, sm, sh, sgpot;
   bool hermite4 = false;     /* the stars move with NbodyHermite4 (the reference's default) instead of the leapfrog */
   std::vector<double> sadot, sadot0, sa2dot, sa3dot;
+  /* block time steps of the stars (Simulation::ComputeBlockTimesteps, N-body parts): level, integer step and start,
+     start time, end-of-step flag, and who is active in the current step */
+  std::vector<long long> slevel, snstep, snlast;
+  std::vector<double> stlast;
+  std::vector<char> send, sact;
 };
 
 struct gsph_handle {

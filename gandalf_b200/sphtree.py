@@ -247,6 +247,12 @@ class GpuSphTree(object):
                 out[k] = np.zeros((ns, nd))
             self._check(self._L.gsph_integrator_get_star_derivatives(self._h, out["adot"].ctypes.data,
                                                                      out["a2dot"].ctypes.data, out["a3dot"].ctypes.data))
+        if ns > 0 and int(self.params["Nlevels"]) > 1:      # block time steps: the stars' own levels
+            for k in ("level", "nstep", "nlast"):
+                out[k] = np.zeros(ns, dtype=np.int64)
+            out["tlast"] = np.zeros(ns)
+            self._check(self._L.gsph_integrator_get_star_levels(self._h, out["level"].ctypes.data, out["nstep"].ctypes.data,
+                                                                out["nlast"].ctypes.data, out["tlast"].ctypes.data))
         return out
 
     def IntegratorAdvance(self):

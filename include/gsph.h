@@ -335,14 +335,16 @@ int gsph_get_stats(gsph_handle* h, gsph_stats* st);
  *   Simulation::ComputeGlobalTimestep            src/Common/Simulation.cpp:1669-1745
  *   TimeIntegration::CheckBoundaries             src/Common/Integration.cpp:11-75
  * around the operators above (BuildTree, UpdateAllSphProperties, ZeroAccelerations, force pass).
- * Block time steps (gsph_integrator_config::Nlevels > 1, single device): additionally
+ * Block time steps (gsph_integrator_config::Nlevels > 1; several devices through gsph_integrator_advance /
+ * _check_timesteps / _finish): additionally
  *   Simulation::ComputeBlockTimesteps            src/Common/Simulation.cpp:1764-2199
  *   SphLeapfrogKDK::CheckTimesteps               src/Hydrodynamics/SphLeapfrogKDK.cpp:284-339 (neighbour-level limiter; the
  *                                                passes are repeated for the particles it wakes, SphSimulation.cpp:658-756)
  *   the thermal refresh of every particle before the force pass (nradstep = 1, SphSimulation.cpp:669-679).
  * gsph_integrator_begin then sets up the hierarchy like PostInitialConditionsSetup (a resynchronisation at n = 0).
- * Star particles: gsph_integrator_set_stars below (one global time step only).  Not covered (GSPH_EINVAL): sinks,
- * external potentials, dust, sph_single_timestep, block time steps on several ranks or with stars.     */
+ * Star particles: gsph_integrator_set_stars / _set_stars_hermite4 below, with one global time step or on block time
+ * steps of their own.  Not covered (GSPH_EINVAL): sinks, external potentials, dust, sph_single_timestep, block time
+ * steps together with mirror walls.                                                                              */
 typedef struct gsph_integrator_config {
   double  accel_mult, courant_mult, energy_mult;   /* Parameters.cpp:239,240,263 (0.3, 0.15, 0.4)      */
   int32_t energy_integration;   /* 1: u is integrated explicitly (gas_eos = energy_eqn,
@@ -398,6 +400,10 @@ int gsph_integrator_get_stars(gsph_handle* h, double* rows, int Nstar);
  * get_star_derivatives adot, a2dot, a3dot (Nstar x ndim each, NULL = not wanted).                               */
 int gsph_integrator_set_stars_hermite4(gsph_handle* h, const double* rows, int Nstar, double nbody_mult);
 int gsph_integrator_get_star_derivatives(gsph_handle* h, double* adot, double* a2dot, double* a3dot);
+/* with block time steps (Nlevels > 1) the stars have levels of their own, at least the deepest one the gas occupies
+ * (Simulation::ComputeBlockTimesteps, Simulation.cpp:1858-1872, 2024-2068, 2146-2152): only the stars at the end of
+ * their step get new forces, the correction and EndTimestep.  level, nstep, nlast: int64[Nstar], tlast: double[Nstar]. */
+int gsph_integrator_get_star_levels(gsph_handle* h, int64_t* level, int64_t* nstep, int64_t* nlast, double* tlast);
 int gsph_integrator_advance(gsph_handle* h, int* tree_mode, double* timestep);
 int gsph_integrator_finish(gsph_handle* h);
 /* Block time steps (Nlevels > 1) in a host-driven loop (several devices): between the passes and

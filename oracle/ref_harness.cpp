@@ -191,6 +191,16 @@ struct Harness
       dump_f64(stage + ".star_r", sr, Ns, ndim); dump_f64(stage + ".star_v", sv, Ns, ndim);
       dump_f64(stage + ".star_a", sa, Ns, ndim); dump_f64(stage + ".star_m", sm, Ns);
       dump_f64(stage + ".star_h", sh, Ns); dump_f64(stage + ".star_gpot", sg, Ns);
+      // block time steps of the stars (NbodyParticle: level, nstep, nlast, tlast)
+      {
+        vector<int> sl(Ns), sns(Ns), snl(Ns); vector<double> stl(Ns);
+        for (int i = 0; i < Ns; i++) {
+          sl[i] = sim->nbody->stardata[i].level; sns[i] = sim->nbody->stardata[i].nstep; snl[i] = sim->nbody->stardata[i].nlast;
+          stl[i] = sim->nbody->stardata[i].tlast;
+        }
+        dump_i32(stage + ".star_level", sl, Ns); dump_i32(stage + ".star_nstep", sns, Ns); dump_i32(stage + ".star_nlast", snl, Ns);
+        dump_f64(stage + ".star_tlast", stl, Ns);
+      }
       // Hermite-4 derivatives (NbodyParticle: adot, a2dot, a3dot)
       dump_f64(stage + ".star_adot", sad, Ns, ndim); dump_f64(stage + ".star_a2dot", sa2, Ns, ndim);
       dump_f64(stage + ".star_a3dot", sa3, Ns, ndim);

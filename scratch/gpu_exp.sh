@@ -2,6 +2,4 @@
 tag=${1:-x1}
 out=gpurun_out/$tag
 mkdir -p $out
-for w in khi bossbodenheimer glass; do
-  echo "== bench $w"; timeout 900 python bench.py --workload $w --steps 3 --warmup 3 > $out/bench_$w.json 2> $out/bench_$w.err; python scratch/show_bench.py $out/bench_$w.json | head -2 | cut -c1-400; tail -2 $out/bench_$w.err | cut -c1-300
-done
+echo "== pytest"; timeout 1500 python -m pytest tests/test_gpu_mainloop.py -m gpu -x -q 2>&1 | tail -30 | cut -c1-250 | tee $out/pytest.txt

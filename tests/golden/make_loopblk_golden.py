@@ -21,7 +21,8 @@ import refio  # noqa: E402
 from conftest import load_golden, stage  # noqa: E402
 from make_loop_golden import BASE  # noqa: E402
 
-CASES = {"adsod": (20, 4), "box3d_mm97": (20, 4), "sphere_grav_fastmono": (20, 4), "adsod+cd2010": (20, 4)}       # name -> (steps, Nlevels)
+CASES = {"adsod": (20, 4), "box3d_mm97": (20, 4), "sphere_grav_fastmono": (20, 4), "adsod+cd2010": (20, 4),
+         "sphere_grav_stars+hermite4": (20, 4), "sphere_grav_stars+lfkdk": (20, 4)}   # star particles on their own levels       # name -> (steps, Nlevels)
 FIELDS = ["r", "v", "a", "atree", "m", "h", "u", "rho", "invomega", "zeta", "hfactor", "hrangesqd", "sound", "pressure",
           "alpha", "dalphadt", "dudt", "div_v", "gpot", "ptype", "level", "levelneib", "nstep", "nlast", "dt", "dt_next",
           "tlast", "r0", "v0", "a0", "u0", "dudt0"]
@@ -34,6 +35,8 @@ def main():
         params, d = load_golden(name.split("+")[0])
         p = dict(BASE)
         p.update(params)
+        if name.endswith(("+hermite4", "+lfkdk")):          # the N-body integrator of the three stars of that golden
+            p["nbody"] = name.split("+")[1]
         if name.endswith("+cd2010"):                         # the Cullen & Dehnen switch on the same initial conditions
             p.update(time_dependent_avisc="cd2010", alpha_visc_min=0.1)
         p.update({k: BASE[k] for k in ("run_id", "ic", "Nstepsmax", "tend", "neib_search")})
@@ -42,13 +45,16 @@ def main():
         order = np.argsort(s["iorig"])
         ic = {k: s[k][order] for k in ("r", "v", "m", "h", "u")}
         p.setdefault("Nhydromax", 8*len(ic["m"]))
-        out, info = refio.run_mainloop(p, ic, steps, gpu=False, kind="std", dumps="setup")
+        out, info = refio.run_mainloop(p, ic, steps, gpu=False, kind="std", dumps="setup", stars=d.get("stars"))
         assert info["steps"] == steps
         fix = {"param." + k: np.array(str(v)) for k, v in p.items()}
         for st in ("setup", "loop"):
             o = np.argsort(out[st + ".iorig"])
             for f in FIELDS:
                 fix["%s.%s" % (st, f)] = out["%s.%s" % (st, f)][o]
+            for k in out:
+                if k.startswith(st + ".star_"):
+                    fix[k] = out[k]
             src = info["setup"] if st == "setup" else info
             for k in SIM:
                 fix["%s.sim_%s" % (st, k)] = np.float64(src[k]) if k in ("dt_max", "timestep", "t") else np.int64(src[k])

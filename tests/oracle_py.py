@@ -652,12 +652,34 @@ def mainloop_block(params, setup, sim, steps, trace=None):
     dt_max, timestep, t = float(sim["dt_max"]), float(sim["timestep"]), float(sim["t"])
     size = [p.boxmax[k] - p.boxmin[k] for k in range(nd)]
     end_ts = np.zeros(N, dtype=bool)
+    # star particles (NbodyLeapfrogKDK / NbodyHermite4 with their own block time steps): at least on the deepest level
+    # the gas occupies (Simulation.cpp:1858-1872, 2024-2068)
+    stars = "star_r" in s
+    rows = None
+    if stars:
+        nm = float(params.get("nbody_mult", 0.1))
+        hermite = params.get("nbody", "hermite4") == "hermite4"
+        S = {k: s["star_" + k].reshape(-1, nd).copy() for k in ("r", "v", "a")}
+        S["m"], S["h"] = s["star_m"].copy(), s["star_h"].copy()
+        ns = len(S["m"])
+        for k in ("adot", "a2dot", "a3dot"):
+            S[k] = s["star_" + k].reshape(-1, nd).copy() if hermite else np.zeros((ns, nd))
+        S["r0"], S["v0"], S["a0"], S["adot0"] = S["r"].copy(), S["v"].copy(), S["a"].copy(), S["adot"].copy()
+        S["gpot"] = np.zeros(ns)
+        S["level"] = s["star_level"].astype(np.int64); S["nstep"] = s["star_nstep"].astype(np.int64)
+        S["nlast"] = s["star_nlast"].astype(np.int64); S["tlast"] = s["star_tlast"].astype(np.float64)
+        S["end"] = np.zeros(ns, dtype=bool)
+
+        def star_dt(i):
+            if hermite:
+                return hermite4_timestep(nm, S["a"][i:i + 1], S["adot"][i:i + 1], S["a2dot"][i:i + 1], S["a3dot"][i:i + 1], S["h"][i:i + 1])
+            return float(nm*np.sqrt(S["h"][i]/(np.sqrt(float(np.dot(S["a"][i], S["a"][i]))) + 1.0e-50)))
 
     def passes(active, tr):
         """UpdateAllSphProperties, ZeroAccelerations and the force pass for the active particles; tr = the tree
         BuildTree stocked with the smoothing lengths of the start of the step (cdistsqd!), refreshed here with the
         new ones like tree->UpdateAllHmaxValues (GradhSphTree.cpp:268)"""
-        dens = density(p, s["r"], s["m"], s["h"], s["u"])
+        dens = density(p, s["r"], s["m"], s["h"], s["u"], stars=rows)
         for k in ("h", "rho", "invomega", "zeta", "hfactor", "hrangesqd", "u", "sound", "pressure"):
             s[k] = np.where(active, dens[k], s[k])
         if tr is not None:
@@ -676,6 +698,9 @@ def mainloop_block(params, setup, sim, steps, trace=None):
         s["u"], s["sound"], s["pressure"] = thermal_all(p, s["rho"], s["u"])
         if p.self_gravity:
             f = tr.hydro_grav_forces(s)
+            if stars:                                       # ComputeStarGravForces for the active particles
+                ga, gat, gg = star_grav_forces(p, s["r"], s["h"], S["r"], S["m"], S["h"])
+                f["a"] = f["a"] + ga; f["atree"] = f["atree"] + gat; f["gpot"] = f["gpot"] + gg
             s["atree"] = np.where(active[:, None], f["atree"], s["atree"])
             s["gpot"] = np.where(active, f["gpot"], s["gpot"])
         else:
@@ -708,6 +733,15 @@ def mainloop_block(params, setup, sim, steps, trace=None):
         if energy:
             s["u"] = s["u0"] + s["dudt0"]*dtp
         active = dn == s["nstep"]
+        if stars:                                           # Nbody*::AdvanceParticles
+            sdt = (t - S["tlast"])[:, None]
+            S["r"] = S["r0"] + S["v0"]*sdt + 0.5*S["a0"]*sdt*sdt
+            S["v"] = S["v0"] + S["a0"]*sdt
+            if hermite:
+                S["r"] = S["r0"] + S["v0"]*sdt + 0.5*S["a0"]*sdt*sdt + 0.16666666666666666666666*S["adot0"]*sdt*sdt*sdt
+                S["v"] = S["v0"] + S["a0"]*sdt + 0.5*S["adot0"]*sdt*sdt
+            sact = (n - S["nlast"]) == S["nstep"]
+            rows = np.concatenate([S["r"], S["m"][:, None], S["h"][:, None]], axis=1)
         # ---- CheckBoundaries (periodic wrap only here)
         for k in range(nd):
             if p.periodic[k]:
@@ -732,15 +766,42 @@ def mainloop_block(params, setup, sim, steps, trace=None):
             if not ok.any():
                 break
             nredo += 1
+        # ---- the N-body block of MainLoop (SphSimulation.cpp:771-812): forces and correction of the ACTIVE stars
+        if stars and sact.any():
+            ga, gad, gg, _ = tr.star_gas_forces(S["r"], S["v"], S["h"])
+            if hermite:
+                ssa, ssad, ssg = star_star_forces_hermite(p, S["r"], S["v"], S["m"], S["h"])
+            else:
+                ssa, ssg = star_star_forces(p, S["r"], S["m"], S["h"]); ssad = np.zeros_like(ssa); gad = np.zeros_like(ga)
+            S["a"] = np.where(sact[:, None], ga + ssa, S["a"]); S["gpot"] = np.where(sact, gg + ssg, S["gpot"])
+            S["adot"] = np.where(sact[:, None], gad + ssad, S["adot"])
+            for i in np.nonzero(sact)[0]:
+                dts = t - S["tlast"][i]
+                if hermite:
+                    dt3 = float(np.power(np.float32(dts), np.float32(3.0))); invdt = 1.0/dts
+                    S["a2dot"][i] = (-6.0*(S["a0"][i] - S["a"][i]) - dts*(4.0*S["adot0"][i] + 2.0*S["adot"][i]))*invdt*invdt
+                    S["a3dot"][i] = (12.0*(S["a0"][i] - S["a"][i]) + 6.0*dts*(S["adot0"][i] + S["adot"][i]))*invdt*invdt*invdt
+                    S["r"][i] = S["r"][i] + S["a2dot"][i]*dt3*dts/24.0 + S["a3dot"][i]*dt3*dts*dts/120.0
+                    S["v"][i] = S["v"][i] + S["a2dot"][i]*dt3/6.0 + S["a3dot"][i]*dt3*dts/24.0
+                else:
+                    S["v"][i] = S["v"][i] + 0.5*(S["a"][i] - S["a0"][i])*dts
         # ---- ComputeBlockTimesteps
         ts = particle_timesteps(p, s, cm, am, em, energy)
         if n == nresync:
             n = 0
             s["dt_next"] = ts.copy()
             timestep = float(ts.min())
+            if stars:
+                sts = np.array([star_dt(i) for i in range(ns)])
+                timestep = min(timestep, float(sts.min()))
             level_max = Nlevels - 1
             level_step = level_max
             dt_max = timestep*2.0**level_max
+            if stars:
+                lmh = min(int(timestep_level(np.array([float(ts.min())]), dt_max)[0]), level_max)
+                S["level"] = np.maximum(np.minimum(timestep_level(sts, dt_max), level_max), lmh)
+                S["nlast"][:] = n; S["nstep"] = _pow2int(level_step - S["level"]); S["tlast"][:] = t
+                S["end"][:] = True
             lev = np.minimum(timestep_level(ts, dt_max), level_max)
             s["level"] = lev; s["levelneib"] = lev.copy()
             s["nstep"] = _pow2int(level_step - lev)
@@ -771,22 +832,41 @@ def mainloop_block(params, setup, sim, steps, trace=None):
             s["dt_next"] = np.where(atend, s["nstep"]*timestep, s["dt_next"])
             end_ts |= atend
             level_max = int(s["level"].max())
+            if stars:
+                lmh = level_max                                 # level_max_hydro
+                for i in range(ns):
+                    if n - S["nlast"][i] == S["nstep"][i]:
+                        nstep_i, last = int(S["nstep"][i]), int(S["level"][i])
+                        lv = max(int(timestep_level(np.array([star_dt(i)]), dt_max)[0]), lmh)
+                        if lv < last and lv > lmh and last > 1 and n % (2*nstep_i) == 0:
+                            S["level"][i] = last - 1
+                        elif lv > last:
+                            S["level"][i] = lv
+                        S["nlast"][i] = n; S["nstep"][i] = _pow2int(level_step - S["level"][i]); S["tlast"][i] = t
+                        S["end"][i] = True
+                level_max = max(level_max, int(S["level"].max()))
             istep = 2**(level_step - level_max_old + 1)
             if level_max > level_max_old:
                 nfactor = 2**(level_max - level_max_old)
                 n *= nfactor
                 s["nstep"] = s["nstep"]*nfactor; s["nlast"] = s["nlast"]*nfactor
+                if stars:
+                    S["nstep"] = S["nstep"]*nfactor; S["nlast"] = S["nlast"]*nfactor
             elif level_max <= level_max_old - 1 and level_max_old > 1 and n % istep == 0:
                 level_max = level_max_old - 1
                 nfactor = 2**(level_max_old - level_max)
                 n //= nfactor
                 s["nlast"] = s["nlast"]//nfactor; s["nstep"] = s["nstep"]//nfactor
+                if stars:
+                    S["nstep"] = S["nstep"]//nfactor; S["nlast"] = S["nlast"]//nfactor
             else:
                 level_max = level_max_old
             level_step = level_max
             nresync = 2**level_step
             timestep = dt_max/float(nresync)
             s["nstep"] = np.where(s["nlast"] == n, _pow2int(level_step - s["level"]), s["nstep"])
+            if stars:
+                S["nstep"] = np.where(S["nlast"] == n, _pow2int(level_step - S["level"]), S["nstep"])
         # ---- EndTimestep
         e = end_ts
         s["v"] = np.where(e[:, None], s["v"] + 0.5*s["dt"][:, None]*(s["a"] - s["a0"]), s["v"])
@@ -803,7 +883,16 @@ def mainloop_block(params, setup, sim, steps, trace=None):
         s["dt"] = np.where(e, s["dt_next"], s["dt"])
         s["dt_next"] = np.where(e, 0.0, s["dt_next"])
         end_ts[:] = False
+        if stars:                                           # Nbody*::EndTimestep
+            e = S["end"]
+            for k0, k1 in (("r0", "r"), ("v0", "v"), ("a0", "a"), ("adot0", "adot")):
+                S[k0] = np.where(e[:, None], S[k1], S[k0])
+            S["nlast"] = np.where(e, n, S["nlast"]); S["tlast"] = np.where(e, t, S["tlast"])
+            S["end"][:] = False
         if trace is not None:
             trace.append(dict(n=n, nresync=nresync, level_max=level_max, timestep=timestep, t=t, nredo=nredo))
     sim_out = dict(n=n, nresync=nresync, level_max=level_max, level_step=level_step, dt_max=dt_max, timestep=timestep, t=t)
+    if stars:
+        for k in ("r", "v", "a", "adot", "a2dot", "a3dot", "gpot", "level", "nstep", "nlast", "tlast"):
+            s["star_" + k] = S[k]
     return s, sim_out

@@ -99,6 +99,23 @@ def check_block_state(s, sim, ref, refsim, tol):
         assert np.abs(np.asarray(s[f]) - ref[f]).max() <= 1e-11*np.abs(ref[f]).max(), f
 
 
+def check_block_stars(s, ref, params, tol):
+    """star particles on their own block time steps: identical levels and integer times, state to `tol` (the jerk and
+    the higher derivatives of Hermite-4 pass through single-precision powf in the reference: 1e-5)"""
+    if "star_r" not in ref:
+        return
+    for k in ("level", "nstep", "nlast"):
+        assert np.array_equal(np.asarray(s["star_" + k]).astype(np.int64), ref["star_" + k].astype(np.int64)), k
+    assert np.abs(np.asarray(s["star_tlast"]) - ref["star_tlast"]).max() <= 1e-11*np.abs(ref["star_tlast"]).max()
+    for k in ("r", "v", "a"):
+        a = np.asarray(s["star_" + k])
+        assert vec_err(a, ref["star_" + k].reshape(a.shape)).max() < tol, k
+    if params.get("nbody", "hermite4") == "hermite4":
+        for k in ("adot", "a2dot", "a3dot"):
+            a = np.asarray(s["star_" + k])
+            assert vec_err(a, ref["star_" + k].reshape(a.shape)).max() < max(tol, 1e-5), k
+
+
 def test_block_fixtures_exist():
     assert len(LOOPBLK_CASES) >= 3
 
@@ -116,3 +133,4 @@ def test_block_timestep_restatement_matches_reference(name):
         steps = 20                     # (kept: about 10 s each)
     s, sim = orc.mainloop_block(params, setup, sim0, steps)
     check_block_state(s, sim, loop, sim1, 1e-9)
+    check_block_stars(s, loop, params, 1e-9)
