@@ -326,9 +326,9 @@ typedef struct gsph_stats {
 int gsph_get_stats(gsph_handle* h, gsph_stats* st);
 
 /*--------------------------------------------------------------------------------------------------
- * Device-resident main loop: leapfrog kick-drift-kick with ONE global time step
- * (Nlevels = 1), so that particles stay in HBM between steps instead of travelling over PCIe
- * around every operator call.  Replaces, for that configuration,
+ * Device-resident main loop: leapfrog kick-drift-kick with one global time step
+ * (Nlevels = 1) or hierarchical block time steps, so that particles stay in HBM between steps instead
+ * of travelling over PCIe around every operator call.  Replaces, for sph_integration = lfkdk,
  *   SphSimulation::MainLoop                      src/Hydrodynamics/SphSimulation.cpp:574-880
  *   SphLeapfrogKDK::AdvanceParticles/EndTimestep src/Hydrodynamics/SphLeapfrogKDK.cpp:76-125,226-270
  *   SphIntegration::Timestep                     src/Hydrodynamics/SphIntegration.cpp:76-124
