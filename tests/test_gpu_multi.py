@@ -85,6 +85,22 @@ for workload, NP in (("cloud", 150000), ("glass", 64**3), ("glass+cd2010", 40**3
         nact = tree.Stats().n_active
         tree.close()
         return ps, state, blk
+    def run_stars(world_, rank_, steps, nlevels):
+        # star particles (the reference's default Hermite-4 integrator on the host of every rank, gas-on-star forces
+        # from the replicated tree) with one global step or on block time steps of their own
+        ps = fresh()
+        tree = g.GpuSphTree(dict(params, nbody="hermite4", Nlevels=nlevels), device=lr)
+        drv = domain.DomainDriver(tree, rank_, world_)
+        tree.IntegratorSetStars(np.array([[0.1, 0.05, -0.08], [1.4, -0.3, 0.2]]), np.zeros((2, 3)),
+                                np.array([0.05, 0.1]), np.array([0.05, 0.08]))
+        drv.IntegratorBegin(ps, compute_forces=True)
+        drv.MainLoop(steps)
+        tree.Download(ps)
+        st, state = tree.IntegratorGetStars(), tree.IntegratorState()
+        tree.close()
+        return ps, st, state
+    if workload == "cloud":
+        sres = [run_stars(world, rank, 4, nl) for nl in (1, 4)]
     if workload in ("cloud", "glass"):
         bloop, bstate, bblk = run_block(world, rank, 7)
     loop, lstate = run_loop(world, rank, 3)
@@ -121,6 +137,15 @@ for workload, NP in (("cloud", 150000), ("glass", 64**3), ("glass+cd2010", 40**3
             for f in ("r", "v", "a", "h", "rho", "u", "dudt", "level", "levelneib") + (("atree", "gpot") if grav else ()):
                 assert np.array_equal(bloop[f], sb[f]), (workload, "block", f, np.abs(bloop[f] - sb[f]).max())
             print("multi-GPU block time steps ok:", workload, "levels", np.unique(sb["level"]).tolist(), "n", sbblk["n"])
+        if workload == "cloud":
+            for (mp, mst, mstate), nl in zip(sres, (1, 4)):
+                sp, sst, sstate = run_stars(1, 0, 4, nl)
+                assert mstate == sstate, (nl, mstate, sstate)
+                for k in sst:
+                    assert np.array_equal(mst[k], sst[k]), ("stars", nl, k)
+                for f in ("r", "v", "a", "h", "rho", "atree", "gpot"):
+                    assert np.array_equal(mp[f], sp[f]), ("stars", nl, f)
+            print("multi-GPU star particles ok (hermite4, Nlevels 1 and 4)")
         print("multi-GPU parity ok:", workload, N, "particles, world", world)
 dist.barrier()
 """
