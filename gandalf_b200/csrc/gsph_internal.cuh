@@ -212,6 +212,7 @@ struct gsph_handle {
   int32_t* cand = nullptr; size_t cand_cap_per_warp = 0; int cand_warps = 0;
   int32_t* nlist = nullptr; size_t nlist_cap = 0; int nlist_warps = 0;   /* per warp: [cap][32] neighbour ids */
   void* gravlist = nullptr; size_t gravlist_bytes = 0;   /* interaction lists of the decoupled gravity pass (two batches) */
+  size_t gravlist_budget = 0;   /* bytes the gravity lists may take (decided once: cudaMemGetInfo is not free) */
   cudaStream_t aux_stream = nullptr;                      /* the walk kernels of the decoupled gravity pass */
   cudaEvent_t ev_grav[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   /* walked[2], consumed[2], fork */
   bool gstack_on = false;        /* this launch is a retry with the stacks in HBM */
