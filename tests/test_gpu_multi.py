@@ -62,10 +62,10 @@ for workload, NP in (("cloud", 150000), ("glass", 64**3), ("glass+cd2010", 40**3
         drv.Download(ps, mask=2, only=("a", "dudt", "div_v", "levelneib") + (("atree", "gpot") if grav else ()), gather=True)
         tree.Synchronize(); tree.close()
         return ps, lo, hi
-    def run_loop(world_, rank_, steps):
+    def run_loop(world_, rank_, steps, **extra):
         # device-resident main loop: replicated integrator state, sharded passes (DomainDriver.MainLoop)
         ps = fresh()
-        tree = g.GpuSphTree(params, device=lr)
+        tree = g.GpuSphTree(dict(params, **extra), device=lr)
         drv = domain.DomainDriver(tree, rank_, world_)
         drv.IntegratorBegin(ps, compute_forces=True)
         drv.MainLoop(steps)
@@ -101,6 +101,8 @@ for workload, NP in (("cloud", 150000), ("glass", 64**3), ("glass+cd2010", 40**3
         return ps, st, state
     if workload == "cloud":
         sres = [run_stars(world, rank, 4, nl) for nl in (1, 4)]
+        # rebuild / restock / extrapolate schedule of HydroTree::BuildTree across the ranks (only rebuilds are sharded)
+        mixloop, mixstate = run_loop(world, rank, 6, ntreebuildstep=3, ntreestockstep=2)
     if workload in ("cloud", "glass"):
         bloop, bstate, bblk = run_block(world, rank, 7)
     loop, lstate = run_loop(world, rank, 3)
@@ -146,6 +148,10 @@ for workload, NP in (("cloud", 150000), ("glass", 64**3), ("glass+cd2010", 40**3
                 for f in ("r", "v", "a", "h", "rho", "atree", "gpot"):
                     assert np.array_equal(mp[f], sp[f]), ("stars", nl, f)
             print("multi-GPU star particles ok (hermite4, Nlevels 1 and 4)")
+            smix, smixstate = run_loop(1, 0, 6, ntreebuildstep=3, ntreestockstep=2)
+            assert mixstate == smixstate, (mixstate, smixstate)
+            for f in ("r", "v", "a", "h", "rho", "atree", "gpot"):
+                assert np.array_equal(mixloop[f], smix[f]), ("tree schedule", f)
         print("multi-GPU parity ok:", workload, N, "particles, world", world)
 dist.barrier()
 """
