@@ -77,7 +77,7 @@ class IntegratorConfig(C.Structure):
     _fields_ = [("accel_mult", C.c_double), ("courant_mult", C.c_double), ("energy_mult", C.c_double),
                 ("energy_integration", C.c_int32), ("ntreebuildstep", C.c_int32), ("ntreestockstep", C.c_int32),
                 ("sink_particles", C.c_int32), ("Nlevels", C.c_int32), ("level_diff_max", C.c_int32),
-                ("reserved", C.c_int32 * 2)]
+                ("sph_single_timestep", C.c_int32), ("reserved", C.c_int32 * 1)]
 
 
 class BlockState(C.Structure):

@@ -513,8 +513,10 @@ __global__ void blk_check_kernel(int N, DevPtrs H, BlkPtrs B, int n, int level_s
 template <int NDIM>
 __global__ void blk_timestep_kernel(int N, DevPtrs H, BlkPtrs B, DevParams dp, gsph_integrator_config ic, int mode, int n,
                                     int level_step, int level_max, double dt_max, double timestep, int op, int nfactor,
-                                    unsigned long long* red)
+                                    unsigned long long* red, int single_level)
 {
+  /* single_level >= 0: sph_single_timestep = 1, the level every gas particle that starts a step now is put on
+     (level_max_hydro; Simulation.cpp:1889-1902, 2092-2099) */
   const int i = blockIdx.x*blockDim.x + threadIdx.x;
   const int ldm = ic.level_diff_max > 0 ? ic.level_diff_max : 1;
   bool bad = false;
@@ -530,6 +532,7 @@ __global__ void blk_timestep_kernel(int N, DevPtrs H, BlkPtrs B, DevParams dp, g
     else if (mode == 1) {
       int level = timestep_level(B.dt_next[i], dt_max);
       if (level > level_max) level = level_max;
+      if (single_level >= 0) level = single_level;
       H.i[I_LEVEL][i] = level; H.i[I_LEVELNEIB][i] = level;
       const int ns = pow2int(level_step - level);
       B.nstep[i] = ns; B.nlast[i] = n;
@@ -567,7 +570,10 @@ __global__ void blk_timestep_kernel(int N, DevPtrs H, BlkPtrs B, DevParams dp, g
       int ns = B.nstep[i], nl = B.nlast[i];
       if (op == 1) { ns *= nfactor; nl *= nfactor; }
       else if (op == 2) { ns /= nfactor; nl /= nfactor; }
-      if (nl == n) ns = pow2int(level_step - H.i[I_LEVEL][i]);
+      if (nl == n) {
+        if (single_level >= 0) H.i[I_LEVEL][i] = single_level;
+        ns = pow2int(level_step - H.i[I_LEVEL][i]);
+      }
       B.nstep[i] = ns; B.nlast[i] = nl;
     }
   }
@@ -1878,13 +1884,14 @@ static inline int timestep_level_host(double dt, double dt_max)
 
 #define BLK_LAUNCH(MODE, OP, NFACTOR)                                                                        \
   INTEG_LAUNCH(blk_timestep_kernel, (int) h->N, devptrs(h->H, h->HI), blk_ptrs(h), h->dp, I.cfg, MODE, (int) I.n, I.level_step, \
-               I.level_max, I.dt_max, I.timestep, OP, NFACTOR, I.red)
+               I.level_max, I.dt_max, I.timestep, OP, NFACTOR, I.red, single_level)
 
 static int blk_compute_timesteps(gsph_handle* h)
 {
   IntegState& I = h->integ;
   const unsigned long long init[3] = {0x7ff0000000000000ull, 0ull, 0ull};
   unsigned long long res[3];
+  int single_level = -1;                                  /* sph_single_timestep: set below where the level is known */
   CUDA_TRY(h, cudaMemcpyAsync(I.red, init, sizeof init, cudaMemcpyHostToDevice, h->stream));
   if (I.n == I.nresync) {                                 /* synchronise every step and rebuild the hierarchy */
     I.n = 0;
@@ -1899,9 +1906,10 @@ static int blk_compute_timesteps(gsph_handle* h)
     I.level_max = I.cfg.Nlevels - 1;
     I.level_step = I.level_max;                            /* + integration_step - 1, = 0 for the KDK leapfrog */
     I.dt_max = I.timestep*pow(2.0, I.level_max);
+    const int lmh = std::min(timestep_level_host(ts, I.dt_max), I.level_max);     /* level_max_hydro */
+    if (I.cfg.sph_single_timestep) single_level = lmh;
     if (I.nstar > 0) {
       /* the stars sit at least on the deepest level the gas occupies (Simulation.cpp:1858-1872) */
-      const int lmh = std::min(timestep_level_host(ts, I.dt_max), I.level_max);
       for (int s = 0; s < I.nstar; s++) {
         I.slevel[s] = std::max(std::min(timestep_level_host(sdt[s], I.dt_max), I.level_max), lmh);
         I.snlast[s] = I.n; I.snstep[s] = pow2int(I.level_step - (int) I.slevel[s]); I.stlast[s] = I.t; I.send[s] = 1;
@@ -1918,6 +1926,7 @@ static int blk_compute_timesteps(gsph_handle* h)
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     if (res[1]) { h->err = "Error : Hydro timestep too large"; return GSPH_ESTATE; }
     I.level_max = (int) res[2];
+    if (I.cfg.sph_single_timestep) single_level = I.level_max;    /* level_max_hydro of this step */
     if (I.nstar > 0) {                                     /* the stars at the end of their step (Simulation.cpp:2024-2068) */
       const int lmh = I.level_max;                         /* level_max_hydro */
       for (int s = 0; s < I.nstar; s++) {

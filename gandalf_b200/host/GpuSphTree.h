@@ -273,9 +273,8 @@ class GpuSphTree : public GradhSphTree<ndim, GradhSphParticle>
     if (sp["sph_integration"] != "lfkdk" || ip["Nlevels"] < 1)
       ExceptionHandler::getIstance().raise("GpuSphTree: the device-resident main loop needs sph_integration = lfkdk");
     // hierarchical block time steps (Nlevels > 1): the device loop starts with a resynchronisation of the hierarchy like
-    // PostInitialConditionsSetup, so begin there (or at a step with n == nresync); the single-step switch is not built
-    if (ip["Nlevels"] > 1 && ip["sph_single_timestep"] != 0)
-      ExceptionHandler::getIstance().raise("GpuSphTree: sph_single_timestep with Nlevels > 1 is not on the accelerated path");
+    // PostInitialConditionsSetup, so begin there (or at a step with n == nresync)
+
     // MainLoop's sink search / accretion / stellar-property update (SphSimulation.cpp:815-833) is not on this path
     if (ip["sink_particles"] != 0 || ip["create_sinks"] != 0)
       ExceptionHandler::getIstance().raise("GpuSphTree: sink_particles / create_sinks are not on the accelerated path of the device-resident main loop");
@@ -286,6 +285,7 @@ class GpuSphTree : public GradhSphTree<ndim, GradhSphParticle>
     ic.ntreebuildstep = ip["ntreebuildstep"]; ic.ntreestockstep = ip["ntreestockstep"];
     ic.sink_particles = ip["sink_particles"];
     ic.Nlevels = ip["Nlevels"]; ic.level_diff_max = ip["level_diff_max"];
+    ic.sph_single_timestep = ip["sph_single_timestep"] != 0 ? 1 : 0;
     resident_levels = ic.Nlevels; resident_energy = ic.energy_integration != 0;
     check(gsph_set_stars(handle, NULL, 0));
     upload(sph);

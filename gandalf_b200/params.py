@@ -73,8 +73,6 @@ def integrator_config_from_params(p):
         raise ValueError("sph_integration = %s is not on the accelerated path (lfkdk only)" % q["sph_integration"])
     if int(q["Nlevels"]) < 1:
         raise ValueError("Nlevels must be >= 1")
-    if int(q["Nlevels"]) > 1 and int(q["sph_single_timestep"]) != 0:
-        raise ValueError("sph_single_timestep = 1 is not on the accelerated path of the device-resident main loop")
     if int(q["sink_particles"]) != 0 or int(q["create_sinks"]) != 0:
         # MainLoop would run SearchForNewSinkParticles / AccreteMassToSinks / UpdateStellarProperties
         # (SphSimulation.cpp:815-833): not on the accelerated path
@@ -88,6 +86,7 @@ def integrator_config_from_params(p):
     c.sink_particles = int(q["sink_particles"])
     c.Nlevels = int(q["Nlevels"])
     c.level_diff_max = int(q["level_diff_max"])
+    c.sph_single_timestep = 1 if int(q["sph_single_timestep"]) != 0 else 0
     return c
 
 

@@ -343,8 +343,8 @@ int gsph_get_stats(gsph_handle* h, gsph_stats* st);
  *   the thermal refresh of every particle before the force pass (nradstep = 1, SphSimulation.cpp:669-679).
  * gsph_integrator_begin then sets up the hierarchy like PostInitialConditionsSetup (a resynchronisation at n = 0).
  * Star particles: gsph_integrator_set_stars / _set_stars_hermite4 below, with one global time step or on block time
- * steps of their own.  Not covered (GSPH_EINVAL): sinks, external potentials, dust, sph_single_timestep, block time
- * steps together with mirror walls.                                                                              */
+ * steps of their own.  Not covered (GSPH_EINVAL): sinks, external potentials, dust, block time steps together with
+ * mirror walls.                                                                              */
 typedef struct gsph_integrator_config {
   double  accel_mult, courant_mult, energy_mult;   /* Parameters.cpp:239,240,263 (0.3, 0.15, 0.4)      */
   int32_t energy_integration;   /* 1: u is integrated explicitly (gas_eos = energy_eqn,
@@ -357,7 +357,9 @@ typedef struct gsph_integrator_config {
                                    (Simulation::ComputeBlockTimesteps, Simulation.cpp:1764-2199)                   */
   int32_t level_diff_max;       /* largest level difference between neighbours (Parameters.cpp:245, 1);
                                    0 is read as the default 1                                                     */
-  int32_t reserved[2];
+  int32_t sph_single_timestep;  /* Parameters.cpp:246: with Nlevels > 1 every gas particle runs on the deepest level the gas
+                                   needs (star particles may sit below it); Simulation.cpp:1889-1902, 2092-2099            */
+  int32_t reserved[1];
 } gsph_integrator_config;
 
 /* Start from the particles of the last gsph_upload (host order is kept).

@@ -22,7 +22,9 @@ from conftest import load_golden, stage  # noqa: E402
 from make_loop_golden import BASE  # noqa: E402
 
 CASES = {"adsod": (20, 4), "box3d_mm97": (20, 4), "sphere_grav_fastmono": (20, 4), "adsod+cd2010": (20, 4),
-         "sphere_grav_stars+hermite4": (20, 4), "sphere_grav_stars+lfkdk": (20, 4)}   # star particles on their own levels       # name -> (steps, Nlevels)
+         "sphere_grav_stars+hermite4": (20, 4), "sphere_grav_stars+lfkdk": (20, 4),   # star particles on their own levels
+         # sph_single_timestep = 1: every gas particle on the deepest gas level, the stars below it
+         "sphere_grav_stars+hermite4+single": (20, 4), "adsod+single": (12, 4)}       # name -> (steps, Nlevels)
 FIELDS = ["r", "v", "a", "atree", "m", "h", "u", "rho", "invomega", "zeta", "hfactor", "hrangesqd", "sound", "pressure",
           "alpha", "dalphadt", "dudt", "div_v", "gpot", "ptype", "level", "levelneib", "nstep", "nlast", "dt", "dt_next",
           "tlast", "r0", "v0", "a0", "u0", "dudt0"]
@@ -35,9 +37,13 @@ def main():
         params, d = load_golden(name.split("+")[0])
         p = dict(BASE)
         p.update(params)
-        if name.endswith(("+hermite4", "+lfkdk")):          # the N-body integrator of the three stars of that golden
-            p["nbody"] = name.split("+")[1]
-        if name.endswith("+cd2010"):                         # the Cullen & Dehnen switch on the same initial conditions
+        opts = name.split("+")[1:]
+        for o in opts:
+            if o in ("hermite4", "lfkdk"):                   # the N-body integrator of the three stars of that golden
+                p["nbody"] = o
+            if o == "single":
+                p["sph_single_timestep"] = 1
+        if "cd2010" in opts:                         # the Cullen & Dehnen switch on the same initial conditions
             p.update(time_dependent_avisc="cd2010", alpha_visc_min=0.1)
         p.update({k: BASE[k] for k in ("run_id", "ic", "Nstepsmax", "tend", "neib_search")})
         p["Nlevels"] = nlev

@@ -642,6 +642,7 @@ def mainloop_block(params, setup, sim, steps, trace=None):
     tdav = params.get("time_dependent_avisc", "none") != "none"
     Nlevels = int(params["Nlevels"])
     ldm = int(params.get("level_diff_max", 1))
+    single = int(params.get("sph_single_timestep", 0)) == 1      # every gas particle on the deepest gas level
     s = {k: np.array(v, copy=True) for k, v in setup.items()}
     N = len(s["m"])
     for k in ("r", "v", "a", "atree", "r0", "v0", "a0"):
@@ -803,6 +804,8 @@ def mainloop_block(params, setup, sim, steps, trace=None):
                 S["nlast"][:] = n; S["nstep"] = _pow2int(level_step - S["level"]); S["tlast"][:] = t
                 S["end"][:] = True
             lev = np.minimum(timestep_level(ts, dt_max), level_max)
+            if single:                                      # Simulation.cpp:1889-1902
+                lev = np.full(N, min(int(timestep_level(np.array([float(ts.min())]), dt_max)[0]), level_max), dtype=np.int64)
             s["level"] = lev; s["levelneib"] = lev.copy()
             s["nstep"] = _pow2int(level_step - lev)
             s["nlast"] = np.full(N, n, dtype=np.int64)
@@ -832,6 +835,8 @@ def mainloop_block(params, setup, sim, steps, trace=None):
             s["dt_next"] = np.where(atend, s["nstep"]*timestep, s["dt_next"])
             end_ts |= atend
             level_max = int(s["level"].max())
+            if single:                                      # Simulation.cpp:2092-2099 (before the integer time is rescaled)
+                s["level"] = np.where(s["nlast"] == n, level_max, s["level"])
             if stars:
                 lmh = level_max                                 # level_max_hydro
                 for i in range(ns):

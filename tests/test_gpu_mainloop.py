@@ -164,7 +164,7 @@ def test_device_mainloop_errors_are_loud():
     with pytest.raises(g.GsphError):
         tree2.IntegratorBegin(compute_forces=False)        # stars are not integrated on the device
     with pytest.raises(ValueError):
-        g.GpuSphTree(dict(params, Nlevels=2, sph_single_timestep=1)).IntegratorBegin(ps)
+        g.GpuSphTree(dict(params, sink_particles=1)).IntegratorBegin(ps)   # no sink search / accretion on this path
     tree.close(); tree2.close()
 
 

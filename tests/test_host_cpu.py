@@ -333,12 +333,13 @@ def test_defaults_equal_the_reference():
 
 
 def test_device_loop_rejects_what_it_does_not_run():
-    """the device-resident main loop has no sink search / accretion, block time steps or Hermite stars:
+    """the device-resident main loop has no sink search / accretion and only the lfkdk gas integrator:
     parameter sets that ask for them are refused instead of silently running something else"""
     from gandalf_b200.params import integrator_config_from_params
     c = integrator_config_from_params({"ndim": 3})
     assert c.sink_particles == 0 and c.ntreebuildstep == 1
     assert integrator_config_from_params({"ndim": 3, "Nlevels": 5}).Nlevels == 5          # block time steps are on the path
-    for bad in ({"sink_particles": 1}, {"create_sinks": 1}, {"Nlevels": 5, "sph_single_timestep": 1}, {"sph_integration": "lfdkd"}):
+    assert integrator_config_from_params({"Nlevels": 5, "sph_single_timestep": 1}).sph_single_timestep == 1
+    for bad in ({"sink_particles": 1}, {"create_sinks": 1}, {"sph_integration": "lfdkd"}):
         with pytest.raises(ValueError):
             integrator_config_from_params(dict({"ndim": 3}, **bad))

@@ -127,9 +127,10 @@ def test_block_timestep_restatement_matches_reference(name):
     sizes for every particle -- through added and removed levels and a resynchronisation -- and the same state"""
     params, d = load_golden(name)
     setup, sim0, loop, sim1 = split_blk(d)
-    assert int(params["Nlevels"]) > 1 and len(np.unique(loop["level"])) >= 3
+    single = int(params.get("sph_single_timestep", 0)) == 1    # (then the gas shares ONE level by construction)
+    assert int(params["Nlevels"]) > 1 and (len(np.unique(loop["level"])) >= 3 or single)
     steps = int(d["loop.steps"])
-    if name != "loopblk_adsod":
+    if not name.startswith("loopblk_adsod"):
         steps = 20                     # (kept: about 10 s each)
     s, sim = orc.mainloop_block(params, setup, sim0, steps)
     check_block_state(s, sim, loop, sim1, 1e-9)
