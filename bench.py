@@ -378,13 +378,15 @@ def main_ours(args, rank, world, local_rank):
     # density (d+2)s+8 in + 9s out; forces (2d+11)s+20 in + (d+3)s+4 out (+ (d+2)s with gravity); s = 8
     balg = {"density": (ndim + 2)*8.0 + 8 + 72, "hydro": (2*ndim + 11)*8.0 + 20 + (ndim + 3)*8 + 4 + ((ndim + 2)*8 if grav else 0),
             "gravity": 180.0}
-    # dram__bytes_read+write per particle from the committed ncu --set full capture
-    # (profiles/r2_ncu_full_cloud16m_summary.txt, 16 Mi-particle cloud), scaled to this launch.  Every entry is the
+    # dram__bytes_read+write per particle from the committed ncu --set full capture of the final code
+    # (profiles/r2_ncu_full_cloud16m_final_batches.txt, 16 Mi-particle cloud), scaled to this launch.  Every entry is the
     # whole pass: the pre-walk kernel + the main kernel for density / hydro; for gravity the walk, cells and direct
-    # kernels of all 8 batches of that capture (their interaction lists travel through HBM: 1.1 kB per particle).
-    traffic_pp = {"gravity": 8*(0.130669e9 + 0.745548e9 + 0.967395e9 + 0.109266e9 + 0.334866e9 + 0.113022e9)/16777216.0,
-                  "hydro": (8.889473e9 + 1.854152e9 + 0.657025e9 + 1.546707e9)/16777216.0,
-                  "density": (3.678281e9 + 3.143197e9 + 0.375205e9 + 1.619119e9)/16777216.0}
+    # kernels of the three batches of that capture (their interaction lists travel through HBM: 1.2 kB per particle).
+    traffic_pp = {"gravity": ((0.343695 + 2.074097 + 0.362384 + 2.087211 + 0.345232 + 2.072511) +
+                              (2.576733 + 0.304952 + 2.597583 + 0.305182 + 2.574433 + 0.304954) +
+                              (0.890114 + 0.337520 + 0.908109 + 0.339224 + 0.892161 + 0.337667))*1e9/16777216.0,
+                  "hydro": (8.880299e9 + 1.848491e9 + 0.657022e9 + 1.546330e9)/16777216.0,
+                  "density": (3.672362e9 + 3.160585e9 + 0.375668e9 + 1.619185e9)/16777216.0}
     kernel_names = {"gravity": "gravity_walk_kernel + gravity_cells_kernel + gravity_direct_kernel",
                     "hydro": "hydro_walk_kernel + hydro_kernel", "density": "density_walk_kernel + density_kernel"}
     dom = max(kms, key=lambda k: kms[k])
