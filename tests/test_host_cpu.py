@@ -343,3 +343,25 @@ def test_device_loop_rejects_what_it_does_not_run():
     for bad in ({"sink_particles": 1}, {"create_sinks": 1}, {"sph_integration": "lfdkd"}):
         with pytest.raises(ValueError):
             integrator_config_from_params(dict({"ndim": 3}, **bad))
+
+
+def test_config_workloads_have_the_named_shapes():
+    """the synthetic particle sets of BASELINE configurations 2 and 3 (gandalf_b200/workloads.py), generated on the CPU
+    at a reduced size: KHI = two lattices of densities 1 and 2 with equal particle mass in a periodic unit square,
+    bossbodenheimer = unit-mass sphere in solid-body rotation with an m = 2 mass perturbation"""
+    from gandalf_b200 import workloads
+    p, ic = workloads.khi(60000, device="cpu")
+    r, m, v = ic["r"].numpy(), ic["m"].numpy(), ic["v"].numpy()
+    assert p["ndim"] == 2 and p["kernel"] == "quintic" and p["Nleafmax"] == 12 and p["acond"] == "wadsley2008"
+    assert r.shape[0] == 2 and np.abs(r).max() < 0.5 and abs(m.sum() - 1.5) < 1e-12          # 0.5*1 + 0.5*2
+    inner = np.abs(r[1]) < 0.25
+    assert abs(m[inner].sum() - 1.0) < 1e-12 and np.allclose(m[inner], m[inner][0]) and np.all(v[0][inner] == 0.5)
+    assert np.all(v[0][~inner] == -0.5) and len(np.unique(np.round(r.T, 12), axis=0)) == r.shape[1]
+    p, ic = workloads.bossbodenheimer(20000, device="cpu")
+    r, m, v = ic["r"].numpy(), ic["m"].numpy(), ic["v"].numpy()
+    assert p["gas_eos"] == "barotropic" and p["multipole"] == "fast_monopole" and p["Nleafmax"] == 6 and p["self_gravity"] == 1
+    assert r.shape == (3, 20000) and (r*r).sum(0).max() < 1.0 and abs(m.sum() - 1.0) < 1e-12
+    phi = np.arctan2(r[1], r[0])
+    assert np.corrcoef(m, np.cos(2*phi))[0, 1] > 0.99                                       # the m = 2 mode
+    omega = (r[0]*v[1] - r[1]*v[0])/(r[0]**2 + r[1]**2)
+    assert np.allclose(omega, omega[0]) and np.all(v[2] == 0)                               # solid-body rotation about z
