@@ -2126,7 +2126,6 @@ int gsph_integrator_begin(gsph_handle* h, const gsph_integrator_config* cfg, int
   }
   if (!I.red) CUDA_TRY(h, cudaMalloc(&I.red, 4*sizeof(unsigned long long)));
   if (cfg->Nlevels > 1) {
-    if (h->dp.any_mirror) { h->err = "gsph_integrator_begin: block time steps with mirror boundaries are not on the accelerated path"; return GSPH_EINVAL; }
     if (cfg->Nlevels > 30) { h->err = "gsph_integrator_begin: Nlevels must be <= 30"; return GSPH_EINVAL; }
     if (I.blk_cap < h->Ncap) {
       auto fre = [](void* p) { if (p) cudaFree(p); };

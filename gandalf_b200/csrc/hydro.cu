@@ -356,7 +356,7 @@ hydro_walk_kernel(TreeDev tree, DevParams dp, int cohort_level, int c0, int nc, 
  *           lane reads its own record, applies the reference's predicate (NeighbourManager.h:521)
  *           in exact FP64 arithmetic and evaluates the pair terms.
  *-----------------------------------------------------------------------------------------------*/
-template <int NDIM, int KERN, bool TAB, bool GRAV, bool HYDRO, bool MIRROR>
+template <int NDIM, int KERN, bool TAB, bool GRAV, bool HYDRO, bool MIRROR, bool SCATTER>
 __global__ void __launch_bounds__(HYD_THREADS, 2)
 hydro_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict__ gtables,
              const double2* __restrict__ frec, const double2* __restrict__ geoh, int aux_is_alpha,
@@ -584,6 +584,10 @@ hydro_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict__ 
             else nb.level = (int) r7.y;
             if (price) nb.press = P.f[F_PRESS][jpart];
             pair_terms<NDIM, GRAV, HYDRO>(dp, K, g, dr, drsqd, nb);
+            /* levelneib scatter half (GradhSph.cpp:446, GradhSphTree.cpp:376-382; a mirror image hands it to its
+               original): only instantiated for steps with inactive particles -- with every particle active the
+               relation is symmetric and the gather above already produces the maximum */
+            if (SCATTER && (HYDRO || !GRAV) && P.i[I_LEVELNEIB][jpart] < g.level) atomicMax(&P.i[I_LEVELNEIB][jpart], g.level);
           }
         }
         __syncwarp();
@@ -719,14 +723,17 @@ neib_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* work_
   }
 }
 
-template <int NDIM, int KERN, bool TAB, bool GRAV, bool HYDRO, bool MIRROR>
+template <int NDIM, int KERN, bool TAB, bool GRAV, bool HYDRO, bool MIRROR, bool SCATTER = false>
 int launch_hydro_m(gsph_handle* h)
 {
+  if constexpr (!SCATTER) {
+    if (!h->all_active) return launch_hydro_m<NDIM, KERN, TAB, GRAV, HYDRO, MIRROR, true>(h);
+  }
   const int Lc = cohort_level_for(h->N, h->tree.ltot, 32);
   constexpr int NTAB = TAB ? (GRAV ? 3 : 1) : 0;
   static_assert(2*32*REC_STRIDE*sizeof(double2) >= NB_WALK_STACK*sizeof(int), "walk stack must fit the stage region");
   const size_t smem = NTAB*GSPH_TABLE_RES*sizeof(double) + HYD_WARPS*2*32*REC_STRIDE*sizeof(double2);
-  auto kern = hydro_kernel<NDIM, KERN, TAB, GRAV, HYDRO, MIRROR>;
+  auto kern = hydro_kernel<NDIM, KERN, TAB, GRAV, HYDRO, MIRROR, SCATTER>;
   CUDA_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
   int bps = 0;
   CUDA_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, HYD_THREADS, smem));
@@ -849,12 +856,9 @@ int dispatch_hydro(gsph_handle* h, int with_gravity)
     rc = tab ? dispatch_mode<NDIM, GSPH_KERNEL_QUINTIC, true>(h, with_gravity)
              : dispatch_mode<NDIM, GSPH_KERNEL_QUINTIC, false>(h, with_gravity);
   if (rc) return rc;
-  /* (with an active slice the scatter of this device's targets lands on particles of every slice: the host
-     layer combines the devices' levelneib arrays with a MAX reduction instead of gathering slices) */
-  if (!h->all_active && (h->dp.hydro_forces || !with_gravity)) {
-    if (h->dp.any_mirror) { h->err = "inactive particles (block time steps) with mirror boundaries are not on the accelerated path"; return GSPH_EINVAL; }
-    rc = launch_neib<NDIM, 2>(h, nullptr, nullptr, nullptr);
-  }
+  /* (the levelneib scatter half of steps with inactive particles happens inside hydro_kernel<..., SCATTER>; with an
+     active slice the scatter of this device's targets lands on particles of every slice: the host layer combines
+     the devices' levelneib arrays with a MAX reduction instead of gathering slices) */
   return rc;
 }
 

@@ -343,8 +343,7 @@ int gsph_get_stats(gsph_handle* h, gsph_stats* st);
  *   the thermal refresh of every particle before the force pass (nradstep = 1, SphSimulation.cpp:669-679).
  * gsph_integrator_begin then sets up the hierarchy like PostInitialConditionsSetup (a resynchronisation at n = 0).
  * Star particles: gsph_integrator_set_stars / _set_stars_hermite4 below, with one global time step or on block time
- * steps of their own.  Not covered (GSPH_EINVAL): sinks, external potentials, dust, block time steps together with
- * mirror walls.                                                                              */
+ * steps of their own.  Not covered (GSPH_EINVAL): sinks, external potentials, dust.                                                                              */
 typedef struct gsph_integrator_config {
   double  accel_mult, courant_mult, energy_mult;   /* Parameters.cpp:239,240,263 (0.3, 0.15, 0.4)      */
   int32_t energy_integration;   /* 1: u is integrated explicitly (gas_eos = energy_eqn,

@@ -2,4 +2,4 @@
 tag=${1:-x1}
 out=gpurun_out/$tag
 mkdir -p $out
-echo "== launch list (default command, 64M)"; timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $out/launches64m.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-resident > $out/launches64m.log 2>&1; wc -l $out/launches64m.csv
+echo "== pytest"; timeout 1500 python -m pytest tests/test_gpu_mainloop.py -m gpu -x -q -k "block" 2>&1 | tail -25 | cut -c1-250 | tee $out/pytest.txt

@@ -24,7 +24,8 @@ from make_loop_golden import BASE  # noqa: E402
 CASES = {"adsod": (20, 4), "box3d_mm97": (20, 4), "sphere_grav_fastmono": (20, 4), "adsod+cd2010": (20, 4),
          "sphere_grav_stars+hermite4": (20, 4), "sphere_grav_stars+lfkdk": (20, 4),   # star particles on their own levels
          # sph_single_timestep = 1: every gas particle on the deepest gas level, the stars below it
-         "sphere_grav_stars+hermite4+single": (20, 4), "adsod+single": (12, 4)}       # name -> (steps, Nlevels)
+         "sphere_grav_stars+hermite4+single": (20, 4), "adsod+single": (12, 4),
+         "box3d_mirror": (20, 4)}                              # three mirror walls: images raise levelneib of their originals       # name -> (steps, Nlevels)
 FIELDS = ["r", "v", "a", "atree", "m", "h", "u", "rho", "invomega", "zeta", "hfactor", "hrangesqd", "sound", "pressure",
           "alpha", "dalphadt", "dudt", "div_v", "gpot", "ptype", "level", "levelneib", "nstep", "nlast", "dt", "dt_next",
           "tlast", "r0", "v0", "a0", "u0", "dudt0"]

@@ -743,13 +743,26 @@ def mainloop_block(params, setup, sim, steps, trace=None):
                 S["v"] = S["v0"] + S["a0"]*sdt + 0.5*S["adot0"]*sdt*sdt
             sact = (n - S["nlast"]) == S["nstep"]
             rows = np.concatenate([S["r"], S["m"][:, None], S["h"][:, None]], axis=1)
-        # ---- CheckBoundaries (periodic wrap only here)
+        # ---- CheckBoundaries (Integration.cpp:11-75): periodic wrap, mirror reflection
         for k in range(nd):
+            walls = dict((side, w) for (kk, w), side in zip(getattr(p, "mirrors", []),
+                                                           getattr(p, "mirror_sides", [])) if kk == k)
+            lo = s["r"][:, k] < p.boxmin[k]
             if p.periodic[k]:
-                lo = s["r"][:, k] < p.boxmin[k]
                 s["r"][lo, k] += size[k]; s["r0"][lo, k] += size[k]
-                hi = s["r"][:, k] > p.boxmax[k]
+            if "lhs" in walls:
+                for arr in (s["r"], s["r0"]):
+                    arr[lo, k] = 2.0*p.boxmin[k] - arr[lo, k]
+                for arr in (s["v"], s["v0"], s["a"], s["a0"]):
+                    arr[lo, k] = -arr[lo, k]
+            hi = s["r"][:, k] > p.boxmax[k]
+            if p.periodic[k]:
                 s["r"][hi, k] -= size[k]; s["r0"][hi, k] -= size[k]
+            if "rhs" in walls:
+                for arr in (s["r"], s["r0"]):
+                    arr[hi, k] = 2.0*p.boxmax[k] - arr[hi, k]
+                for arr in (s["v"], s["v0"], s["a"], s["a0"]):
+                    arr[hi, k] = -arr[hi, k]
         # ---- passes, repeated while CheckTimesteps activates more particles
         nredo = 0
         tr = Tree(p, s["r"], s["v"], s["m"], s["h"], s["atree"], s["gpot"]) if p.self_gravity else None
