@@ -49,6 +49,8 @@ class GpuSphTree : public GradhSphTree<ndim, GradhSphParticle>
   bool staged;                ///< device copy matches the host array of this step
   int resident_levels = 1;    ///< Nlevels of the device-resident loop started by ResidentBegin
   bool resident_energy = true; ///< ... and whether it integrates u (SphLeapfrogKDK touches u0, dudt0 only then)
+  int resident_stars = 0;     ///< star particles handed to the device loop
+  bool resident_h4 = false;   ///< ... integrated with NbodyHermite4
 
   static int lookup(const std::string& v, const char* const* names, int n, const char* what) {
     for (int i = 0; i < n; i++) if (v == names[i]) return i;
@@ -265,7 +267,11 @@ class GpuSphTree : public GradhSphTree<ndim, GradhSphParticle>
   //-----------------------------------------------------------------------------------------------
   /// Call after PostInitialConditionsSetup (or any completed MainLoop): ships the complete particle
   /// state and starts the device loop at simulation time t.
-  void ResidentBegin(Sph<ndim>* sph, Parameters* params, const double t)
+  void ResidentBegin(Sph<ndim>* sph, Parameters* params, const double t) { ResidentBegin(sph, NULL, params, t); }
+
+  /// ... with the star particles of `nbody` (nbody = lfkdk or the default hermite4, nbody_softening = 1, open
+  /// boundaries): their integrator runs inside the device loop (host side of libgsph, around the gas-on-star pass).
+  void ResidentBegin(Sph<ndim>* sph, Nbody<ndim>* nbody, Parameters* params, const double t)
   {
     std::map<std::string, int>& ip = params->intparams;
     std::map<std::string, double>& fp = params->floatparams;
@@ -288,6 +294,28 @@ class GpuSphTree : public GradhSphTree<ndim, GradhSphParticle>
     ic.sph_single_timestep = ip["sph_single_timestep"] != 0 ? 1 : 0;
     resident_levels = ic.Nlevels; resident_energy = ic.energy_integration != 0;
     check(gsph_set_stars(handle, NULL, 0));
+    resident_stars = 0;
+    if (nbody != NULL && nbody->Nstar > 0) {
+      const bool h4 = sp["nbody"] == "hermite4";
+      if (!h4 && sp["nbody"] != "lfkdk")
+        ExceptionHandler::getIstance().raise("GpuSphTree: nbody = " + sp["nbody"] + " is not on the accelerated path (lfkdk, hermite4)");
+      if (ic.Nlevels > 1)
+        ExceptionHandler::getIstance().raise("GpuSphTree: the hand-over of star particles on block time steps is not built (start such a run with gsph_integrator_begin)");
+      const int ns = nbody->Nstar, row = (h4 ? 6 : 3)*ndim + 2;
+      std::vector<double> rows((size_t) ns*row);
+      for (int s = 0; s < ns; s++) {
+        const StarParticle<ndim>& st = nbody->stardata[s];
+        double* q = &rows[(size_t) s*row];
+        for (int k = 0; k < ndim; k++) {
+          q[k] = st.r[k]; q[ndim + k] = st.v[k]; q[2*ndim + k] = st.a[k];
+          if (h4) { q[3*ndim + k] = st.adot[k]; q[4*ndim + k] = st.a2dot[k]; q[5*ndim + k] = st.a3dot[k]; }
+        }
+        q[row - 2] = st.m; q[row - 1] = st.h;
+      }
+      check(h4 ? gsph_integrator_set_stars_hermite4(handle, rows.data(), ns, fp["nbody_mult"])
+               : gsph_integrator_set_stars(handle, rows.data(), ns, fp["nbody_mult"]));
+      resident_stars = ns; resident_h4 = h4;
+    }
     upload(sph);
     check(gsph_integrator_begin(handle, &ic, 0, t));
     staged = false;
@@ -301,6 +329,30 @@ class GpuSphTree : public GradhSphTree<ndim, GradhSphParticle>
   /// steps every particle sits somewhere inside its own step: its level, nstep, nlast, dt, dt_next, tlast and the
   /// start-of-step state r0, v0, a0, u0, dudt0 come from the device as they are, and *blk receives the scalars of
   /// the hierarchy (Simulation::n, nresync, level_max, level_step, dt_max).
+  /// ... and the star particles as Nbody*::EndTimestep leaves them (r0 = r, v0 = v, a0 = a, adot0 = adot, tlast = t).
+  void ResidentFetch(Sph<ndim>* sph, Nbody<ndim>* nbody, double* t_out, double* timestep_out, long long* nsteps_out)
+  {
+    double t = 0.0;
+    ResidentFetch(sph, &t, timestep_out, nsteps_out, NULL);
+    if (t_out) *t_out = t;
+    if (nbody == NULL || resident_stars == 0) return;
+    const int ns = resident_stars;
+    std::vector<double> rows((size_t) ns*(3*ndim + 3)), ad((size_t) ns*ndim), a2((size_t) ns*ndim), a3((size_t) ns*ndim);
+    check(gsph_integrator_get_stars(handle, rows.data(), ns));
+    if (resident_h4) check(gsph_integrator_get_star_derivatives(handle, ad.data(), a2.data(), a3.data()));
+    for (int s = 0; s < ns; s++) {
+      StarParticle<ndim>& st = nbody->stardata[s];
+      const double* q = &rows[(size_t) s*(3*ndim + 3)];
+      for (int k = 0; k < ndim; k++) {
+        st.r[k] = st.r0[k] = q[k]; st.v[k] = st.v0[k] = q[ndim + k]; st.a[k] = st.a0[k] = q[2*ndim + k];
+        if (resident_h4) { st.adot[k] = st.adot0[k] = ad[(size_t) s*ndim + k]; st.a2dot[k] = a2[(size_t) s*ndim + k]; st.a3dot[k] = a3[(size_t) s*ndim + k]; }
+      }
+      st.gpot = q[3*ndim + 2];
+      st.level = 0; st.nstep = 1; st.nlast = 0; st.tlast = t; st.dt_next = 0;
+      st.flags.unset(active); st.flags.unset(end_timestep);
+    }
+  }
+
   void ResidentFetch(Sph<ndim>* sph, double* t_out, double* timestep_out, long long* nsteps_out, gsph_block_state* blk = NULL)
   {
     download(sph, GSPH_F_ALL);

@@ -545,11 +545,14 @@ static int run(Parameters* params, const string& icfile, double perturb, const s
       // reference's own MainLoop (gandalf_b200/host/GpuSphTree.h: ResidentBegin / MainLoop / Fetch)
       GpuSphTree<ndim>* gt = static_cast<GpuSphTree<ndim>*>(sim->sphneib);
       const int K = std::min(g_resident, g_mainloop);
-      gt->ResidentBegin(sim->sph, sim->simparams, sim->t);
+      const bool with_stars = sim->nbody->Nstar > 0;
+      if (with_stars) gt->ResidentBegin(sim->sph, sim->nbody, sim->simparams, sim->t);
+      else gt->ResidentBegin(sim->sph, sim->simparams, sim->t);
       gt->ResidentMainLoop(K);
       double tt = 0.0, ts = 0.0; long long ns = 0;
       gsph_block_state bs;
-      gt->ResidentFetch(sim->sph, &tt, &ts, &ns, &bs);
+      if (with_stars) { gt->ResidentFetch(sim->sph, sim->nbody, &tt, &ts, &ns); bs.n = 0; }
+      else gt->ResidentFetch(sim->sph, &tt, &ts, &ns, &bs);
       sim->t = tt; sim->timestep = ts; sim->n = 0;
       if (sim->Nlevels > 1) {                         // the hierarchy of the block time steps as the device left it
         sim->n = (int) bs.n; sim->nresync = (int) bs.nresync; sim->level_max = bs.level_max;

@@ -116,6 +116,34 @@ def test_reference_hands_over_with_block_time_steps(name, steps, resident):
     assert scaled_err(dev["loop.dudt"][og], cpu["loop.dudt"][oc]).max() < tol
 
 
+@pytest.mark.parametrize("nbody", ["hermite4", "lfkdk"])
+def test_reference_hands_over_with_star_particles(nbody):
+    """the hand-over with three star particles: GpuSphTree::ResidentBegin(sph, nbody, ...) ships the stars of the
+    reference's own N-body object (r, v, a and -- Hermite-4 -- adot, a2dot, a3dot), the device loop integrates them
+    with the reference's integrator for 2 steps, ResidentFetch(sph, nbody, ...) restores them as Nbody*::EndTimestep
+    leaves them and the reference's own MainLoop carries on.  Gas and stars == the all-CPU run."""
+    if refio.harness_path("gpu") is None:
+        pytest.skip("oracle/_ref/ref_harness_gpu not built")
+    p, ic = _case("sphere_grav_stars")
+    p = dict(p, nbody=nbody)
+    _, d = load_golden("sphere_grav_stars")
+    cpu, ci = refio.run_mainloop(p, ic, 4, gpu=False, stars=d["stars"])
+    dev, di = refio.run_mainloop(p, ic, 4, gpu=True, resident=2, stars=d["stars"])
+    assert ci["steps"] == di["steps"] == 4
+    # (Hermite-4: the Aarseth step follows the jerk; the reference's gas-on-star jerk is single precision)
+    assert abs(ci["t"] - di["t"]) <= (1e-8 if nbody == "hermite4" else 1e-12)*abs(ci["t"])
+    oc, og = np.argsort(cpu["loop.iorig"]), np.argsort(dev["loop.iorig"])
+    for f in ("r", "v", "a"):
+        a, b = dev["loop." + f][og], cpu["loop." + f][oc]
+        e = np.linalg.norm(a - b, axis=1)/np.maximum(np.linalg.norm(b, axis=1), np.abs(b).max()*1e-6)
+        assert e.max() < 1e-6, (f, e.max())
+    for f in ("h", "rho", "u", "gpot"):
+        assert rel_err(dev["loop." + f][og], cpu["loop." + f][oc]).max() < 1e-6, f
+    for f in ("star_r", "star_v", "star_a"):
+        a, b = dev["loop." + f], cpu["loop." + f]
+        assert np.abs(a - b).max() <= 1e-6*np.abs(b).max(), f
+
+
 def test_reference_mainloop_with_stars_and_gpu_tree():
     """three star particles: the gas feels them (ComputeStarGravForces, star terms of zeta) and they feel
     the gas through GpuSphTree::UpdateAllStarGasForces; the reference's own N-body integrator moves them.
