@@ -634,10 +634,10 @@ hydro_kernel(PartView P, TreeDev tree, DevParams dp, const double* __restrict__ 
   }
 }
 
-/* levelneib scatter half (GradhSph.cpp:446, GradhSphTree.cpp:376-382): only needed when some
- * particles are inactive -- with every particle active the neighbour relation is symmetric and the
- * gather above already produces the maximum.  Also serves the parity API (neighbour counts / lists). */
-template <int NDIM, int MODE /*0 count, 1 fill, 2 levelneib scatter*/>
+/* The parity API: neighbour counts / lists of every particle with the reference's predicate.  (The levelneib scatter
+ * half of steps with inactive particles used to be a third mode of this kernel; it now lives in
+ * hydro_kernel<..., SCATTER>.)                                                                             */
+template <int NDIM, int MODE /*0 count, 1 fill*/>
 __global__ void __launch_bounds__(HYD_THREADS)
 neib_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* work_counter,
             int32_t* cand_all, int cand_cap, DevStatus* st, const int32_t* perm, int32_t* counts,
@@ -661,7 +661,6 @@ neib_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* work_
     const int node = ncohort - 1 + c;
     const int cfirst = tree.first[node], ccount = tree.count[node];
     if (ccount == 0) continue;
-    if (MODE == 2 && (tree.nactive[node] == 0 || GSPH_RANGE_OUTSIDE_SLICE(dp, cfirst, ccount))) continue;
     CandList cl{cand, cand_cap, 0, st};
     ScatterGatherVisitor<NDIM> V{tree, dp, cl, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, {0, 0, 0}, false};
 #pragma unroll
@@ -680,7 +679,6 @@ neib_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* work_
       if (live) {
         const unsigned fl = (unsigned) P.i[I_FLAGS][i];
         if (fl & GSPH_FLAG_DEAD) live = false;
-        if (MODE == 2 && (!(fl & GSPH_FLAG_ACTIVE) || !GSPH_IN_SLICE(dp, i))) live = false;
       }
       if (live) {
 #pragma unroll
@@ -713,7 +711,6 @@ neib_kernel(PartView P, TreeDev tree, DevParams dp, int cohort_level, int* work_
           const double drsqd = dot_exact<NDIM>(dr);
           if (live && (drsqd < hr2 || drsqd < geom[jj*4 + 3])) {
             if (MODE == 1) idx[off + n] = perm[jidx[warp][jj]];
-            if (MODE == 2) atomicMax(&P.i[I_LEVELNEIB][jidx[warp][jj]], lev);
             n++;
           }
         }
