@@ -75,6 +75,35 @@ class ParticleSet(object):
             self.data[k][...] = v
         return self
 
+    # ---- the reference's array names (Simulation::ImportArray, Simulation.cpp:1442-1612; SphSnapshot::ExtractArray,
+    #      SphSnapshot.cpp:529-600): "x" "y" "z" "vx" "vy" "vz" "ax" "ay" "az" "m" "h" "rho" "u" "dudt" "gpot" "iorig"
+    _ARRAY_NAMES = {"x": ("r", 0), "y": ("r", 1), "z": ("r", 2), "vx": ("v", 0), "vy": ("v", 1), "vz": ("v", 2),
+                    "ax": ("a", 0), "ay": ("a", 1), "az": ("a", 2), "m": ("m", None), "h": ("h", None),
+                    "rho": ("rho", None), "u": ("u", None), "dudt": ("dudt", None), "gpot": ("gpot", None),
+                    "iorig": ("iorig", None)}
+
+    def _array(self, name):
+        if name not in self._ARRAY_NAMES:
+            raise ValueError("Warning: the selected array: %s has not been recognized" % name)
+        f, k = self._ARRAY_NAMES[name]
+        if k is not None and k >= self.ndim:
+            raise ValueError("Error: is not possible to use a dimension higher than %d for %s" % (self.ndim, name))
+        if f not in self.data:
+            raise KeyError("the particle set does not hold %s" % f)
+        return self.data[f] if k is None else self.data[f][:, k]
+
+    def ImportArray(self, values, name):
+        """Simulation::ImportArray for the gas particles: one quantity by the reference's name"""
+        a = self._array(name)
+        values = np.asarray(values)
+        if values.shape != (self.N,):
+            raise ValueError("ImportArray: %d values for %d particles" % (values.size, self.N))
+        a[...] = values
+
+    def ExtractArray(self, name):
+        """SphSnapshot::ExtractArray for the gas particles: a contiguous copy of one quantity"""
+        return np.ascontiguousarray(self._array(name)).copy()
+
     def view(self, only=None):
         """gsph_particle_view over the current arrays (never cached: the reference may reallocate
         its array between calls, GradhSph.cpp:83-111)."""

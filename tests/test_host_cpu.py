@@ -365,3 +365,27 @@ def test_config_workloads_have_the_named_shapes():
     assert np.corrcoef(m, np.cos(2*phi))[0, 1] > 0.99                                       # the m = 2 mode
     omega = (r[0]*v[1] - r[1]*v[0])/(r[0]**2 + r[1]**2)
     assert np.allclose(omega, omega[0]) and np.all(v[2] == 0)                               # solid-body rotation about z
+
+
+def test_particle_set_speaks_the_reference_array_names():
+    """ParticleSet.ImportArray / ExtractArray take the reference's quantity names (Simulation::ImportArray,
+    Simulation.cpp:1442-1612; SphSnapshot::ExtractArray, SphSnapshot.cpp:529-600) on SoA and AoS layouts"""
+    import pytest
+    import gandalf_b200 as g
+    rng = np.random.default_rng(5)
+    for layout in ("soa", "aos"):
+        ps = g.ParticleSet(7, 2, layout)
+        vals = {n: rng.normal(size=7) for n in ("x", "y", "vx", "vy", "m", "h", "rho", "u")}
+        for n, v in vals.items():
+            ps.ImportArray(v, n)
+        assert np.array_equal(ps["r"][:, 1], vals["y"]) and np.array_equal(ps["v"][:, 0], vals["vx"])
+        for n, v in vals.items():
+            out = ps.ExtractArray(n)
+            assert out.flags["C_CONTIGUOUS"] and np.array_equal(out, v)
+        assert np.array_equal(ps.ExtractArray("iorig"), np.arange(7))
+        with pytest.raises(ValueError):
+            ps.ExtractArray("z")                      # no third dimension
+        with pytest.raises(ValueError):
+            ps.ImportArray(np.zeros(7), "temperature")
+        with pytest.raises(ValueError):
+            ps.ImportArray(np.zeros(6), "x")
